@@ -1,0 +1,446 @@
+"""Host-side mirror of the reference's public API for the offline render path, over the C ABI.
+
+Same type and member names as GraphAudio.Core (OfflineAudioContext.cs:18,30,108; AudioParam.cs:252-312;
+Nodes/AudioBufferSourceNode.cs:32,67,79,116; Nodes/BiQuadFilterNode.cs:21,42,47,52; Nodes/GainNode.cs:14;
+Nodes/ConvolverNode.cs:25,87,95; Nodes/AudioNode.cs:68), so that graph-building code written for the reference
+reads the same here.  The nodes only RECORD topology and automation; `OfflineAudioContext.Render` flattens the
+recorded graph into gac_voice_desc / gac_bus_desc arrays and makes ONE call into libgraphaudio_cuda.so.
+
+This module is the Python twin of the C++ mirror in graphaudio_b200/host/graphaudio_cuda.hpp and of the C#
+package sketched in INTEGRATION.md; pytest drives the library through it.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional
+
+import numpy as np
+
+from . import _native as N
+
+
+# ---- exception types the reference throws, keyed by gac_status ------------------------------------------
+class ArgumentException(ValueError):
+    pass
+
+
+class ArgumentOutOfRangeException(ArgumentException):
+    pass
+
+
+class InvalidOperationException(RuntimeError):
+    pass
+
+
+class ObjectDisposedException(InvalidOperationException):
+    pass
+
+
+class NotSupportedException(RuntimeError):
+    """Graph shape outside the accelerated hot path."""
+
+
+class CudaException(RuntimeError):
+    pass
+
+
+_ERR = {
+    N.GAC_ERR_INVALID_ARGUMENT: ArgumentException,
+    N.GAC_ERR_OUT_OF_RANGE: ArgumentOutOfRangeException,
+    N.GAC_ERR_INVALID_OPERATION: InvalidOperationException,
+    N.GAC_ERR_DISPOSED: ObjectDisposedException,
+    N.GAC_ERR_UNSUPPORTED: NotSupportedException,
+}
+
+
+def check(rc: int):
+    if rc != N.GAC_OK:
+        raise _ERR.get(rc, CudaException)(f"[gac {rc}] {N.last_error()}")
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fptr(a):
+    return a.ctypes.data_as(N.fp)
+
+
+class FilterType:  # Nodes/BiQuadFilterNode.cs:288-298
+    Lowpass, Highpass, Bandpass, Notch, Allpass, Peaking, Lowshelf, Highshelf = range(8)
+
+
+class PlayableAudioBuffer:
+    """PlayableAudioBuffer.cs — planar float32 sample container; uploaded to HBM on first use by a context."""
+
+    def __init__(self, channels, sample_rate):
+        if len(channels) < 1 or len(channels) > 32:
+            raise ArgumentOutOfRangeException("Channel count must be between 1 and 32")
+        if sample_rate <= 0:
+            raise ArgumentOutOfRangeException("Sample rate must be positive")
+        self.channels = [_f32(c) for c in channels]
+        self.SampleRate = int(sample_rate)
+        self.NumberOfChannels = len(self.channels)
+        self.Length = int(self.channels[0].shape[0])
+        self._handles = {}
+
+    @staticmethod
+    def FromChannelArrays(channelData, sampleRate):  # :122-143
+        if len(channelData) == 0:
+            raise ArgumentException("Channel data cannot be or empty")
+        n = len(channelData[0])
+        if any(len(c) != n for c in channelData):
+            raise ArgumentException("All channels must have the same length")
+        return PlayableAudioBuffer(channelData, sampleRate)
+
+    @staticmethod
+    def FromMonoArray(audioData, sampleRate):  # :148-157
+        return PlayableAudioBuffer([audioData], sampleRate)
+
+    @staticmethod
+    def FromStereoArrays(leftChannel, rightChannel, sampleRate):  # :162-173
+        if len(leftChannel) != len(rightChannel):
+            raise ArgumentException("Left and right channels must have the same length")
+        return PlayableAudioBuffer([leftChannel, rightChannel], sampleRate)
+
+    def _handle(self, ctx: "OfflineAudioContext"):
+        h = self._handles.get(id(ctx))
+        if h is None:
+            ptrs = (N.fp * self.NumberOfChannels)(*[_fptr(c) for c in self.channels])
+            out = C.c_void_p()
+            check(N.lib().gac_buffer_create(ctx._h, ptrs, self.NumberOfChannels, self.Length, self.SampleRate, C.byref(out)))
+            h = out.value
+            self._handles[id(ctx)] = h
+            ctx._owned_buffers.append(h)
+        return h
+
+
+class AudioParam:
+    """AudioParam.cs — value + time-sorted automation events (clamped at schedule time, :254,268,282,299)."""
+
+    def __init__(self, default, mn, mx):
+        self.DefaultValue, self.MinValue, self.MaxValue = float(default), float(mn), float(mx)
+        self._value = np.float32(default)
+        self._events: List[tuple] = []  # (type, value, target, time, time_constant)
+
+    def _clamp(self, v):
+        v = np.float32(v)
+        return np.float32(min(max(v, np.float32(self.MinValue)), np.float32(self.MaxValue)))
+
+    @property
+    def Value(self):
+        return float(self._value)
+
+    @Value.setter
+    def Value(self, v):  # :34-49: clamps and clears every scheduled event
+        self._value = self._clamp(v)
+        self._events = []
+
+    def _add(self, ev):  # AddEvent :333-352, stable upper-bound insert
+        lo, hi = 0, len(self._events)
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if ev[3] < self._events[mid][3]:
+                hi = mid
+            else:
+                lo = mid + 1
+        self._events.insert(lo, ev)
+
+    def SetValueAtTime(self, value, startTime):
+        self._add((0, float(self._clamp(value)), 0.0, float(startTime), 0.0))
+
+    def LinearRampToValueAtTime(self, value, endTime):
+        self._add((1, float(self._clamp(value)), 0.0, float(endTime), 0.0))
+
+    def ExponentialRampToValueAtTime(self, value, endTime):
+        v = self._clamp(value)
+        if v <= 0:
+            raise ArgumentException("Exponential ramp target must be > 0")  # :283-284
+        self._add((2, float(v), 0.0, float(endTime), 0.0))
+
+    def SetTargetAtTime(self, target, startTime, timeConstant):
+        self._add((3, 0.0, float(self._clamp(target)), float(startTime), float(timeConstant)))
+
+    def CancelScheduledValues(self, cancelTime):  # :312-331
+        self._events = [e for e in self._events if e[3] < cancelTime]
+
+    def _desc(self, keep: list) -> N.gac_param:
+        p = N.gac_param()
+        p.value = float(self._value)
+        p.n_events = len(self._events)
+        if self._events:
+            arr = (N.gac_event * len(self._events))()
+            for i, (t, v, tg, tm, tc) in enumerate(self._events):
+                arr[i].type, arr[i].value, arr[i].target, arr[i].time, arr[i].time_constant = t, v, tg, tm, tc
+            keep.append(arr)
+            p.events = arr
+        return p
+
+
+class AudioNode:
+    """Nodes/AudioNode.cs — records connections; Connect returns the destination to allow chaining (:68-73)."""
+
+    def __init__(self, context: "OfflineAudioContext", n_inputs=1, n_outputs=1):
+        self.Context = context
+        self._in: List["AudioNode"] = []   # upstream nodes in connection order (AudioNodeInput._connectedOutputs)
+        self._out: List["AudioNode"] = []
+        self._n_inputs, self._n_outputs = n_inputs, n_outputs
+        context._nodes.append(self)
+
+    def Connect(self, destination: "AudioNode", outputIndex=0, inputIndex=0):
+        if outputIndex < 0 or outputIndex >= self._n_outputs:
+            raise ArgumentOutOfRangeException("outputIndex")
+        if inputIndex < 0 or inputIndex >= destination._n_inputs:
+            raise ArgumentOutOfRangeException("inputIndex")
+        if destination is self:
+            raise InvalidOperationException("Cannot connect a node to itself")  # AudioNodeOutput.cs:43-44
+        if destination not in self._out:
+            self._out.append(destination)
+            destination._in.append(self)
+        return destination
+
+    def Disconnect(self, destination: Optional["AudioNode"] = None):
+        for d in ([destination] if destination is not None else list(self._out)):
+            if d in self._out:
+                self._out.remove(d)
+                d._in.remove(self)
+
+
+class AudioDestinationNode(AudioNode):
+    def __init__(self, context):
+        super().__init__(context, 1, 0)
+
+
+class AudioBufferSourceNode(AudioNode):
+    def __init__(self, context):
+        super().__init__(context, 0, 1)
+        self.PlaybackRate = AudioParam(1.0, 0.001, 1000.0)  # k-rate, Nodes/AudioBufferSourceNode.cs:76
+        self.Buffer: Optional[PlayableAudioBuffer] = None
+        self.Loop = False
+        self._started = False
+        self._when = math.nan
+        self._offset = 0.0
+        self._duration = math.inf
+        self._stop = math.nan
+
+    def Start(self, when=0.0, offset=0.0, duration=math.inf):  # :79-114
+        if self._started:
+            raise InvalidOperationException("AudioBufferSourceNode can only be started once.")
+        if self.Buffer is None:
+            raise InvalidOperationException("Cannot start without a buffer set")
+        self._started = True
+        self._when, self._offset, self._duration = float(when), float(offset), float(duration)
+
+    def Stop(self, when=0.0):  # :116-129
+        if math.isnan(self._stop):
+            self._stop = max(0.0, float(when))
+        else:
+            self._stop = min(self._stop, max(0.0, float(when)))
+
+
+class BiQuadFilterNode(AudioNode):
+    def __init__(self, context):
+        super().__init__(context)
+        self.Type = FilterType.Lowpass
+        self.Frequency = AudioParam(1000.0, 1.0, context.SampleRate / 2.0)  # :63-68
+        self.Q = AudioParam(1.0, 0.001, 1000.0)                             # :70-75
+        self.Gain = AudioParam(0.0, -60.0, 60.0)                            # :77-82 (k-rate)
+
+
+class GainNode(AudioNode):
+    def __init__(self, context):
+        super().__init__(context)
+        fmax = float(np.finfo(np.float32).max)
+        self.Gain = AudioParam(1.0, -fmax, fmax)  # Nodes/GainNode.cs:19-24
+
+
+class ConvolverNode(AudioNode):
+    def __init__(self, context):
+        super().__init__(context)
+        self.Normalize = True          # Nodes/ConvolverNode.cs:87
+        self.EnableTrueStereo = True   # :95
+        self._buffer = None
+        self._ir = None
+
+    @property
+    def Buffer(self):
+        return self._buffer
+
+    @Buffer.setter
+    def Buffer(self, value):  # :25-79: the convolvers are built here, with the Normalize value of this moment
+        if value is self._buffer:
+            return
+        if value is None:
+            self._buffer, self._ir = None, None
+            return
+        ctx = self.Context
+        out = C.c_void_p()
+        check(N.lib().gac_ir_prepare(ctx._h, value._handle(ctx), int(self.Normalize), int(self.EnableTrueStereo), C.byref(out)))
+        ctx._owned_irs.append(out.value)
+        self._buffer, self._ir = value, out.value
+
+
+class OfflineAudioContext:
+    """OfflineAudioContext.cs — `Render` is the one call that crosses into libgraphaudio_cuda.so."""
+
+    def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32):
+        self._h = None
+        if sampleRate <= 0:
+            raise ArgumentOutOfRangeException("sampleRate")  # AudioContextBase.cs:37-38
+        self.SampleRate = int(sampleRate)
+        self._nodes: List[AudioNode] = []
+        self._owned_buffers: List[int] = []
+        self._owned_irs: List[int] = []
+        desc = N.gac_context_desc()
+        desc.sample_rate, desc.quantum, desc.partition, desc.device_id, desc.mac_variant = self.SampleRate, 128, partition, device_id, mac_variant
+        desc.reserved[0] = tile_blocks
+        out = C.c_void_p()
+        check(N.lib().gac_context_create(C.byref(desc), C.byref(out)))
+        self._h = out.value
+        self.Destination = AudioDestinationNode(self)
+        self._frames_rendered = 0
+        self.last_stats = None
+
+    # ---- graph flattening: destination <- (bus chain <- fan-in)? <- voice chain <- source
+    def _op_desc(self, node, keep):
+        op = N.gac_op_desc()
+        if isinstance(node, BiQuadFilterNode):
+            op.kind, op.filter_type = N.GAC_OP_BIQUAD, int(node.Type)
+            op.p0, op.p1, op.p2 = node.Frequency._desc(keep), node.Q._desc(keep), node.Gain._desc(keep)
+        elif isinstance(node, GainNode):
+            op.kind = N.GAC_OP_GAIN
+            op.p0 = node.Gain._desc(keep)
+        elif isinstance(node, ConvolverNode):
+            op.kind = N.GAC_OP_CONVOLVER
+            op.ir = node._ir
+        else:
+            raise NotSupportedException(f"{type(node).__name__} is outside the accelerated path")
+        return op
+
+    def _walk_voice(self, node):
+        """node .. upstream to a source through single-input nodes -> (source, [ops source->node]) or None if unconnected."""
+        ops = []
+        while not isinstance(node, AudioBufferSourceNode):
+            if len(node._out) > 1:
+                raise NotSupportedException("fan-out inside a voice chain is outside the accelerated path (SURVEY.md §8f-2)")
+            ops.append(node)
+            if len(node._in) == 0:
+                return None
+            if len(node._in) > 1:
+                raise NotSupportedException("nested fan-in is outside the accelerated path")
+            node = node._in[0]
+        if len(node._out) > 1:
+            raise NotSupportedException("a source feeding several nodes is outside the accelerated path (SURVEY.md §8f-2)")
+        return node, list(reversed(ops))
+
+    def _flatten(self):
+        keep = []
+        voices, buses, dest_inputs = [], [], []
+        for head in self.Destination._in:
+            # walk up while the chain is single-input; the first node with >= 2 inputs is the bus fan-in
+            chain, node = [], head
+            while not isinstance(node, AudioBufferSourceNode) and len(node._in) == 1:
+                chain.append(node)
+                node = node._in[0]
+            if isinstance(node, AudioBufferSourceNode):
+                voices.append((node, list(reversed(chain)), -1))
+                dest_inputs.append(~(len(voices) - 1))
+                continue
+            if len(node._in) == 0:
+                continue  # nothing connected: contributes silence
+            chain.append(node)  # node has the fan-in input; it and everything below it run on the bus
+            bus_index = len(buses)
+            buses.append(list(reversed(chain)))
+            dest_inputs.append(bus_index)
+            for up in node._in:
+                r = self._walk_voice(up)
+                if r is not None:
+                    voices.append((r[0], r[1], bus_index))
+        # the destination input itself may be the fan-in (several voices straight into Destination): handled above
+        vdesc = (N.gac_voice_desc * max(1, len(voices)))()
+        for i, (src, ops, bus) in enumerate(voices):
+            if not src._started or src.Buffer is None:
+                when = math.nan
+            else:
+                when = src._when
+            if src.Loop:
+                raise NotSupportedException("looping sources are outside the accelerated path (SURVEY.md §8f-3)")
+            v = vdesc[i]
+            v.source = src.Buffer._handle(self) if src.Buffer is not None else None
+            v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop
+            v.playback_rate = src.PlaybackRate.Value
+            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep) for o in ops])
+            keep.append(arr)
+            v.n_ops, v.ops, v.bus = len(ops), arr, bus
+        bdesc = (N.gac_bus_desc * max(1, len(buses)))()
+        for i, ops in enumerate(buses):
+            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep) for o in ops])
+            keep.append(arr)
+            bdesc[i].n_ops, bdesc[i].ops = len(ops), arr
+        darr = (C.c_int32 * max(1, len(dest_inputs)))(*dest_inputs)
+        g = N.gac_graph_desc()
+        g.n_voices, g.voices, g.n_buses, g.buses = len(voices), vdesc, len(buses), bdesc
+        g.n_dest_inputs, g.dest_inputs = len(dest_inputs), darr
+        keep += [vdesc, bdesc, darr]
+        return g, keep
+
+    def _graph(self):
+        g, keep = self._flatten()
+        out = C.c_void_p()
+        check(N.lib().gac_graph_create(self._h, C.byref(g), C.byref(out)))
+        return out.value
+
+    def Render(self, output_or_count, frameCount=None, startIndex=0):
+        """Render(float[][] output, int frameCount, int startIndex = 0)  (OfflineAudioContext.cs:30)
+        or  float[][] Render(int frameCount)  (:108).  Successive calls continue the timeline (:55-100)."""
+        if self._h is None:
+            raise ObjectDisposedException("OfflineAudioContext")
+        if frameCount is None:
+            n = int(output_or_count)
+            if n <= 0:
+                raise ArgumentOutOfRangeException("Frame count must be positive.")
+            out = np.zeros((2, n), np.float32)
+            self.Render(out, n, 0)
+            return out
+        output = output_or_count
+        if len(output) == 0:
+            raise ArgumentException("Output buffer must have at least one channel.")
+        if frameCount <= 0:
+            raise ArgumentOutOfRangeException("Frame count must be positive.")
+        if startIndex < 0:
+            raise ArgumentOutOfRangeException("Start index must be non-negative.")
+        rows = [output[c] for c in range(len(output))]
+        for c, r in enumerate(rows):
+            if r is None:
+                raise ArgumentException(f"Channel {c} buffer is null.")
+            if r.dtype != np.float32 or not r.flags.c_contiguous:
+                raise ArgumentException("channel buffers must be contiguous float32")
+            if r.shape[0] < startIndex + frameCount:
+                raise ArgumentException(f"Channel {c} buffer is too small. Required: {startIndex + frameCount}, Available: {r.shape[0]}")
+        graph = self._graph()
+        try:
+            ptrs = (N.fp * len(rows))(*[_fptr(r) for r in rows])
+            check(N.lib().gac_render(self._h, graph, self._frames_rendered, int(frameCount), ptrs, len(rows), int(startIndex)))
+            self._frames_rendered += int(frameCount)
+            st = N.gac_stats()
+            check(N.lib().gac_get_stats(self._h, C.byref(st)))
+            self.last_stats = st.as_dict()
+        finally:
+            N.lib().gac_graph_destroy(graph)
+
+    def Dispose(self):
+        if self._h is not None:
+            L = N.lib()
+            for h in self._owned_irs:
+                L.gac_ir_destroy(h)
+            for h in self._owned_buffers:
+                L.gac_buffer_destroy(h)
+            L.gac_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass

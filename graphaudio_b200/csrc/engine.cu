@@ -1,0 +1,869 @@
+// engine.cu — the C ABI of include/graphaudio_cuda.h: handles, error plumbing, graph flattening and the
+// batched render schedule.  The reference renders one 128-frame quantum at a time by pulling through the node
+// graph (AudioContextBase.ProcessBlock, AudioContextBase.cs:52-81; AudioNode.ProcessInternal, Nodes/AudioNode.cs:152-183).
+// Offline, every input is known up front, so a render here is a short sequence of large kernels over
+// [voice, channel, time]:  source -> (automation, biquad, gain)* -> rFFT -> spectral MAC -> irFFT+OLA -> mix.
+//
+// No CPU fallback exists: if there is no CUDA device the entry points fail with GAC_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/graphaudio_cuda.h"
+#include "gac_kernels.h"
+
+using namespace gac;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      int code_ = (e_ == cudaErrorMemoryAllocation) ? GAC_ERR_OUT_OF_MEMORY                              \
+                  : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? GAC_ERR_NO_DEVICE   \
+                                                                                   : GAC_ERR_CUDA;       \
+      return fail(code_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+    }                                                                                                    \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ handles
+struct ParamH {
+  float value = 0.f;
+  std::vector<gac_event> ev;
+};
+struct OpH {
+  int kind = 0;
+  int ftype = 0;
+  ParamH p0, p1, p2;
+  const gac_ir* ir = nullptr;
+};
+struct VoiceH {
+  const gac_buffer* src = nullptr;
+  double when = 0, offset = 0, duration = 0, stop_when = 0;
+  float rate = 1.f;
+  std::vector<OpH> ops;
+  int bus = -1;
+};
+struct BusH {
+  std::vector<OpH> ops;
+};
+
+struct NcclApi;
+
+struct gac_context {
+  uint32_t magic = 0x47414331;  // "GAC1"
+  int device = 0;
+  int fs = 48000;
+  int B = 128;
+  int mac_variant = 0;
+  int tile_blocks = 32;
+  cudaStream_t stream = nullptr;
+  float2* d_tw = nullptr;  // e^{-2 pi i k/(2B)}, k < B
+  std::vector<double> h_bt;  // block start times, accumulated as AudioContextBase.cs:78-79
+  double* d_bt = nullptr;
+  int64_t bt_cap = 0;
+  gac_stats stats{};
+  // NCCL (optional)
+  void* comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  size_t scratch_budget = (size_t)24 << 30;
+};
+struct gac_buffer {
+  gac_context* ctx;
+  int nch;
+  int64_t n;
+  int rate;
+  float* d = nullptr;  // [nch][stride]
+  int64_t stride;
+};
+struct gac_ir {
+  gac_context* ctx;
+  int nch;
+  bool true_stereo;
+  int P, P16;
+  int64_t frames;
+  float2* d_H = nullptr;  // [nch][P16][B]
+  float* d_scale = nullptr;
+};
+struct gac_graph {
+  gac_context* ctx;
+  std::vector<VoiceH> voices;
+  std::vector<BusH> buses;
+  std::vector<int> dest_inputs;
+};
+
+static bool ctx_ok(gac_context* c) { return c && c->magic == 0x47414331; }
+
+// ------------------------------------------------------------------------------------------ scratch + timing
+// Stream-ordered scratch allocations, all released at the end of a render.
+struct Scratch {
+  gac_context* ctx;
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  explicit Scratch(gac_context* c) : ctx(c) {}
+  template <typename T>
+  int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    size_t b = std::max<size_t>(count * sizeof(T), 16);
+    cudaError_t e = cudaMallocAsync(&p, b, ctx->stream);
+    if (e != cudaSuccess) {
+      return fail(e == cudaErrorMemoryAllocation ? GAC_ERR_OUT_OF_MEMORY : GAC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", b,
+                  cudaGetErrorString(e));
+    }
+    ptrs.push_back(p);
+    bytes += b;
+    *out = (T*)p;
+    return GAC_OK;
+  }
+  // upload a host vector (stream-ordered; the vector must stay alive until the stream is synchronised)
+  template <typename T>
+  int upload(T** out, const std::vector<T>& v) {
+    int rc = alloc(out, v.size());
+    if (rc) return rc;
+    if (!v.empty()) {
+      cudaError_t e = cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    }
+    return GAC_OK;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+    ptrs.clear();
+  }
+  ~Scratch() { release(); }
+};
+
+enum Cat { C_SOURCE, C_AUTO, C_BIQUAD, C_GAIN, C_FFT_FWD, C_MAC, C_FFT_INV, C_MIX, C_D2H, C_COUNT };
+struct Timer {
+  gac_context* ctx;
+  struct Span {
+    cudaEvent_t a, b;
+    int cat;
+  };
+  std::vector<Span> spans;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  explicit Timer(gac_context* c) : ctx(c) {
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    cudaEventRecord(t0, ctx->stream);
+  }
+  int begin(int cat) {
+    Span s;
+    cudaEventCreate(&s.a);
+    cudaEventCreate(&s.b);
+    s.cat = cat;
+    cudaEventRecord(s.a, ctx->stream);
+    spans.push_back(s);
+    return (int)spans.size() - 1;
+  }
+  void end(int id) { cudaEventRecord(spans[id].b, ctx->stream); }
+  void finish(gac_stats* st) {
+    cudaEventRecord(t1, ctx->stream);
+    cudaEventSynchronize(t1);
+    double acc[C_COUNT] = {0};
+    for (auto& s : spans) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, s.a, s.b);
+      acc[s.cat] += ms;
+    }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, t0, t1);
+    st->ms_total = tot;
+    st->ms_source = acc[C_SOURCE];
+    st->ms_automation = acc[C_AUTO];
+    st->ms_biquad = acc[C_BIQUAD];
+    st->ms_gain = acc[C_GAIN];
+    st->ms_fft_fwd = acc[C_FFT_FWD];
+    st->ms_mac = acc[C_MAC];
+    st->ms_fft_inv = acc[C_FFT_INV];
+    st->ms_mix = acc[C_MIX];
+    st->ms_d2h = acc[C_D2H];
+  }
+  ~Timer() {
+    for (auto& s : spans) {
+      cudaEventDestroy(s.a);
+      cudaEventDestroy(s.b);
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+  }
+};
+
+// keeps host-side job arrays alive until the stream has consumed them
+struct HostKeep {
+  std::vector<std::shared_ptr<void>> items;
+  template <typename T>
+  std::vector<T>& make() {
+    auto p = std::make_shared<std::vector<T>>();
+    items.push_back(p);
+    return *p;
+  }
+};
+
+// ------------------------------------------------------------------------------------------ library
+extern "C" int gac_version(void) { return GAC_ABI_VERSION; }
+extern "C" const char* gac_last_error(void) { return g_err; }
+extern "C" int gac_device_count(int* count) {
+  if (!count) return fail(GAC_ERR_INVALID_ARGUMENT, "count is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(GAC_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return GAC_OK;
+}
+
+static int ensure_block_times(gac_context* ctx, int64_t nq) {
+  if ((int64_t)ctx->h_bt.size() >= nq + 1 && ctx->d_bt) return GAC_OK;
+  // _currentTime += 128.0 / SampleRate, accumulated block after block (AudioContextBase.cs:78-79)
+  int64_t want = std::max<int64_t>(nq + 1, 4096);
+  double inc = (double)128 / (double)ctx->fs;
+  double t = ctx->h_bt.empty() ? 0.0 : ctx->h_bt.back();
+  if (ctx->h_bt.empty()) ctx->h_bt.push_back(0.0);
+  while ((int64_t)ctx->h_bt.size() < want) {
+    t = t + inc;
+    ctx->h_bt.push_back(t);
+  }
+  if (ctx->d_bt) cudaFree(ctx->d_bt);
+  CU(cudaMalloc(&ctx->d_bt, ctx->h_bt.size() * sizeof(double)));
+  CU(cudaMemcpy(ctx->d_bt, ctx->h_bt.data(), ctx->h_bt.size() * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->bt_cap = (int64_t)ctx->h_bt.size();
+  return GAC_OK;
+}
+
+extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** out) {
+  if (!desc || !out) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (desc->sample_rate <= 0) return fail(GAC_ERR_OUT_OF_RANGE, "sampleRate must be positive");  // AudioContextBase.cs:37-38
+  if (desc->quantum != 0 && desc->quantum != 128) return fail(GAC_ERR_INVALID_ARGUMENT, "quantum must be 128 (AudioBuffer.FramesPerBlock)");
+  int B = desc->partition == 0 ? 128 : desc->partition;
+  if (B != 128 && B != 256 && B != 512) return fail(GAC_ERR_INVALID_ARGUMENT, "partition must be 128, 256 or 512");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(GAC_ERR_NO_DEVICE, "no CUDA device (%s); libgraphaudio_cuda has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+  int dev = desc->device_id;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(GAC_ERR_OUT_OF_RANGE, "device_id %d out of range (%d devices)", dev, ndev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(GAC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+  CU(cudaSetDevice(dev));
+  auto ctx = std::make_unique<gac_context>();
+  ctx->device = dev;
+  ctx->fs = desc->sample_rate;
+  ctx->B = B;
+  ctx->mac_variant = desc->mac_variant;
+  ctx->tile_blocks = desc->reserved[0] == 64 ? 64 : 32;
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  // keep freed scratch in the pool between renders
+  cudaMemPool_t pool;
+  CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thr = UINT64_MAX;
+  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  // twiddles e^{-2 pi i k / N}, N = 2B, in double then rounded once
+  std::vector<float2> tw(B);
+  const double pi = 3.14159265358979323846;
+  for (int k = 0; k < B; k++) {
+    double a = -2.0 * pi * (double)k / (double)(2 * B);
+    tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  CU(cudaMalloc(&ctx->d_tw, sizeof(float2) * B));
+  CU(cudaMemcpy(ctx->d_tw, tw.data(), sizeof(float2) * B, cudaMemcpyHostToDevice));
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->scratch_budget = std::max<size_t>((size_t)1 << 30, free_b / 3);
+  int rc = ensure_block_times(ctx.get(), 8192);
+  if (rc) return rc;
+  *out = ctx.release();
+  return GAC_OK;
+}
+
+extern "C" int gac_comm_destroy(gac_context* ctx);
+extern "C" int gac_context_destroy(gac_context* ctx) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or already destroyed");
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) gac_comm_destroy(ctx);
+  cudaFree(ctx->d_tw);
+  cudaFree(ctx->d_bt);
+  cudaStreamDestroy(ctx->stream);
+  ctx->magic = 0;
+  delete ctx;
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ buffers
+extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels, int n_channels, int64_t n_frames, int sample_rate,
+                                 gac_buffer** out) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!channels || !out) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (n_channels < 1 || n_channels > 32) return fail(GAC_ERR_OUT_OF_RANGE, "Channel count must be between 1 and 32");  // PlayableAudioBuffer.cs:47-48
+  if (n_frames < 0) return fail(GAC_ERR_OUT_OF_RANGE, "Length must be non-negative");
+  if (sample_rate <= 0) return fail(GAC_ERR_OUT_OF_RANGE, "Sample rate must be positive");
+  for (int c = 0; c < n_channels; c++)
+    if (!channels[c]) return fail(GAC_ERR_INVALID_ARGUMENT, "channel %d is null", c);
+  CU(cudaSetDevice(ctx->device));
+  auto b = std::make_unique<gac_buffer>();
+  b->ctx = ctx;
+  b->nch = n_channels;
+  b->n = n_frames;
+  b->rate = sample_rate;
+  b->stride = ((n_frames + 8 + 63) / 64) * 64;  // a little slack so 4-tap reads never leave the allocation
+  CU(cudaMalloc(&b->d, sizeof(float) * b->stride * n_channels));
+  CU(cudaMemsetAsync(b->d, 0, sizeof(float) * b->stride * n_channels, ctx->stream));
+  for (int c = 0; c < n_channels; c++)
+    CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // the caller may reuse its arrays as soon as we return
+  *out = b.release();
+  return GAC_OK;
+}
+extern "C" int gac_buffer_destroy(gac_buffer* buf) {
+  if (!buf) return fail(GAC_ERR_INVALID_ARGUMENT, "buffer is null");
+  cudaSetDevice(buf->ctx->device);
+  cudaStreamSynchronize(buf->ctx->stream);
+  cudaFree(buf->d);
+  delete buf;
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ IR prepare (K0)
+static int upload_now(gac_context* ctx, void* dst, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return GAC_OK;
+}
+
+static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir) {
+  const int B = ctx->B;
+  ir->P = (int)((frames + B - 1) / B);  // ceil(L / blockSize)  PartitionedConvolver.cs:44
+  ir->P16 = std::max(16, ((ir->P + 15) / 16) * 16);
+  CU(cudaMalloc(&ir->d_H, sizeof(float2) * (size_t)nch * ir->P16 * B));
+  CU(cudaMemsetAsync(ir->d_H, 0, sizeof(float2) * (size_t)nch * ir->P16 * B, ctx->stream));
+  CU(cudaMalloc(&ir->d_scale, sizeof(float) * nch));
+  std::vector<const float*> chp(nch);
+  for (int c = 0; c < nch; c++) chp[c] = d_ir + c * stride;
+  const float** d_chp = nullptr;
+  CU(cudaMalloc(&d_chp, sizeof(float*) * nch));
+  int rc = upload_now(ctx, d_chp, chp.data(), sizeof(float*) * nch);
+  if (rc) return rc;
+  if (normalize && frames > 0) {
+    // (float)Math.Pow(10, GainCalibration * 0.05f) with GainCalibration = -58  (PartitionedConvolver.cs:95,101)
+    const float cal = (float)std::pow(10.0, (double)(-58.f * 0.05f));
+    launch_ir_scale(d_chp, nch, frames, cal, ir->d_scale, ctx->stream);
+  } else {
+    std::vector<float> ones(nch, 1.0f);
+    rc = upload_now(ctx, ir->d_scale, ones.data(), sizeof(float) * nch);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  std::vector<FftFwdJob> jobs(nch);
+  for (int c = 0; c < nch; c++) {
+    FftFwdJob& j = jobs[c];
+    j.in = d_ir + c * stride;
+    j.out = ir->d_H + (size_t)c * ir->P16 * B;
+    j.scale = ir->d_scale + c;
+    j.gain = nullptr;
+    j.gain_const = 1.0f;
+    j.n_valid = frames;
+    j.n_blocks = ir->P;
+    j.gate_lo = 0;
+    j.gate_hi = std::numeric_limits<int64_t>::max();
+  }
+  FftFwdJob* d_jobs = nullptr;
+  CU(cudaMalloc(&d_jobs, sizeof(FftFwdJob) * nch));
+  rc = upload_now(ctx, d_jobs, jobs.data(), sizeof(FftFwdJob) * nch);
+  if (rc) return rc;
+  launch_rfft_fwd(d_jobs, nch, ir->P, B, ctx->d_tw, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_jobs);
+  cudaFree(d_chp);
+  return GAC_OK;
+}
+
+extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int normalize, int true_stereo, gac_ir** out) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!buf || !out) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (buf->rate != ctx->fs)  // Nodes/ConvolverNode.cs:48-49
+    return fail(GAC_ERR_INVALID_OPERATION,
+                "Impulse response buffer sample rate must match the audio context sample rate. Impulse response buffer sample rate: %d, "
+                "Audio context sample rate: %d.",
+                buf->rate, ctx->fs);
+  bool ts = (buf->nch == 4 && true_stereo);
+  if (!(buf->nch == 1 || buf->nch == 2 || ts))
+    return fail(GAC_ERR_UNSUPPORTED, "impulse responses with %d discrete channels are outside the accelerated path (1, 2, or 4 with true stereo)", buf->nch);
+  if (buf->n <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "impulse response is empty");
+  CU(cudaSetDevice(ctx->device));
+  auto ir = std::make_unique<gac_ir>();
+  ir->ctx = ctx;
+  ir->nch = buf->nch;
+  ir->true_stereo = ts;
+  ir->frames = buf->n;
+  int rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get());
+  if (rc) {
+    cudaFree(ir->d_H);
+    cudaFree(ir->d_scale);
+    return rc;
+  }
+  *out = ir.release();
+  return GAC_OK;
+}
+extern "C" int gac_ir_destroy(gac_ir* ir) {
+  if (!ir) return fail(GAC_ERR_INVALID_ARGUMENT, "ir is null");
+  cudaSetDevice(ir->ctx->device);
+  cudaStreamSynchronize(ir->ctx->stream);
+  cudaFree(ir->d_H);
+  cudaFree(ir->d_scale);
+  delete ir;
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ graph
+static int copy_param(const gac_param& p, ParamH* out, const char* what) {
+  out->value = p.value;
+  if (p.n_events < 0) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: negative event count", what);
+  if (p.n_events > 0 && !p.events) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: events is null", what);
+  out->ev.assign(p.events, p.events + p.n_events);
+  for (int i = 0; i < p.n_events; i++) {
+    if (out->ev[i].type < 0 || out->ev[i].type > 3) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: bad event type", what);
+    if (i > 0 && out->ev[i].time < out->ev[i - 1].time) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: events must be sorted by time (AudioParam.AddEvent order)", what);
+  }
+  return GAC_OK;
+}
+static int copy_ops(gac_context* ctx, int n, const gac_op_desc* ops, std::vector<OpH>* out) {
+  if (n < 0 || (n > 0 && !ops)) return fail(GAC_ERR_INVALID_ARGUMENT, "bad op list");
+  out->resize(n);
+  for (int i = 0; i < n; i++) {
+    OpH& o = (*out)[i];
+    o.kind = ops[i].kind;
+    o.ftype = ops[i].filter_type;
+    int rc;
+    switch (o.kind) {
+      case GAC_OP_BIQUAD:
+        if (o.ftype < 0 || o.ftype > 7) return fail(GAC_ERR_INVALID_ARGUMENT, "bad filter type %d", o.ftype);
+        if ((rc = copy_param(ops[i].p0, &o.p0, "biquad.frequency"))) return rc;
+        if ((rc = copy_param(ops[i].p1, &o.p1, "biquad.Q"))) return rc;
+        if ((rc = copy_param(ops[i].p2, &o.p2, "biquad.gain"))) return rc;
+        break;
+      case GAC_OP_GAIN:
+        if ((rc = copy_param(ops[i].p0, &o.p0, "gain.gain"))) return rc;
+        break;
+      case GAC_OP_CONVOLVER:
+        o.ir = ops[i].ir;
+        if (o.ir && o.ir->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "impulse response belongs to another context");
+        if (o.ir && o.ir->nch != 2) return fail(GAC_ERR_UNSUPPORTED, "only stereo impulse responses are on the accelerated graph path in this version (mono / true-stereo: SURVEY.md 8f-1)");
+        break;
+      default:
+        return fail(GAC_ERR_INVALID_ARGUMENT, "unknown op kind %d", o.kind);
+    }
+  }
+  return GAC_OK;
+}
+
+extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, gac_graph** out) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!desc || !out) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (desc->n_voices < 0 || desc->n_buses < 0) return fail(GAC_ERR_INVALID_ARGUMENT, "negative counts");
+  if (desc->n_voices > 0 && !desc->voices) return fail(GAC_ERR_INVALID_ARGUMENT, "voices is null");
+  if (desc->n_buses > 0 && !desc->buses) return fail(GAC_ERR_INVALID_ARGUMENT, "buses is null");
+  auto g = std::make_unique<gac_graph>();
+  g->ctx = ctx;
+  g->voices.resize(desc->n_voices);
+  for (int v = 0; v < desc->n_voices; v++) {
+    const gac_voice_desc& d = desc->voices[v];
+    VoiceH& h = g->voices[v];
+    if (!d.source) return fail(GAC_ERR_INVALID_OPERATION, "voice %d: Cannot start without a buffer set", v);  // AudioBufferSourceNode.cs:86-87
+    if (d.source->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: buffer belongs to another context", v);
+    if (d.source->nch > 2) return fail(GAC_ERR_UNSUPPORTED, "voice %d: sources with more than 2 channels are outside the accelerated path", v);
+    if (d.bus < -1 || d.bus >= desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: bus index %d out of range", v, d.bus);
+    if (!(d.playback_rate >= 0.001f && d.playback_rate <= 1000.f)) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: playbackRate outside [0.001, 1000]", v);
+    h.src = d.source;
+    h.when = d.start_when;
+    h.offset = d.start_offset;
+    h.duration = d.start_duration;
+    h.stop_when = d.stop_when;
+    h.rate = d.playback_rate;
+    h.bus = d.bus;
+    int rc = copy_ops(ctx, d.n_ops, d.ops, &h.ops);
+    if (rc) return rc;
+  }
+  g->buses.resize(desc->n_buses);
+  for (int b = 0; b < desc->n_buses; b++) {
+    int rc = copy_ops(ctx, desc->buses[b].n_ops, desc->buses[b].ops, &g->buses[b].ops);
+    if (rc) return rc;
+  }
+  if (desc->dest_inputs && desc->n_dest_inputs > 0) {
+    g->dest_inputs.assign(desc->dest_inputs, desc->dest_inputs + desc->n_dest_inputs);
+    for (int x : g->dest_inputs) {
+      if (x >= 0 && x >= desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "dest_inputs: bus %d out of range", x);
+      if (x < 0 && (~x >= desc->n_voices || g->voices[~x].bus != -1)) return fail(GAC_ERR_INVALID_ARGUMENT, "dest_inputs: voice %d is not a direct voice", ~x);
+    }
+  } else {
+    for (int b = 0; b < desc->n_buses; b++) g->dest_inputs.push_back(b);
+    for (int v = 0; v < desc->n_voices; v++)
+      if (g->voices[v].bus == -1) g->dest_inputs.push_back(~v);
+  }
+  *out = g.release();
+  return GAC_OK;
+}
+extern "C" int gac_graph_destroy(gac_graph* g) {
+  if (!g) return fail(GAC_ERR_INVALID_ARGUMENT, "graph is null");
+  delete g;
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ render
+struct Sig {
+  float* p[2];
+  int64_t lo = 0, hi = 0;  // frames flagged non-silent (multiples of 128)
+  const std::vector<OpH>* ops = nullptr;
+};
+
+struct RenderEnv {
+  gac_context* ctx;
+  Scratch* scratch;
+  HostKeep* keep;
+  Timer* timer;
+  int64_t Npad, NQ, QB;
+  int64_t launches = 0;
+  int64_t conv_units = 0;
+  double alg_bytes = 0, macs = 0;
+  std::map<Sig*, std::pair<const float*, float>> fused;  // GainNode folded into the next convolver's forward FFT
+};
+
+static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector<ParamJob>& jobs, float** out_table) {
+  *out_table = nullptr;
+  if (p.ev.empty()) return GAC_OK;
+  float* tab = nullptr;
+  int rc = env.scratch->alloc(&tab, a_rate ? (size_t)env.Npad : (size_t)env.NQ);
+  if (rc) return rc;
+  auto& hev = env.keep->make<DevEvent>();
+  hev.resize(p.ev.size());
+  static_assert(sizeof(DevEvent) == sizeof(gac_event), "event layout");
+  memcpy(hev.data(), p.ev.data(), sizeof(gac_event) * p.ev.size());
+  DevEvent* dev = nullptr;
+  rc = env.scratch->upload(&dev, hev);
+  if (rc) return rc;
+  ParamJob j;
+  j.value = p.value;
+  j.n_events = (int)p.ev.size();
+  j.events = dev;
+  j.out = tab;
+  j.a_rate = a_rate ? 1 : 0;
+  jobs.push_back(j);
+  *out_table = tab;
+  return GAC_OK;
+}
+
+static int run_param_jobs(RenderEnv& env, std::vector<ParamJob>& jobs) {
+  if (jobs.empty()) return GAC_OK;
+  auto& hj = env.keep->make<ParamJob>();
+  hj = jobs;
+  ParamJob* dj = nullptr;
+  int rc = env.scratch->upload(&dj, hj);
+  if (rc) return rc;
+  int t = env.timer->begin(C_AUTO);
+  // a-rate and k-rate jobs share a launch; the kernel branches per job
+  launch_param_eval(dj, (int)hj.size(), env.ctx->d_bt, env.NQ, env.ctx->fs, env.ctx->stream);
+  env.timer->end(t);
+  env.launches += ((int64_t)hj.size() + 65534) / 65535;
+  CU(cudaGetLastError());
+  return GAC_OK;
+}
+
+// ---- the convolver: K5 -> K6 -> K7 for a list of channel-convolvers (one PartitionedConvolver each)
+struct ConvItem {
+  float* x;               // time-domain channel, convolved in place
+  const float2* H;        // packed IR spectra [P16][B]
+  int P;
+  int64_t lo, hi;         // non-silent input frames
+  const float* gain_tab;  // fused preceding GainNode (may be null)
+  float gain_const;
+};
+
+static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
+  gac_context* ctx = env.ctx;
+  const int B = ctx->B;
+  const int TB = ctx->tile_blocks;
+  const int64_t QB = env.QB;
+  const int64_t QBpad = ((QB + TB - 1) / TB) * TB;
+  const int64_t rowsX = TB + QBpad;  // TB zero rows in front (blocks -TB..-1)
+  const int groups = B / 128;
+  // sub-batches bounded by the scratch budget
+  const size_t per_ch = (size_t)(rowsX + QBpad) * B * sizeof(float2);
+  size_t max_items = std::max<size_t>(2, ctx->scratch_budget / per_ch);
+  for (size_t i0 = 0; i0 < items.size(); i0 += max_items) {
+    const size_t ni = std::min(max_items, items.size() - i0);
+    const size_t nch = ni;
+    float2 *dX = nullptr, *dY = nullptr;
+    int rc = env.scratch->alloc(&dX, nch * rowsX * B);
+    if (rc) return rc;
+    rc = env.scratch->alloc(&dY, nch * QBpad * B);
+    if (rc) return rc;
+    // zero the front pad and the tail rows of X (rows the forward FFT does not write)
+    CU(cudaMemset2DAsync(dX, (size_t)rowsX * B * sizeof(float2), 0, (size_t)TB * B * sizeof(float2), nch, ctx->stream));
+    if (QBpad > QB)
+      CU(cudaMemset2DAsync(dX + (size_t)(TB + QB) * B, (size_t)rowsX * B * sizeof(float2), 0, (size_t)(QBpad - QB) * B * sizeof(float2), nch, ctx->stream));
+    auto& fj = env.keep->make<FftFwdJob>();
+    auto& mj = env.keep->make<MacJob>();
+    auto& ij = env.keep->make<FftInvJob>();
+    auto& tiles = env.keep->make<MacTile>();
+    for (size_t i = 0; i < ni; i++) {
+      ConvItem& it = items[i0 + i];
+      {
+        const size_t ch = i;
+        float2* Xc = dX + ch * rowsX * B + (size_t)TB * B;  // row 0
+        float2* Yc = dY + ch * QBpad * B;
+        const float2* Hc = it.H;
+        FftFwdJob f;
+        f.in = it.x;
+        f.out = Xc;
+        f.scale = nullptr;
+        f.gain = it.gain_tab;
+        f.gain_const = it.gain_const;
+        f.n_valid = env.Npad;
+        f.n_blocks = QB;
+        f.gate_lo = it.lo;
+        f.gate_hi = it.hi;
+        fj.push_back(f);
+        for (int g = 0; g < groups; g++) {
+          MacJob m;
+          m.X = Xc + g * 128;
+          m.H = Hc + g * 128;
+          m.Y = Yc + g * 128;
+          m.P = it.P;
+          m.has_dc = (g == 0);
+          mj.push_back(m);
+        }
+        FftInvJob v;
+        v.in = Yc;
+        v.out = it.x;
+        v.n_blocks = QB;
+        ij.push_back(v);
+        // accounting: one unit = one channel-convolver block of B frames through P partitions
+        const double P = it.P, C = B + 1;
+        env.conv_units += QB;
+        env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
+      }
+    }
+    // tiles, heaviest first (stable: tiles of one job stay adjacent for L2 reuse of its H and X rows)
+    for (int j = 0; j < (int)mj.size(); j++)
+      for (int64_t b0 = 0; b0 < QB; b0 += TB) tiles.push_back(MacTile{j, (int)b0});
+    auto stages = [&](const MacTile& t) {
+      int p16 = (mj[t.job].P + 15) / 16;
+      int causal = (t.b0 + TB) / 16;
+      return std::min(p16, causal);
+    };
+    std::stable_sort(tiles.begin(), tiles.end(), [&](const MacTile& a, const MacTile& b) { return stages(a) > stages(b); });
+    for (auto& t : tiles) env.macs += (double)stages(t) * 16.0 * TB * 128.0;
+
+    FftFwdJob* dfj = nullptr;
+    MacJob* dmj = nullptr;
+    FftInvJob* dij = nullptr;
+    MacTile* dt = nullptr;
+    if ((rc = env.scratch->upload(&dfj, fj))) return rc;
+    if ((rc = env.scratch->upload(&dmj, mj))) return rc;
+    if ((rc = env.scratch->upload(&dij, ij))) return rc;
+    if ((rc = env.scratch->upload(&dt, tiles))) return rc;
+
+    int t = env.timer->begin(C_FFT_FWD);
+    launch_rfft_fwd(dfj, (int)fj.size(), QB, B, ctx->d_tw, ctx->stream);
+    env.timer->end(t);
+    CU(cudaGetLastError());
+    t = env.timer->begin(C_MAC);
+    if (ctx->mac_variant == 1)
+      launch_mac_stream(dmj, (int)mj.size(), QB, B, ctx->stream);
+    else
+      launch_mac_tiled(dmj, dt, (int)tiles.size(), B, TB, ctx->stream);
+    env.timer->end(t);
+    CU(cudaGetLastError());
+    t = env.timer->begin(C_FFT_INV);
+    launch_irfft_ola(dij, (int)ij.size(), QB, B, ctx->d_tw, ctx->stream);
+    env.timer->end(t);
+    CU(cudaGetLastError());
+    env.launches += 3;
+  }
+  return GAC_OK;
+}
+
+// Runs every signal's op chain, position by position, batching equal kinds across signals.
+static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
+  gac_context* ctx = env.ctx;
+  size_t maxlen = 0;
+  for (auto& s : sigs) maxlen = std::max(maxlen, s.ops ? s.ops->size() : 0);
+  for (size_t pos = 0; pos < maxlen; pos++) {
+    std::vector<size_t> gains, biquads, convs;
+    for (size_t i = 0; i < sigs.size(); i++) {
+      if (!sigs[i].ops || pos >= sigs[i].ops->size()) continue;
+      switch ((*sigs[i].ops)[pos].kind) {
+        case GAC_OP_GAIN: gains.push_back(i); break;
+        case GAC_OP_BIQUAD: biquads.push_back(i); break;
+        case GAC_OP_CONVOLVER: convs.push_back(i); break;
+      }
+    }
+    // ---------------- GainNode (K2 + K4).  A gain directly followed by a convolver is fused into K5.
+    if (!gains.empty()) {
+      std::vector<ParamJob> pj;
+      std::vector<float*> tabs(gains.size(), nullptr);
+      for (size_t k = 0; k < gains.size(); k++) {
+        int rc = param_table(env, (*sigs[gains[k]].ops)[pos].p0, true, pj, &tabs[k]);
+        if (rc) return rc;
+      }
+      int rc = run_param_jobs(env, pj);
+      if (rc) return rc;
+      auto& gj = env.keep->make<GainJob>();
+      for (size_t k = 0; k < gains.size(); k++) {
+        Sig& s = sigs[gains[k]];
+        const auto& ops = *s.ops;
+        const bool next_is_conv = pos + 1 < ops.size() && ops[pos + 1].kind == GAC_OP_CONVOLVER && ops[pos + 1].ir;
+        if (next_is_conv) {
+          // fused into the convolver's forward FFT load (K4 inside K5): same float32 multiply, same gating
+          env.fused[&s] = std::make_pair((const float*)tabs[k], ops[pos].p0.value);
+          continue;
+        }
+        GainJob g;
+        g.sig[0] = s.p[0];
+        g.sig[1] = s.p[1];
+        g.gain = tabs[k];
+        g.gain_const = ops[pos].p0.value;
+        g.lo = s.lo;
+        g.hi = s.hi;
+        gj.push_back(g);
+      }
+      if (!gj.empty()) {
+        GainJob* dg = nullptr;
+        if ((rc = env.scratch->upload(&dg, gj))) return rc;
+        int t = env.timer->begin(C_GAIN);
+        launch_gain(dg, (int)gj.size(), env.Npad, ctx->stream);
+        env.timer->end(t);
+        env.launches += 1;
+        CU(cudaGetLastError());
+      }
+    }
+    // ---------------- BiQuadFilterNode (K2 + K3)
+    if (!biquads.empty()) {
+      const size_t per_job = (size_t)env.Npad * (5 * 4 + 4 + 4 + 2) + (size_t)env.NQ * 12;
+      const size_t max_jobs = std::max<size_t>(1, ctx->scratch_budget / per_job);
+      for (size_t k0 = 0; k0 < biquads.size(); k0 += max_jobs) {
+        const size_t nk = std::min(max_jobs, biquads.size() - k0);
+        std::vector<ParamJob> pj;
+        auto& bj = env.keep->make<BiquadJob>();
+        for (size_t k = 0; k < nk; k++) {
+          Sig& s = sigs[biquads[k0 + k]];
+          const OpH& op = (*s.ops)[pos];
+          BiquadJob j{};
+          float *tf = nullptr, *tq = nullptr, *tg = nullptr;
+          int rc;
+          if ((rc = param_table(env, op.p0, true, pj, &tf))) return rc;
+          if ((rc = param_table(env, op.p1, true, pj, &tq))) return rc;
+          if ((rc = param_table(env, op.p2, false, pj, &tg))) return rc;
+          j.sig[0] = s.p[0];
+          j.sig[1] = s.p[1];
+          j.freq = tf;
+          j.q = tq;
+          j.gain = tg;
+          j.freq_const = op.p0.value;
+          j.q_const = op.p1.value;
+          j.gain_const = op.p2.value;
+          j.type = op.ftype;
+          j.lo = s.lo;
+          j.hi = s.hi;
+          if ((rc = env.scratch->alloc(&j.coef, (size_t)env.Npad * 5))) return rc;
+          bj.push_back(j);
+        }
+        int rc = run_param_jobs(env, pj);
+        if (rc) return rc;
+        BiquadJob* dbj = nullptr;
+        uint8_t* dsel = nullptr;
+        int32_t* dlast = nullptr;
+        if ((rc = env.scratch->upload(&dbj, bj))) return rc;
+        if ((rc = env.scratch->alloc(&dsel, nk * 2 * (size_t)env.Npad))) return rc;
+        if ((rc = env.scratch->alloc(&dlast, nk * 2 * (size_t)env.NQ))) return rc;
+        int t = env.timer->begin(C_BIQUAD);
+        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dsel, dlast, ctx->stream);
+        env.timer->end(t);
+        env.launches += 4;
+        CU(cudaGetLastError());
+      }
+    }
+    // ---------------- ConvolverNode (K5, K6, K7)
+    if (!convs.empty()) {
+      std::vector<ConvItem> items;
+      auto& zj = env.keep->make<GainJob>();
+      for (size_t k = 0; k < convs.size(); k++) {
+        Sig& s = sigs[convs[k]];
+        const OpH& op = (*s.ops)[pos];
+        if (!op.ir) {
+          // ConvolverNode without a Buffer clears its output (ConvolverNode.cs:107-119): silence from here on
+          GainJob g;
+          g.sig[0] = s.p[0];
+          g.sig[1] = s.p[1];
+          g.gain = nullptr;
+          g.gain_const = 0.f;
+          g.lo = 0;
+          g.hi = 0;
+          zj.push_back(g);
+          s.lo = s.hi = 0;
+          continue;
+        }
+        const float* gtab = nullptr;
+        float gconst = 1.0f;
+        auto f = env.fused.find(&s);
+        if (f != env.fused.end()) {
+          gtab = f->second.first;
+          gconst = f->second.second;
+          env.fused.erase(f);
+        }
+        for (int c = 0; c < 2; c++) {
+          ConvItem it;
+          it.x = s.p[c];
+          it.H = op.ir->d_H + (size_t)c * op.ir->P16 * ctx->B;
+          it.P = op.ir->P;
+          it.lo = s.lo;
+          it.hi = s.hi;
+          it.gain_tab = gtab;
+          it.gain_const = gconst;
+          items.push_back(it);
+        }
+        s.lo = 0;  // ConvolverNode always marks its output non-silent (ConvolverNode.cs:153)
+        s.hi = env.Npad;
+      }
+      if (!zj.empty()) {
+        GainJob* dz = nullptr;
+        int rc = env.scratch->upload(&dz, zj);
+        if (rc) return rc;
+        launch_gain(dz, (int)zj.size(), env.Npad, ctx->stream);
+        env.launches += 1;
+      }
+      int rc = conv_batch(env, items);
+      if (rc) return rc;
+    }
+  }
+  return GAC_OK;
+}
+
+// source stage, render drivers, NCCL bus reduce and the kernel-level entry points
+#include "engine_render.inl"

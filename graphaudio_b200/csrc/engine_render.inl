@@ -1,0 +1,801 @@
+// engine_render.inl — included at the bottom of engine.cu.
+// Source planning (AudioBufferSourceNode semantics), the render drivers, the NCCL bus reduce and the
+// kernel-level test entry points.
+
+// ------------------------------------------------------------------------------------------ source stage (K1)
+struct ResampleTable {
+  std::vector<int32_t> k;
+  std::vector<float> t;
+  int64_t n_active_blocks = 0;
+  int64_t n_zero_from = 0;
+  int32_t* d_k = nullptr;
+  float* d_t = nullptr;
+};
+
+// Nodes/AudioBufferSourceNode.cs:131-376, non-loop paths.  Decides, on the host, which quanta the source emits
+// (block-granular start/stop :137-143; final block dropped :360-368) and, for the CubicResampler path, replays
+// the data-independent phase recurrence of CubicResampler.cs:40-60 exactly (double Pos, (int)Pos consumes).
+static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices, std::vector<Sig>& sigs) {
+  gac_context* ctx = env.ctx;
+  const double inc = (double)128 / (double)ctx->fs;
+  const std::vector<double>& bt = ctx->h_bt;
+  auto& cj = env.keep->make<SourceJob>();
+  auto& rj = env.keep->make<ResampleJob>();
+  std::map<std::tuple<double, int64_t, int64_t, int64_t>, std::shared_ptr<ResampleTable>> tables;
+  const double inf = std::numeric_limits<double>::infinity();
+
+  for (size_t i = 0; i < voices.size(); i++) {
+    const VoiceH& v = *voices[i];
+    Sig& s = sigs[i];
+    const gac_buffer* buf = v.src;
+    s.lo = s.hi = 0;
+    const float* src0 = buf->d;
+    const float* src1 = buf->nch > 1 ? buf->d + buf->stride : buf->d;  // mono: 1 -> 2 up-mix copies the channel (AudioNodeInput.cs:201-213)
+    SourceJob job{};
+    job.src[0] = src0;
+    job.src[1] = src1;
+    job.dst[0] = s.p[0];
+    job.dst[1] = s.p[1];
+    job.pos0 = 0;
+    job.out0 = 0;
+    job.n_emit = 0;
+    if (std::isnan(v.when)) {  // Start() never called: ProduceSilence forever
+      cj.push_back(job);
+      continue;
+    }
+    const double startTime = std::max(0.0, v.when);            // :93
+    const double offset = std::max(0.0, v.offset);             // :94
+    const int64_t pos = (int64_t)(offset * (double)buf->rate);  // :96
+    double stopTime = std::numeric_limits<double>::quiet_NaN();
+    if (!std::isinf(v.duration) && v.duration >= 0) stopTime = startTime + v.duration;  // :106-110 (and Stop() is then ignored, :120-121)
+    else if (!std::isnan(v.stop_when)) stopTime = std::max(0.0, v.stop_when);           // :123-125
+    // first playing block: t1 = t0 + 128/fs > startTime ; playing while t0 < stopTime  (:133-143)
+    int64_t b_start = 0;
+    {
+      int64_t lo = 0, hi = env.NQ;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (bt[mid] + inc > startTime) hi = mid; else lo = mid + 1;
+      }
+      b_start = lo;
+    }
+    int64_t b_stop = env.NQ;
+    if (!std::isnan(stopTime)) {
+      int64_t lo = b_start, hi = env.NQ;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (!(bt[mid] < stopTime)) hi = mid; else lo = mid + 1;
+      }
+      b_stop = lo;
+    }
+    int64_t durEnd = v.duration < inf ? (int64_t)(offset * (double)buf->rate) + (int64_t)(v.duration * (double)buf->rate) : buf->n;  // :179-182
+    durEnd = std::min(durEnd, buf->n);
+    const double ratio = (double)buf->rate / (double)ctx->fs;  // :168
+    const double eff = ratio * (double)v.rate;                 // :169
+    const int64_t max_blocks = std::max<int64_t>(0, b_stop - b_start);
+    if (max_blocks == 0 || pos >= durEnd) {
+      cj.push_back(job);
+      continue;
+    }
+    if (eff == 1.0) {
+      // block k (k-th playing block) is emitted iff pos + 128(k+1) < durEnd (:224,:360), and is then a full block
+      int64_t n_data = (durEnd - pos + 127) / 128 - 1;
+      int64_t nb = std::max<int64_t>(0, std::min(n_data, max_blocks));
+      job.pos0 = pos;
+      job.out0 = b_start * 128;
+      job.n_emit = nb * 128;
+      s.lo = job.out0;
+      s.hi = job.out0 + job.n_emit;
+      cj.push_back(job);
+    } else {
+      const int64_t avail = durEnd - pos;
+      const int64_t n_out_max = max_blocks * 128;
+      auto key = std::make_tuple(eff, pos, durEnd, n_out_max);
+      auto it = tables.find(key);
+      std::shared_ptr<ResampleTable> tab;
+      if (it != tables.end()) {
+        tab = it->second;
+      } else {
+        tab = std::make_shared<ResampleTable>();
+        env.keep->items.push_back(tab);
+        if (avail >= 4) {
+          tab->k.reserve((size_t)n_out_max);
+          tab->t.reserve((size_t)n_out_max);
+          int64_t inPos = 4;  // priming: four Shift()s (CubicResampler.cs:31-35)
+          double Pos = 0.0;
+          int64_t m = 0, M = -1;
+          int64_t active = 0;
+          for (int64_t blk = 0; blk < max_blocks; blk++) {
+            int64_t produced = 0;
+            for (int i = 0; i < 128; i++) {
+              int consume = (int)Pos;                  // :42
+              if (inPos + consume > avail) { M = m; break; }  // :43-44
+              inPos += consume;
+              Pos -= consume;                          // :49
+              tab->k.push_back((int32_t)(inPos - 4));
+              tab->t.push_back((float)Pos);            // :51
+              Pos += eff;                              // :59
+              m++;
+              produced++;
+            }
+            // :360-368: a block that produced nothing, or after which every input frame is consumed, is cleared
+            if (produced == 0 || pos + inPos >= durEnd) break;
+            active = blk + 1;
+            if (M >= 0) break;  // stalled inside a kept block: the next block produces nothing
+          }
+          tab->n_active_blocks = active;
+          tab->n_zero_from = (M >= 0) ? M : m;
+          tab->k.resize((size_t)std::min<int64_t>(m, active * 128));
+          tab->t.resize(tab->k.size());
+          if (!tab->k.empty()) {
+            int rc;
+            if ((rc = env.scratch->upload(&tab->d_k, tab->k))) return rc;
+            if ((rc = env.scratch->upload(&tab->d_t, tab->t))) return rc;
+          }
+        }
+        tables[key] = tab;
+      }
+      if (tab->n_active_blocks == 0) {
+        cj.push_back(job);
+        continue;
+      }
+      ResampleJob r{};
+      r.src[0] = src0 + pos;
+      r.src[1] = src1 + pos;
+      r.dst[0] = s.p[0];
+      r.dst[1] = s.p[1];
+      r.k = tab->d_k;
+      r.t = tab->d_t;
+      r.out0 = b_start * 128;
+      r.n_emit = tab->n_active_blocks * 128;
+      r.n_zero_from = std::min<int64_t>(tab->n_zero_from, (int64_t)tab->k.size());
+      s.lo = r.out0;
+      s.hi = r.out0 + r.n_emit;
+      rj.push_back(r);
+    }
+  }
+  int t = env.timer->begin(C_SOURCE);
+  if (!cj.empty()) {
+    SourceJob* d = nullptr;
+    int rc = env.scratch->upload(&d, cj);
+    if (rc) return rc;
+    launch_source_copy(d, (int)cj.size(), env.Npad, ctx->stream);
+    env.launches++;
+  }
+  if (!rj.empty()) {
+    ResampleJob* d = nullptr;
+    int rc = env.scratch->upload(&d, rj);
+    if (rc) return rc;
+    launch_resample(d, (int)rj.size(), env.Npad, ctx->stream);
+    env.launches++;
+  }
+  env.timer->end(t);
+  CU(cudaGetLastError());
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NCCL (dlopen'ed)
+struct NcclUid {
+  char internal[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = (int (*)(NcclUid*))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void**, int, NcclUid, int))dlsym(api.lib, "ncclCommInitRank");
+      api.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclReduce");
+      api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.Reduce || !api.CommDestroy) return nullptr;
+  return &api;
+}
+static int nccl_fail(NcclApi* a, int r, const char* what) {
+  return fail(GAC_ERR_NCCL, "%s failed: %s", what, (a && a->GetErrorString) ? a->GetErrorString(r) : "nccl error");
+}
+
+extern "C" int gac_comm_unique_id(void* id128) {
+  if (!id128) return fail(GAC_ERR_INVALID_ARGUMENT, "id is null");
+  NcclApi* a = nccl_api();
+  if (!a) return fail(GAC_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  NcclUid uid;
+  int r = a->GetUniqueId(&uid);
+  if (r != 0) return nccl_fail(a, r, "ncclGetUniqueId");
+  memcpy(id128, uid.internal, 128);
+  return GAC_OK;
+}
+extern "C" int gac_comm_init(gac_context* ctx, const void* id128, int rank, int n_ranks) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(GAC_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+  NcclApi* a = nccl_api();
+  if (!a) return fail(GAC_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->comm) gac_comm_destroy(ctx);
+  NcclUid uid;
+  memcpy(uid.internal, id128, 128);
+  void* comm = nullptr;
+  int r = a->CommInitRank(&comm, n_ranks, uid, rank);
+  if (r != 0) return nccl_fail(a, r, "ncclCommInitRank");
+  ctx->comm = comm;
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  return GAC_OK;
+}
+extern "C" int gac_comm_destroy(gac_context* ctx) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (ctx->comm) {
+    NcclApi* a = nccl_api();
+    cudaStreamSynchronize(ctx->stream);
+    if (a) a->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ctx->rank = 0;
+  ctx->n_ranks = 1;
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ render core
+struct RenderArgs {
+  const gac_graph* const* graphs = nullptr;
+  int n_graphs = 0;
+  int64_t first_frame = 0, n_frames = 0;
+  float* const* h_out = nullptr;  // [n_graphs * n_out_channels] host rows, or null
+  float* d_out = nullptr;         // [n_graphs][n_out_channels][n_frames] device, or null
+  int n_out = 2;
+  int64_t start_index = 0;
+  bool sharded = false;
+  int root = 0;
+  bool sync = true;
+};
+
+static int mix_into(RenderEnv& env, std::vector<MixJob>& jobs, std::vector<MixInput>& inputs) {
+  if (jobs.empty()) return GAC_OK;
+  auto& hj = env.keep->make<MixJob>();
+  auto& hi = env.keep->make<MixInput>();
+  hj = jobs;
+  hi = inputs;
+  MixJob* dj = nullptr;
+  MixInput* di = nullptr;
+  int rc;
+  if ((rc = env.scratch->upload(&dj, hj))) return rc;
+  if ((rc = env.scratch->upload(&di, hi))) return rc;
+  int t = env.timer->begin(C_MIX);
+  for (size_t j0 = 0; j0 < hj.size(); j0 += 65535) {
+    size_t nj = std::min<size_t>(65535, hj.size() - j0);
+    launch_mix(dj + j0, (int)nj, di, env.Npad, env.ctx->stream);
+    env.launches++;
+  }
+  env.timer->end(t);
+  CU(cudaGetLastError());
+  return GAC_OK;
+}
+
+static int render_core(gac_context* ctx, const RenderArgs& a) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");  // ObjectDisposedException (AudioContextBase.cs:54-55)
+  if (!a.graphs || a.n_graphs <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "no graph");
+  if (a.n_frames <= 0) return fail(GAC_ERR_OUT_OF_RANGE, "Frame count must be positive.");         // OfflineAudioContext.cs:35-36
+  if (a.first_frame < 0 || a.start_index < 0) return fail(GAC_ERR_OUT_OF_RANGE, "Start index must be non-negative.");  // :38-39
+  if (a.n_out < 1) return fail(GAC_ERR_INVALID_ARGUMENT, "Output buffer must have at least one channel.");             // :32-33
+  if (a.n_out > 2) return fail(GAC_ERR_OUT_OF_RANGE, "the destination has 2 channels (AudioDestinationNode.cs:17)");
+  for (int g = 0; g < a.n_graphs; g++) {
+    if (!a.graphs[g]) return fail(GAC_ERR_INVALID_ARGUMENT, "graph %d is null", g);
+    if (a.graphs[g]->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "graph %d belongs to another context", g);
+  }
+  if (a.h_out)
+    for (int i = 0; i < a.n_graphs * a.n_out; i++)
+      if (!a.h_out[i]) return fail(GAC_ERR_INVALID_ARGUMENT, "Channel %d buffer is null.", i % a.n_out);  // :47-48
+  if (a.sharded && !ctx->comm && ctx->n_ranks > 1) return fail(GAC_ERR_INVALID_OPERATION, "gac_comm_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+
+  const int B = ctx->B;
+  const int64_t total = a.first_frame + a.n_frames;
+  RenderEnv env;
+  Scratch scratch(ctx);
+  HostKeep keep;
+  Timer timer(ctx);
+  env.ctx = ctx;
+  env.scratch = &scratch;
+  env.keep = &keep;
+  env.timer = &timer;
+  env.Npad = ((total + B - 1) / B) * B;
+  env.NQ = env.Npad / 128;
+  env.QB = env.Npad / B;
+  int rc = ensure_block_times(ctx, env.NQ + 1);
+  if (rc) return rc;
+
+  // ---- voices
+  std::vector<const VoiceH*> voices;
+  std::vector<int> voice_graph;
+  for (int g = 0; g < a.n_graphs; g++)
+    for (auto& v : a.graphs[g]->voices) {
+      voices.push_back(&v);
+      voice_graph.push_back(g);
+    }
+  const size_t S = voices.size();
+  float* d_sig = nullptr;
+  if ((rc = scratch.alloc(&d_sig, std::max<size_t>(1, S) * 2 * (size_t)env.Npad))) return rc;
+  std::vector<Sig> sigs(S);
+  for (size_t i = 0; i < S; i++) {
+    sigs[i].p[0] = d_sig + (i * 2 + 0) * (size_t)env.Npad;
+    sigs[i].p[1] = d_sig + (i * 2 + 1) * (size_t)env.Npad;
+    sigs[i].ops = &voices[i]->ops;
+  }
+  if ((rc = plan_sources(env, voices, sigs))) return rc;
+  if ((rc = run_chains(env, sigs))) return rc;
+
+  // ---- buses: fan-in in connection (= voice index) order, AudioNodeInput.cs:118-137
+  size_t NB = 0;
+  std::vector<size_t> bus_base(a.n_graphs);
+  for (int g = 0; g < a.n_graphs; g++) {
+    bus_base[g] = NB;
+    NB += a.graphs[g]->buses.size();
+  }
+  float* d_bus = nullptr;
+  std::vector<Sig> buses(NB);
+  if (NB) {
+    if ((rc = scratch.alloc(&d_bus, NB * 2 * (size_t)env.Npad))) return rc;
+    std::vector<MixJob> mjobs;
+    std::vector<MixInput> minputs;
+    size_t vbase = 0;
+    for (int g = 0; g < a.n_graphs; g++) {
+      const gac_graph* gr = a.graphs[g];
+      for (size_t b = 0; b < gr->buses.size(); b++) {
+        Sig& bs = buses[bus_base[g] + b];
+        bs.p[0] = d_bus + ((bus_base[g] + b) * 2 + 0) * (size_t)env.Npad;
+        bs.p[1] = d_bus + ((bus_base[g] + b) * 2 + 1) * (size_t)env.Npad;
+        bs.ops = &gr->buses[b].ops;
+        MixJob mj;
+        mj.dst[0] = bs.p[0];
+        mj.dst[1] = bs.p[1];
+        mj.first_input = (int)minputs.size();
+        int64_t lo = std::numeric_limits<int64_t>::max(), hi = 0;
+        for (size_t v = 0; v < gr->voices.size(); v++) {
+          if (gr->voices[v].bus != (int)b) continue;
+          const Sig& vs = sigs[vbase + v];
+          if (vs.hi <= vs.lo) continue;  // silent throughout: never mixed (:127)
+          MixInput in;
+          in.src[0] = vs.p[0];
+          in.src[1] = vs.p[1];
+          in.lo = vs.lo;
+          in.hi = vs.hi;
+          minputs.push_back(in);
+          lo = std::min(lo, vs.lo);
+          hi = std::max(hi, vs.hi);
+        }
+        mj.n_inputs = (int)minputs.size() - mj.first_input;
+        bs.lo = mj.n_inputs ? lo : 0;  // non-silent where any input was mixed (convex hull)
+        bs.hi = mj.n_inputs ? hi : 0;
+        mjobs.push_back(mj);
+      }
+      vbase += gr->voices.size();
+    }
+    if ((rc = mix_into(env, mjobs, minputs))) return rc;
+
+    if (a.sharded && ctx->n_ranks > 1) {
+      // the one exchange step: per-rank partial bus sums -> root, float32 sum over NVLink/NVSwitch
+      NcclApi* api = nccl_api();
+      if (!api) return fail(GAC_ERR_NCCL, "libnccl.so.2 could not be loaded");
+      int t = timer.begin(C_MIX);
+      int r = api->Reduce(d_bus, d_bus, NB * 2 * (size_t)env.Npad, /*ncclFloat32*/ 7, /*ncclSum*/ 0, a.root, ctx->comm, ctx->stream);
+      timer.end(t);
+      if (r != 0) return nccl_fail(api, r, "ncclReduce");
+      for (auto& bs : buses) {  // other ranks' voices may be audible anywhere
+        bs.lo = 0;
+        bs.hi = env.Npad;
+      }
+    }
+  }
+  const bool is_root = !a.sharded || ctx->n_ranks <= 1 || ctx->rank == a.root;
+  if (is_root) {
+    if ((rc = run_chains(env, buses))) return rc;
+    // ---- destination: fan-in of buses and direct voices in connection order; alias when there is exactly one input
+    std::vector<const float*> dest0(a.n_graphs), dest1(a.n_graphs);
+    float* d_dest = nullptr;
+    std::vector<MixJob> mjobs;
+    std::vector<MixInput> minputs;
+    size_t vbase = 0;
+    size_t need = 0;
+    for (int g = 0; g < a.n_graphs; g++)
+      if (a.graphs[g]->dest_inputs.size() != 1) need++;
+    if (need && (rc = scratch.alloc(&d_dest, need * 2 * (size_t)env.Npad))) return rc;
+    size_t used = 0;
+    for (int g = 0; g < a.n_graphs; g++) {
+      const gac_graph* gr = a.graphs[g];
+      auto sig_of = [&](int x) -> const Sig& { return x >= 0 ? buses[bus_base[g] + x] : sigs[vbase + (size_t)(~x)]; };
+      if (gr->dest_inputs.size() == 1 && sig_of(gr->dest_inputs[0]).lo == 0 && sig_of(gr->dest_inputs[0]).hi == env.Npad) {
+        const Sig& s = sig_of(gr->dest_inputs[0]);  // (0 + x) == x exactly
+        dest0[g] = s.p[0];
+        dest1[g] = s.p[1];
+      } else {
+        if (gr->dest_inputs.size() == 1) {  // rare: single input with silent-flagged quanta; needs its own buffer
+          float* extra = nullptr;
+          if ((rc = scratch.alloc(&extra, 2 * (size_t)env.Npad))) return rc;
+          dest0[g] = extra;
+          dest1[g] = extra + env.Npad;
+        } else {
+          dest0[g] = d_dest + (used * 2 + 0) * (size_t)env.Npad;
+          dest1[g] = d_dest + (used * 2 + 1) * (size_t)env.Npad;
+          used++;
+        }
+        MixJob mj;
+        mj.dst[0] = const_cast<float*>(dest0[g]);
+        mj.dst[1] = const_cast<float*>(dest1[g]);
+        mj.first_input = (int)minputs.size();
+        for (int x : gr->dest_inputs) {
+          const Sig& s = sig_of(x);
+          if (s.hi <= s.lo) continue;
+          MixInput in;
+          in.src[0] = s.p[0];
+          in.src[1] = s.p[1];
+          in.lo = s.lo;
+          in.hi = s.hi;
+          minputs.push_back(in);
+        }
+        mj.n_inputs = (int)minputs.size() - mj.first_input;
+        mjobs.push_back(mj);
+      }
+      vbase += gr->voices.size();
+    }
+    if ((rc = mix_into(env, mjobs, minputs))) return rc;
+
+    // ---- output: frames [first_frame, first_frame + n_frames) (OfflineAudioContext.cs:77-101)
+    int t = timer.begin(C_D2H);
+    for (int g = 0; g < a.n_graphs; g++) {
+      for (int c = 0; c < a.n_out; c++) {
+        const float* src = (c == 0 ? dest0[g] : dest1[g]) + a.first_frame;
+        if (a.h_out) {
+          CU(cudaMemcpyAsync(a.h_out[(size_t)g * a.n_out + c] + a.start_index, src, sizeof(float) * (size_t)a.n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+        } else if (a.d_out) {
+          CU(cudaMemcpyAsync(a.d_out + ((size_t)g * a.n_out + c) * (size_t)a.n_frames, src, sizeof(float) * (size_t)a.n_frames, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+        }
+      }
+    }
+    timer.end(t);
+  }
+  // ---- finish: the host job arrays in `keep` must outlive the stream work, so every render synchronises here
+  gac_stats st{};
+  timer.finish(&st);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "render failed: %s", cudaGetErrorString(e));
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "render failed: %s", cudaGetErrorString(e));
+  st.conv_units = env.conv_units;
+  st.algorithmic_bytes = env.alg_bytes;
+  st.mac_complex_macs = env.macs;
+  st.kernel_launches = env.launches;
+  st.voices = (int64_t)S;
+  st.frames = a.n_frames;
+  ctx->stats = st;
+  return GAC_OK;
+}
+
+extern "C" int gac_render(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames, float* const* out_channels,
+                          int n_out_channels, int64_t start_index) {
+  if (!out_channels) return fail(GAC_ERR_INVALID_ARGUMENT, "Output buffer must have at least one channel.");
+  RenderArgs a;
+  a.graphs = &graph;
+  a.n_graphs = 1;
+  a.first_frame = first_frame;
+  a.n_frames = n_frames;
+  a.h_out = out_channels;
+  a.n_out = n_out_channels;
+  a.start_index = start_index;
+  return render_core(ctx, a);
+}
+extern "C" int gac_render_device(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames, float* d_out, int n_out_channels,
+                                 int sync) {
+  if (!d_out) return fail(GAC_ERR_INVALID_ARGUMENT, "d_out is null");
+  RenderArgs a;
+  a.graphs = &graph;
+  a.n_graphs = 1;
+  a.first_frame = first_frame;
+  a.n_frames = n_frames;
+  a.d_out = d_out;
+  a.n_out = n_out_channels;
+  a.sync = sync != 0;
+  return render_core(ctx, a);
+}
+extern "C" int gac_render_batch(gac_context* ctx, const gac_graph* const* graphs, int n_graphs, int64_t n_frames, float* const* out_channels,
+                                int n_out_channels) {
+  if (!out_channels) return fail(GAC_ERR_INVALID_ARGUMENT, "Output buffer must have at least one channel.");
+  RenderArgs a;
+  a.graphs = graphs;
+  a.n_graphs = n_graphs;
+  a.n_frames = n_frames;
+  a.h_out = out_channels;
+  a.n_out = n_out_channels;
+  return render_core(ctx, a);
+}
+extern "C" int gac_render_sharded(gac_context* ctx, const gac_graph* shard, int64_t n_frames, int root, float* const* out_channels,
+                                  int n_out_channels) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!shard) return fail(GAC_ERR_INVALID_ARGUMENT, "graph is null");
+  for (auto& v : shard->voices)
+    if (v.bus < 0) return fail(GAC_ERR_UNSUPPORTED, "sharded renders need every voice routed through a bus (the bus is what is reduced)");
+  if (shard->buses.empty()) return fail(GAC_ERR_UNSUPPORTED, "sharded renders need at least one bus");
+  const bool is_root = ctx->n_ranks <= 1 || ctx->rank == root;
+  if (is_root && !out_channels) return fail(GAC_ERR_INVALID_ARGUMENT, "Output buffer must have at least one channel.");
+  RenderArgs a;
+  a.graphs = &shard;
+  a.n_graphs = 1;
+  a.n_frames = n_frames;
+  a.h_out = is_root ? out_channels : nullptr;
+  a.n_out = n_out_channels;
+  a.sharded = true;
+  a.root = root;
+  return render_core(ctx, a);
+}
+
+extern "C" int gac_get_stats(gac_context* ctx, gac_stats* out) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!out) return fail(GAC_ERR_INVALID_ARGUMENT, "out is null");
+  *out = ctx->stats;
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ kernel-level entry points
+// Host pointers in, host pointers out; used by the parity tests to pin each kernel against the oracle.
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <typename T> T* as() { return (T*)p; }
+};
+static int dev_alloc(DevBuf& b, size_t bytes) {
+  CU(cudaMalloc(&b.p, std::max<size_t>(bytes, 16)));
+  return GAC_OK;
+}
+
+extern "C" int gac_rfft_fwd_batch(gac_context* ctx, const float* x, int n_signals, int64_t n_blocks, float* spectra) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!x || !spectra || n_signals <= 0 || n_blocks <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int B = ctx->B;
+  const size_t n = (size_t)n_signals * n_blocks * B;
+  DevBuf dx, dX, dj;
+  int rc;
+  if ((rc = dev_alloc(dx, n * 4)) || (rc = dev_alloc(dX, n * 8)) || (rc = dev_alloc(dj, sizeof(FftFwdJob) * n_signals))) return rc;
+  CU(cudaMemcpyAsync(dx.p, x, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<FftFwdJob> jobs(n_signals);
+  for (int s = 0; s < n_signals; s++) {
+    jobs[s] = FftFwdJob{dx.as<float>() + (size_t)s * n_blocks * B, dX.as<float2>() + (size_t)s * n_blocks * B, nullptr, nullptr, 1.0f,
+                        n_blocks * B, n_blocks, 0, std::numeric_limits<int64_t>::max()};
+  }
+  CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(FftFwdJob) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
+  launch_rfft_fwd(dj.as<FftFwdJob>(), n_signals, n_blocks, B, ctx->d_tw, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(spectra, dX.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAC_OK;
+}
+
+extern "C" int gac_irfft_ola_batch(gac_context* ctx, const float* Y, int n_signals, int64_t n_blocks, float* y) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!Y || !y || n_signals <= 0 || n_blocks <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int B = ctx->B;
+  const size_t n = (size_t)n_signals * n_blocks * B;
+  DevBuf dY, dy, dj;
+  int rc;
+  if ((rc = dev_alloc(dY, n * 8)) || (rc = dev_alloc(dy, n * 4)) || (rc = dev_alloc(dj, sizeof(FftInvJob) * n_signals))) return rc;
+  CU(cudaMemcpyAsync(dY.p, Y, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<FftInvJob> jobs(n_signals);
+  for (int s = 0; s < n_signals; s++)
+    jobs[s] = FftInvJob{dY.as<float2>() + (size_t)s * n_blocks * B, dy.as<float>() + (size_t)s * n_blocks * B, n_blocks};
+  CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(FftInvJob) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
+  launch_irfft_ola(dj.as<FftInvJob>(), n_signals, n_blocks, B, ctx->d_tw, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(y, dy.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAC_OK;
+}
+
+extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H, int n_signals, int64_t n_blocks, int n_partitions, int variant,
+                                float* Y) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!X || !H || !Y || n_signals <= 0 || n_blocks <= 0 || n_partitions <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int B = ctx->B;
+  const int TB = ctx->tile_blocks;
+  const int64_t QBpad = ((n_blocks + TB - 1) / TB) * TB;
+  const int64_t rowsX = TB + QBpad;
+  const int P16 = std::max(16, ((n_partitions + 15) / 16) * 16);
+  const int groups = B / 128;
+  DevBuf dX, dH, dY, dj, dt;
+  int rc;
+  if ((rc = dev_alloc(dX, (size_t)n_signals * rowsX * B * 8)) || (rc = dev_alloc(dH, (size_t)n_signals * P16 * B * 8)) ||
+      (rc = dev_alloc(dY, (size_t)n_signals * QBpad * B * 8)))
+    return rc;
+  CU(cudaMemsetAsync(dX.p, 0, (size_t)n_signals * rowsX * B * 8, ctx->stream));
+  CU(cudaMemsetAsync(dH.p, 0, (size_t)n_signals * P16 * B * 8, ctx->stream));
+  std::vector<MacJob> jobs;
+  std::vector<MacTile> tiles;
+  for (int s = 0; s < n_signals; s++) {
+    float2* Xs = dX.as<float2>() + (size_t)s * rowsX * B + (size_t)TB * B;
+    float2* Hs = dH.as<float2>() + (size_t)s * P16 * B;
+    float2* Ys = dY.as<float2>() + (size_t)s * QBpad * B;
+    CU(cudaMemcpyAsync(Xs, X + (size_t)s * n_blocks * B * 2, (size_t)n_blocks * B * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(Hs, H + (size_t)s * n_partitions * B * 2, (size_t)n_partitions * B * 8, cudaMemcpyHostToDevice, ctx->stream));
+    for (int g = 0; g < groups; g++) jobs.push_back(MacJob{Xs + g * 128, Hs + g * 128, Ys + g * 128, n_partitions, g == 0});
+  }
+  for (int j = 0; j < (int)jobs.size(); j++)
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += TB) tiles.push_back(MacTile{j, (int)b0});
+  if ((rc = dev_alloc(dj, sizeof(MacJob) * jobs.size())) || (rc = dev_alloc(dt, sizeof(MacTile) * tiles.size()))) return rc;
+  CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(MacJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dt.p, tiles.data(), sizeof(MacTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (variant == 1)
+    launch_mac_stream(dj.as<MacJob>(), (int)jobs.size(), n_blocks, B, ctx->stream);
+  else
+    launch_mac_tiled(dj.as<MacJob>(), dt.as<MacTile>(), (int)tiles.size(), B, TB, ctx->stream);
+  CU(cudaGetLastError());
+  for (int s = 0; s < n_signals; s++)
+    CU(cudaMemcpyAsync(Y + (size_t)s * n_blocks * B * 2, dY.as<float2>() + (size_t)s * QBpad * B, (size_t)n_blocks * B * 8, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAC_OK;
+}
+
+extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signals, int64_t n_frames, const float* ir, int64_t ir_frames,
+                                  int normalize, float* y) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!x || !ir || !y || n_signals <= 0 || n_frames <= 0 || ir_frames <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int B = ctx->B;
+  const int64_t Npad = ((n_frames + B - 1) / B) * B;
+  // impulse responses: one n_signals-channel "buffer"
+  DevBuf dir;
+  int rc;
+  const int64_t stride = ((ir_frames + 8 + 63) / 64) * 64;
+  if ((rc = dev_alloc(dir, (size_t)n_signals * stride * 4))) return rc;
+  CU(cudaMemsetAsync(dir.p, 0, (size_t)n_signals * stride * 4, ctx->stream));
+  for (int s = 0; s < n_signals; s++)
+    CU(cudaMemcpyAsync(dir.as<float>() + (size_t)s * stride, ir + (size_t)s * ir_frames, (size_t)ir_frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+  gac_ir irh{};
+  irh.ctx = ctx;
+  irh.nch = n_signals;
+  rc = ir_prepare_device(ctx, dir.as<float>(), stride, n_signals, ir_frames, normalize != 0, &irh);
+  DevBuf holdH, holdS;
+  holdH.p = irh.d_H;
+  holdS.p = irh.d_scale;
+  if (rc) return rc;
+  DevBuf dx;
+  if ((rc = dev_alloc(dx, (size_t)n_signals * Npad * 4))) return rc;
+  CU(cudaMemsetAsync(dx.p, 0, (size_t)n_signals * Npad * 4, ctx->stream));
+  for (int s = 0; s < n_signals; s++)
+    CU(cudaMemcpyAsync(dx.as<float>() + (size_t)s * Npad, x + (size_t)s * n_frames, (size_t)n_frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    RenderEnv env;
+    Scratch scratch(ctx);
+    HostKeep keep;
+    Timer timer(ctx);
+    env.ctx = ctx;
+    env.scratch = &scratch;
+    env.keep = &keep;
+    env.timer = &timer;
+    env.Npad = Npad;
+    env.NQ = Npad / 128;
+    env.QB = Npad / B;
+    std::vector<ConvItem> items(n_signals);
+    for (int s = 0; s < n_signals; s++)
+      items[s] = ConvItem{dx.as<float>() + (size_t)s * Npad, irh.d_H + (size_t)s * irh.P16 * B, irh.P, 0, Npad, nullptr, 1.0f};
+    rc = conv_batch(env, items);
+    gac_stats st{};
+    timer.finish(&st);
+    cudaStreamSynchronize(ctx->stream);
+    if (rc) return rc;
+    st.conv_units = env.conv_units;
+    st.algorithmic_bytes = env.alg_bytes;
+    st.mac_complex_macs = env.macs;
+    st.kernel_launches = env.launches;
+    st.voices = n_signals;
+    st.frames = n_frames;
+    ctx->stats = st;
+  }
+  for (int s = 0; s < n_signals; s++)
+    CU(cudaMemcpyAsync(y + (size_t)s * n_frames, dx.as<float>() + (size_t)s * Npad, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAC_OK;
+}
+
+extern "C" int gac_automation_eval(gac_context* ctx, const gac_param* param, int a_rate, int64_t n_frames, float* values) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!param || !values || n_frames <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  ParamH p;
+  int rc = copy_param(*param, &p, "param");
+  if (rc) return rc;
+  const int64_t NQ = (n_frames + 127) / 128;
+  if ((rc = ensure_block_times(ctx, NQ + 1))) return rc;
+  DevBuf dev, dout, dj;
+  if ((rc = dev_alloc(dev, sizeof(DevEvent) * std::max<size_t>(1, p.ev.size()))) || (rc = dev_alloc(dout, (size_t)NQ * 128 * 4)) ||
+      (rc = dev_alloc(dj, sizeof(ParamJob))))
+    return rc;
+  if (!p.ev.empty()) CU(cudaMemcpyAsync(dev.p, p.ev.data(), sizeof(gac_event) * p.ev.size(), cudaMemcpyHostToDevice, ctx->stream));
+  ParamJob j{p.value, (int)p.ev.size(), dev.as<DevEvent>(), dout.as<float>(), a_rate ? 1 : 0};
+  CU(cudaMemcpyAsync(dj.p, &j, sizeof(j), cudaMemcpyHostToDevice, ctx->stream));
+  launch_param_eval(dj.as<ParamJob>(), 1, ctx->d_bt, NQ, ctx->fs, ctx->stream);
+  CU(cudaGetLastError());
+  if (a_rate) {
+    CU(cudaMemcpyAsync(values, dout.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  } else {
+    // k-rate: one value per quantum, repeated 128 times by the reference (AudioParam.cs:164)
+    std::vector<float> q((size_t)NQ);
+    CU(cudaMemcpyAsync(q.data(), dout.p, (size_t)NQ * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int64_t n = 0; n < n_frames; n++) values[n] = q[(size_t)(n >> 7)];
+  }
+  return GAC_OK;
+}
+
+extern "C" int gac_resample_cubic(gac_context* ctx, const float* in, int64_t n_in, double rate, int64_t n_out, float* out, int64_t* produced,
+                                  int64_t* consumed) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!in || !out || n_in < 0 || n_out <= 0 || !(rate > 0)) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  // phase recurrence on the host (CubicResampler.cs:40-60), interpolation on the device
+  std::vector<int32_t> k;
+  std::vector<float> t;
+  int64_t inPos = 0, m = 0;
+  if (n_in >= 4) {
+    inPos = 4;
+    double Pos = 0.0;
+    while (m < n_out) {
+      int consume = (int)Pos;
+      if (inPos + consume > n_in) break;
+      inPos += consume;
+      Pos -= consume;
+      k.push_back((int32_t)(inPos - 4));
+      t.push_back((float)Pos);
+      Pos += rate;
+      m++;
+    }
+  } else {
+    inPos = n_in;
+  }
+  if (produced) *produced = m;
+  if (consumed) *consumed = inPos;
+  for (int64_t i = 0; i < n_out; i++) out[i] = 0.f;
+  if (m == 0) return GAC_OK;
+  const int64_t n_pad = ((m + 3) / 4) * 4;
+  DevBuf din, dk, dt, dout, dj;
+  int rc;
+  if ((rc = dev_alloc(din, (size_t)(n_in + 8) * 4)) || (rc = dev_alloc(dk, (size_t)m * 4)) || (rc = dev_alloc(dt, (size_t)m * 4)) ||
+      (rc = dev_alloc(dout, (size_t)n_pad * 2 * 4)) || (rc = dev_alloc(dj, sizeof(ResampleJob))))
+    return rc;
+  CU(cudaMemcpyAsync(din.p, in, (size_t)n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dk.p, k.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dt.p, t.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ResampleJob j{};
+  j.src[0] = j.src[1] = din.as<float>();
+  j.dst[0] = dout.as<float>();
+  j.dst[1] = dout.as<float>() + n_pad;
+  j.k = dk.as<int32_t>();
+  j.t = dt.as<float>();
+  j.out0 = 0;
+  j.n_emit = m;
+  j.n_zero_from = m;
+  CU(cudaMemcpyAsync(dj.p, &j, sizeof(j), cudaMemcpyHostToDevice, ctx->stream));
+  launch_resample(dj.as<ResampleJob>(), 1, m, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAC_OK;
+}

@@ -1,0 +1,132 @@
+// gac_kernels.h — launcher declarations for the sm_100a kernels (internal; not part of the C ABI).
+//
+// Data layout in HBM:
+//   time-domain signals   float  sig[S][2][Npad]           planar, Npad multiple of the partition B
+//   spectra ("packed")    float2 X[chan][rows][B]          row = one partition/block; bin 0 holds
+//                                                           (DC.re, Nyquist.re), bins 1..B-1 (re, im).
+//                                                           The reference stores C = B+1 planar re/im
+//                                                           floats (PartitionedConvolver.cs:41,46-51);
+//                                                           DC and Nyquist are purely real
+//                                                           (FftFlat/RealFourierTransform.cs:76-78).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gac {
+
+// ------------------------------------------------------------------ FFT (fft.cu)
+// Twiddle table e^{-2*pi*i*k/N}, k in [0, N/2), N = 2B, as float2, computed on the host in double.
+struct FftFwdJob {
+  const float* in;       // B-sample blocks, contiguous: block b at in + b*B
+  float2* out;           // packed spectra: block b at out + b*B
+  const float* scale;    // optional device scalar multiplied into every sample (IR normalisation), or nullptr
+  const float* gain;     // optional per-sample gain table (fused GainNode), or nullptr
+  float gain_const;      // constant gain used when gain == nullptr (1.0f = none)
+  int64_t n_valid;       // samples of `in` that exist; the rest of the last block reads as zero
+  int64_t n_blocks;
+  int64_t gate_lo, gate_hi;  // samples outside [gate_lo, gate_hi) read as zero (silent-flagged quanta)
+};
+void launch_rfft_fwd(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
+
+struct FftInvJob {
+  const float2* in;  // packed spectra, block b at in + b*B
+  float* out;        // B-sample blocks, block b at out + b*B ; out[b] = r_b[0:B] + r_{b-1}[B:2B]
+  int64_t n_blocks;
+};
+void launch_irfft_ola(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
+
+// ------------------------------------------------------------------ spectral MAC (mac.cu)
+// One job = one channel-convolver bin-group of 128 bins:  Y[b][k] = sum_p X[b-p][k] * H[p][k].
+struct MacJob {
+  const float2* X;  // points at row 0 (block 0), bin-group offset applied; rows [-pad_rows, rows_alloc) readable
+  const float2* H;  // row p at H + p*stride; rows [0, P16) readable (zero beyond P)
+  float2* Y;        // row b at Y + b*stride
+  int P;            // partitions
+  int has_dc;       // bin-group 0 carries the packed (DC, Nyquist) pair in bin 0
+};
+struct MacTile {
+  int job;
+  int b0;  // first output block of the tile
+};
+constexpr int kMacT = 16;         // output blocks per thread (register tile)
+constexpr int kMacChunk = 16;     // partitions per pipeline stage
+int mac_tile_blocks(int variant);  // output blocks per CTA for the tiled kernel (32 or 64)
+void launch_mac_tiled(const MacJob* d_jobs, const MacTile* d_tiles, int n_tiles, int stride, int tile_blocks, cudaStream_t s);
+void launch_mac_stream(const MacJob* d_jobs, int n_jobs, int64_t n_blocks, int stride, cudaStream_t s);
+
+// ------------------------------------------------------------------ node kernels (nodes.cu)
+struct DevEvent {  // bit-compatible with gac_event / AudioParam.cs:360-367
+  int32_t type;
+  float value;
+  float target;
+  double time;
+  double time_constant;
+};
+struct ParamJob {
+  float value;
+  int n_events;
+  const DevEvent* events;
+  float* out;       // [n_frames] for a-rate, [n_blocks] for k-rate
+  int a_rate;
+};
+void launch_param_eval(const ParamJob* d_jobs, int n_jobs, const double* d_block_time, int64_t n_quanta, int sample_rate, cudaStream_t s);
+
+struct SourceJob {
+  const float* src[2];  // channel pointers (both the same for a mono buffer: the 1->2 up-mix copy of AudioNodeInput.cs:201-213)
+  float* dst[2];        // sig rows
+  int64_t pos0;         // buffer frame that lands on out frame out0
+  int64_t out0;         // first emitted output frame (multiple of 128)
+  int64_t n_emit;       // emitted frames (multiple of 128)
+};
+void launch_source_copy(const SourceJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
+
+struct ResampleJob {
+  const float* src[2];
+  float* dst[2];
+  const int32_t* k;   // per output frame: index of S0 in the source (S0..S3 = src[k..k+3])
+  const float* t;     // per output frame: fractional position
+  int64_t out0;       // first output frame
+  int64_t n_emit;     // frames for which (k,t) exist and the block is kept
+  int64_t n_zero_from;  // frames >= this (relative to out0) inside kept blocks are zero (stall point)
+};
+void launch_resample(const ResampleJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
+
+struct GainJob {
+  float* sig[2];
+  const float* gain;  // a-rate table or nullptr
+  float gain_const;
+  int64_t lo, hi;     // active frame range; outside -> zeros (silent-flagged blocks, GainNode.cs:41-46)
+};
+void launch_gain(const GainJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
+
+struct BiquadJob {
+  float* sig[2];
+  const float* freq;   // a-rate table or nullptr
+  const float* q;      // a-rate table or nullptr
+  const float* gain;   // k-rate table [n_quanta] or nullptr
+  float freq_const, q_const, gain_const;
+  int type;
+  int64_t lo, hi;      // active frame range (multiples of 128)
+  float* coef;         // scratch [n_frames][5] (b0,b1,b2,a1,a2) per frame
+};
+// d_sel: scratch uint8 [n_jobs][2][n_frames] (recompute flags); d_last: scratch int32 [n_jobs][2][n_quanta]
+void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, uint8_t* d_sel,
+                   int32_t* d_last, cudaStream_t s);
+
+struct MixJob {       // dst[c][n] = (((0 + src0) + src1) + ...) over active ranges, AudioNodeInput.cs:118-137
+  float* dst[2];
+  int first_input;    // index into the MixInput array
+  int n_inputs;
+};
+struct MixInput {
+  const float* src[2];
+  int64_t lo, hi;     // frames where the input is non-silent
+};
+void launch_mix(const MixJob* d_jobs, int n_jobs, const MixInput* d_inputs, int64_t n_frames, cudaStream_t s);
+
+// IR preparation (PartitionedConvolver.cs:93-102): scale[ch] from the channel's RMS
+void launch_ir_scale(const float* const* d_channels, int n_channels, int64_t n_frames, float calibration, float* d_scale, cudaStream_t s);
+
+void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
+
+}  // namespace gac

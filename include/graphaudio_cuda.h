@@ -1,0 +1,250 @@
+/* graphaudio_cuda.h — C ABI of libgraphaudio_cuda.so
+ *
+ * B200-native (sm_100a) batched implementation of GraphAudio's offline graph-render hot path:
+ * AudioBufferSourceNode (+CubicResampler) -> BiQuadFilterNode* -> GainNode -> ConvolverNode
+ * (uniformly partitioned FFT convolution) -> fan-in bus -> destination, for many voices at once.
+ *
+ * This is the boundary a `GraphAudio.Cuda` C# package P/Invokes ([LibraryImport("graphaudio_cuda")],
+ * cdecl — the idiom of GraphAudio.IO/Libsndfile.cs:36-68 and GraphAudio.Realtime/Miniaudio.cs:305-349);
+ * see INTEGRATION.md for the binding.  Plain pointers and sizes only.
+ *
+ * Every function returns GAC_OK (0) or a negative gac_status; the message is available from
+ * gac_last_error() (thread-local, owned by the library — cf. sf_strerror, Libsndfile.cs:48-56).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * GAC_ERR_NO_DEVICE.
+ *
+ * All reference citations are relative to /root/reference/GraphAudio.Core/.
+ */
+#ifndef GRAPHAUDIO_CUDA_H_
+#define GRAPHAUDIO_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAC_ABI_VERSION 1
+
+/* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */
+typedef enum gac_status {
+  GAC_OK = 0,
+  GAC_ERR_INVALID_ARGUMENT = -1,  /* ArgumentException            (OfflineAudioContext.cs:32-51)            */
+  GAC_ERR_OUT_OF_RANGE = -2,      /* ArgumentOutOfRangeException  (OfflineAudioContext.cs:35-39)            */
+  GAC_ERR_INVALID_OPERATION = -3, /* InvalidOperationException    (Nodes/ConvolverNode.cs:45-49)            */
+  GAC_ERR_DISPOSED = -4,          /* ObjectDisposedException      (AudioContextBase.cs:54-55)               */
+  GAC_ERR_NO_DEVICE = -5,         /* no CUDA device / wrong architecture: there is no CPU fallback          */
+  GAC_ERR_CUDA = -6,              /* a CUDA runtime call failed (message carries cudaGetErrorString)        */
+  GAC_ERR_OUT_OF_MEMORY = -7,
+  GAC_ERR_NCCL = -8,
+  GAC_ERR_UNSUPPORTED = -9        /* graph shape outside the accelerated path (SURVEY.md §8f "next")        */
+} gac_status;
+
+typedef struct gac_context gac_context; /* ≙ OfflineAudioContext                                  */
+typedef struct gac_buffer gac_buffer;   /* ≙ PlayableAudioBuffer (device-resident copy)            */
+typedef struct gac_ir gac_ir;           /* ≙ the PartitionedConvolver[] a ConvolverNode owns       */
+typedef struct gac_graph gac_graph;     /* a flattened, immutable render graph                     */
+
+/* ---- library ---- */
+int gac_version(void);
+const char* gac_last_error(void);
+int gac_device_count(int* count);
+
+/* ---- context ≙ OfflineAudioContext(int sampleRate = 48000)  (OfflineAudioContext.cs:18) ---- */
+typedef struct gac_context_desc {
+  int sample_rate; /* > 0                                                                            */
+  int quantum;     /* AudioBuffer.FramesPerBlock; must be 128 (AudioBuffer.cs:10)                    */
+  int partition;   /* PartitionedConvolver blockSize (PartitionedConvolver.cs:37): 128 (what
+                      ConvolverNode uses, ConvolverNode.cs:55) or 256/512 (offline-only option;
+                      same linear convolution, different rounding points).  0 = 128.                 */
+  int device_id;   /* CUDA ordinal; -1 = current device                                              */
+  int mac_variant; /* 0 = default (register-tiled), 1 = streaming one-pass-per-quantum (reference
+                      op order, unfused; the T=1 roofline contract of SURVEY.md §8d)                 */
+  int reserved[3];
+} gac_context_desc;
+
+int gac_context_create(const gac_context_desc* desc, gac_context** out);
+int gac_context_destroy(gac_context* ctx);
+
+/* ---- buffers ≙ PlayableAudioBuffer.FromChannelArrays (PlayableAudioBuffer.cs:122-143) ----
+ * `channels` are caller-owned host arrays, copied (to HBM) during the call, as CopyToChannel
+ * copies (PlayableAudioBuffer.cs:84-93).  1..32 channels, equal lengths. */
+int gac_buffer_create(gac_context* ctx, const float* const* channels, int n_channels, int64_t n_frames,
+                      int sample_rate, gac_buffer** out);
+int gac_buffer_destroy(gac_buffer* buf);
+
+/* ---- ConvolverNode.Buffer = ir  (Nodes/ConvolverNode.cs:25-79 -> PartitionedConvolver ctor
+ * PartitionedConvolver.cs:37-102): per-channel RMS normalisation, partition, zero-pad, rFFT.
+ * Fails with GAC_ERR_INVALID_OPERATION if the buffer's rate differs from the context's (:48-49).
+ * Supported IR channel counts on the accelerated path: 1, 2 (discrete) and 4 with true_stereo. */
+int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int normalize, int true_stereo, gac_ir** out);
+int gac_ir_destroy(gac_ir* ir);
+
+/* ---- automation ≙ AudioParam (AudioParam.cs) ----
+ * gac_event is bit-compatible with the reference's private AutomationEvent struct
+ * (AudioParam.cs:360-367: enum(int) Type; float Value; float Target; double Time; double TimeConstant). */
+typedef enum gac_event_type {
+  GAC_EVENT_SET_VALUE = 0,        /* SetValueAtTime                 AudioParam.cs:252 */
+  GAC_EVENT_LINEAR_RAMP = 1,      /* LinearRampToValueAtTime        AudioParam.cs:266 */
+  GAC_EVENT_EXPONENTIAL_RAMP = 2, /* ExponentialRampToValueAtTime   AudioParam.cs:280 */
+  GAC_EVENT_SET_TARGET = 3        /* SetTargetAtTime                AudioParam.cs:297 */
+} gac_event_type;
+
+typedef struct gac_event {
+  int32_t type;
+  float value;
+  float target;
+  double time;
+  double time_constant;
+} gac_event;
+
+/* A parameter as the render thread sees it: the static `_value` plus the time-sorted event list
+ * exactly as AddEvent leaves it (stable upper-bound insert, AudioParam.cs:333-352).  Values must
+ * already be clamped to the param's range (the reference clamps at schedule time, :254,268,282,299). */
+typedef struct gac_param {
+  float value;
+  int32_t n_events;
+  const gac_event* events;
+} gac_param;
+
+/* ---- per-voice processing chain ---- */
+typedef enum gac_op_kind {
+  GAC_OP_BIQUAD = 1,   /* BiQuadFilterNode  Nodes/BiQuadFilterNode.cs:87-258 */
+  GAC_OP_GAIN = 2,     /* GainNode          Nodes/GainNode.cs:29-61          */
+  GAC_OP_CONVOLVER = 3 /* ConvolverNode     Nodes/ConvolverNode.cs:102-155   */
+} gac_op_kind;
+
+typedef enum gac_filter_type { /* FilterType, Nodes/BiQuadFilterNode.cs:288-298 */
+  GAC_FILTER_LOWPASS = 0,
+  GAC_FILTER_HIGHPASS = 1,
+  GAC_FILTER_BANDPASS = 2,
+  GAC_FILTER_NOTCH = 3,
+  GAC_FILTER_ALLPASS = 4,
+  GAC_FILTER_PEAKING = 5,
+  GAC_FILTER_LOWSHELF = 6,
+  GAC_FILTER_HIGHSHELF = 7
+} gac_filter_type;
+
+typedef struct gac_op_desc {
+  int32_t kind;        /* gac_op_kind                                                         */
+  int32_t filter_type; /* BIQUAD: gac_filter_type                                             */
+  gac_param p0;        /* BIQUAD: Frequency (a-rate)   GAIN: Gain (a-rate)                    */
+  gac_param p1;        /* BIQUAD: Q (a-rate)                                                   */
+  gac_param p2;        /* BIQUAD: Gain in dB (k-rate)                                          */
+  const gac_ir* ir;    /* CONVOLVER: prepared impulse response; NULL ≙ ConvolverNode without a
+                          Buffer, which outputs silence (ConvolverNode.cs:107-119)             */
+} gac_op_desc;
+
+/* One voice = AudioBufferSourceNode -> ops[0] -> ops[1] -> ... -> bus (or destination).
+ * Source semantics: Nodes/AudioBufferSourceNode.cs:79-143 (Start/Stop are block-granular),
+ * :186-235 (rate == 1 copy path), :236-358 (CubicResampler path), :360-372 (final block dropped). */
+typedef struct gac_voice_desc {
+  const gac_buffer* source; /* 1 or 2 channels                                                 */
+  double start_when;        /* Start(when, offset, duration); duration = +inf for "whole buffer" */
+  double start_offset;
+  double start_duration;
+  double stop_when;         /* Stop(when); NaN = never called                                   */
+  float playback_rate;      /* PlaybackRate.Value (k-rate, no automation on this path)          */
+  int32_t n_ops;
+  const gac_op_desc* ops;
+  int32_t bus;              /* index into buses, or -1: connected straight to the destination   */
+} gac_voice_desc;
+
+/* A bus = fan-in AudioNodeInput (AudioNodeInput.cs:100-138) followed by a chain of ops
+ * (typically one GainNode), connected to the destination.  Voices are summed in ascending voice
+ * index = connection order, float32, skipping silent-flagged blocks (:121-132). */
+typedef struct gac_bus_desc {
+  int32_t n_ops;
+  const gac_op_desc* ops;
+} gac_bus_desc;
+
+typedef struct gac_graph_desc {
+  int32_t n_voices;
+  const gac_voice_desc* voices;
+  int32_t n_buses;
+  const gac_bus_desc* buses;
+  /* Connection order at the destination's input: entries >= 0 are bus indices, entries < 0 are
+   * ~voice_index for voices with bus == -1.  NULL = buses in index order, then direct voices. */
+  int32_t n_dest_inputs;
+  const int32_t* dest_inputs;
+} gac_graph_desc;
+
+int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, gac_graph** out);
+int gac_graph_destroy(gac_graph* graph);
+
+/* ---- render ≙ OfflineAudioContext.Render(float[][] output, int frameCount, int startIndex = 0)
+ * (OfflineAudioContext.cs:30-102).  Renders frames [first_frame, first_frame + n_frames) of the
+ * graph's timeline (first_frame lets a caller reproduce successive Render calls, :55-100) into
+ * caller-allocated host arrays out_channels[c][start_index ...]; n_out_channels is 1 or 2 (the
+ * destination is stereo, Nodes/AudioDestinationNode.cs:17).  Synchronous: returns after the
+ * device->host copy. */
+int gac_render(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames,
+               float* const* out_channels, int n_out_channels, int64_t start_index);
+
+/* As gac_render, but the result stays in HBM: d_out is a device pointer to [n_out_channels][n_frames]
+ * float32 (row stride n_frames).  Asynchronous on the context's stream unless sync != 0. */
+int gac_render_device(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames,
+                      float* d_out, int n_out_channels, int sync);
+
+/* Batch of independent renders (BASELINE config 4: one OfflineAudioContext per render): graph g is
+ * rendered into out_channels[g * n_out_channels + c].  All graphs share n_frames. */
+int gac_render_batch(gac_context* ctx, const gac_graph* const* graphs, int n_graphs, int64_t n_frames,
+                     float* const* out_channels, int n_out_channels);
+
+/* ---- multi-GPU bus mix (one process per GPU) ----
+ * The voices of one logical graph are sharded over ranks; each rank renders its shard with
+ * gac_render_device(…) up to the bus fan-in, then a single ncclReduce(sum, float32) over
+ * NVLink/NVSwitch delivers the bus to the root, which applies the bus ops and returns the result. */
+#define GAC_NCCL_UNIQUE_ID_BYTES 128
+int gac_comm_unique_id(void* id128);
+int gac_comm_init(gac_context* ctx, const void* id128, int rank, int n_ranks);
+int gac_comm_destroy(gac_context* ctx);
+/* Collective render: every rank passes its shard graph (whose voices feed bus 0 / the destination
+ * directly; bus ops must be identical on all ranks and are applied on the root AFTER the reduce).
+ * Only the root (rank `root`) writes out_channels. */
+int gac_render_sharded(gac_context* ctx, const gac_graph* shard, int64_t n_frames, int root,
+                       float* const* out_channels, int n_out_channels);
+
+/* ---- statistics of the last render on this context ---- */
+typedef struct gac_stats {
+  double ms_total;      /* device time of the whole render (CUDA events on the context stream)      */
+  double ms_source;     /* K1 source copy / cubic resample                                          */
+  double ms_automation; /* K2 a-rate parameter evaluation                                           */
+  double ms_biquad;     /* K3 coefficient tables + recursive lanes                                  */
+  double ms_gain;       /* K4                                                                       */
+  double ms_fft_fwd;    /* K5                                                                       */
+  double ms_mac;        /* K6 spectral multiply-accumulate                                          */
+  double ms_fft_inv;    /* K7 inverse FFT + overlap-add                                             */
+  double ms_mix;        /* fan-in sums + bus ops                                                    */
+  double ms_d2h;
+  int64_t conv_units;          /* channel-convolver blocks processed (SURVEY.md §8d "unit")         */
+  double algorithmic_bytes;    /* Σ units · (16·P·C + 8·C + 8·B), the T=1 contract                  */
+  double mac_complex_macs;     /* complex MACs actually issued by K6 (after causal skipping)        */
+  int64_t kernel_launches;     /* kernels launched by the last render                               */
+  int64_t voices;
+  int64_t frames;
+} gac_stats;
+int gac_get_stats(gac_context* ctx, gac_stats* out);
+
+/* ---- kernel-level entry points (used by the parity tests; host pointers in, host pointers out) ----
+ * x: [n_signals][n_blocks*B] float32 time-domain blocks -> spectra [n_signals][n_blocks][B] complex64,
+ * packed: bin 0 = (DC.re, Nyquist.re), bins 1..B-1 = (re, im).          ≙ PartitionedConvolver.cs:106-124 */
+int gac_rfft_fwd_batch(gac_context* ctx, const float* x, int n_signals, int64_t n_blocks, float* spectra);
+/* Y[s][b][k] = Σ_p X[s][b-p][k]·H[s][p][k] (X[<0] = 0), packed layout as above.   ≙ :154-223      */
+int gac_spectral_mac(gac_context* ctx, const float* X, const float* H, int n_signals, int64_t n_blocks,
+                     int n_partitions, int variant, float* Y);
+/* inverse rFFT of every block + overlap-add -> y [n_signals][n_blocks*B]           ≙ :134-150      */
+int gac_irfft_ola_batch(gac_context* ctx, const float* Y, int n_signals, int64_t n_blocks, float* y);
+/* whole PartitionedConvolver for n_signals independent (x, ir) pairs               ≙ :37-152       */
+int gac_convolve_batch(gac_context* ctx, const float* x, int n_signals, int64_t n_frames, const float* ir,
+                       int64_t ir_frames, int normalize, float* y);
+/* a-rate evaluation of one parameter for frames [0, n_frames)                      ≙ AudioParam.cs:114-141 */
+int gac_automation_eval(gac_context* ctx, const gac_param* param, int a_rate, int64_t n_frames, float* values);
+/* CubicResampler over one input, one Process call                                  ≙ CubicResampler.cs:26-63 */
+int gac_resample_cubic(gac_context* ctx, const float* in, int64_t n_in, double rate, int64_t n_out, float* out,
+                       int64_t* produced, int64_t* consumed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHAUDIO_CUDA_H_ */

@@ -1,0 +1,209 @@
+"""End-to-end parity (GPU): OfflineAudioContext.Render through the C ABI vs the CPU oracle on identical synthetic
+inputs.  Gate: max |y_gpu - y_oracle| <= 1e-5 of full scale (float32) — BASELINE.json north_star.
+
+The graphs are the BASELINE configs at sizes the oracle renders in seconds; the same builder code drives both sides.
+"""
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _apis():
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    return G, O
+
+
+def _voices(nv, src_frames, ir_frames, src_channels=2):
+    out = []
+    for v in range(nv):
+        src, ir = synth.make_voice_inputs(v, src_frames, ir_frames, src_channels)
+        out.append((src, ir, synth.voice_gains(v)))
+    return out
+
+
+def _compare(gctx, octx, n, tol=TOL):
+    yg = gctx.Render(n)
+    yo = octx.Render(n)
+    peak = np.abs(yo).max()
+    err = np.abs(yg - yo).max()
+    assert peak > 1e-3, "degenerate test signal"
+    assert err <= tol, (err, peak)
+    return yg, yo
+
+
+def test_c1_single_convolver():
+    """C1 shape: stereo source -> ConvolverNode(stereo IR) -> destination (48 kHz, 0.25 s IR, 1 s input + tail)."""
+    G, O = _apis()
+    fs = 48000
+    src, ir = synth.make_voice_inputs(0, fs, fs // 4)
+    g = synth.build_c1(G, fs, src, ir)
+    o = synth.build_c1(O, fs, src, ir)
+    yg, yo = _compare(g, o, fs + fs // 2)
+    # source end rule (AudioBufferSourceNode.cs:224,360-362): exactly 128*floor((L-1)/128) input frames are emitted;
+    # after the tail has rung out the output is exactly silent
+    g.Dispose()
+
+
+def test_c2_gain_automation_and_bus_mix():
+    """C2 shape: 6 voices x (gain automation -> per-voice stereo IR) -> bus GainNode(1/8) -> destination."""
+    G, O = _apis()
+    fs = 48000
+    voices = _voices(6, fs, 12000)
+    g = synth.build_c2(G, fs, voices, 1.0 / 8, t_scale=0.1)
+    o = synth.build_c2(O, fs, voices, 1.0 / 8, t_scale=0.1)
+    _compare(g, o, fs + 16000)
+    g.Dispose()
+
+
+@pytest.mark.parametrize("f0,f1,q", [(2000.0, 12000.0, 0.707), (200.0, 2000.0, 0.707), (500.0, 8000.0, 8.0)])
+def test_c3_biquad_sweep(f0, f1, q):
+    """C3 shape: biquad lowpass with an a-rate exponential cutoff sweep -> gain -> convolver -> bus."""
+    G, O = _apis()
+    fs = 48000
+    voices = _voices(4, fs // 2, 6000)
+    g = synth.build_c3(G, fs, voices, 1.0 / 4, f0=f0, f1=f1, t_scale=0.05, q=q)
+    o = synth.build_c3(O, fs, voices, 1.0 / 4, f0=f0, f1=f1, t_scale=0.05, q=q)
+    _compare(g, o, fs // 2 + 8000)
+    g.Dispose()
+
+
+def test_c4_biquad_chain_independent_render():
+    G, O = _apis()
+    fs = 48000
+    src, ir = synth.make_voice_inputs(5, fs // 2, 6000)
+    g = synth.build_c4(G, fs, src, ir, t_scale=0.1)
+    o = synth.build_c4(O, fs, src, ir, t_scale=0.1)
+    _compare(g, o, fs // 2 + 8000)
+    g.Dispose()
+
+
+@pytest.mark.parametrize("partition", [128, 512])
+def test_c5_resampled_source(partition):
+    """C5 shape: 44.1 kHz buffer in a 96 kHz context (CubicResampler, rate 0.459375) -> gain -> convolver -> bus.
+    partition=512 is the offline-only option: same linear convolution, different rounding points, same 1e-5 gate
+    against the reference's 128-frame ConvolverNode."""
+    G, O = _apis()
+    fs, src_rate = 96000, 44100
+    voices = []
+    for v in range(3):
+        src = [synth.splitmix_uniform(4 * v + c, 22050) for c in range(2)]
+        ir = [synth.decay_ir(4 * v + 2 + c, 20000) for c in range(2)]
+        voices.append((src, ir, synth.voice_gains(v)))
+    g = synth.build_c5(G, fs, src_rate, voices, 0.5, t_scale=0.05, partition=partition)
+    o = synth.build_c5(O, fs, src_rate, voices, 0.5, t_scale=0.05)
+    _compare(g, o, 48000 + 24000)
+    g.Dispose()
+
+
+def test_chunked_render_equals_single_render():
+    """KAT: Render(n1) + Render(n2) == Render(n1 + n2) for non-multiples of 128 (OfflineAudioContext.cs:55-100)."""
+    G, O = _apis()
+    fs = 48000
+    src, ir = synth.make_voice_inputs(1, 20000, 3000)
+    a = synth.build_c1(G, fs, src, ir)
+    b = synth.build_c1(G, fs, src, ir)
+    whole = a.Render(10000)
+    p1 = b.Render(3333)
+    p2 = b.Render(6667)
+    assert np.array_equal(np.concatenate([p1, p2], axis=1), whole)
+    a.Dispose()
+    b.Dispose()
+
+
+def test_mono_source_upmix_and_source_end_rule():
+    """mono source: 1 -> 2 up-mix copies the channel (AudioNodeInput.cs:201-213); emitted length 128*floor((L-1)/128)."""
+    G, O = _apis()
+    fs = 48000
+    L = 128 * 10  # a multiple of 128: the last FULL block is dropped too
+    x = synth.splitmix_uniform(9, L)
+    outs = []
+    for api in (G, O):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromMonoArray(x, fs)
+        g = api.GainNode(ctx)
+        g.Gain.Value = 0.5
+        s.Connect(g).Connect(ctx.Destination)
+        s.Start()
+        outs.append(ctx.Render(L + 256))
+    yg, yo = outs
+    assert np.array_equal(yg, yo)  # copy + float32 multiply: bit-exact
+    emitted = 128 * ((L - 1) // 128)
+    assert np.array_equal(yg[0, :emitted], (x[:emitted] * np.float32(0.5)))
+    assert np.array_equal(yg[0], yg[1])
+    assert not yg[:, emitted:].any()
+
+
+def test_start_stop_block_granular():
+    """Start(when)/Stop(when) are block-granular: playback begins at frame 0 of the first block whose end is past `when`."""
+    G, O = _apis()
+    fs = 48000
+    x = synth.splitmix_uniform(11, 30000)
+    outs = []
+    for api in (G, O):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromMonoArray(x, fs)
+        s.Connect(ctx.Destination)
+        s.Start(0.0301, 0.01, 0.2)
+        outs.append(ctx.Render(20000))
+    assert np.array_equal(outs[0], outs[1])
+    assert outs[0].any()
+
+
+def test_fan_in_order_and_direct_voices():
+    """two voices straight into the destination + one bus: float32 ((0 + a) + b) in connection order (AudioNodeInput.cs:118-137)."""
+    G, O = _apis()
+    fs = 48000
+    outs = []
+    for api in (G, O):
+        ctx = api.OfflineAudioContext(fs)
+        bus = api.GainNode(ctx)
+        bus.Gain.Value = 0.7
+        for v in range(3):
+            s = api.AudioBufferSourceNode(ctx)
+            s.Buffer = api.PlayableAudioBuffer.FromStereoArrays(synth.splitmix_uniform(50 + 2 * v, 9000), synth.splitmix_uniform(51 + 2 * v, 9000), fs)
+            g = api.GainNode(ctx)
+            g.Gain.Value = 0.3 + 0.1 * v
+            s.Connect(g).Connect(bus)
+            s.Start(0.01 * v)
+        d = api.AudioBufferSourceNode(ctx)
+        d.Buffer = api.PlayableAudioBuffer.FromMonoArray(synth.splitmix_uniform(60, 5000), fs)
+        d.Connect(ctx.Destination)
+        bus.Connect(ctx.Destination)
+        d.Start()
+        outs.append(ctx.Render(10000))
+    assert np.array_equal(outs[0], outs[1])  # adds and multiplies only: bit-exact, including the summation order
+
+
+def test_streaming_mac_variant_matches_oracle_tighter():
+    """mac_variant=1 keeps the reference's unfused op order; only the float32 FFTs differ from the oracle."""
+    G, O = _apis()
+    fs = 48000
+    src, ir = synth.make_voice_inputs(2, 24000, 6000)
+    g = synth.build_c1(G, fs, src, ir, mac_variant=1)
+    o = synth.build_c1(O, fs, src, ir)
+    _compare(g, o, 30000, tol=2e-6)
+    g.Dispose()
+
+
+def test_error_mapping():
+    G, O = _apis()
+    ctx = G.OfflineAudioContext(48000)
+    with pytest.raises(G.ArgumentOutOfRangeException):
+        ctx.Render(0)
+    with pytest.raises(G.ArgumentOutOfRangeException):
+        ctx.Render(np.zeros((2, 10), np.float32), 10, -1)
+    with pytest.raises(G.ArgumentException):
+        ctx.Render(np.zeros((2, 10), np.float32), 11, 0)
+    conv = G.ConvolverNode(ctx)
+    with pytest.raises(G.InvalidOperationException):  # IR rate mismatch, ConvolverNode.cs:48-49
+        conv.Buffer = G.PlayableAudioBuffer.FromMonoArray(np.ones(100, np.float32), 44100)
+    ctx.Dispose()
+    with pytest.raises(G.ObjectDisposedException):
+        ctx.Render(128)

@@ -331,7 +331,7 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
   b->n = n_frames;
   b->rate = sample_rate;
   b->stride = ((n_frames + 8 + 63) / 64) * 64;  // a little slack so 4-tap reads never leave the allocation
-  CU(cudaMalloc(&b->d, sizeof(float) * b->stride * n_channels));
+  CU(cudaMallocAsync(&b->d, sizeof(float) * b->stride * n_channels, ctx->stream));
   CU(cudaMemsetAsync(b->d, 0, sizeof(float) * b->stride * n_channels, ctx->stream));
   for (int c = 0; c < n_channels; c++)
     CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, ctx->stream));
@@ -342,8 +342,8 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
 extern "C" int gac_buffer_destroy(gac_buffer* buf) {
   if (!buf) return fail(GAC_ERR_INVALID_ARGUMENT, "buffer is null");
   cudaSetDevice(buf->ctx->device);
-  cudaStreamSynchronize(buf->ctx->stream);
-  cudaFree(buf->d);
+  // stream-ordered free: safe behind any render still queued on the context stream
+  cudaFreeAsync(buf->d, buf->ctx->stream);
   delete buf;
   return GAC_OK;
 }
@@ -358,13 +358,13 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   const int B = ctx->B;
   ir->P = (int)((frames + B - 1) / B);  // ceil(L / blockSize)  PartitionedConvolver.cs:44
   ir->P16 = std::max(16, ((ir->P + 15) / 16) * 16);
-  CU(cudaMalloc(&ir->d_H, sizeof(float2) * (size_t)nch * ir->P16 * B));
+  CU(cudaMallocAsync(&ir->d_H, sizeof(float2) * (size_t)nch * ir->P16 * B, ctx->stream));
   CU(cudaMemsetAsync(ir->d_H, 0, sizeof(float2) * (size_t)nch * ir->P16 * B, ctx->stream));
-  CU(cudaMalloc(&ir->d_scale, sizeof(float) * nch));
+  CU(cudaMallocAsync(&ir->d_scale, sizeof(float) * nch, ctx->stream));
   std::vector<const float*> chp(nch);
   for (int c = 0; c < nch; c++) chp[c] = d_ir + c * stride;
   const float** d_chp = nullptr;
-  CU(cudaMalloc(&d_chp, sizeof(float*) * nch));
+  CU(cudaMallocAsync(&d_chp, sizeof(float*) * nch, ctx->stream));
   int rc = upload_now(ctx, d_chp, chp.data(), sizeof(float*) * nch);
   if (rc) return rc;
   if (normalize && frames > 0) {
@@ -375,7 +375,7 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
     std::vector<float> ones(nch, 1.0f);
     rc = upload_now(ctx, ir->d_scale, ones.data(), sizeof(float) * nch);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));
+    // (pageable source: the copy is staged before cudaMemcpyAsync returns)
   }
   std::vector<FftFwdJob> jobs(nch);
   for (int c = 0; c < nch; c++) {
@@ -391,14 +391,14 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
     j.gate_hi = std::numeric_limits<int64_t>::max();
   }
   FftFwdJob* d_jobs = nullptr;
-  CU(cudaMalloc(&d_jobs, sizeof(FftFwdJob) * nch));
+  CU(cudaMallocAsync(&d_jobs, sizeof(FftFwdJob) * nch, ctx->stream));
   rc = upload_now(ctx, d_jobs, jobs.data(), sizeof(FftFwdJob) * nch);
   if (rc) return rc;
   launch_rfft_fwd(d_jobs, nch, ir->P, B, ctx->d_tw, ctx->stream);
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_jobs);
-  cudaFree(d_chp);
+  // no host synchronisation: every later use of the spectra is ordered on the same stream
+  cudaFreeAsync(d_jobs, ctx->stream);
+  cudaFreeAsync(d_chp, ctx->stream);
   return GAC_OK;
 }
 
@@ -423,8 +423,8 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
   ir->frames = buf->n;
   int rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get());
   if (rc) {
-    cudaFree(ir->d_H);
-    cudaFree(ir->d_scale);
+    if (ir->d_H) cudaFreeAsync(ir->d_H, ctx->stream);
+    if (ir->d_scale) cudaFreeAsync(ir->d_scale, ctx->stream);
     return rc;
   }
   *out = ir.release();
@@ -433,9 +433,9 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
 extern "C" int gac_ir_destroy(gac_ir* ir) {
   if (!ir) return fail(GAC_ERR_INVALID_ARGUMENT, "ir is null");
   cudaSetDevice(ir->ctx->device);
-  cudaStreamSynchronize(ir->ctx->stream);
-  cudaFree(ir->d_H);
-  cudaFree(ir->d_scale);
+  // stream-ordered free
+  cudaFreeAsync(ir->d_H, ir->ctx->stream);
+  cudaFreeAsync(ir->d_scale, ir->ctx->stream);
   delete ir;
   return GAC_OK;
 }
@@ -697,14 +697,14 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
     if (ctx->mac_variant == 1)
       launch_mac_stream(dmj, (int)mj.size(), QB, B, ctx->stream);
     else
-      launch_mac_tiled(dmj, dt, (int)tiles.size(), B, TB, ctx->stream);
+      { int pmax = 1; for (auto& m : mj) pmax = std::max(pmax, m.P); launch_mac_tiled(dmj, (int)mj.size(), dt, (int)tiles.size(), QB, pmax, B, TB, ctx->mac_variant, ctx->stream); }
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
     launch_irfft_ola(dij, (int)ij.size(), QB, B, ctx->d_tw, ctx->stream);
     env.timer->end(t);
     CU(cudaGetLastError());
-    env.launches += 3;
+    env.launches += (ctx->mac_variant == 1) ? 3 : 4;  // K5, K6 (+ k_mac_dc), K7
   }
   return GAC_OK;
 }

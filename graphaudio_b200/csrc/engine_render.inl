@@ -643,7 +643,7 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
   if (variant == 1)
     launch_mac_stream(dj.as<MacJob>(), (int)jobs.size(), n_blocks, B, ctx->stream);
   else
-    launch_mac_tiled(dj.as<MacJob>(), dt.as<MacTile>(), (int)tiles.size(), B, TB, ctx->stream);
+    launch_mac_tiled(dj.as<MacJob>(), (int)jobs.size(), dt.as<MacTile>(), (int)tiles.size(), n_blocks, n_partitions, B, TB, variant, ctx->stream);
   CU(cudaGetLastError());
   for (int s = 0; s < n_signals; s++)
     CU(cudaMemcpyAsync(Y + (size_t)s * n_blocks * B * 2, dY.as<float2>() + (size_t)s * QBpad * B, (size_t)n_blocks * B * 8, cudaMemcpyDeviceToHost,

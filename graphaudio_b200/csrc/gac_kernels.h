@@ -51,7 +51,10 @@ struct MacTile {
 constexpr int kMacT = 16;         // output blocks per thread (register tile)
 constexpr int kMacChunk = 16;     // partitions per pipeline stage
 int mac_tile_blocks(int variant);  // output blocks per CTA for the tiled kernel (32 or 64)
-void launch_mac_tiled(const MacJob* d_jobs, const MacTile* d_tiles, int n_tiles, int stride, int tile_blocks, cudaStream_t s);
+// flavour: 0 = packed FFMA2 accumulation (default), 2 = scalar FFMA
+// (two launches: the tiled kernel, then k_mac_dc for the packed DC/Nyquist bin; p_max = largest P among the jobs)
+void launch_mac_tiled(const MacJob* d_jobs, int n_jobs, const MacTile* d_tiles, int n_tiles, int64_t n_blocks, int p_max, int stride,
+                      int tile_blocks, int flavour, cudaStream_t s);
 void launch_mac_stream(const MacJob* d_jobs, int n_jobs, int64_t n_blocks, int stride, cudaStream_t s);
 
 // ------------------------------------------------------------------ node kernels (nodes.cu)

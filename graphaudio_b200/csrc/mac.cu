@@ -7,16 +7,20 @@
 // time axis b is a parallel axis:
 //     Y[b][k] = sum_{p=0}^{min(P-1, b)} X[b-p][k] * H[p][k]
 //
-// Two kernels:
+// Kernels:
 //  * k_mac_stream — one pass over X and H per output block, separate mul/sub/add in the reference's
 //    order (p ascending, :195-204).  Bit-identical to the CPU oracle for identical spectra.  This is the
 //    "T = 1" algorithm whose bytes SURVEY.md §8(d) defines as the roofline contract.
 //  * k_mac_tiled — the production kernel.  Each thread owns one frequency bin and T = 16 consecutive
-//    output blocks; it keeps a sliding window of 16 input spectra values in registers, so every H[p][k]
+//    output blocks; it keeps a sliding window of 16 input-spectrum values in registers, so every H[p][k]
 //    and X[j][k] fetched from shared memory feeds 16 complex MACs.  A CTA covers 128 bins x TB output
 //    blocks (TB = 32 or 64); H chunks and X rows are staged into shared memory by TMA bulk copies
 //    (cp.async.bulk + mbarrier), double buffered.  Per-CTA traffic is 2 KB per 16*TB*128 complex MACs,
-//    i.e. the kernel is bound by the FP32 FMA pipe, not by HBM or L2.
+//    i.e. the kernel is bound by the FP32 FMA pipe, not by HBM or L2.  Two accumulation flavours:
+//    packed FFMA2 (default) and scalar FFMA.
+//  * k_mac_dc — bin 0 of the packed layout holds two purely real bins (DC, Nyquist), whose products are
+//    real products, not complex ones.  The tiled kernel treats bin 0 like any other bin (no divergence in
+//    the hot loop) and this small kernel overwrites Y[b][0] with the two real convolutions (0.4 % extra work).
 #include <cstdio>
 
 #include "gac_kernels.h"
@@ -64,6 +68,40 @@ void launch_mac_stream(const MacJob* d_jobs, int n_jobs, int64_t n_blocks, int s
 }
 
 // --------------------------------------------------------------------------------------------
+// k_mac_dc : Y[b][0] = (sum_p X[b-p][0].x * H[p][0].x , sum_p X[b-p][0].y * H[p][0].y), p ascending.
+// grid (ceil(n_blocks / 256), n_jobs), 256 threads, thread = output block.  X column 0 and H column 0 of the job
+// are gathered into shared memory once per CTA.
+// --------------------------------------------------------------------------------------------
+constexpr int kDcThreads = 256;
+__global__ void __launch_bounds__(kDcThreads) k_mac_dc(const MacJob* __restrict__ jobs, int64_t n_blocks, int stride, int p_max) {
+  const MacJob job = jobs[blockIdx.y];
+  if (!job.has_dc) return;
+  extern __shared__ float2 dsm[];
+  float2* hs = dsm;           // [p_max]
+  float2* xs = dsm + p_max;   // [kDcThreads + p_max - 1] : xs[i] = X[b0 - (P-1) + i][0]
+  const int P = job.P;
+  const int64_t b0 = (int64_t)blockIdx.x * kDcThreads;
+  for (int p = threadIdx.x; p < P; p += kDcThreads) hs[p] = job.H[(int64_t)p * stride];
+  for (int i = threadIdx.x; i < kDcThreads + P - 1; i += kDcThreads) {
+    int64_t j = b0 - (P - 1) + i;
+    xs[i] = (j >= 0 && j < n_blocks) ? job.X[j * stride] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int64_t b = b0 + threadIdx.x;
+  if (b >= n_blocks) return;
+  float ar = 0.f, ai = 0.f;
+  const float2* xw = xs + threadIdx.x + (P - 1);  // xw[-p] = X[b - p][0]
+#pragma unroll 4
+  for (int p = 0; p < P; p++) {
+    float2 x = xw[-p];
+    float2 h = hs[p];
+    ar = fmaf(x.x, h.x, ar);
+    ai = fmaf(x.y, h.y, ai);
+  }
+  job.Y[b * stride] = make_float2(ar, ai);
+}
+
+// --------------------------------------------------------------------------------------------
 // k_mac_tiled
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,32 +144,63 @@ struct MacCfg {
 // One pipeline stage for one thread: 16 partitions p = pbase..pbase+15, 16 output blocks each.
 // xa points at ring row of block (B0 - pbase) [row 0 of its 16-row group], xb at row 0 of the group below;
 // because tiles and stages are 16-aligned, X[B0 - pbase - j] is xa[0] for j = 0 and xb[(16 - j) * 128] for j >= 1.
-template <bool DC>
+// Sliding window: win[(t - j) & 15] holds X[B0 + t - pbase - j]; sub-step j loads the one new element into the slot
+// that fell out of the window.  All indices are compile-time after unrolling, so the window lives in registers.
 __device__ __forceinline__ void mac_stage(float2 (&acc)[kMacT], float2 (&win)[kMacT], const float2* __restrict__ hst,
-                                          const float2* __restrict__ xa, const float2* __restrict__ xb, bool dc) {
+                                          const float2* __restrict__ xa, const float2* __restrict__ xb) {
 #pragma unroll
   for (int j = 0; j < kMacChunk; j++) {
     const float2 h = hst[j * 128];
     win[(16 - j) & 15] = (j == 0) ? xa[0] : xb[(16 - j) * 128];
-    float ha = h.x, hb = h.y, hc = h.y, hd = h.x;
-    if (DC) {
-      // bin 0 = two independent real bins (DC, Nyquist): re += x.re*h.re ; im += x.im*h.im
-      hb = dc ? 0.f : h.y;
-      hc = dc ? 0.f : h.y;
-      hd = dc ? h.y : h.x;
-    }
 #pragma unroll
     for (int t = 0; t < kMacT; t++) {
       const float2 x = win[(t - j) & 15];
-      acc[t].x = fmaf(x.x, ha, acc[t].x);
-      acc[t].x = fmaf(-x.y, hb, acc[t].x);
-      acc[t].y = fmaf(x.x, hc, acc[t].y);
-      acc[t].y = fmaf(x.y, hd, acc[t].y);
+      acc[t].x = fmaf(x.x, h.x, acc[t].x);
+      acc[t].x = fmaf(-x.y, h.y, acc[t].x);
+      acc[t].y = fmaf(x.x, h.y, acc[t].y);
+      acc[t].y = fmaf(x.y, h.x, acc[t].y);
     }
   }
 }
 
-template <int NS>
+// ---- packed-FP32 flavour (Blackwell FFMA2, PTX fma.rn.f32x2): one instruction = two FMAs on an aligned register pair.
+// SASS FFMA2 can broadcast a scalar register to both halves (R.F32) and swap the halves of a pair (.LO_HI), so
+//   A += h.re * (x.re, x.im)          -> (sum h.re*x.re, sum h.re*x.im)
+//   B += h.im * swap(x.re, x.im)      -> (sum h.im*x.im, sum h.im*x.re)
+// need no operand shuffling at all; the complex sum is re = A.lo - B.lo, im = A.hi + B.hi at the end.  Every operand is
+// an aligned even/odd pair, so the register-bank conflicts that cap the scalar FFMA form at ~63 % of the FMA pipe
+// (acc.x/x.x vs acc.x/x.y parities cannot all differ while (x.x, x.y) arrive as an LDS.64 pair) do not arise.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+__device__ __forceinline__ void mac_stage_f2(uint64_t (&A)[kMacT], uint64_t (&Bq)[kMacT], float2 (&win)[kMacT],
+                                             const float2* __restrict__ hst, const float2* __restrict__ xa,
+                                             const float2* __restrict__ xb) {
+#pragma unroll
+  for (int j = 0; j < kMacChunk; j++) {
+    const float2 h = hst[j * 128];
+    win[(16 - j) & 15] = (j == 0) ? xa[0] : xb[(16 - j) * 128];
+    const uint64_t h1 = pk2(h.x, h.x);
+    const uint64_t h2 = pk2(h.y, h.y);
+#pragma unroll
+    for (int t = 0; t < kMacT; t++) {
+      const float2 x = win[(t - j) & 15];
+      A[t] = ffma2(h1, pk2(x.x, x.y), A[t]);
+      Bq[t] = ffma2(h2, pk2(x.y, x.x), Bq[t]);
+    }
+  }
+}
+
+template <int NS, bool F2>
 __global__ void __launch_bounds__(MacCfg<NS>::THREADS, (NS <= 2 ? 2 : 1))
     k_mac_tiled(const MacJob* __restrict__ jobs, const MacTile* __restrict__ tiles, int stride) {
   using Cfg = MacCfg<NS>;
@@ -147,8 +216,6 @@ __global__ void __launch_bounds__(MacCfg<NS>::THREADS, (NS <= 2 ? 2 : 1))
   const int b0 = tile.b0;  // multiple of TB (hence of 16)
   const int k = threadIdx.x & 127;
   const int sub = threadIdx.x >> 7;
-  const bool warp_dc = job.has_dc && k < 32;  // warp-uniform
-  const bool dc = job.has_dc && k == 0;
   // stages: chunks of 16 partitions, skipping chunks that only meet X rows before block 0 (all zero)
   const int p16 = (job.P + kMacChunk - 1) / kMacChunk;
   const int causal = (b0 + Cfg::TB) / 16;
@@ -186,10 +253,13 @@ __global__ void __launch_bounds__(MacCfg<NS>::THREADS, (NS <= 2 ? 2 : 1))
     }
   }
 
-  float2 acc[T];
+  float2 acc[F2 ? 1 : T];
+  uint64_t accA[F2 ? T : 1], accB[F2 ? T : 1];
   float2 win[T];
 #pragma unroll
-  for (int t = 0; t < T; t++) acc[t] = make_float2(0.f, 0.f);
+  for (int t = 0; t < (F2 ? 1 : T); t++) acc[t] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < (F2 ? T : 1); t++) accA[t] = accB[t] = 0ull;
   const int B0 = b0 + sub * T;  // first output block of this thread; its group is G0 + sub
 
   uint32_t phase0 = 0u, phase1 = 0u;
@@ -224,37 +294,62 @@ __global__ void __launch_bounds__(MacCfg<NS>::THREADS, (NS <= 2 ? 2 : 1))
       for (int t = 1; t < T; t++) win[t] = xa[t * 128];
     }
     const float2* __restrict__ hst = hs + (size_t)buf * kMacChunk * 128 + k;
-    if (warp_dc) {
-      mac_stage<true>(acc, win, hst, xa, xb, dc);
+    if constexpr (F2) {
+      mac_stage_f2(accA, accB, win, hst, xa, xb);
     } else {
-      mac_stage<false>(acc, win, hst, xa, xb, false);
+      mac_stage(reinterpret_cast<float2(&)[kMacT]>(acc), win, hst, xa, xb);
     }
   }
   float2* __restrict__ Y = job.Y + (int64_t)B0 * stride + k;
+  if constexpr (F2) {
 #pragma unroll
-  for (int t = 0; t < T; t++) Y[(int64_t)t * stride] = acc[t];
+    for (int t = 0; t < T; t++) {
+      float al, ah, bl, bh;
+      upk2(accA[t], al, ah);
+      upk2(accB[t], bl, bh);
+      Y[(int64_t)t * stride] = make_float2(al - bl, ah + bh);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < T; t++) Y[(int64_t)t * stride] = acc[t];
+  }
 }
 
 int mac_tile_blocks(int variant) { return variant == 64 ? 64 : 32; }
 
-void launch_mac_tiled(const MacJob* d_jobs, const MacTile* d_tiles, int n_tiles, int stride, int tile_blocks, cudaStream_t s) {
+template <int NS, bool F2>
+static void launch_mac_tiled_t(const MacJob* d_jobs, const MacTile* d_tiles, int n_tiles, int stride, cudaStream_t s) {
+  using Cfg = MacCfg<NS>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_mac_tiled<NS, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    attr = true;
+  }
+  k_mac_tiled<NS, F2><<<n_tiles, Cfg::THREADS, Cfg::SMEM, s>>>(d_jobs, d_tiles, stride);
+}
+
+void launch_mac_tiled(const MacJob* d_jobs, int n_jobs, const MacTile* d_tiles, int n_tiles, int64_t n_blocks, int p_max, int stride,
+                      int tile_blocks, int flavour, cudaStream_t s) {
   if (n_tiles <= 0) return;
+  const bool f2 = flavour != 2;  // 0 = FFMA2 (default), 2 = scalar FFMA
   if (tile_blocks == 64) {
-    using Cfg = MacCfg<4>;
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(k_mac_tiled<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-      attr = true;
-    }
-    k_mac_tiled<4><<<n_tiles, Cfg::THREADS, Cfg::SMEM, s>>>(d_jobs, d_tiles, stride);
+    if (f2) launch_mac_tiled_t<4, true>(d_jobs, d_tiles, n_tiles, stride, s);
+    else launch_mac_tiled_t<4, false>(d_jobs, d_tiles, n_tiles, stride, s);
   } else {
-    using Cfg = MacCfg<2>;
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(k_mac_tiled<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-      attr = true;
-    }
-    k_mac_tiled<2><<<n_tiles, Cfg::THREADS, Cfg::SMEM, s>>>(d_jobs, d_tiles, stride);
+    if (f2) launch_mac_tiled_t<2, true>(d_jobs, d_tiles, n_tiles, stride, s);
+    else launch_mac_tiled_t<2, false>(d_jobs, d_tiles, n_tiles, stride, s);
+  }
+  // bin 0 = (DC, Nyquist): two real convolutions, written over the generic result
+  const size_t smem = (size_t)(2 * p_max + kDcThreads) * sizeof(float2);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(k_mac_dc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+    dim3 grid((unsigned)((n_blocks + kDcThreads - 1) / kDcThreads), (unsigned)nj);
+    k_mac_dc<<<grid, kDcThreads, smem, s>>>(d_jobs + j0, n_blocks, stride, p_max);
   }
 }
 

@@ -275,6 +275,13 @@ class ConvolverNode(AudioNode):
             self._buffer, self._ir = None, None
             return
         ctx = self.Context
+        if value.SampleRate != ctx.SampleRate:  # Nodes/ConvolverNode.cs:48-49 (the library checks again)
+            raise InvalidOperationException(
+                "Impulse response buffer sample rate must match the audio context sample rate. "
+                f"Impulse response buffer sample rate: {value.SampleRate}, Audio context sample rate: {ctx.SampleRate}.")
+        if ctx._record_only:
+            self._buffer, self._ir = value, None
+            return
         out = C.c_void_p()
         check(N.lib().gac_ir_prepare(ctx._h, value._handle(ctx), int(self.Normalize), int(self.EnableTrueStereo), C.byref(out)))
         ctx._owned_irs.append(out.value)
@@ -284,7 +291,10 @@ class ConvolverNode(AudioNode):
 class OfflineAudioContext:
     """OfflineAudioContext.cs — `Render` is the one call that crosses into libgraphaudio_cuda.so."""
 
-    def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32):
+    def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32, _record_only=False):
+        """partition / device_id / mac_variant / tile_blocks map onto gac_context_desc.  `_record_only=True` builds a context
+        without a device handle: nodes, automation and topology can be recorded and inspected (`_topology()`), Render raises.
+        It exists for the CPU unit tests of the host-side logic; it is not a fallback."""
         self._h = None
         if sampleRate <= 0:
             raise ArgumentOutOfRangeException("sampleRate")  # AudioContextBase.cs:37-38
@@ -292,12 +302,14 @@ class OfflineAudioContext:
         self._nodes: List[AudioNode] = []
         self._owned_buffers: List[int] = []
         self._owned_irs: List[int] = []
-        desc = N.gac_context_desc()
-        desc.sample_rate, desc.quantum, desc.partition, desc.device_id, desc.mac_variant = self.SampleRate, 128, partition, device_id, mac_variant
-        desc.reserved[0] = tile_blocks
-        out = C.c_void_p()
-        check(N.lib().gac_context_create(C.byref(desc), C.byref(out)))
-        self._h = out.value
+        self._record_only = bool(_record_only)
+        if not self._record_only:
+            desc = N.gac_context_desc()
+            desc.sample_rate, desc.quantum, desc.partition, desc.device_id, desc.mac_variant = self.SampleRate, 128, partition, device_id, mac_variant
+            desc.reserved[0] = tile_blocks
+            out = C.c_void_p()
+            check(N.lib().gac_context_create(C.byref(desc), C.byref(out)))
+            self._h = out.value
         self.Destination = AudioDestinationNode(self)
         self._frames_rendered = 0
         self.last_stats = None
@@ -334,8 +346,8 @@ class OfflineAudioContext:
             raise NotSupportedException("a source feeding several nodes is outside the accelerated path (SURVEY.md §8f-2)")
         return node, list(reversed(ops))
 
-    def _flatten(self):
-        keep = []
+    def _topology(self):
+        """Pure host logic (no device needed): ([(source, [ops], bus)], [[bus ops]], [dest input codes])."""
         voices, buses, dest_inputs = [], [], []
         for head in self.Destination._in:
             # walk up while the chain is single-input; the first node with >= 2 inputs is the bus fan-in
@@ -358,6 +370,11 @@ class OfflineAudioContext:
                 if r is not None:
                     voices.append((r[0], r[1], bus_index))
         # the destination input itself may be the fan-in (several voices straight into Destination): handled above
+        return voices, buses, dest_inputs
+
+    def _flatten(self):
+        keep = []
+        voices, buses, dest_inputs = self._topology()
         vdesc = (N.gac_voice_desc * max(1, len(voices)))()
         for i, (src, ops, bus) in enumerate(voices):
             if not src._started or src.Buffer is None:
@@ -394,6 +411,8 @@ class OfflineAudioContext:
     def Render(self, output_or_count, frameCount=None, startIndex=0):
         """Render(float[][] output, int frameCount, int startIndex = 0)  (OfflineAudioContext.cs:30)
         or  float[][] Render(int frameCount)  (:108).  Successive calls continue the timeline (:55-100)."""
+        if self._record_only:
+            raise InvalidOperationException("record-only context: there is no CPU render path (build the library and use a B200)")
         if self._h is None:
             raise ObjectDisposedException("OfflineAudioContext")
         if frameCount is None:

@@ -1,0 +1,134 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/graphaudio_cuda.h declares, struct layouts
+match the header, the host-side mirror records topology/automation like the reference, and there is NO CPU fallback."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import graphaudio_b200 as G
+from graphaudio_b200 import _native as N
+from graphaudio_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "graphaudio_cuda.h")
+
+
+def _declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gac_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = N.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 24
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in graphaudio_cuda.h but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(N.SIGNATURES) == declared
+
+
+def test_version_and_struct_layouts():
+    assert N.lib().gac_version() == 1
+    # gac_event must be bit-compatible with AutomationEvent (AudioParam.cs:360-367): int, float, float, (pad), double, double
+    assert C.sizeof(N.gac_event) == 32
+    assert N.gac_event.time.offset == 16 and N.gac_event.time_constant.offset == 24
+    assert C.sizeof(N.gac_param) == 16
+    assert C.sizeof(N.gac_context_desc) == 32
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    n = C.c_int(-1)
+    rc = N.lib().gac_device_count(C.byref(n))
+    assert rc == N.GAC_ERR_NO_DEVICE and n.value == 0
+    with pytest.raises(G.CudaException) as e:
+        G.OfflineAudioContext(48000)
+    assert "no CPU fallback" in str(e.value)
+    assert N.lib().gac_render(None, None, 0, 128, None, 2, 0) != 0  # null handles are rejected, never rendered on the host
+
+
+def test_audio_param_event_order_and_clamping():
+    """AddEvent keeps time order with a stable upper-bound insert (AudioParam.cs:333-352); values clamp at schedule time."""
+    ctx = G.OfflineAudioContext(48000, _record_only=True)
+    bq = G.BiQuadFilterNode(ctx)
+    f = bq.Frequency
+    f.LinearRampToValueAtTime(5000.0, 2.0)
+    f.SetValueAtTime(100.0, 1.0)
+    f.SetValueAtTime(200.0, 1.0)      # equal times keep call order
+    f.SetValueAtTime(1e9, 0.5)        # clamped to fs/2
+    f.SetTargetAtTime(0.0, 3.0, 0.1)  # clamped to the minimum (1 Hz)
+    ev = f._events
+    assert [e[3] for e in ev] == [0.5, 1.0, 1.0, 2.0, 3.0]
+    assert [e[1] for e in ev[:4]] == [24000.0, 100.0, 200.0, 5000.0]
+    assert ev[4][0] == 3 and ev[4][2] == 1.0
+    f.CancelScheduledValues(1.0)      # removes events with time >= 1.0 (:312-331)
+    assert [e[3] for e in f._events] == [0.5]
+    f.Value = 0.0                     # clamps and clears (:34-49)
+    assert f.Value == 1.0 and f._events == []
+    with pytest.raises(G.ArgumentException):
+        G.GainNode(ctx).Gain.ExponentialRampToValueAtTime(0.0, 1.0)
+
+
+def test_topology_flattening_matches_connection_order():
+    ctx = G.OfflineAudioContext(48000, _record_only=True)
+    buf = G.PlayableAudioBuffer.FromMonoArray(np.zeros(256, np.float32), 48000)
+    bus = G.GainNode(ctx)
+    direct = G.AudioBufferSourceNode(ctx)
+    direct.Buffer = buf
+    direct.Connect(ctx.Destination)          # destination input 0: a direct voice
+    bus.Connect(ctx.Destination)             # destination input 1: the bus
+    chains = []
+    for v in range(3):
+        s = G.AudioBufferSourceNode(ctx)
+        s.Buffer = buf
+        bq, g, cv = G.BiQuadFilterNode(ctx), G.GainNode(ctx), G.ConvolverNode(ctx)
+        s.Connect(bq).Connect(g).Connect(cv).Connect(bus)
+        s.Start(0.1 * v)
+        chains.append((s, [bq, g, cv]))
+    voices, buses, dest = ctx._topology()
+    assert dest == [~0, 0]
+    assert voices[0][0] is direct and voices[0][2] == -1
+    for i, (s, ops) in enumerate(chains):
+        assert voices[1 + i][0] is s and voices[1 + i][1] == ops and voices[1 + i][2] == 0
+    assert buses == [[bus]]
+    with pytest.raises(G.InvalidOperationException):
+        chains[0][0].Start()  # "can only be started once" (AudioBufferSourceNode.cs:83-84)
+    with pytest.raises(G.InvalidOperationException):
+        ctx.Render(128)       # record-only context: no CPU render path exists
+
+
+def test_unsupported_shapes_are_rejected_loudly():
+    ctx = G.OfflineAudioContext(48000, _record_only=True)
+    buf = G.PlayableAudioBuffer.FromMonoArray(np.zeros(256, np.float32), 48000)
+    s = G.AudioBufferSourceNode(ctx)
+    s.Buffer = buf
+    a, b, bus = G.GainNode(ctx), G.GainNode(ctx), G.GainNode(ctx)
+    s.Connect(a).Connect(bus)
+    s.Connect(b).Connect(bus)  # fan-out: a source feeding two chains (ReverbEffect-style dry/wet split)
+    bus.Connect(ctx.Destination)
+    with pytest.raises(G.NotSupportedException):
+        ctx._topology()
+    with pytest.raises(G.InvalidOperationException):  # ConvolverNode.cs:48-49
+        G.ConvolverNode(ctx).Buffer = G.PlayableAudioBuffer.FromMonoArray(np.ones(8, np.float32), 44100)
+    with pytest.raises(G.ArgumentException):
+        G.PlayableAudioBuffer.FromChannelArrays([np.zeros(4), np.zeros(5)], 48000)  # PlayableAudioBuffer.cs:130-134
+
+
+def test_shard_ranges_partition_exactly():
+    for n in (0, 1, 7, 64, 1024):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = sharding.shard_range(n, r, world)
+                got += list(range(lo, hi))
+            assert got == list(range(n))
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
+    assert math.isclose(sum(len(sharding.shard_list(list(range(10)), r, 4)) for r in range(4)), 10)

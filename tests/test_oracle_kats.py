@@ -1,0 +1,287 @@
+"""CPU tests: the oracle (oracle/ga_oracle.cpp) against known answers derived from the reference source
+and against independent math (numpy / scipy).  The reference ships no tests or golden vectors of its own, so these
+known-answer tests — each citing the reference lines it pins — are what anchors the oracle ("parity unpinned" otherwise).
+The committed fixtures under tests/golden/ freeze the oracle's output so that later edits cannot drift silently.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy.signal import fftconvolve, lfilter
+
+from oracle import ga_oracle as O
+from tests import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------ FFT conventions (FftFlat/RealFourierTransform.cs:62-131)
+@pytest.mark.parametrize("n", [2, 8, 256, 1024])
+def test_rfft_matches_numpy_convention(n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    X = O.rfft_forward(x)
+    assert np.abs(X - np.fft.rfft(x)).max() < 1e-12 * n  # Forward == numpy.fft.rfft (Math.NET sign convention :80-84)
+    assert X[0].imag == 0 and X[-1].imag == 0            # DC and Nyquist purely real (:76-78)
+    assert np.abs(O.rfft_inverse(X) - x).max() < 1e-13   # Inverse is the exact inverse (2/N scaling :46,129)
+
+
+def test_rfft_rejects_non_power_of_two():
+    with pytest.raises(ValueError):
+        O.rfft_forward(np.zeros(12))  # RealFourierTransform.cs:38-41
+
+
+# ------------------------------------------------------------------ PartitionedConvolver (PartitionedConvolver.cs)
+def test_delta_ir_is_a_pure_delay():
+    """Normalize=false, IR = delta[n-d] => output = input delayed by d (ring direction + overlap-add, :104-152)."""
+    x = synth.splitmix_uniform(1, 128 * 30)
+    d = 200
+    ir = np.zeros(300, np.float32)
+    ir[d] = 1.0
+    y = O.PartitionedConvolver(ir, 128, False).process(x)
+    assert np.abs(y[d:] - x[:-d]).max() <= 2.5e-7
+    assert np.abs(y[:d]).max() <= 1e-7
+
+
+@pytest.mark.parametrize("block,ir_len", [(128, 24000), (128, 129), (512, 5000), (128, 1)])
+def test_equals_linear_convolution(block, ir_len):
+    n = block * 60
+    x = synth.splitmix_uniform(2, n)
+    ir = synth.decay_ir(3, ir_len) if ir_len > 1 else np.array([0.5], np.float32)
+    pc = O.PartitionedConvolver(ir, block, True)
+    y = pc.process(x)
+    scale = np.float32(O.normalization_scale(ir))
+    ref = fftconvolve(x.astype(np.float64), (ir * scale).astype(np.float64))[:n]
+    assert np.abs(y - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+    assert pc.partitions == math.ceil(ir_len / block)  # :44
+
+
+def test_normalization_scale_known_answers():
+    # all-ones IR: rms = 1 => scale = (1/1) * (float)10^(-58 * 0.05f)   (:93-102)
+    s = O.normalization_scale(np.ones(1000, np.float32))
+    assert s == np.float32(10.0 ** float(np.float32(-58) * np.float32(0.05)))
+    assert abs(s - 1.2589e-3) < 1e-6
+    # rms below MinPower (1.25e-4) is clamped
+    s2 = O.normalization_scale(np.full(100, 1e-6, np.float32))
+    assert s2 == np.float32(np.float32(1.0) / np.float32(0.000125)) * np.float32(s)
+    # each channel is normalised by its OWN rms (ConvolverNode.cs:51-56): two channels, different scales
+    a, b = synth.decay_ir(1, 1000), synth.decay_ir(2, 1000) * np.float32(0.1)
+    assert O.normalization_scale(a) != O.normalization_scale(b)
+
+
+def test_ir_spectra_are_float32_of_double_fft():
+    ir = synth.decay_ir(5, 300)
+    pc = O.PartitionedConvolver(ir, 128, False)
+    re, im = pc.ir_spectra()
+    blk = np.zeros(256)
+    blk[:300 - 256] = ir[256:]
+    ref = np.fft.rfft(blk)
+    assert np.array_equal(re[2], ref.real.astype(np.float32)) or np.abs(re[2] - ref.real).max() < 1e-7
+    assert re.shape == (3, 129)  # P = ceil(300/128), C = B + 1 (:41,44)
+
+
+# ------------------------------------------------------------------ CubicResampler (CubicResampler.cs:26-63)
+def test_resampler_known_answers():
+    x = np.arange(100, dtype=np.float32)
+    y, consumed = O.resample(x, 50, 1.0)
+    assert y[0] == x[1]                       # primed by 4 samples, first output is in[1] (:31-35,51-52)
+    assert np.array_equal(y[:20], x[1:21])    # rate 1, t = 0: passes S1 through
+    y2, _ = O.resample(x, 150, 0.5)
+    assert np.allclose(y2[:100], 1.0 + 0.5 * np.arange(100), atol=1e-5)  # Catmull-Rom reproduces a linear ramp
+    # output count for L inputs at rate r: stops when the next consume would pass the end (:43-44)
+    y3, c3 = O.resample(x[:10], 1000, 0.459375)
+    assert c3 == 10 and y3.shape[0] == int(np.ceil((10 - 4 + 1) / 0.459375))
+    y4, c4 = O.resample(x[:3], 10, 0.5)
+    assert y4.shape[0] == 0 and c4 == 3       # fewer than 4 inputs: never primed (:37-38)
+
+
+# ------------------------------------------------------------------ AudioParam (AudioParam.cs:169-247)
+def _gain_param():
+    ctx = O.OfflineAudioContext(48000)
+    return ctx, O.GainNode(ctx).Gain
+
+
+def test_automation_schedule():
+    ctx, p = _gain_param()
+    p.SetValueAtTime(0.5, 0.0)
+    p.LinearRampToValueAtTime(1.0, 0.01)
+    p.ExponentialRampToValueAtTime(0.25, 0.02)
+    p.SetTargetAtTime(0.0, 0.02, 0.005)
+    v = p.evaluate(12)
+    t = np.zeros(12 * 128)
+    bt = 0.0
+    for b in range(12):  # blockTime accumulates by repeated addition (AudioContextBase.cs:78-79)
+        t[b * 128:(b + 1) * 128] = bt + np.arange(128) * (1.0 / 48000)
+        bt = bt + 128.0 / 48000
+    ref = np.where(t < 0.01, 0.5 + 0.5 * np.clip(t / 0.01, 0, 1),
+                   np.where(t < 0.02, 1.0 * 0.25 ** np.clip((t - 0.01) / 0.01, 0, 1), 0.25 * np.exp(-(t - 0.02) / 0.005)))
+    assert np.abs(v - ref).max() < 1e-6
+
+
+def test_first_event_ramp_is_a_step():
+    ctx, p = _gain_param()
+    p.Value = 0.25
+    p.LinearRampToValueAtTime(1.0, 0.01)  # first event is a ramp: static value until its end time (:181-184)
+    v = p.evaluate(6)
+    k = int(np.ceil(0.01 * 48000))
+    assert np.all(v[:k] == np.float32(0.25)) and np.all(v[k + 1:] == np.float32(1.0))
+
+
+def test_ramp_after_set_target_starts_from_zero_value_field():
+    ctx, p = _gain_param()
+    p.SetValueAtTime(0.8, 0.0)
+    p.SetTargetAtTime(0.2, 0.001, 0.01)
+    p.LinearRampToValueAtTime(1.0, 0.004)  # interpolates from the SetTarget event's Value field, which is 0 (:186-190)
+    v = p.evaluate(2)
+    i = 100  # t = 100/48000 = 2.08 ms, inside the ramp segment [1 ms, 4 ms]
+    u = (i / 48000 - 0.001) / 0.003
+    assert abs(v[i] - u * 1.0) < 1e-6
+
+
+def test_value_setter_cancels_events_and_clamps():
+    ctx = O.OfflineAudioContext(48000)
+    bq = O.BiQuadFilterNode(ctx)
+    bq.Frequency.SetValueAtTime(500.0, 0.0)
+    bq.Frequency.Value = 1e9  # clamped to fs/2 and clears the schedule (:34-49)
+    assert np.all(bq.Frequency.evaluate(1) == np.float32(24000.0))
+    bq.Frequency.ExponentialRampToValueAtTime(-1.0, 1.0)  # clamped to the minimum (1 Hz) BEFORE the > 0 check (:282-284)
+    with pytest.raises(O.ArgumentException):
+        O.GainNode(ctx).Gain.ExponentialRampToValueAtTime(-1.0, 1.0)  # "Exponential ramp target must be > 0"
+
+
+# ------------------------------------------------------------------ graph-level semantics
+def _source_to_dest(x, fs=48000, ops=None, n=None, stereo=False):
+    ctx = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(ctx)
+    s.Buffer = O.PlayableAudioBuffer.FromStereoArrays(x, x[::-1].copy(), fs) if stereo else O.PlayableAudioBuffer.FromMonoArray(x, fs)
+    node = s
+    made = []
+    for mk in ops or []:
+        nd = mk(ctx)
+        node = node.Connect(nd)
+        made.append(nd)
+    node.Connect(ctx.Destination)
+    s.Start()
+    return ctx, ctx.Render(n or len(x)), made
+
+
+@pytest.mark.parametrize("L", [1280, 1281, 1300, 1407, 1408, 100, 129])
+def test_source_end_rule(L):
+    """rate == 1, buffer length L => exactly 128*floor((L-1)/128) frames are emitted (AudioBufferSourceNode.cs:224,360-362)."""
+    x = synth.splitmix_uniform(4, L) + np.float32(2.0)  # never zero
+    _, y, _ = _source_to_dest(x, n=L + 256)
+    emitted = 128 * ((L - 1) // 128)
+    assert np.array_equal(y[0, :emitted], x[:emitted])
+    assert not y[:, emitted:].any()
+    assert np.array_equal(y[0], y[1])  # mono -> stereo up-mix copies the channel (AudioNodeInput.cs:201-213)
+
+
+def test_chunked_render_equals_single_render():
+    x = synth.splitmix_uniform(6, 5000)
+    ir = synth.decay_ir(7, 700)
+
+    def build():
+        ctx = O.OfflineAudioContext(48000)
+        s = O.AudioBufferSourceNode(ctx)
+        s.Buffer = O.PlayableAudioBuffer.FromMonoArray(x, 48000)
+        c = O.ConvolverNode(ctx)
+        c.Buffer = O.PlayableAudioBuffer.FromStereoArrays(ir, ir[::-1].copy(), 48000)
+        s.Connect(c).Connect(ctx.Destination)
+        s.Start()
+        return ctx
+    whole = build().Render(3000)
+    c2 = build()
+    parts = np.concatenate([c2.Render(1000), c2.Render(777), c2.Render(1223)], axis=1)  # OfflineAudioContext.cs:55-100
+    assert np.array_equal(whole, parts)
+
+
+def test_biquad_constant_matches_rbj_closed_form():
+    """f = 1000, Q = 1 (the defaults): one coefficient set, closed-form RBJ lowpass; checked against scipy.lfilter."""
+    fs = 48000
+    x = synth.splitmix_uniform(8, 128 * 40)
+    _, y, _ = _source_to_dest(x, ops=[lambda c: O.BiQuadFilterNode(c)], n=128 * 40)
+    w0 = 2 * np.pi * 1000.0 / fs
+    alpha = np.sin(w0) / 2.0
+    b = np.array([(1 - np.cos(w0)) / 2, 1 - np.cos(w0), (1 - np.cos(w0)) / 2]) / (1 + alpha)
+    a = np.array([1.0, -2 * np.cos(w0) / (1 + alpha), (1 - alpha) / (1 + alpha)])
+    emitted = 128 * 39
+    ref = lfilter(b, a, x[:emitted].astype(np.float64))
+    assert np.abs(y[0, :emitted] - ref).max() < 2e-5  # float32 DF-II vs float64 reference
+
+
+def test_biquad_nondefault_constant_and_silent_tail():
+    fs = 48000
+    x = synth.splitmix_uniform(9, 128 * 20)
+
+    def mk(c):
+        b = O.BiQuadFilterNode(c)
+        b.Type = O.FilterType.Highpass
+        b.Frequency.Value = 3000.0
+        b.Q.Value = 2.0
+        return b
+    _, y, _ = _source_to_dest(x, ops=[mk], n=128 * 24)
+    w0 = 2 * np.pi * 3000.0 / fs
+    alpha = np.sin(w0) / 4.0
+    b = np.array([(1 + np.cos(w0)) / 2, -(1 + np.cos(w0)), (1 + np.cos(w0)) / 2]) / (1 + alpha)
+    a = np.array([1.0, -2 * np.cos(w0) / (1 + alpha), (1 - alpha) / (1 + alpha)])
+    emitted = 128 * 19
+    ref = lfilter(b, a, x[:emitted].astype(np.float64))
+    assert np.abs(y[0, :emitted] - ref).max() < 2e-5
+    # once the source block is flagged silent the filter emits zeros: the tail is CUT, not rung out (BiQuadFilterNode.cs:103-108)
+    assert not y[:, emitted:].any()
+
+
+def test_fan_in_order_is_connection_order():
+    fs = 48000
+    a = np.full(256, 1e8, np.float32)
+    b = np.full(256, -1e8, np.float32)
+    c = np.full(256, 1.0, np.float32)
+
+    def run(order):
+        ctx = O.OfflineAudioContext(fs)
+        for arr in order:
+            s = O.AudioBufferSourceNode(ctx)
+            s.Buffer = O.PlayableAudioBuffer.FromMonoArray(arr, fs)
+            s.Connect(ctx.Destination)
+            s.Start()
+        return ctx.Render(128)
+    assert np.all(run([a, b, c])[0] == 1.0)   # ((0 + 1e8) - 1e8) + 1 = 1     (AudioNodeInput.cs:118-137)
+    assert np.all(run([a, c, b])[0] == 0.0)   # ((0 + 1e8) + 1) - 1e8 = 0 in float32
+
+
+def test_convolver_rate_mismatch_raises():
+    ctx = O.OfflineAudioContext(48000)
+    c = O.ConvolverNode(ctx)
+    with pytest.raises(O.InvalidOperationException):  # ConvolverNode.cs:48-49
+        c.Buffer = O.PlayableAudioBuffer.FromMonoArray(np.ones(10, np.float32), 44100)
+
+
+# ------------------------------------------------------------------ committed golden fixtures
+def _golden_c2():
+    fs = 48000
+    voices = []
+    for v in range(2):
+        src, ir = synth.make_voice_inputs(v, 6000, 1500)
+        voices.append((src, ir, synth.voice_gains(v)))
+    return synth.build_c2(O, fs, voices, 0.5, t_scale=0.01).Render(8000)
+
+
+def _golden_c3():
+    fs = 48000
+    voices = []
+    for v in range(2):
+        src, ir = synth.make_voice_inputs(10 + v, 6000, 1000)
+        voices.append((src, ir, synth.voice_gains(v)))
+    return synth.build_c3(O, fs, voices, 0.5, f0=300.0, f1=9000.0, t_scale=0.01, q=2.0).Render(8000)
+
+
+@pytest.mark.parametrize("name,fn", [("c2_small", _golden_c2), ("c3_small", _golden_c3)])
+def test_golden_fixture(name, fn):
+    """tests/golden/*.npy were generated by tests/golden/make_golden.py from this oracle; bit-exact on the same libm."""
+    path = os.path.join(GOLDEN, name + ".npy")
+    y = fn()
+    ref = np.load(path)
+    assert y.shape == ref.shape
+    # identical on the generating machine; other glibc builds may differ in the last ulp of sinf/cosf/pow
+    assert np.abs(y - ref).max() <= 1e-6

@@ -1,0 +1,151 @@
+// Native.cs — P/Invoke surface of libgraphaudio_cuda.so (include/graphaudio_cuda.h), in the idiom of
+// GraphAudio.IO/Libsndfile.cs:36-68 and GraphAudio.Realtime/Miniaudio.cs:305-349 ([LibraryImport] + cdecl).
+// Source only: this repository's image has no dotnet toolchain, so the file is reviewed by reading.
+using System;
+using System.Runtime.CompilerServices;
+using System.Runtime.InteropServices;
+
+namespace GraphAudio.Cuda;
+
+internal enum GacStatus
+{
+    Ok = 0, InvalidArgument = -1, OutOfRange = -2, InvalidOperation = -3, Disposed = -4,
+    NoDevice = -5, Cuda = -6, OutOfMemory = -7, Nccl = -8, Unsupported = -9
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct GacContextDesc
+{
+    public int SampleRate, Quantum, Partition, DeviceId, MacVariant;
+    public fixed int Reserved[3];
+}
+
+/// <summary>Bit-compatible with AudioParam.AutomationEvent (AudioParam.cs:360-367).</summary>
+[StructLayout(LayoutKind.Sequential)]
+internal struct GacEvent
+{
+    public int Type;
+    public float Value;
+    public float Target;
+    public double Time;
+    public double TimeConstant;
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct GacParam
+{
+    public float Value;
+    public int EventCount;
+    public GacEvent* Events;
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct GacOpDesc
+{
+    public int Kind;        // 1 biquad, 2 gain, 3 convolver
+    public int FilterType;  // (int)FilterType
+    public GacParam P0, P1, P2;
+    public IntPtr Ir;
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct GacVoiceDesc
+{
+    public IntPtr Source;
+    public double StartWhen, StartOffset, StartDuration, StopWhen;
+    public float PlaybackRate;
+    public int OpCount;
+    public GacOpDesc* Ops;
+    public int Bus;
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct GacBusDesc
+{
+    public int OpCount;
+    public GacOpDesc* Ops;
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal unsafe struct GacGraphDesc
+{
+    public int VoiceCount;
+    public GacVoiceDesc* Voices;
+    public int BusCount;
+    public GacBusDesc* Buses;
+    public int DestInputCount;
+    public int* DestInputs;
+}
+
+internal static unsafe partial class Native
+{
+    private const string Lib = "graphaudio_cuda";
+
+    [LibraryImport(Lib, EntryPoint = "gac_version")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int Version();
+
+    [LibraryImport(Lib, EntryPoint = "gac_last_error")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial IntPtr LastErrorPtr();   // thread-local, owned by the library (cf. sf_strerror)
+
+    [LibraryImport(Lib, EntryPoint = "gac_context_create")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ContextCreate(GacContextDesc* desc, out IntPtr ctx);
+
+    [LibraryImport(Lib, EntryPoint = "gac_context_destroy")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ContextDestroy(IntPtr ctx);
+
+    [LibraryImport(Lib, EntryPoint = "gac_buffer_create")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int BufferCreate(IntPtr ctx, float** channels, int channelCount, long frames, int sampleRate, out IntPtr buffer);
+
+    [LibraryImport(Lib, EntryPoint = "gac_buffer_destroy")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int BufferDestroy(IntPtr buffer);
+
+    [LibraryImport(Lib, EntryPoint = "gac_ir_prepare")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int IrPrepare(IntPtr ctx, IntPtr buffer, int normalize, int trueStereo, out IntPtr ir);
+
+    [LibraryImport(Lib, EntryPoint = "gac_ir_destroy")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int IrDestroy(IntPtr ir);
+
+    [LibraryImport(Lib, EntryPoint = "gac_graph_create")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int GraphCreate(IntPtr ctx, GacGraphDesc* desc, out IntPtr graph);
+
+    [LibraryImport(Lib, EntryPoint = "gac_graph_destroy")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int GraphDestroy(IntPtr graph);
+
+    [LibraryImport(Lib, EntryPoint = "gac_render")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int Render(IntPtr ctx, IntPtr graph, long firstFrame, long frames, float** outChannels, int channelCount, long startIndex);
+
+    [LibraryImport(Lib, EntryPoint = "gac_render_batch")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int RenderBatch(IntPtr ctx, IntPtr* graphs, int graphCount, long frames, float** outChannels, int channelCount);
+
+    internal static string LastError() => Marshal.PtrToStringUTF8(LastErrorPtr()) ?? string.Empty;
+
+    /// <summary>Maps gac_status onto the exception types the reference throws at the same places
+    /// (OfflineAudioContext.cs:32-51, ConvolverNode.cs:45-49, AudioContextBase.cs:54-55).</summary>
+    internal static void Check(int status)
+    {
+        if (status == 0) return;
+        string msg = LastError();
+        throw (GacStatus)status switch
+        {
+            GacStatus.InvalidArgument => new ArgumentException(msg),
+            GacStatus.OutOfRange => new ArgumentOutOfRangeException(null, msg),
+            GacStatus.InvalidOperation => new InvalidOperationException(msg),
+            GacStatus.Disposed => new ObjectDisposedException(nameof(OfflineAudioContext), msg),
+            GacStatus.Unsupported => new NotSupportedException(msg),
+            GacStatus.OutOfMemory => new OutOfMemoryException(msg),
+            _ => new InvalidOperationException($"graphaudio_cuda error {status}: {msg}")
+        };
+    }
+}

@@ -1,0 +1,85 @@
+// OfflineAudioContext.cs (GraphAudio.Cuda) — the render entry point of the mirror API.  The node / param / buffer
+// mirror types (AudioBufferSourceNode, BiQuadFilterNode, GainNode, ConvolverNode, AudioParam, PlayableAudioBuffer) record
+// topology and automation exactly like graphaudio_b200/host/graphaudio_cuda.hpp (the C++ twin, which IS built and
+// tested in this repository); only the part that crosses the ABI is spelled out here.
+// Source only: no dotnet toolchain in this image.
+using System;
+using System.Collections.Generic;
+
+namespace GraphAudio.Cuda;
+
+public sealed unsafe class OfflineAudioContext : IDisposable
+{
+    private IntPtr _ctx;
+    private long _framesRendered;
+    public int SampleRate { get; }
+    public AudioDestinationNode Destination { get; }
+
+    public OfflineAudioContext(int sampleRate = 48000)   // OfflineAudioContext.cs:18
+    {
+        if (sampleRate <= 0) throw new ArgumentOutOfRangeException(nameof(sampleRate));   // AudioContextBase.cs:37-38
+        SampleRate = sampleRate;
+        var desc = new GacContextDesc { SampleRate = sampleRate, Quantum = 128, Partition = 128, DeviceId = -1 };
+        Native.Check(Native.ContextCreate(&desc, out _ctx));
+        Destination = new AudioDestinationNode(this);
+    }
+
+    internal IntPtr Handle => _ctx != IntPtr.Zero ? _ctx : throw new ObjectDisposedException(nameof(OfflineAudioContext));
+
+    /// <summary>Render(float[][] output, int frameCount, int startIndex = 0) — OfflineAudioContext.cs:30.</summary>
+    public void Render(float[][] output, int frameCount, int startIndex = 0)
+    {
+        if (output.Length == 0) throw new ArgumentException("Output buffer must have at least one channel.", nameof(output));
+        if (frameCount <= 0) throw new ArgumentOutOfRangeException(nameof(frameCount), "Frame count must be positive.");
+        if (startIndex < 0) throw new ArgumentOutOfRangeException(nameof(startIndex), "Start index must be non-negative.");
+        for (int ch = 0; ch < output.Length; ch++)
+        {
+            if (output[ch] is null) throw new ArgumentException($"Channel {ch} buffer is null.", nameof(output));
+            if (output[ch].Length < startIndex + frameCount)
+                throw new ArgumentException($"Channel {ch} buffer is too small. Required: {startIndex + frameCount}, Available: {output[ch].Length}", nameof(output));
+        }
+        // GraphFlattener walks Destination <- bus chain <- fan-in <- voice chains <- sources (connection order preserved)
+        // and pins the event arrays; see Flatten() in graphaudio_cuda.hpp for the algorithm.
+        using var flat = GraphFlattener.Flatten(this);
+        Native.Check(Native.GraphCreate(Handle, flat.Desc, out IntPtr graph));
+        try
+        {
+            // planar float[][] pinned and passed as float**, the way SteamAudioNodeBase.PinBuffersAndProcess does
+            // (GraphAudio.SteamAudio/Nodes/SteamAudioNodeBase.cs:74-135)
+            var handles = new System.Runtime.InteropServices.GCHandle[output.Length];
+            float** rows = stackalloc float*[output.Length];
+            try
+            {
+                for (int ch = 0; ch < output.Length; ch++)
+                {
+                    handles[ch] = System.Runtime.InteropServices.GCHandle.Alloc(output[ch], System.Runtime.InteropServices.GCHandleType.Pinned);
+                    rows[ch] = (float*)handles[ch].AddrOfPinnedObject();
+                }
+                Native.Check(Native.Render(Handle, graph, _framesRendered, frameCount, rows, output.Length, startIndex));
+                _framesRendered += frameCount;   // successive Render calls continue the timeline (:55-100)
+            }
+            finally
+            {
+                foreach (var h in handles) if (h.IsAllocated) h.Free();
+            }
+        }
+        finally
+        {
+            Native.GraphDestroy(graph);
+        }
+    }
+
+    /// <summary>float[][] Render(int frameCount) — OfflineAudioContext.cs:108.</summary>
+    public float[][] Render(int frameCount)
+    {
+        if (frameCount <= 0) throw new ArgumentOutOfRangeException(nameof(frameCount), "Frame count must be positive.");
+        var output = new[] { new float[frameCount], new float[frameCount] };
+        Render(output, frameCount);
+        return output;
+    }
+
+    public void Dispose()
+    {
+        if (_ctx != IntPtr.Zero) { Native.ContextDestroy(_ctx); _ctx = IntPtr.Zero; }
+    }
+}

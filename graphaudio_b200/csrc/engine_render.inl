@@ -236,6 +236,14 @@ extern "C" int gac_comm_init(gac_context* ctx, const void* id128, int rank, int 
   ctx->comm = comm;
   ctx->rank = rank;
   ctx->n_ranks = n_ranks;
+  // NCCL connects its channels lazily on the first collective: pay that here, not inside the first render
+  float* d_warm = nullptr;
+  CU(cudaMallocAsync(&d_warm, 256 * sizeof(float), ctx->stream));
+  CU(cudaMemsetAsync(d_warm, 0, 256 * sizeof(float), ctx->stream));
+  r = a->Reduce(d_warm, d_warm, 256, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, ctx->comm, ctx->stream);
+  if (r != 0) return nccl_fail(a, r, "ncclReduce (warm-up)");
+  CU(cudaFreeAsync(d_warm, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return GAC_OK;
 }
 extern "C" int gac_comm_destroy(gac_context* ctx) {

@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     ObjectDisposedException,
     OfflineAudioContext,
     PlayableAudioBuffer,
+    RenderBatch,
 )
 
 __all__ = [

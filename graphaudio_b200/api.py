@@ -105,6 +105,7 @@ class PlayableAudioBuffer:
         return PlayableAudioBuffer([leftChannel, rightChannel], sampleRate)
 
     def _handle(self, ctx: "OfflineAudioContext"):
+        ctx = ctx._root()  # forks share the parent's device handle
         h = self._handles.get(id(ctx))
         if h is None:
             ptrs = (N.fp * self.NumberOfChannels)(*[_fptr(c) for c in self.channels])
@@ -448,7 +449,33 @@ class OfflineAudioContext:
         finally:
             N.lib().gac_graph_destroy(graph)
 
+    # ---- batches of independent renders share one device context
+    def Fork(self):
+        """A new, empty OfflineAudioContext (own Destination, own timeline) that records against this context's device
+        handle.  Used with RenderBatch; disposing the parent disposes the shared handle."""
+        child = OfflineAudioContext.__new__(OfflineAudioContext)
+        child._h = self._h
+        child.SampleRate = self.SampleRate
+        child._nodes = []
+        child._owned_buffers = self._owned_buffers
+        child._owned_irs = self._owned_irs
+        child._record_only = self._record_only
+        child._parent = self
+        child.Destination = AudioDestinationNode(child)
+        child._frames_rendered = 0
+        child.last_stats = None
+        return child
+
+    def _root(self):
+        c = self
+        while getattr(c, "_parent", None) is not None:
+            c = c._parent
+        return c
+
     def Dispose(self):
+        if getattr(self, "_parent", None) is not None:
+            self._h = None  # forks do not own the handle
+            return
         if self._h is not None:
             L = N.lib()
             for h in self._owned_irs:
@@ -463,3 +490,33 @@ class OfflineAudioContext:
             self.Dispose()
         except Exception:
             pass
+
+
+def RenderBatch(contexts, frameCount):
+    """BASELINE config 4: many independent OfflineAudioContexts rendered in ONE native call (gac_render_batch).
+
+    `contexts` are graphs recorded against a shared device context: build each with `OfflineAudioContext.Fork()` of a
+    common parent (they share the parent's gac_context, hence its stream and scratch pool).  Returns float32
+    [len(contexts), 2, frameCount].  Equivalent to calling Render(frameCount) on each context in turn, as the reference
+    would (one context per render, OfflineAudioContext.cs:30), but batched across renders on the device."""
+    if frameCount <= 0:
+        raise ArgumentOutOfRangeException("Frame count must be positive.")
+    if not contexts:
+        raise ArgumentException("no contexts")
+    root = contexts[0]._root()
+    if any(c._root() is not root for c in contexts):
+        raise ArgumentException("all contexts of a batch must be forks of the same parent context")
+    L = N.lib()
+    graphs = [c._graph() for c in contexts]
+    try:
+        out = np.zeros((len(contexts), 2, frameCount), np.float32)
+        rows = (N.fp * (2 * len(contexts)))(*[_fptr(out[g, c]) for g in range(len(contexts)) for c in range(2)])
+        garr = (C.c_void_p * len(graphs))(*graphs)
+        check(L.gac_render_batch(root._h, garr, len(graphs), int(frameCount), rows, 2))
+        st = N.gac_stats()
+        check(L.gac_get_stats(root._h, C.byref(st)))
+        root.last_stats = st.as_dict()
+        return out
+    finally:
+        for g in graphs:
+            L.gac_graph_destroy(g)

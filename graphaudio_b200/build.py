@@ -25,6 +25,7 @@ SOURCES = [
     ("mac.cu", []),
     ("fft.cu", []),
     ("nodes.cu", ["--fmad=false"]),
+    ("biquad.cu", ["--fmad=false"]),
     ("engine.cu", ["-Xcompiler", "-fvisibility=default"]),
 ]
 HEADERS = ["gac_kernels.h", "engine_render.inl", os.path.join("..", "..", "include", "graphaudio_cuda.h")]

@@ -765,12 +765,24 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     }
     // ---------------- BiQuadFilterNode (K2 + K3)
     if (!biquads.empty()) {
-      const size_t per_job = (size_t)env.Npad * (5 * 4 + 4 + 4 + 2) + (size_t)env.NQ * 12;
+      const size_t per_job = (size_t)env.Npad * (2 * (4 + 16 + 8 + 4) + 4 + 4) + (size_t)env.NQ * (16 + 4);
       const size_t max_jobs = std::max<size_t>(1, ctx->scratch_budget / per_job);
       for (size_t k0 = 0; k0 < biquads.size(); k0 += max_jobs) {
         const size_t nk = std::min(max_jobs, biquads.size() - k0);
         std::vector<ParamJob> pj;
         auto& bj = env.keep->make<BiquadJob>();
+        int32_t* idx_all = nullptr;
+        float4* s1_all = nullptr;
+        float2* s2_all = nullptr;
+        float* w_all = nullptr;
+        {
+          int rc;
+          const size_t rows = ((nk + 15) / 16) * 16 * 2;  // the lanes kernel addresses whole 32-row groups
+          if ((rc = env.scratch->alloc(&idx_all, nk * 2 * (size_t)env.Npad))) return rc;
+          if ((rc = env.scratch->alloc(&s1_all, rows * (size_t)env.Npad))) return rc;
+          if ((rc = env.scratch->alloc(&s2_all, nk * 2 * (size_t)env.Npad))) return rc;
+          if ((rc = env.scratch->alloc(&w_all, rows * (size_t)env.Npad))) return rc;
+        }
         for (size_t k = 0; k < nk; k++) {
           Sig& s = sigs[biquads[k0 + k]];
           const OpH& op = (*s.ops)[pos];
@@ -791,21 +803,23 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           j.type = op.ftype;
           j.lo = s.lo;
           j.hi = s.hi;
-          if ((rc = env.scratch->alloc(&j.coef, (size_t)env.Npad * 5))) return rc;
+          j.idx = idx_all + k * 2 * (size_t)env.Npad;
+          j.s1 = s1_all + k * 2 * (size_t)env.Npad;
+          j.s2 = s2_all + k * 2 * (size_t)env.Npad;
+          j.w = w_all + k * 2 * (size_t)env.Npad;
           bj.push_back(j);
         }
         int rc = run_param_jobs(env, pj);
         if (rc) return rc;
         BiquadJob* dbj = nullptr;
-        uint8_t* dsel = nullptr;
-        int32_t* dlast = nullptr;
+        int32_t *dlast = nullptr, *dent = nullptr;
         if ((rc = env.scratch->upload(&dbj, bj))) return rc;
-        if ((rc = env.scratch->alloc(&dsel, nk * 2 * (size_t)env.Npad))) return rc;
         if ((rc = env.scratch->alloc(&dlast, nk * 2 * (size_t)env.NQ))) return rc;
+        if ((rc = env.scratch->alloc(&dent, nk * 2 * (size_t)env.NQ))) return rc;
         int t = env.timer->begin(C_BIQUAD);
-        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dsel, dlast, ctx->stream);
+        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, w_all, ctx->stream);
         env.timer->end(t);
-        env.launches += 4;
+        env.launches += 5;
         CU(cudaGetLastError());
       }
     }

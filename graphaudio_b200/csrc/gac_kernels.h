@@ -110,11 +110,16 @@ struct BiquadJob {
   float freq_const, q_const, gain_const;
   int type;
   int64_t lo, hi;      // active frame range (multiples of 128)
-  float* coef;         // scratch [n_frames][5] (b0,b1,b2,a1,a2) per frame
+  // scratch, per job (c = channel, n = frame):
+  int32_t* idx;        // [2][n_frames] frame whose (f, Q) gave the coefficients in force, -1 = the quantum's entry set
+  float4* s1;          // [2][n_frames] (x, a1, a2, b0)
+  float2* s2;          // [2][n_frames] (b1, b2)
+  float* w;            // [2][n_frames] Direct-Form-II state sequence
 };
-// d_sel: scratch uint8 [n_jobs][2][n_frames] (recompute flags); d_last: scratch int32 [n_jobs][2][n_quanta]
-void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, uint8_t* d_sel,
-                   int32_t* d_last, cudaStream_t s);
+// scratch: d_last, d_ent int32 [n_jobs][2][n_quanta].  d_s1_all / d_w_all are the batch-wide arrays [n_jobs][2][n_frames] that
+// job k's s1 / w point into (job k at offset k*2*n_frames): the lanes kernel addresses rows arithmetically.
+void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
+                   int32_t* d_ent, const float4* d_s1_all, float* d_w_all, cudaStream_t s);
 
 struct MixJob {       // dst[c][n] = (((0 + src0) + src1) + ...) over active ranges, AudioNodeInput.cs:118-137
   float* dst[2];

@@ -207,3 +207,29 @@ def test_error_mapping():
     ctx.Dispose()
     with pytest.raises(G.ObjectDisposedException):
         ctx.Render(128)
+
+
+def test_c4_render_batch_of_independent_contexts():
+    """BASELINE config 4 shape: a batch of independent renders (biquad chain + convolver each) in one gac_render_batch call
+    equals the per-context oracle renders."""
+    G, O = _apis()
+    fs = 48000
+    parent = G.OfflineAudioContext(fs)
+    forks, refs = [], []
+    for r in range(5):
+        src, ir = synth.make_voice_inputs(20 + r, 10000 + 700 * r, 3000)
+
+        class _Api:  # build_c4 against a fork of the shared device context
+            pass
+        shim = _Api()
+        for name in ("AudioBufferSourceNode", "BiQuadFilterNode", "ConvolverNode", "PlayableAudioBuffer", "FilterType"):
+            setattr(shim, name, getattr(G, name))
+        shim.OfflineAudioContext = lambda _fs, _p=parent: _p.Fork()
+        forks.append(synth.build_c4(shim, fs, src, ir, t_scale=0.03))
+        refs.append(synth.build_c4(O, fs, src, ir, t_scale=0.03).Render(16000))
+    out = G.RenderBatch(forks, 16000)
+    assert out.shape == (5, 2, 16000)
+    for r in range(5):
+        assert np.abs(refs[r]).max() > 1e-3
+        assert np.abs(out[r] - refs[r]).max() <= TOL, r
+    parent.Dispose()

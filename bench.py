@@ -278,10 +278,16 @@ def run_ours(args, wl):
         e2e_note = "communicator bootstrap outside the timed region; H2D + IR prepare + sharded render + D2H inside"
     lat = []
     for i in range(2 + args.steps):
-        c = G.OfflineAudioContext(FS, device_id=local, tile_blocks=args.tile_blocks, partition=args.partition)
-        comm(c)
+        def fresh():
+            return G.OfflineAudioContext(FS, device_id=local, tile_blocks=args.tile_blocks, partition=args.partition,
+                                         async_upload=not args.sync_upload)
+        if world > 1:
+            c = fresh()
+            comm(c)
         barrier()
         t0 = time.perf_counter()
+        if world == 1:
+            c = fresh()  # N = 1: creating the context is part of the step
         build_into(G, wl, voices, c)
         if world > 1:
             g = c._graph()
@@ -373,6 +379,8 @@ def main():
     ap.add_argument("--tile-blocks", dest="tile_blocks", type=int, default=32)
     ap.add_argument("--cpu-voices", dest="cpu_voices", type=int, default=8)
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--sync-upload", dest="sync_upload", action="store_true",
+                    help="e2e arm: copy every buffer during gac_buffer_create (reference semantics) instead of GAC_FLAG_ASYNC_UPLOAD")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -16,8 +16,7 @@ internal enum GacStatus
 [StructLayout(LayoutKind.Sequential)]
 internal unsafe struct GacContextDesc
 {
-    public int SampleRate, Quantum, Partition, DeviceId, MacVariant;
-    public fixed int Reserved[3];
+    public int SampleRate, Quantum, Partition, DeviceId, MacVariant, TileBlocks, Flags, Reserved;
 }
 
 /// <summary>Bit-compatible with AudioParam.AutomationEvent (AudioParam.cs:360-367).</summary>

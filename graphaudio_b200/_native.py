@@ -30,7 +30,10 @@ fpp = C.POINTER(fp)
 
 class gac_context_desc(C.Structure):
     _fields_ = [("sample_rate", C.c_int), ("quantum", C.c_int), ("partition", C.c_int), ("device_id", C.c_int),
-                ("mac_variant", C.c_int), ("reserved", C.c_int * 3)]
+                ("mac_variant", C.c_int), ("tile_blocks", C.c_int), ("flags", C.c_int), ("reserved", C.c_int)]
+
+
+GAC_FLAG_ASYNC_UPLOAD = 1
 
 
 class gac_event(C.Structure):
@@ -80,6 +83,7 @@ SIGNATURES = {
     "gac_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "gac_context_create": (C.c_int, [C.POINTER(gac_context_desc), C.POINTER(C.c_void_p)]),
     "gac_context_destroy": (C.c_int, [C.c_void_p]),
+    "gac_synchronize": (C.c_int, [C.c_void_p]),
     "gac_buffer_create": (C.c_int, [C.c_void_p, fpp, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     "gac_buffer_destroy": (C.c_int, [C.c_void_p]),
     "gac_ir_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

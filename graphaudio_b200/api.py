@@ -292,7 +292,8 @@ class ConvolverNode(AudioNode):
 class OfflineAudioContext:
     """OfflineAudioContext.cs — `Render` is the one call that crosses into libgraphaudio_cuda.so."""
 
-    def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32, _record_only=False):
+    def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32, async_upload=False,
+                 _record_only=False):
         """partition / device_id / mac_variant / tile_blocks map onto gac_context_desc.  `_record_only=True` builds a context
         without a device handle: nodes, automation and topology can be recorded and inspected (`_topology()`), Render raises.
         It exists for the CPU unit tests of the host-side logic; it is not a fallback."""
@@ -307,7 +308,10 @@ class OfflineAudioContext:
         if not self._record_only:
             desc = N.gac_context_desc()
             desc.sample_rate, desc.quantum, desc.partition, desc.device_id, desc.mac_variant = self.SampleRate, 128, partition, device_id, mac_variant
-            desc.reserved[0] = tile_blocks
+            desc.tile_blocks = tile_blocks
+            # async_upload: page-locked source arrays are uploaded asynchronously (GAC_FLAG_ASYNC_UPLOAD); the arrays handed
+            # to PlayableAudioBuffer must then stay untouched until Render returns
+            desc.flags = N.GAC_FLAG_ASYNC_UPLOAD if async_upload else 0
             out = C.c_void_p()
             check(N.lib().gac_context_create(C.byref(desc), C.byref(out)))
             self._h = out.value

@@ -86,6 +86,10 @@ struct gac_context {
   void* comm = nullptr;
   int rank = 0, n_ranks = 1;
   size_t scratch_budget = (size_t)24 << 30;
+  // opt-in asynchronous uploads (GAC_FLAG_ASYNC_UPLOAD): H2D copies run on their own stream and overlap IR
+  // preparation and the first voice batches of the next render
+  bool async_upload = false;
+  cudaStream_t copy_stream = nullptr;
 };
 struct gac_buffer {
   gac_context* ctx;
@@ -94,7 +98,12 @@ struct gac_buffer {
   int rate;
   float* d = nullptr;  // [nch][stride]
   int64_t stride;
+  cudaEvent_t ready = nullptr;  // async upload: recorded on the copy stream behind the last H2D copy
 };
+// orders the context stream behind a buffer's (possibly still running) upload
+static inline void wait_ready(gac_context* ctx, const gac_buffer* b) {
+  if (b && b->ready) cudaStreamWaitEvent(ctx->stream, b->ready, 0);
+}
 struct gac_ir {
   gac_context* ctx;
   int nch;
@@ -245,9 +254,9 @@ static int ensure_block_times(gac_context* ctx, int64_t nq) {
     t = t + inc;
     ctx->h_bt.push_back(t);
   }
-  if (ctx->d_bt) cudaFree(ctx->d_bt);
-  CU(cudaMalloc(&ctx->d_bt, ctx->h_bt.size() * sizeof(double)));
-  CU(cudaMemcpy(ctx->d_bt, ctx->h_bt.data(), ctx->h_bt.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (ctx->d_bt) cudaFreeAsync(ctx->d_bt, ctx->stream);
+  CU(cudaMallocAsync(&ctx->d_bt, ctx->h_bt.size() * sizeof(double), ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_bt, ctx->h_bt.data(), ctx->h_bt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   ctx->bt_cap = (int64_t)ctx->h_bt.size();
   return GAC_OK;
 }
@@ -266,22 +275,39 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   int dev = desc->device_id;
   if (dev < 0) CU(cudaGetDevice(&dev));
   if (dev >= ndev) return fail(GAC_ERR_OUT_OF_RANGE, "device_id %d out of range (%d devices)", dev, ndev);
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) return fail(GAC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+  // per-device facts are queried once per process (cudaGetDeviceProperties / cudaMemGetInfo cost milliseconds)
+  struct DevInfo {
+    bool known = false;
+    int major = 0, minor = 0;
+    size_t budget = (size_t)24 << 30;
+  };
+  static DevInfo dev_info[64];
+  if (dev >= 64) return fail(GAC_ERR_OUT_OF_RANGE, "device_id %d not supported", dev);
+  DevInfo& di = dev_info[dev];
   CU(cudaSetDevice(dev));
+  if (!di.known) {
+    CU(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, dev));
+    CU(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, dev));
+    // keep freed scratch in the pool between renders
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) di.budget = std::max<size_t>((size_t)1 << 30, free_b / 3);
+    di.known = true;
+  }
+  if (di.major != 10) return fail(GAC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, di.major, di.minor);
   auto ctx = std::make_unique<gac_context>();
   ctx->device = dev;
   ctx->fs = desc->sample_rate;
   ctx->B = B;
   ctx->mac_variant = desc->mac_variant;
-  ctx->tile_blocks = desc->reserved[0] == 64 ? 64 : 32;
+  ctx->tile_blocks = desc->tile_blocks == 64 ? 64 : 32;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  // keep freed scratch in the pool between renders
-  cudaMemPool_t pool;
-  CU(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t thr = UINT64_MAX;
-  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  ctx->async_upload = (desc->flags & GAC_FLAG_ASYNC_UPLOAD) != 0;
+  if (ctx->async_upload) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  ctx->scratch_budget = di.budget;
   // twiddles e^{-2 pi i k / N}, N = 2B, in double then rounded once
   std::vector<float2> tw(B);
   const double pi = 3.14159265358979323846;
@@ -289,13 +315,19 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
     double a = -2.0 * pi * (double)k / (double)(2 * B);
     tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
   }
-  CU(cudaMalloc(&ctx->d_tw, sizeof(float2) * B));
-  CU(cudaMemcpy(ctx->d_tw, tw.data(), sizeof(float2) * B, cudaMemcpyHostToDevice));
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->scratch_budget = std::max<size_t>((size_t)1 << 30, free_b / 3);
+  CU(cudaMallocAsync(&ctx->d_tw, sizeof(float2) * B, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_tw, tw.data(), sizeof(float2) * B, cudaMemcpyHostToDevice, ctx->stream));  // pageable: staged before return
   int rc = ensure_block_times(ctx.get(), 8192);
   if (rc) return rc;
   *out = ctx.release();
+  return GAC_OK;
+}
+
+extern "C" int gac_synchronize(gac_context* ctx) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return GAC_OK;
 }
 
@@ -305,8 +337,13 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) gac_comm_destroy(ctx);
-  cudaFree(ctx->d_tw);
-  cudaFree(ctx->d_bt);
+  if (ctx->d_tw) cudaFreeAsync(ctx->d_tw, ctx->stream);
+  if (ctx->d_bt) cudaFreeAsync(ctx->d_bt, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaStreamDestroy(ctx->stream);
   ctx->magic = 0;
   delete ctx;
@@ -331,11 +368,29 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
   b->n = n_frames;
   b->rate = sample_rate;
   b->stride = ((n_frames + 8 + 63) / 64) * 64;  // a little slack so 4-tap reads never leave the allocation
-  CU(cudaMallocAsync(&b->d, sizeof(float) * b->stride * n_channels, ctx->stream));
-  CU(cudaMemsetAsync(b->d, 0, sizeof(float) * b->stride * n_channels, ctx->stream));
+  // Asynchronous path (opt-in, and only for page-locked sources — pageable copies are staged synchronously by the
+  // runtime anyway): the copy is queued on the copy stream and the call returns; the arrays must stay valid and
+  // unmodified until the next gac_render* / gac_synchronize returns.
+  bool async = ctx->async_upload;
+  if (async) {
+    for (int c = 0; c < n_channels && async; c++) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, channels[c]) != cudaSuccess || attr.type != cudaMemoryTypeHost) async = false;
+      cudaGetLastError();
+    }
+  }
+  cudaStream_t st = async ? ctx->copy_stream : ctx->stream;
+  CU(cudaMallocAsync(&b->d, sizeof(float) * b->stride * n_channels, st));
+  // the slack behind each channel is never read: k_source_copy stays inside [0, n) and the resampler's taps are the last
+  // four CONSUMED frames (k + 3 <= n - 1)
   for (int c = 0; c < n_channels; c++)
-    CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));  // the caller may reuse its arrays as soon as we return
+    CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, st));
+  if (async) {
+    CU(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(b->ready, st));
+  } else {
+    CU(cudaStreamSynchronize(st));  // the caller may reuse its arrays as soon as we return
+  }
   *out = b.release();
   return GAC_OK;
 }
@@ -343,6 +398,10 @@ extern "C" int gac_buffer_destroy(gac_buffer* buf) {
   if (!buf) return fail(GAC_ERR_INVALID_ARGUMENT, "buffer is null");
   cudaSetDevice(buf->ctx->device);
   // stream-ordered free: safe behind any render still queued on the context stream
+  if (buf->ready) {
+    cudaStreamWaitEvent(buf->ctx->stream, buf->ready, 0);
+    cudaEventDestroy(buf->ready);
+  }
   cudaFreeAsync(buf->d, buf->ctx->stream);
   delete buf;
   return GAC_OK;
@@ -358,47 +417,25 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   const int B = ctx->B;
   ir->P = (int)((frames + B - 1) / B);  // ceil(L / blockSize)  PartitionedConvolver.cs:44
   ir->P16 = std::max(16, ((ir->P + 15) / 16) * 16);
-  CU(cudaMallocAsync(&ir->d_H, sizeof(float2) * (size_t)nch * ir->P16 * B, ctx->stream));
-  CU(cudaMemsetAsync(ir->d_H, 0, sizeof(float2) * (size_t)nch * ir->P16 * B, ctx->stream));
-  CU(cudaMallocAsync(&ir->d_scale, sizeof(float) * nch, ctx->stream));
-  std::vector<const float*> chp(nch);
-  for (int c = 0; c < nch; c++) chp[c] = d_ir + c * stride;
-  const float** d_chp = nullptr;
-  CU(cudaMallocAsync(&d_chp, sizeof(float*) * nch, ctx->stream));
-  int rc = upload_now(ctx, d_chp, chp.data(), sizeof(float*) * nch);
-  if (rc) return rc;
-  if (normalize && frames > 0) {
-    // (float)Math.Pow(10, GainCalibration * 0.05f) with GainCalibration = -58  (PartitionedConvolver.cs:95,101)
-    const float cal = (float)std::pow(10.0, (double)(-58.f * 0.05f));
-    launch_ir_scale(d_chp, nch, frames, cal, ir->d_scale, ctx->stream);
-  } else {
-    std::vector<float> ones(nch, 1.0f);
-    rc = upload_now(ctx, ir->d_scale, ones.data(), sizeof(float) * nch);
-    if (rc) return rc;
-    // (pageable source: the copy is staged before cudaMemcpyAsync returns)
-  }
-  std::vector<FftFwdJob> jobs(nch);
-  for (int c = 0; c < nch; c++) {
-    FftFwdJob& j = jobs[c];
-    j.in = d_ir + c * stride;
-    j.out = ir->d_H + (size_t)c * ir->P16 * B;
-    j.scale = ir->d_scale + c;
-    j.gain = nullptr;
-    j.gain_const = 1.0f;
-    j.n_valid = frames;
-    j.n_blocks = ir->P;
-    j.gate_lo = 0;
-    j.gate_hi = std::numeric_limits<int64_t>::max();
-  }
-  FftFwdJob* d_jobs = nullptr;
-  CU(cudaMallocAsync(&d_jobs, sizeof(FftFwdJob) * nch, ctx->stream));
-  rc = upload_now(ctx, d_jobs, jobs.data(), sizeof(FftFwdJob) * nch);
-  if (rc) return rc;
-  launch_rfft_fwd(d_jobs, nch, ir->P, B, ctx->d_tw, ctx->stream);
+  // one stream-ordered allocation: spectra [nch][P16][B] float2 followed by the per-channel scales
+  const size_t hbytes = sizeof(float2) * (size_t)nch * ir->P16 * B;
+  CU(cudaMallocAsync(&ir->d_H, hbytes + sizeof(float) * nch, ctx->stream));
+  ir->d_scale = reinterpret_cast<float*>(reinterpret_cast<char*>(ir->d_H) + hbytes);
+  CU(cudaMemsetAsync(ir->d_H, 0, hbytes, ctx->stream));  // rows >= P stay zero (the tiled MAC reads P16 rows)
+  // (float)Math.Pow(10, GainCalibration * 0.05f) with GainCalibration = -58  (PartitionedConvolver.cs:95,101)
+  const float cal = (float)std::pow(10.0, (double)(-58.f * 0.05f));
+  launch_ir_scale(d_ir, stride, nch, frames, normalize && frames > 0 ? 1 : 0, cal, ir->d_scale, ctx->stream);
+  FftFwdUniform u;
+  u.in_base = d_ir;
+  u.in_stride = stride;
+  u.out_base = ir->d_H;
+  u.out_stride = (int64_t)ir->P16 * B;
+  u.scale_base = ir->d_scale;
+  u.n_valid = frames;
+  u.n_blocks = ir->P;
+  launch_rfft_fwd_uniform(u, nch, B, ctx->d_tw, ctx->stream);
   CU(cudaGetLastError());
   // no host synchronisation: every later use of the spectra is ordered on the same stream
-  cudaFreeAsync(d_jobs, ctx->stream);
-  cudaFreeAsync(d_chp, ctx->stream);
   return GAC_OK;
 }
 
@@ -421,10 +458,10 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
   ir->nch = buf->nch;
   ir->true_stereo = ts;
   ir->frames = buf->n;
+  wait_ready(ctx, buf);
   int rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get());
   if (rc) {
     if (ir->d_H) cudaFreeAsync(ir->d_H, ctx->stream);
-    if (ir->d_scale) cudaFreeAsync(ir->d_scale, ctx->stream);
     return rc;
   }
   *out = ir.release();
@@ -435,7 +472,6 @@ extern "C" int gac_ir_destroy(gac_ir* ir) {
   cudaSetDevice(ir->ctx->device);
   // stream-ordered free
   cudaFreeAsync(ir->d_H, ir->ctx->stream);
-  cudaFreeAsync(ir->d_scale, ir->ctx->stream);
   delete ir;
   return GAC_OK;
 }

@@ -28,6 +28,7 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
     const VoiceH& v = *voices[i];
     Sig& s = sigs[i];
     const gac_buffer* buf = v.src;
+    wait_ready(ctx, buf);  // asynchronous upload still in flight: order this voice batch behind it
     s.lo = s.hi = 0;
     const float* src0 = buf->d;
     const float* src1 = buf->nch > 1 ? buf->d + buf->stride : buf->d;  // mono: 1 -> 2 up-mix copies the channel (AudioNodeInput.cs:201-213)
@@ -345,8 +346,22 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     sigs[i].p[1] = d_sig + (i * 2 + 1) * (size_t)env.Npad;
     sigs[i].ops = &voices[i]->ops;
   }
-  if ((rc = plan_sources(env, voices, sigs))) return rc;
-  if ((rc = run_chains(env, sigs))) return rc;
+  // With asynchronous uploads some source buffers may still be in flight: process the voices in a few batches so that
+  // the first ones (whose data has landed) run while the copy engine delivers the rest.  Otherwise one batch.
+  size_t n_pending = 0;
+  for (auto* v : voices)
+    if (v->src->ready && cudaEventQuery(v->src->ready) == cudaErrorNotReady) n_pending++;
+  cudaGetLastError();
+  const size_t n_batches = (n_pending > 0 && S >= 16) ? 4 : 1;
+  for (size_t bi = 0; bi < n_batches; bi++) {
+    const size_t v0 = S * bi / n_batches, v1 = S * (bi + 1) / n_batches;
+    if (v1 <= v0) continue;
+    std::vector<const VoiceH*> vsub(voices.begin() + v0, voices.begin() + v1);
+    std::vector<Sig> ssub(sigs.begin() + v0, sigs.begin() + v1);
+    if ((rc = plan_sources(env, vsub, ssub))) return rc;
+    if ((rc = run_chains(env, ssub))) return rc;
+    std::copy(ssub.begin(), ssub.end(), sigs.begin() + v0);
+  }
 
   // ---- buses: fan-in in connection (= voice index) order, AudioNodeInput.cs:118-137
   size_t NB = 0;
@@ -679,9 +694,8 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
   irh.ctx = ctx;
   irh.nch = n_signals;
   rc = ir_prepare_device(ctx, dir.as<float>(), stride, n_signals, ir_frames, normalize != 0, &irh);
-  DevBuf holdH, holdS;
-  holdH.p = irh.d_H;
-  holdS.p = irh.d_scale;
+  DevBuf holdH;
+  holdH.p = irh.d_H;  // (the scales live at the end of the same allocation)
   if (rc) return rc;
   DevBuf dx;
   if ((rc = dev_alloc(dx, (size_t)n_signals * Npad * 4))) return rc;

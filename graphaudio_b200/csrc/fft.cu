@@ -105,12 +105,35 @@ constexpr int kFftWarps = 4;  // warps (= concurrent transforms) per CTA
 // grid = (ceil(max_blocks / (kFftWarps*BLOCKS_PER_WARP)), n_jobs)
 // --------------------------------------------------------------------------------------------
 template <int LOG2H, int BPW>
+__device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2* __restrict__ tw);
+
+template <int LOG2H, int BPW>
 __global__ void __launch_bounds__(kFftWarps * 32) k_rfft_fwd(const FftFwdJob* __restrict__ jobs, const float2* __restrict__ tw) {
+  const FftFwdJob job = jobs[blockIdx.y];
+  rfft_fwd_body<LOG2H, BPW>(job, tw);
+}
+// same transform, jobs described arithmetically (no job array in HBM): channel y of one buffer.  Used by IR preparation.
+template <int LOG2H, int BPW>
+__global__ void __launch_bounds__(kFftWarps * 32) k_rfft_fwd_uniform(FftFwdUniform u, const float2* __restrict__ tw) {
+  FftFwdJob job;
+  job.in = u.in_base + (int64_t)blockIdx.y * u.in_stride;
+  job.out = u.out_base + (int64_t)blockIdx.y * u.out_stride;
+  job.scale = u.scale_base ? u.scale_base + blockIdx.y : nullptr;
+  job.gain = nullptr;
+  job.gain_const = 1.0f;
+  job.n_valid = u.n_valid;
+  job.n_blocks = u.n_blocks;
+  job.gate_lo = 0;
+  job.gate_hi = INT64_MAX;
+  rfft_fwd_body<LOG2H, BPW>(job, tw);
+}
+
+template <int LOG2H, int BPW>
+__device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2* __restrict__ tw) {
   using F = WarpFft<LOG2H>;
   constexpr int H = F::H, R = F::R;
   __shared__ float2 tile[kFftWarps][H + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const FftFwdJob job = jobs[blockIdx.y];
   F fft;
   fft.init(tw, lane);
   float2 twk[R];  // split twiddles e^{-2 pi i k / N}, k = lane + 32 j
@@ -267,6 +290,21 @@ static void launch_inv_t(const FftInvJob* jobs, int n_jobs, int64_t max_blocks, 
   constexpr int BPW = 16;
   dim3 grid((unsigned)((max_blocks + kFftWarps * BPW - 1) / (kFftWarps * BPW)), (unsigned)n_jobs);
   k_irfft_ola<LOG2H, BPW><<<grid, kFftWarps * 32, 0, s>>>(jobs, tw);
+}
+
+template <int LOG2H>
+static void launch_fwd_uniform_t(const FftFwdUniform& u, int n_jobs, const float2* tw, cudaStream_t s) {
+  constexpr int BPW = 4;
+  dim3 grid((unsigned)((u.n_blocks + kFftWarps * BPW - 1) / (kFftWarps * BPW)), (unsigned)n_jobs);
+  k_rfft_fwd_uniform<LOG2H, BPW><<<grid, kFftWarps * 32, 0, s>>>(u, tw);
+}
+void launch_rfft_fwd_uniform(const FftFwdUniform& u, int n_jobs, int B, const float2* d_tw, cudaStream_t s) {
+  if (n_jobs <= 0 || u.n_blocks <= 0) return;
+  switch (B) {
+    case 128: launch_fwd_uniform_t<7>(u, n_jobs, d_tw, s); break;
+    case 256: launch_fwd_uniform_t<8>(u, n_jobs, d_tw, s); break;
+    case 512: launch_fwd_uniform_t<9>(u, n_jobs, d_tw, s); break;
+  }
 }
 
 void launch_rfft_fwd(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s) {

@@ -27,6 +27,16 @@ struct FftFwdJob {
   int64_t gate_lo, gate_hi;  // samples outside [gate_lo, gate_hi) read as zero (silent-flagged quanta)
 };
 void launch_rfft_fwd(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
+// the same transform for the channels of ONE buffer, described arithmetically and passed by value (no job array upload)
+struct FftFwdUniform {
+  const float* in_base;     // channel y at in_base + y*in_stride
+  int64_t in_stride;
+  float2* out_base;         // channel y at out_base + y*out_stride
+  int64_t out_stride;
+  const float* scale_base;  // channel y's scale at scale_base[y], or nullptr
+  int64_t n_valid, n_blocks;
+};
+void launch_rfft_fwd_uniform(const FftFwdUniform& u, int n_jobs, int B, const float2* d_tw, cudaStream_t s);
 
 struct FftInvJob {
   const float2* in;  // packed spectra, block b at in + b*B
@@ -133,7 +143,9 @@ struct MixInput {
 void launch_mix(const MixJob* d_jobs, int n_jobs, const MixInput* d_inputs, int64_t n_frames, cudaStream_t s);
 
 // IR preparation (PartitionedConvolver.cs:93-102): scale[ch] from the channel's RMS
-void launch_ir_scale(const float* const* d_channels, int n_channels, int64_t n_frames, float calibration, float* d_scale, cudaStream_t s);
+// channel c at d_base + c*stride; normalize == 0 writes 1.0
+void launch_ir_scale(const float* d_base, int64_t stride, int n_channels, int64_t n_frames, int normalize, float calibration, float* d_scale,
+                     cudaStream_t s);
 
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
 

@@ -201,9 +201,13 @@ void launch_mix(const MixJob* d_jobs, int n_jobs, const MixInput* d_inputs, int6
 // ============================================================================================ K0
 // scale = (1 / max(rms, 1.25e-4)) * calibration ; rms via a double sum of float32 squares (PartitionedConvolver.cs:93-102).
 // The reference sums sequentially; a tree sum in double differs by ~1e-16 relative, far below float32 resolution.
-__global__ void __launch_bounds__(1024) k_ir_scale(const float* const* __restrict__ channels, int64_t n_frames, float calibration,
-                                                   float* __restrict__ scale) {
-  const float* r = channels[blockIdx.x];
+__global__ void __launch_bounds__(1024) k_ir_scale(const float* __restrict__ base, int64_t stride, int64_t n_frames, int normalize,
+                                                   float calibration, float* __restrict__ scale) {
+  if (!normalize) {  // Normalize = false: scale stays 1 (PartitionedConvolver.cs:67-68)
+    if (threadIdx.x == 0) scale[blockIdx.x] = 1.0f;
+    return;
+  }
+  const float* r = base + (int64_t)blockIdx.x * stride;
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < n_frames; i += 1024) {
     float sq = r[i] * r[i];  // float * float (:98)
@@ -223,9 +227,10 @@ __global__ void __launch_bounds__(1024) k_ir_scale(const float* const* __restric
     }
   }
 }
-void launch_ir_scale(const float* const* d_channels, int n_channels, int64_t n_frames, float calibration, float* d_scale, cudaStream_t s) {
+void launch_ir_scale(const float* d_base, int64_t stride, int n_channels, int64_t n_frames, int normalize, float calibration, float* d_scale,
+                     cudaStream_t s) {
   if (n_channels <= 0) return;
-  k_ir_scale<<<n_channels, 1024, 0, s>>>(d_channels, n_frames, calibration, d_scale);
+  k_ir_scale<<<n_channels, 1024, 0, s>>>(d_base, stride, n_frames, normalize, calibration, d_scale);
 }
 
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s) { cudaMemsetAsync(p, 0, bytes, s); }

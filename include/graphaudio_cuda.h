@@ -58,13 +58,25 @@ typedef struct gac_context_desc {
                       ConvolverNode uses, ConvolverNode.cs:55) or 256/512 (offline-only option;
                       same linear convolution, different rounding points).  0 = 128.                 */
   int device_id;   /* CUDA ordinal; -1 = current device                                              */
-  int mac_variant; /* 0 = default (register-tiled), 1 = streaming one-pass-per-quantum (reference
-                      op order, unfused; the T=1 roofline contract of SURVEY.md §8d)                 */
-  int reserved[3];
+  int mac_variant; /* 0 = default (register-tiled, packed FFMA2), 2 = register-tiled scalar FFMA,
+                      1 = streaming one-pass-per-quantum (reference op order, unfused; the T=1
+                      roofline contract of SURVEY.md §8d)                                            */
+  int tile_blocks; /* output blocks per CTA of the tiled MAC: 32 (default, 0) or 64                  */
+  int flags;       /* GAC_FLAG_*                                                                     */
+  int reserved;
 } gac_context_desc;
+
+/* Asynchronous uploads: when set AND the arrays passed to gac_buffer_create are page-locked (cudaHostAlloc /
+ * cudaHostRegister), the host->device copy is queued on a copy stream and gac_buffer_create returns at once; the
+ * arrays must stay valid and unmodified until the next gac_render* / gac_synchronize on the context returns.  IR
+ * preparation and the first voice batches of the render overlap the remaining copies.  Default (flag clear): the
+ * reference's semantics — the data is copied during the call (PlayableAudioBuffer.cs:84-93). */
+#define GAC_FLAG_ASYNC_UPLOAD 1
 
 int gac_context_create(const gac_context_desc* desc, gac_context** out);
 int gac_context_destroy(gac_context* ctx);
+/* Blocks until every queued upload and render of the context has finished. */
+int gac_synchronize(gac_context* ctx);
 
 /* ---- buffers ≙ PlayableAudioBuffer.FromChannelArrays (PlayableAudioBuffer.cs:122-143) ----
  * `channels` are caller-owned host arrays, copied (to HBM) during the call, as CopyToChannel

@@ -509,7 +509,7 @@ static int copy_ops(gac_context* ctx, int n, const gac_op_desc* ops, std::vector
       case GAC_OP_CONVOLVER:
         o.ir = ops[i].ir;
         if (o.ir && o.ir->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "impulse response belongs to another context");
-        if (o.ir && o.ir->nch != 2) return fail(GAC_ERR_UNSUPPORTED, "only stereo impulse responses are on the accelerated graph path in this version (mono / true-stereo: SURVEY.md 8f-1)");
+        if (o.ir && !(o.ir->nch == 1 || o.ir->nch == 2 || (o.ir->nch == 4 && o.ir->true_stereo))) return fail(GAC_ERR_UNSUPPORTED, "discrete impulse responses with %d channels are outside the accelerated path", o.ir->nch);
         break;
       default:
         return fail(GAC_ERR_INVALID_ARGUMENT, "unknown op kind %d", o.kind);
@@ -575,6 +575,7 @@ extern "C" int gac_graph_destroy(gac_graph* g) {
 struct Sig {
   float* p[2];
   int64_t lo = 0, hi = 0;  // frames flagged non-silent (multiples of 128)
+  int ch = 2;              // logical channel count of the block the reference would carry here (rows are always 2; mono = duplicated)
   const std::vector<OpH>* ops = nullptr;
 };
 
@@ -630,14 +631,34 @@ static int run_param_jobs(RenderEnv& env, std::vector<ParamJob>& jobs) {
   return GAC_OK;
 }
 
-// ---- the convolver: K5 -> K6 -> K7 for a list of channel-convolvers (one PartitionedConvolver each)
+// ---- the convolver: K5 -> K6 -> K7.  One ConvItem = one ConvolverNode instance of one signal
+// (Nodes/ConvolverNode.cs:102-155): 1-2 forward transforms, 1-4 channel-convolvers (PartitionedConvolver each),
+// 1-2 inverse transforms.
+//   stereo IR     : fwd L, R        mac (L,H0) (R,H1)                    inv Y0 -> L ; Y1 -> R              (:145-151)
+//   mono IR       : fwd (L+R)/sqrt2 mac (M,H0)                           inv Y0 -> L and R (1 -> 2 up-mix)   (AudioNodeInput.cs:214-228, 201-213)
+//   true stereo   : fwd L, R        mac (L,H0) (R,H2) (L,H1) (R,H3)      inv Y0+Y1 -> L ; Y2+Y3 -> R         (:127-144)
 struct ConvItem {
-  float* x;               // time-domain channel, convolved in place
-  const float2* H;        // packed IR spectra [P16][B]
-  int P;
-  int64_t lo, hi;         // non-silent input frames
-  const float* gain_tab;  // fused preceding GainNode (may be null)
-  float gain_const;
+  int n_fwd = 0;
+  struct {
+    const float* in;
+    const float* in2;  // down-mix partner or nullptr
+    float mix_scale;
+  } fwd[2];
+  int64_t lo = 0, hi = 0;            // non-silent input frames
+  const float* gain_tab = nullptr;   // fused preceding GainNode (may be null)
+  float gain_const = 1.0f;
+  int n_mac = 0;
+  struct {
+    int x;            // which forward spectrum feeds this channel-convolver
+    const float2* H;  // packed IR spectra [P16][B]
+  } mac[4];
+  int P = 0;
+  int n_inv = 0;
+  struct {
+    int y, y2;        // spectrogram(s) of which channel-convolver(s); y2 = -1: none
+    float* out;
+    float* out2;      // duplicate destination or nullptr
+  } inv[2];
 };
 
 static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
@@ -648,35 +669,40 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
   const int64_t QBpad = ((QB + TB - 1) / TB) * TB;
   const int64_t rowsX = TB + QBpad;  // TB zero rows in front (blocks -TB..-1)
   const int groups = B / 128;
-  // sub-batches bounded by the scratch budget
-  const size_t per_ch = (size_t)(rowsX + QBpad) * B * sizeof(float2);
-  size_t max_items = std::max<size_t>(2, ctx->scratch_budget / per_ch);
-  for (size_t i0 = 0; i0 < items.size(); i0 += max_items) {
-    const size_t ni = std::min(max_items, items.size() - i0);
-    const size_t nch = ni;
+  // sub-batches bounded by the scratch budget (an item needs up to 2 X and 4 Y spectrograms)
+  const size_t xbytes = (size_t)rowsX * B * sizeof(float2), ybytes = (size_t)QBpad * B * sizeof(float2);
+  for (size_t i0 = 0; i0 < items.size();) {
+    size_t ni = 0, nx = 0, ny = 0;
+    while (i0 + ni < items.size()) {
+      const ConvItem& it = items[i0 + ni];
+      if (ni > 0 && (nx + it.n_fwd) * xbytes + (ny + it.n_mac) * ybytes > ctx->scratch_budget) break;
+      nx += it.n_fwd;
+      ny += it.n_mac;
+      ni++;
+    }
     float2 *dX = nullptr, *dY = nullptr;
-    int rc = env.scratch->alloc(&dX, nch * rowsX * B);
+    int rc = env.scratch->alloc(&dX, nx * rowsX * B);
     if (rc) return rc;
-    rc = env.scratch->alloc(&dY, nch * QBpad * B);
+    rc = env.scratch->alloc(&dY, ny * QBpad * B);
     if (rc) return rc;
     // zero the front pad and the tail rows of X (rows the forward FFT does not write)
-    CU(cudaMemset2DAsync(dX, (size_t)rowsX * B * sizeof(float2), 0, (size_t)TB * B * sizeof(float2), nch, ctx->stream));
+    CU(cudaMemset2DAsync(dX, xbytes, 0, (size_t)TB * B * sizeof(float2), nx, ctx->stream));
     if (QBpad > QB)
-      CU(cudaMemset2DAsync(dX + (size_t)(TB + QB) * B, (size_t)rowsX * B * sizeof(float2), 0, (size_t)(QBpad - QB) * B * sizeof(float2), nch, ctx->stream));
+      CU(cudaMemset2DAsync(dX + (size_t)(TB + QB) * B, xbytes, 0, (size_t)(QBpad - QB) * B * sizeof(float2), nx, ctx->stream));
     auto& fj = env.keep->make<FftFwdJob>();
     auto& mj = env.keep->make<MacJob>();
     auto& ij = env.keep->make<FftInvJob>();
     auto& tiles = env.keep->make<MacTile>();
+    size_t xi = 0, yi = 0;
     for (size_t i = 0; i < ni; i++) {
       ConvItem& it = items[i0 + i];
-      {
-        const size_t ch = i;
-        float2* Xc = dX + ch * rowsX * B + (size_t)TB * B;  // row 0
-        float2* Yc = dY + ch * QBpad * B;
-        const float2* Hc = it.H;
+      float2* Xc[2] = {nullptr, nullptr};
+      float2* Yc[4] = {nullptr, nullptr, nullptr, nullptr};
+      for (int k = 0; k < it.n_fwd; k++) {
+        Xc[k] = dX + (xi++) * rowsX * B + (size_t)TB * B;  // row 0
         FftFwdJob f;
-        f.in = it.x;
-        f.out = Xc;
+        f.in = it.fwd[k].in;
+        f.out = Xc[k];
         f.scale = nullptr;
         f.gain = it.gain_tab;
         f.gain_const = it.gain_const;
@@ -684,25 +710,34 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
         f.n_blocks = QB;
         f.gate_lo = it.lo;
         f.gate_hi = it.hi;
+        f.in2 = it.fwd[k].in2;
+        f.mix_scale = it.fwd[k].mix_scale;
         fj.push_back(f);
+      }
+      for (int k = 0; k < it.n_mac; k++) {
+        Yc[k] = dY + (yi++) * QBpad * B;
         for (int g = 0; g < groups; g++) {
           MacJob m;
-          m.X = Xc + g * 128;
-          m.H = Hc + g * 128;
-          m.Y = Yc + g * 128;
+          m.X = Xc[it.mac[k].x] + g * 128;
+          m.H = it.mac[k].H + g * 128;
+          m.Y = Yc[k] + g * 128;
           m.P = it.P;
           m.has_dc = (g == 0);
           mj.push_back(m);
         }
-        FftInvJob v;
-        v.in = Yc;
-        v.out = it.x;
-        v.n_blocks = QB;
-        ij.push_back(v);
         // accounting: one unit = one channel-convolver block of B frames through P partitions
         const double P = it.P, C = B + 1;
         env.conv_units += QB;
         env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
+      }
+      for (int k = 0; k < it.n_inv; k++) {
+        FftInvJob v;
+        v.in = Yc[it.inv[k].y];
+        v.out = it.inv[k].out;
+        v.n_blocks = QB;
+        v.in2 = it.inv[k].y2 >= 0 ? Yc[it.inv[k].y2] : nullptr;
+        v.out2 = it.inv[k].out2;
+        ij.push_back(v);
       }
     }
     // tiles, heaviest first (stable: tiles of one job stay adjacent for L2 reuse of its H and X rows)
@@ -741,6 +776,7 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
     env.timer->end(t);
     CU(cudaGetLastError());
     env.launches += (ctx->mac_variant == 1) ? 3 : 4;  // K5, K6 (+ k_mac_dc), K7
+    i0 += ni;
   }
   return GAC_OK;
 }
@@ -773,6 +809,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       auto& gj = env.keep->make<GainJob>();
       for (size_t k = 0; k < gains.size(); k++) {
         Sig& s = sigs[gains[k]];
+        s.ch = 2;  // the node's input is Max-mode with channelCount 2: a mono upstream is up-mixed by copy (AudioNodeInput.cs:157-166,201-213)
         const auto& ops = *s.ops;
         const bool next_is_conv = pos + 1 < ops.size() && ops[pos + 1].kind == GAC_OP_CONVOLVER && ops[pos + 1].ir;
         if (next_is_conv) {
@@ -821,6 +858,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         }
         for (size_t k = 0; k < nk; k++) {
           Sig& s = sigs[biquads[k0 + k]];
+          s.ch = 2;
           const OpH& op = (*s.ops)[pos];
           BiquadJob j{};
           float *tf = nullptr, *tq = nullptr, *tg = nullptr;
@@ -887,17 +925,51 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           gconst = f->second.second;
           env.fused.erase(f);
         }
-        for (int c = 0; c < 2; c++) {
-          ConvItem it;
-          it.x = s.p[c];
-          it.H = op.ir->d_H + (size_t)c * op.ir->P16 * ctx->B;
-          it.P = op.ir->P;
-          it.lo = s.lo;
-          it.hi = s.hi;
-          it.gain_tab = gtab;
-          it.gain_const = gconst;
-          items.push_back(it);
+        const gac_ir* ir = op.ir;
+        auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
+        ConvItem it;
+        it.P = ir->P;
+        it.lo = s.lo;
+        it.hi = s.hi;
+        it.gain_tab = gtab;
+        it.gain_const = gconst;
+        if (ir->nch == 1) {
+          // input forced to 1 channel (ConvolverNode.cs:72-76): a stereo upstream is down-mixed (L + R) * (1/sqrt(2)),
+          // a mono upstream is taken as is (AudioNodeInput.cs:188-228); the mono result is copied to both rows
+          it.n_fwd = 1;
+          it.fwd[0] = {s.p[0], s.ch == 2 ? s.p[1] : nullptr, 1.0f / sqrtf(2.0f)};
+          it.n_mac = 1;
+          it.mac[0] = {0, Hch(0)};
+          it.n_inv = 1;
+          it.inv[0] = {0, -1, s.p[0], s.p[1]};
+          s.ch = 1;
+        } else if (ir->nch == 2) {
+          it.n_fwd = 2;
+          it.fwd[0] = {s.p[0], nullptr, 1.0f};
+          it.fwd[1] = {s.p[1], nullptr, 1.0f};
+          it.n_mac = 2;
+          it.mac[0] = {0, Hch(0)};
+          it.mac[1] = {1, Hch(1)};
+          it.n_inv = 2;
+          it.inv[0] = {0, -1, s.p[0], nullptr};
+          it.inv[1] = {1, -1, s.p[1], nullptr};
+          s.ch = 2;
+        } else {
+          // true stereo (ConvolverNode.cs:127-144): L = c0(inL) + c2(inR), R = c1(inL) + c3(inR); X spectra shared
+          it.n_fwd = 2;
+          it.fwd[0] = {s.p[0], nullptr, 1.0f};
+          it.fwd[1] = {s.p[1], nullptr, 1.0f};
+          it.n_mac = 4;
+          it.mac[0] = {0, Hch(0)};
+          it.mac[1] = {1, Hch(2)};
+          it.mac[2] = {0, Hch(1)};
+          it.mac[3] = {1, Hch(3)};
+          it.n_inv = 2;
+          it.inv[0] = {0, 1, s.p[0], nullptr};
+          it.inv[1] = {2, 3, s.p[1], nullptr};
+          s.ch = 2;
         }
+        items.push_back(it);
         s.lo = 0;  // ConvolverNode always marks its output non-silent (ConvolverNode.cs:153)
         s.hi = env.Npad;
       }

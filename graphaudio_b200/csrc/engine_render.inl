@@ -30,6 +30,7 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
     const gac_buffer* buf = v.src;
     wait_ready(ctx, buf);  // asynchronous upload still in flight: order this voice batch behind it
     s.lo = s.hi = 0;
+    s.ch = buf->nch;  // the source emits a block with the buffer's channel count (AudioBufferSourceNode.cs:157-163)
     const float* src0 = buf->d;
     const float* src1 = buf->nch > 1 ? buf->d + buf->stride : buf->d;  // mono: 1 -> 2 up-mix copies the channel (AudioNodeInput.cs:201-213)
     SourceJob job{};
@@ -716,7 +717,19 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
     env.QB = Npad / B;
     std::vector<ConvItem> items(n_signals);
     for (int s = 0; s < n_signals; s++)
-      items[s] = ConvItem{dx.as<float>() + (size_t)s * Npad, irh.d_H + (size_t)s * irh.P16 * B, irh.P, 0, Npad, nullptr, 1.0f};
+    {
+      ConvItem& it = items[s];
+      float* xs = dx.as<float>() + (size_t)s * Npad;
+      it.n_fwd = 1;
+      it.fwd[0] = {xs, nullptr, 1.0f};
+      it.lo = 0;
+      it.hi = Npad;
+      it.n_mac = 1;
+      it.mac[0] = {0, irh.d_H + (size_t)s * irh.P16 * B};
+      it.P = irh.P;
+      it.n_inv = 1;
+      it.inv[0] = {0, -1, xs, nullptr};
+    }
     rc = conv_batch(env, items);
     gac_stats st{};
     timer.finish(&st);

@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(kFftWarps * 32) k_rfft_fwd_uniform(FftFwdUnifo
   job.scale = u.scale_base ? u.scale_base + blockIdx.y : nullptr;
   job.gain = nullptr;
   job.gain_const = 1.0f;
+  job.in2 = nullptr;
+  job.mix_scale = 1.0f;
   job.n_valid = u.n_valid;
   job.n_blocks = u.n_blocks;
   job.gate_lo = 0;
@@ -164,8 +166,19 @@ __device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2
           // silent-flagged quanta read as zero; fused GainNode multiply (Nodes/GainNode.cs:49-58)
           float g0 = job.gain ? job.gain[g] : job.gain_const;
           float g1 = job.gain ? job.gain[g + 1 < job.n_valid ? g + 1 : g] : job.gain_const;
-          x.x = (g >= job.gate_lo && g < job.gate_hi) ? x.x * g0 : 0.f;
-          x.y = (g + 1 >= job.gate_lo && g + 1 < job.gate_hi) ? x.y * g1 : 0.f;
+          x.x = (g >= job.gate_lo && g < job.gate_hi) ? __fmul_rn(x.x, g0) : 0.f;
+          x.y = (g + 1 >= job.gate_lo && g + 1 < job.gate_hi) ? __fmul_rn(x.y, g1) : 0.f;
+          if (job.in2) {
+            // stereo -> mono down-mix at the input of a mono-IR convolver: dst = (L + R) * (1/sqrt(2))  (AudioNodeInput.cs:214-228)
+            const float* in_b = job.in2 + b * H;
+            float2 y = make_float2(0.f, 0.f);
+            if (g + 1 < job.n_valid) y = *reinterpret_cast<const float2*>(in_b + 2 * n);
+            else if (g < job.n_valid) y.x = in_b[2 * n];
+            y.x = (g >= job.gate_lo && g < job.gate_hi) ? __fmul_rn(y.x, g0) : 0.f;
+            y.y = (g + 1 >= job.gate_lo && g + 1 < job.gate_hi) ? __fmul_rn(y.y, g1) : 0.f;
+            x.x = __fmul_rn(__fadd_rn(x.x, y.x), job.mix_scale);
+            x.y = __fmul_rn(__fadd_rn(x.y, y.y), job.mix_scale);
+          }
           x.x = x.x * sc;  // float * float, as `sourceIr[offset + i] * scale` (PartitionedConvolver.cs:80)
           x.y = x.y * sc;
         }
@@ -219,17 +232,16 @@ __global__ void __launch_bounds__(kFftWarps * 32) k_irfft_ola(const FftInvJob* _
 #pragma unroll
   for (int j = 0; j < R; j++) twk[j] = tw[lane + 32 * j];
   constexpr int HALF = (R >= 2) ? R / 2 : 1;
-  float2 ov[HALF];
+  float2 ov[HALF], ov2[HALF];
 #pragma unroll
-  for (int j = 0; j < HALF; j++) ov[j] = make_float2(0.f, 0.f);
+  for (int j = 0; j < HALF; j++) ov[j] = ov2[j] = make_float2(0.f, 0.f);
 
   const int64_t b_first = ((int64_t)blockIdx.x * kFftWarps + warp) * BPW;
   if (b_first >= job.n_blocks) return;
   const float inv_h = 1.0f / (float)H;
-  for (int bi = (b_first > 0 ? -1 : 0); bi < BPW; bi++) {
-    const int64_t b = b_first + bi;
-    if (b >= job.n_blocks) break;
-    const float2* in = job.in + b * H;
+  // One inverse transform of block b of spectrogram `spec`: lo[] = float32(r[0:B]) + overlap, overlap <- float32(r[B:2B]).
+  auto pass = [&](const float2* __restrict__ spec, int64_t b, float2 (&ovr)[HALF], float2 (&lo)[HALF]) {
+    const float2* in = spec + b * H;
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; j++) tile[warp][lane + 32 * j] = in[lane + 32 * j];
@@ -259,22 +271,34 @@ __global__ void __launch_bounds__(kFftWarps * 32) k_irfft_ola(const FftInvJob* _
     for (int j = 0; j < R; j++) tile[warp][F::out_index(j, lane)] = make_float2(v[j].x * inv_h, v[j].y * inv_h);
     __syncwarp();
     // tile now holds r[0..2H) as floats (r[2m] = Re z[m], r[2m+1] = Im z[m])
+#pragma unroll
+    for (int j = 0; j < HALF; j++) {
+      const float2 r = tile[warp][lane + 32 * j];  // float2 index in the lower half
+      lo[j] = make_float2(r.x + ovr[j].x, r.y + ovr[j].y);
+      ovr[j] = tile[warp][H / 2 + lane + 32 * j];
+    }
+  };
+  for (int bi = (b_first > 0 ? -1 : 0); bi < BPW; bi++) {
+    const int64_t b = b_first + bi;
+    if (b >= job.n_blocks) break;
+    float2 lo[HALF];
+    pass(job.in, b, ov, lo);
+    if (job.in2) {
+      // true-stereo: out = c_a(in) + c_b(in) as ConvolverNode.Sum adds the two convolver outputs (ConvolverNode.cs:137-143,158-164)
+      float2 lo2[HALF];
+      pass(job.in2, b, ov2, lo2);
+#pragma unroll
+      for (int j = 0; j < HALF; j++) lo[j] = make_float2(lo[j].x + lo2[j].x, lo[j].y + lo2[j].y);
+    }
     if (bi >= 0) {
       float* out = job.out + b * H;
 #pragma unroll
-      for (int j = 0; j < HALF; j++) {
-        int idx = lane + 32 * j;  // float2 index in the lower half: idx < H/2
-        if (R >= 2 || idx < H / 2) {
-          float2 r = tile[warp][idx];
-          float2 o = make_float2(r.x + ov[j].x, r.y + ov[j].y);
-          *reinterpret_cast<float2*>(out + 2 * idx) = o;
-        }
-      }
-    }
+      for (int j = 0; j < HALF; j++) *reinterpret_cast<float2*>(out + 2 * (lane + 32 * j)) = lo[j];
+      if (job.out2) {  // mono result duplicated into the second row (1 -> 2 up-mix copy at the next input)
+        float* out2 = job.out2 + b * H;
 #pragma unroll
-    for (int j = 0; j < HALF; j++) {
-      int idx = H / 2 + lane + 32 * j;
-      if (R >= 2 || idx < H) ov[j] = tile[warp][idx];
+        for (int j = 0; j < HALF; j++) *reinterpret_cast<float2*>(out2 + 2 * (lane + 32 * j)) = lo[j];
+      }
     }
   }
 }

@@ -25,6 +25,8 @@ struct FftFwdJob {
   int64_t n_valid;       // samples of `in` that exist; the rest of the last block reads as zero
   int64_t n_blocks;
   int64_t gate_lo, gate_hi;  // samples outside [gate_lo, gate_hi) read as zero (silent-flagged quanta)
+  const float* in2 = nullptr;  // optional second channel: input = (in + in2) * mix_scale (stereo -> mono down-mix)
+  float mix_scale = 1.0f;
 };
 void launch_rfft_fwd(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
 // the same transform for the channels of ONE buffer, described arithmetically and passed by value (no job array upload)
@@ -42,6 +44,8 @@ struct FftInvJob {
   const float2* in;  // packed spectra, block b at in + b*B
   float* out;        // B-sample blocks, block b at out + b*B ; out[b] = r_b[0:B] + r_{b-1}[B:2B]
   int64_t n_blocks;
+  const float2* in2 = nullptr;  // optional second spectrogram: out = ola(in) + ola(in2)  (true-stereo Sum)
+  float* out2 = nullptr;        // optional second destination receiving the same samples (mono -> both rows)
 };
 void launch_irfft_ola(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
 

@@ -26,6 +26,7 @@ SOURCES = [
     ("fft.cu", []),
     ("nodes.cu", ["--fmad=false"]),
     ("biquad.cu", ["--fmad=false"]),
+    ("biquad_lanes.cu", ["--fmad=false"]),
     ("engine.cu", ["-Xcompiler", "-fvisibility=default"]),
 ]
 HEADERS = ["gac_kernels.h", "engine_render.inl", os.path.join("..", "..", "include", "graphaudio_cuda.h")]

@@ -7,132 +7,19 @@
 //                                            channel 1 inherits channel 0's end state): for every (channel, frame) the frame
 //                                            whose (f, Q) produced the coefficients in force, or -1 = "what the block started with"
 //   k_biquad_entry    one thread per voice   which coefficient set the reference's fields hold when a quantum starts
-//   k_biquad_resolve  parallel over frames   RBJ (glibc-exact sinf/cosf, :149-258) of the frame in force -> (x, a1, a2, b0), (b1, b2)
-//   k_biquad_lanes    one lane per (voice, channel): ONLY w = x - a1*w1 - a2*w2 (:137) is sequential; 3-stage cp.async
-//                     pipeline of 32-frame slabs so that the lane never waits on HBM
+//   k_biquad_resolve  parallel over frames   RBJ (glibc-exact sinf/cosf, :149-258) of the frame in force; writes (b0, b1, b2) per
+//                                            (channel, frame) and the slab-transposed stream (x, a1, a2) the lanes read
+//   k_biquad_lanes    one lane per (voice, channel): ONLY w = x - a1*w1 - a2*w2 (:137) is sequential; one TMA bulk copy per
+//                     32-frame slab of 32 lanes (16 KB), mbarrier ring, one bulk store of the w tile (biquad_lanes.cu)
 //   k_biquad_output   parallel over frames   y = b0*w + b1*w1 + b2*w2 (:138) from the stored w sequence (same ops, same order)
-#include "gac_kernels.h"
+//
+// Slab-transposed layout (shared by resolve, lanes and output): rows are grouped 32 at a time (16 voices x 2 channels = one
+// warp of lanes), time is cut into slabs of 32 frames, and inside a slab the FRAME index is major and the row index minor:
+//     S1T[group][slab][frame 0..31][row 0..31]  float4 (x, a1, a2, -)         WT[group][slab][frame][row]  float
+// so that a slab is one contiguous 16 KB (4 KB) block for TMA and lane r's LDS.128 / STS.32 at frame i are conflict-free.
+#include "biquad_math.cuh"
 
 namespace gac {
-
-// glibc's sinf/cosf (sysdeps/ieee754/flt-32/s_sincosf.h — the ARM optimized-routines algorithm that .NET's
-// MathF.Sin/Cos reach through the platform libm on Linux): double-precision pi/2 reduction + double polynomial,
-// rounded once to float.  Restated here so that the RBJ coefficients (BiQuadFilterNode.cs:151-153) come out
-// bit-identical to the CPU oracle; verified exhaustively on the host for every float in [1e-5, 3.2].
-// Valid for 0 <= x < 120 (w0 = 2*pi*f/fs lies in (0, pi]).
-__device__ __forceinline__ void sincosf_libm(float y, float* sn, float* cs) {
-  const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
-  const double c0 = 1.0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
-  const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
-  double x = (double)y;
-  int n = 0;
-  double sgn = 1.0;
-  bool neg = false;
-  const unsigned top = (__float_as_uint(y) >> 20) & 0x7ff;
-  if (top >= 0x3f4) {  // |y| >= pi/4  (abstop12(pio4) = 0x3f4)
-    double r = x * hpi_inv;
-    n = ((int)r + 0x800000) >> 24;
-    x = x - (double)n * hpi;
-    sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
-    neg = (n & 2) != 0;
-  } else if (top < 0x398) {  // |y| < 2^-12
-    *sn = y;
-    *cs = 1.0f;
-    return;
-  }
-  const double x2 = x * x;
-  const double xs = x * sgn;
-  // sine polynomial on (xs, x2), cosine polynomial on (x2) with the sign of table 1 when n & 2
-  double sinp, cosp;
-  {
-    double x3 = xs * x2;
-    double S1 = s2 + x2 * s3;
-    double x7 = x3 * x2;
-    double sv = xs + x3 * s1;
-    sinp = sv + x7 * S1;
-  }
-  {
-    double C0 = neg ? -c0 : c0, C1 = neg ? -c1 : c1, C2 = neg ? -c2 : c2, C3 = neg ? -c3 : c3, C4 = neg ? -c4 : c4;
-    double x4 = x2 * x2;
-    double cc2 = C3 + x2 * C4;
-    double cc1 = C0 + x2 * C1;
-    double x6 = x4 * x2;
-    double cv = cc1 + x4 * C2;
-    cosp = cv + x6 * cc2;
-  }
-  // sinf uses poly(n), cosf uses poly(n ^ 1): even -> sine polynomial, odd -> cosine polynomial
-  if ((n & 1) == 0) {
-    *sn = (float)sinp;
-    *cs = (float)cosp;
-  } else {
-    *sn = (float)cosp;
-    // cosf with odd n evaluates the sine polynomial; the table-1 switch only negates cosine coefficients,
-    // the sign of the sine polynomial is carried by xs
-    *cs = (float)sinp;
-  }
-}
-
-struct Coef {
-  float b0, b1, b2, a1, a2;
-};
-
-// UpdateCoefficients, BiQuadFilterNode.cs:149-258
-__device__ Coef rbj(int type, float frequency, float q, float gain, int sample_rate) {
-  float w0 = 2.f * 3.14159274f * frequency / (float)sample_rate;  // left to right in float32 (:151)
-  float sinW0, cosW0;
-  sincosf_libm(w0, &sinW0, &cosW0);
-  float alpha = sinW0 / (2.f * q);
-  float a0, a1, a2, b0, b1, b2;
-  switch (type) {
-    case 0: b0 = (1.f - cosW0) / 2.f; b1 = 1.f - cosW0; b2 = (1.f - cosW0) / 2.f; a0 = 1.f + alpha; a1 = -2.f * cosW0; a2 = 1.f - alpha; break;
-    case 1: b0 = (1.f + cosW0) / 2.f; b1 = -(1.f + cosW0); b2 = (1.f + cosW0) / 2.f; a0 = 1.f + alpha; a1 = -2.f * cosW0; a2 = 1.f - alpha; break;
-    case 2: b0 = alpha; b1 = 0.f; b2 = -alpha; a0 = 1.f + alpha; a1 = -2.f * cosW0; a2 = 1.f - alpha; break;
-    case 3: b0 = 1.f; b1 = -2.f * cosW0; b2 = 1.f; a0 = 1.f + alpha; a1 = -2.f * cosW0; a2 = 1.f - alpha; break;
-    case 4: b0 = 1.f - alpha; b1 = -2.f * cosW0; b2 = 1.f + alpha; a0 = 1.f + alpha; a1 = -2.f * cosW0; a2 = 1.f - alpha; break;
-    case 5: {
-      float A = (float)pow(10.0, (double)(gain / 40.f));  // MathF.Pow -> powf; double pow rounded to float agrees except on rare ties
-      b0 = 1.f + alpha * A; b1 = -2.f * cosW0; b2 = 1.f - alpha * A; a0 = 1.f + alpha / A; a1 = -2.f * cosW0; a2 = 1.f - alpha / A; break;
-    }
-    case 6: {
-      float A = (float)pow(10.0, (double)(gain / 40.f));
-      float sqrtA = sqrtf(A);
-      float beta = sqrtA / q;
-      b0 = A * ((A + 1.f) - (A - 1.f) * cosW0 + beta * sinW0);
-      b1 = 2.f * A * ((A - 1.f) - (A + 1.f) * cosW0);
-      b2 = A * ((A + 1.f) - (A - 1.f) * cosW0 - beta * sinW0);
-      a0 = (A + 1.f) + (A - 1.f) * cosW0 + beta * sinW0;
-      a1 = -2.f * ((A - 1.f) + (A + 1.f) * cosW0);
-      a2 = (A + 1.f) + (A - 1.f) * cosW0 - beta * sinW0;
-      break;
-    }
-    case 7: {
-      float A = (float)pow(10.0, (double)(gain / 40.f));
-      float sqrtA = sqrtf(A);
-      float beta = sqrtA / q;
-      b0 = A * ((A + 1.f) + (A - 1.f) * cosW0 + beta * sinW0);
-      b1 = -2.f * A * ((A - 1.f) + (A + 1.f) * cosW0);
-      b2 = A * ((A + 1.f) + (A - 1.f) * cosW0 - beta * sinW0);
-      a0 = (A + 1.f) - (A - 1.f) * cosW0 + beta * sinW0;
-      a1 = 2.f * ((A - 1.f) - (A + 1.f) * cosW0);
-      a2 = (A + 1.f) - (A - 1.f) * cosW0 - beta * sinW0;
-      break;
-    }
-    default: b0 = 1.f; b1 = 0.f; b2 = 0.f; a0 = 1.f; a1 = 0.f; a2 = 0.f; break;
-  }
-  Coef c;
-  c.b0 = b0 / a0; c.b1 = b1 / a0; c.b2 = b2 / a0; c.a1 = a1 / a0; c.a2 = a2 / a0;  // :253-257
-  return c;
-}
-
-__device__ __forceinline__ float clamped_freq(const BiquadJob& job, int64_t n, float nyq) {
-  float f = job.freq ? job.freq[n] : job.freq_const;
-  return f < 1.f ? 1.f : (f > nyq ? nyq : f);  // Math.Clamp(freq, 1, fs/2)  :123
-}
-__device__ __forceinline__ float clamped_q(const BiquadJob& job, int64_t n) {
-  float q = job.q ? job.q[n] : job.q_const;
-  return q > 0.001f ? q : 0.001f;  // Math.Max(0.001f, q)  :124
-}
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K3a: the hysteresis walk (:121-134).  CTA = 128 consecutive quanta of one job; thread = one quantum, which walks
@@ -221,161 +108,87 @@ __global__ void __launch_bounds__(64) k_biquad_entry(int n_jobs, int64_t n_quant
   }
 }
 
-// K3c: coefficients in force at every (channel, frame): RBJ of the frame the walk selected, with the k-rate gain of
-// that frame's block.  Writes the two streams the lanes / the output pass read.
-__global__ void __launch_bounds__(256) k_biquad_resolve(const BiquadJob* __restrict__ jobs, int sample_rate, int64_t n_quanta,
-                                                        int64_t n_frames, const int32_t* __restrict__ ent_base) {
-  const int jid = blockIdx.y;
-  const BiquadJob job = jobs[jid];
-  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;  // over 2 * n_frames
-  if (t >= 2 * n_frames) return;
-  const int c = t >= n_frames ? 1 : 0;
-  const int64_t n = t - (int64_t)c * n_frames;
-  if (n < job.lo || n >= job.hi) return;
-  int32_t i = job.idx[t];
-  if (i < 0) i = ent_base[((size_t)jid * 2 + c) * n_quanta + (n >> 7)];
-  Coef k;
-  if (i >= 0) {
-    const float nyq = (float)sample_rate / 2.f;
-    k = rbj(job.type, clamped_freq(job, i, nyq), clamped_q(job, i), job.gain ? job.gain[i >> 7] : job.gain_const, sample_rate);
-  } else {
-    k.b0 = k.b1 = k.b2 = k.a1 = k.a2 = 0.f;  // unreachable for active frames: the first one always recomputes (dirty)
-  }
-  job.s1[t] = make_float4(job.sig[c][n], k.a1, k.a2, k.b0);
-  job.s2[t] = make_float2(k.b1, k.b2);
-}
-
-// K3d: the recursion.  One lane per (job, channel); the only sequential arithmetic left is
-//     w = x - a1*w1 - a2*w2        (:137, left to right, unfused)
-// A warp owns 32 lanes (16 voices x 2 channels) = 32 consecutive rows of the batch-wide (x, a1, a2, b0) stream
-// s1_all[row][n_frames].  Slabs of 32 frames travel global -> shared through a 3-stage cp.async pipeline (one warp
-// instruction copies one 512 B row; rows that are silent in the slab are zero-filled by the src-size form, so the
-// producer code is branch-free); a lane reads its row with conflict-free LDS.128, collects four w's in registers and
-// writes them to a small tile that is stored coalesced.
-constexpr int kSlab = 32;
-constexpr int kBqStages = 3;
-constexpr int kSStride = kSlab * 4 + 4;   // floats per stream row (528 B)
-constexpr int kWStride = 36;              // floats per w row (144 B)
-constexpr int kStageFloats = 32 * kSStride;
-constexpr size_t kBqSmem = (size_t)(kBqStages * kStageFloats) * sizeof(float);
-
-// 16-byte async copy; copies src_bytes (0 or 16) and zero-fills the rest
-__device__ __forceinline__ void cp_async16_zfill(uint32_t smem, const void* gmem, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
-                                                     const float4* __restrict__ s1_all, float* __restrict__ w_all) {
-  extern __shared__ __align__(16) float bq_smem[];
-  __shared__ __align__(16) float wt[32 * kWStride];
-  const int lane = threadIdx.x;
-  const int j = blockIdx.x * 16 + (lane >> 1);
-  const bool valid = j < n_jobs;
-  const int64_t my_lo = valid ? jobs[j].lo : 0, my_hi = valid ? jobs[j].hi : 0;
-  int64_t lo = my_hi > my_lo ? my_lo : INT64_MAX, hi = my_hi > my_lo ? my_hi : 0;
-  for (int o = 16; o > 0; o >>= 1) {
-    int64_t lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
-    lo = lo2 < lo ? lo2 : lo;
-    hi = hi2 > hi ? hi2 : hi;
-  }
-  if (hi <= lo) return;
-  const int n_slabs = (int)((hi - lo) / kSlab);  // ranges are multiples of 128
-  const size_t row0 = (size_t)blockIdx.x * 32;   // first row of this warp in the batch-wide streams
-  const float4* __restrict__ src0 = s1_all + row0 * (size_t)n_frames + lane;
-  float* __restrict__ dst0 = w_all + row0 * (size_t)n_frames;
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(bq_smem) + lane * 16;
-
-  auto row_mask = [&](int64_t base) -> unsigned { return __ballot_sync(0xffffffffu, base >= my_lo && base < my_hi); };
-  auto issue = [&](int s) {
-    if (s < n_slabs) {
-      const int64_t base = lo + (int64_t)s * kSlab;
-      const unsigned mask = row_mask(base);
-      const uint32_t st = smem0 + (uint32_t)((s % kBqStages) * kStageFloats * 4);
-      const float4* src = src0 + base;
-#pragma unroll
-      for (int i = 0; i < 32; i++)
-        cp_async16_zfill(st + i * (kSStride * 4), src + (size_t)i * n_frames, ((mask >> i) & 1u) ? 16 : 0);
-    }
-    cp_async_commit();
-  };
-
-  for (int s = 0; s < kBqStages - 1; s++) issue(s);
-  float w1 = 0.f, w2 = 0.f;
-  for (int s = 0; s < n_slabs; s++) {
-    issue(s + kBqStages - 1);
-    cp_async_wait<kBqStages - 1>();
-    __syncwarp();
-    const int64_t base = lo + (int64_t)s * kSlab;
-    const float* __restrict__ row = bq_smem + (s % kBqStages) * kStageFloats + lane * kSStride;
-    float* __restrict__ wrow = wt + lane * kWStride;
-    // silent rows read zeros (zero-filled), so their w stays 0 and nothing of them is stored: no branch needed
-#pragma unroll
-    for (int i4 = 0; i4 < kSlab / 4; i4++) {
-      float wo[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const float4 r = *reinterpret_cast<const float4*>(row + (i4 * 4 + u) * 4);  // (x, a1, a2, b0)
-        const float w = r.x - r.y * w1 - r.z * w2;
-        w2 = w1;
-        w1 = w;
-        wo[u] = w;
+// K3c: coefficients in force at every (channel, frame): RBJ of the frame the walk selected, with the k-rate gain of that
+// frame's block.  CTA = one slab of one 32-row group: thread (r = tid / 32, i = tid % 32) reads row r along time
+// (coalesced), the (x, a1, a2) tile is transposed through shared memory and written as one contiguous 16 KB block.
+__global__ void __launch_bounds__(1024) k_biquad_resolve(const BiquadJob* __restrict__ jobs, int n_jobs, int sample_rate, int64_t n_quanta,
+                                                         int64_t n_frames, const int32_t* __restrict__ ent_base, float4* __restrict__ s1t) {
+  __shared__ float4 tile[32][33];
+  const int r = threadIdx.x >> 5, i = threadIdx.x & 31;
+  const int64_t slab = blockIdx.x;
+  const int g = blockIdx.y;
+  const int jid = g * 16 + (r >> 1);
+  const int c = r & 1;
+  const int64_t n = slab * 32 + i;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (jid < n_jobs) {
+    const BiquadJob& job = jobs[jid];
+    if (n >= job.lo && n < job.hi) {
+      const int64_t t = (int64_t)c * n_frames + n;
+      int32_t k = job.idx[t];
+      if (k < 0) k = ent_base[((size_t)jid * 2 + c) * n_quanta + (n >> 7)];
+      Coef co;
+      if (k >= 0) {
+        const float nyq = (float)sample_rate / 2.f;
+        co = rbj(job.type, clamped_freq(job, k, nyq), clamped_q(job, k), job.gain ? job.gain[k >> 7] : job.gain_const, sample_rate);
+      } else {
+        co.b0 = co.b1 = co.b2 = co.a1 = co.a2 = 0.f;  // unreachable for active frames: the first one always recomputes (dirty)
       }
-      *reinterpret_cast<float4*>(wrow + i4 * 4) = make_float4(wo[0], wo[1], wo[2], wo[3]);
+      v = make_float4(job.sig[c][n], co.a1, co.a2, 0.f);
+      job.s2[t] = make_float4(co.b0, co.b1, co.b2, 0.f);
     }
-    __syncwarp();
-    const unsigned mask = row_mask(base);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {  // coalesced store of the w tile: 32 rows x 8 chunks of 16 B
-      const int q = lane + 32 * i, r = q >> 3, ch = q & 7;
-      if ((mask >> r) & 1u)
-        *reinterpret_cast<float4*>(dst0 + (size_t)r * n_frames + base + ch * 4) = *reinterpret_cast<const float4*>(wt + r * kWStride + ch * 4);
-    }
-    __syncwarp();
   }
+  tile[i][r] = v;
+  __syncthreads();
+  // tile[frame][row] -> S1T[g][slab][frame][row]: thread tid writes element (frame = tid / 32, row = tid % 32)
+  const size_t n_slabs = (size_t)(n_frames / 32);
+  s1t[((size_t)g * n_slabs + slab) * 1024 + threadIdx.x] = tile[threadIdx.x >> 5][threadIdx.x & 31];
 }
 
-// K3e: y = b0*w + b1*w1 + b2*w2 (:138) from the stored w sequence; frames outside the non-silent range are cleared (:103-108)
-__global__ void __launch_bounds__(256) k_biquad_output(const BiquadJob* __restrict__ jobs, int64_t n_frames) {
-  const BiquadJob job = jobs[blockIdx.y];
-  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (t >= 2 * n_frames) return;
-  const int c = t >= n_frames ? 1 : 0;
-  const int64_t n = t - (int64_t)c * n_frames;
+// K3e: y = b0*w + b1*w1 + b2*w2 (:138) from the stored w sequence; frames outside the non-silent range are cleared (:103-108).
+// CTA = one slab of one 32-row group; the w tile (plus the last two frames of the previous slab) is transposed back through
+// shared memory so that both the WT reads and the sig writes are coalesced.
+__global__ void __launch_bounds__(1024) k_biquad_output(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
+                                                        const float* __restrict__ wt) {
+  __shared__ float tile[34][33];  // rows 0,1 = frames 30,31 of the previous slab; rows 2..33 = this slab
+  const int r = threadIdx.x >> 5, i = threadIdx.x & 31;
+  const int64_t slab = blockIdx.x;
+  const int g = blockIdx.y;
+  const size_t n_slabs = (size_t)(n_frames / 32);
+  const float* cur = wt + ((size_t)g * n_slabs + slab) * 1024;
+  tile[2 + (threadIdx.x >> 5)][threadIdx.x & 31] = cur[threadIdx.x];
+  if (threadIdx.x < 64) {
+    float p = 0.f;
+    if (slab > 0) p = (cur - 1024)[30 * 32 + threadIdx.x];
+    tile[threadIdx.x >> 5][threadIdx.x & 31] = p;
+  }
+  __syncthreads();
+  const int jid = g * 16 + (r >> 1);
+  if (jid >= n_jobs) return;
+  const int c = r & 1;
+  const BiquadJob& job = jobs[jid];
+  const int64_t n = slab * 32 + i;
   float y = 0.f;
   if (n >= job.lo && n < job.hi) {
-    const float* w = job.w + (size_t)c * n_frames;
-    const float w0 = w[n];
-    const float w1 = n - 1 >= job.lo ? w[n - 1] : 0.f;
-    const float w2 = n - 2 >= job.lo ? w[n - 2] : 0.f;
-    const float b0 = job.s1[t].w;
-    const float2 b12 = job.s2[t];
-    y = b0 * w0 + b12.x * w1 + b12.y * w2;
+    const float w0 = tile[2 + i][r];
+    const float w1 = n - 1 >= job.lo ? tile[1 + i][r] : 0.f;
+    const float w2 = n - 2 >= job.lo ? tile[i][r] : 0.f;
+    const float4 b = job.s2[(int64_t)c * n_frames + n];
+    y = b.x * w0 + b.y * w1 + b.z * w2;
   }
   job.sig[c][n] = y;
 }
 
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, const float4* d_s1_all, float* d_w_all, cudaStream_t s) {
+                   int32_t* d_ent, float4* d_s1t, float* d_wt, cudaStream_t s) {
   if (n_jobs <= 0 || n_frames <= 0) return;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_biquad_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBqSmem);
-    attr = true;
-  }
-  for (int j0 = 0; j0 < n_jobs; j0 += 32768) {
-    int nj = n_jobs - j0 < 32768 ? n_jobs - j0 : 32768;
-    int32_t* last = d_last + (size_t)j0 * 2 * n_quanta;
-    int32_t* ent = d_ent + (size_t)j0 * 2 * n_quanta;
-    k_biquad_select<<<dim3((unsigned)((n_quanta + kSelQ - 1) / kSelQ), (unsigned)nj), kSelQ, 0, s>>>(d_jobs + j0, sample_rate, n_quanta, n_frames, last);
-    k_biquad_entry<<<(unsigned)((nj + 63) / 64), 64, 0, s>>>(nj, n_quanta, last, ent);
-    k_biquad_resolve<<<dim3((unsigned)((2 * n_frames + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, sample_rate, n_quanta, n_frames, ent);
-    k_biquad_lanes<<<(unsigned)((nj + 15) / 16), 32, kBqSmem, s>>>(d_jobs + j0, nj, n_frames, d_s1_all + (size_t)j0 * 2 * n_frames,
-                                                                     d_w_all + (size_t)j0 * 2 * n_frames);
-    k_biquad_output<<<dim3((unsigned)((2 * n_frames + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames);
-  }
+  const int groups = (n_jobs + 15) / 16;
+  const unsigned n_slabs = (unsigned)(n_frames / 32);
+  k_biquad_select<<<dim3((unsigned)((n_quanta + kSelQ - 1) / kSelQ), (unsigned)n_jobs), kSelQ, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last);
+  k_biquad_entry<<<(unsigned)((n_jobs + 63) / 64), 64, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
+  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 1024, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t);
+  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_wt, s);
+  k_biquad_output<<<dim3(n_slabs, (unsigned)groups), 1024, 0, s>>>(d_jobs, n_jobs, n_frames, d_wt);
 }
 
 }  // namespace gac

@@ -838,19 +838,18 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     }
     // ---------------- BiQuadFilterNode (K2 + K3)
     if (!biquads.empty()) {
-      const size_t per_job = (size_t)env.Npad * (2 * (4 + 16 + 8 + 4) + 4 + 4) + (size_t)env.NQ * (16 + 4);
-      const size_t max_jobs = std::max<size_t>(1, ctx->scratch_budget / per_job);
+      const size_t per_job = (size_t)env.Npad * (2 * (4 + 16 + 16 + 4) + 4 + 4) + (size_t)env.NQ * (16 + 4);
+      const size_t max_jobs = std::min<size_t>(65535, std::max<size_t>(1, ctx->scratch_budget / per_job));
       for (size_t k0 = 0; k0 < biquads.size(); k0 += max_jobs) {
         const size_t nk = std::min(max_jobs, biquads.size() - k0);
         std::vector<ParamJob> pj;
         auto& bj = env.keep->make<BiquadJob>();
         int32_t* idx_all = nullptr;
-        float4* s1_all = nullptr;
-        float2* s2_all = nullptr;
+        float4 *s1_all = nullptr, *s2_all = nullptr;
         float* w_all = nullptr;
         {
           int rc;
-          const size_t rows = ((nk + 15) / 16) * 16 * 2;  // the lanes kernel addresses whole 32-row groups
+          const size_t rows = ((nk + 15) / 16) * 32;  // slab-transposed streams cover whole 32-row groups
           if ((rc = env.scratch->alloc(&idx_all, nk * 2 * (size_t)env.Npad))) return rc;
           if ((rc = env.scratch->alloc(&s1_all, rows * (size_t)env.Npad))) return rc;
           if ((rc = env.scratch->alloc(&s2_all, nk * 2 * (size_t)env.Npad))) return rc;
@@ -878,9 +877,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           j.lo = s.lo;
           j.hi = s.hi;
           j.idx = idx_all + k * 2 * (size_t)env.Npad;
-          j.s1 = s1_all + k * 2 * (size_t)env.Npad;
           j.s2 = s2_all + k * 2 * (size_t)env.Npad;
-          j.w = w_all + k * 2 * (size_t)env.Npad;
           bj.push_back(j);
         }
         int rc = run_param_jobs(env, pj);

@@ -126,14 +126,17 @@ struct BiquadJob {
   int64_t lo, hi;      // active frame range (multiples of 128)
   // scratch, per job (c = channel, n = frame):
   int32_t* idx;        // [2][n_frames] frame whose (f, Q) gave the coefficients in force, -1 = the quantum's entry set
-  float4* s1;          // [2][n_frames] (x, a1, a2, b0)
-  float2* s2;          // [2][n_frames] (b1, b2)
-  float* w;            // [2][n_frames] Direct-Form-II state sequence
+  float4* s2;          // [2][n_frames] (b0, b1, b2, -)
 };
-// scratch: d_last, d_ent int32 [n_jobs][2][n_quanta].  d_s1_all / d_w_all are the batch-wide arrays [n_jobs][2][n_frames] that
-// job k's s1 / w point into (job k at offset k*2*n_frames): the lanes kernel addresses rows arithmetically.
+// scratch: d_last, d_ent int32 [n_jobs][2][n_quanta]; the slab-transposed batch-wide streams (layout: biquad.cu header)
+//   d_s1t float4 [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  (x, a1, a2, -)
+//   d_wt  float  [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  Direct-Form-II state sequence w
+// n_jobs <= 65535 per call.
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, const float4* d_s1_all, float* d_w_all, cudaStream_t s);
+                   int32_t* d_ent, float4* d_s1t, float* d_wt, cudaStream_t s);
+
+// K3d alone (biquad_lanes.cu): the w recursion over the slab-transposed streams, TMA-fed
+void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, float* d_wt, cudaStream_t s);
 
 struct MixJob {       // dst[c][n] = (((0 + src0) + src1) + ...) over active ranges, AudioNodeInput.cs:118-137
   float* dst[2];

@@ -357,14 +357,14 @@ class OfflineAudioContext:
         for head in self.Destination._in:
             # walk up while the chain is single-input; the first node with >= 2 inputs is the bus fan-in
             chain, node = [], head
-            while not isinstance(node, AudioBufferSourceNode) and len(node._in) == 1:
+            while not isinstance(node, AudioBufferSourceNode) and len(node._in) == 1 and not getattr(node, "_force_bus", False):
                 chain.append(node)
                 node = node._in[0]
             if isinstance(node, AudioBufferSourceNode):
                 voices.append((node, list(reversed(chain)), -1))
                 dest_inputs.append(~(len(voices) - 1))
                 continue
-            if len(node._in) == 0:
+            if len(node._in) == 0 and not getattr(node, "_force_bus", False):
                 continue  # nothing connected: contributes silence
             chain.append(node)  # node has the fan-in input; it and everything below it run on the bus
             bus_index = len(buses)
@@ -447,6 +447,39 @@ class OfflineAudioContext:
             ptrs = (N.fp * len(rows))(*[_fptr(r) for r in rows])
             check(N.lib().gac_render(self._h, graph, self._frames_rendered, int(frameCount), ptrs, len(rows), int(startIndex)))
             self._frames_rendered += int(frameCount)
+            st = N.gac_stats()
+            check(N.lib().gac_get_stats(self._h, C.byref(st)))
+            self.last_stats = st.as_dict()
+        finally:
+            N.lib().gac_graph_destroy(graph)
+
+    # ---- multi-GPU: voices sharded over processes, one NCCL reduce of the bus (gac_render_sharded)
+    def MarkBus(self, node):
+        """Declares `node`'s input as the fan-in that is reduced across ranks.  Needed because a shard may hold one voice
+        (or none): the flattening would otherwise fold `voice -> node -> destination` into a single direct voice and
+        apply the bus ops before the reduce instead of after it."""
+        node._force_bus = True
+        return node
+
+    def CommInit(self, unique_id: bytes, rank: int, world: int):
+        check(N.lib().gac_comm_init(self._h, unique_id, int(rank), int(world)))
+
+    @staticmethod
+    def CommUniqueId() -> bytes:
+        buf = (C.c_char * 128)()
+        check(N.lib().gac_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def RenderSharded(self, output, frameCount, root=0):
+        """Collective: every rank renders its shard up to the bus, the buses are summed onto `root` by one ncclReduce, the
+        root applies the bus ops and fills `output` (float32 [2][>= frameCount]); other ranks leave it untouched."""
+        if frameCount <= 0:
+            raise ArgumentOutOfRangeException("Frame count must be positive.")
+        graph = self._graph()
+        try:
+            rows = [output[c] for c in range(len(output))]
+            ptrs = (N.fp * len(rows))(*[_fptr(r) for r in rows])
+            check(N.lib().gac_render_sharded(self._h, graph, int(frameCount), int(root), ptrs, len(rows)))
             st = N.gac_stats()
             check(N.lib().gac_get_stats(self._h, C.byref(st)))
             self.last_stats = st.as_dict()

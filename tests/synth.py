@@ -73,6 +73,7 @@ def build_c2(api, fs, voices, bus_gain, t_scale=1.0, **ctx_kw):
     bus = api.GainNode(ctx)
     bus.Gain.Value = bus_gain
     bus.Connect(ctx.Destination)
+    ctx.bus = bus  # handle for callers that shard the voices over ranks (OfflineAudioContext.MarkBus)
     for src, ir, g in voices:
         s = api.AudioBufferSourceNode(ctx)
         s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, fs)
@@ -91,6 +92,7 @@ def build_c3(api, fs, voices, bus_gain, f0=2000.0, f1=12000.0, t_scale=1.0, q=0.
     bus = api.GainNode(ctx)
     bus.Gain.Value = bus_gain
     bus.Connect(ctx.Destination)
+    ctx.bus = bus  # handle for callers that shard the voices over ranks (OfflineAudioContext.MarkBus)
     for src, ir, g in voices:
         s = api.AudioBufferSourceNode(ctx)
         s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, fs)
@@ -135,6 +137,7 @@ def build_c5(api, fs, src_rate, voices, bus_gain, t_scale=1.0, **ctx_kw):
     bus = api.GainNode(ctx)
     bus.Gain.Value = bus_gain
     bus.Connect(ctx.Destination)
+    ctx.bus = bus  # handle for callers that shard the voices over ranks (OfflineAudioContext.MarkBus)
     for src, ir, g in voices:
         s = api.AudioBufferSourceNode(ctx)
         s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, src_rate)

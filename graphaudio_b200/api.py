@@ -217,13 +217,24 @@ class AudioBufferSourceNode(AudioNode):
     def __init__(self, context):
         super().__init__(context, 0, 1)
         self.PlaybackRate = AudioParam(1.0, 0.001, 1000.0)  # k-rate, Nodes/AudioBufferSourceNode.cs:76
-        self.Buffer: Optional[PlayableAudioBuffer] = None
+        self._buffer: Optional[PlayableAudioBuffer] = None
         self.Loop = False
         self._started = False
         self._when = math.nan
         self._offset = 0.0
         self._duration = math.inf
         self._stop = math.nan
+
+    @property
+    def Buffer(self):  # :67-71
+        return self._buffer
+
+    @Buffer.setter
+    def Buffer(self, value):
+        self._buffer = value
+        # upload now rather than at Render: with async_upload the copy engine works while the rest of the graph is built
+        if value is not None and not self.Context._record_only and self.Context._h is not None:
+            value._handle(self.Context)
 
     def Start(self, when=0.0, offset=0.0, duration=math.inf):  # :79-114
         if self._started:

@@ -353,7 +353,8 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   for (auto* v : voices)
     if (v->src->ready && cudaEventQuery(v->src->ready) == cudaErrorNotReady) n_pending++;
   cudaGetLastError();
-  const size_t n_batches = (n_pending > 0 && S >= 16) ? 4 : 1;
+  // (buffers are uploaded in creation order, so the pending ones are the last voices)
+  const size_t n_batches = (n_pending > 0 && S >= 16) ? 1 + (3 * n_pending + S - 1) / S : 1;
   for (size_t bi = 0; bi < n_batches; bi++) {
     const size_t v0 = S * bi / n_batches, v1 = S * (bi + 1) / n_batches;
     if (v1 <= v0) continue;

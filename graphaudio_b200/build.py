@@ -24,12 +24,13 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = [
     ("mac.cu", []),
     ("fft.cu", []),
+    ("fft2.cu", []),
     ("nodes.cu", ["--fmad=false"]),
     ("biquad.cu", ["--fmad=false"]),
     ("biquad_lanes.cu", ["--fmad=false"]),
     ("engine.cu", ["-Xcompiler", "-fvisibility=default"]),
 ]
-HEADERS = ["gac_kernels.h", "engine_render.inl", os.path.join("..", "..", "include", "graphaudio_cuda.h")]
+HEADERS = ["gac_kernels.h", "fft2_core.cuh", "engine_render.inl", os.path.join("..", "..", "include", "graphaudio_cuda.h")]
 
 
 def _nvcc() -> str:

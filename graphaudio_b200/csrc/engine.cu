@@ -78,6 +78,7 @@ struct gac_context {
   int tile_blocks = 32;
   cudaStream_t stream = nullptr;
   float2* d_tw = nullptr;  // e^{-2 pi i k/(2B)}, k < B
+  float2* d_tw2 = nullptr; // e^{-2 pi i e/8192}, e < 8192: twiddles of the second-level (block-time) FFT, fft2.cu
   std::vector<double> h_bt;  // block start times, accumulated as AudioContextBase.cs:78-79
   double* d_bt = nullptr;
   int64_t bt_cap = 0;
@@ -112,6 +113,9 @@ struct gac_ir {
   int64_t frames;
   float2* d_H = nullptr;  // [nch][P16][B]
   float* d_scale = nullptr;
+  // second-level spectra (fft2.cu): [nch][B+1][M2], or null when the context's mac_variant never uses them
+  float2* d_H2 = nullptr;
+  int M2 = 0, Lh = 0;
 };
 struct gac_graph {
   gac_context* ctx;
@@ -121,6 +125,15 @@ struct gac_graph {
 };
 
 static bool ctx_ok(gac_context* c) { return c && c->magic == 0x47414331; }
+
+// mac_variant: 0 = auto (second-level FFT when the IR has >= kFft2MinP partitions, else register-tiled FFMA2),
+// 1 = streaming (reference op order), 2 = register-tiled scalar FFMA, 3 = second-level FFT (forced), 4 = register-tiled FFMA2 (forced)
+constexpr int kFft2MinP = 64;
+static bool wants_fft2(const gac_context* c) { return c->mac_variant == 0 || c->mac_variant == 3; }
+static bool use_fft2(const gac_context* c, int P, int M2) {
+  if (M2 <= 0) return false;
+  return c->mac_variant == 3 || (c->mac_variant == 0 && P >= kFft2MinP);
+}
 
 // ------------------------------------------------------------------------------------------ scratch + timing
 // Stream-ordered scratch allocations, all released at the end of a render.
@@ -317,6 +330,18 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   }
   CU(cudaMallocAsync(&ctx->d_tw, sizeof(float2) * B, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_tw, tw.data(), sizeof(float2) * B, cudaMemcpyHostToDevice, ctx->stream));  // pageable: staged before return
+  {
+    static std::vector<float2> tw2;  // same for every context: computed once per process
+    if (tw2.empty()) {
+      tw2.resize(kFft2TwLen);
+      for (int e = 0; e < kFft2TwLen; e++) {
+        double a = -2.0 * pi * (double)e / (double)kFft2TwLen;
+        tw2[e] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+    }
+    CU(cudaMallocAsync(&ctx->d_tw2, sizeof(float2) * kFft2TwLen, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_tw2, tw2.data(), sizeof(float2) * kFft2TwLen, cudaMemcpyHostToDevice, ctx->stream));
+  }
   int rc = ensure_block_times(ctx.get(), 8192);
   if (rc) return rc;
   *out = ctx.release();
@@ -338,6 +363,7 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) gac_comm_destroy(ctx);
   if (ctx->d_tw) cudaFreeAsync(ctx->d_tw, ctx->stream);
+  if (ctx->d_tw2) cudaFreeAsync(ctx->d_tw2, ctx->stream);
   if (ctx->d_bt) cudaFreeAsync(ctx->d_bt, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) {
@@ -435,6 +461,14 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   u.n_blocks = ir->P;
   launch_rfft_fwd_uniform(u, nch, B, ctx->d_tw, ctx->stream);
   CU(cudaGetLastError());
+  // second-level spectra: FFT of every bin's partition sequence along p (fft2.cu)
+  ir->M2 = wants_fft2(ctx) ? fft2_pick_m(ir->P, &ir->Lh) : 0;
+  if (ir->M2 > 0 && !use_fft2(ctx, ir->P, ir->M2)) ir->M2 = 0;
+  if (ir->M2 > 0) {
+    CU(cudaMallocAsync(&ir->d_H2, sizeof(float2) * (size_t)nch * (B + 1) * ir->M2, ctx->stream));
+    launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, nch, B, ir->P, ir->M2, ir->d_H2, ctx->d_tw2, ctx->stream);
+    CU(cudaGetLastError());
+  }
   // no host synchronisation: every later use of the spectra is ordered on the same stream
   return GAC_OK;
 }
@@ -462,6 +496,7 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
   int rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get());
   if (rc) {
     if (ir->d_H) cudaFreeAsync(ir->d_H, ctx->stream);
+    if (ir->d_H2) cudaFreeAsync(ir->d_H2, ctx->stream);
     return rc;
   }
   *out = ir.release();
@@ -472,6 +507,7 @@ extern "C" int gac_ir_destroy(gac_ir* ir) {
   cudaSetDevice(ir->ctx->device);
   // stream-ordered free
   cudaFreeAsync(ir->d_H, ir->ctx->stream);
+  if (ir->d_H2) cudaFreeAsync(ir->d_H2, ir->ctx->stream);
   delete ir;
   return GAC_OK;
 }
@@ -588,6 +624,8 @@ struct RenderEnv {
   int64_t launches = 0;
   int64_t conv_units = 0;
   double alg_bytes = 0, macs = 0;
+  double mac_flops = 0, mac_bytes = 0;  // flops issued / bytes the K6 variant in use has to move (X, H, Y once)
+  int mac_used = 0;                     // K6 variant of the last convolver batch (1 stream, 2/4 tiled, 3 second-level FFT)
   std::map<Sig*, std::pair<const float*, float>> fused;  // GainNode folded into the next convolver's forward FFT
 };
 
@@ -651,8 +689,10 @@ struct ConvItem {
   struct {
     int x;            // which forward spectrum feeds this channel-convolver
     const float2* H;  // packed IR spectra [P16][B]
+    const float2* H2; // second-level IR spectra [B+1][M2] (null: direct MAC)
   } mac[4];
   int P = 0;
+  int M2 = 0, Lh = 0;  // second-level transform length / history blocks (0: direct MAC)
   int n_inv = 0;
   struct {
     int y, y2;        // spectrogram(s) of which channel-convolver(s); y2 = -1: none
@@ -661,7 +701,7 @@ struct ConvItem {
   } inv[2];
 };
 
-static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
+static int conv_batch_direct(RenderEnv& env, std::vector<ConvItem>& items) {
   gac_context* ctx = env.ctx;
   const int B = ctx->B;
   const int TB = ctx->tile_blocks;
@@ -729,6 +769,7 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
         const double P = it.P, C = B + 1;
         env.conv_units += QB;
         env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
+        env.mac_bytes += 8.0 * B * ((double)QB * 2 + P);  // X and Y once, H once
       }
       for (int k = 0; k < it.n_inv; k++) {
         FftInvJob v;
@@ -749,7 +790,11 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
       return std::min(p16, causal);
     };
     std::stable_sort(tiles.begin(), tiles.end(), [&](const MacTile& a, const MacTile& b) { return stages(a) > stages(b); });
-    for (auto& t : tiles) env.macs += (double)stages(t) * 16.0 * TB * 128.0;
+    for (auto& t : tiles) {
+      env.macs += (double)stages(t) * 16.0 * TB * 128.0;
+      env.mac_flops += 8.0 * (double)stages(t) * 16.0 * TB * 128.0;
+    }
+    env.mac_used = ctx->mac_variant == 1 ? 1 : (ctx->mac_variant == 2 ? 2 : 4);
 
     FftFwdJob* dfj = nullptr;
     MacJob* dmj = nullptr;
@@ -768,7 +813,11 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
     if (ctx->mac_variant == 1)
       launch_mac_stream(dmj, (int)mj.size(), QB, B, ctx->stream);
     else
-      { int pmax = 1; for (auto& m : mj) pmax = std::max(pmax, m.P); launch_mac_tiled(dmj, (int)mj.size(), dt, (int)tiles.size(), QB, pmax, B, TB, ctx->mac_variant, ctx->stream); }
+    {
+      int pmax = 1;
+      for (auto& m : mj) pmax = std::max(pmax, m.P);
+      launch_mac_tiled(dmj, (int)mj.size(), dt, (int)tiles.size(), QB, pmax, B, TB, ctx->mac_variant == 2 ? 2 : 0, ctx->stream);
+    }
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
@@ -777,6 +826,124 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
     CU(cudaGetLastError());
     env.launches += (ctx->mac_variant == 1) ? 3 : 4;  // K5, K6 (+ k_mac_dc), K7
     i0 += ni;
+  }
+  return GAC_OK;
+}
+
+// The convolver with the spectral MAC done as a fast convolution along block time (fft2.cu):
+// K5 (transposing) -> k_fft2_conv -> K7 (transposing), over transposed spectrograms XT/YT[chan][B+1][Qs].
+static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) {
+  gac_context* ctx = env.ctx;
+  const int B = ctx->B, C = B + 1;
+  const int64_t QB = env.QB;
+  const int64_t Qs = ((QB + 15) / 16) * 16;  // row stride: rows start 128-byte aligned
+  const size_t sbytes = (size_t)C * Qs * sizeof(float2);
+  int log2m = 0;
+  while ((1 << log2m) < M) log2m++;
+  for (size_t i0 = 0; i0 < items.size();) {
+    size_t ni = 0, nx = 0, ny = 0;
+    while (i0 + ni < items.size()) {
+      const ConvItem& it = items[i0 + ni];
+      if (ni > 0 && (nx + it.n_fwd + ny + it.n_mac) * sbytes > ctx->scratch_budget) break;
+      nx += it.n_fwd;
+      ny += it.n_mac;
+      ni++;
+    }
+    float2 *dX = nullptr, *dY = nullptr;
+    int rc = env.scratch->alloc(&dX, nx * (size_t)C * Qs);
+    if (rc) return rc;
+    rc = env.scratch->alloc(&dY, ny * (size_t)C * Qs);
+    if (rc) return rc;
+    auto& fj = env.keep->make<FftFwdJob>();
+    auto& cj = env.keep->make<Fft2Job>();
+    auto& ij = env.keep->make<FftInvJob>();
+    size_t xi = 0, yi = 0;
+    int max_seg = 0;
+    for (size_t i = 0; i < ni; i++) {
+      ConvItem& it = items[i0 + i];
+      float2* Xc[2] = {nullptr, nullptr};
+      float2* Yc[4] = {nullptr, nullptr, nullptr, nullptr};
+      for (int k = 0; k < it.n_fwd; k++) {
+        Xc[k] = dX + (xi++) * (size_t)C * Qs;
+        FftFwdJob f;
+        f.in = it.fwd[k].in;
+        f.out = Xc[k];
+        f.scale = nullptr;
+        f.gain = it.gain_tab;
+        f.gain_const = it.gain_const;
+        f.n_valid = env.Npad;
+        f.n_blocks = QB;
+        f.gate_lo = it.lo;
+        f.gate_hi = it.hi;
+        f.in2 = it.fwd[k].in2;
+        f.mix_scale = it.fwd[k].mix_scale;
+        fj.push_back(f);
+      }
+      const int V = M - it.Lh;
+      const int nseg = (int)((QB + V - 1) / V);
+      max_seg = std::max(max_seg, nseg);
+      for (int k = 0; k < it.n_mac; k++) {
+        Yc[k] = dY + (yi++) * (size_t)C * Qs;
+        Fft2Job j;
+        j.X = Xc[it.mac[k].x];
+        j.H2 = it.mac[k].H2;
+        j.Y = Yc[k];
+        j.Lh = it.Lh;
+        j.nseg = nseg;
+        cj.push_back(j);
+        const double P = it.P;
+        env.conv_units += QB;
+        env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
+        env.macs += (double)QB * P * C;  // complex MACs the direct sum would need (not issued: see mac_flops)
+        env.mac_flops += (double)nseg * C * (2.0 * 5.0 * M * log2m + 6.0 * M);
+        env.mac_bytes += 8.0 * C * ((double)nseg * M + (double)M + (double)QB);  // XT windows, H2 row, YT
+      }
+      for (int k = 0; k < it.n_inv; k++) {
+        FftInvJob v;
+        v.in = Yc[it.inv[k].y];
+        v.out = it.inv[k].out;
+        v.n_blocks = QB;
+        v.in2 = it.inv[k].y2 >= 0 ? Yc[it.inv[k].y2] : nullptr;
+        v.out2 = it.inv[k].out2;
+        ij.push_back(v);
+      }
+    }
+    env.mac_used = 3;
+    FftFwdJob* dfj = nullptr;
+    Fft2Job* dcj = nullptr;
+    FftInvJob* dij = nullptr;
+    if ((rc = env.scratch->upload(&dfj, fj))) return rc;
+    if ((rc = env.scratch->upload(&dcj, cj))) return rc;
+    if ((rc = env.scratch->upload(&dij, ij))) return rc;
+    int t = env.timer->begin(C_FFT_FWD);
+    launch_rfft_fwd_t(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
+    env.timer->end(t);
+    CU(cudaGetLastError());
+    t = env.timer->begin(C_MAC);
+    launch_fft2_conv(dcj, (int)cj.size(), max_seg, C, M, ctx->d_tw2, QB, Qs, Qs, ctx->stream);
+    env.timer->end(t);
+    CU(cudaGetLastError());
+    t = env.timer->begin(C_FFT_INV);
+    launch_irfft_ola_t(dij, (int)ij.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
+    env.timer->end(t);
+    CU(cudaGetLastError());
+    env.launches += 3;
+    i0 += ni;
+  }
+  return GAC_OK;
+}
+
+// splits the items by K6 variant (direct MAC / second-level FFT of each length) and runs each class batched
+static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
+  std::map<int, std::vector<ConvItem>> classes;
+  for (auto& it : items) {
+    bool f2 = it.M2 > 0;
+    for (int k = 0; k < it.n_mac; k++) f2 = f2 && it.mac[k].H2 != nullptr;
+    classes[f2 ? it.M2 : 0].push_back(it);
+  }
+  for (auto& kv : classes) {
+    int rc = kv.first == 0 ? conv_batch_direct(env, kv.second) : conv_batch_fft2(env, kv.second, kv.first);
+    if (rc) return rc;
   }
   return GAC_OK;
 }
@@ -924,8 +1091,11 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         }
         const gac_ir* ir = op.ir;
         auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
+        auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * ir->M2) : (const float2*)nullptr; };
         ConvItem it;
         it.P = ir->P;
+        it.M2 = ir->d_H2 ? ir->M2 : 0;
+        it.Lh = ir->Lh;
         it.lo = s.lo;
         it.hi = s.hi;
         it.gain_tab = gtab;
@@ -936,7 +1106,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           it.n_fwd = 1;
           it.fwd[0] = {s.p[0], s.ch == 2 ? s.p[1] : nullptr, 1.0f / sqrtf(2.0f)};
           it.n_mac = 1;
-          it.mac[0] = {0, Hch(0)};
+          it.mac[0] = {0, Hch(0), H2ch(0)};
           it.n_inv = 1;
           it.inv[0] = {0, -1, s.p[0], s.p[1]};
           s.ch = 1;
@@ -945,8 +1115,8 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           it.fwd[0] = {s.p[0], nullptr, 1.0f};
           it.fwd[1] = {s.p[1], nullptr, 1.0f};
           it.n_mac = 2;
-          it.mac[0] = {0, Hch(0)};
-          it.mac[1] = {1, Hch(1)};
+          it.mac[0] = {0, Hch(0), H2ch(0)};
+          it.mac[1] = {1, Hch(1), H2ch(1)};
           it.n_inv = 2;
           it.inv[0] = {0, -1, s.p[0], nullptr};
           it.inv[1] = {1, -1, s.p[1], nullptr};
@@ -957,10 +1127,10 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           it.fwd[0] = {s.p[0], nullptr, 1.0f};
           it.fwd[1] = {s.p[1], nullptr, 1.0f};
           it.n_mac = 4;
-          it.mac[0] = {0, Hch(0)};
-          it.mac[1] = {1, Hch(2)};
-          it.mac[2] = {0, Hch(1)};
-          it.mac[3] = {1, Hch(3)};
+          it.mac[0] = {0, Hch(0), H2ch(0)};
+          it.mac[1] = {1, Hch(2), H2ch(2)};
+          it.mac[2] = {0, Hch(1), H2ch(1)};
+          it.mac[3] = {1, Hch(3), H2ch(3)};
           it.n_inv = 2;
           it.inv[0] = {0, 1, s.p[0], nullptr};
           it.inv[1] = {2, 3, s.p[1], nullptr};

@@ -505,6 +505,9 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   st.conv_units = env.conv_units;
   st.algorithmic_bytes = env.alg_bytes;
   st.mac_complex_macs = env.macs;
+  st.mac_flops = env.mac_flops;
+  st.mac_bytes_moved = env.mac_bytes;
+  st.mac_variant_used = env.mac_used;
   st.kernel_launches = env.launches;
   st.voices = (int64_t)S;
   st.frames = a.n_frames;
@@ -638,6 +641,60 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
   if (!X || !H || !Y || n_signals <= 0 || n_blocks <= 0 || n_partitions <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
   CU(cudaSetDevice(ctx->device));
   const int B = ctx->B;
+  if (variant == 3) {
+    // second-level FFT path (fft2.cu): transposed spectrograms XT/YT[s][B+1][Qs]; the packed (DC, Nyquist) bin is
+    // unpacked into rows 0 and B on the way in and packed again on the way out (host side: this is a test entry point)
+    int Lh = 0;
+    const int M = fft2_pick_m(n_partitions, &Lh);
+    if (M <= 0) return fail(GAC_ERR_UNSUPPORTED, "%d partitions exceed the second-level transform (use variant 0/2)", n_partitions);
+    const int C = B + 1;
+    const int64_t Qs = ((n_blocks + 15) / 16) * 16;
+    const int P16 = std::max(16, ((n_partitions + 15) / 16) * 16);
+    std::vector<float2> xt((size_t)n_signals * C * Qs, make_float2(0.f, 0.f));
+    const float2* Xh = reinterpret_cast<const float2*>(X);
+    for (int s = 0; s < n_signals; s++)
+      for (int64_t b = 0; b < n_blocks; b++)
+        for (int k = 0; k < B; k++) {
+          const float2 v = Xh[((size_t)s * n_blocks + b) * B + k];
+          if (k == 0) {
+            xt[((size_t)s * C + 0) * Qs + b] = make_float2(v.x, 0.f);
+            xt[((size_t)s * C + B) * Qs + b] = make_float2(v.y, 0.f);
+          } else {
+            xt[((size_t)s * C + k) * Qs + b] = v;
+          }
+        }
+    DevBuf dXT, dYT, dH, dH2, dj;
+    int rc;
+    if ((rc = dev_alloc(dXT, xt.size() * 8)) || (rc = dev_alloc(dYT, xt.size() * 8)) || (rc = dev_alloc(dH, (size_t)n_signals * P16 * B * 8)) ||
+        (rc = dev_alloc(dH2, (size_t)n_signals * C * M * 8)) || (rc = dev_alloc(dj, sizeof(Fft2Job) * n_signals)))
+      return rc;
+    CU(cudaMemcpyAsync(dXT.p, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dH.p, 0, (size_t)n_signals * P16 * B * 8, ctx->stream));
+    for (int s = 0; s < n_signals; s++)
+      CU(cudaMemcpyAsync(dH.as<float2>() + (size_t)s * P16 * B, H + (size_t)s * n_partitions * B * 2, (size_t)n_partitions * B * 8,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    launch_fft2_prep(dH.as<float2>(), (int64_t)P16 * B, n_signals, B, n_partitions, M, dH2.as<float2>(), ctx->d_tw2, ctx->stream);
+    const int V = M - Lh;
+    const int nseg = (int)((n_blocks + V - 1) / V);
+    std::vector<Fft2Job> jobs(n_signals);
+    for (int s = 0; s < n_signals; s++)
+      jobs[s] = Fft2Job{dXT.as<float2>() + (size_t)s * C * Qs, dH2.as<float2>() + (size_t)s * C * M, dYT.as<float2>() + (size_t)s * C * Qs, Lh, nseg};
+    CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(Fft2Job) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
+    launch_fft2_conv(dj.as<Fft2Job>(), n_signals, nseg, C, M, ctx->d_tw2, n_blocks, Qs, Qs, ctx->stream);
+    CU(cudaGetLastError());
+    std::vector<float2> yt(xt.size());
+    CU(cudaMemcpyAsync(yt.data(), dYT.p, yt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float2* Yh = reinterpret_cast<float2*>(Y);
+    for (int s = 0; s < n_signals; s++)
+      for (int64_t b = 0; b < n_blocks; b++)
+        for (int k = 0; k < B; k++) {
+          float2 v = yt[((size_t)s * C + k) * Qs + b];
+          if (k == 0) v.y = yt[((size_t)s * C + B) * Qs + b].x;
+          Yh[((size_t)s * n_blocks + b) * B + k] = v;
+        }
+    return GAC_OK;
+  }
   const int TB = ctx->tile_blocks;
   const int64_t QBpad = ((n_blocks + TB - 1) / TB) * TB;
   const int64_t rowsX = TB + QBpad;
@@ -668,7 +725,7 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
   if (variant == 1)
     launch_mac_stream(dj.as<MacJob>(), (int)jobs.size(), n_blocks, B, ctx->stream);
   else
-    launch_mac_tiled(dj.as<MacJob>(), (int)jobs.size(), dt.as<MacTile>(), (int)tiles.size(), n_blocks, n_partitions, B, TB, variant, ctx->stream);
+    launch_mac_tiled(dj.as<MacJob>(), (int)jobs.size(), dt.as<MacTile>(), (int)tiles.size(), n_blocks, n_partitions, B, TB, variant == 2 ? 2 : 0, ctx->stream);
   CU(cudaGetLastError());
   for (int s = 0; s < n_signals; s++)
     CU(cudaMemcpyAsync(Y + (size_t)s * n_blocks * B * 2, dY.as<float2>() + (size_t)s * QBpad * B, (size_t)n_blocks * B * 8, cudaMemcpyDeviceToHost,
@@ -696,8 +753,9 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
   irh.ctx = ctx;
   irh.nch = n_signals;
   rc = ir_prepare_device(ctx, dir.as<float>(), stride, n_signals, ir_frames, normalize != 0, &irh);
-  DevBuf holdH;
+  DevBuf holdH, holdH2;
   holdH.p = irh.d_H;  // (the scales live at the end of the same allocation)
+  holdH2.p = irh.d_H2;
   if (rc) return rc;
   DevBuf dx;
   if ((rc = dev_alloc(dx, (size_t)n_signals * Npad * 4))) return rc;
@@ -726,8 +784,10 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
       it.lo = 0;
       it.hi = Npad;
       it.n_mac = 1;
-      it.mac[0] = {0, irh.d_H + (size_t)s * irh.P16 * B};
+      it.mac[0] = {0, irh.d_H + (size_t)s * irh.P16 * B, irh.d_H2 ? irh.d_H2 + (size_t)s * (B + 1) * irh.M2 : nullptr};
       it.P = irh.P;
+      it.M2 = irh.d_H2 ? irh.M2 : 0;
+      it.Lh = irh.Lh;
       it.n_inv = 1;
       it.inv[0] = {0, -1, xs, nullptr};
     }
@@ -739,6 +799,9 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
     st.conv_units = env.conv_units;
     st.algorithmic_bytes = env.alg_bytes;
     st.mac_complex_macs = env.macs;
+    st.mac_flops = env.mac_flops;
+    st.mac_bytes_moved = env.mac_bytes;
+    st.mac_variant_used = env.mac_used;
     st.kernel_launches = env.launches;
     st.voices = n_signals;
     st.frames = n_frames;

@@ -1,0 +1,191 @@
+// fft2.cu — K6 as a fast convolution along BLOCK TIME ("second-level FFT").
+//
+// Replaces PartitionedConvolver.ProcessSpectralConvolution (PartitionedConvolver.cs:154-223) together with the
+// frequency-domain delay line it walks (:115-128).  For one channel-convolver and one frequency bin k the reference
+// computes, quantum after quantum,
+//     Y[b][k] = sum_{p=0}^{P-1} X[b-p][k] * H[p][k]                       (complex, X[<0] = 0)
+// i.e. a causal linear convolution of the bin's input-spectrum sequence X[.][k] with the bin's partition sequence
+// H[.][k] along the block index b.  Offline, the whole sequence X[0..Q) is known, so that convolution is done with a
+// second FFT of length M along b (overlap-save: every segment of M input spectra yields V = M - Lh valid outputs,
+// Lh >= P-1):  Q*P complex MACs per bin become (Q/V) * (2 * 5 M log2 M + 6 M) flops.  For the BASELINE shapes
+// (P = 750, Q = 4500, M = 2048) that is 27x fewer flops than the direct sum, and the kernel is no longer bound by
+// the FP32 pipe but by moving X, H2 and Y through HBM once.
+//
+// Layout: "transposed" spectrograms  XT[chan][k][b]  (k = 0..B, C = B+1 rows as in the reference, :41; row 0 = DC and
+// row B = Nyquist, both real sequences stored with zero imaginary part; b contiguous), written by the transposing
+// variant of K5 and read by the transposing variant of K7 (fft.cu).  The prepared second-level IR spectra are
+// H2[irchan][k][M] (digit-reversed along M, scaled by 1/M), built once per impulse response by k_fft2_prep.
+//
+// One CTA = one (channel-convolver, bin, segment): M/8 threads x 8 points, radix-8 in-place FFT through shared
+// memory (fft2_core.cuh), pointwise product, mirrored inverse, store of the V valid outputs.
+#include <algorithm>
+
+#include "fft2_core.cuh"
+#include "gac_kernels.h"
+
+namespace gac {
+
+using namespace f2;
+
+int fft2_pick_m(int P, int* Lh_out) {
+  int Lh = ((std::max(P - 1, 0) + 15) / 16) * 16;
+  if (Lh_out) *Lh_out = Lh;
+  for (int M = 512; M <= 8192; M *= 2)
+    if (M - Lh >= M / 2) return M;
+  if (8192 - Lh >= 1024) return 8192;
+  return 0;  // impulse response too long for one second-level transform: the caller falls back to the direct MAC
+}
+
+template <int M, int S>
+__device__ __forceinline__ void fwd_rest(float2 (&v)[8], float2* sm, const float2* __restrict__ tw, int t) {
+  if constexpr (S > 8) {
+    fwd_stage<S, true>(v, sm, tw, t);
+    __syncthreads();
+    fwd_rest<M, S / 8>(v, sm, tw, t);
+  }
+}
+template <int M, int S>
+__device__ __forceinline__ void inv_rest(float2 (&v)[8], float2* sm, const float2* __restrict__ tw, int t) {
+  // S = span of the stage to run now; stages below M store and hand over to the next larger span
+  if constexpr (S < M) {
+    inv_stage<S, true>(v, sm, tw, t);
+    __syncthreads();
+    inv_rest<M, S * 8>(v, sm, tw, t);
+  } else {
+    inv_stage<M, false>(v, sm, tw, t);
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(M / 8) k_fft2_conv(const Fft2Job* __restrict__ jobs, const float2* __restrict__ tw, int64_t n_blocks,
+                                                     int64_t xs, int64_t ys) {
+  using P = Plan<M>;
+  constexpr int T = P::T;
+  extern __shared__ __align__(16) float2 sm[];
+  const Fft2Job job = jobs[blockIdx.z];
+  const int seg = blockIdx.x;
+  if (seg >= job.nseg) return;
+  const int k = blockIdx.y;
+  const int t = threadIdx.x;
+  const int V = M - job.Lh;
+  const int64_t b_first = (int64_t)seg * V - job.Lh;  // block index of window element 0
+  const float2* __restrict__ xrow = job.X + (int64_t)k * xs;
+  float2 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int64_t b = b_first + t + T * j;
+    v[j] = (b >= 0 && b < n_blocks) ? xrow[b] : make_float2(0.f, 0.f);
+  }
+  // this bin's IR spectrum at positions 8t .. 8t+7 (issued early: consumed after the forward transform)
+  float4 h4[4];
+  {
+    const float4* __restrict__ hp = reinterpret_cast<const float4*>(job.H2 + (int64_t)k * M + 8 * t);
+#pragma unroll
+    for (int q = 0; q < 4; q++) h4[q] = hp[q];
+  }
+  fwd_stage<M, false>(v, sm, tw, t);
+  __syncthreads();
+  fwd_rest<M, M / 8>(v, sm, tw, t);
+  float2 u[8];
+  to_points<P::TAIL>(u, sm, t);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    u[2 * q] = cmulf(u[2 * q], make_float2(h4[q].x, h4[q].y));
+    u[2 * q + 1] = cmulf(u[2 * q + 1], make_float2(h4[q].z, h4[q].w));
+  }
+  from_points<P::TAIL>(u, sm, t);
+  __syncthreads();
+  inv_rest<M, (P::TAIL == 1 ? 64 : P::SL)>(v, sm, tw, t);
+  float2* __restrict__ yrow = job.Y + (int64_t)k * ys;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int n = t + T * j;
+    const int64_t b = b_first + n;
+    if (n >= job.Lh && b < n_blocks) yrow[b] = v[j];
+  }
+}
+
+// H2[ch][k][.] = forward second-level FFT of the bin-k partition sequence H[ch][0..P)[k], zero-padded to M, times 1/M.
+// H is the packed first-level layout [ch][P16][B] (bin 0 = (DC, Nyquist)); rows k = 0 and k = B unpack it.
+template <int M>
+__global__ void __launch_bounds__(M / 8) k_fft2_prep(const float2* __restrict__ H, int64_t h_ch_stride, int B, int P, float2* __restrict__ H2,
+                                                     const float2* __restrict__ tw) {
+  using Pl = Plan<M>;
+  constexpr int T = Pl::T;
+  extern __shared__ __align__(16) float2 sm[];
+  const int k = blockIdx.x, ch = blockIdx.y, t = threadIdx.x;
+  const float2* __restrict__ Hc = H + (int64_t)ch * h_ch_stride;
+  const int col = (k == B) ? 0 : k;
+  float2 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int p = t + T * j;
+    float2 h = make_float2(0.f, 0.f);
+    if (p < P) {
+      h = Hc[(int64_t)p * B + col];
+      if (k == 0) h = make_float2(h.x, 0.f);
+      else if (k == B) h = make_float2(h.y, 0.f);
+    }
+    v[j] = h;
+  }
+  fwd_stage<M, false>(v, sm, tw, t);
+  __syncthreads();
+  fwd_rest<M, M / 8>(v, sm, tw, t);
+  float2 u[8];
+  to_points<Pl::TAIL>(u, sm, t);
+  const float sc = 1.0f / (float)M;
+  float4* __restrict__ out = reinterpret_cast<float4*>(H2 + ((int64_t)ch * (B + 1) + k) * M + 8 * t);
+#pragma unroll
+  for (int q = 0; q < 4; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
+}
+
+template <int M>
+static void conv_t(const Fft2Job* d_jobs, dim3 grid, const float2* d_tw2, int64_t n_blocks, int64_t xs, int64_t ys, cudaStream_t s) {
+  constexpr size_t smem = sizeof(float2) * smem_elems(M);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(k_fft2_conv<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  k_fft2_conv<M><<<grid, M / 8, smem, s>>>(d_jobs, d_tw2, n_blocks, xs, ys);
+}
+template <int M>
+static void prep_t(const float2* d_H, int64_t h_ch_stride, dim3 grid, int B, int P, float2* d_H2, const float2* d_tw2, cudaStream_t s) {
+  constexpr size_t smem = sizeof(float2) * smem_elems(M);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(k_fft2_prep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  k_fft2_prep<M><<<grid, M / 8, smem, s>>>(d_H, h_ch_stride, B, P, d_H2, d_tw2);
+}
+
+void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tw2, int64_t n_blocks, int64_t xs, int64_t ys,
+                      cudaStream_t s) {
+  if (n_jobs <= 0 || max_seg <= 0) return;
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+    dim3 grid((unsigned)max_seg, (unsigned)C, (unsigned)nj);
+    switch (M) {
+      case 512: conv_t<512>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
+      case 1024: conv_t<1024>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
+      case 2048: conv_t<2048>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
+      case 4096: conv_t<4096>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
+      case 8192: conv_t<8192>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
+    }
+  }
+}
+
+void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, int P, int M, float2* d_H2, const float2* d_tw2, cudaStream_t s) {
+  if (n_ch <= 0) return;
+  dim3 grid((unsigned)(B + 1), (unsigned)n_ch);
+  switch (M) {
+    case 512: prep_t<512>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
+    case 1024: prep_t<1024>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
+    case 2048: prep_t<2048>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
+    case 4096: prep_t<4096>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
+    case 8192: prep_t<8192>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
+  }
+}
+
+}  // namespace gac

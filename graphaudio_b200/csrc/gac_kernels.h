@@ -29,6 +29,9 @@ struct FftFwdJob {
   float mix_scale = 1.0f;
 };
 void launch_rfft_fwd(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
+// transposing variant (feeds fft2.cu): job.out is the XT channel base; bin k of block b lands at out[k*t_stride + b],
+// k = 0..B (row 0 = (DC, 0), row B = (Nyquist, 0))
+void launch_rfft_fwd_t(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tw, cudaStream_t s);
 // the same transform for the channels of ONE buffer, described arithmetically and passed by value (no job array upload)
 struct FftFwdUniform {
   const float* in_base;     // channel y at in_base + y*in_stride
@@ -48,6 +51,9 @@ struct FftInvJob {
   float* out2 = nullptr;        // optional second destination receiving the same samples (mono -> both rows)
 };
 void launch_irfft_ola(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
+// transposing variant: job.in / job.in2 are YT channel bases (bin k of block b at in[k*t_stride + b], k = 0..B); with in2 the
+// two spectrograms are summed BEFORE the inverse transform (the transform is linear; ConvolverNode.Sum adds afterwards)
+void launch_irfft_ola_t(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tw, cudaStream_t s);
 
 // ------------------------------------------------------------------ spectral MAC (mac.cu)
 // One job = one channel-convolver bin-group of 128 bins:  Y[b][k] = sum_p X[b-p][k] * H[p][k].
@@ -70,6 +76,23 @@ int mac_tile_blocks(int variant);  // output blocks per CTA for the tiled kernel
 void launch_mac_tiled(const MacJob* d_jobs, int n_jobs, const MacTile* d_tiles, int n_tiles, int64_t n_blocks, int p_max, int stride,
                       int tile_blocks, int flavour, cudaStream_t s);
 void launch_mac_stream(const MacJob* d_jobs, int n_jobs, int64_t n_blocks, int stride, cudaStream_t s);
+
+// ------------------------------------------------------------------ second-level FFT MAC (fft2.cu)
+// One job = one channel-convolver over transposed spectrograms: row k (k = 0..B) of XT/YT at X + k*xs / Y + k*ys.
+struct Fft2Job {
+  const float2* X;   // XT channel base
+  const float2* H2;  // prepared second-level IR spectra of the IR channel: [B+1][M]
+  float2* Y;         // YT channel base
+  int Lh;            // history blocks per segment (>= P-1, multiple of 16); V = M - Lh valid outputs per segment
+  int nseg;          // ceil(n_blocks / V)
+};
+constexpr int kFft2TwLen = 8192;  // twiddle table exp(-2 pi i e / 8192)
+// second-level transform length for P partitions (512..8192), 0 if the IR is too long; *Lh = history length
+int fft2_pick_m(int P, int* Lh);
+void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tw2, int64_t n_blocks, int64_t xs, int64_t ys,
+                      cudaStream_t s);
+// H: packed first-level IR spectra [n_ch][...h_ch_stride...] rows of B -> H2 [n_ch][B+1][M]
+void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, int P, int M, float2* d_H2, const float2* d_tw2, cudaStream_t s);
 
 // ------------------------------------------------------------------ node kernels (nodes.cu)
 struct DevEvent {  // bit-compatible with gac_event / AudioParam.cs:360-367

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GAC_ABI_VERSION 1
+#define GAC_ABI_VERSION 2
 
 /* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */
 typedef enum gac_status {
@@ -58,9 +58,14 @@ typedef struct gac_context_desc {
                       ConvolverNode uses, ConvolverNode.cs:55) or 256/512 (offline-only option;
                       same linear convolution, different rounding points).  0 = 128.                 */
   int device_id;   /* CUDA ordinal; -1 = current device                                              */
-  int mac_variant; /* 0 = default (register-tiled, packed FFMA2), 2 = register-tiled scalar FFMA,
-                      1 = streaming one-pass-per-quantum (reference op order, unfused; the T=1
-                      roofline contract of SURVEY.md §8d)                                            */
+  int mac_variant; /* spectral MAC (K6) algorithm:
+                      0 = default: fast convolution along block time (a second FFT over the partition
+                          axis, csrc/fft2.cu) for impulse responses of >= 64 partitions, register-tiled
+                          direct sum (packed FFMA2) below;
+                      1 = streaming one-pass-per-quantum direct sum (reference op order, unfused: the
+                          T=1 roofline contract of SURVEY.md §8d; bit-exact against the oracle);
+                      2 = register-tiled direct sum, scalar FFMA;   4 = register-tiled, packed FFMA2;
+                      3 = second-level FFT for every impulse response                                */
   int tile_blocks; /* output blocks per CTA of the tiled MAC: 32 (default, 0) or 64                  */
   int flags;       /* GAC_FLAG_*                                                                     */
   int reserved;
@@ -231,10 +236,14 @@ typedef struct gac_stats {
   double ms_d2h;
   int64_t conv_units;          /* channel-convolver blocks processed (SURVEY.md §8d "unit")         */
   double algorithmic_bytes;    /* Σ units · (16·P·C + 8·C + 8·B), the T=1 contract                  */
-  double mac_complex_macs;     /* complex MACs actually issued by K6 (after causal skipping)        */
+  double mac_complex_macs;     /* complex MACs of the direct sum (after causal skipping)            */
   int64_t kernel_launches;     /* kernels launched by the last render                               */
   int64_t voices;
   int64_t frames;
+  double mac_flops;            /* flops K6 actually issued (direct: 8/cMAC; second-level FFT: 2 FFTs + product per segment) */
+  double mac_bytes_moved;      /* bytes the K6 variant in use has to move through HBM (X, H, Y once) */
+  int32_t mac_variant_used;    /* 1 stream, 2/4 register-tiled, 3 second-level FFT (last convolver batch) */
+  int32_t reserved;
 } gac_stats;
 int gac_get_stats(gac_context* ctx, gac_stats* out);
 

@@ -180,14 +180,14 @@ __global__ void __launch_bounds__(1024) k_biquad_output(const BiquadJob* __restr
 }
 
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, float4* d_s1t, float* d_wt, cudaStream_t s) {
+                   int32_t* d_ent, float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad, cudaStream_t s) {
   if (n_jobs <= 0 || n_frames <= 0) return;
   const int groups = (n_jobs + 15) / 16;
   const unsigned n_slabs = (unsigned)(n_frames / 32);
   k_biquad_select<<<dim3((unsigned)((n_quanta + kSelQ - 1) / kSelQ), (unsigned)n_jobs), kSelQ, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last);
   k_biquad_entry<<<(unsigned)((n_jobs + 63) / 64), 64, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
   k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 1024, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t);
-  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_wt, s);
+  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_wt, d_states, d_first_bad, s);
   k_biquad_output<<<dim3(n_slabs, (unsigned)groups), 1024, 0, s>>>(d_jobs, n_jobs, n_frames, d_wt);
 }
 

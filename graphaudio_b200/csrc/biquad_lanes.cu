@@ -2,6 +2,17 @@
 //     w[n] = x[n] - a1[n]*w[n-1] - a2[n]*w[n-2]          (float32, left to right, unfused; compiled with --fmad=false)
 // One lane per (voice, channel); a warp owns one 32-row group of the slab-transposed stream (layout: biquad.cu header).
 //
+// Time is cut into segments that run CONCURRENTLY, speculate-and-verify, still bit-exact:
+//   * segment k > 0 starts kWarm frames early from the state (0, 0) and discards what it computes before its own first
+//     frame.  A stable biquad forgets its state, and in float32 two trajectories fed the same input do not merely get
+//     close, they become bit-identical (measured: after ~300 frames for the BASELINE lowpass sweep, a few thousand for
+//     Q = 8 at 1 kHz), after which they stay identical forever because the recursion is deterministic;
+//   * every segment records the state it started its own frames with and the state it ended with; k_biquad_verify checks
+//     end[k-1] == start[k] BITWISE along the chain.  The first segment is exact by construction, so if every link matches,
+//     every sample equals the sequential result bit for bit;
+//   * if a link does not match (very low cutoff / very high Q never merge), the repair launch recomputes that 32-row group
+//     sequentially from the last verified state: the result is always exact, only the speed-up is lost for that group.
+//
 // The recursion is latency-bound (three dependent FP32 ops per frame), so everything else is kept out of the warp's
 // instruction stream: 128 frames of the whole group are ONE contiguous 64 KB block that lane 0 fetches with a single
 // TMA bulk copy (cp.async.bulk + mbarrier, 3-stage ring); lane r reads (x, a1, a2) of frame i at [i][r] — consecutive lanes,
@@ -40,12 +51,18 @@ __device__ __forceinline__ void bq_bulk_s2g(void* dst, uint32_t src, uint32_t by
 
 constexpr int kSlab = 128;   // frames per pipeline stage = 4 consecutive 32-frame layout slabs (contiguous in HBM)
 constexpr int kStages = 3;   // stages in flight
+constexpr int kWarmSlabs = 64;  // warm-up of a speculative segment: 64 * 128 = 8192 frames
 constexpr int kStageBytes = kSlab * 32 * 16;  // 64 KB
 constexpr int kWtBytes = kSlab * 32 * 4;      // 16 KB
 constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 2 * kWtBytes + 64;
 
+// states: float2 [groups][n_seg][2 (start, end)][32 rows];  first_bad: int [groups] (n_seg = all links verified)
+// REPAIR = false: grid (groups, n_seg), segment blockIdx.y runs speculatively.  REPAIR = true: grid (groups), the group
+// re-runs sequentially from segment first_bad[g] (does nothing if every link matched).
+template <bool REPAIR>
 __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
-                                                     const float4* __restrict__ s1t, float* __restrict__ wt_all) {
+                                                     const float4* __restrict__ s1t, float* __restrict__ wt_all, int seg_slabs, int n_seg,
+                                                     float2* __restrict__ states, const int* __restrict__ first_bad) {
   extern __shared__ __align__(128) unsigned char lanes_smem[];
   float* wt = reinterpret_cast<float*>(lanes_smem + kStages * kStageBytes);                    // [2][32 frames][32 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(lanes_smem + kStages * kStageBytes + 2 * kWtBytes);  // [kStages]
@@ -60,10 +77,19 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     hi = hi2 > hi ? hi2 : hi;
   }
   if (hi <= lo) return;
-  const int n_slabs = (int)((hi - lo) / kSlab);        // ranges are multiples of 128 frames
+  const int total_slabs = (int)((hi - lo) / kSlab);    // ranges are multiples of 128 frames
+  // this CTA's slabs (relative to lo): [s_first, s_end), of which [s_first, s_own) is warm-up (computed, not stored)
+  int seg = REPAIR ? first_bad[blockIdx.x] : (int)blockIdx.y;
+  if (seg >= n_seg) return;
+  const int s_own = seg * seg_slabs;
+  if (s_own >= total_slabs) return;
+  const int s_end = REPAIR ? total_slabs : (s_own + seg_slabs < total_slabs ? s_own + seg_slabs : total_slabs);
+  const int s_first = (REPAIR || seg == 0) ? s_own : (s_own - kWarmSlabs > 0 ? s_own - kWarmSlabs : 0);
+  const int n_slabs = s_end - s_first;
+  float2* st_group = states + (size_t)blockIdx.x * n_seg * 64;
   // element (frame n, row r) of group g lives at (g * n_frames + n) * 32 + r in both streams
-  const float4* __restrict__ src = s1t + ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo) * 32;
-  float* __restrict__ dst = wt_all + ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo) * 32;
+  const float4* __restrict__ src = s1t + ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo + (size_t)s_first * kSlab) * 32;
+  float* __restrict__ dst = wt_all + ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo + (size_t)s_first * kSlab) * 32;
   const uint32_t bar0 = bq_smem_u32(bars);
   const uint32_t stage0 = bq_smem_u32(lanes_smem);
   const uint32_t wt0 = bq_smem_u32(wt);
@@ -84,14 +110,21 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
 
   for (int s = 0; s < kStages - 1; s++) issue(s);
   float w1 = 0.f, w2 = 0.f;
+  if (REPAIR && seg > 0) {  // the last verified state: what segment seg-1 ended with
+    const float2 e = st_group[((size_t)(seg - 1) * 2 + 1) * 32 + lane];
+    w1 = e.x;
+    w2 = e.y;
+  }
+  const int n_warm = s_own - s_first;
   uint32_t phases = 0u;  // bit st = parity to wait for on stage st
   for (int s = 0; s < n_slabs; s++) {
+    if (s == n_warm && !REPAIR) st_group[((size_t)seg * 2 + 0) * 32 + lane] = make_float2(w1, w2);  // state at the segment's first own frame
     __syncwarp();                // every lane is done reading the stage that is refilled next
     issue(s + kStages - 1);
     const int st = s % kStages;
     bq_mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
     phases ^= 1u << st;
-    const int64_t base = lo + (int64_t)s * kSlab;
+    const int64_t base = lo + (int64_t)(s_first + s) * kSlab;
     const bool act = base >= my_lo && base < my_hi;  // silent-flagged quanta: state untouched (:103-108)
     // the w tile written two iterations ago must have been read out by its bulk store before it is overwritten
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -125,20 +158,67 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
     __syncwarp();
     if (lane == 0) {
-      bq_bulk_s2g(dst + (size_t)s * (kSlab * 32), wt0 + (uint32_t)((s & 1) * kWtBytes), kWtBytes);
+      if (s >= n_warm) bq_bulk_s2g(dst + (size_t)s * (kSlab * 32), wt0 + (uint32_t)((s & 1) * kWtBytes), kWtBytes);  // warm-up output is discarded
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (REPAIR) {
+    // (the chain behind the repaired segment is not needed any more)
+  } else {
+    st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
+  }
 }
 
-void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, float* d_wt, cudaStream_t s) {
+// first_bad[g] = first segment k >= 1 whose speculative start state differs (bitwise, any of the 32 rows) from the state
+// segment k-1 ended with; n_seg if the whole chain verifies.  One warp per group.
+__global__ void __launch_bounds__(32) k_biquad_verify(int n_seg, const float2* __restrict__ states, int* __restrict__ first_bad) {
+  const int lane = threadIdx.x;
+  const uint2* st = reinterpret_cast<const uint2*>(states) + (size_t)blockIdx.x * n_seg * 64;
+  int bad = n_seg;
+  for (int k = 1; k < n_seg; k++) {
+    const uint2 e = st[((size_t)(k - 1) * 2 + 1) * 32 + lane];
+    const uint2 b = st[((size_t)k * 2 + 0) * 32 + lane];
+    const bool differ = e.x != b.x || e.y != b.y;
+    if (__any_sync(0xffffffffu, differ)) {
+      bad = k;
+      break;
+    }
+  }
+  if (lane == 0) first_bad[blockIdx.x] = bad;
+}
+
+int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs_out) {
+  // one CTA (= one warp, 208 KB of staging) per SM: as many concurrent segments as there are SMs per group, but segments no
+  // shorter than the warm-up (below that the redundant work outweighs the concurrency)
+  const int groups = (n_jobs + 15) / 16;
+  const int total_slabs = (int)((n_frames + kSlab - 1) / kSlab);
+  int n_seg = 148 / (groups > 0 ? groups : 1);
+  if (n_seg < 1) n_seg = 1;
+  int seg_slabs = (total_slabs + n_seg - 1) / n_seg;
+  if (seg_slabs < kWarmSlabs) seg_slabs = kWarmSlabs;
+  n_seg = (total_slabs + seg_slabs - 1) / seg_slabs;
+  if (n_seg < 1) n_seg = 1;
+  if (seg_slabs_out) *seg_slabs_out = seg_slabs;
+  return n_seg;
+}
+
+void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad,
+                         cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_biquad_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
+    cudaFuncSetAttribute(k_biquad_lanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
+    cudaFuncSetAttribute(k_biquad_lanes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
     attr = true;
   }
-  k_biquad_lanes<<<(unsigned)((n_jobs + 15) / 16), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_wt);
+  const unsigned groups = (unsigned)((n_jobs + 15) / 16);
+  int seg_slabs = 0;
+  const int n_seg = biquad_lane_segments(n_jobs, n_frames, &seg_slabs);
+  k_biquad_lanes<false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_wt, seg_slabs, n_seg, d_states, nullptr);
+  if (n_seg > 1) {
+    k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad);
+    k_biquad_lanes<true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_wt, seg_slabs, n_seg, d_states, d_first_bad);
+  }
 }
 
 }  // namespace gac

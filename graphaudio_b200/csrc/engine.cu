@@ -79,6 +79,7 @@ struct gac_context {
   cudaStream_t stream = nullptr;
   float2* d_tw = nullptr;  // e^{-2 pi i k/(2B)}, k < B
   float2* d_tw2 = nullptr; // e^{-2 pi i e/8192}, e < 8192: twiddles of the second-level (block-time) FFT, fft2.cu
+  float2* d_tab16 = nullptr; // (points into the d_tw2 allocation) per-M twiddle tables of the radix-16 plan
   std::vector<double> h_bt;  // block start times, accumulated as AudioContextBase.cs:78-79
   double* d_bt = nullptr;
   int64_t bt_cap = 0;
@@ -333,14 +334,16 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   {
     static std::vector<float2> tw2;  // same for every context: computed once per process
     if (tw2.empty()) {
-      tw2.resize(kFft2TwLen);
+      tw2.resize(kFft2TwLen + fft2_table_total());
       for (int e = 0; e < kFft2TwLen; e++) {
         double a = -2.0 * pi * (double)e / (double)kFft2TwLen;
         tw2[e] = make_float2((float)std::cos(a), (float)std::sin(a));
       }
+      fft2_fill_tables(tw2.data() + kFft2TwLen);
     }
-    CU(cudaMallocAsync(&ctx->d_tw2, sizeof(float2) * kFft2TwLen, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_tw2, tw2.data(), sizeof(float2) * kFft2TwLen, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMallocAsync(&ctx->d_tw2, sizeof(float2) * tw2.size(), ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_tw2, tw2.data(), sizeof(float2) * tw2.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->d_tab16 = ctx->d_tw2 + kFft2TwLen;
   }
   int rc = ensure_block_times(ctx.get(), 8192);
   if (rc) return rc;
@@ -466,7 +469,7 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   if (ir->M2 > 0 && !use_fft2(ctx, ir->P, ir->M2)) ir->M2 = 0;
   if (ir->M2 > 0) {
     CU(cudaMallocAsync(&ir->d_H2, sizeof(float2) * (size_t)nch * (B + 1) * ir->M2, ctx->stream));
-    launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, nch, B, ir->P, ir->M2, ir->d_H2, ctx->d_tw2, ctx->stream);
+    launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, nch, B, ir->P, ir->M2, ir->d_H2, ctx->d_tw2, ctx->d_tab16, ctx->stream);
     CU(cudaGetLastError());
   }
   // no host synchronisation: every later use of the spectra is ordered on the same stream
@@ -920,7 +923,7 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_MAC);
-    launch_fft2_conv(dcj, (int)cj.size(), max_seg, C, M, ctx->d_tw2, QB, Qs, Qs, ctx->stream);
+    launch_fft2_conv(dcj, (int)cj.size(), max_seg, C, M, ctx->d_tw2, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
@@ -1054,10 +1057,15 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if ((rc = env.scratch->upload(&dbj, bj))) return rc;
         if ((rc = env.scratch->alloc(&dlast, nk * 2 * (size_t)env.NQ))) return rc;
         if ((rc = env.scratch->alloc(&dent, nk * 2 * (size_t)env.NQ))) return rc;
+        float2* dstates = nullptr;
+        int* dbad = nullptr;
+        const int n_seg = biquad_lane_segments((int)nk, env.Npad, nullptr);
+        if ((rc = env.scratch->alloc(&dstates, ((nk + 15) / 16) * (size_t)n_seg * 64))) return rc;
+        if ((rc = env.scratch->alloc(&dbad, (nk + 15) / 16))) return rc;
         int t = env.timer->begin(C_BIQUAD);
-        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, w_all, ctx->stream);
+        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, w_all, dstates, dbad, ctx->stream);
         env.timer->end(t);
-        env.launches += 5;
+        env.launches += n_seg > 1 ? 7 : 5;
         CU(cudaGetLastError());
       }
     }

@@ -673,14 +673,14 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
     for (int s = 0; s < n_signals; s++)
       CU(cudaMemcpyAsync(dH.as<float2>() + (size_t)s * P16 * B, H + (size_t)s * n_partitions * B * 2, (size_t)n_partitions * B * 8,
                          cudaMemcpyHostToDevice, ctx->stream));
-    launch_fft2_prep(dH.as<float2>(), (int64_t)P16 * B, n_signals, B, n_partitions, M, dH2.as<float2>(), ctx->d_tw2, ctx->stream);
+    launch_fft2_prep(dH.as<float2>(), (int64_t)P16 * B, n_signals, B, n_partitions, M, dH2.as<float2>(), ctx->d_tw2, ctx->d_tab16, ctx->stream);
     const int V = M - Lh;
     const int nseg = (int)((n_blocks + V - 1) / V);
     std::vector<Fft2Job> jobs(n_signals);
     for (int s = 0; s < n_signals; s++)
       jobs[s] = Fft2Job{dXT.as<float2>() + (size_t)s * C * Qs, dH2.as<float2>() + (size_t)s * C * M, dYT.as<float2>() + (size_t)s * C * Qs, Lh, nseg};
     CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(Fft2Job) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
-    launch_fft2_conv(dj.as<Fft2Job>(), n_signals, nseg, C, M, ctx->d_tw2, n_blocks, Qs, Qs, ctx->stream);
+    launch_fft2_conv(dj.as<Fft2Job>(), n_signals, nseg, C, M, ctx->d_tw2, ctx->d_tab16, n_blocks, Qs, Qs, ctx->stream);
     CU(cudaGetLastError());
     std::vector<float2> yt(xt.size());
     CU(cudaMemcpyAsync(yt.data(), dYT.p, yt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -16,9 +16,12 @@
 // variant of K5 and read by the transposing variant of K7 (fft.cu).  The prepared second-level IR spectra are
 // H2[irchan][k][M] (digit-reversed along M, scaled by 1/M), built once per impulse response by k_fft2_prep.
 //
-// One CTA = one (channel-convolver, bin, segment): M/8 threads x 8 points, radix-8 in-place FFT through shared
-// memory (fft2_core.cuh), pointwise product, mirrored inverse, store of the V valid outputs.
+// One CTA = one (channel-convolver, bin, segment): in-place FFT through shared memory (fft2_core.cuh), pointwise
+// product, mirrored inverse, store of the V valid outputs.  M <= 4096: radix-16 plan, M/16 threads x 16 points, four
+// shared-memory crossings (k_fft2_conv16); M = 8192: radix-8 plan, M/8 threads x 8 points (k_fft2_conv).  The two plans
+// order the spectrum differently, so H2 is always prepared by the plan that consumes it.
 #include <algorithm>
+#include <cmath>
 
 #include "fft2_core.cuh"
 #include "gac_kernels.h"
@@ -139,6 +142,131 @@ __global__ void __launch_bounds__(M / 8) k_fft2_prep(const float2* __restrict__ 
   for (int q = 0; q < 4; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Radix-16 plan (M = 512 .. 4096): T = M/16 threads, 16 points per thread, four shared-memory crossings per item.
+// tab = this M's twiddle table (r16::table_elems(M) entries, layout in fft2_core.cuh).
+template <int M>
+__global__ void __launch_bounds__(M / 16) k_fft2_conv16(const Fft2Job* __restrict__ jobs, const float2* __restrict__ tab, int64_t n_blocks, int64_t xs,
+                                                        int64_t ys) {
+  using P = r16::Plan<M>;
+  constexpr int T = P::T;
+  extern __shared__ __align__(16) float2 sm[];
+  const Fft2Job job = jobs[blockIdx.z];
+  const int seg = blockIdx.x;
+  if (seg >= job.nseg) return;
+  const int k = blockIdx.y;
+  const int t = threadIdx.x;
+  const int V = M - job.Lh;
+  const int64_t b_first = (int64_t)seg * V - job.Lh;
+  const float2* __restrict__ xrow = job.X + (int64_t)k * xs;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int64_t b = b_first + t + T * j;
+    v[j] = (b >= 0 && b < n_blocks) ? xrow[b] : make_float2(0.f, 0.f);
+  }
+  r16::fwd_a<M>(v, sm, tab, t);
+  __syncthreads();
+  r16::fwd_b<M>(sm, tab, t);
+  __syncthreads();
+  {
+    float2 u[16];
+    r16::load16(u, sm, t);
+    const float4* __restrict__ hp = reinterpret_cast<const float4*>(job.H2 + (int64_t)k * M + 16 * t);
+    float4 h4[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) h4[q] = hp[q];
+    r16::stage_c<P::L, false>(u);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      u[2 * q] = cmulf(u[2 * q], make_float2(h4[q].x, h4[q].y));
+      u[2 * q + 1] = cmulf(u[2 * q + 1], make_float2(h4[q].z, h4[q].w));
+    }
+    r16::stage_c<P::L, true>(u);
+    r16::store16(u, sm, t);
+  }
+  __syncthreads();
+  r16::inv_b<M>(sm, tab, t);
+  __syncthreads();
+  r16::inv_a<M>(v, sm, tab, t);
+  float2* __restrict__ yrow = job.Y + (int64_t)k * ys;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int n = t + T * j;
+    const int64_t b = b_first + n;
+    if (n >= job.Lh && b < n_blocks) yrow[b] = v[j];
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(M / 16) k_fft2_prep16(const float2* __restrict__ H, int64_t h_ch_stride, int B, int P, float2* __restrict__ H2,
+                                                        const float2* __restrict__ tab) {
+  using Pl = r16::Plan<M>;
+  constexpr int T = Pl::T;
+  extern __shared__ __align__(16) float2 sm[];
+  const int k = blockIdx.x, ch = blockIdx.y, t = threadIdx.x;
+  const float2* __restrict__ Hc = H + (int64_t)ch * h_ch_stride;
+  const int col = (k == B) ? 0 : k;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int p = t + T * j;
+    float2 h = make_float2(0.f, 0.f);
+    if (p < P) {
+      h = Hc[(int64_t)p * B + col];
+      if (k == 0) h = make_float2(h.x, 0.f);
+      else if (k == B) h = make_float2(h.y, 0.f);
+    }
+    v[j] = h;
+  }
+  r16::fwd_a<M>(v, sm, tab, t);
+  __syncthreads();
+  r16::fwd_b<M>(sm, tab, t);
+  __syncthreads();
+  float2 u[16];
+  r16::load16(u, sm, t);
+  r16::stage_c<Pl::L, false>(u);
+  const float sc = 1.0f / (float)M;
+  float4* __restrict__ out = reinterpret_cast<float4*>(H2 + ((int64_t)ch * (B + 1) + k) * M + 16 * t);
+#pragma unroll
+  for (int q = 0; q < 8; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
+}
+
+int fft2_table_offset(int M) {  // offset of M's radix-16 twiddle table inside the concatenated table buffer
+  int off = 0;
+  for (int m = 512; m < M; m *= 2) off += r16::table_elems(m);
+  return off;
+}
+int fft2_table_total() { return fft2_table_offset(8192); }
+void fft2_fill_tables(float2* host) {
+  const double pi = 3.14159265358979323846;
+  for (int M = 512; M <= 4096; M *= 2) {
+    float2* tab = host + fft2_table_offset(M);
+    const int T = M / 16, L = M / 256;
+    for (int q = 0; q < 4; q++) {
+      for (int t = 0; t < T; t++) {
+        const double a = -2.0 * pi * (double)(t << q) / (double)M;
+        tab[q * T + t] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+      for (int i = 0; i < L; i++) {
+        const double a = -2.0 * pi * (double)(i << q) / (double)(16 * L);
+        tab[4 * T + q * L + i] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+    }
+  }
+}
+
+template <int M>
+static void conv16_t(const Fft2Job* d_jobs, dim3 grid, const float2* d_tab, int64_t n_blocks, int64_t xs, int64_t ys, cudaStream_t s) {
+  constexpr size_t smem = sizeof(float2) * r16::smem_elems(M);
+  k_fft2_conv16<M><<<grid, M / 16, smem, s>>>(d_jobs, d_tab + fft2_table_offset(M), n_blocks, xs, ys);
+}
+template <int M>
+static void prep16_t(const float2* d_H, int64_t h_ch_stride, dim3 grid, int B, int P, float2* d_H2, const float2* d_tab, cudaStream_t s) {
+  constexpr size_t smem = sizeof(float2) * r16::smem_elems(M);
+  k_fft2_prep16<M><<<grid, M / 16, smem, s>>>(d_H, h_ch_stride, B, P, d_H2, d_tab + fft2_table_offset(M));
+}
+
 template <int M>
 static void conv_t(const Fft2Job* d_jobs, dim3 grid, const float2* d_tw2, int64_t n_blocks, int64_t xs, int64_t ys, cudaStream_t s) {
   constexpr size_t smem = sizeof(float2) * smem_elems(M);
@@ -160,30 +288,31 @@ static void prep_t(const float2* d_H, int64_t h_ch_stride, dim3 grid, int B, int
   k_fft2_prep<M><<<grid, M / 8, smem, s>>>(d_H, h_ch_stride, B, P, d_H2, d_tw2);
 }
 
-void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tw2, int64_t n_blocks, int64_t xs, int64_t ys,
-                      cudaStream_t s) {
+void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tw2, const float2* d_tab16, int64_t n_blocks,
+                      int64_t xs, int64_t ys, cudaStream_t s) {
   if (n_jobs <= 0 || max_seg <= 0) return;
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
     dim3 grid((unsigned)max_seg, (unsigned)C, (unsigned)nj);
     switch (M) {
-      case 512: conv_t<512>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
-      case 1024: conv_t<1024>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
-      case 2048: conv_t<2048>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
-      case 4096: conv_t<4096>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
+      case 512: conv16_t<512>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
+      case 1024: conv16_t<1024>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
+      case 2048: conv16_t<2048>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
+      case 4096: conv16_t<4096>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
       case 8192: conv_t<8192>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
     }
   }
 }
 
-void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, int P, int M, float2* d_H2, const float2* d_tw2, cudaStream_t s) {
+void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, int P, int M, float2* d_H2, const float2* d_tw2, const float2* d_tab16,
+                      cudaStream_t s) {
   if (n_ch <= 0) return;
   dim3 grid((unsigned)(B + 1), (unsigned)n_ch);
   switch (M) {
-    case 512: prep_t<512>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
-    case 1024: prep_t<1024>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
-    case 2048: prep_t<2048>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
-    case 4096: prep_t<4096>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
+    case 512: prep16_t<512>(d_H, h_ch_stride, grid, B, P, d_H2, d_tab16, s); break;
+    case 1024: prep16_t<1024>(d_H, h_ch_stride, grid, B, P, d_H2, d_tab16, s); break;
+    case 2048: prep16_t<2048>(d_H, h_ch_stride, grid, B, P, d_H2, d_tab16, s); break;
+    case 4096: prep16_t<4096>(d_H, h_ch_stride, grid, B, P, d_H2, d_tab16, s); break;
     case 8192: prep_t<8192>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s); break;
   }
 }

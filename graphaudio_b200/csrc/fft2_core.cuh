@@ -240,4 +240,197 @@ F2_HD void inv_stage(float2 (&v)[8], float2* sm, const float2* __restrict__ tw, 
 
 #undef F2_HD
 }  // namespace f2
+// =====================================================================================================================
+// Radix-16 plan (production path for M = 512 .. 4096):  M = 16 * 16 * L,  L in {2, 4, 8, 16},  T = M/16 threads, 16 points
+// per thread.  Three stages
+//     A: span M,    radix 16, stride T          (fed from global memory, twiddles w_M^(t r))
+//     B: span 16 L, radix 16, stride L          (twiddles w_16L^(i r))
+//     C: 16/L contiguous L-point transforms on the thread's 16 contiguous points 16 t .. 16 t + 15, no twiddles
+// so a forward + inverse pair crosses shared memory four times (A->B, B->C, C'->B', B'->A') instead of six, which is
+// what bounds the radix-8 plan (ncu: l1tex data pipe 87 % busy).  The register slot q of a thread after stage C IS the
+// spectrum position 16 t + q by definition: the IR spectra are produced by the same code, so no order is ever undone.
+// Twiddles come from per-M tables laid out [4][T] (+ [4][L]) holding w^(i 2^q), q = 0..3, so that a warp reads
+// consecutive entries; the other powers are composed with one or two complex products.
+namespace r16 {
+
+#define F2_HD __host__ __device__ __forceinline__
+using f2::addf;
+using f2::cmulcf;
+using f2::cmulf;
+using f2::subf;
+
+F2_HD int pad(int e) { return e + ((e >> 4) << 1) + ((e >> 7) << 3); }
+constexpr int smem_elems(int M) { return M + (M >> 4) * 2 + (M >> 7) * 8; }
+constexpr int table_elems(int M) { return 4 * (M / 16) + 4 * (M / 256); }  // [4][T] stage A, [4][L] stage B
+
+F2_HD constexpr int rev4(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r >> 3) & 1); }
+
+// radix-8 butterfly on v[O .. O+7] (same conventions as f2::bf8)
+template <bool INV, int O, int N>
+F2_HD void bf8_at(float2 (&v)[N]) {
+  float2 x[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) x[j] = v[O + j];
+  f2::bf8<INV>(x);
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[O + j] = x[j];
+}
+
+// Radix-16 butterfly.  Forward: in v[j] = x_j, out v[rev4(r)] = sum_j x_j e^{-2 pi i j r / 16}.
+// Inverse: in v[rev4(r)] = X_r, out v[j] = sum_r X_r e^{+2 pi i j r / 16}.
+template <bool INV>
+F2_HD void bf16(float2 (&v)[16]) {
+  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, c2 = 0.70710678118654752440f;
+  // w16^j = (wr[j], -wi[j]) for the forward transform
+  const float wr[8] = {1.f, c1, c2, s1, 0.f, -s1, -c2, -c1};
+  const float wi[8] = {0.f, s1, c2, c1, 1.f, c1, c2, s1};
+  if (!INV) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float2 a = v[j], b = v[j + 8];
+      v[j] = addf(a, b);
+      const float2 d = subf(a, b);
+      if (j == 0) v[8] = d;
+      else if (j == 4) v[12] = make_float2(d.y, -d.x);
+      else v[j + 8] = make_float2(d.x * wr[j] + d.y * wi[j], d.y * wr[j] - d.x * wi[j]);  // d * (wr - i wi)
+    }
+    bf8_at<false, 0>(v);
+    bf8_at<false, 8>(v);
+  } else {
+    bf8_at<true, 0>(v);
+    bf8_at<true, 8>(v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float2 a = v[j], b = v[j + 8];
+      float2 bp;
+      if (j == 0) bp = b;
+      else if (j == 4) bp = make_float2(-b.y, b.x);
+      else bp = make_float2(b.x * wr[j] - b.y * wi[j], b.y * wr[j] + b.x * wi[j]);          // b * (wr + i wi)
+      v[j] = addf(a, bp);
+      v[j + 8] = subf(a, bp);
+    }
+  }
+}
+
+// w[r] = w^r, r = 1..15, from the four table entries w^1, w^2, w^4, w^8
+F2_HD void compose(float2 w1, float2 w2, float2 w4, float2 w8, float2 (&w)[16]) {
+  w[1] = w1; w[2] = w2; w[4] = w4; w[8] = w8;
+  w[3] = cmulf(w1, w2);
+  w[5] = cmulf(w1, w4);
+  w[6] = cmulf(w2, w4);
+  w[7] = cmulf(w[3], w4);
+  w[9] = cmulf(w1, w8);
+  w[10] = cmulf(w2, w8);
+  w[11] = cmulf(w[3], w8);
+  w[12] = cmulf(w4, w8);
+  w[13] = cmulf(w[5], w8);
+  w[14] = cmulf(w[6], w8);
+  w[15] = cmulf(w[7], w8);
+}
+
+template <int M>
+struct Plan {
+  static constexpr int T = M / 16;
+  static constexpr int L = M / 256;
+  static_assert(M == 512 || M == 1024 || M == 2048 || M == 4096, "radix-16 plan: M = 256 L, L in {2,4,8,16}");
+};
+
+// tab: [4][T] then [4][L]
+template <int M>
+F2_HD void twiddles_a(const float2* __restrict__ tab, int t, float2 (&w)[16]) {
+  constexpr int T = Plan<M>::T;
+  compose(tab[t], tab[T + t], tab[2 * T + t], tab[3 * T + t], w);
+}
+template <int M>
+F2_HD void twiddles_b(const float2* __restrict__ tab, int i, float2 (&w)[16]) {
+  constexpr int T = Plan<M>::T, L = Plan<M>::L;
+  const float2* tb = tab + 4 * T;
+  compose(tb[i], tb[L + i], tb[2 * L + i], tb[3 * L + i], w);
+}
+
+// ---- forward
+template <int M>
+F2_HD void fwd_a(float2 (&v)[16], float2* sm, const float2* __restrict__ tab, int t) {  // v[j] = x[t + T j]
+  constexpr int T = Plan<M>::T;
+  bf16<false>(v);
+  float2 w[16];
+  twiddles_a<M>(tab, t, w);
+  sm[pad(t)] = v[0];
+#pragma unroll
+  for (int r = 1; r < 16; r++) sm[pad(t + T * r)] = cmulf(v[rev4(r)], w[r]);
+}
+template <int M>
+F2_HD void fwd_b(float2* sm, const float2* __restrict__ tab, int t) {
+  constexpr int L = Plan<M>::L;
+  const int blk = t / L, i = t % L, base = blk * 16 * L + i;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) v[j] = sm[pad(base + L * j)];
+  bf16<false>(v);
+  float2 w[16];
+  twiddles_b<M>(tab, i, w);
+  sm[pad(base)] = v[0];
+#pragma unroll
+  for (int r = 1; r < 16; r++) sm[pad(base + L * r)] = cmulf(v[rev4(r)], w[r]);
+}
+// stage C on the 16 contiguous points of the thread (in registers)
+template <int L, bool INV>
+F2_HD void stage_c(float2 (&u)[16]) {
+  if (L == 16) {
+    bf16<INV>(u);
+  } else if (L == 8) {
+    bf8_at<INV, 0>(u);
+    bf8_at<INV, 8>(u);
+  } else {
+    float2 a[8], b[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { a[q] = u[q]; b[q] = u[8 + q]; }
+    f2::tail<L, INV>(a);
+    f2::tail<L, INV>(b);
+#pragma unroll
+    for (int q = 0; q < 8; q++) { u[q] = a[q]; u[8 + q] = b[q]; }
+  }
+}
+F2_HD void load16(float2 (&u)[16], const float2* sm, int t) {
+  const float4* p = reinterpret_cast<const float4*>(sm + pad(16 * t));
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 x = p[q];
+    u[2 * q] = make_float2(x.x, x.y);
+    u[2 * q + 1] = make_float2(x.z, x.w);
+  }
+}
+F2_HD void store16(const float2 (&u)[16], float2* sm, int t) {
+  float4* p = reinterpret_cast<float4*>(sm + pad(16 * t));
+#pragma unroll
+  for (int q = 0; q < 8; q++) p[q] = make_float4(u[2 * q].x, u[2 * q].y, u[2 * q + 1].x, u[2 * q + 1].y);
+}
+// ---- inverse
+template <int M>
+F2_HD void inv_b(float2* sm, const float2* __restrict__ tab, int t) {
+  constexpr int L = Plan<M>::L;
+  const int blk = t / L, i = t % L, base = blk * 16 * L + i;
+  float2 w[16];
+  twiddles_b<M>(tab, i, w);
+  float2 v[16];
+  v[0] = sm[pad(base)];
+#pragma unroll
+  for (int r = 1; r < 16; r++) v[rev4(r)] = cmulcf(sm[pad(base + L * r)], w[r]);
+  bf16<true>(v);
+#pragma unroll
+  for (int j = 0; j < 16; j++) sm[pad(base + L * j)] = v[j];
+}
+template <int M>
+F2_HD void inv_a(float2 (&v)[16], const float2* sm, const float2* __restrict__ tab, int t) {  // out v[j] = M x[t + T j]
+  constexpr int T = Plan<M>::T;
+  float2 w[16];
+  twiddles_a<M>(tab, t, w);
+  v[0] = sm[pad(t)];
+#pragma unroll
+  for (int r = 1; r < 16; r++) v[rev4(r)] = cmulcf(sm[pad(t + T * r)], w[r]);
+  bf16<true>(v);
+}
+
+#undef F2_HD
+}  // namespace r16
 }  // namespace gac

@@ -89,10 +89,14 @@ struct Fft2Job {
 constexpr int kFft2TwLen = 8192;  // twiddle table exp(-2 pi i e / 8192)
 // second-level transform length for P partitions (512..8192), 0 if the IR is too long; *Lh = history length
 int fft2_pick_m(int P, int* Lh);
-void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tw2, int64_t n_blocks, int64_t xs, int64_t ys,
-                      cudaStream_t s);
+// d_tw2: the 8192-entry table (radix-8 plan, M = 8192); d_tab16: the concatenated radix-16 tables (M = 512 .. 4096)
+int fft2_table_total();              // float2 entries of the concatenated radix-16 tables
+void fft2_fill_tables(float2* host);  // fills them (double precision, rounded once)
+void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tw2, const float2* d_tab16, int64_t n_blocks,
+                      int64_t xs, int64_t ys, cudaStream_t s);
 // H: packed first-level IR spectra [n_ch][...h_ch_stride...] rows of B -> H2 [n_ch][B+1][M]
-void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, int P, int M, float2* d_H2, const float2* d_tw2, cudaStream_t s);
+void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, int P, int M, float2* d_H2, const float2* d_tw2, const float2* d_tab16,
+                      cudaStream_t s);
 
 // ------------------------------------------------------------------ node kernels (nodes.cu)
 struct DevEvent {  // bit-compatible with gac_event / AudioParam.cs:360-367
@@ -155,11 +159,15 @@ struct BiquadJob {
 //   d_s1t float4 [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  (x, a1, a2, -)
 //   d_wt  float  [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  Direct-Form-II state sequence w
 // n_jobs <= 65535 per call.
+// d_states: float2 [ceil(n_jobs/16)][n_seg][2][32] and d_first_bad: int [ceil(n_jobs/16)], n_seg = biquad_lane_segments(...)
+// (the recursion runs as concurrent, verified time segments: biquad_lanes.cu header)
+int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs);
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, float4* d_s1t, float* d_wt, cudaStream_t s);
+                   int32_t* d_ent, float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad, cudaStream_t s);
 
 // K3d alone (biquad_lanes.cu): the w recursion over the slab-transposed streams, TMA-fed
-void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, float* d_wt, cudaStream_t s);
+void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad,
+                         cudaStream_t s);
 
 struct MixJob {       // dst[c][n] = (((0 + src0) + src1) + ...) over active ranges, AudioNodeInput.cs:118-137
   float* dst[2];

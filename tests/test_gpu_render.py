@@ -60,9 +60,11 @@ def test_c2_gain_automation_and_bus_mix():
     g.Dispose()
 
 
-@pytest.mark.parametrize("f0,f1,q", [(2000.0, 12000.0, 0.707), (200.0, 2000.0, 0.707), (500.0, 8000.0, 8.0)])
+@pytest.mark.parametrize("f0,f1,q", [(2000.0, 12000.0, 0.707), (200.0, 2000.0, 0.707), (500.0, 8000.0, 8.0), (40.0, 60.0, 20.0)])
 def test_c3_biquad_sweep(f0, f1, q):
-    """C3 shape: biquad lowpass with an a-rate exponential cutoff sweep -> gain -> convolver -> bus."""
+    """C3 shape: biquad lowpass with an a-rate exponential cutoff sweep -> gain -> convolver -> bus.
+    The recursion runs as concurrent time segments that are verified bit for bit (biquad_lanes.cu); the 40 Hz / Q = 20 case
+    never forgets its state within the warm-up, so it exercises the sequential repair path."""
     G, O = _apis()
     fs = 48000
     voices = _voices(4, fs // 2, 6000)

@@ -88,61 +88,88 @@ __global__ void __launch_bounds__(kSelQ) k_biquad_select(const BiquadJob* __rest
 }
 
 // K3b: which coefficient set the reference's fields (_b0.._a2) hold when channel c of quantum b starts.
-// ent[c][b] = frame index whose (f, Q) applies, or -1 (only before the very first recompute).  One thread per job.
-__global__ void __launch_bounds__(64) k_biquad_entry(int n_jobs, int64_t n_quanta, const int32_t* __restrict__ last_base,
+// ent[c][b] = frame index whose (f, Q) applies, or -1 (only before the very first recompute).  A "last recompute so far"
+// scan over the quanta: one warp per job, every lane owns a contiguous chunk of quanta (chunk summary, carry across the
+// lanes by shuffles, replay).
+__global__ void __launch_bounds__(32) k_biquad_entry(int n_jobs, int64_t n_quanta, const int32_t* __restrict__ last_base,
                                                      int32_t* __restrict__ ent_base) {
-  int jid = blockIdx.x * 64 + threadIdx.x;
+  const int jid = blockIdx.x, lane = threadIdx.x;
   if (jid >= n_jobs) return;
   const int32_t* last0 = last_base + (size_t)jid * 2 * n_quanta;
   const int32_t* last1 = last0 + n_quanta;
   int32_t* ent0 = ent_base + (size_t)jid * 2 * n_quanta;
   int32_t* ent1 = ent0 + n_quanta;
+  const int64_t chunk = (n_quanta + 31) / 32;
+  const int64_t b_lo = lane * chunk, b_hi = (b_lo + chunk < n_quanta) ? b_lo + chunk : n_quanta;
+  // summary of the chunk: the last recompute inside it (channel 1's wins over channel 0's within a quantum), or -2 = none
+  int32_t tail = -2;
+  for (int64_t b = b_lo; b < b_hi; b++) {
+    const int32_t l0 = last0[b], l1 = last1[b];
+    if (l0 >= 0) tail = l0;
+    if (l1 >= 0) tail = l1;
+  }
+  // carry into this lane = summary of the nearest lower lane that recomputed at all, else -1
   int32_t cur = -1;
-  for (int64_t b = 0; b < n_quanta; b++) {
+  for (int src = 0; src < 31; src++) {
+    const int32_t t = __shfl_sync(0xffffffffu, tail, src);
+    if (src < lane && t != -2) cur = t;
+  }
+  for (int64_t b = b_lo; b < b_hi; b++) {
     ent0[b] = cur;                      // channel 0 starts from the fields as the previous block left them
-    int32_t l0 = last0[b];
-    int32_t c0 = l0 >= 0 ? l0 : cur;
+    const int32_t l0 = last0[b];
+    const int32_t c0 = l0 >= 0 ? l0 : cur;
     ent1[b] = c0;                       // channel 1 starts from channel 0's end state (:110-115)
-    int32_t l1 = last1[b];
+    const int32_t l1 = last1[b];
     cur = l1 >= 0 ? l1 : c0;
   }
 }
 
 // K3c: coefficients in force at every (channel, frame): RBJ of the frame the walk selected, with the k-rate gain of that
-// frame's block.  CTA = one slab of one 32-row group: thread (r = tid / 32, i = tid % 32) reads row r along time
-// (coalesced), the (x, a1, a2) tile is transposed through shared memory and written as one contiguous 16 KB block.
-__global__ void __launch_bounds__(1024) k_biquad_resolve(const BiquadJob* __restrict__ jobs, int n_jobs, int sample_rate, int64_t n_quanta,
-                                                         int64_t n_frames, const int32_t* __restrict__ ent_base, float4* __restrict__ s1t) {
+// frame's block.  CTA = one slab of one 32-row group, 16 warps: warp = voice, lane = frame, and the thread serves BOTH
+// channels: they almost always selected the same frame, so one RBJ evaluation (glibc-exact sinf/cosf, five divisions) feeds
+// both rows.  Reads run along time (coalesced); the (x, a1, a2) tile is transposed through shared memory and written as
+// one contiguous 16 KB block.
+__global__ void __launch_bounds__(512) k_biquad_resolve(const BiquadJob* __restrict__ jobs, int n_jobs, int sample_rate, int64_t n_quanta,
+                                                        int64_t n_frames, const int32_t* __restrict__ ent_base, float4* __restrict__ s1t) {
   __shared__ float4 tile[32][33];
-  const int r = threadIdx.x >> 5, i = threadIdx.x & 31;
+  const int jv = threadIdx.x >> 5, i = threadIdx.x & 31;
   const int64_t slab = blockIdx.x;
   const int g = blockIdx.y;
-  const int jid = g * 16 + (r >> 1);
-  const int c = r & 1;
+  const int jid = g * 16 + jv;
   const int64_t n = slab * 32 + i;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
   if (jid < n_jobs) {
     const BiquadJob& job = jobs[jid];
     if (n >= job.lo && n < job.hi) {
-      const int64_t t = (int64_t)c * n_frames + n;
-      int32_t k = job.idx[t];
-      if (k < 0) k = ent_base[((size_t)jid * 2 + c) * n_quanta + (n >> 7)];
-      Coef co;
-      if (k >= 0) {
-        const float nyq = (float)sample_rate / 2.f;
-        co = rbj(job.type, clamped_freq(job, k, nyq), clamped_q(job, k), job.gain ? job.gain[k >> 7] : job.gain_const, sample_rate);
-      } else {
-        co.b0 = co.b1 = co.b2 = co.a1 = co.a2 = 0.f;  // unreachable for active frames: the first one always recomputes (dirty)
+      int32_t k0 = job.idx[n], k1 = job.idx[n_frames + n];
+      if (k0 < 0) k0 = ent_base[((size_t)jid * 2 + 0) * n_quanta + (n >> 7)];
+      if (k1 < 0) k1 = ent_base[((size_t)jid * 2 + 1) * n_quanta + (n >> 7)];
+      const float nyq = (float)sample_rate / 2.f;
+      Coef c0, c1;
+      c0.b0 = c0.b1 = c0.b2 = c0.a1 = c0.a2 = 0.f;  // k < 0 is unreachable for active frames: the first one always recomputes (dirty)
+      if (k0 >= 0) c0 = rbj(job.type, clamped_freq(job, k0, nyq), clamped_q(job, k0), job.gain ? job.gain[k0 >> 7] : job.gain_const, sample_rate);
+      c1 = c0;
+      if (k1 != k0) {
+        c1.b0 = c1.b1 = c1.b2 = c1.a1 = c1.a2 = 0.f;
+        if (k1 >= 0) c1 = rbj(job.type, clamped_freq(job, k1, nyq), clamped_q(job, k1), job.gain ? job.gain[k1 >> 7] : job.gain_const, sample_rate);
       }
-      v = make_float4(job.sig[c][n], co.a1, co.a2, 0.f);
-      job.s2[t] = make_float4(co.b0, co.b1, co.b2, 0.f);
+      v0 = make_float4(job.sig[0][n], c0.a1, c0.a2, 0.f);
+      v1 = make_float4(job.sig[1][n], c1.a1, c1.a2, 0.f);
+      job.s2[n] = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
+      job.s2[n_frames + n] = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
     }
   }
-  tile[i][r] = v;
+  tile[i][2 * jv] = v0;
+  tile[i][2 * jv + 1] = v1;
   __syncthreads();
-  // tile[frame][row] -> S1T[g][slab][frame][row]: thread tid writes element (frame = tid / 32, row = tid % 32)
+  // tile[frame][row] -> S1T[g][slab][frame][row]: element e = frame * 32 + row
   const size_t n_slabs = (size_t)(n_frames / 32);
-  s1t[((size_t)g * n_slabs + slab) * 1024 + threadIdx.x] = tile[threadIdx.x >> 5][threadIdx.x & 31];
+  float4* dst = s1t + ((size_t)g * n_slabs + slab) * 1024;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int e = threadIdx.x + 512 * h;
+    dst[e] = tile[e >> 5][e & 31];
+  }
 }
 
 // K3e: y = b0*w + b1*w1 + b2*w2 (:138) from the stored w sequence; frames outside the non-silent range are cleared (:103-108).
@@ -185,8 +212,8 @@ void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_
   const int groups = (n_jobs + 15) / 16;
   const unsigned n_slabs = (unsigned)(n_frames / 32);
   k_biquad_select<<<dim3((unsigned)((n_quanta + kSelQ - 1) / kSelQ), (unsigned)n_jobs), kSelQ, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last);
-  k_biquad_entry<<<(unsigned)((n_jobs + 63) / 64), 64, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
-  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 1024, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t);
+  k_biquad_entry<<<(unsigned)n_jobs, 32, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
+  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t);
   launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_wt, d_states, d_first_bad, s);
   k_biquad_output<<<dim3(n_slabs, (unsigned)groups), 1024, 0, s>>>(d_jobs, n_jobs, n_frames, d_wt);
 }

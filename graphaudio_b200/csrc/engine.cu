@@ -468,7 +468,7 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   ir->M2 = wants_fft2(ctx) ? fft2_pick_m(ir->P, &ir->Lh) : 0;
   if (ir->M2 > 0 && !use_fft2(ctx, ir->P, ir->M2)) ir->M2 = 0;
   if (ir->M2 > 0) {
-    CU(cudaMallocAsync(&ir->d_H2, sizeof(float2) * (size_t)nch * (B + 1) * ir->M2, ctx->stream));
+    CU(cudaMallocAsync(&ir->d_H2, sizeof(float2) * (size_t)nch * (B + 1) * fft2_h2_row_elems(ir->M2), ctx->stream));
     launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, nch, B, ir->P, ir->M2, ir->d_H2, ctx->d_tw2, ctx->d_tab16, ctx->stream);
     CU(cudaGetLastError());
   }
@@ -899,7 +899,7 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
         env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
         env.macs += (double)QB * P * C;  // complex MACs the direct sum would need (not issued: see mac_flops)
         env.mac_flops += (double)nseg * C * (2.0 * 5.0 * M * log2m + 6.0 * M);
-        env.mac_bytes += 8.0 * C * ((double)nseg * M + (double)M + (double)QB);  // XT windows, H2 row, YT
+        env.mac_bytes += 8.0 * C * ((double)QB + (double)fft2_h2_row_elems(M) + (double)QB);  // XT once (window overlaps hit L2), H2 row, YT
       }
       for (int k = 0; k < it.n_inv; k++) {
         FftInvJob v;
@@ -1099,7 +1099,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         }
         const gac_ir* ir = op.ir;
         auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
-        auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * ir->M2) : (const float2*)nullptr; };
+        auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(ir->M2)) : (const float2*)nullptr; };
         ConvItem it;
         it.P = ir->P;
         it.M2 = ir->d_H2 ? ir->M2 : 0;

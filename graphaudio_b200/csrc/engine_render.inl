@@ -666,7 +666,7 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
     DevBuf dXT, dYT, dH, dH2, dj;
     int rc;
     if ((rc = dev_alloc(dXT, xt.size() * 8)) || (rc = dev_alloc(dYT, xt.size() * 8)) || (rc = dev_alloc(dH, (size_t)n_signals * P16 * B * 8)) ||
-        (rc = dev_alloc(dH2, (size_t)n_signals * C * M * 8)) || (rc = dev_alloc(dj, sizeof(Fft2Job) * n_signals)))
+        (rc = dev_alloc(dH2, (size_t)n_signals * C * fft2_h2_row_elems(M) * 8)) || (rc = dev_alloc(dj, sizeof(Fft2Job) * n_signals)))
       return rc;
     CU(cudaMemcpyAsync(dXT.p, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(dH.p, 0, (size_t)n_signals * P16 * B * 8, ctx->stream));
@@ -678,7 +678,7 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
     const int nseg = (int)((n_blocks + V - 1) / V);
     std::vector<Fft2Job> jobs(n_signals);
     for (int s = 0; s < n_signals; s++)
-      jobs[s] = Fft2Job{dXT.as<float2>() + (size_t)s * C * Qs, dH2.as<float2>() + (size_t)s * C * M, dYT.as<float2>() + (size_t)s * C * Qs, Lh, nseg};
+      jobs[s] = Fft2Job{dXT.as<float2>() + (size_t)s * C * Qs, dH2.as<float2>() + (size_t)s * C * fft2_h2_row_elems(M), dYT.as<float2>() + (size_t)s * C * Qs, Lh, nseg};
     CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(Fft2Job) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
     launch_fft2_conv(dj.as<Fft2Job>(), n_signals, nseg, C, M, ctx->d_tw2, ctx->d_tab16, n_blocks, Qs, Qs, ctx->stream);
     CU(cudaGetLastError());
@@ -784,7 +784,7 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
       it.lo = 0;
       it.hi = Npad;
       it.n_mac = 1;
-      it.mac[0] = {0, irh.d_H + (size_t)s * irh.P16 * B, irh.d_H2 ? irh.d_H2 + (size_t)s * (B + 1) * irh.M2 : nullptr};
+      it.mac[0] = {0, irh.d_H + (size_t)s * irh.P16 * B, irh.d_H2 ? irh.d_H2 + (size_t)s * (B + 1) * fft2_h2_row_elems(irh.M2) : nullptr};
       it.P = irh.P;
       it.M2 = irh.d_H2 ? irh.M2 : 0;
       it.Lh = irh.Lh;

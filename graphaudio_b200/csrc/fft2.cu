@@ -145,25 +145,83 @@ __global__ void __launch_bounds__(M / 8) k_fft2_prep(const float2* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------------------
 // Radix-16 plan (M = 512 .. 4096): T = M/16 threads, 16 points per thread, four shared-memory crossings per item.
 // tab = this M's twiddle table (r16::table_elems(M) entries, layout in fft2_core.cuh).
+// TMA plumbing (cp.async.bulk + mbarrier; SASS: UBLKCP)
+__device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f2_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void f2_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f2_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void f2_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void f2_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// Shared memory of one CTA: [ FFT buffer (padded) | X window / Y staging (M float2) | H2 row (padded like the FFT buffer) | 2 mbarriers ]
+// H2 rows are stored in global memory in the PADDED order (r16::pad), r16::smem_elems(M) float2 per row, so that one
+// contiguous bulk copy lands them in a layout whose per-thread 128-byte reads are bank-conflict free.
+template <int M>
+constexpr size_t conv16_smem() { return sizeof(float2) * (size_t)(2 * r16::smem_elems(M) + M) + 16; }
+
 template <int M>
 __global__ void __launch_bounds__(M / 16) k_fft2_conv16(const Fft2Job* __restrict__ jobs, const float2* __restrict__ tab, int64_t n_blocks, int64_t xs,
                                                         int64_t ys) {
   using P = r16::Plan<M>;
   constexpr int T = P::T;
-  extern __shared__ __align__(16) float2 sm[];
+  extern __shared__ __align__(128) float2 sm[];
+  constexpr int SE = P::SE;
+  float2* stage = sm + SE;                   // X window in, Y segment out (unpadded: lanes touch consecutive elements)
+  float2* hrow = stage + M;                  // this bin's H2 row (padded order)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hrow + SE);
   const Fft2Job job = jobs[blockIdx.z];
   const int seg = blockIdx.x;
   if (seg >= job.nseg) return;
   const int k = blockIdx.y;
   const int t = threadIdx.x;
   const int V = M - job.Lh;
-  const int64_t b_first = (int64_t)seg * V - job.Lh;
+  const int64_t b_first = (int64_t)seg * V - job.Lh;  // block index of window element 0 (multiple of 16)
   const float2* __restrict__ xrow = job.X + (int64_t)k * xs;
+  // window elements [n_lo, n_hi) exist in the spectrogram; the rest of the window is zero (blocks < 0, blocks >= n_blocks)
+  const int n_lo = b_first < 0 ? (int)(-b_first) : 0;
+  const int64_t avail = n_blocks - b_first;
+  const int n_hi = avail < M ? (int)avail : M;
+  const uint32_t bar_x = f2_smem_u32(bars), bar_h = bar_x + 8;
+  if (t == 0) {
+    f2_mbar_init(bar_x, 1);
+    f2_mbar_init(bar_h, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // one bulk copy each: the window (rounded up to an even element count: the row stride keeps that inside the row)
+    const uint32_t xbytes = (uint32_t)(((n_hi - n_lo + 1) & ~1) * (int)sizeof(float2));
+    f2_mbar_expect_tx(bar_x, xbytes);
+    f2_bulk_g2s(f2_smem_u32(stage + n_lo), xrow + b_first + n_lo, xbytes, bar_x);
+    f2_mbar_expect_tx(bar_h, (uint32_t)(SE * sizeof(float2)));
+    f2_bulk_g2s(f2_smem_u32(hrow), job.H2 + (int64_t)k * SE, (uint32_t)(SE * sizeof(float2)), bar_h);
+  }
+  __syncthreads();  // barrier initialisation visible to every waiter
+  f2_mbar_wait(bar_x, 0);
   float2 v[16];
 #pragma unroll
   for (int j = 0; j < 16; j++) {
-    const int64_t b = b_first + t + T * j;
-    v[j] = (b >= 0 && b < n_blocks) ? xrow[b] : make_float2(0.f, 0.f);
+    const int n = t + T * j;
+    const float2 x = stage[n];
+    v[j] = (n >= n_lo && n < n_hi) ? x : make_float2(0.f, 0.f);
   }
   r16::fwd_a<M>(v, sm, tab, t);
   __syncthreads();
@@ -172,16 +230,12 @@ __global__ void __launch_bounds__(M / 16) k_fft2_conv16(const Fft2Job* __restric
   {
     float2 u[16];
     r16::load16(u, sm, t);
-    const float4* __restrict__ hp = reinterpret_cast<const float4*>(job.H2 + (int64_t)k * M + 16 * t);
-    float4 h4[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) h4[q] = hp[q];
     r16::stage_c<P::L, false>(u);
+    f2_mbar_wait(bar_h, 0);
+    float2 h[16];
+    r16::load16(h, hrow, t);
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      u[2 * q] = cmulf(u[2 * q], make_float2(h4[q].x, h4[q].y));
-      u[2 * q + 1] = cmulf(u[2 * q + 1], make_float2(h4[q].z, h4[q].w));
-    }
+    for (int q = 0; q < 16; q++) u[q] = cmulf(u[q], h[q]);
     r16::stage_c<P::L, true>(u);
     r16::store16(u, sm, t);
   }
@@ -189,12 +243,21 @@ __global__ void __launch_bounds__(M / 16) k_fft2_conv16(const Fft2Job* __restric
   r16::inv_b<M>(sm, tab, t);
   __syncthreads();
   r16::inv_a<M>(v, sm, tab, t);
-  float2* __restrict__ yrow = job.Y + (int64_t)k * ys;
+  // the V valid outputs leave through the staging buffer with one bulk store (everyone has read the X window long ago)
 #pragma unroll
-  for (int j = 0; j < 16; j++) {
-    const int n = t + T * j;
-    const int64_t b = b_first + n;
-    if (n >= job.Lh && b < n_blocks) yrow[b] = v[j];
+  for (int j = 0; j < 16; j++) stage[t + T * j] = v[j];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (t == 0) {
+    const int64_t b0 = b_first + job.Lh;            // first output block of the segment
+    int64_t len = n_blocks - b0;
+    if (len > V) len = V;
+    if (len > 0) {
+      const uint32_t ybytes = (uint32_t)(((len + 1) & ~(int64_t)1) * (int64_t)sizeof(float2));
+      f2_bulk_s2g(job.Y + (int64_t)k * ys + b0, f2_smem_u32(stage + job.Lh), ybytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
   }
 }
 
@@ -227,10 +290,14 @@ __global__ void __launch_bounds__(M / 16) k_fft2_prep16(const float2* __restrict
   r16::load16(u, sm, t);
   r16::stage_c<Pl::L, false>(u);
   const float sc = 1.0f / (float)M;
-  float4* __restrict__ out = reinterpret_cast<float4*>(H2 + ((int64_t)ch * (B + 1) + k) * M + 16 * t);
+  constexpr int SE = Pl::SE;
+  float2* __restrict__ row = H2 + ((int64_t)ch * (B + 1) + k) * SE;
+  float4* __restrict__ out = reinterpret_cast<float4*>(row + r16::pad(16 * t));
 #pragma unroll
   for (int q = 0; q < 8; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
 }
+
+int fft2_h2_row_elems(int M) { return M <= 4096 ? r16::smem_elems(M) : M; }
 
 int fft2_table_offset(int M) {  // offset of M's radix-16 twiddle table inside the concatenated table buffer
   int off = 0;
@@ -258,7 +325,12 @@ void fft2_fill_tables(float2* host) {
 
 template <int M>
 static void conv16_t(const Fft2Job* d_jobs, dim3 grid, const float2* d_tab, int64_t n_blocks, int64_t xs, int64_t ys, cudaStream_t s) {
-  constexpr size_t smem = sizeof(float2) * r16::smem_elems(M);
+  constexpr size_t smem = conv16_smem<M>();
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_fft2_conv16<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
   k_fft2_conv16<M><<<grid, M / 16, smem, s>>>(d_jobs, d_tab + fft2_table_offset(M), n_blocks, xs, ys);
 }
 template <int M>

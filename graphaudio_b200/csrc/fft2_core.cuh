@@ -332,6 +332,7 @@ template <int M>
 struct Plan {
   static constexpr int T = M / 16;
   static constexpr int L = M / 256;
+  static constexpr int SE = M + (M >> 4) * 2 + (M >> 7) * 8;  // == smem_elems(M), usable in device code
   static_assert(M == 512 || M == 1024 || M == 2048 || M == 4096, "radix-16 plan: M = 256 L, L in {2,4,8,16}");
 };
 

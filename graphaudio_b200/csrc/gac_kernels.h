@@ -81,7 +81,7 @@ void launch_mac_stream(const MacJob* d_jobs, int n_jobs, int64_t n_blocks, int s
 // One job = one channel-convolver over transposed spectrograms: row k (k = 0..B) of XT/YT at X + k*xs / Y + k*ys.
 struct Fft2Job {
   const float2* X;   // XT channel base
-  const float2* H2;  // prepared second-level IR spectra of the IR channel: [B+1][M]
+  const float2* H2;  // prepared second-level IR spectra of the IR channel: [B+1][fft2_h2_row_elems(M)]
   float2* Y;         // YT channel base
   int Lh;            // history blocks per segment (>= P-1, multiple of 16); V = M - Lh valid outputs per segment
   int nseg;          // ceil(n_blocks / V)
@@ -89,6 +89,8 @@ struct Fft2Job {
 constexpr int kFft2TwLen = 8192;  // twiddle table exp(-2 pi i e / 8192)
 // second-level transform length for P partitions (512..8192), 0 if the IR is too long; *Lh = history length
 int fft2_pick_m(int P, int* Lh);
+// float2 elements of one H2 row (one bin of one IR channel): M for the radix-8 plan, the padded length for the radix-16 plan
+int fft2_h2_row_elems(int M);
 // d_tw2: the 8192-entry table (radix-8 plan, M = 8192); d_tab16: the concatenated radix-16 tables (M = 512 .. 4096)
 int fft2_table_total();              // float2 entries of the concatenated radix-16 tables
 void fft2_fill_tables(float2* host);  // fills them (double precision, rounded once)

@@ -152,6 +152,50 @@ __device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2
   for (int j = 0; j < R; j++) twk[j] = tw[lane + 32 * j];
   const float sc = job.scale ? *job.scale : 1.0f;
 
+  // TR: the CTA's TBK*H input frames are staged in shared memory first — float4 loads, four groups in flight per thread —
+  // with the gain / silent-gate / down-mix / scale arithmetic applied on the way (same operations, same order as below)
+  float* xs = reinterpret_cast<float*>(tileT + (((H + 1) * LD + 1) & ~1));  // [TBK][H], 16-byte aligned
+  if constexpr (TR) {
+    const int64_t f0 = (int64_t)blockIdx.x * TBK * H;
+    constexpr int NG = TBK * H / 4, U = 4, NT = kFftWarps * 32;
+    for (int i0 = threadIdx.x; i0 < NG; i0 += NT * U) {
+      float4 x[U], gn[U], y[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = i0 + NT * u;
+        const int64_t g = f0 + 4 * (int64_t)i;
+        x[u] = y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gn[u] = make_float4(job.gain_const, job.gain_const, job.gain_const, job.gain_const);
+        if (i < NG && g + 3 < job.n_valid) {  // (n_valid is a multiple of the partition size on this path)
+          x[u] = *reinterpret_cast<const float4*>(job.in + g);
+          if (job.gain) gn[u] = *reinterpret_cast<const float4*>(job.gain + g);
+          if (job.in2) y[u] = *reinterpret_cast<const float4*>(job.in2 + g);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = i0 + NT * u;
+        if (i >= NG) continue;
+        const int64_t g = f0 + 4 * (int64_t)i;
+        const float xe[4] = {x[u].x, x[u].y, x[u].z, x[u].w}, ge[4] = {gn[u].x, gn[u].y, gn[u].z, gn[u].w},
+                    ye[4] = {y[u].x, y[u].y, y[u].z, y[u].w};
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const bool open = g + e >= job.gate_lo && g + e < job.gate_hi;
+          float a = open ? __fmul_rn(xe[e], ge[e]) : 0.f;
+          if (job.in2) {
+            const float b2 = open ? __fmul_rn(ye[e], ge[e]) : 0.f;
+            a = __fmul_rn(__fadd_rn(a, b2), job.mix_scale);
+          }
+          r[e] = a * sc;
+        }
+        *reinterpret_cast<float4*>(xs + 4 * i) = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    __syncthreads();
+  }
+
   int64_t b_first = ((int64_t)blockIdx.x * kFftWarps + warp) * BPW;
   for (int bi = 0; bi < BPW; bi++) {
     int64_t b = b_first + bi;
@@ -165,7 +209,9 @@ __device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2
       if (j < R / 2 || R == 1) {
         int n = j * 32 + lane;
         float2 x = make_float2(0.f, 0.f);
-        if (R > 1 || n < H / 2) {
+        if constexpr (TR) {
+          if (R > 1 || n < H / 2) x = *reinterpret_cast<const float2*>(xs + (warp * BPW + bi) * H + 2 * n);
+        } else if (R > 1 || n < H / 2) {
           int64_t g = base + 2 * n;
           if (g + 1 < job.n_valid) {
             x = *reinterpret_cast<const float2*>(in + 2 * n);
@@ -349,18 +395,43 @@ __global__ void __launch_bounds__(kFftWarps * 32) k_irfft_ola_t(const FftInvJob*
   const FftInvJob job = jobs[blockIdx.y];
   const int64_t b0 = (int64_t)blockIdx.x * TBK;
   if (b0 >= job.n_blocks) return;
-  for (int idx = threadIdx.x; idx < (H + 1) * NC; idx += kFftWarps * 32) {
-    const int row = idx / NC, c = idx % NC;
-    const int64_t b = b0 - 1 + c;
-    float2 y = make_float2(0.f, 0.f);
-    if (b >= 0 && b < job.n_blocks) {
-      y = job.in[(int64_t)row * ts + b];
-      if (job.in2) {
-        const float2 y2 = job.in2[(int64_t)row * ts + b];
-        y = make_float2(y.x + y2.x, y.y + y2.y);
+  // tile load: a thread owns the column cc of the rows rr, rr + RS, ...; eight independent loads are in flight per thread
+  // before anything is stored (the loop is latency-bound otherwise)
+  {
+    constexpr int RS = (kFftWarps * 32) / TBK;     // rows covered per sweep (TBK <= 32 columns per row)
+    const int cc = threadIdx.x % TBK, rr = threadIdx.x / TBK;
+    const int64_t bcol = b0 + cc;
+    const bool col_ok = bcol < job.n_blocks;
+    constexpr int U = 8;
+    for (int r0 = rr; r0 <= H; r0 += RS * U) {
+      float2 y[U], y2[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int row = r0 + RS * u;
+        y[u] = y2[u] = make_float2(0.f, 0.f);
+        if (row <= H && col_ok) {
+          y[u] = job.in[(int64_t)row * ts + bcol];
+          if (job.in2) y2[u] = job.in2[(int64_t)row * ts + bcol];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int row = r0 + RS * u;
+        if (row <= H) tileT[row * LD + cc + 1] = make_float2(y[u].x + y2[u].x, y[u].y + y2[u].y);
       }
     }
-    tileT[row * LD + c] = y;
+    // column 0: the predecessor block b0 - 1 (zero before the first block)
+    for (int row = threadIdx.x; row <= H; row += kFftWarps * 32) {
+      float2 y = make_float2(0.f, 0.f);
+      if (b0 > 0) {
+        y = job.in[(int64_t)row * ts + b0 - 1];
+        if (job.in2) {
+          const float2 y2 = job.in2[(int64_t)row * ts + b0 - 1];
+          y = make_float2(y.x + y2.x, y.y + y2.y);
+        }
+      }
+      tileT[row * LD] = y;
+    }
   }
   F fft;
   fft.init(tw, lane);
@@ -451,7 +522,7 @@ __global__ void __launch_bounds__(kFftWarps * 32) k_irfft_ola_t(const FftInvJob*
 template <int LOG2H, int BPW>
 static void launch_fwd_tt(const FftFwdJob* jobs, int n_jobs, int64_t max_blocks, int64_t ts, const float2* tw, cudaStream_t s) {
   constexpr int H = 1 << LOG2H, TBK = kFftWarps * BPW;
-  constexpr size_t smem = sizeof(float2) * (size_t)(H + 1) * (TBK + 1);
+  constexpr size_t smem = sizeof(float2) * (size_t)((((H + 1) * (TBK + 1)) + 1) & ~1) + sizeof(float) * (size_t)TBK * H;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_rfft_fwd_t<LOG2H, BPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

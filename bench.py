@@ -18,8 +18,11 @@ A "step" is one complete render of the workload.
            D2H of the result are all inside the timed region (wall clock between device synchronisations).
   roofline: dominant kernel = the spectral MAC (K6).  achieved = algorithmic bytes of the reference algorithm
            (per channel-convolver block 16*P*C + 8*C + 8*B, T = 1 contract) / K6's CUDA-event duration.
-           The production kernel is register-tiled over 16 output blocks and re-uses L2, so it moves far fewer DRAM bytes
-           than the contract and runs FP32-bound; `roofline_fp32` reports that side.
+           The production K6 computes the same sums as a fast convolution along block time (a second FFT over the
+           partition axis, csrc/fft2.cu): it moves each spectrogram through HBM once instead of P times, so the contract
+           fraction is >> 1; `roofline_moved` is the honest one — the bytes THIS algorithm has to move (X, H2, Y once)
+           over K6's time against the measured HBM peak, with the ncu-measured DRAM traffic beside it — and
+           `roofline_fp32` gives the flops it issues against the FP32 peak.
   cpu_baseline: the CPU oracle (a C++ restatement of the reference's algorithm; the reference is C#/.NET and cannot run
            here) on a bounded sample of the same workload, 1 thread (the reference renders a context on one thread).
 """
@@ -62,9 +65,10 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def ncu_traffic():
-    """DRAM bytes per K6 launch from the committed ncu --set full capture, if a summary exists."""
-    p = os.path.join(ROOT, "profiles", "mac_traffic.json")
+def ncu_traffic(variant_used):
+    """DRAM bytes per K6 launch on the C2 workload from the committed ncu --set full capture of the variant in use."""
+    name = {3: "k6_fft2_traffic.json"}.get(variant_used, "mac_traffic.json")
+    p = os.path.join(ROOT, "profiles", name)
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -220,7 +224,7 @@ def run_ours(args, wl):
     L = N.lib()
 
     def build():
-        return build_graph(G, wl, voices, device_id=local, tile_blocks=args.tile_blocks, partition=args.partition)
+        return build_graph(G, wl, voices, device_id=local, tile_blocks=args.tile_blocks, partition=args.partition, mac_variant=args.mac_variant)
 
     def comm(ctx):
         if world > 1:
@@ -278,7 +282,7 @@ def run_ours(args, wl):
     # partitions the same linear convolution needs 4x fewer MACs (different rounding points, same 1e-5 gate — tests/).
     extra512 = None
     if world == 1 and args.partition == 128 and not args.no_extra:
-        c5 = build_graph(G, wl, voices, device_id=local, tile_blocks=args.tile_blocks, partition=512)
+        c5 = build_graph(G, wl, voices, device_id=local, tile_blocks=args.tile_blocks, partition=512, mac_variant=args.mac_variant)
         g5 = c5._graph()
         ms5 = []
         for i in range(3 + min(args.steps, 20)):
@@ -302,7 +306,7 @@ def run_ours(args, wl):
     for i in range(2 + args.steps):
         def fresh():
             return G.OfflineAudioContext(FS, device_id=local, tile_blocks=args.tile_blocks, partition=args.partition,
-                                         async_upload=not args.sync_upload)
+                                         mac_variant=args.mac_variant, async_upload=not args.sync_upload)
         if world > 1:
             c = fresh()
             comm(c)
@@ -342,8 +346,18 @@ def run_ours(args, wl):
         mac_ms = float(np.mean([s["ms_mac"] for s in stats]))
         alg_bytes = s_last["algorithmic_bytes"]
         achieved = alg_bytes / (mac_ms * 1e-3) / 1e9
-        traffic = ncu_traffic()
-        flops = 8.0 * s_last["mac_complex_macs"]
+        used = int(s_last["mac_variant_used"])
+        traffic = ncu_traffic(used) if args.workload == "c2" and args.partition == 128 else None
+        flops = s_last["mac_flops"]
+        k6_name = {1: "k_mac_stream (K6, direct sum, reference op order)", 2: "k_mac_tiled (K6, register-tiled direct sum, FFMA)",
+                   4: "k_mac_tiled (K6, register-tiled direct sum, FFMA2)",
+                   3: "k_fft2_conv16 (K6 spectral MAC as a fast convolution along block time)"}.get(used, "K6")
+        moved = s_last["mac_bytes_moved"]
+        conv_ms = float(np.mean([s["ms_fft_fwd"] + s["ms_mac"] + s["ms_fft_inv"] for s in stats]))
+        # bytes the whole convolver (K5 + K6 + K7) has to move once: signal in (+ gain table), XT out/in, H2, YT out/in, signal out
+        units = s_last["conv_units"]
+        Bp = args.partition
+        conv_bytes = units * (4.0 * Bp * 2 + 8.0 * (Bp + 1) * 4) + (moved - units * 16.0 * (Bp + 1) if used == 3 else 0.0)
         sm_mhz = clocks.get("sm_mhz") or sm_max
         fp32_peak_tf = 148 * 128 * 2 * sm_max * 1e6 / 1e12
         line = {
@@ -363,11 +377,16 @@ def run_ours(args, wl):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                         "kernel": "k_mac_tiled (K6 spectral MAC)", "peak_source": peak_src, "ms_per_launch": mac_ms,
+                         "kernel": k6_name, "peak_source": peak_src, "ms_per_launch": mac_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "contract = reference algorithm's bytes (T=1, C=B+1); frac > 1 because the kernel tiles 16 output blocks per thread and re-uses L2 — see roofline_fp32 and profiles/"},
+                         "note": "contract = the reference algorithm's bytes (SURVEY.md 8d: T=1, C=B+1, FDL + IR walked once per quantum); frac >> 1 because K6 here is a fast convolution along block time that moves each spectrogram once — see roofline_moved (bytes this algorithm must move) and traffic (ncu dram bytes)"},
+            "roofline_moved": {"bound": "hbm", "achieved": moved / (mac_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": moved / (mac_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": moved, "kernel": k6_name,
+                               "convolver_K5_K6_K7": {"ms": conv_ms, "bytes": conv_bytes, "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9,
+                                                      "frac": conv_bytes / (conv_ms * 1e-3) / 1e9 / peak}},
             "roofline_fp32": {"bound": "fp32", "achieved": flops / (mac_ms * 1e-3) / 1e12, "peak": fp32_peak_tf, "unit": "TFLOP/s",
                               "frac": flops / (mac_ms * 1e-3) / 1e12 / fp32_peak_tf,
+                              "flops_per_launch": flops,
                               "peak_source": f"148 SMs x 128 FMA/clk x 2 x {sm_max:.0f} MHz (nominal max clock); median SM clock under load {sm_mhz} MHz"},
             "kernel_ms": {k: float(np.mean([s[k] for s in stats])) for k in
                           ["ms_source", "ms_automation", "ms_biquad", "ms_gain", "ms_fft_fwd", "ms_mac", "ms_fft_inv", "ms_mix", "ms_d2h"]},
@@ -403,6 +422,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--partition", type=int, default=128)
     ap.add_argument("--tile-blocks", dest="tile_blocks", type=int, default=32)
+    ap.add_argument("--mac-variant", dest="mac_variant", type=int, default=0,
+                    help="K6 algorithm (gac_context_desc.mac_variant): 0 default (second-level FFT), 1 streaming direct sum, 4 register-tiled direct sum")
     ap.add_argument("--cpu-voices", dest="cpu_voices", type=int, default=8)
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the partition-512 extra measurement")

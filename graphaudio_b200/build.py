@@ -25,6 +25,7 @@ SOURCES = [
     ("mac.cu", []),
     ("fft.cu", []),
     ("fft2.cu", []),
+    ("fft_r16.cu", []),
     ("nodes.cu", ["--fmad=false"]),
     ("biquad.cu", ["--fmad=false"]),
     ("biquad_lanes.cu", ["--fmad=false"]),

@@ -630,14 +630,31 @@ struct RenderEnv {
   double mac_flops = 0, mac_bytes = 0;  // flops issued / bytes the K6 variant in use has to move (X, H, Y once)
   int mac_used = 0;                     // K6 variant of the last convolver batch (1 stream, 2/4 tiled, 3 second-level FFT)
   std::map<Sig*, std::pair<const float*, float>> fused;  // GainNode folded into the next convolver's forward FFT
+  std::map<std::string, float*> param_tables;  // automation tables already evaluated in this render, by (rate, value, events)
 };
 
 static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector<ParamJob>& jobs, float** out_table) {
   *out_table = nullptr;
   if (p.ev.empty()) return GAC_OK;
+  // voices that schedule the same automation (same value, same events) share one table: the curve depends on nothing else
+  std::string key(1, a_rate ? 'a' : 'k');
+  key.append(reinterpret_cast<const char*>(&p.value), sizeof(float));
+  for (const gac_event& e : p.ev) {  // field by field: the struct has 4 bytes of padding
+    key.append(reinterpret_cast<const char*>(&e.type), sizeof(e.type));
+    key.append(reinterpret_cast<const char*>(&e.value), sizeof(e.value));
+    key.append(reinterpret_cast<const char*>(&e.target), sizeof(e.target));
+    key.append(reinterpret_cast<const char*>(&e.time), sizeof(e.time));
+    key.append(reinterpret_cast<const char*>(&e.time_constant), sizeof(e.time_constant));
+  }
+  auto hit = env.param_tables.find(key);
+  if (hit != env.param_tables.end()) {
+    *out_table = hit->second;
+    return GAC_OK;
+  }
   float* tab = nullptr;
   int rc = env.scratch->alloc(&tab, a_rate ? (size_t)env.Npad : (size_t)env.NQ);
   if (rc) return rc;
+  env.param_tables[key] = tab;
   auto& hev = env.keep->make<DevEvent>();
   hev.resize(p.ev.size());
   static_assert(sizeof(DevEvent) == sizeof(gac_event), "event layout");
@@ -919,7 +936,8 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     if ((rc = env.scratch->upload(&dcj, cj))) return rc;
     if ((rc = env.scratch->upload(&dij, ij))) return rc;
     int t = env.timer->begin(C_FFT_FWD);
-    launch_rfft_fwd_t(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
+    if (B == 128) launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, Qs, ctx->d_tab16 + fft2_table_offset(128), ctx->d_tw, ctx->stream);
+    else launch_rfft_fwd_t(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_MAC);
@@ -927,7 +945,8 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
-    launch_irfft_ola_t(dij, (int)ij.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
+    if (B == 128) launch_irfft_ola_t8(dij, (int)ij.size(), QB, Qs, ctx->d_tab16 + fft2_table_offset(128), ctx->d_tw, ctx->stream);
+    else launch_irfft_ola_t(dij, (int)ij.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
     env.timer->end(t);
     CU(cudaGetLastError());
     env.launches += 3;

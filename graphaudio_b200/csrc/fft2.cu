@@ -300,16 +300,24 @@ __global__ void __launch_bounds__(M / 16) k_fft2_prep16(const float2* __restrict
 int fft2_h2_row_elems(int M) { return M <= 4096 ? r16::smem_elems(M) : M; }
 
 int fft2_table_offset(int M) {  // offset of M's radix-16 twiddle table inside the concatenated table buffer
+  // order: 512, 1024, 2048, 4096 (second-level transforms), then 128, 256 (first-level transforms of fft_r16.cu)
   int off = 0;
-  for (int m = 512; m < M; m *= 2) off += r16::table_elems(m);
+  if (M >= 512) {
+    for (int m = 512; m < M; m *= 2) off += r16::table_elems(m);
+    return off;
+  }
+  for (int m = 512; m <= 4096; m *= 2) off += r16::table_elems(m);
+  for (int m = 128; m < M; m *= 2) off += r16::table_elems(m);
   return off;
 }
-int fft2_table_total() { return fft2_table_offset(8192); }
+int fft2_table_total() { return fft2_table_offset(256) + r16::table_elems(256); }
 void fft2_fill_tables(float2* host) {
   const double pi = 3.14159265358979323846;
-  for (int M = 512; M <= 4096; M *= 2) {
+  const int sizes[6] = {512, 1024, 2048, 4096, 128, 256};
+  for (int si = 0; si < 6; si++) {
+    const int M = sizes[si];
     float2* tab = host + fft2_table_offset(M);
-    const int T = M / 16, L = M / 256;
+    const int T = M / 16, L = M >= 512 ? M / 256 : 0;  // L = 0: no stage B (first-level plans)
     for (int q = 0; q < 4; q++) {
       for (int t = 0; t < T; t++) {
         const double a = -2.0 * pi * (double)(t << q) / (double)M;

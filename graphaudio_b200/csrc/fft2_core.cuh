@@ -261,7 +261,7 @@ using f2::subf;
 
 F2_HD int pad(int e) { return e + ((e >> 4) << 1) + ((e >> 7) << 3); }
 constexpr int smem_elems(int M) { return M + (M >> 4) * 2 + (M >> 7) * 8; }
-constexpr int table_elems(int M) { return 4 * (M / 16) + 4 * (M / 256); }  // [4][T] stage A, [4][L] stage B
+constexpr int table_elems(int M) { return 4 * (M / 16) + (M >= 512 ? 4 * (M / 256) : 0); }  // [4][T] stage A, [4][L] stage B
 
 F2_HD constexpr int rev4(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r >> 3) & 1); }
 
@@ -331,9 +331,10 @@ F2_HD void compose(float2 w1, float2 w2, float2 w4, float2 w8, float2 (&w)[16]) 
 template <int M>
 struct Plan {
   static constexpr int T = M / 16;
-  static constexpr int L = M / 256;
+  static constexpr bool HAS_B = M >= 512;           // M = 128, 256 (the first-level transforms of fft_r16.cu): stages A and C only
+  static constexpr int L = HAS_B ? M / 256 : M / 16;
   static constexpr int SE = M + (M >> 4) * 2 + (M >> 7) * 8;  // == smem_elems(M), usable in device code
-  static_assert(M == 512 || M == 1024 || M == 2048 || M == 4096, "radix-16 plan: M = 256 L, L in {2,4,8,16}");
+  static_assert(M == 128 || M == 256 || M == 512 || M == 1024 || M == 2048 || M == 4096, "radix-16 plan: M = 16 L or 256 L, L in {2,4,8,16}");
 };
 
 // tab: [4][T] then [4][L]

@@ -31,8 +31,38 @@ constexpr int smem_elems(int M) { return M + (M >> 4) * 2; }
 
 F2_HD float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 F2_HD float2 cmulcf(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
-F2_HD float2 addf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-F2_HD float2 subf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / sub: one packed instruction on the device (Blackwell FADD2, PTX add/sub.rn.f32x2) — the butterflies are
+// dominated by them (680 of the 1700 instructions of k_fft2_conv16 were scalar FADDs)
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+#endif
+F2_HD float2 addf(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return upk2(r);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+F2_HD float2 subf(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return upk2(r);
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 
 F2_HD constexpr int rev3(int r) { return ((r & 1) << 2) | (r & 2) | ((r >> 2) & 1); }
 

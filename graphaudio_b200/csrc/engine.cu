@@ -9,9 +9,11 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -92,7 +94,21 @@ struct gac_context {
   // preparation and the first voice batches of the next render
   bool async_upload = false;
   cudaStream_t copy_stream = nullptr;
+  // ... and IR preparation runs on its own stream, so that a render never queues behind the preparation of an impulse
+  // response whose upload is still in flight; renders wait on the `ready` event of exactly the IRs they use
+  cudaStream_t prep_stream = nullptr;
+  std::vector<cudaEvent_t> event_pool;  // recycled `ready` events (creating one costs a driver call per buffer)
 };
+static cudaEvent_t take_event(gac_context* ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
 struct gac_buffer {
   gac_context* ctx;
   int nch;
@@ -115,9 +131,13 @@ struct gac_ir {
   float2* d_H = nullptr;  // [nch][P16][B]
   float* d_scale = nullptr;
   // second-level spectra (fft2.cu): [nch][B+1][M2], or null when the context's mac_variant never uses them
-  float2* d_H2 = nullptr;
+  float2* d_H2 = nullptr;  // (inside the d_H allocation)
   int M2 = 0, Lh = 0;
+  cudaEvent_t ready = nullptr;  // async mode: recorded on the preparation stream behind the last preparation kernel
 };
+static inline void wait_ready_ir(gac_context* ctx, const gac_ir* ir) {
+  if (ir && ir->ready) cudaStreamWaitEvent(ctx->stream, ir->ready, 0);
+}
 struct gac_graph {
   gac_context* ctx;
   std::vector<VoiceH> voices;
@@ -320,7 +340,10 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   ctx->tile_blocks = desc->tile_blocks == 64 ? 64 : 32;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->async_upload = (desc->flags & GAC_FLAG_ASYNC_UPLOAD) != 0;
-  if (ctx->async_upload) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (ctx->async_upload) {
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+  }
   ctx->scratch_budget = di.budget;
   // twiddles e^{-2 pi i k / N}, N = 2B, in double then rounded once
   std::vector<float2> tw(B);
@@ -347,6 +370,12 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   }
   int rc = ensure_block_times(ctx.get(), 8192);
   if (rc) return rc;
+  if (ctx->prep_stream) {  // the preparation stream reads the twiddle tables uploaded above
+    cudaEvent_t e = take_event(ctx.get());
+    CU(cudaEventRecord(e, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->prep_stream, e, 0));
+    ctx->event_pool.push_back(e);
+  }
   *out = ctx.release();
   return GAC_OK;
 }
@@ -355,6 +384,7 @@ extern "C" int gac_synchronize(gac_context* ctx) {
   if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
   CU(cudaSetDevice(ctx->device));
   if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+  if (ctx->prep_stream) CU(cudaStreamSynchronize(ctx->prep_stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return GAC_OK;
 }
@@ -373,6 +403,11 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
   }
+  if (ctx->prep_stream) {
+    cudaStreamSynchronize(ctx->prep_stream);
+    cudaStreamDestroy(ctx->prep_stream);
+  }
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   ctx->magic = 0;
   delete ctx;
@@ -400,14 +435,8 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
   // Asynchronous path (opt-in, and only for page-locked sources — pageable copies are staged synchronously by the
   // runtime anyway): the copy is queued on the copy stream and the call returns; the arrays must stay valid and
   // unmodified until the next gac_render* / gac_synchronize returns.
-  bool async = ctx->async_upload;
-  if (async) {
-    for (int c = 0; c < n_channels && async; c++) {
-      cudaPointerAttributes attr;
-      if (cudaPointerGetAttributes(&attr, channels[c]) != cudaSuccess || attr.type != cudaMemoryTypeHost) async = false;
-      cudaGetLastError();
-    }
-  }
+  // (pageable arrays are still correct here: the runtime stages them before cudaMemcpyAsync returns)
+  const bool async = ctx->async_upload;
   cudaStream_t st = async ? ctx->copy_stream : ctx->stream;
   CU(cudaMallocAsync(&b->d, sizeof(float) * b->stride * n_channels, st));
   // the slack behind each channel is never read: k_source_copy stays inside [0, n) and the resampler's taps are the last
@@ -415,7 +444,7 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
   for (int c = 0; c < n_channels; c++)
     CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, st));
   if (async) {
-    CU(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
+    b->ready = take_event(ctx);
     CU(cudaEventRecord(b->ready, st));
   } else {
     CU(cudaStreamSynchronize(st));  // the caller may reuse its arrays as soon as we return
@@ -429,7 +458,7 @@ extern "C" int gac_buffer_destroy(gac_buffer* buf) {
   // stream-ordered free: safe behind any render still queued on the context stream
   if (buf->ready) {
     cudaStreamWaitEvent(buf->ctx->stream, buf->ready, 0);
-    cudaEventDestroy(buf->ready);
+    buf->ctx->event_pool.push_back(buf->ready);
   }
   cudaFreeAsync(buf->d, buf->ctx->stream);
   delete buf;
@@ -442,18 +471,26 @@ static int upload_now(gac_context* ctx, void* dst, const void* src, size_t bytes
   return GAC_OK;
 }
 
-static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir) {
+// `st` = the stream the preparation runs on (the context stream, or the preparation stream in async mode)
+static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir,
+                             cudaStream_t st) {
   const int B = ctx->B;
   ir->P = (int)((frames + B - 1) / B);  // ceil(L / blockSize)  PartitionedConvolver.cs:44
   ir->P16 = std::max(16, ((ir->P + 15) / 16) * 16);
-  // one stream-ordered allocation: spectra [nch][P16][B] float2 followed by the per-channel scales
+  ir->M2 = wants_fft2(ctx) ? fft2_pick_m(ir->P, &ir->Lh) : 0;
+  if (ir->M2 > 0 && !use_fft2(ctx, ir->P, ir->M2)) ir->M2 = 0;
+  // one stream-ordered allocation: spectra [nch][P16][B] float2, the second-level spectra, the per-channel scales
   const size_t hbytes = sizeof(float2) * (size_t)nch * ir->P16 * B;
-  CU(cudaMallocAsync(&ir->d_H, hbytes + sizeof(float) * nch, ctx->stream));
-  ir->d_scale = reinterpret_cast<float*>(reinterpret_cast<char*>(ir->d_H) + hbytes);
-  CU(cudaMemsetAsync(ir->d_H, 0, hbytes, ctx->stream));  // rows >= P stay zero (the tiled MAC reads P16 rows)
+  const size_t h2bytes = ir->M2 > 0 ? sizeof(float2) * (size_t)nch * (B + 1) * fft2_h2_row_elems(ir->M2) : 0;
+  CU(cudaMallocAsync(&ir->d_H, hbytes + h2bytes + sizeof(float) * nch, st));
+  ir->d_H2 = h2bytes ? reinterpret_cast<float2*>(reinterpret_cast<char*>(ir->d_H) + hbytes) : nullptr;
+  ir->d_scale = reinterpret_cast<float*>(reinterpret_cast<char*>(ir->d_H) + hbytes + h2bytes);
+  // rows P .. P16 stay zero (the register-tiled MAC reads whole 16-row chunks); rows < P are written by the transform
+  if (ir->P16 > ir->P)
+    CU(cudaMemset2DAsync(ir->d_H + (size_t)ir->P * B, sizeof(float2) * (size_t)ir->P16 * B, 0, sizeof(float2) * (size_t)(ir->P16 - ir->P) * B, nch, st));
   // (float)Math.Pow(10, GainCalibration * 0.05f) with GainCalibration = -58  (PartitionedConvolver.cs:95,101)
   const float cal = (float)std::pow(10.0, (double)(-58.f * 0.05f));
-  launch_ir_scale(d_ir, stride, nch, frames, normalize && frames > 0 ? 1 : 0, cal, ir->d_scale, ctx->stream);
+  launch_ir_scale(d_ir, stride, nch, frames, normalize && frames > 0 ? 1 : 0, cal, ir->d_scale, st);
   FftFwdUniform u;
   u.in_base = d_ir;
   u.in_stride = stride;
@@ -462,17 +499,14 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   u.scale_base = ir->d_scale;
   u.n_valid = frames;
   u.n_blocks = ir->P;
-  launch_rfft_fwd_uniform(u, nch, B, ctx->d_tw, ctx->stream);
+  launch_rfft_fwd_uniform(u, nch, B, ctx->d_tw, st);
   CU(cudaGetLastError());
   // second-level spectra: FFT of every bin's partition sequence along p (fft2.cu)
-  ir->M2 = wants_fft2(ctx) ? fft2_pick_m(ir->P, &ir->Lh) : 0;
-  if (ir->M2 > 0 && !use_fft2(ctx, ir->P, ir->M2)) ir->M2 = 0;
   if (ir->M2 > 0) {
-    CU(cudaMallocAsync(&ir->d_H2, sizeof(float2) * (size_t)nch * (B + 1) * fft2_h2_row_elems(ir->M2), ctx->stream));
-    launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, nch, B, ir->P, ir->M2, ir->d_H2, ctx->d_tw2, ctx->d_tab16, ctx->stream);
+    launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, nch, B, ir->P, ir->M2, ir->d_H2, ctx->d_tw2, ctx->d_tab16, st);
     CU(cudaGetLastError());
   }
-  // no host synchronisation: every later use of the spectra is ordered on the same stream
+  // no host synchronisation: every later use of the spectra is ordered behind `st` (same stream, or the `ready` event)
   return GAC_OK;
 }
 
@@ -495,12 +529,16 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
   ir->nch = buf->nch;
   ir->true_stereo = ts;
   ir->frames = buf->n;
-  wait_ready(ctx, buf);
-  int rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get());
+  cudaStream_t st = ctx->prep_stream ? ctx->prep_stream : ctx->stream;
+  if (buf->ready) CU(cudaStreamWaitEvent(st, buf->ready, 0));  // the IR's upload may still be in flight
+  int rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get(), st);
   if (rc) {
-    if (ir->d_H) cudaFreeAsync(ir->d_H, ctx->stream);
-    if (ir->d_H2) cudaFreeAsync(ir->d_H2, ctx->stream);
+    if (ir->d_H) cudaFreeAsync(ir->d_H, st);
     return rc;
+  }
+  if (ctx->prep_stream) {
+    ir->ready = take_event(ctx);
+    CU(cudaEventRecord(ir->ready, st));
   }
   *out = ir.release();
   return GAC_OK;
@@ -508,9 +546,12 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
 extern "C" int gac_ir_destroy(gac_ir* ir) {
   if (!ir) return fail(GAC_ERR_INVALID_ARGUMENT, "ir is null");
   cudaSetDevice(ir->ctx->device);
-  // stream-ordered free
+  // stream-ordered free, behind the preparation and behind any render still queued on the context stream
+  if (ir->ready) {
+    cudaStreamWaitEvent(ir->ctx->stream, ir->ready, 0);
+    ir->ctx->event_pool.push_back(ir->ready);
+  }
   cudaFreeAsync(ir->d_H, ir->ctx->stream);
-  if (ir->d_H2) cudaFreeAsync(ir->d_H2, ir->ctx->stream);
   delete ir;
   return GAC_OK;
 }
@@ -1117,6 +1158,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           env.fused.erase(f);
         }
         const gac_ir* ir = op.ir;
+        wait_ready_ir(ctx, ir);
         auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
         auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(ir->M2)) : (const float2*)nullptr; };
         ConvItem it;

@@ -297,7 +297,20 @@ static int mix_into(RenderEnv& env, std::vector<MixJob>& jobs, std::vector<MixIn
   return GAC_OK;
 }
 
+// GAC_TRACE=1: host-side timestamps of a render's phases on stderr (diagnostics only)
+struct HostTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  HostTrace() : on(getenv("GAC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[gac_trace] %-28s +%.3f ms\n", what, ms);
+  }
+};
+
 static int render_core(gac_context* ctx, const RenderArgs& a) {
+  HostTrace trace;
   if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");  // ObjectDisposedException (AudioContextBase.cs:54-55)
   if (!a.graphs || a.n_graphs <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "no graph");
   if (a.n_frames <= 0) return fail(GAC_ERR_OUT_OF_RANGE, "Frame count must be positive.");         // OfflineAudioContext.cs:35-36
@@ -347,22 +360,43 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     sigs[i].p[1] = d_sig + (i * 2 + 1) * (size_t)env.Npad;
     sigs[i].ops = &voices[i]->ops;
   }
-  // With asynchronous uploads some source buffers may still be in flight: process the voices in a few batches so that
-  // the first ones (whose data has landed) run while the copy engine delivers the rest.  Otherwise one batch.
-  size_t n_pending = 0;
-  for (auto* v : voices)
-    if (v->src->ready && cudaEventQuery(v->src->ready) == cudaErrorNotReady) n_pending++;
+  // With asynchronous uploads some buffers may still be in flight (and their impulse responses not yet prepared).  Uploads
+  // are queued in creation order, so the voices whose data has landed form a prefix: that prefix runs at once as one batch,
+  // the rest follows in small batches so that little work is left when the copy engine delivers the last buffer.
+  auto landed = [&](const VoiceH* v) {
+    if (v->src->ready && cudaEventQuery(v->src->ready) == cudaErrorNotReady) return false;
+    for (const OpH& op : v->ops)
+      if (op.kind == GAC_OP_CONVOLVER && op.ir && op.ir->ready && cudaEventQuery(op.ir->ready) == cudaErrorNotReady) return false;
+    return true;
+  };
+  if (trace.on && ctx->copy_stream && atoi(getenv("GAC_TRACE")) >= 2) {  // diagnostics: when do the uploads end?
+    cudaStreamSynchronize(ctx->copy_stream);
+    trace.mark("uploads finished");
+    if (ctx->prep_stream) cudaStreamSynchronize(ctx->prep_stream);
+    trace.mark("IR preparation finished");
+  }
+  size_t v_ready = 0;
+  while (v_ready < S && landed(voices[v_ready])) v_ready++;
   cudaGetLastError();
-  // (buffers are uploaded in creation order, so the pending ones are the last voices)
-  const size_t n_batches = (n_pending > 0 && S >= 16) ? 1 + (3 * n_pending + S - 1) / S : 1;
-  for (size_t bi = 0; bi < n_batches; bi++) {
-    const size_t v0 = S * bi / n_batches, v1 = S * (bi + 1) / n_batches;
+  std::vector<size_t> cuts;
+  cuts.push_back(0);
+  if (v_ready < S && S >= 16) {
+    if (v_ready >= 4) cuts.push_back(v_ready);
+    const size_t rest = S - cuts.back();
+    const size_t chunk = std::max<size_t>(4, (rest + 2) / 3);
+    for (size_t v = cuts.back() + chunk; v < S; v += chunk) cuts.push_back(v);
+  }
+  cuts.push_back(S);
+  if (trace.on) fprintf(stderr, "[gac_trace] voices %zu landed %zu batches %zu\n", S, v_ready, cuts.size() - 1);
+  for (size_t bi = 0; bi + 1 < cuts.size(); bi++) {
+    const size_t v0 = cuts[bi], v1 = cuts[bi + 1];
     if (v1 <= v0) continue;
     std::vector<const VoiceH*> vsub(voices.begin() + v0, voices.begin() + v1);
     std::vector<Sig> ssub(sigs.begin() + v0, sigs.begin() + v1);
     if ((rc = plan_sources(env, vsub, ssub))) return rc;
     if ((rc = run_chains(env, ssub))) return rc;
     std::copy(ssub.begin(), ssub.end(), sigs.begin() + v0);
+    trace.mark("voice batch queued");
   }
 
   // ---- buses: fan-in in connection (= voice index) order, AudioNodeInput.cs:118-137
@@ -496,10 +530,14 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     timer.end(t);
   }
   // ---- finish: the host job arrays in `keep` must outlive the stream work, so every render synchronises here
+  trace.mark("everything queued");
   gac_stats st{};
   timer.finish(&st);
+  trace.mark("device finished");
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "render failed: %s", cudaGetErrorString(e));
+  // the async-upload contract releases the caller's arrays when a render returns: buffers this render did not use too
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "render failed: %s", cudaGetErrorString(e));
   st.conv_units = env.conv_units;
@@ -752,10 +790,9 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
   gac_ir irh{};
   irh.ctx = ctx;
   irh.nch = n_signals;
-  rc = ir_prepare_device(ctx, dir.as<float>(), stride, n_signals, ir_frames, normalize != 0, &irh);
-  DevBuf holdH, holdH2;
-  holdH.p = irh.d_H;  // (the scales live at the end of the same allocation)
-  holdH2.p = irh.d_H2;
+  rc = ir_prepare_device(ctx, dir.as<float>(), stride, n_signals, ir_frames, normalize != 0, &irh, ctx->stream);
+  DevBuf holdH;
+  holdH.p = irh.d_H;  // (the second-level spectra and the scales live in the same allocation)
   if (rc) return rc;
   DevBuf dx;
   if ((rc = dev_alloc(dx, (size_t)n_signals * Npad * 4))) return rc;

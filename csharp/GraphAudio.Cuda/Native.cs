@@ -56,6 +56,7 @@ internal unsafe struct GacVoiceDesc
     public int OpCount;
     public GacOpDesc* Ops;
     public int Bus;
+    public int Input;   // 0 = fed by Source; k > 0 = fed by the output of bus k-1
 }
 
 [StructLayout(LayoutKind.Sequential)]
@@ -63,6 +64,9 @@ internal unsafe struct GacBusDesc
 {
     public int OpCount;
     public GacOpDesc* Ops;
+    public int Target;      // 0 = destination, k > 0 = input of bus k-1, -1 = only read by bus-fed chains
+    public int InputCount;  // connection order at the fan-in (entries >= 0: bus indices, < 0: ~voice index); 0 / null = default
+    public int* Inputs;
 }
 
 [StructLayout(LayoutKind.Sequential)]

@@ -53,11 +53,12 @@ class gac_op_desc(C.Structure):
 class gac_voice_desc(C.Structure):
     _fields_ = [("source", C.c_void_p), ("start_when", C.c_double), ("start_offset", C.c_double),
                 ("start_duration", C.c_double), ("stop_when", C.c_double), ("playback_rate", C.c_float),
-                ("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc)), ("bus", C.c_int32)]
+                ("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc)), ("bus", C.c_int32), ("input", C.c_int32)]
 
 
 class gac_bus_desc(C.Structure):
-    _fields_ = [("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc))]
+    _fields_ = [("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc)), ("target", C.c_int32), ("n_inputs", C.c_int32),
+                ("inputs", C.POINTER(C.c_int32))]
 
 
 class gac_graph_desc(C.Structure):

@@ -346,71 +346,158 @@ class OfflineAudioContext:
             raise NotSupportedException(f"{type(node).__name__} is outside the accelerated path")
         return op
 
-    def _walk_voice(self, node):
-        """node .. upstream to a source through single-input nodes -> (source, [ops source->node]) or None if unconnected."""
-        ops = []
-        while not isinstance(node, AudioBufferSourceNode):
-            if len(node._out) > 1:
-                raise NotSupportedException("fan-out inside a voice chain is outside the accelerated path (SURVEY.md §8f-2)")
-            ops.append(node)
-            if len(node._in) == 0:
-                return None
-            if len(node._in) > 1:
-                raise NotSupportedException("nested fan-in is outside the accelerated path")
-            node = node._in[0]
-        if len(node._out) > 1:
-            raise NotSupportedException("a source feeding several nodes is outside the accelerated path (SURVEY.md §8f-2)")
-        return node, list(reversed(ops))
+    def _topology_full(self):
+        """Pure host logic (no device needed).  Cuts the node graph into the three things the C ABI knows:
+          * voices  — chains of single-input / single-output nodes fed by an AudioBufferSourceNode: (source, [ops], bus, -1)
+          * buses   — a node with several inputs (AudioNodeInput fan-in, summed in connection order) plus the chain behind it
+          * chains fed by a bus output — (None, [ops], bus, input_bus): a node whose output feeds several nodes ends a bus
+            (one is inserted if the signal was not a bus yet), and every branch reads that bus
+        which together express any acyclic graph of the supported nodes, e.g. GraphAudio.Kit's ReverbEffect
+        (input -> dry gain -> output ; input -> convolver -> wet gain -> output, Effects/ReverbEffect.cs:63-91) and AudioBus
+        hierarchies (AudioBus.cs:76-114).  Returns (voices, bus_ops, dest_inputs, bus_targets, bus_inputs)."""
+        dest = self.Destination
+        # nodes that reach the destination
+        live, stack = set(), [dest]
+        while stack:
+            n = stack.pop()
+            if id(n) in live:
+                continue
+            live.add(id(n))
+            stack.extend(n._in)
+
+        def outs(n):
+            return [d for d in n._out if id(d) in live]
+
+        def is_src(n):
+            return isinstance(n, AudioBufferSourceNode)
+
+        def fan_in(n):  # starts a bus
+            return n is not dest and not is_src(n) and (len(n._in) != 1 or getattr(n, "_force_bus", False))
+
+        voices, bus_ops, bus_targets, bus_inputs, dest_inputs = [], [], [], [], []
+        bus_of_head = {}   # id(fan-in node or materialised tail) -> bus index
+        edge_code = {}     # (id(upstream), id(downstream)) -> input code at the downstream fan-in (>= 0 bus, < 0 ~voice)
+
+        def chain_from(first):
+            """[first, ...] downstream while the link is single-output -> single-input and does not enter a bus / the destination"""
+            chain, n = [], first
+            while True:
+                chain.append(n)
+                o = outs(n)
+                if len(o) != 1 or o[0] is dest or fan_in(o[0]):
+                    return chain
+                n = o[0]
+
+        def new_bus(ops):
+            bus_ops.append(ops)
+            bus_targets.append(-1)  # -1: no direct target (yet); 0: destination; k > 0: bus k - 1
+            bus_inputs.append([])
+            return len(bus_ops) - 1
+
+        def emit(tail, code_is_bus, code):
+            """records where the signal at `tail` (a bus, or the voice `code`) goes; fan-out materialises a bus"""
+            o = outs(tail)
+            if len(o) == 1:
+                edge_code[(id(tail), id(o[0]))] = code if code_is_bus else ~code
+                if code_is_bus:
+                    pending_bus_target.append((code, o[0]))
+                else:
+                    pending_voice_target.append((code, o[0]))
+                return
+            # fan-out (or a dead end): every branch reads a bus
+            if not code_is_bus:
+                b = new_bus([])
+                bus_inputs[b].append(~code)
+                voices[code][2] = b
+                code = b
+            for d in o:
+                branch(code, tail, d)
+
+        def branch(bus, tail, d):
+            """the edge tail -> d of a signal that lives in bus `bus`"""
+            if d is dest or fan_in(d):
+                voices.append([None, [], -2, bus])  # pass-through chain: the bus output as an input of d
+                v = len(voices) - 1
+                edge_code[(id(tail), id(d))] = ~v
+                pending_voice_target.append((v, d))
+            else:
+                ch = chain_from(d)
+                voices.append([None, ch, -2, bus])
+                emit(ch[-1], False, len(voices) - 1)
+
+        pending_voice_target, pending_bus_target = [], []
+        # 1. source-fed voices: one per live out-edge of every source
+        for n in self._nodes:
+            if not is_src(n) or id(n) not in live:
+                continue
+            for d in outs(n):
+                if d is dest or fan_in(d):
+                    voices.append([n, [], -2, -1])
+                    v = len(voices) - 1
+                    edge_code[(id(n), id(d))] = ~v
+                    pending_voice_target.append((v, d))
+                else:
+                    ch = chain_from(d)
+                    voices.append([n, ch, -2, -1])
+                    emit(ch[-1], False, len(voices) - 1)
+        # 2. buses: every live fan-in node, with the chain behind it
+        for n in self._nodes:
+            if id(n) not in live or not fan_in(n):
+                continue
+            if len(n._in) == 0 and not getattr(n, "_force_bus", False):
+                continue  # nothing connected: contributes silence (its consumers see a missing input)
+            ch = chain_from(n)
+            b = new_bus(ch)
+            bus_of_head[id(n)] = b
+            emit(ch[-1], True, b)
+        # 3. resolve targets now that every fan-in has its bus index
+        for v, d in pending_voice_target:
+            voices[v][2] = -1 if d is dest else bus_of_head[id(d)]
+        for b, d in pending_bus_target:
+            bus_targets[b] = 0 if d is dest else bus_of_head[id(d)] + 1
+        # 4. connection order at every fan-in and at the destination
+        for n in self._nodes:
+            if id(n) in bus_of_head:
+                b = bus_of_head[id(n)]
+                bus_inputs[b] = [edge_code[(id(u), id(n))] for u in n._in if (id(u), id(n)) in edge_code] + bus_inputs[b]
+        dest_inputs = [edge_code[(id(u), id(dest))] for u in dest._in if (id(u), id(dest)) in edge_code]
+        # materialised fan-out buses keep the single input recorded in emit()
+        return [tuple(v) for v in voices], bus_ops, dest_inputs, bus_targets, bus_inputs
 
     def _topology(self):
-        """Pure host logic (no device needed): ([(source, [ops], bus)], [[bus ops]], [dest input codes])."""
-        voices, buses, dest_inputs = [], [], []
-        for head in self.Destination._in:
-            # walk up while the chain is single-input; the first node with >= 2 inputs is the bus fan-in
-            chain, node = [], head
-            while not isinstance(node, AudioBufferSourceNode) and len(node._in) == 1 and not getattr(node, "_force_bus", False):
-                chain.append(node)
-                node = node._in[0]
-            if isinstance(node, AudioBufferSourceNode):
-                voices.append((node, list(reversed(chain)), -1))
-                dest_inputs.append(~(len(voices) - 1))
-                continue
-            if len(node._in) == 0 and not getattr(node, "_force_bus", False):
-                continue  # nothing connected: contributes silence
-            chain.append(node)  # node has the fan-in input; it and everything below it run on the bus
-            bus_index = len(buses)
-            buses.append(list(reversed(chain)))
-            dest_inputs.append(bus_index)
-            for up in node._in:
-                r = self._walk_voice(up)
-                if r is not None:
-                    voices.append((r[0], r[1], bus_index))
-        # the destination input itself may be the fan-in (several voices straight into Destination): handled above
+        """([(source, [ops], bus, input_bus)], [[bus ops]], [dest input codes]) — see _topology_full."""
+        voices, buses, dest_inputs, _, _ = self._topology_full()
         return voices, buses, dest_inputs
 
     def _flatten(self):
         keep = []
-        voices, buses, dest_inputs = self._topology()
+        voices, buses, dest_inputs, bus_targets, bus_inputs = self._topology_full()
         vdesc = (N.gac_voice_desc * max(1, len(voices)))()
-        for i, (src, ops, bus) in enumerate(voices):
-            if not src._started or src.Buffer is None:
-                when = math.nan
-            else:
-                when = src._when
-            if src.Loop:
-                raise NotSupportedException("looping sources are outside the accelerated path (SURVEY.md §8f-3)")
+        for i, (src, ops, bus, input_bus) in enumerate(voices):
             v = vdesc[i]
-            v.source = src.Buffer._handle(self) if src.Buffer is not None else None
-            v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop
-            v.playback_rate = src.PlaybackRate.Value
+            if src is not None:
+                if not src._started or src.Buffer is None:
+                    when = math.nan
+                else:
+                    when = src._when
+                if src.Loop:
+                    raise NotSupportedException("looping sources are outside the accelerated path (SURVEY.md §8f-3)")
+                v.source = src.Buffer._handle(self) if src.Buffer is not None else None
+                v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop
+                v.playback_rate = src.PlaybackRate.Value
+            else:
+                v.source = None
+                v.playback_rate = 1.0
             arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep) for o in ops])
             keep.append(arr)
-            v.n_ops, v.ops, v.bus = len(ops), arr, bus
+            v.n_ops, v.ops, v.bus, v.input = len(ops), arr, bus, input_bus + 1
         bdesc = (N.gac_bus_desc * max(1, len(buses)))()
         for i, ops in enumerate(buses):
             arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep) for o in ops])
-            keep.append(arr)
+            inp = (C.c_int32 * max(1, len(bus_inputs[i])))(*bus_inputs[i])
+            keep += [arr, inp]
             bdesc[i].n_ops, bdesc[i].ops = len(ops), arr
+            bdesc[i].target, bdesc[i].n_inputs, bdesc[i].inputs = bus_targets[i], len(bus_inputs[i]), inp
         darr = (C.c_int32 * max(1, len(dest_inputs)))(*dest_inputs)
         g = N.gac_graph_desc()
         g.n_voices, g.voices, g.n_buses, g.buses = len(voices), vdesc, len(buses), bdesc

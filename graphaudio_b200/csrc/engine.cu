@@ -64,9 +64,12 @@ struct VoiceH {
   float rate = 1.f;
   std::vector<OpH> ops;
   int bus = -1;
+  int input_bus = -1;  // >= 0: the chain is fed by that bus's output instead of a source buffer
 };
 struct BusH {
   std::vector<OpH> ops;
+  int target = -1;          // -1 destination, >= 0 parent bus, -2 none (only read by bus-fed chains)
+  std::vector<int> inputs;  // connection order at the fan-in: >= 0 bus index, < 0 ~voice index
 };
 
 struct NcclApi;
@@ -611,12 +614,16 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
   for (int v = 0; v < desc->n_voices; v++) {
     const gac_voice_desc& d = desc->voices[v];
     VoiceH& h = g->voices[v];
-    if (!d.source) return fail(GAC_ERR_INVALID_OPERATION, "voice %d: Cannot start without a buffer set", v);  // AudioBufferSourceNode.cs:86-87
-    if (d.source->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: buffer belongs to another context", v);
-    if (d.source->nch > 2) return fail(GAC_ERR_UNSUPPORTED, "voice %d: sources with more than 2 channels are outside the accelerated path", v);
+    if (d.input < 0 || d.input > desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: input bus %d out of range", v, d.input - 1);
+    h.input_bus = d.input - 1;
+    if (h.input_bus < 0) {
+      if (!d.source) return fail(GAC_ERR_INVALID_OPERATION, "voice %d: Cannot start without a buffer set", v);  // AudioBufferSourceNode.cs:86-87
+      if (d.source->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: buffer belongs to another context", v);
+      if (d.source->nch > 2) return fail(GAC_ERR_UNSUPPORTED, "voice %d: sources with more than 2 channels are outside the accelerated path", v);
+      if (!(d.playback_rate >= 0.001f && d.playback_rate <= 1000.f)) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: playbackRate outside [0.001, 1000]", v);
+    }
     if (d.bus < -1 || d.bus >= desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: bus index %d out of range", v, d.bus);
-    if (!(d.playback_rate >= 0.001f && d.playback_rate <= 1000.f)) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: playbackRate outside [0.001, 1000]", v);
-    h.src = d.source;
+    h.src = h.input_bus < 0 ? d.source : nullptr;
     h.when = d.start_when;
     h.offset = d.start_offset;
     h.duration = d.start_duration;
@@ -628,17 +635,37 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
   }
   g->buses.resize(desc->n_buses);
   for (int b = 0; b < desc->n_buses; b++) {
-    int rc = copy_ops(ctx, desc->buses[b].n_ops, desc->buses[b].ops, &g->buses[b].ops);
+    const gac_bus_desc& d = desc->buses[b];
+    int rc = copy_ops(ctx, d.n_ops, d.ops, &g->buses[b].ops);
     if (rc) return rc;
+    if (d.target < -1 || d.target > desc->n_buses || d.target == b + 1) return fail(GAC_ERR_OUT_OF_RANGE, "bus %d: target %d out of range", b, d.target);
+    g->buses[b].target = d.target == 0 ? -1 : (d.target < 0 ? -2 : d.target - 1);
+  }
+  for (int b = 0; b < desc->n_buses; b++) {
+    const gac_bus_desc& d = desc->buses[b];
+    BusH& h = g->buses[b];
+    if (d.inputs && d.n_inputs > 0) {
+      h.inputs.assign(d.inputs, d.inputs + d.n_inputs);
+      for (int x : h.inputs) {
+        if (x >= 0 && (x >= desc->n_buses || g->buses[x].target != b)) return fail(GAC_ERR_INVALID_ARGUMENT, "bus %d: input bus %d does not target it", b, x);
+        if (x < 0 && (~x >= desc->n_voices || g->voices[~x].bus != b)) return fail(GAC_ERR_INVALID_ARGUMENT, "bus %d: input voice %d is not routed to it", b, ~x);
+      }
+    } else {
+      for (int v = 0; v < desc->n_voices; v++)
+        if (g->voices[v].bus == b) h.inputs.push_back(~v);
+      for (int c = 0; c < desc->n_buses; c++)
+        if (g->buses[c].target == b) h.inputs.push_back(c);
+    }
   }
   if (desc->dest_inputs && desc->n_dest_inputs > 0) {
     g->dest_inputs.assign(desc->dest_inputs, desc->dest_inputs + desc->n_dest_inputs);
     for (int x : g->dest_inputs) {
-      if (x >= 0 && x >= desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "dest_inputs: bus %d out of range", x);
+      if (x >= 0 && (x >= desc->n_buses || g->buses[x].target != -1)) return fail(GAC_ERR_OUT_OF_RANGE, "dest_inputs: bus %d out of range or not connected to the destination", x);
       if (x < 0 && (~x >= desc->n_voices || g->voices[~x].bus != -1)) return fail(GAC_ERR_INVALID_ARGUMENT, "dest_inputs: voice %d is not a direct voice", ~x);
     }
   } else {
-    for (int b = 0; b < desc->n_buses; b++) g->dest_inputs.push_back(b);
+    for (int b = 0; b < desc->n_buses; b++)
+      if (g->buses[b].target == -1) g->dest_inputs.push_back(b);
     for (int v = 0; v < desc->n_voices; v++)
       if (g->voices[v].bus == -1) g->dest_inputs.push_back(~v);
   }

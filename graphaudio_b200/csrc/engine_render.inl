@@ -360,74 +360,122 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     sigs[i].p[1] = d_sig + (i * 2 + 1) * (size_t)env.Npad;
     sigs[i].ops = &voices[i]->ops;
   }
+  // ---- stage 1: the chains fed by source buffers.
   // With asynchronous uploads some buffers may still be in flight (and their impulse responses not yet prepared).  Uploads
   // are queued in creation order, so the voices whose data has landed form a prefix: that prefix runs at once as one batch,
   // the rest follows in small batches so that little work is left when the copy engine delivers the last buffer.
   auto landed = [&](const VoiceH* v) {
-    if (v->src->ready && cudaEventQuery(v->src->ready) == cudaErrorNotReady) return false;
+    if (v->src && v->src->ready && cudaEventQuery(v->src->ready) == cudaErrorNotReady) return false;
     for (const OpH& op : v->ops)
       if (op.kind == GAC_OP_CONVOLVER && op.ir && op.ir->ready && cudaEventQuery(op.ir->ready) == cudaErrorNotReady) return false;
     return true;
   };
-  if (trace.on && ctx->copy_stream && atoi(getenv("GAC_TRACE")) >= 2) {  // diagnostics: when do the uploads end?
-    cudaStreamSynchronize(ctx->copy_stream);
-    trace.mark("uploads finished");
-    if (ctx->prep_stream) cudaStreamSynchronize(ctx->prep_stream);
-    trace.mark("IR preparation finished");
-  }
-  size_t v_ready = 0;
-  while (v_ready < S && landed(voices[v_ready])) v_ready++;
-  cudaGetLastError();
-  std::vector<size_t> cuts;
-  cuts.push_back(0);
-  if (v_ready < S && S >= 16) {
-    if (v_ready >= 4) cuts.push_back(v_ready);
-    const size_t rest = S - cuts.back();
-    const size_t chunk = std::max<size_t>(4, (rest + 2) / 3);
-    for (size_t v = cuts.back() + chunk; v < S; v += chunk) cuts.push_back(v);
-  }
-  cuts.push_back(S);
-  if (trace.on) fprintf(stderr, "[gac_trace] voices %zu landed %zu batches %zu\n", S, v_ready, cuts.size() - 1);
-  for (size_t bi = 0; bi + 1 < cuts.size(); bi++) {
-    const size_t v0 = cuts[bi], v1 = cuts[bi + 1];
-    if (v1 <= v0) continue;
-    std::vector<const VoiceH*> vsub(voices.begin() + v0, voices.begin() + v1);
-    std::vector<Sig> ssub(sigs.begin() + v0, sigs.begin() + v1);
-    if ((rc = plan_sources(env, vsub, ssub))) return rc;
-    if ((rc = run_chains(env, ssub))) return rc;
-    std::copy(ssub.begin(), ssub.end(), sigs.begin() + v0);
-    trace.mark("voice batch queued");
+  std::vector<size_t> src_voices;  // indices of the source-fed chains
+  for (size_t i = 0; i < S; i++)
+    if (voices[i]->input_bus < 0) src_voices.push_back(i);
+  const size_t S0 = src_voices.size();
+  std::vector<char> voice_done(S, 0);
+  {
+    size_t v_ready = 0;
+    while (v_ready < S0 && landed(voices[src_voices[v_ready]])) v_ready++;
+    cudaGetLastError();
+    std::vector<size_t> cuts;
+    cuts.push_back(0);
+    if (v_ready < S0 && S0 >= 16) {
+      if (v_ready >= 4) cuts.push_back(v_ready);
+      const size_t rest = S0 - cuts.back();
+      const size_t chunk = std::max<size_t>(4, (rest + 2) / 3);
+      for (size_t v = cuts.back() + chunk; v < S0; v += chunk) cuts.push_back(v);
+    }
+    cuts.push_back(S0);
+    if (trace.on) fprintf(stderr, "[gac_trace] voices %zu landed %zu batches %zu\n", S0, v_ready, cuts.size() - 1);
+    for (size_t bi = 0; bi + 1 < cuts.size(); bi++) {
+      const size_t v0 = cuts[bi], v1 = cuts[bi + 1];
+      if (v1 <= v0) continue;
+      std::vector<const VoiceH*> vsub;
+      std::vector<Sig> ssub;
+      for (size_t k = v0; k < v1; k++) {
+        vsub.push_back(voices[src_voices[k]]);
+        ssub.push_back(sigs[src_voices[k]]);
+      }
+      if ((rc = plan_sources(env, vsub, ssub))) return rc;
+      if ((rc = run_chains(env, ssub))) return rc;
+      for (size_t k = v0; k < v1; k++) {
+        sigs[src_voices[k]] = ssub[k - v0];
+        voice_done[src_voices[k]] = 1;
+      }
+      trace.mark("voice batch queued");
+    }
   }
 
-  // ---- buses: fan-in in connection (= voice index) order, AudioNodeInput.cs:118-137
+  // ---- stage 2: buses (fan-in in connection order, AudioNodeInput.cs:118-137, then the bus ops) and the chains fed by bus
+  // outputs, in dependency order: every round mixes the buses whose inputs are complete, then runs the chains they feed
   size_t NB = 0;
-  std::vector<size_t> bus_base(a.n_graphs);
-  for (int g = 0; g < a.n_graphs; g++) {
-    bus_base[g] = NB;
-    NB += a.graphs[g]->buses.size();
+  std::vector<size_t> bus_base(a.n_graphs), voice_base(a.n_graphs);
+  {
+    size_t vb = 0;
+    for (int g = 0; g < a.n_graphs; g++) {
+      bus_base[g] = NB;
+      voice_base[g] = vb;
+      NB += a.graphs[g]->buses.size();
+      vb += a.graphs[g]->voices.size();
+    }
   }
+  bool hierarchy = S0 != S;
+  for (int g = 0; g < a.n_graphs; g++)
+    for (auto& b : a.graphs[g]->buses) hierarchy = hierarchy || b.target != -1;
+  if (a.sharded && ctx->n_ranks > 1 && hierarchy)
+    return fail(GAC_ERR_UNSUPPORTED, "sharded renders need a flat graph: voices -> buses -> destination (the buses are what is reduced)");
+  const bool is_root = !a.sharded || ctx->n_ranks <= 1 || ctx->rank == a.root;
   float* d_bus = nullptr;
   std::vector<Sig> buses(NB);
+  std::vector<char> bus_done(NB, 0);
   if (NB) {
     if ((rc = scratch.alloc(&d_bus, NB * 2 * (size_t)env.Npad))) return rc;
-    std::vector<MixJob> mjobs;
-    std::vector<MixInput> minputs;
-    size_t vbase = 0;
-    for (int g = 0; g < a.n_graphs; g++) {
-      const gac_graph* gr = a.graphs[g];
-      for (size_t b = 0; b < gr->buses.size(); b++) {
+    for (int g = 0; g < a.n_graphs; g++)
+      for (size_t b = 0; b < a.graphs[g]->buses.size(); b++) {
         Sig& bs = buses[bus_base[g] + b];
         bs.p[0] = d_bus + ((bus_base[g] + b) * 2 + 0) * (size_t)env.Npad;
         bs.p[1] = d_bus + ((bus_base[g] + b) * 2 + 1) * (size_t)env.Npad;
-        bs.ops = &gr->buses[b].ops;
+        bs.ops = &a.graphs[g]->buses[b].ops;
+      }
+  }
+  for (size_t round = 0;; round++) {
+    // buses whose inputs are all available
+    std::vector<size_t> ready;
+    for (int g = 0; g < a.n_graphs; g++) {
+      const gac_graph* gr = a.graphs[g];
+      for (size_t b = 0; b < gr->buses.size(); b++) {
+        if (bus_done[bus_base[g] + b]) continue;
+        bool ok = true;
+        for (int x : gr->buses[b].inputs) ok = ok && (x >= 0 ? bus_done[bus_base[g] + (size_t)x] : voice_done[voice_base[g] + (size_t)(~x)]);
+        if (ok) ready.push_back(bus_base[g] + b);
+      }
+    }
+    std::vector<size_t> fed;  // chains fed by a finished bus
+    if (ready.empty()) {
+      for (size_t i = 0; i < S; i++) {
+        if (voice_done[i] || voices[i]->input_bus < 0) continue;
+        if (bus_done[bus_base[voice_graph[i]] + (size_t)voices[i]->input_bus]) fed.push_back(i);
+      }
+      if (fed.empty()) break;
+    }
+    std::vector<MixJob> mjobs;
+    std::vector<MixInput> minputs;
+    if (!ready.empty()) {
+      for (size_t gb : ready) {
+        int g = 0;
+        while (g + 1 < a.n_graphs && bus_base[g + 1] <= gb) g++;
+        const gac_graph* gr = a.graphs[g];
+        const BusH& bh = gr->buses[gb - bus_base[g]];
+        Sig& bs = buses[gb];
         MixJob mj;
         mj.dst[0] = bs.p[0];
         mj.dst[1] = bs.p[1];
         mj.first_input = (int)minputs.size();
         int64_t lo = std::numeric_limits<int64_t>::max(), hi = 0;
-        for (size_t v = 0; v < gr->voices.size(); v++) {
-          if (gr->voices[v].bus != (int)b) continue;
-          const Sig& vs = sigs[vbase + v];
+        for (int x : bh.inputs) {
+          const Sig& vs = x >= 0 ? buses[bus_base[g] + (size_t)x] : sigs[voice_base[g] + (size_t)(~x)];
           if (vs.hi <= vs.lo) continue;  // silent throughout: never mixed (:127)
           MixInput in;
           in.src[0] = vs.p[0];
@@ -443,27 +491,68 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         bs.hi = mj.n_inputs ? hi : 0;
         mjobs.push_back(mj);
       }
-      vbase += gr->voices.size();
-    }
-    if ((rc = mix_into(env, mjobs, minputs))) return rc;
-
-    if (a.sharded && ctx->n_ranks > 1) {
-      // the one exchange step: per-rank partial bus sums -> root, float32 sum over NVLink/NVSwitch
-      NcclApi* api = nccl_api();
-      if (!api) return fail(GAC_ERR_NCCL, "libnccl.so.2 could not be loaded");
-      int t = timer.begin(C_MIX);
-      int r = api->Reduce(d_bus, d_bus, NB * 2 * (size_t)env.Npad, /*ncclFloat32*/ 7, /*ncclSum*/ 0, a.root, ctx->comm, ctx->stream);
-      timer.end(t);
-      if (r != 0) return nccl_fail(api, r, "ncclReduce");
-      for (auto& bs : buses) {  // other ranks' voices may be audible anywhere
-        bs.lo = 0;
-        bs.hi = env.Npad;
+      if ((rc = mix_into(env, mjobs, minputs))) return rc;
+      if (a.sharded && ctx->n_ranks > 1) {
+        // the one exchange step: per-rank partial bus sums -> root, float32 sum over NVLink/NVSwitch (flat graphs: every bus is
+        // ready in the first round, so the whole bus block is reduced at once)
+        NcclApi* api = nccl_api();
+        if (!api) return fail(GAC_ERR_NCCL, "libnccl.so.2 could not be loaded");
+        int t = timer.begin(C_MIX);
+        int r = api->Reduce(d_bus, d_bus, NB * 2 * (size_t)env.Npad, /*ncclFloat32*/ 7, /*ncclSum*/ 0, a.root, ctx->comm, ctx->stream);
+        timer.end(t);
+        if (r != 0) return nccl_fail(api, r, "ncclReduce");
+        for (auto& bs : buses) {  // other ranks' voices may be audible anywhere
+          bs.lo = 0;
+          bs.hi = env.Npad;
+        }
       }
+      if (is_root) {
+        std::vector<Sig> sub;
+        for (size_t gb : ready) sub.push_back(buses[gb]);
+        if ((rc = run_chains(env, sub))) return rc;
+        for (size_t k = 0; k < ready.size(); k++) buses[ready[k]] = sub[k];
+      }
+      for (size_t gb : ready) bus_done[gb] = 1;
+      continue;
+    }
+    // chains fed by bus outputs: the chain works on its own copy of the bus signal ((0 + x) == x, silent quanta stay silent)
+    std::vector<Sig> sub;
+    for (size_t i : fed) {
+      const Sig& src = buses[bus_base[voice_graph[i]] + (size_t)voices[i]->input_bus];
+      Sig& s = sigs[i];
+      MixJob mj;
+      mj.dst[0] = s.p[0];
+      mj.dst[1] = s.p[1];
+      mj.first_input = (int)minputs.size();
+      if (src.hi > src.lo) {
+        MixInput in;
+        in.src[0] = src.p[0];
+        in.src[1] = src.p[1];
+        in.lo = src.lo;
+        in.hi = src.hi;
+        minputs.push_back(in);
+      }
+      mj.n_inputs = (int)minputs.size() - mj.first_input;
+      mjobs.push_back(mj);
+      s.lo = src.lo;
+      s.hi = src.hi;
+      s.ch = src.ch;
+      sub.push_back(s);
+    }
+    if (is_root) {
+      if ((rc = mix_into(env, mjobs, minputs))) return rc;
+      if ((rc = run_chains(env, sub))) return rc;
+    }
+    for (size_t k = 0; k < fed.size(); k++) {
+      sigs[fed[k]] = sub[k];
+      voice_done[fed[k]] = 1;
     }
   }
-  const bool is_root = !a.sharded || ctx->n_ranks <= 1 || ctx->rank == a.root;
+  for (size_t i = 0; i < S; i++)
+    if (!voice_done[i]) return fail(GAC_ERR_INVALID_ARGUMENT, "the graph has a cycle or a chain fed by a bus that never completes");
+  for (size_t b = 0; b < NB; b++)
+    if (!bus_done[b]) return fail(GAC_ERR_INVALID_ARGUMENT, "the graph has a cycle through bus %zu", b);
   if (is_root) {
-    if ((rc = run_chains(env, buses))) return rc;
     // ---- destination: fan-in of buses and direct voices in connection order; alias when there is exactly one input
     std::vector<const float*> dest0(a.n_graphs), dest1(a.n_graphs);
     float* d_dest = nullptr;

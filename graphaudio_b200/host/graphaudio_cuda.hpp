@@ -352,7 +352,7 @@ class OfflineAudioContext {
       f.ops.emplace_back();
       for (auto* n : chain) f.ops.back().push_back(OpDesc(n));
       busOps.push_back(f.ops.size() - 1);
-      f.buses.push_back(gac_bus_desc{(int32_t)chain.size(), nullptr});
+      f.buses.push_back(gac_bus_desc{(int32_t)chain.size(), nullptr, 0, 0, nullptr});
       f.dest.push_back(bus);
       for (AudioNode* up : node->in_) {
         AudioBufferSourceNode* s = nullptr;

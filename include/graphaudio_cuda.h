@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GAC_ABI_VERSION 2
+#define GAC_ABI_VERSION 3
 
 /* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */
 typedef enum gac_status {
@@ -165,14 +165,28 @@ typedef struct gac_voice_desc {
   int32_t n_ops;
   const gac_op_desc* ops;
   int32_t bus;              /* index into buses, or -1: connected straight to the destination   */
+  int32_t input;            /* 0: the chain is fed by `source` (an AudioBufferSourceNode).
+                               k > 0: the chain is fed by the OUTPUT of bus k-1 (fan-out of a mixed or
+                               processed signal, e.g. the dry / wet branches of GraphAudio.Kit's
+                               ReverbEffect, Effects/ReverbEffect.cs:63-91); `source` and the Start/Stop
+                               fields are then ignored                                           */
 } gac_voice_desc;
 
 /* A bus = fan-in AudioNodeInput (AudioNodeInput.cs:100-138) followed by a chain of ops
- * (typically one GainNode), connected to the destination.  Voices are summed in ascending voice
- * index = connection order, float32, skipping silent-flagged blocks (:121-132). */
+ * (typically one GainNode), connected to the destination, to another bus, or read by further chains.
+ * Inputs are summed in connection order, float32, skipping silent-flagged blocks (:121-132).
+ * Voices, buses and chains fed by buses together express any acyclic graph of the supported nodes:
+ * a node with several inputs is a bus, a node whose output feeds several nodes ends a bus (or is a
+ * source, which may feed several voices). */
 typedef struct gac_bus_desc {
   int32_t n_ops;
   const gac_op_desc* ops;
+  int32_t target;        /* where the bus output is connected: 0 = the destination, k > 0 = an input of bus
+                            k-1 (bus hierarchies, GraphAudio.Kit/AudioBus.cs:76-114), -1 = nowhere directly
+                            (it is only consumed by chains with input = this bus + 1)                      */
+  int32_t n_inputs;      /* connection order at the bus fan-in (AudioNodeInput.cs:118-137): entries >= 0  */
+  const int32_t* inputs; /* are bus indices, entries < 0 are ~voice_index.  NULL = the voices routed here
+                            in index order, then the buses targeting this one in index order              */
 } gac_bus_desc;
 
 typedef struct gac_graph_desc {

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_version_and_struct_layouts():
-    assert N.lib().gac_version() == 2
+    assert N.lib().gac_version() == 3
     # gac_event must be bit-compatible with AutomationEvent (AudioParam.cs:360-367): int, float, float, (pad), double, double
     assert C.sizeof(N.gac_event) == 32
     assert N.gac_event.time.offset == 16 and N.gac_event.time_constant.offset == 24
@@ -105,19 +105,43 @@ def test_topology_flattening_matches_connection_order():
         ctx.Render(128)       # record-only context: no CPU render path exists
 
 
-def test_unsupported_shapes_are_rejected_loudly():
+def test_fan_out_and_bus_hierarchies_flatten_to_buses_and_bus_fed_chains():
+    """ReverbEffect-style dry / wet split (GraphAudio.Kit/Effects/ReverbEffect.cs:63-91) behind a two-source input, into a
+    master bus: the fan-in nodes become buses, the node whose output fans out ends a bus, each branch is a chain fed by it."""
     ctx = G.OfflineAudioContext(48000, _record_only=True)
     buf = G.PlayableAudioBuffer.FromMonoArray(np.zeros(256, np.float32), 48000)
-    s = G.AudioBufferSourceNode(ctx)
+    s1, s2 = G.AudioBufferSourceNode(ctx), G.AudioBufferSourceNode(ctx)
+    s1.Buffer = s2.Buffer = buf
+    inp, dry, conv, wet, out, master = (G.GainNode(ctx), G.GainNode(ctx), G.ConvolverNode(ctx), G.GainNode(ctx), G.GainNode(ctx),
+                                        G.GainNode(ctx))
+    s1.Connect(inp)
+    s2.Connect(inp)
+    inp.Connect(dry).Connect(out)
+    inp.Connect(conv).Connect(wet).Connect(out)
+    out.Connect(master).Connect(ctx.Destination)
+    voices, buses, dest, targets, inputs = ctx._topology_full()
+    assert [(v[0], v[1], v[2], v[3]) for v in voices] == [(s1, [], 0, -1), (s2, [], 0, -1), (None, [dry], 1, 0), (None, [conv, wet], 1, 0)]
+    assert buses == [[inp], [out, master]]
+    assert targets == [-1, 0] and inputs == [[~0, ~1], [~2, ~3]] and dest == [1]
+    # a source feeding two chains: two voices share the source; a voice chain that fans out is materialised as a bus
+    ctx2 = G.OfflineAudioContext(48000, _record_only=True)
+    s = G.AudioBufferSourceNode(ctx2)
     s.Buffer = buf
-    a, b, bus = G.GainNode(ctx), G.GainNode(ctx), G.GainNode(ctx)
-    s.Connect(a).Connect(bus)
-    s.Connect(b).Connect(bus)  # fan-out: a source feeding two chains (ReverbEffect-style dry/wet split)
-    bus.Connect(ctx.Destination)
-    with pytest.raises(G.NotSupportedException):
-        ctx._topology()
+    a, b, pre, bus = G.GainNode(ctx2), G.GainNode(ctx2), G.BiQuadFilterNode(ctx2), G.GainNode(ctx2)
+    s.Connect(pre)
+    pre.Connect(a).Connect(bus)
+    pre.Connect(b).Connect(bus)
+    bus.Connect(ctx2.Destination)
+    voices, buses, dest, targets, inputs = ctx2._topology_full()
+    assert voices[0][0] is s and voices[0][1] == [pre] and voices[0][3] == -1       # source -> pre, materialised in a bus
+    mat = voices[0][2]
+    assert buses[mat] == [] and inputs[mat] == [~0] and targets[mat] == -1
+    assert sorted(v[1][0] is a for v in voices[1:]) == [False, True] and all(v[3] == mat for v in voices[1:])
+
+
+def test_unsupported_shapes_are_rejected_loudly():
     with pytest.raises(G.InvalidOperationException):  # ConvolverNode.cs:48-49
-        G.ConvolverNode(ctx).Buffer = G.PlayableAudioBuffer.FromMonoArray(np.ones(8, np.float32), 44100)
+        G.ConvolverNode(G.OfflineAudioContext(48000, _record_only=True)).Buffer = G.PlayableAudioBuffer.FromMonoArray(np.ones(8, np.float32), 44100)
     with pytest.raises(G.ArgumentException):
         G.PlayableAudioBuffer.FromChannelArrays([np.zeros(4), np.zeros(5)], 48000)  # PlayableAudioBuffer.cs:130-134
 

@@ -185,3 +185,21 @@ def test_chunked_render_equals_single_render_second_level_fft():
     assert np.abs(np.concatenate([p1, p2], axis=1) - whole).max() <= 2e-6
     a.Dispose()
     b.Dispose()
+
+
+@pytest.mark.parametrize("partition", [128, 512])
+def test_long_ir_at_96k_through_the_render_path(partition):
+    """3 s impulse response at 96 kHz: 2250 partitions of 128 frames -> the M = 8192 radix-8 second-level plan;
+    563 partitions of 512 frames -> M = 2048 with the B = 512 first-level kernels.  Against the oracle (128-frame partitions)."""
+    G, O = _apis()
+    fs = 96000
+    src = [synth.splitmix_uniform(900 + c, fs // 2) for c in range(2)]
+    ir = [synth.decay_ir(910 + c, 3 * fs) for c in range(2)]
+    g = synth.build_c1(G, fs, src, ir, partition=partition)
+    o = synth.build_c1(O, fs, src, ir)
+    n = fs // 2 + 3 * fs
+    yg, yo = g.Render(n), o.Render(n)
+    assert g.last_stats["mac_variant_used"] == 3
+    assert np.abs(yo).max() > 1e-2
+    assert np.abs(yg - yo).max() <= TOL
+    g.Dispose()

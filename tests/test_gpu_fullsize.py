@@ -87,3 +87,17 @@ def test_delta_source_reproduces_normalised_ir_at_full_ir_length():
         ref = ir[c] * np.float32(O.normalization_scale(ir[c]))
         assert np.abs(y[c, :IR] - ref).max() <= 2e-7
         assert np.abs(y[c, IR:]).max() <= 1e-7
+
+
+def test_c3_full_length_subset_matches_oracle():
+    """BASELINE configs[2] geometry (biquad lowpass sweep -> gain -> 2 s IR, 12 s) on a 4-voice subset against the oracle:
+    the biquad recursion runs as verified concurrent time segments over the full 576 000 frames."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    voices = _voices(4)
+    g = synth.build_c3(G, FS, voices, 1.0 / 2)
+    yg = g.Render(N)
+    yo = synth.build_c3(O, FS, voices, 1.0 / 2).Render(N)
+    assert np.abs(yo).max() > 0.05
+    assert np.abs(yg - yo).max() <= 1e-5
+    g.Dispose()

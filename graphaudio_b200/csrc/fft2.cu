@@ -35,7 +35,9 @@ int fft2_pick_m(int P, int* Lh_out) {
   if (Lh_out) *Lh_out = Lh;
   for (int M = 512; M <= 8192; M *= 2)
     if (M - Lh >= M / 2) return M;
-  if (8192 - Lh >= 1024) return 8192;
+  // Longer impulse responses still win with short segments: V = 256 valid outputs per 8192-point segment is ~25 kFLOP per output
+  // block and bin against 8 P = 63 kFLOP for the direct sum at P = 7900 (and the direct sum re-reads X P/16 times from L2).
+  if (8192 - Lh >= 256) return 8192;
   return 0;  // impulse response too long for one second-level transform: the caller falls back to the direct MAC
 }
 

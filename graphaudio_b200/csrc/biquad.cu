@@ -9,13 +9,12 @@
 //   k_biquad_entry    one thread per voice   which coefficient set the reference's fields hold when a quantum starts
 //   k_biquad_resolve  parallel over frames   RBJ (glibc-exact sinf/cosf, :149-258) of the frame in force; writes (b0, b1, b2) per
 //                                            (channel, frame) and the slab-transposed stream (x, a1, a2) the lanes read
-//   k_biquad_lanes    one lane per (voice, channel): ONLY w = x - a1*w1 - a2*w2 (:137) is sequential; one TMA bulk copy per
-//                     32-frame slab of 32 lanes (16 KB), mbarrier ring, one bulk store of the w tile (biquad_lanes.cu)
-//   k_biquad_output   parallel over frames   y = b0*w + b1*w1 + b2*w2 (:138) from the stored w sequence (same ops, same order)
+//   k_biquad_lanes    one lane per (voice, channel): w = x - a1*w1 - a2*w2 (:137) is the sequential chain, y = b0*w + b1*w1 +
+//                     b2*w2 (:138) rides along off the critical path; TMA-fed, concurrent verified time segments (biquad_lanes.cu)
 //
 // Slab-transposed layout (shared by resolve, lanes and output): rows are grouped 32 at a time (16 voices x 2 channels = one
 // warp of lanes), time is cut into slabs of 32 frames, and inside a slab the FRAME index is major and the row index minor:
-//     S1T[group][slab][frame 0..31][row 0..31]  float4 (x, a1, a2, -)         WT[group][slab][frame][row]  float
+//     S1T[group][slab][frame 0..31][row 0..31]  float4 (x, a1, a2, -)         S2T[group][slab][frame][row]  float4 (b0, b1, b2, -)
 // so that a slab is one contiguous 16 KB (4 KB) block for TMA and lane r's LDS.128 / STS.32 at frame i are conflict-free.
 #include "biquad_math.cuh"
 
@@ -127,95 +126,85 @@ __global__ void __launch_bounds__(32) k_biquad_entry(int n_jobs, int64_t n_quant
 // K3c: coefficients in force at every (channel, frame): RBJ of the frame the walk selected, with the k-rate gain of that
 // frame's block.  CTA = one slab of one 32-row group, 16 warps: warp = voice, lane = frame, and the thread serves BOTH
 // channels: they almost always selected the same frame, so one RBJ evaluation (glibc-exact sinf/cosf, five divisions) feeds
-// both rows.  Reads run along time (coalesced); the (x, a1, a2) tile is transposed through shared memory and written as
-// one contiguous 16 KB block.
+// both rows; and lanes that selected the SAME frame (constant parameters: one recompute per quantum) elect one of them to
+// evaluate it (__match_any_sync) and take its result by shuffle.  Reads run along time (coalesced); the (x, a1, a2) and
+// (b0, b1, b2) tiles are transposed through shared memory and written as contiguous 16 KB blocks; frames outside the
+// voice's non-silent range are cleared here (:103-108) because the recursion kernel only writes inside it.
+__device__ __forceinline__ Coef rbj_shared(const BiquadJob& job, int32_t k, float nyq, int sample_rate) {
+  // one evaluation per distinct k in the warp
+  const unsigned peers = __match_any_sync(0xffffffffu, k);
+  const int leader = __ffs(peers) - 1;
+  Coef c;
+  c.b0 = c.b1 = c.b2 = c.a1 = c.a2 = 0.f;  // k < 0 is unreachable for active frames: the first one always recomputes (dirty)
+  if ((int)(threadIdx.x & 31) == leader && k >= 0)
+    c = rbj(job.type, clamped_freq(job, k, nyq), clamped_q(job, k), job.gain ? job.gain[k >> 7] : job.gain_const, sample_rate);
+  c.b0 = __shfl_sync(0xffffffffu, c.b0, leader);
+  c.b1 = __shfl_sync(0xffffffffu, c.b1, leader);
+  c.b2 = __shfl_sync(0xffffffffu, c.b2, leader);
+  c.a1 = __shfl_sync(0xffffffffu, c.a1, leader);
+  c.a2 = __shfl_sync(0xffffffffu, c.a2, leader);
+  return c;
+}
+
 __global__ void __launch_bounds__(512) k_biquad_resolve(const BiquadJob* __restrict__ jobs, int n_jobs, int sample_rate, int64_t n_quanta,
-                                                        int64_t n_frames, const int32_t* __restrict__ ent_base, float4* __restrict__ s1t) {
+                                                        int64_t n_frames, const int32_t* __restrict__ ent_base, float4* __restrict__ s1t,
+                                                        float4* __restrict__ s2t) {
   __shared__ float4 tile[32][33];
+  __shared__ float4 tile2[32][33];
   const int jv = threadIdx.x >> 5, i = threadIdx.x & 31;
   const int64_t slab = blockIdx.x;
   const int g = blockIdx.y;
   const int jid = g * 16 + jv;
   const int64_t n = slab * 32 + i;
-  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-  if (jid < n_jobs) {
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, u0 = v0, u1 = v0;
+  if (jid < n_jobs) {  // (warp-uniform, like the range test below: ranges are multiples of 128 frames, a warp covers 32)
     const BiquadJob& job = jobs[jid];
     if (n >= job.lo && n < job.hi) {
       int32_t k0 = job.idx[n], k1 = job.idx[n_frames + n];
       if (k0 < 0) k0 = ent_base[((size_t)jid * 2 + 0) * n_quanta + (n >> 7)];
       if (k1 < 0) k1 = ent_base[((size_t)jid * 2 + 1) * n_quanta + (n >> 7)];
       const float nyq = (float)sample_rate / 2.f;
-      Coef c0, c1;
-      c0.b0 = c0.b1 = c0.b2 = c0.a1 = c0.a2 = 0.f;  // k < 0 is unreachable for active frames: the first one always recomputes (dirty)
-      if (k0 >= 0) c0 = rbj(job.type, clamped_freq(job, k0, nyq), clamped_q(job, k0), job.gain ? job.gain[k0 >> 7] : job.gain_const, sample_rate);
-      c1 = c0;
-      if (k1 != k0) {
-        c1.b0 = c1.b1 = c1.b2 = c1.a1 = c1.a2 = 0.f;
-        if (k1 >= 0) c1 = rbj(job.type, clamped_freq(job, k1, nyq), clamped_q(job, k1), job.gain ? job.gain[k1 >> 7] : job.gain_const, sample_rate);
+      const Coef c0 = rbj_shared(job, k0, nyq, sample_rate);
+      Coef c1 = c0;
+      if (__any_sync(0xffffffffu, k1 != k0)) {
+        const Coef alt = rbj_shared(job, k1, nyq, sample_rate);
+        if (k1 != k0) c1 = alt;
       }
       v0 = make_float4(job.sig[0][n], c0.a1, c0.a2, 0.f);
       v1 = make_float4(job.sig[1][n], c1.a1, c1.a2, 0.f);
-      job.s2[n] = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
-      job.s2[n_frames + n] = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
+      u0 = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
+      u1 = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
+    } else if (n < n_frames) {
+      job.sig[0][n] = 0.f;
+      job.sig[1][n] = 0.f;
     }
   }
   tile[i][2 * jv] = v0;
   tile[i][2 * jv + 1] = v1;
+  tile2[i][2 * jv] = u0;
+  tile2[i][2 * jv + 1] = u1;
   __syncthreads();
-  // tile[frame][row] -> S1T[g][slab][frame][row]: element e = frame * 32 + row
+  // tile[frame][row] -> S1T / S2T [g][slab][frame][row]: element e = frame * 32 + row
   const size_t n_slabs = (size_t)(n_frames / 32);
   float4* dst = s1t + ((size_t)g * n_slabs + slab) * 1024;
+  float4* dst2 = s2t + ((size_t)g * n_slabs + slab) * 1024;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const int e = threadIdx.x + 512 * h;
     dst[e] = tile[e >> 5][e & 31];
+    dst2[e] = tile2[e >> 5][e & 31];
   }
-}
-
-// K3e: y = b0*w + b1*w1 + b2*w2 (:138) from the stored w sequence; frames outside the non-silent range are cleared (:103-108).
-// CTA = one slab of one 32-row group; the w tile (plus the last two frames of the previous slab) is transposed back through
-// shared memory so that both the WT reads and the sig writes are coalesced.
-__global__ void __launch_bounds__(1024) k_biquad_output(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
-                                                        const float* __restrict__ wt) {
-  __shared__ float tile[34][33];  // rows 0,1 = frames 30,31 of the previous slab; rows 2..33 = this slab
-  const int r = threadIdx.x >> 5, i = threadIdx.x & 31;
-  const int64_t slab = blockIdx.x;
-  const int g = blockIdx.y;
-  const size_t n_slabs = (size_t)(n_frames / 32);
-  const float* cur = wt + ((size_t)g * n_slabs + slab) * 1024;
-  tile[2 + (threadIdx.x >> 5)][threadIdx.x & 31] = cur[threadIdx.x];
-  if (threadIdx.x < 64) {
-    float p = 0.f;
-    if (slab > 0) p = (cur - 1024)[30 * 32 + threadIdx.x];
-    tile[threadIdx.x >> 5][threadIdx.x & 31] = p;
-  }
-  __syncthreads();
-  const int jid = g * 16 + (r >> 1);
-  if (jid >= n_jobs) return;
-  const int c = r & 1;
-  const BiquadJob& job = jobs[jid];
-  const int64_t n = slab * 32 + i;
-  float y = 0.f;
-  if (n >= job.lo && n < job.hi) {
-    const float w0 = tile[2 + i][r];
-    const float w1 = n - 1 >= job.lo ? tile[1 + i][r] : 0.f;
-    const float w2 = n - 2 >= job.lo ? tile[i][r] : 0.f;
-    const float4 b = job.s2[(int64_t)c * n_frames + n];
-    y = b.x * w0 + b.y * w1 + b.z * w2;
-  }
-  job.sig[c][n] = y;
 }
 
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad, cudaStream_t s) {
+                   int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_first_bad, cudaStream_t s) {
   if (n_jobs <= 0 || n_frames <= 0) return;
   const int groups = (n_jobs + 15) / 16;
   const unsigned n_slabs = (unsigned)(n_frames / 32);
   k_biquad_select<<<dim3((unsigned)((n_quanta + kSelQ - 1) / kSelQ), (unsigned)n_jobs), kSelQ, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last);
   k_biquad_entry<<<(unsigned)n_jobs, 32, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
-  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t);
-  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_wt, d_states, d_first_bad, s);
-  k_biquad_output<<<dim3(n_slabs, (unsigned)groups), 1024, 0, s>>>(d_jobs, n_jobs, n_frames, d_wt);
+  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t);
+  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_first_bad, s);
 }
 
 }  // namespace gac

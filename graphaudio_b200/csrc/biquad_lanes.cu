@@ -13,10 +13,11 @@
 //   * if a link does not match (very low cutoff / very high Q never merge), the repair launch recomputes that 32-row group
 //     sequentially from the last verified state: the result is always exact, only the speed-up is lost for that group.
 //
-// The recursion is latency-bound (three dependent FP32 ops per frame), so everything else is kept out of the warp's
-// instruction stream: 128 frames of the whole group are ONE contiguous 64 KB block that lane 0 fetches with a single
-// TMA bulk copy (cp.async.bulk + mbarrier, 3-stage ring); lane r reads (x, a1, a2) of frame i at [i][r] — consecutive lanes,
-// consecutive 16 bytes, conflict-free — and the 16 KB tile of w leaves with one bulk store.
+// The recursion is latency-bound (three dependent FP32 ops per frame), so everything else is kept out of the dependent
+// chain: 64 frames of the whole group are two contiguous 32 KB blocks — (x, a1, a2) and (b0, b1, b2) — that lane 0 fetches with
+// TMA bulk copies (cp.async.bulk + mbarrier, 3-stage ring); lane r reads frame i at [i][r] — consecutive lanes, consecutive
+// 16 bytes, conflict-free — and y = b0*w + b1*w[n-1] + b2*w[n-2] (:138) is formed from the chain's results while the next
+// loads are in flight; each lane stores its row's 32 results as one 128-byte line.
 #include "gac_kernels.h"
 
 namespace gac {
@@ -49,27 +50,27 @@ __device__ __forceinline__ void bq_bulk_s2g(void* dst, uint32_t src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
-constexpr int kSlab = 128;   // frames per pipeline stage = 4 consecutive 32-frame layout slabs (contiguous in HBM)
+constexpr int kSlab = 64;    // frames per pipeline stage = 2 consecutive 32-frame layout slabs (contiguous in HBM)
 constexpr int kStages = 3;   // stages in flight
-constexpr int kWarmSlabs = 64;  // warm-up of a speculative segment: 64 * 128 = 8192 frames
-constexpr int kStageBytes = kSlab * 32 * 16;  // 64 KB
-constexpr int kWtBytes = kSlab * 32 * 4;      // 16 KB
-constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 2 * kWtBytes + 64;
+constexpr int kWarmSlabs = 128;  // warm-up of a speculative segment: 128 * 64 = 8192 frames
+constexpr int kTileBytes = kSlab * 32 * 16;   // one stream's stage: 32 KB
+constexpr int kStageBytes = 2 * kTileBytes;   // (x, a1, a2) tile + (b0, b1, b2) tile
+constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64;
 
 // states: float2 [groups][n_seg][2 (start, end)][32 rows];  first_bad: int [groups] (n_seg = all links verified)
 // REPAIR = false: grid (groups, n_seg), segment blockIdx.y runs speculatively.  REPAIR = true: grid (groups), the group
 // re-runs sequentially from segment first_bad[g] (does nothing if every link matched).
 template <bool REPAIR>
 __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
-                                                     const float4* __restrict__ s1t, float* __restrict__ wt_all, int seg_slabs, int n_seg,
+                                                     const float4* __restrict__ s1t, const float4* __restrict__ s2t, int seg_slabs, int n_seg,
                                                      float2* __restrict__ states, const int* __restrict__ first_bad) {
   extern __shared__ __align__(128) unsigned char lanes_smem[];
-  float* wt = reinterpret_cast<float*>(lanes_smem + kStages * kStageBytes);                    // [2][32 frames][32 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lanes_smem + kStages * kStageBytes + 2 * kWtBytes);  // [kStages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lanes_smem + kStages * kStageBytes);  // [kStages]
   const int lane = threadIdx.x;
   const int j = blockIdx.x * 16 + (lane >> 1);
   const bool valid = j < n_jobs;
   const int64_t my_lo = valid ? jobs[j].lo : 0, my_hi = valid ? jobs[j].hi : 0;
+  float* __restrict__ my_sig = valid ? jobs[j].sig[lane & 1] : nullptr;
   int64_t lo = my_hi > my_lo ? my_lo : INT64_MAX, hi = my_hi > my_lo ? my_hi : 0;
   for (int o = 16; o > 0; o >>= 1) {
     int64_t lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     hi = hi2 > hi ? hi2 : hi;
   }
   if (hi <= lo) return;
-  const int total_slabs = (int)((hi - lo) / kSlab);    // ranges are multiples of 128 frames
-  // this CTA's slabs (relative to lo): [s_first, s_end), of which [s_first, s_own) is warm-up (computed, not stored)
+  const int total_slabs = (int)((hi - lo + kSlab - 1) / kSlab);  // ranges are multiples of 128 frames
+  // this CTA's slabs (relative to lo): [s_first, s_end), of which [s_first, s_own) is warm-up (recursion only, nothing written)
   int seg = REPAIR ? first_bad[blockIdx.x] : (int)blockIdx.y;
   if (seg >= n_seg) return;
   const int s_own = seg * seg_slabs;
@@ -86,13 +87,14 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
   const int s_end = REPAIR ? total_slabs : (s_own + seg_slabs < total_slabs ? s_own + seg_slabs : total_slabs);
   const int s_first = (REPAIR || seg == 0) ? s_own : (s_own - kWarmSlabs > 0 ? s_own - kWarmSlabs : 0);
   const int n_slabs = s_end - s_first;
+  const int n_warm = s_own - s_first;
   float2* st_group = states + (size_t)blockIdx.x * n_seg * 64;
   // element (frame n, row r) of group g lives at (g * n_frames + n) * 32 + r in both streams
-  const float4* __restrict__ src = s1t + ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo + (size_t)s_first * kSlab) * 32;
-  float* __restrict__ dst = wt_all + ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo + (size_t)s_first * kSlab) * 32;
+  const size_t base_elem = ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo + (size_t)s_first * kSlab) * 32;
+  const float4* __restrict__ src1 = s1t + base_elem;
+  const float4* __restrict__ src2 = s2t + base_elem;
   const uint32_t bar0 = bq_smem_u32(bars);
   const uint32_t stage0 = bq_smem_u32(lanes_smem);
-  const uint32_t wt0 = bq_smem_u32(wt);
 
   if (lane == 0) {
     for (int s = 0; s < kStages; s++) bq_mbar_init(bar0 + 8 * s, 1);
@@ -103,8 +105,10 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
   auto issue = [&](int s) {
     if (s < n_slabs && lane == 0) {
       const int st = s % kStages;
-      bq_mbar_expect_tx(bar0 + 8 * st, kStageBytes);
-      bq_bulk_g2s(stage0 + st * kStageBytes, src + (size_t)s * (kSlab * 32), kStageBytes, bar0 + 8 * st);
+      const bool own = s >= n_warm;  // the output coefficients are not needed while warming up
+      bq_mbar_expect_tx(bar0 + 8 * st, own ? kStageBytes : kTileBytes);
+      bq_bulk_g2s(stage0 + st * kStageBytes, src1 + (size_t)s * (kSlab * 32), kTileBytes, bar0 + 8 * st);
+      if (own) bq_bulk_g2s(stage0 + st * kStageBytes + kTileBytes, src2 + (size_t)s * (kSlab * 32), kTileBytes, bar0 + 8 * st);
     }
   };
 
@@ -115,7 +119,6 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     w1 = e.x;
     w2 = e.y;
   }
-  const int n_warm = s_own - s_first;
   uint32_t phases = 0u;  // bit st = parity to wait for on stage st
   for (int s = 0; s < n_slabs; s++) {
     if (s == n_warm && !REPAIR) st_group[((size_t)seg * 2 + 0) * 32 + lane] = make_float2(w1, w2);  // state at the segment's first own frame
@@ -126,48 +129,49 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     phases ^= 1u << st;
     const int64_t base = lo + (int64_t)(s_first + s) * kSlab;
     const bool act = base >= my_lo && base < my_hi;  // silent-flagged quanta: state untouched (:103-108)
-    // the w tile written two iterations ago must have been read out by its bulk store before it is overwritten
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncwarp();
-    const float4* __restrict__ rows = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes) + lane;  // [i][lane]
-    float* __restrict__ wrow = wt + (s & 1) * (kSlab * 32) + lane;
+    const bool own = s >= n_warm;
+    const float4* __restrict__ rows = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes) + lane;           // [i][lane]: (x, a1, a2, -)
+    const float4* __restrict__ outs = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes + kTileBytes) + lane;  // (b0, b1, b2, -)
     if (act) {
-      // 32 frames at a time: all loads first, then the dependent chain from registers, then all stores, so that the
-      // 30-cycle LDS latency is paid once per 32 frames (the warp is alone on its SM sub-partition; nothing else hides it)
+      // 32 frames at a time: all loads first, then the dependent chain from registers, so that the 30-cycle LDS latency is paid
+      // once per 32 frames (the warp is alone on its SM sub-partition; nothing else hides it); then y, off the critical path
 #pragma unroll 1
       for (int q = 0; q < kSlab / 32; q++) {
-        float x[32], p1[32], p2[32], wo[32];
+        float x[32], p1[32], p2[32], wo[34];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          const float4 r = rows[(q * 32 + i) * 32];        // (x, a1, a2, -)
+          const float4 r = rows[(q * 32 + i) * 32];
           x[i] = r.x;
           p1[i] = r.y;
           p2[i] = r.z;
         }
+        wo[0] = w2;
+        wo[1] = w1;
 #pragma unroll
         for (int i = 0; i < 32; i++) {
           const float w = x[i] - p1[i] * w1 - p2[i] * w2;  // :137
           w2 = w1;
           w1 = w;
-          wo[i] = w;
+          wo[i + 2] = w;
         }
+        if (own) {
+          float* __restrict__ dst = my_sig + base + q * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i++) wrow[(q * 32 + i) * 32] = wo[i];
+          for (int i4 = 0; i4 < 8; i4++) {
+            float y[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int i = 4 * i4 + e;
+              const float4 b = outs[(q * 32 + i) * 32];
+              y[e] = b.x * wo[i + 2] + b.y * wo[i + 1] + b.z * wo[i];  // :138  y = b0*w + b1*w1 + b2*w2
+            }
+            *reinterpret_cast<float4*>(dst + 4 * i4) = make_float4(y[0], y[1], y[2], y[3]);
+          }
+        }
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
-    __syncwarp();
-    if (lane == 0) {
-      if (s >= n_warm) bq_bulk_s2g(dst + (size_t)s * (kSlab * 32), wt0 + (uint32_t)((s & 1) * kWtBytes), kWtBytes);  // warm-up output is discarded
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  if (REPAIR) {
-    // (the chain behind the repaired segment is not needed any more)
-  } else {
-    st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
-  }
+  if (!REPAIR) st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
 }
 
 // first_bad[g] = first segment k >= 1 whose speculative start state differs (bitwise, any of the 32 rows) from the state
@@ -203,8 +207,8 @@ int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs_out) {
   return n_seg;
 }
 
-void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad,
-                         cudaStream_t s) {
+void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,
+                         int* d_first_bad, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_biquad_lanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
@@ -214,10 +218,10 @@ void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, 
   const unsigned groups = (unsigned)((n_jobs + 15) / 16);
   int seg_slabs = 0;
   const int n_seg = biquad_lane_segments(n_jobs, n_frames, &seg_slabs);
-  k_biquad_lanes<false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_wt, seg_slabs, n_seg, d_states, nullptr);
+  k_biquad_lanes<false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr);
   if (n_seg > 1) {
     k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad);
-    k_biquad_lanes<true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_wt, seg_slabs, n_seg, d_states, d_first_bad);
+    k_biquad_lanes<true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad);
   }
 }
 

@@ -1095,7 +1095,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     }
     // ---------------- BiQuadFilterNode (K2 + K3)
     if (!biquads.empty()) {
-      const size_t per_job = (size_t)env.Npad * (2 * (4 + 16 + 16 + 4) + 4 + 4) + (size_t)env.NQ * (16 + 4);
+      const size_t per_job = (size_t)env.Npad * (2 * (4 + 16 + 16) + 4 + 4) + (size_t)env.NQ * (16 + 4);
       const size_t max_jobs = std::min<size_t>(65535, std::max<size_t>(1, ctx->scratch_budget / per_job));
       for (size_t k0 = 0; k0 < biquads.size(); k0 += max_jobs) {
         const size_t nk = std::min(max_jobs, biquads.size() - k0);
@@ -1103,14 +1103,12 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         auto& bj = env.keep->make<BiquadJob>();
         int32_t* idx_all = nullptr;
         float4 *s1_all = nullptr, *s2_all = nullptr;
-        float* w_all = nullptr;
         {
           int rc;
           const size_t rows = ((nk + 15) / 16) * 32;  // slab-transposed streams cover whole 32-row groups
           if ((rc = env.scratch->alloc(&idx_all, nk * 2 * (size_t)env.Npad))) return rc;
           if ((rc = env.scratch->alloc(&s1_all, rows * (size_t)env.Npad))) return rc;
-          if ((rc = env.scratch->alloc(&s2_all, nk * 2 * (size_t)env.Npad))) return rc;
-          if ((rc = env.scratch->alloc(&w_all, rows * (size_t)env.Npad))) return rc;
+          if ((rc = env.scratch->alloc(&s2_all, rows * (size_t)env.Npad))) return rc;
         }
         for (size_t k = 0; k < nk; k++) {
           Sig& s = sigs[biquads[k0 + k]];
@@ -1134,7 +1132,6 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           j.lo = s.lo;
           j.hi = s.hi;
           j.idx = idx_all + k * 2 * (size_t)env.Npad;
-          j.s2 = s2_all + k * 2 * (size_t)env.Npad;
           bj.push_back(j);
         }
         int rc = run_param_jobs(env, pj);
@@ -1150,9 +1147,9 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if ((rc = env.scratch->alloc(&dstates, ((nk + 15) / 16) * (size_t)n_seg * 64))) return rc;
         if ((rc = env.scratch->alloc(&dbad, (nk + 15) / 16))) return rc;
         int t = env.timer->begin(C_BIQUAD);
-        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, w_all, dstates, dbad, ctx->stream);
+        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, s2_all, dstates, dbad, ctx->stream);
         env.timer->end(t);
-        env.launches += n_seg > 1 ? 7 : 5;
+        env.launches += n_seg > 1 ? 6 : 4;
         CU(cudaGetLastError());
       }
     }

@@ -161,21 +161,20 @@ struct BiquadJob {
   int64_t lo, hi;      // active frame range (multiples of 128)
   // scratch, per job (c = channel, n = frame):
   int32_t* idx;        // [2][n_frames] frame whose (f, Q) gave the coefficients in force, -1 = the quantum's entry set
-  float4* s2;          // [2][n_frames] (b0, b1, b2, -)
 };
 // scratch: d_last, d_ent int32 [n_jobs][2][n_quanta]; the slab-transposed batch-wide streams (layout: biquad.cu header)
 //   d_s1t float4 [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  (x, a1, a2, -)
-//   d_wt  float  [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  Direct-Form-II state sequence w
+//   d_s2t float4 [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  (b0, b1, b2, -)
 // n_jobs <= 65535 per call.
 // d_states: float2 [ceil(n_jobs/16)][n_seg][2][32] and d_first_bad: int [ceil(n_jobs/16)], n_seg = biquad_lane_segments(...)
 // (the recursion runs as concurrent, verified time segments: biquad_lanes.cu header)
 int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs);
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad, cudaStream_t s);
+                   int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_first_bad, cudaStream_t s);
 
 // K3d alone (biquad_lanes.cu): the w recursion over the slab-transposed streams, TMA-fed
-void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, float* d_wt, float2* d_states, int* d_first_bad,
-                         cudaStream_t s);
+void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,
+                         int* d_first_bad, cudaStream_t s);
 
 struct MixJob {       // dst[c][n] = (((0 + src0) + src1) + ...) over active ranges, AudioNodeInput.cs:118-137
   float* dst[2];

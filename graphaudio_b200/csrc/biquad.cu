@@ -21,69 +21,115 @@
 namespace gac {
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K3a: the hysteresis walk (:121-134).  CTA = 128 consecutive quanta of one job; thread = one quantum, which walks
-// channel 0 then channel 1.  f / Q / idx travel through shared-memory tiles of [128 quanta][32 frames] so that global
-// traffic is coalesced although every thread walks its own 128 frames.
+// K3a: the hysteresis walk (:121-134).  One WARP per quantum of one job: the lanes load the quantum's 128 clamped (f, Q)
+// pairs (float4 each, coalesced) and decide the two cases that cover practically every quantum without walking it:
+//   * every frame differs from its predecessor beyond the hysteresis (an a-rate sweep): every frame recomputes, provided
+//     frame 0 does (channel 0: against the 1000 Hz / Q 1 the block restarts with, or the dirty flag; channel 1: against
+//     channel 0's last frame);
+//   * every frame equals frame 0 (constant parameters): at most frame 0 of channel 0 recomputes, channel 1 never does.
+// Anything else (drifts slower than the hysteresis) is walked serially by lane 0 from the staged values, exactly as the
+// reference loop does.
 //   idx[c][n]  = frame whose (f, Q) produced the coefficients in force at (channel c, frame n); -1 = the set the quantum
 //                started with (resolved by k_biquad_entry)
 //   last[c][b] = frame of channel c's last recompute in quantum b, or -1
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kSelQ = 64;  // quanta (= threads) per CTA
-__global__ void __launch_bounds__(kSelQ) k_biquad_select(const BiquadJob* __restrict__ jobs, int sample_rate, int64_t n_quanta,
-                                                         int64_t n_frames, int32_t* __restrict__ last_base) {
-  __shared__ float tf[kSelQ][33];
-  __shared__ float tq[kSelQ][33];
-  __shared__ int32_t ti[kSelQ][33];
-  const int jid = blockIdx.y;
-  const BiquadJob job = jobs[jid];
-  const int64_t b0 = (int64_t)blockIdx.x * kSelQ;
-  const int64_t b = b0 + threadIdx.x;
+constexpr int kSelWarps = 8;
+__device__ __forceinline__ bool bq_differs(float f, float q, float uf, float uq) {
+  return fabsf(f - uf) > 0.001f || fabsf(q - uq) > 0.0001f;  // :126 (gain never differs inside a block)
+}
+__global__ void __launch_bounds__(kSelWarps * 32) k_biquad_select(const BiquadJob* __restrict__ jobs, int sample_rate, int64_t n_quanta,
+                                                                  int64_t n_frames, int32_t* __restrict__ last_base) {
+  __shared__ float sf[kSelWarps][128];
+  __shared__ float sq[kSelWarps][128];
+  __shared__ int32_t si[kSelWarps][2][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jid = blockIdx.y;
+  const int64_t b = (int64_t)blockIdx.x * kSelWarps + warp;
+  if (b >= n_quanta) return;
+  const BiquadJob job = jobs[jid];
   int32_t* last = last_base + (size_t)jid * 2 * n_quanta;
   const int64_t n0 = b * 128;
-  const bool active = b < n_quanta && n0 >= job.lo && n0 < job.hi;  // silent-flagged block: state untouched (:103-108)
-  const float nyq = (float)sample_rate / 2.f;
-  float usedF = 1000.f, usedQ = 1.0f;
-  bool dirty = (n0 == job.lo);  // _coefficientsDirty is still set when the first non-silent block arrives
-  for (int c = 0; c < 2; c++) {
-    int32_t cur = -1;
-    for (int ci = 0; ci < 4; ci++) {
-      // cooperative tile load: row r = quantum b0 + r, 32 consecutive frames
-      for (int r = warp; r < kSelQ; r += kSelQ / 32) {
-        const int64_t n = (b0 + r) * 128 + ci * 32 + lane;
-        float f = job.freq_const, q = job.q_const;
-        if (n < n_frames) {
-          if (job.freq) f = job.freq[n];
-          if (job.q) q = job.q[n];
-        }
-        tf[r][lane] = f < 1.f ? 1.f : (f > nyq ? nyq : f);  // Math.Clamp(freq, 1, fs/2)   :123
-        tq[r][lane] = q > 0.001f ? q : 0.001f;              // Math.Max(0.001f, q)         :124
-      }
-      __syncthreads();
-      if (active) {
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-          const float f = tf[threadIdx.x][i], q = tq[threadIdx.x][i];
-          const bool re = dirty || fabsf(f - usedF) > 0.001f || fabsf(q - usedQ) > 0.0001f;  // :126 (gain never differs inside a block)
-          if (re) {
-            usedF = f;
-            usedQ = q;
-            dirty = false;
-            cur = (int32_t)(n0 + ci * 32 + i);
-          }
-          ti[threadIdx.x][i] = cur;
-        }
-      }
-      __syncthreads();
-      for (int r = warp; r < kSelQ; r += kSelQ / 32) {
-        const int64_t qb = b0 + r;
-        const int64_t n = qb * 128 + ci * 32 + lane;
-        if (qb < n_quanta && n >= job.lo && n < job.hi) job.idx[(size_t)c * n_frames + n] = ti[r][lane];
-      }
-      __syncthreads();
-    }
-    if (b < n_quanta) last[(size_t)c * n_quanta + b] = active ? cur : -1;
+  if (!(n0 >= job.lo && n0 < job.hi)) {  // silent-flagged block: state untouched (:103-108)
+    if (lane == 0) last[b] = last[n_quanta + b] = -1;
+    return;
   }
+  const float nyq = (float)sample_rate / 2.f;
+  float f[4], q[4];
+  {
+    float4 f4 = make_float4(job.freq_const, job.freq_const, job.freq_const, job.freq_const);
+    float4 q4 = make_float4(job.q_const, job.q_const, job.q_const, job.q_const);
+    if (job.freq) f4 = *reinterpret_cast<const float4*>(job.freq + n0 + 4 * lane);
+    if (job.q) q4 = *reinterpret_cast<const float4*>(job.q + n0 + 4 * lane);
+    const float fe[4] = {f4.x, f4.y, f4.z, f4.w}, qe[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      f[e] = fe[e] < 1.f ? 1.f : (fe[e] > nyq ? nyq : fe[e]);  // Math.Clamp(freq, 1, fs/2)   :123
+      q[e] = qe[e] > 0.001f ? qe[e] : 0.001f;                   // Math.Max(0.001f, q)         :124
+    }
+  }
+  // predecessor of this lane's first frame, frame 0 and frame 127 of the quantum
+  const float pf = __shfl_up_sync(0xffffffffu, f[3], 1), pq = __shfl_up_sync(0xffffffffu, q[3], 1);
+  const float f0 = __shfl_sync(0xffffffffu, f[0], 0), q0 = __shfl_sync(0xffffffffu, q[0], 0);
+  const float fl = __shfl_sync(0xffffffffu, f[3], 31), ql = __shfl_sync(0xffffffffu, q[3], 31);
+  bool all_diff = true, all_same = true;
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const float uf = e == 0 ? pf : f[e - 1], uq = e == 0 ? pq : q[e - 1];
+    if (!(lane == 0 && e == 0)) all_diff = all_diff && bq_differs(f[e], q[e], uf, uq);
+    all_same = all_same && f[e] == f0 && q[e] == q0;
+  }
+  all_diff = __all_sync(0xffffffffu, all_diff);
+  all_same = __all_sync(0xffffffffu, all_same);
+  const bool dirty0 = (n0 == job.lo);  // _coefficientsDirty is still set when the first non-silent block arrives
+  const bool r0 = dirty0 || bq_differs(f0, q0, 1000.f, 1.0f);
+  int32_t* idx0 = job.idx + n0 + 4 * lane;
+  int32_t* idx1 = job.idx + n_frames + n0 + 4 * lane;
+  if (all_same) {
+    const int32_t k = r0 ? (int32_t)n0 : -1;
+    *reinterpret_cast<int4*>(idx0) = make_int4(k, k, k, k);
+    *reinterpret_cast<int4*>(idx1) = make_int4(-1, -1, -1, -1);
+    if (lane == 0) {
+      last[b] = k;
+      last[n_quanta + b] = -1;
+    }
+    return;
+  }
+  const bool r1 = bq_differs(f0, q0, fl, ql);  // channel 1 starts from channel 0's end state (:110-115)
+  if (all_diff && r0 && r1) {
+    const int32_t k = (int32_t)(n0 + 4 * lane);
+    *reinterpret_cast<int4*>(idx0) = make_int4(k, k + 1, k + 2, k + 3);
+    *reinterpret_cast<int4*>(idx1) = make_int4(k, k + 1, k + 2, k + 3);
+    if (lane == 0) last[b] = last[n_quanta + b] = (int32_t)(n0 + 127);
+    return;
+  }
+  // general case: the reference's walk, channel 0 then channel 1, by one lane over the staged values
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    sf[warp][4 * lane + e] = f[e];
+    sq[warp][4 * lane + e] = q[e];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    float usedF = 1000.f, usedQ = 1.0f;
+    bool dirty = dirty0;
+    for (int c = 0; c < 2; c++) {
+      int32_t cur = -1;
+      for (int i = 0; i < 128; i++) {
+        const float fi = sf[warp][i], qi = sq[warp][i];
+        if (dirty || bq_differs(fi, qi, usedF, usedQ)) {
+          usedF = fi;
+          usedQ = qi;
+          dirty = false;
+          cur = (int32_t)(n0 + i);
+        }
+        si[warp][c][i] = cur;
+      }
+      last[(size_t)c * n_quanta + b] = cur;
+    }
+  }
+  __syncwarp();
+  *reinterpret_cast<int4*>(idx0) = *reinterpret_cast<const int4*>(&si[warp][0][4 * lane]);
+  *reinterpret_cast<int4*>(idx1) = *reinterpret_cast<const int4*>(&si[warp][1][4 * lane]);
 }
 
 // K3b: which coefficient set the reference's fields (_b0.._a2) hold when channel c of quantum b starts.
@@ -201,7 +247,7 @@ void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_
   if (n_jobs <= 0 || n_frames <= 0) return;
   const int groups = (n_jobs + 15) / 16;
   const unsigned n_slabs = (unsigned)(n_frames / 32);
-  k_biquad_select<<<dim3((unsigned)((n_quanta + kSelQ - 1) / kSelQ), (unsigned)n_jobs), kSelQ, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last);
+  k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_jobs), kSelWarps * 32, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last);
   k_biquad_entry<<<(unsigned)n_jobs, 32, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
   k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t);
   launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_first_bad, s);

@@ -74,6 +74,16 @@ struct BusH {
 
 struct NcclApi;
 
+// CubicResampler phase table of one source geometry: (k, t) per output frame (engine_render.inl, plan_sources)
+struct ResampleTable {
+  std::vector<int32_t> k;
+  std::vector<float> t;
+  int64_t n_active_blocks = 0;
+  int64_t n_zero_from = 0;
+  int32_t* d_k = nullptr;
+  float* d_t = nullptr;
+};
+
 struct gac_context {
   uint32_t magic = 0x47414331;  // "GAC1"
   int device = 0;
@@ -101,6 +111,7 @@ struct gac_context {
   // response whose upload is still in flight; renders wait on the `ready` event of exactly the IRs they use
   cudaStream_t prep_stream = nullptr;
   std::vector<cudaEvent_t> event_pool;  // recycled `ready` events (creating one costs a driver call per buffer)
+  std::map<std::tuple<double, int64_t, int64_t, int64_t>, std::shared_ptr<ResampleTable>> resample_cache;
 };
 static cudaEvent_t take_event(gac_context* ctx) {
   if (!ctx->event_pool.empty()) {
@@ -398,6 +409,10 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) gac_comm_destroy(ctx);
+  for (auto& kv : ctx->resample_cache) {
+    if (kv.second->d_k) cudaFreeAsync(kv.second->d_k, ctx->stream);
+    if (kv.second->d_t) cudaFreeAsync(kv.second->d_t, ctx->stream);
+  }
   if (ctx->d_tw) cudaFreeAsync(ctx->d_tw, ctx->stream);
   if (ctx->d_tw2) cudaFreeAsync(ctx->d_tw2, ctx->stream);
   if (ctx->d_bt) cudaFreeAsync(ctx->d_bt, ctx->stream);

@@ -3,14 +3,7 @@
 // kernel-level test entry points.
 
 // ------------------------------------------------------------------------------------------ source stage (K1)
-struct ResampleTable {
-  std::vector<int32_t> k;
-  std::vector<float> t;
-  int64_t n_active_blocks = 0;
-  int64_t n_zero_from = 0;
-  int32_t* d_k = nullptr;
-  float* d_t = nullptr;
-};
+// (struct ResampleTable lives in engine.cu: the tables are cached in the context across renders)
 
 // Nodes/AudioBufferSourceNode.cs:131-376, non-loop paths.  Decides, on the host, which quanta the source emits
 // (block-granular start/stop :137-143; final block dropped :360-368) and, for the CubicResampler path, replays
@@ -21,7 +14,7 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
   const std::vector<double>& bt = ctx->h_bt;
   auto& cj = env.keep->make<SourceJob>();
   auto& rj = env.keep->make<ResampleJob>();
-  std::map<std::tuple<double, int64_t, int64_t, int64_t>, std::shared_ptr<ResampleTable>> tables;
+  auto& tables = ctx->resample_cache;  // the phase recurrence depends on (rate, offset, end, length) only: replayed once per context
   const double inf = std::numeric_limits<double>::infinity();
 
   for (size_t i = 0; i < voices.size(); i++) {
@@ -98,8 +91,15 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
       if (it != tables.end()) {
         tab = it->second;
       } else {
+        if (tables.size() >= 16) {  // bounded: drop everything (stream-ordered frees behind any render still using them)
+          for (auto& kv : tables) {
+            if (kv.second->d_k) cudaFreeAsync(kv.second->d_k, ctx->stream);
+            if (kv.second->d_t) cudaFreeAsync(kv.second->d_t, ctx->stream);
+            env.keep->items.push_back(kv.second);  // host vectors may still be the source of a queued copy
+          }
+          tables.clear();
+        }
         tab = std::make_shared<ResampleTable>();
-        env.keep->items.push_back(tab);
         if (avail >= 4) {
           tab->k.reserve((size_t)n_out_max);
           tab->t.reserve((size_t)n_out_max);
@@ -130,9 +130,11 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
           tab->k.resize((size_t)std::min<int64_t>(m, active * 128));
           tab->t.resize(tab->k.size());
           if (!tab->k.empty()) {
-            int rc;
-            if ((rc = env.scratch->upload(&tab->d_k, tab->k))) return rc;
-            if ((rc = env.scratch->upload(&tab->d_t, tab->t))) return rc;
+            // context-owned device copies (not render scratch): later renders of the same source geometry reuse them
+            CU(cudaMallocAsync(&tab->d_k, tab->k.size() * sizeof(int32_t), ctx->stream));
+            CU(cudaMallocAsync(&tab->d_t, tab->t.size() * sizeof(float), ctx->stream));
+            CU(cudaMemcpyAsync(tab->d_k, tab->k.data(), tab->k.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(tab->d_t, tab->t.data(), tab->t.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
           }
         }
         tables[key] = tab;

@@ -12,8 +12,11 @@
 //   k_biquad_lanes    one lane per (voice, channel): w = x - a1*w1 - a2*w2 (:137) is the sequential chain, y = b0*w + b1*w1 +
 //                     b2*w2 (:138) rides along off the critical path; TMA-fed, concurrent verified time segments (biquad_lanes.cu)
 //
-// Slab-transposed layout (shared by resolve, lanes and output): rows are grouped 32 at a time (16 voices x 2 channels = one
-// warp of lanes), time is cut into slabs of 32 frames, and inside a slab the FRAME index is major and the row index minor:
+// Slab-transposed layout (shared by resolve and lanes): rows are grouped 32 at a time (16 voices x 2 channels = one
+// warp of lanes), time is cut into slabs of 32 frames, and inside a slab the FRAME index is major and the row index minor
+// (per-row layout, below) — or, when the select pass proved that both channels of every voice of the group share one
+// coefficient set per frame (always, except for drifts slower than the hysteresis), the VOICE index is minor and an element
+// carries both channels' samples: [frame][voice 0..15] (a1, a2, xL, xR) / (b0, b1, b2, -), half the bytes:
 //     S1T[group][slab][frame 0..31][row 0..31]  float4 (x, a1, a2, -)         S2T[group][slab][frame][row]  float4 (b0, b1, b2, -)
 // so that a slab is one contiguous 16 KB (4 KB) block for TMA and lane r's LDS.128 / STS.32 at frame i are conflict-free.
 #include "biquad_math.cuh"
@@ -38,7 +41,7 @@ __device__ __forceinline__ bool bq_differs(float f, float q, float uf, float uq)
   return fabsf(f - uf) > 0.001f || fabsf(q - uq) > 0.0001f;  // :126 (gain never differs inside a block)
 }
 __global__ void __launch_bounds__(kSelWarps * 32) k_biquad_select(const BiquadJob* __restrict__ jobs, int sample_rate, int64_t n_quanta,
-                                                                  int64_t n_frames, int32_t* __restrict__ last_base) {
+                                                                  int64_t n_frames, int32_t* __restrict__ last_base, int* __restrict__ wide) {
   __shared__ float sf[kSelWarps][128];
   __shared__ float sq[kSelWarps][128];
   __shared__ int32_t si[kSelWarps][2][128];
@@ -126,6 +129,17 @@ __global__ void __launch_bounds__(kSelWarps * 32) k_biquad_select(const BiquadJo
       }
       last[(size_t)c * n_quanta + b] = cur;
     }
+    // the two channels of this voice may now be governed by different coefficient sets somewhere in the quantum: its 32-row
+    // group takes the per-row stream layout (both closed-form cases above provably share one set per frame)
+    // (frames before a channel's first recompute use the entry set: channel 0's is what the previous quantum left, channel 1's
+    // is channel 0's last recompute of THIS quantum if there was one — k_biquad_entry — so "-1 in both" is not always equal)
+    const int32_t l0 = last[b];
+    bool differ = false;
+    for (int i = 0; i < 128; i++) {
+      const int32_t a = si[warp][0][i], c = si[warp][1][i];
+      differ = differ || a != c || (c < 0 && l0 >= 0);
+    }
+    if (differ) atomicOr(&wide[jid >> 4], 1);
   }
   __syncwarp();
   *reinterpret_cast<int4*>(idx0) = *reinterpret_cast<const int4*>(&si[warp][0][4 * lane]);
@@ -194,7 +208,7 @@ __device__ __forceinline__ Coef rbj_shared(const BiquadJob& job, int32_t k, floa
 
 __global__ void __launch_bounds__(512) k_biquad_resolve(const BiquadJob* __restrict__ jobs, int n_jobs, int sample_rate, int64_t n_quanta,
                                                         int64_t n_frames, const int32_t* __restrict__ ent_base, float4* __restrict__ s1t,
-                                                        float4* __restrict__ s2t) {
+                                                        float4* __restrict__ s2t, const int* __restrict__ wide_flags) {
   __shared__ float4 tile[32][33];
   __shared__ float4 tile2[32][33];
   const int jv = threadIdx.x >> 5, i = threadIdx.x & 31;
@@ -225,20 +239,31 @@ __global__ void __launch_bounds__(512) k_biquad_resolve(const BiquadJob* __restr
       job.sig[1][n] = 0.f;
     }
   }
-  tile[i][2 * jv] = v0;
-  tile[i][2 * jv + 1] = v1;
-  tile2[i][2 * jv] = u0;
-  tile2[i][2 * jv + 1] = u1;
-  __syncthreads();
-  // tile[frame][row] -> S1T / S2T [g][slab][frame][row]: element e = frame * 32 + row
-  const size_t n_slabs = (size_t)(n_frames / 32);
-  float4* dst = s1t + ((size_t)g * n_slabs + slab) * 1024;
-  float4* dst2 = s2t + ((size_t)g * n_slabs + slab) * 1024;
+  const size_t group_base = (size_t)g * (size_t)n_frames * 32;
+  if (wide_flags[g]) {
+    // per-row layout: tile[frame][row] -> S1T / S2T [g][slab][frame][row 0..31], element e = frame * 32 + row
+    tile[i][2 * jv] = v0;
+    tile[i][2 * jv + 1] = v1;
+    tile2[i][2 * jv] = u0;
+    tile2[i][2 * jv + 1] = u1;
+    __syncthreads();
+    float4* dst = s1t + group_base + (size_t)slab * 1024;
+    float4* dst2 = s2t + group_base + (size_t)slab * 1024;
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int e = threadIdx.x + 512 * h;
-    dst[e] = tile[e >> 5][e & 31];
-    dst2[e] = tile2[e >> 5][e & 31];
+    for (int h = 0; h < 2; h++) {
+      const int e = threadIdx.x + 512 * h;
+      dst[e] = tile[e >> 5][e & 31];
+      dst2[e] = tile2[e >> 5][e & 31];
+    }
+  } else {
+    // per-voice layout (both channels share the coefficient set at every frame of this group):
+    // S1T [g][slab][frame][voice 0..15] = (a1, a2, xL, xR), S2T = (b0, b1, b2, -): half the bytes of the per-row layout
+    tile[i][jv] = make_float4(v0.y, v0.z, v0.x, v1.x);
+    tile2[i][jv] = u0;
+    __syncthreads();
+    const int e = threadIdx.x;  // element e = frame * 16 + voice
+    s1t[group_base + (size_t)slab * 512 + e] = tile[e >> 4][e & 15];
+    s2t[group_base + (size_t)slab * 512 + e] = tile2[e >> 4][e & 15];
   }
 }
 
@@ -247,10 +272,12 @@ void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_
   if (n_jobs <= 0 || n_frames <= 0) return;
   const int groups = (n_jobs + 15) / 16;
   const unsigned n_slabs = (unsigned)(n_frames / 32);
-  k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_jobs), kSelWarps * 32, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last);
+  int* d_wide = d_first_bad + groups;  // [groups] stream layout flags, set by the select pass
+  cudaMemsetAsync(d_wide, 0, sizeof(int) * groups, s);
+  k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_jobs), kSelWarps * 32, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last, d_wide);
   k_biquad_entry<<<(unsigned)n_jobs, 32, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
-  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t);
-  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_first_bad, s);
+  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t, d_wide);
+  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_first_bad, d_wide, s);
 }
 
 }  // namespace gac

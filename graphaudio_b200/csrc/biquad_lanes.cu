@@ -63,7 +63,8 @@ constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64;
 template <bool REPAIR>
 __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
                                                      const float4* __restrict__ s1t, const float4* __restrict__ s2t, int seg_slabs, int n_seg,
-                                                     float2* __restrict__ states, const int* __restrict__ first_bad) {
+                                                     float2* __restrict__ states, const int* __restrict__ first_bad,
+                                                     const int* __restrict__ wide_flags) {
   extern __shared__ __align__(128) unsigned char lanes_smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(lanes_smem + kStages * kStageBytes);  // [kStages]
   const int lane = threadIdx.x;
@@ -89,8 +90,14 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
   const int n_slabs = s_end - s_first;
   const int n_warm = s_own - s_first;
   float2* st_group = states + (size_t)blockIdx.x * n_seg * 64;
-  // element (frame n, row r) of group g lives at (g * n_frames + n) * 32 + r in both streams
-  const size_t base_elem = ((size_t)blockIdx.x * (size_t)n_frames + (size_t)lo + (size_t)s_first * kSlab) * 32;
+  // stream layout of this group (biquad.cu header): per row — element (frame n, row r) at n * 32 + r — or per voice —
+  // element (frame n, voice v) at n * 16 + v, carrying (a1, a2, xL, xR); both relative to the group base g * n_frames * 32
+  const bool wide = wide_flags[blockIdx.x] != 0;
+  const int RS = wide ? 32 : 16;                      // elements per frame
+  const int ridx = wide ? lane : (lane >> 1);         // this lane's element within a frame
+  const bool right = (lane & 1) != 0;
+  const uint32_t tile_bytes = (uint32_t)(kSlab * RS * 16);
+  const size_t base_elem = (size_t)blockIdx.x * (size_t)n_frames * 32 + ((size_t)lo + (size_t)s_first * kSlab) * RS;
   const float4* __restrict__ src1 = s1t + base_elem;
   const float4* __restrict__ src2 = s2t + base_elem;
   const uint32_t bar0 = bq_smem_u32(bars);
@@ -106,9 +113,9 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     if (s < n_slabs && lane == 0) {
       const int st = s % kStages;
       const bool own = s >= n_warm;  // the output coefficients are not needed while warming up
-      bq_mbar_expect_tx(bar0 + 8 * st, own ? kStageBytes : kTileBytes);
-      bq_bulk_g2s(stage0 + st * kStageBytes, src1 + (size_t)s * (kSlab * 32), kTileBytes, bar0 + 8 * st);
-      if (own) bq_bulk_g2s(stage0 + st * kStageBytes + kTileBytes, src2 + (size_t)s * (kSlab * 32), kTileBytes, bar0 + 8 * st);
+      bq_mbar_expect_tx(bar0 + 8 * st, own ? 2 * tile_bytes : tile_bytes);
+      bq_bulk_g2s(stage0 + st * kStageBytes, src1 + (size_t)s * (kSlab * RS), tile_bytes, bar0 + 8 * st);
+      if (own) bq_bulk_g2s(stage0 + st * kStageBytes + kTileBytes, src2 + (size_t)s * (kSlab * RS), tile_bytes, bar0 + 8 * st);
     }
   };
 
@@ -130,8 +137,8 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     const int64_t base = lo + (int64_t)(s_first + s) * kSlab;
     const bool act = base >= my_lo && base < my_hi;  // silent-flagged quanta: state untouched (:103-108)
     const bool own = s >= n_warm;
-    const float4* __restrict__ rows = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes) + lane;           // [i][lane]: (x, a1, a2, -)
-    const float4* __restrict__ outs = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes + kTileBytes) + lane;  // (b0, b1, b2, -)
+    const float4* __restrict__ rows = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes) + ridx;               // [i][element]
+    const float4* __restrict__ outs = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes + kTileBytes) + ridx;  // (b0, b1, b2, -)
     if (act) {
       // 32 frames at a time: all loads first, then the dependent chain from registers, so that the 30-cycle LDS latency is paid
       // once per 32 frames (the warp is alone on its SM sub-partition; nothing else hides it); then y, off the critical path
@@ -140,10 +147,10 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
         float x[32], p1[32], p2[32], wo[34];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          const float4 r = rows[(q * 32 + i) * 32];
-          x[i] = r.x;
-          p1[i] = r.y;
-          p2[i] = r.z;
+          const float4 r = rows[(q * 32 + i) * RS];
+          x[i] = wide ? r.x : (right ? r.w : r.z);  // per row: (x, a1, a2, -); per voice: (a1, a2, xL, xR)
+          p1[i] = wide ? r.y : r.x;
+          p2[i] = wide ? r.z : r.y;
         }
         wo[0] = w2;
         wo[1] = w1;
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
 #pragma unroll
             for (int e = 0; e < 4; e++) {
               const int i = 4 * i4 + e;
-              const float4 b = outs[(q * 32 + i) * 32];
+              const float4 b = outs[(q * 32 + i) * RS];
               y[e] = b.x * wo[i + 2] + b.y * wo[i + 1] + b.z * wo[i];  // :138  y = b0*w + b1*w1 + b2*w2
             }
             *reinterpret_cast<float4*>(dst + 4 * i4) = make_float4(y[0], y[1], y[2], y[3]);
@@ -208,7 +215,7 @@ int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs_out) {
 }
 
 void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,
-                         int* d_first_bad, cudaStream_t s) {
+                         int* d_first_bad, const int* d_wide, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_biquad_lanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
@@ -218,10 +225,10 @@ void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, 
   const unsigned groups = (unsigned)((n_jobs + 15) / 16);
   int seg_slabs = 0;
   const int n_seg = biquad_lane_segments(n_jobs, n_frames, &seg_slabs);
-  k_biquad_lanes<false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr);
+  k_biquad_lanes<false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr, d_wide);
   if (n_seg > 1) {
     k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad);
-    k_biquad_lanes<true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad);
+    k_biquad_lanes<true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad, d_wide);
   }
 }
 

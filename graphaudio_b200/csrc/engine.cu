@@ -1160,7 +1160,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         int* dbad = nullptr;
         const int n_seg = biquad_lane_segments((int)nk, env.Npad, nullptr);
         if ((rc = env.scratch->alloc(&dstates, ((nk + 15) / 16) * (size_t)n_seg * 64))) return rc;
-        if ((rc = env.scratch->alloc(&dbad, (nk + 15) / 16))) return rc;
+        if ((rc = env.scratch->alloc(&dbad, 2 * ((nk + 15) / 16)))) return rc;
         int t = env.timer->begin(C_BIQUAD);
         launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, s2_all, dstates, dbad, ctx->stream);
         env.timer->end(t);

@@ -235,3 +235,35 @@ def test_c4_render_batch_of_independent_contexts():
         assert np.abs(refs[r]).max() > 1e-3
         assert np.abs(out[r] - refs[r]).max() <= TOL, r
     parent.Dispose()
+
+
+def test_biquad_slow_drift_takes_the_general_walk_and_the_per_row_layout():
+    """A cutoff that drifts slower than the 1e-3 Hz hysteresis recomputes every few frames, at different frames in the two
+    channels (channel 1 starts each block from channel 0's last value): exercises the serial walk of k_biquad_select and the
+    per-row stream layout of the recursion kernel; a second voice with a constant filter shares the 32-row group."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+
+    def build(api):
+        ctx = api.OfflineAudioContext(fs)
+        for v, (f0, f1) in enumerate([(1000.0, 1004.0), (700.0, 700.0), (2500.0, 2500.4)]):
+            s = api.AudioBufferSourceNode(ctx)
+            s.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(700 + 4 * v + c, 30000) for c in range(2)], fs)
+            bq = api.BiQuadFilterNode(ctx)
+            bq.Type = api.FilterType.Lowpass if v != 1 else api.FilterType.Peaking
+            bq.Q.Value = 1.5
+            bq.Gain.Value = 3.0
+            bq.Frequency.SetValueAtTime(f0, 0.0)
+            if f1 != f0:
+                bq.Frequency.LinearRampToValueAtTime(f1, 0.6)
+            g = api.GainNode(ctx)
+            g.Gain.Value = 0.3
+            s.Connect(bq).Connect(g).Connect(ctx.Destination)
+            s.Start()
+        return ctx
+    n = 30000
+    yg = build(G).Render(n)
+    yo = build(O).Render(n)
+    assert np.abs(yo).max() > 1e-2
+    assert np.abs(yg - yo).max() <= TOL

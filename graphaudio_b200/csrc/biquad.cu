@@ -217,27 +217,62 @@ __global__ void __launch_bounds__(512) k_biquad_resolve(const BiquadJob* __restr
   const int jid = g * 16 + jv;
   const int64_t n = slab * 32 + i;
   float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, u0 = v0, u1 = v0;
-  if (jid < n_jobs) {  // (warp-uniform, like the range test below: ranges are multiples of 128 frames, a warp covers 32)
+  // Voices of a group very often run the SAME filter automation (one table, deduplicated by the engine, or the same constants):
+  // then the coefficient set of (frame, selected frame k) is the same for all of them, and only the group's first voice
+  // evaluates RBJ; the others take it from shared memory when their parameters and their selected frame coincide with its.
+  __shared__ int32_t lead_k[32];
+  __shared__ float lead_c[5][32];
+  const bool in_range = jid < n_jobs && n >= jobs[jid].lo && n < jobs[jid].hi;  // warp-uniform: ranges are multiples of 128 frames
+  int32_t k0 = -1, k1 = -1;
+  if (in_range) {
     const BiquadJob& job = jobs[jid];
-    if (n >= job.lo && n < job.hi) {
-      int32_t k0 = job.idx[n], k1 = job.idx[n_frames + n];
-      if (k0 < 0) k0 = ent_base[((size_t)jid * 2 + 0) * n_quanta + (n >> 7)];
-      if (k1 < 0) k1 = ent_base[((size_t)jid * 2 + 1) * n_quanta + (n >> 7)];
-      const float nyq = (float)sample_rate / 2.f;
-      const Coef c0 = rbj_shared(job, k0, nyq, sample_rate);
-      Coef c1 = c0;
-      if (__any_sync(0xffffffffu, k1 != k0)) {
-        const Coef alt = rbj_shared(job, k1, nyq, sample_rate);
-        if (k1 != k0) c1 = alt;
+    k0 = job.idx[n];
+    k1 = job.idx[n_frames + n];
+    if (k0 < 0) k0 = ent_base[((size_t)jid * 2 + 0) * n_quanta + (n >> 7)];
+    if (k1 < 0) k1 = ent_base[((size_t)jid * 2 + 1) * n_quanta + (n >> 7)];
+  }
+  const float nyq = (float)sample_rate / 2.f;
+  Coef c0;
+  c0.b0 = c0.b1 = c0.b2 = c0.a1 = c0.a2 = 0.f;
+  if (jv == 0) {
+    if (in_range) c0 = rbj_shared(jobs[jid], k0, nyq, sample_rate);
+    lead_k[i] = in_range ? k0 : INT32_MIN;
+    lead_c[0][i] = c0.b0;
+    lead_c[1][i] = c0.b1;
+    lead_c[2][i] = c0.b2;
+    lead_c[3][i] = c0.a1;
+    lead_c[4][i] = c0.a2;
+  }
+  __syncthreads();
+  if (in_range) {
+    const BiquadJob& job = jobs[jid];
+    if (jv != 0) {
+      const BiquadJob& lead = jobs[g * 16];
+      const bool same_params = job.type == lead.type && job.freq == lead.freq && job.q == lead.q && job.gain == lead.gain &&
+                               job.freq_const == lead.freq_const && job.q_const == lead.q_const && job.gain_const == lead.gain_const;
+      const bool reuse = same_params && k0 == lead_k[i];
+      if (__all_sync(0xffffffffu, reuse)) {
+        c0.b0 = lead_c[0][i];
+        c0.b1 = lead_c[1][i];
+        c0.b2 = lead_c[2][i];
+        c0.a1 = lead_c[3][i];
+        c0.a2 = lead_c[4][i];
+      } else {
+        c0 = rbj_shared(job, k0, nyq, sample_rate);
       }
-      v0 = make_float4(job.sig[0][n], c0.a1, c0.a2, 0.f);
-      v1 = make_float4(job.sig[1][n], c1.a1, c1.a2, 0.f);
-      u0 = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
-      u1 = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
-    } else if (n < n_frames) {
-      job.sig[0][n] = 0.f;
-      job.sig[1][n] = 0.f;
     }
+    Coef c1 = c0;
+    if (__any_sync(0xffffffffu, k1 != k0)) {
+      const Coef alt = rbj_shared(job, k1, nyq, sample_rate);
+      if (k1 != k0) c1 = alt;
+    }
+    v0 = make_float4(job.sig[0][n], c0.a1, c0.a2, 0.f);
+    v1 = make_float4(job.sig[1][n], c1.a1, c1.a2, 0.f);
+    u0 = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
+    u1 = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
+  } else if (jid < n_jobs && n < n_frames) {
+    jobs[jid].sig[0][n] = 0.f;
+    jobs[jid].sig[1][n] = 0.f;
   }
   const size_t group_base = (size_t)g * (size_t)n_frames * 32;
   if (wide_flags[g]) {

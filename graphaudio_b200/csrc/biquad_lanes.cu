@@ -50,9 +50,10 @@ __device__ __forceinline__ void bq_bulk_s2g(void* dst, uint32_t src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
-constexpr int kSlab = 64;    // frames per pipeline stage = 2 consecutive 32-frame layout slabs (contiguous in HBM)
-constexpr int kStages = 3;   // stages in flight
-constexpr int kWarmSlabs = 128;  // warm-up of a speculative segment: 128 * 64 = 8192 frames
+constexpr int kSlab = 32;    // frames per pipeline stage = one 32-frame layout slab
+constexpr int kStages = 3;   // stages in flight (96 KB per CTA: two CTAs, i.e. two concurrent segments, per SM)
+constexpr int kWarmSlabs = 256;  // warm-up of a speculative segment: 256 * 32 = 8192 frames
+constexpr int kLaneSlots = 2 * 148;  // concurrent single-warp CTAs
 constexpr int kTileBytes = kSlab * 32 * 16;   // one stream's stage: 32 KB
 constexpr int kStageBytes = 2 * kTileBytes;   // (x, a1, a2) tile + (b0, b1, b2) tile
 constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64;
@@ -60,13 +61,14 @@ constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64;
 // states: float2 [groups][n_seg][2 (start, end)][32 rows];  first_bad: int [groups] (n_seg = all links verified)
 // REPAIR = false: grid (groups, n_seg), segment blockIdx.y runs speculatively.  REPAIR = true: grid (groups), the group
 // re-runs sequentially from segment first_bad[g] (does nothing if every link matched).
-template <bool REPAIR>
+template <bool REPAIR, bool WIDE>
 __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
                                                      const float4* __restrict__ s1t, const float4* __restrict__ s2t, int seg_slabs, int n_seg,
                                                      float2* __restrict__ states, const int* __restrict__ first_bad,
                                                      const int* __restrict__ wide_flags) {
   extern __shared__ __align__(128) unsigned char lanes_smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(lanes_smem + kStages * kStageBytes);  // [kStages]
+  if ((wide_flags[blockIdx.x] != 0) != WIDE) return;  // the other instantiation serves this group
   const int lane = threadIdx.x;
   const int j = blockIdx.x * 16 + (lane >> 1);
   const bool valid = j < n_jobs;
@@ -92,11 +94,10 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
   float2* st_group = states + (size_t)blockIdx.x * n_seg * 64;
   // stream layout of this group (biquad.cu header): per row — element (frame n, row r) at n * 32 + r — or per voice —
   // element (frame n, voice v) at n * 16 + v, carrying (a1, a2, xL, xR); both relative to the group base g * n_frames * 32
-  const bool wide = wide_flags[blockIdx.x] != 0;
-  const int RS = wide ? 32 : 16;                      // elements per frame
-  const int ridx = wide ? lane : (lane >> 1);         // this lane's element within a frame
+  constexpr int RS = WIDE ? 32 : 16;                  // elements per frame
+  const int ridx = WIDE ? lane : (lane >> 1);         // this lane's element within a frame
   const bool right = (lane & 1) != 0;
-  const uint32_t tile_bytes = (uint32_t)(kSlab * RS * 16);
+  constexpr uint32_t tile_bytes = (uint32_t)(kSlab * RS * 16);
   const size_t base_elem = (size_t)blockIdx.x * (size_t)n_frames * 32 + ((size_t)lo + (size_t)s_first * kSlab) * RS;
   const float4* __restrict__ src1 = s1t + base_elem;
   const float4* __restrict__ src2 = s2t + base_elem;
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
 #pragma unroll
         for (int i = 0; i < 32; i++) {
           const float4 r = rows[(q * 32 + i) * RS];
-          x[i] = wide ? r.x : (right ? r.w : r.z);  // per row: (x, a1, a2, -); per voice: (a1, a2, xL, xR)
-          p1[i] = wide ? r.y : r.x;
-          p2[i] = wide ? r.z : r.y;
+          x[i] = WIDE ? r.x : (right ? r.w : r.z);  // per row: (x, a1, a2, -); per voice: (a1, a2, xL, xR)
+          p1[i] = WIDE ? r.y : r.x;
+          p2[i] = WIDE ? r.z : r.y;
         }
         wo[0] = w2;
         wo[1] = w1;
@@ -200,11 +201,11 @@ __global__ void __launch_bounds__(32) k_biquad_verify(int n_seg, const float2* _
 }
 
 int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs_out) {
-  // one CTA (= one warp, 208 KB of staging) per SM: as many concurrent segments as there are SMs per group, but segments no
-  // shorter than the warm-up (below that the redundant work outweighs the concurrency)
+  // one CTA = one warp with 96 KB of staging, two per SM: as many concurrent segments as there are slots per group, but
+  // segments no shorter than the warm-up (below that the redundant work outweighs the concurrency)
   const int groups = (n_jobs + 15) / 16;
   const int total_slabs = (int)((n_frames + kSlab - 1) / kSlab);
-  int n_seg = 148 / (groups > 0 ? groups : 1);
+  int n_seg = kLaneSlots / (groups > 0 ? groups : 1);
   if (n_seg < 1) n_seg = 1;
   int seg_slabs = (total_slabs + n_seg - 1) / n_seg;
   if (seg_slabs < kWarmSlabs) seg_slabs = kWarmSlabs;
@@ -218,17 +219,22 @@ void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, 
                          int* d_first_bad, const int* d_wide, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_biquad_lanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
-    cudaFuncSetAttribute(k_biquad_lanes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
+    cudaFuncSetAttribute(k_biquad_lanes<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
+    cudaFuncSetAttribute(k_biquad_lanes<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
+    cudaFuncSetAttribute(k_biquad_lanes<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
+    cudaFuncSetAttribute(k_biquad_lanes<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
     attr = true;
   }
   const unsigned groups = (unsigned)((n_jobs + 15) / 16);
   int seg_slabs = 0;
   const int n_seg = biquad_lane_segments(n_jobs, n_frames, &seg_slabs);
-  k_biquad_lanes<false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr, d_wide);
+  // both stream layouts are launched; a CTA whose group uses the other layout exits at once
+  k_biquad_lanes<false, false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr, d_wide);
+  k_biquad_lanes<false, true><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr, d_wide);
   if (n_seg > 1) {
     k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad);
-    k_biquad_lanes<true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad, d_wide);
+    k_biquad_lanes<true, false><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad, d_wide);
+    k_biquad_lanes<true, true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad, d_wide);
   }
 }
 

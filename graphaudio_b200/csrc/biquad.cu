@@ -303,16 +303,16 @@ __global__ void __launch_bounds__(512) k_biquad_resolve(const BiquadJob* __restr
 }
 
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_first_bad, cudaStream_t s) {
+                   int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_flags, cudaStream_t s) {
   if (n_jobs <= 0 || n_frames <= 0) return;
   const int groups = (n_jobs + 15) / 16;
   const unsigned n_slabs = (unsigned)(n_frames / 32);
-  int* d_wide = d_first_bad + groups;  // [groups] stream layout flags, set by the select pass
+  int* d_wide = d_flags + groups;  // [groups] stream layout flags, set by the select pass (layout of d_flags: biquad_lanes.cu)
   cudaMemsetAsync(d_wide, 0, sizeof(int) * groups, s);
   k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_jobs), kSelWarps * 32, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last, d_wide);
   k_biquad_entry<<<(unsigned)n_jobs, 32, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
   k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t, d_wide);
-  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_first_bad, d_wide, s);
+  launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_flags, s);
 }
 
 }  // namespace gac

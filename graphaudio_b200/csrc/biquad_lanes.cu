@@ -56,18 +56,24 @@ constexpr int kWarmSlabs = 256;  // warm-up of a speculative segment: 256 * 32 =
 constexpr int kLaneSlots = 2 * 148;  // concurrent single-warp CTAs
 constexpr int kTileBytes = kSlab * 32 * 16;   // one stream's stage: 32 KB
 constexpr int kStageBytes = 2 * kTileBytes;   // (x, a1, a2) tile + (b0, b1, b2) tile
-constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64;
+constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64 + kStages * 256;  // stages, barriers, staged speculative states (repair)
 
-// states: float2 [groups][n_seg][2 (start, end)][32 rows];  first_bad: int [groups] (n_seg = all links verified)
-// REPAIR = false: grid (groups, n_seg), segment blockIdx.y runs speculatively.  REPAIR = true: grid (groups), the group
-// re-runs sequentially from segment first_bad[g] (does nothing if every link matched).
+// states: float2 [groups][n_seg][2 (start, end)][32 rows], then slab_states: float2 [groups][n_frames / 32][32 rows] (the state
+// after every 32-frame slab of the speculative pass).  flags: int [groups] first_bad, [groups] layout, [groups][n_seg] link_bad.
+//
+// REPAIR = false: grid (groups, n_seg), segment blockIdx.y runs speculatively.
+// REPAIR = true : grid (groups).  For every link the verification found broken, the group re-runs from the last true state —
+//   the end state of the previous segment — and compares its state with the speculative pass's after every slab: the moment
+//   all 32 rows coincide bitwise it has re-joined the speculative trajectory, everything behind that point is already right,
+//   and it moves on to the next broken link.  A segment that never re-joins hands its state on to the next one.
 template <bool REPAIR, bool WIDE>
 __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
                                                      const float4* __restrict__ s1t, const float4* __restrict__ s2t, int seg_slabs, int n_seg,
-                                                     float2* __restrict__ states, const int* __restrict__ first_bad,
-                                                     const int* __restrict__ wide_flags) {
+                                                     float2* __restrict__ states, float2* __restrict__ slab_states, const int* __restrict__ first_bad,
+                                                     const int* __restrict__ wide_flags, const int* __restrict__ link_bad) {
   extern __shared__ __align__(128) unsigned char lanes_smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(lanes_smem + kStages * kStageBytes);  // [kStages]
+  float2* spec_sm = reinterpret_cast<float2*>(lanes_smem + kStages * kStageBytes + 64);  // [kStages][32]: the speculative pass's state after the slab
   if ((wide_flags[blockIdx.x] != 0) != WIDE) return;  // the other instantiation serves this group
   const int lane = threadIdx.x;
   const int j = blockIdx.x * 16 + (lane >> 1);
@@ -82,25 +88,15 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
   }
   if (hi <= lo) return;
   const int total_slabs = (int)((hi - lo + kSlab - 1) / kSlab);  // ranges are multiples of 128 frames
-  // this CTA's slabs (relative to lo): [s_first, s_end), of which [s_first, s_own) is warm-up (recursion only, nothing written)
-  int seg = REPAIR ? first_bad[blockIdx.x] : (int)blockIdx.y;
-  if (seg >= n_seg) return;
-  const int s_own = seg * seg_slabs;
-  if (s_own >= total_slabs) return;
-  const int s_end = REPAIR ? total_slabs : (s_own + seg_slabs < total_slabs ? s_own + seg_slabs : total_slabs);
-  const int s_first = (REPAIR || seg == 0) ? s_own : (s_own - kWarmSlabs > 0 ? s_own - kWarmSlabs : 0);
-  const int n_slabs = s_end - s_first;
-  const int n_warm = s_own - s_first;
   float2* st_group = states + (size_t)blockIdx.x * n_seg * 64;
+  float2* slab_group = slab_states + ((size_t)blockIdx.x * (size_t)(n_frames / kSlab) + (size_t)(lo / kSlab)) * 32;  // [slab relative to lo][row]
   // stream layout of this group (biquad.cu header): per row — element (frame n, row r) at n * 32 + r — or per voice —
   // element (frame n, voice v) at n * 16 + v, carrying (a1, a2, xL, xR); both relative to the group base g * n_frames * 32
   constexpr int RS = WIDE ? 32 : 16;                  // elements per frame
   const int ridx = WIDE ? lane : (lane >> 1);         // this lane's element within a frame
   const bool right = (lane & 1) != 0;
   constexpr uint32_t tile_bytes = (uint32_t)(kSlab * RS * 16);
-  const size_t base_elem = (size_t)blockIdx.x * (size_t)n_frames * 32 + ((size_t)lo + (size_t)s_first * kSlab) * RS;
-  const float4* __restrict__ src1 = s1t + base_elem;
-  const float4* __restrict__ src2 = s2t + base_elem;
+  const size_t group_elem = (size_t)blockIdx.x * (size_t)n_frames * 32 + (size_t)lo * RS;
   const uint32_t bar0 = bq_smem_u32(bars);
   const uint32_t stage0 = bq_smem_u32(lanes_smem);
 
@@ -109,46 +105,47 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-
-  auto issue = [&](int s) {
-    if (s < n_slabs && lane == 0) {
-      const int st = s % kStages;
-      const bool own = s >= n_warm;  // the output coefficients are not needed while warming up
-      bq_mbar_expect_tx(bar0 + 8 * st, own ? 2 * tile_bytes : tile_bytes);
-      bq_bulk_g2s(stage0 + st * kStageBytes, src1 + (size_t)s * (kSlab * RS), tile_bytes, bar0 + 8 * st);
-      if (own) bq_bulk_g2s(stage0 + st * kStageBytes + kTileBytes, src2 + (size_t)s * (kSlab * RS), tile_bytes, bar0 + 8 * st);
-    }
-  };
-
-  for (int s = 0; s < kStages - 1; s++) issue(s);
+  uint32_t phases = 0u;  // bit st = parity to wait for on stage st (persists across runs)
   float w1 = 0.f, w2 = 0.f;
-  if (REPAIR && seg > 0) {  // the last verified state: what segment seg-1 ended with
-    const float2 e = st_group[((size_t)(seg - 1) * 2 + 1) * 32 + lane];
-    w1 = e.x;
-    w2 = e.y;
-  }
-  uint32_t phases = 0u;  // bit st = parity to wait for on stage st
-  for (int s = 0; s < n_slabs; s++) {
-    if (s == n_warm && !REPAIR) st_group[((size_t)seg * 2 + 0) * 32 + lane] = make_float2(w1, w2);  // state at the segment's first own frame
-    __syncwarp();                // every lane is done reading the stage that is refilled next
-    issue(s + kStages - 1);
-    const int st = s % kStages;
-    bq_mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
-    phases ^= 1u << st;
-    const int64_t base = lo + (int64_t)(s_first + s) * kSlab;
-    const bool act = base >= my_lo && base < my_hi;  // silent-flagged quanta: state untouched (:103-108)
-    const bool own = s >= n_warm;
-    const float4* __restrict__ rows = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes) + ridx;               // [i][element]
-    const float4* __restrict__ outs = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes + kTileBytes) + ridx;  // (b0, b1, b2, -)
-    if (act) {
-      // 32 frames at a time: all loads first, then the dependent chain from registers, so that the 30-cycle LDS latency is paid
-      // once per 32 frames (the warp is alone on its SM sub-partition; nothing else hides it); then y, off the critical path
-#pragma unroll 1
-      for (int q = 0; q < kSlab / 32; q++) {
+
+  // One run: slabs [s_first, s_end) relative to lo, the first n_warm of them recursion only (nothing written).
+  // REJOIN: stop as soon as the state after a slab equals the one the speculative pass recorded there; returns true then.
+  auto run = [&](const int s_first, const int n_warm, const int s_end, const bool rejoin) -> bool {
+    const int n_slabs = s_end - s_first;
+    const float4* __restrict__ src1 = s1t + group_elem + (size_t)s_first * kSlab * RS;
+    const float4* __restrict__ src2 = s2t + group_elem + (size_t)s_first * kSlab * RS;
+    auto issue = [&](int s) {
+      if (s < n_slabs && lane == 0) {
+        const int st = s % kStages;
+        const bool own = s >= n_warm;  // the output coefficients are not needed while warming up
+        const bool spec = REPAIR && rejoin && own;  // the state to compare with travels with the slab (a dependent global load
+                                                    // per slab would cost more than the slab's recursion)
+        bq_mbar_expect_tx(bar0 + 8 * st, (own ? 2 * tile_bytes : tile_bytes) + (spec ? 256u : 0u));
+        bq_bulk_g2s(stage0 + st * kStageBytes, src1 + (size_t)s * (kSlab * RS), tile_bytes, bar0 + 8 * st);
+        if (own) bq_bulk_g2s(stage0 + st * kStageBytes + kTileBytes, src2 + (size_t)s * (kSlab * RS), tile_bytes, bar0 + 8 * st);
+        if (spec) bq_bulk_g2s(bq_smem_u32(spec_sm + st * 32), slab_group + (size_t)(s_first + s) * 32, 256u, bar0 + 8 * st);
+      }
+    };
+    for (int s = 0; s < kStages - 1; s++) issue(s);
+    for (int s = 0; s < n_slabs; s++) {
+      if (s == n_warm && !REPAIR) st_group[((size_t)blockIdx.y * 2 + 0) * 32 + lane] = make_float2(w1, w2);  // state at the segment's first own frame
+      __syncwarp();                // every lane is done reading the stage that is refilled next
+      issue(s + kStages - 1);
+      const int st = s % kStages;
+      bq_mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
+      phases ^= 1u << st;
+      const int64_t base = lo + (int64_t)(s_first + s) * kSlab;
+      const bool act = base >= my_lo && base < my_hi;  // silent-flagged quanta: state untouched (:103-108)
+      const bool own = s >= n_warm;
+      const float4* __restrict__ rows = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes) + ridx;               // [i][element]
+      const float4* __restrict__ outs = reinterpret_cast<const float4*>(lanes_smem + st * kStageBytes + kTileBytes) + ridx;  // (b0, b1, b2, -)
+      if (act) {
+        // 32 frames: all loads first, then the dependent chain from registers, so that the 30-cycle LDS latency is paid once per
+        // slab (the warp shares its SM sub-partition with at most one other); then y, off the critical path
         float x[32], p1[32], p2[32], wo[34];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          const float4 r = rows[(q * 32 + i) * RS];
+          const float4 r = rows[i * RS];
           x[i] = WIDE ? r.x : (right ? r.w : r.z);  // per row: (x, a1, a2, -); per voice: (a1, a2, xL, xR)
           p1[i] = WIDE ? r.y : r.x;
           p2[i] = WIDE ? r.z : r.y;
@@ -163,39 +160,81 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
           wo[i + 2] = w;
         }
         if (own) {
-          float* __restrict__ dst = my_sig + base + q * 32;
+          float* __restrict__ dst = my_sig + base;
 #pragma unroll
           for (int i4 = 0; i4 < 8; i4++) {
             float y[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
               const int i = 4 * i4 + e;
-              const float4 b = outs[(q * 32 + i) * RS];
+              const float4 b = outs[i * RS];
               y[e] = b.x * wo[i + 2] + b.y * wo[i + 1] + b.z * wo[i];  // :138  y = b0*w + b1*w1 + b2*w2
             }
             *reinterpret_cast<float4*>(dst + 4 * i4) = make_float4(y[0], y[1], y[2], y[3]);
           }
         }
       }
+      if (own) {
+        float2* rec = slab_group + (size_t)(s_first + s) * 32 + lane;
+        if (REPAIR && rejoin) {
+          const float2 spec = spec_sm[st * 32 + lane];
+          const bool same = __float_as_uint(spec.x) == __float_as_uint(w1) && __float_as_uint(spec.y) == __float_as_uint(w2);
+          if (__all_sync(0xffffffffu, same)) {
+            // re-joined: drain the stages already requested, so that the next run starts from quiescent barriers
+            for (int o = s + 1; o < n_slabs && o <= s + kStages - 1; o++) {
+              const int so = o % kStages;
+              bq_mbar_wait(bar0 + 8 * so, (phases >> so) & 1u);
+              phases ^= 1u << so;
+            }
+            __syncwarp();
+            return true;
+          }
+        }
+        *rec = make_float2(w1, w2);
+      }
+    }
+    return false;
+  };
+
+  if (!REPAIR) {
+    const int seg = (int)blockIdx.y;
+    const int s_own = seg * seg_slabs;
+    if (s_own >= total_slabs) return;
+    const int s_end = s_own + seg_slabs < total_slabs ? s_own + seg_slabs : total_slabs;
+    const int s_first = seg == 0 ? s_own : (s_own - kWarmSlabs > 0 ? s_own - kWarmSlabs : 0);
+    run(s_first, s_own - s_first, s_end, false);
+    st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
+  } else {
+    bool carry = false;
+    for (int seg = first_bad[blockIdx.x]; seg < n_seg; seg++) {
+      const int s_own = seg * seg_slabs;
+      if (s_own >= total_slabs) break;
+      if (!carry && !link_bad[(size_t)blockIdx.x * n_seg + seg]) continue;
+      if (!carry) {  // the last true state: what segment seg-1 ended with (verified, or repaired and re-joined before its end)
+        const float2 e = st_group[((size_t)(seg - 1) * 2 + 1) * 32 + lane];
+        w1 = e.x;
+        w2 = e.y;
+      }
+      const int s_end = s_own + seg_slabs < total_slabs ? s_own + seg_slabs : total_slabs;
+      carry = !run(s_own, 0, s_end, true);
     }
   }
-  if (!REPAIR) st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
 }
 
 // first_bad[g] = first segment k >= 1 whose speculative start state differs (bitwise, any of the 32 rows) from the state
-// segment k-1 ended with; n_seg if the whole chain verifies.  One warp per group.
-__global__ void __launch_bounds__(32) k_biquad_verify(int n_seg, const float2* __restrict__ states, int* __restrict__ first_bad) {
+// segment k-1 ended with (n_seg if the whole chain verifies); link_bad[g][k] says so for every link.  One warp per group.
+__global__ void __launch_bounds__(32) k_biquad_verify(int n_seg, const float2* __restrict__ states, int* __restrict__ first_bad,
+                                                      int* __restrict__ link_bad) {
   const int lane = threadIdx.x;
   const uint2* st = reinterpret_cast<const uint2*>(states) + (size_t)blockIdx.x * n_seg * 64;
   int bad = n_seg;
+  if (lane == 0) link_bad[(size_t)blockIdx.x * n_seg] = 0;
   for (int k = 1; k < n_seg; k++) {
     const uint2 e = st[((size_t)(k - 1) * 2 + 1) * 32 + lane];
     const uint2 b = st[((size_t)k * 2 + 0) * 32 + lane];
-    const bool differ = e.x != b.x || e.y != b.y;
-    if (__any_sync(0xffffffffu, differ)) {
-      bad = k;
-      break;
-    }
+    const bool differ = __any_sync(0xffffffffu, e.x != b.x || e.y != b.y);
+    if (differ && bad == n_seg) bad = k;
+    if (lane == 0) link_bad[(size_t)blockIdx.x * n_seg + k] = differ ? 1 : 0;
   }
   if (lane == 0) first_bad[blockIdx.x] = bad;
 }
@@ -215,8 +254,16 @@ int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs_out) {
   return n_seg;
 }
 
+// scratch sizes for launch_biquad: float2 elements (segment states + per-slab states) and ints (flags)
+void biquad_scratch_sizes(int n_jobs, int64_t n_frames, size_t* n_float2, size_t* n_int) {
+  const size_t groups = (size_t)((n_jobs + 15) / 16);
+  const int n_seg = biquad_lane_segments(n_jobs, n_frames, nullptr);
+  *n_float2 = groups * (size_t)n_seg * 64 + groups * (size_t)(n_frames / kSlab + 1) * 32;
+  *n_int = groups * 2 + groups * (size_t)n_seg;
+}
+
 void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,
-                         int* d_first_bad, const int* d_wide, cudaStream_t s) {
+                         int* d_flags, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_biquad_lanes<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
@@ -228,13 +275,17 @@ void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, 
   const unsigned groups = (unsigned)((n_jobs + 15) / 16);
   int seg_slabs = 0;
   const int n_seg = biquad_lane_segments(n_jobs, n_frames, &seg_slabs);
+  float2* d_slab = d_states + (size_t)groups * n_seg * 64;
+  int* d_first_bad = d_flags;
+  const int* d_wide = d_flags + groups;
+  int* d_link = d_flags + 2 * groups;
   // both stream layouts are launched; a CTA whose group uses the other layout exits at once
-  k_biquad_lanes<false, false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr, d_wide);
-  k_biquad_lanes<false, true><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, nullptr, d_wide);
+  k_biquad_lanes<false, false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, nullptr, d_wide, nullptr);
+  k_biquad_lanes<false, true><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, nullptr, d_wide, nullptr);
   if (n_seg > 1) {
-    k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad);
-    k_biquad_lanes<true, false><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad, d_wide);
-    k_biquad_lanes<true, true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_first_bad, d_wide);
+    k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad, d_link);
+    k_biquad_lanes<true, false><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, d_first_bad, d_wide, d_link);
+    k_biquad_lanes<true, true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, d_first_bad, d_wide, d_link);
   }
 }
 

@@ -1159,12 +1159,14 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         float2* dstates = nullptr;
         int* dbad = nullptr;
         const int n_seg = biquad_lane_segments((int)nk, env.Npad, nullptr);
-        if ((rc = env.scratch->alloc(&dstates, ((nk + 15) / 16) * (size_t)n_seg * 64))) return rc;
-        if ((rc = env.scratch->alloc(&dbad, 2 * ((nk + 15) / 16)))) return rc;
+        size_t n_f2 = 0, n_i = 0;
+        biquad_scratch_sizes((int)nk, env.Npad, &n_f2, &n_i);
+        if ((rc = env.scratch->alloc(&dstates, n_f2))) return rc;
+        if ((rc = env.scratch->alloc(&dbad, n_i))) return rc;
         int t = env.timer->begin(C_BIQUAD);
         launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, s2_all, dstates, dbad, ctx->stream);
         env.timer->end(t);
-        env.launches += n_seg > 1 ? 6 : 4;
+        env.launches += n_seg > 1 ? 9 : 6;
         CU(cudaGetLastError());
       }
     }

@@ -166,16 +166,16 @@ struct BiquadJob {
 //   d_s1t float4 [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  (x, a1, a2, -)
 //   d_s2t float4 [ceil(n_jobs/16)][n_frames/32][32 frames][32 rows]  (b0, b1, b2, -)
 // n_jobs <= 65535 per call.
-// d_states: float2 [ceil(n_jobs/16)][n_seg][2][32] and d_first_bad: int [2 * ceil(n_jobs/16)] (first failing link per group, then the
-// stream-layout flag per group), n_seg = biquad_lane_segments(...)
-// (the recursion runs as concurrent, verified time segments: biquad_lanes.cu header)
+// d_states (float2) and d_flags (int): scratch of the sizes biquad_scratch_sizes() reports (segment / slab states of the
+// speculative recursion, verification flags, stream-layout flags; layout: biquad_lanes.cu)
 int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs);
+void biquad_scratch_sizes(int n_jobs, int64_t n_frames, size_t* n_float2, size_t* n_int);
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
-                   int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_first_bad, cudaStream_t s);
+                   int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_flags, cudaStream_t s);
 
-// K3d alone (biquad_lanes.cu): the w recursion over the slab-transposed streams, TMA-fed
+// K3d alone (biquad_lanes.cu): the recursion over the slab-transposed streams, TMA-fed
 void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,
-                         int* d_first_bad, const int* d_wide, cudaStream_t s);
+                         int* d_flags, cudaStream_t s);
 
 struct MixJob {       // dst[c][n] = (((0 + src0) + src1) + ...) over active ranges, AudioNodeInput.cs:118-137
   float* dst[2];

@@ -276,25 +276,6 @@ def run_ours(args, wl):
     wall_ms_step = float(tmax[1]) / args.steps
     L.gac_graph_destroy(graph)
 
-    # ---- extra (N = 1): the offline-only partition option.  ConvolverNode hard-codes 128-frame partitions
-    # (ConvolverNode.cs:55) and the headline above keeps that; PartitionedConvolver itself takes the block size as a
-    # constructor argument (PartitionedConvolver.cs:37), and offline there is no latency reason for 128: with 512-frame
-    # partitions the same linear convolution needs 4x fewer MACs (different rounding points, same 1e-5 gate — tests/).
-    extra512 = None
-    if world == 1 and args.partition == 128 and not args.no_extra:
-        c5 = build_graph(G, wl, voices, device_id=local, tile_blocks=args.tile_blocks, partition=512, mac_variant=args.mac_variant)
-        g5 = c5._graph()
-        ms5 = []
-        for i in range(3 + min(args.steps, 20)):
-            check(L.gac_render_device(c5._h, g5, 0, n, C.c_void_p(d_out.data_ptr()), 2, 1))
-            check(L.gac_get_stats(c5._h, C.byref(st)))
-            if i >= 3:
-                ms5.append(st.ms_total)
-        L.gac_graph_destroy(g5)
-        c5.Dispose()
-        extra512 = {"ms_per_step": float(np.mean(ms5)), "value": wl["voices"] * wl["render_s"] / (float(np.mean(ms5)) * 1e-3),
-                    "unit": "voice-s/s", "note": "same workload with 512-frame partitions (offline-only option, not the headline)"}
-
     # ---- e2e arm: host arrays -> public API -> host result, everything inside the timed region.
     # Per step: a fresh OfflineAudioContext, PlayableAudioBuffer uploads (H2D from pinned host memory),
     # ConvolverNode.Buffer (IR preparation), Connect, Render (D2H of the result on the root).
@@ -393,8 +374,6 @@ def run_ours(args, wl):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        if extra512:
-            line["extra_partition_512"] = extra512
         line["e2e"]["async_upload"] = not args.sync_upload
         print(json.dumps(line))
     ctx.Dispose()
@@ -426,7 +405,7 @@ def main():
                     help="K6 algorithm (gac_context_desc.mac_variant): 0 default (second-level FFT), 1 streaming direct sum, 4 register-tiled direct sum")
     ap.add_argument("--cpu-voices", dest="cpu_voices", type=int, default=8)
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
-    ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the partition-512 extra measurement")
+    ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="(accepted for compatibility; there is no extra measurement any more)")
     ap.add_argument("--sync-upload", dest="sync_upload", action="store_true",
                     help="e2e arm: copy every buffer during gac_buffer_create (reference semantics) instead of GAC_FLAG_ASYNC_UPLOAD")
     args = ap.parse_args()

@@ -23,12 +23,13 @@ __device__ __forceinline__ float interp_linear(float v0, double t0, float v1, do
   float d = v1 - v0;
   return (float)((double)v0 + (double)d * u);
 }
-__device__ __forceinline__ float interp_exponential(float v0, double t0, float v1, double t1, double t) {  // :228-237
-  if (v0 <= 0.f || v1 <= 0.f) return interp_linear(v0, t0, v1, t1, t);
+// v0 * Math.Pow(v1 / v0, u) (:236) evaluated as v0 * exp(u * log(ratio)) with log(ratio) computed once per event interval
+// (`lr`, cached by the caller): within 2 ulp(double) of pow, i.e. the same float32 except on rounding ties, like the device's
+// own pow against glibc's; half the FP64 work of a pow per frame.
+__device__ __forceinline__ float interp_exponential(float v0, double t0, float v1, double t1, double t, double lr) {  // :228-237
   double u = (t - t0) / (t1 - t0);
   u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
-  float ratio = v1 / v0;
-  return (float)((double)v0 * pow((double)ratio, u));
+  return (float)((double)v0 * exp(u * lr));
 }
 __device__ __forceinline__ float set_target(const DevEvent& e, float base, double t) {  // :240-247
   double elapsed = t - e.time;
@@ -37,42 +38,66 @@ __device__ __forceinline__ float set_target(const DevEvent& e, float base, doubl
   float d = base - e.target;
   return (float)((double)e.target + (double)d * exp(-elapsed / tc));
 }
-// ComputeValueAtTime AudioParam.cs:169-217
-__device__ float value_at_time(float value, const DevEvent* __restrict__ ev, int count, double time) {
+// ComputeValueAtTime AudioParam.cs:169-217, split into "which event interval is `time` in" and "evaluate inside it" so that a
+// thread walking consecutive samples scans the event list once: `i` = first event with time < e.time (count = past the last),
+// `boundary` = value of the last non-SetTarget event before i (the param's static value if there is none).
+__device__ __forceinline__ void advance_interval(const DevEvent* __restrict__ ev, int count, double time, int& i, float& boundary) {
+  while (i < count && !(time < ev[i].time)) {
+    if (ev[i].type != 3) boundary = ev[i].value;
+    i++;
+  }
+}
+__device__ __forceinline__ float eval_interval(float value, const DevEvent* __restrict__ ev, int count, int i, float boundary, double time,
+                                               int& lr_i, double& lr) {
   if (count == 0) return value;
-  float boundary = value;
-  for (int i = 0; i < count; i++) {
+  if (i < count) {
+    if (i == 0) return boundary;
     const DevEvent e = ev[i];
-    if (time < e.time) {
-      if (i == 0) return boundary;
-      const DevEvent prev = ev[i - 1];
-      if (e.type == 1) return interp_linear(prev.value, prev.time, e.value, e.time, time);
-      if (e.type == 2) return interp_exponential(prev.value, prev.time, e.value, e.time, time);
-      if (prev.type == 3) return set_target(prev, boundary, time);
-      return prev.value;
+    const DevEvent prev = ev[i - 1];
+    if (e.type == 1) return interp_linear(prev.value, prev.time, e.value, e.time, time);
+    if (e.type == 2) {
+      if (prev.value <= 0.f || e.value <= 0.f) return interp_linear(prev.value, prev.time, e.value, e.time, time);  // :230-231
+      if (lr_i != i) {
+        const float ratio = e.value / prev.value;  // formed in float32 (:235)
+        lr = log((double)ratio);
+        lr_i = i;
+      }
+      return interp_exponential(prev.value, prev.time, e.value, e.time, time, lr);
     }
-    if (e.type != 3) boundary = e.value;
+    if (prev.type == 3) return set_target(prev, boundary, time);
+    return prev.value;
   }
   const DevEvent last = ev[count - 1];
   if (last.type == 3) return set_target(last, boundary, time);
   return last.value;
 }
 
+// a-rate: a thread evaluates 4 consecutive frames (one float4 store); k-rate: one quantum per thread
 __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__ jobs, const double* __restrict__ block_time,
                                                     int64_t n_quanta, int sample_rate) {
   const ParamJob job = jobs[blockIdx.y];
   const double dt = 1.0 / (double)sample_rate;  // AudioParam.cs:116
+  int i = 0, lr_i = -1;
+  double lr = 0.0;
+  float boundary = job.value;
   if (job.a_rate) {
-    int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t n = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (n >= n_quanta * 128) return;
-    int64_t b = n >> 7;
-    int i = (int)(n & 127);
-    double t = block_time[b] + (double)i * dt;  // :120
-    job.out[n] = value_at_time(job.value, job.events, job.n_events, t);
+    const double t0 = block_time[n >> 7];  // the four frames share a quantum (4 divides 128)
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const double t = t0 + (double)((int)(n & 127) + e) * dt;  // :120
+      advance_interval(job.events, job.n_events, t, i, boundary);
+      v[e] = eval_interval(job.value, job.events, job.n_events, i, boundary, t, lr_i, lr);
+    }
+    *reinterpret_cast<float4*>(job.out + n) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
-    int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (b >= n_quanta) return;
-    job.out[b] = value_at_time(job.value, job.events, job.n_events, block_time[b]);  // ComputeKRate :144-146
+    const double t = block_time[b];
+    advance_interval(job.events, job.n_events, t, i, boundary);
+    job.out[b] = eval_interval(job.value, job.events, job.n_events, i, boundary, t, lr_i, lr);  // ComputeKRate :144-146
   }
 }
 
@@ -80,7 +105,7 @@ void launch_param_eval(const ParamJob* d_jobs, int n_jobs, const double* d_block
   if (n_jobs <= 0 || n_quanta <= 0) return;
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    dim3 grid((unsigned)((n_quanta * 128 + 255) / 256), (unsigned)nj);
+    dim3 grid((unsigned)((n_quanta * 32 + 255) / 256), (unsigned)nj);  // a-rate: 4 frames per thread (k-rate jobs use the first CTAs)
     k_param_eval<<<grid, 256, 0, s>>>(d_jobs + j0, d_block_time, n_quanta, sample_rate);
   }
 }

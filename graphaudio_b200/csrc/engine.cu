@@ -1019,8 +1019,7 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     if ((rc = env.scratch->upload(&dcj, cj))) return rc;
     if ((rc = env.scratch->upload(&dij, ij))) return rc;
     int t = env.timer->begin(C_FFT_FWD);
-    if (B == 128) launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, Qs, ctx->d_tab16 + fft2_table_offset(128), ctx->d_tw, ctx->stream);
-    else launch_rfft_fwd_t(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
+    launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_MAC);
@@ -1028,8 +1027,7 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
-    if (B == 128) launch_irfft_ola_t8(dij, (int)ij.size(), QB, Qs, ctx->d_tab16 + fft2_table_offset(128), ctx->d_tw, ctx->stream);
-    else launch_irfft_ola_t(dij, (int)ij.size(), QB, B, Qs, ctx->d_tw, ctx->stream);
+    launch_irfft_ola_t8(dij, (int)ij.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
     env.timer->end(t);
     CU(cudaGetLastError());
     env.launches += 3;

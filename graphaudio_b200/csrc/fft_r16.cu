@@ -1,7 +1,8 @@
-// fft_r16.cu — K5 / K7 for 128-frame partitions (what ConvolverNode uses, Nodes/ConvolverNode.cs:55) with a radix-16
-// first-level transform: EIGHT threads per 128-point complex transform, 16 points per thread (fft2_core.cuh, plan M = 128:
-// stage A = one radix-16 butterfly over stride 8 + twiddles, one exchange through shared memory, stage C = two 8-point
-// transforms on the thread's 16 contiguous points).  The warp-per-transform kernels of fft.cu spend ~620 warp instructions
+// fft_r16.cu — K5 / K7 with a radix-16 first-level transform: H/16 threads per H-point complex transform, 16 points per thread
+// (fft2_core.cuh).  H = 128 frames per partition (what ConvolverNode uses, Nodes/ConvolverNode.cs:55): EIGHT threads per
+// transform, stage A = one radix-16 butterfly over stride 8 + twiddles, one exchange through shared memory, stage C = two 8-point
+// transforms on the thread's 16 contiguous points.  H = 256: 16 threads, stage C = one 16-point transform.  H = 512 (BASELINE
+// config 5): 32 threads, stages A and B (two exchanges) and a radix-2 stage C.  The warp-per-transform kernels of fft.cu spend ~620 warp instructions
 // per transform (radix-2 + five shuffle stages, ncu: 45 % issue utilisation, instruction-bound); this core needs ~5x fewer.
 //
 // Same arithmetic contract as fft.cu: Forward == numpy.fft.rfft of the zero-padded 256-frame block, Inverse == irfft +
@@ -13,49 +14,65 @@
 namespace gac {
 
 namespace {
-constexpr int H = 128;            // complex points per transform = frames per partition
-constexpr int TPT = 8;            // threads per transform
-constexpr int NTHR = 128;         // threads per CTA -> 16 transforms in flight, 4 per warp
-constexpr int ZS = 152;           // float2 per transform buffer: r16::smem_elems(128) = 144, +8 so that the four buffers of a warp
-                                  // start 64 bytes apart modulo 128 (half-warp = two transforms: conflict-free 64-bit accesses)
-constexpr int LD = 33;            // leading dimension of the [bin][block] tile (odd: conflict-free column access)
-constexpr int TILE = (H + 1) * LD + 1;  // float2, rounded to an even count (16-byte alignment of what follows)
+constexpr int NTHR = 128;         // threads per CTA
 
 __device__ __forceinline__ float2 cmul1(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cmulc1(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 
-// frequency index of register slot q of thread t after stage C (validated on the host: scratch/fft2_host_test.cu)
-__device__ __forceinline__ constexpr int slot_k(int t, int q) { return 2 * t + (q >> 3) + 16 * f2::rev3(q & 7); }
-// tile column of (warp w, group-in-warp gi, round): a bijection onto 0..31 chosen so that a half-warp's writes of one
-// bin-row pair land in 16 different bank pairs
-__device__ __forceinline__ int tile_col(int w, int gi, int rnd) { return 8 * gi + 2 * w + rnd; }
+// Geometry of the first-level transform of H complex points (H = frames per partition): T = H/16 threads per transform,
+// NTHR/T transforms in flight per CTA, two rounds per CTA -> COLS tile columns (blocks).
+template <int H>
+struct Geo {
+  static constexpr int T = H / 16;
+  static constexpr int GROUPS = NTHR / T;          // 16 / 8 / 4
+  static constexpr int COLS = 2 * GROUPS;          // 32 / 16 / 8
+  static constexpr int LD = COLS + 1;              // odd leading dimension of the [bin][block] tile: conflict-free column access
+  static constexpr int TILE = ((H + 1) * LD + 1) & ~1;  // float2, even count (16-byte alignment of what follows)
+  static constexpr int ZS = r16::Plan<H>::SE + 8;  // float2 per transform buffer; +8: neighbouring buffers start 64 bytes apart mod 128
+  // frequency index of register slot q of thread t after stage C (validated against a DFT on the host: scratch/fft2_host_test.cu)
+  __device__ __forceinline__ static constexpr int slot_k(int t, int q) {
+    return H == 128 ? 2 * t + (q >> 3) + 16 * f2::rev3(q & 7)
+           : H == 256 ? t + 16 * r16::rev4(q)
+                      : (t >> 1) + 16 * (8 * (t & 1) + (q >> 1)) + 256 * (q & 1);
+  }
+  // tile column of (group, round): a group's two columns are neighbours (K7 hands the even column's upper half to the odd one
+  // in registers).  H = 128: 8 gi + 2 w + rnd, chosen so that a half-warp's two transforms write 16 different bank pairs;
+  // H >= 256: a half-warp is one transform, any assignment is conflict-free.
+  __device__ __forceinline__ static int tile_col(int tid, int rnd) {
+    if (H == 128) return 8 * ((tid >> 3) & 3) + 2 * (tid >> 5) + rnd;
+    return 2 * (tid / T) + rnd;
+  }
+};
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K5: 32 consecutive blocks of one channel -> 129 rows x 32 columns of XT.
-// tab = radix-16 twiddle table of M = 128 ([4][8]); tw = split twiddles e^{-2 pi i k / 256}, k < 128.
+// K5: COLS consecutive blocks of one channel -> H+1 rows x COLS columns of XT.
+// tab = radix-16 twiddle table of M = H; tw = split twiddles e^{-2 pi i k / (2H)}, k < H.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHR, 4) k_rfft_fwd_t8(const FftFwdJob* __restrict__ jobs, const float2* __restrict__ tab,
-                                                         const float2* __restrict__ tw, int64_t ts) {
+template <int H>
+__global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const FftFwdJob* __restrict__ jobs, const float2* __restrict__ tab,
+                                                                        const float2* __restrict__ tw, int64_t ts) {
+  using G = Geo<H>;
+  constexpr int T = G::T, LD = G::LD, COLS = G::COLS;
   extern __shared__ __align__(16) float2 smem[];
-  float2* tileT = smem;         // [129][33]
-  float2* zb = smem + TILE;     // [16][ZS]
+  float2* tileT = smem;            // [H + 1][LD]
+  float2* zb = smem + G::TILE;     // [GROUPS][ZS]
   const FftFwdJob job = jobs[blockIdx.y];
   const int tid = threadIdx.x;
   const float sc = job.scale ? *job.scale : 1.0f;
-  const int64_t b0 = (int64_t)blockIdx.x * 32;
-  const int t = tid & 7, w = tid >> 5, gi = (tid >> 3) & 3;
-  float2* zg = zb + (tid >> 3) * ZS;
+  const int64_t b0 = (int64_t)blockIdx.x * COLS;
+  const int t = tid % T;
+  float2* zg = zb + (tid / T) * G::ZS;
 
   // Both rounds' input frames (and gain-table entries) are requested before anything is computed: 32 independent 8-byte
-  // loads in flight per thread.  Thread t of a group owns z[n] = x[2n] + i x[2n+1] for n = t + 8 j, j < 8.
+  // loads in flight per thread.  Thread t of a group owns z[n] = x[2n] + i x[2n+1] for n = t + T j, j < 8.
   float2 xin[2][8], gin[2][8];
 #pragma unroll
   for (int rnd = 0; rnd < 2; rnd++) {
-    const int64_t f0 = (b0 + tile_col(w, gi, rnd)) * H;
+    const int64_t f0 = (b0 + G::tile_col(tid, rnd)) * H;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const int64_t g = f0 + 2 * (t + 8 * j);
+      const int64_t g = f0 + 2 * (t + T * j);
       xin[rnd][j] = make_float2(0.f, 0.f);
       gin[rnd][j] = make_float2(job.gain_const, job.gain_const);
       if (g + 1 < job.n_valid) {  // n_valid is a multiple of the partition size on this path
@@ -66,14 +83,14 @@ __global__ void __launch_bounds__(NTHR, 4) k_rfft_fwd_t8(const FftFwdJob* __rest
   }
 #pragma unroll
   for (int rnd = 0; rnd < 2; rnd++) {
-    const int bl = tile_col(w, gi, rnd);
+    const int bl = G::tile_col(tid, rnd);
     const int64_t f0 = (b0 + bl) * H;
     // fused GainNode multiply (Nodes/GainNode.cs:49-58), silent-quantum gate, stereo -> mono down-mix (AudioNodeInput.cs:214-228),
-    // IR scale; the zero-padded upper half of the block (PartitionedConvolver.cs:107) gives z[n >= 64] = 0
+    // IR scale; the zero-padded upper half of the block (PartitionedConvolver.cs:107) gives z[n >= H/2] = 0
     float2 v[16];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const int64_t g = f0 + 2 * (t + 8 * j);
+      const int64_t g = f0 + 2 * (t + T * j);
       const bool open0 = g >= job.gate_lo && g < job.gate_hi, open1 = g + 1 >= job.gate_lo && g + 1 < job.gate_hi;
       float a0 = open0 ? __fmul_rn(xin[rnd][j].x, gin[rnd][j].x) : 0.f;
       float a1 = open1 ? __fmul_rn(xin[rnd][j].y, gin[rnd][j].y) : 0.f;
@@ -90,22 +107,26 @@ __global__ void __launch_bounds__(NTHR, 4) k_rfft_fwd_t8(const FftFwdJob* __rest
     }
     r16::fwd_a<H>(v, zg, tab, t);
     __syncwarp();
+    if constexpr (r16::Plan<H>::HAS_B) {
+      r16::fwd_b<H>(zg, tab, t);
+      __syncwarp();
+    }
     float2 u[16];
     r16::load16(u, zg, t);
-    r16::stage_c<8, false>(u);
+    r16::stage_c<r16::Plan<H>::L, false>(u);
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 16; q++) zg[slot_k(t, q)] = u[q];  // natural order Z[k]
+    for (int q = 0; q < 16; q++) zg[G::slot_k(t, q)] = u[q];  // natural order Z[k]
     __syncwarp();
-    // split step: E = (Z[k] + conj Z[H-k]) / 2 ; O = (Z[k] - conj Z[H-k]) / (2i) ; X[k] = E + e^{-2 pi i k / 256} O
+    // split step: E = (Z[k] + conj Z[H-k]) / 2 ; O = (Z[k] - conj Z[H-k]) / (2i) ; X[k] = E + e^{-2 pi i k / 2H} O
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      const int k = t + 8 * j;
+      const int k = t + T * j;
       const float2 a = zg[k];
       const float2 c = zg[(H - k) & (H - 1)];
       if (k == 0) {
         tileT[bl] = make_float2(a.x + a.y, 0.f);           // row 0: DC
-        tileT[H * LD + bl] = make_float2(a.x - a.y, 0.f);  // row 128: Nyquist
+        tileT[H * LD + bl] = make_float2(a.x - a.y, 0.f);  // row H: Nyquist
       } else {
         const float2 e = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
         const float2 o = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));
@@ -116,33 +137,36 @@ __global__ void __launch_bounds__(NTHR, 4) k_rfft_fwd_t8(const FftFwdJob* __rest
     __syncwarp();
   }
   __syncthreads();
-  for (int idx = tid; idx < (H + 1) * 32; idx += NTHR) {
-    const int row = idx >> 5, c = idx & 31;
+  for (int idx = tid; idx < (H + 1) * COLS; idx += NTHR) {
+    const int row = idx / COLS, c = idx % COLS;
     if (b0 + c < job.n_blocks) job.out[(int64_t)row * ts + b0 + c] = tileT[row * LD + c];
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K7: 31 consecutive blocks of one channel (tile columns 1..31) plus their predecessor (column 0) from YT; inverse
+// K7: COLS - 1 consecutive blocks of one channel (tile columns 1..COLS-1) plus their predecessor (column 0) from YT; inverse
 // transforms, overlap-add (PartitionedConvolver.cs:146-150: out[i] = (float)r[i] + overlap[i]; overlap[i] = (float)r[i+B]).
 // Every column's upper half goes to shared memory; after one barrier each column adds its left neighbour's.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kInvCols = 31;  // new blocks per CTA
+template <int H>
 __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restrict__ jobs, const float2* __restrict__ tab, const float2* __restrict__ tw,
                                                        int64_t ts) {
+  using G = Geo<H>;
+  constexpr int T = G::T, LD = G::LD, COLS = G::COLS;
   extern __shared__ __align__(16) float2 smem[];
-  float2* tileT = smem;                                // [129][33], column c <-> block b0 - 1 + c
-  float2* zb = smem + TILE;                            // [16][ZS]
-  float2* hi = zb + 16 * ZS;                           // [16][64]: upper halves r[B:2B] of the odd columns, as float2 pairs
+  float2* tileT = smem;                                // [H + 1][LD], column c <-> block b0 - 1 + c
+  float2* zb = smem + G::TILE;                         // [GROUPS][ZS]
+  float2* hi = zb + G::GROUPS * G::ZS;                 // [GROUPS][H/2]: upper halves r[B:2B] of the odd columns, as float2 pairs
   const FftInvJob job = jobs[blockIdx.y];
   const int tid = threadIdx.x;
-  const int64_t b0 = (int64_t)blockIdx.x * kInvCols;
+  const int64_t b0 = (int64_t)blockIdx.x * (COLS - 1);
   if (b0 >= job.n_blocks) return;
   {
     // tile load: thread = column cc of rows rr, rr + 4, ...  The whole 33 KB tile is put in flight at once with 8-byte
     // cp.async copies (LDGSTS, zero-filled outside the spectrogram): the kernel is latency-bound otherwise (ncu: 75 % of the
     // samples on long_scoreboard with register-staged loads).  True-stereo pairs need an add and take the register path.
-    const int cc = tid & 31, rr = tid >> 5;
+    constexpr int RSTEP = NTHR / COLS;  // rows covered per sweep
+    const int cc = tid % COLS, rr = tid / COLS;
     const int64_t bcol = b0 - 1 + cc;
     const bool col_ok = bcol >= 0 && bcol < job.n_blocks;
     if (!job.in2) {
@@ -150,18 +174,18 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
       const float2* src0 = job.in + (col_ok ? bcol : 0);
       const uint32_t nbytes = col_ok ? 8u : 0u;
 #pragma unroll 4
-      for (int row = rr; row <= H; row += 4)
+      for (int row = rr; row <= H; row += RSTEP)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst0 + (uint32_t)(row * LD * 8)), "l"(src0 + (int64_t)row * ts), "r"(nbytes)
                      : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
       constexpr int U = 8;
-      for (int r0 = rr; r0 <= H; r0 += 4 * U) {
+      for (int r0 = rr; r0 <= H; r0 += RSTEP * U) {
         float2 y[U], y2[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const int row = r0 + 4 * u;
+          const int row = r0 + RSTEP * u;
           y[u] = y2[u] = make_float2(0.f, 0.f);
           if (row <= H && col_ok) {
             y[u] = job.in[(int64_t)row * ts + bcol];
@@ -170,24 +194,24 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const int row = r0 + 4 * u;
+          const int row = r0 + RSTEP * u;
           if (row <= H) tileT[row * LD + cc] = make_float2(y[u].x + y2[u].x, y[u].y + y2[u].y);
         }
       }
     }
   }
   __syncthreads();
-  const int t = tid & 7, w = tid >> 5, gi = (tid >> 3) & 3;
-  float2* zg = zb + (tid >> 3) * ZS;
+  const int t = tid % T;
+  float2* zg = zb + (tid / T) * G::ZS;
   const float inv_h = 1.0f / (float)H;
   float2 lo[2][8], carry[8];
 #pragma unroll
   for (int rnd = 0; rnd < 2; rnd++) {
-    const int c = tile_col(w, gi, rnd);
-    // inverse split step: Z[k] = E + i O with E = (X[k] + conj X[H-k]) / 2, O = (X[k] - conj X[H-k]) / 2 * e^{+2 pi i k / 256}
+    const int c = G::tile_col(tid, rnd);
+    // inverse split step: Z[k] = E + i O with E = (X[k] + conj X[H-k]) / 2, O = (X[k] - conj X[H-k]) / 2 * e^{+2 pi i k / 2H}
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      const int k = t + 8 * j;
+      const int k = t + T * j;
       float2 z;
       if (k == 0) {
         const float x0 = tileT[c].x, xh = tileT[H * LD + c].x;  // DC, Nyquist
@@ -205,15 +229,19 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
     __syncwarp();
     float2 u[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) u[q] = zg[slot_k(t, q)];
+    for (int q = 0; q < 16; q++) u[q] = zg[G::slot_k(t, q)];
     __syncwarp();
-    r16::stage_c<8, true>(u);
+    r16::stage_c<r16::Plan<H>::L, true>(u);
     r16::store16(u, zg, t);
     __syncwarp();
+    if constexpr (r16::Plan<H>::HAS_B) {
+      r16::inv_b<H>(zg, tab, t);
+      __syncwarp();
+    }
     float2 v[16];
     r16::inv_a<H>(v, zg, tab, t);
     __syncwarp();
-    // v[j] = H * z[t + 8 j]; r[2n] = Re z[n], r[2n+1] = Im z[n]: n < 64 is the block's own half, n >= 64 the carried one.
+    // v[j] = H * z[t + T j]; r[2n] = Re z[n], r[2n+1] = Im z[n]: n < H/2 is the block's own half, n >= H/2 the carried one.
     // A group's two columns are neighbours (even c in round 0, c + 1 in round 1): the even column's upper half is handed over
     // in registers, only the odd column's goes through shared memory to the group that owns column c + 2.
 #pragma unroll
@@ -221,57 +249,78 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
       lo[rnd][j] = make_float2(v[j].x * inv_h, v[j].y * inv_h);
       const float2 up = make_float2(v[j + 8].x * inv_h, v[j + 8].y * inv_h);
       if (rnd == 0) carry[j] = up;
-      else hi[(c >> 1) * 64 + t + 8 * j] = up;
+      else hi[(c >> 1) * (H / 2) + t + T * j] = up;
     }
   }
   __syncthreads();
 #pragma unroll
   for (int rnd = 0; rnd < 2; rnd++) {
-    const int c = tile_col(w, gi, rnd);
+    const int c = G::tile_col(tid, rnd);
     const int64_t b = b0 - 1 + c;
     if (c >= 1 && b < job.n_blocks) {
       float* out = job.out + b * H;
       float* out2 = job.out2 ? job.out2 + b * H : nullptr;  // mono result duplicated (1 -> 2 up-mix copy at the next input)
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const float2 o = rnd == 1 ? carry[j] : hi[((c - 1) >> 1) * 64 + t + 8 * j];
+        const float2 o = rnd == 1 ? carry[j] : hi[((c - 1) >> 1) * (H / 2) + t + T * j];
         const float2 r = make_float2(lo[rnd][j].x + o.x, lo[rnd][j].y + o.y);
-        *reinterpret_cast<float2*>(out + 2 * (t + 8 * j)) = r;
-        if (out2) *reinterpret_cast<float2*>(out2 + 2 * (t + 8 * j)) = r;
+        *reinterpret_cast<float2*>(out + 2 * (t + T * j)) = r;
+        if (out2) *reinterpret_cast<float2*>(out2 + 2 * (t + T * j)) = r;
       }
     }
   }
 }
 
-constexpr size_t kFwdSmem = sizeof(float2) * (size_t)(TILE + 16 * ZS);
-constexpr size_t kInvSmem = sizeof(float2) * (size_t)(TILE + 16 * ZS + 16 * 64);
-
-void launch_rfft_fwd_t8(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab128, const float2* d_tw,
-                        cudaStream_t s) {
-  if (n_jobs <= 0 || max_blocks <= 0) return;
+template <int H>
+static void fwd_launch(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
+  using G = Geo<H>;
+  constexpr size_t smem = sizeof(float2) * (size_t)(G::TILE + G::GROUPS * G::ZS);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_rfft_fwd_t8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    cudaFuncSetAttribute(k_rfft_fwd_t8<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    dim3 grid((unsigned)((max_blocks + 31) / 32), (unsigned)nj);
-    k_rfft_fwd_t8<<<grid, NTHR, kFwdSmem, s>>>(d_jobs + j0, d_tab128, d_tw, t_stride);
+    dim3 grid((unsigned)((max_blocks + G::COLS - 1) / G::COLS), (unsigned)nj);
+    k_rfft_fwd_t8<H><<<grid, NTHR, smem, s>>>(d_jobs + j0, d_tab, d_tw, t_stride);
   }
 }
-void launch_irfft_ola_t8(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab128, const float2* d_tw,
-                         cudaStream_t s) {
-  if (n_jobs <= 0 || max_blocks <= 0) return;
+template <int H>
+static void inv_launch(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
+  using G = Geo<H>;
+  constexpr size_t smem = sizeof(float2) * (size_t)(G::TILE + G::GROUPS * G::ZS + G::GROUPS * (H / 2));
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_irfft_ola_t8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInvSmem);
+    cudaFuncSetAttribute(k_irfft_ola_t8<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    dim3 grid((unsigned)((max_blocks + kInvCols - 1) / kInvCols), (unsigned)nj);
-    k_irfft_ola_t8<<<grid, NTHR, kInvSmem, s>>>(d_jobs + j0, d_tab128, d_tw, t_stride);
+    dim3 grid((unsigned)((max_blocks + G::COLS - 2) / (G::COLS - 1)), (unsigned)nj);
+    k_irfft_ola_t8<H><<<grid, NTHR, smem, s>>>(d_jobs + j0, d_tab, d_tw, t_stride);
+  }
+}
+
+// d_tab16 = the concatenated radix-16 twiddle tables (fft2.cu); B = 128, 256 or 512 frames per partition
+void launch_rfft_fwd_t8(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tab16, const float2* d_tw,
+                        cudaStream_t s) {
+  if (n_jobs <= 0 || max_blocks <= 0) return;
+  const float2* tab = d_tab16 + fft2_table_offset(B);
+  switch (B) {
+    case 128: fwd_launch<128>(d_jobs, n_jobs, max_blocks, t_stride, tab, d_tw, s); break;
+    case 256: fwd_launch<256>(d_jobs, n_jobs, max_blocks, t_stride, tab, d_tw, s); break;
+    case 512: fwd_launch<512>(d_jobs, n_jobs, max_blocks, t_stride, tab, d_tw, s); break;
+  }
+}
+void launch_irfft_ola_t8(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tab16, const float2* d_tw,
+                         cudaStream_t s) {
+  if (n_jobs <= 0 || max_blocks <= 0) return;
+  const float2* tab = d_tab16 + fft2_table_offset(B);
+  switch (B) {
+    case 128: inv_launch<128>(d_jobs, n_jobs, max_blocks, t_stride, tab, d_tw, s); break;
+    case 256: inv_launch<256>(d_jobs, n_jobs, max_blocks, t_stride, tab, d_tw, s); break;
+    case 512: inv_launch<512>(d_jobs, n_jobs, max_blocks, t_stride, tab, d_tw, s); break;
   }
 }
 

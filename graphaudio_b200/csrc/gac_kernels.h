@@ -94,10 +94,10 @@ int fft2_h2_row_elems(int M);
 // d_tw2: the 8192-entry table (radix-8 plan, M = 8192); d_tab16: the concatenated radix-16 tables (M = 512 .. 4096)
 int fft2_table_total();              // float2 entries of the concatenated radix-16 tables
 int fft2_table_offset(int M);        // where M's table starts (M = 128, 256: the first-level transforms of fft_r16.cu)
-// K5 / K7 for 128-frame partitions with the radix-16 first-level core (fft_r16.cu); same job structs and layouts as the _t launchers
-void launch_rfft_fwd_t8(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab128, const float2* d_tw,
+// K5 / K7 with the radix-16 first-level core (fft_r16.cu; B = 128, 256, 512); same job structs and layouts as the _t launchers
+void launch_rfft_fwd_t8(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tab16, const float2* d_tw,
                         cudaStream_t s);
-void launch_irfft_ola_t8(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab128, const float2* d_tw,
+void launch_irfft_ola_t8(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tab16, const float2* d_tw,
                          cudaStream_t s);
 void fft2_fill_tables(float2* host);  // fills them (double precision, rounded once)
 void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tw2, const float2* d_tab16, int64_t n_blocks,

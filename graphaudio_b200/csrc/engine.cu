@@ -714,6 +714,11 @@ struct RenderEnv {
   int mac_used = 0;                     // K6 variant of the last convolver batch (1 stream, 2/4 tiled, 3 second-level FFT)
   std::map<Sig*, std::pair<const float*, float>> fused;  // GainNode folded into the next convolver's forward FFT
   std::map<std::string, float*> param_tables;  // automation tables already evaluated in this render, by (rate, value, events)
+  // automation tables are carved out of chunks (one stream-ordered allocation per 16 tables) and the events of a batch of
+  // parameter jobs travel in one upload: a driver call per table and per event list costs more than evaluating them
+  float* tab_chunk = nullptr;
+  size_t tab_left = 0;
+  std::vector<DevEvent>* ev_host = nullptr;
 };
 
 static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector<ParamJob>& jobs, float** out_table) {
@@ -734,21 +739,26 @@ static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector
     *out_table = hit->second;
     return GAC_OK;
   }
-  float* tab = nullptr;
-  int rc = env.scratch->alloc(&tab, a_rate ? (size_t)env.Npad : (size_t)env.NQ);
-  if (rc) return rc;
+  const size_t need = (((a_rate ? (size_t)env.Npad : (size_t)env.NQ) + 63) / 64) * 64;  // 256-byte aligned slices
+  if (env.tab_left < need) {
+    const size_t chunk = std::max(need, (size_t)16 * (size_t)env.Npad);
+    int rc = env.scratch->alloc(&env.tab_chunk, chunk);
+    if (rc) return rc;
+    env.tab_left = chunk;
+  }
+  float* tab = env.tab_chunk;
+  env.tab_chunk += need;
+  env.tab_left -= need;
   env.param_tables[key] = tab;
-  auto& hev = env.keep->make<DevEvent>();
-  hev.resize(p.ev.size());
+  if (!env.ev_host) env.ev_host = &env.keep->make<DevEvent>();
   static_assert(sizeof(DevEvent) == sizeof(gac_event), "event layout");
-  memcpy(hev.data(), p.ev.data(), sizeof(gac_event) * p.ev.size());
-  DevEvent* dev = nullptr;
-  rc = env.scratch->upload(&dev, hev);
-  if (rc) return rc;
+  const size_t off = env.ev_host->size();
+  env.ev_host->resize(off + p.ev.size());
+  memcpy(env.ev_host->data() + off, p.ev.data(), sizeof(gac_event) * p.ev.size());
   ParamJob j;
   j.value = p.value;
   j.n_events = (int)p.ev.size();
-  j.events = dev;
+  j.events = reinterpret_cast<const DevEvent*>(off);  // offset into the batch's event block; made a pointer by run_param_jobs
   j.out = tab;
   j.a_rate = a_rate ? 1 : 0;
   jobs.push_back(j);
@@ -758,10 +768,15 @@ static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector
 
 static int run_param_jobs(RenderEnv& env, std::vector<ParamJob>& jobs) {
   if (jobs.empty()) return GAC_OK;
+  DevEvent* dev = nullptr;
+  int rc = env.scratch->upload(&dev, *env.ev_host);
+  if (rc) return rc;
+  env.ev_host = nullptr;  // the next batch starts its own block (this one stays alive in `keep`)
   auto& hj = env.keep->make<ParamJob>();
   hj = jobs;
+  for (ParamJob& j : hj) j.events = dev + reinterpret_cast<size_t>(j.events);
   ParamJob* dj = nullptr;
-  int rc = env.scratch->upload(&dj, hj);
+  rc = env.scratch->upload(&dj, hj);
   if (rc) return rc;
   int t = env.timer->begin(C_AUTO);
   // a-rate and k-rate jobs share a launch; the kernel branches per job

@@ -128,19 +128,20 @@ def make_inputs(wl, rank, pinned):
     alloc = None
     if pinned:
         import torch
-        def alloc(n):  # noqa: E306
-            return torch.empty(n, dtype=torch.float32, pin_memory=True).numpy()
+        def alloc(rows, n):  # noqa: E306  one page-locked block per buffer, the channels are its rows
+            return torch.empty((rows, n), dtype=torch.float32, pin_memory=True).numpy()
     voices = []
     for i in range(V):
         v = rank * V + i
         src, ir = synth.make_voice_inputs(v, nsrc, nir)
         if alloc:
-            ps, pi = [], []
-            for a in src:
-                b = alloc(a.shape[0]); b[:] = a; ps.append(b)
-            for a in ir:
-                b = alloc(a.shape[0]); b[:] = a; pi.append(b)
-            src, ir = ps, pi
+            ps = alloc(len(src), src[0].shape[0])
+            pi = alloc(len(ir), ir[0].shape[0])
+            for c, a in enumerate(src):
+                ps[c, :] = a
+            for c, a in enumerate(ir):
+                pi[c, :] = a
+            src, ir = [ps[c] for c in range(len(src))], [pi[c] for c in range(len(ir))]
         voices.append((src, ir, synth.voice_gains(v)))
     return voices
 

@@ -459,8 +459,16 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
   CU(cudaMallocAsync(&b->d, sizeof(float) * b->stride * n_channels, st));
   // the slack behind each channel is never read: k_source_copy stays inside [0, n) and the resampler's taps are the last
   // four CONSUMED frames (k + 3 <= n - 1)
-  for (int c = 0; c < n_channels; c++)
-    CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, st));
+  bool contiguous = n_channels > 1 && n_frames > 0;
+  for (int c = 1; c < n_channels && contiguous; c++) contiguous = channels[c] == channels[c - 1] + n_frames;
+  if (contiguous) {
+    // the channel arrays are rows of one host block (a pinned staging buffer): one strided copy instead of one per channel
+    CU(cudaMemcpy2DAsync(b->d, sizeof(float) * b->stride, channels[0], sizeof(float) * n_frames, sizeof(float) * n_frames, (size_t)n_channels,
+                         cudaMemcpyHostToDevice, st));
+  } else {
+    for (int c = 0; c < n_channels; c++)
+      CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, st));
+  }
   if (async) {
     b->ready = take_event(ctx);
     CU(cudaEventRecord(b->ready, st));

@@ -28,7 +28,9 @@ struct Geo {
   static constexpr int COLS = 2 * GROUPS;          // 32 / 16 / 8
   static constexpr int LD = COLS + 1;              // odd leading dimension of the [bin][block] tile: conflict-free column access
   static constexpr int TILE = ((H + 1) * LD + 1) & ~1;  // float2, even count (16-byte alignment of what follows)
-  static constexpr int ZS = r16::Plan<H>::SE + 8;  // float2 per transform buffer; +8: neighbouring buffers start 64 bytes apart mod 128
+  // float2 per transform buffer: the padded extent r16::pad(H - 1) + 1 rounded up to 16, plus 8 so that neighbouring buffers start
+  // 64 bytes apart modulo 128 (H = 128: a half-warp is two transforms, their 64-bit accesses must not share banks): 152 / 312 / 616
+  static constexpr int ZS = (((H - 1) + 2 * ((H - 1) >> 4) + 8 * ((H - 1) >> 7) + 1 + 15) & ~15) + 8;
   // frequency index of register slot q of thread t after stage C (validated against a DFT on the host: scratch/fft2_host_test.cu)
   __device__ __forceinline__ static constexpr int slot_k(int t, int q) {
     return H == 128 ? 2 * t + (q >> 3) + 16 * f2::rev3(q & 7)
@@ -156,7 +158,8 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
   extern __shared__ __align__(16) float2 smem[];
   float2* tileT = smem;                                // [H + 1][LD], column c <-> block b0 - 1 + c
   float2* zb = smem + G::TILE;                         // [GROUPS][ZS]
-  float2* hi = zb + G::GROUPS * G::ZS;                 // [GROUPS][H/2]: upper halves r[B:2B] of the odd columns, as float2 pairs
+  float2* hi = zb + G::GROUPS * G::ZS;                 // [GROUPS][HS]: upper halves r[B:2B] of the odd columns, as float2 pairs
+  constexpr int HS = H / 2 + 8;                        // (+8: two groups of a half-warp 64 bytes apart modulo 128)
   const FftInvJob job = jobs[blockIdx.y];
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * (COLS - 1);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
       lo[rnd][j] = make_float2(v[j].x * inv_h, v[j].y * inv_h);
       const float2 up = make_float2(v[j + 8].x * inv_h, v[j + 8].y * inv_h);
       if (rnd == 0) carry[j] = up;
-      else hi[(c >> 1) * (H / 2) + t + T * j] = up;
+      else hi[(c >> 1) * HS + t + T * j] = up;
     }
   }
   __syncthreads();
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
       float* out2 = job.out2 ? job.out2 + b * H : nullptr;  // mono result duplicated (1 -> 2 up-mix copy at the next input)
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const float2 o = rnd == 1 ? carry[j] : hi[((c - 1) >> 1) * (H / 2) + t + T * j];
+        const float2 o = rnd == 1 ? carry[j] : hi[((c - 1) >> 1) * HS + t + T * j];
         const float2 r = make_float2(lo[rnd][j].x + o.x, lo[rnd][j].y + o.y);
         *reinterpret_cast<float2*>(out + 2 * (t + T * j)) = r;
         if (out2) *reinterpret_cast<float2*>(out2 + 2 * (t + T * j)) = r;
@@ -289,7 +292,7 @@ static void fwd_launch(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, 
 template <int H>
 static void inv_launch(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
   using G = Geo<H>;
-  constexpr size_t smem = sizeof(float2) * (size_t)(G::TILE + G::GROUPS * G::ZS + G::GROUPS * (H / 2));
+  constexpr size_t smem = sizeof(float2) * (size_t)(G::TILE + G::GROUPS * G::ZS + G::GROUPS * (H / 2 + 8));
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_irfft_ola_t8<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

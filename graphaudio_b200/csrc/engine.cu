@@ -704,6 +704,9 @@ extern "C" int gac_graph_destroy(gac_graph* g) {
 // ------------------------------------------------------------------------------------------ render
 struct Sig {
   float* p[2];
+  // not yet materialised: frames [lo, hi) of the signal are read in place from the source buffer (lazy[c][n] for n in [lo, hi));
+  // set for rate-1 sources that feed a convolver directly (or through a fused GainNode), so that no copy of the source is made
+  const float* lazy[2] = {nullptr, nullptr};
   int64_t lo = 0, hi = 0;  // frames flagged non-silent (multiples of 128)
   int ch = 2;              // logical channel count of the block the reference would carry here (rows are always 2; mono = duplicated)
   const std::vector<OpH>* ops = nullptr;
@@ -1223,6 +1226,9 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         wait_ready_ir(ctx, ir);
         auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
         auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(ir->M2)) : (const float2*)nullptr; };
+        const float* in0 = s.lazy[0] ? s.lazy[0] : s.p[0];
+        const float* in1 = s.lazy[0] ? s.lazy[1] : s.p[1];
+        s.lazy[0] = s.lazy[1] = nullptr;  // the convolver's output is written to the signal's own rows
         ConvItem it;
         it.P = ir->P;
         it.M2 = ir->d_H2 ? ir->M2 : 0;
@@ -1235,7 +1241,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           // input forced to 1 channel (ConvolverNode.cs:72-76): a stereo upstream is down-mixed (L + R) * (1/sqrt(2)),
           // a mono upstream is taken as is (AudioNodeInput.cs:188-228); the mono result is copied to both rows
           it.n_fwd = 1;
-          it.fwd[0] = {s.p[0], s.ch == 2 ? s.p[1] : nullptr, 1.0f / sqrtf(2.0f)};
+          it.fwd[0] = {in0, s.ch == 2 ? in1 : nullptr, 1.0f / sqrtf(2.0f)};
           it.n_mac = 1;
           it.mac[0] = {0, Hch(0), H2ch(0)};
           it.n_inv = 1;
@@ -1243,8 +1249,8 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           s.ch = 1;
         } else if (ir->nch == 2) {
           it.n_fwd = 2;
-          it.fwd[0] = {s.p[0], nullptr, 1.0f};
-          it.fwd[1] = {s.p[1], nullptr, 1.0f};
+          it.fwd[0] = {in0, nullptr, 1.0f};
+          it.fwd[1] = {in1, nullptr, 1.0f};
           it.n_mac = 2;
           it.mac[0] = {0, Hch(0), H2ch(0)};
           it.mac[1] = {1, Hch(1), H2ch(1)};
@@ -1255,8 +1261,8 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         } else {
           // true stereo (ConvolverNode.cs:127-144): L = c0(inL) + c2(inR), R = c1(inL) + c3(inR); X spectra shared
           it.n_fwd = 2;
-          it.fwd[0] = {s.p[0], nullptr, 1.0f};
-          it.fwd[1] = {s.p[1], nullptr, 1.0f};
+          it.fwd[0] = {in0, nullptr, 1.0f};
+          it.fwd[1] = {in1, nullptr, 1.0f};
           it.n_mac = 4;
           it.mac[0] = {0, Hch(0), H2ch(0)};
           it.mac[1] = {1, Hch(2), H2ch(2)};

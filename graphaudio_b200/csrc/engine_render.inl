@@ -81,7 +81,19 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
       job.n_emit = nb * 128;
       s.lo = job.out0;
       s.hi = job.out0 + job.n_emit;
-      cj.push_back(job);
+      // A convolver (second-level-FFT path) that follows directly, or behind a GainNode that is fused into its forward
+      // transform, reads the source buffer in place: K5 only touches frames inside [lo, hi), which map into the buffer.
+      const std::vector<OpH>& ops = v.ops;
+      const OpH* conv = nullptr;
+      if (!ops.empty() && ops[0].kind == GAC_OP_CONVOLVER) conv = &ops[0];
+      else if (ops.size() > 1 && ops[0].kind == GAC_OP_GAIN && ops[1].kind == GAC_OP_CONVOLVER) conv = &ops[1];
+      const bool in_place = conv && conv->ir && conv->ir->d_H2 && nb > 0 && ((job.pos0 - job.out0) % 2 == 0);
+      if (in_place) {
+        s.lazy[0] = src0 + (job.pos0 - job.out0);
+        s.lazy[1] = src1 + (job.pos0 - job.out0);
+      } else {
+        cj.push_back(job);
+      }
     } else {
       const int64_t avail = durEnd - pos;
       const int64_t n_out_max = max_blocks * 128;

@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
       const int64_t g = f0 + 2 * (t + T * j);
       xin[rnd][j] = make_float2(0.f, 0.f);
       gin[rnd][j] = make_float2(job.gain_const, job.gain_const);
-      if (g + 1 < job.n_valid) {  // n_valid is a multiple of the partition size on this path
+      // n_valid is a multiple of the partition size on this path; frames outside the non-silent range [gate_lo, gate_hi)
+      // (multiples of 128) read as zero and are NOT loaded: `in` may alias a source buffer that only covers that range
+      if (g + 1 < job.n_valid && g >= job.gate_lo && g < job.gate_hi) {
         xin[rnd][j] = *reinterpret_cast<const float2*>(job.in + g);
         if (job.gain) gin[rnd][j] = *reinterpret_cast<const float2*>(job.gain + g);
       }
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
       float a1 = open1 ? __fmul_rn(xin[rnd][j].y, gin[rnd][j].y) : 0.f;
       if (job.in2) {
         float2 y = make_float2(0.f, 0.f);
-        if (g + 1 < job.n_valid) y = *reinterpret_cast<const float2*>(job.in2 + g);
+        if (g + 1 < job.n_valid && g >= job.gate_lo && g < job.gate_hi) y = *reinterpret_cast<const float2*>(job.in2 + g);
         const float c0 = open0 ? __fmul_rn(y.x, gin[rnd][j].x) : 0.f;
         const float c1 = open1 ? __fmul_rn(y.y, gin[rnd][j].y) : 0.f;
         a0 = __fmul_rn(__fadd_rn(a0, c0), job.mix_scale);

@@ -12,7 +12,7 @@
 // factor 1/M is folded into the prepared IR spectra.
 //
 // The code is written as per-thread PHASES with no barrier inside: a kernel calls the phases with __syncthreads()
-// between them, and a host harness (scratch/fft2_host_test.cu) replays them thread by thread to validate the index
+// between them, and a host harness (tools/fft2_host_test.cu) replays them thread by thread to validate the index
 // algebra without a GPU.
 #pragma once
 #include <cuda_runtime.h>

@@ -31,7 +31,7 @@ struct Geo {
   // float2 per transform buffer: the padded extent r16::pad(H - 1) + 1 rounded up to 16, plus 8 so that neighbouring buffers start
   // 64 bytes apart modulo 128 (H = 128: a half-warp is two transforms, their 64-bit accesses must not share banks): 152 / 312 / 616
   static constexpr int ZS = (((H - 1) + 2 * ((H - 1) >> 4) + 8 * ((H - 1) >> 7) + 1 + 15) & ~15) + 8;
-  // frequency index of register slot q of thread t after stage C (validated against a DFT on the host: scratch/fft2_host_test.cu)
+  // frequency index of register slot q of thread t after stage C (validated against a DFT on the host: tools/fft2_host_test.cu)
   __device__ __forceinline__ static constexpr int slot_k(int t, int q) {
     return H == 128 ? 2 * t + (q >> 3) + 16 * f2::rev3(q & 7)
            : H == 256 ? t + 16 * r16::rev4(q)

@@ -46,15 +46,12 @@ __device__ __forceinline__ void bq_bulk_g2s(uint32_t dst, const void* src, uint3
                "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void bq_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
 
 constexpr int kSlab = 32;    // frames per pipeline stage = one 32-frame layout slab
 constexpr int kStages = 3;   // stages in flight (96 KB per CTA: two CTAs, i.e. two concurrent segments, per SM)
 constexpr int kWarmSlabs = 256;  // warm-up of a speculative segment: 256 * 32 = 8192 frames
 constexpr int kLaneSlots = 2 * 148;  // concurrent single-warp CTAs
-constexpr int kTileBytes = kSlab * 32 * 16;   // one stream's stage: 32 KB
+constexpr int kTileBytes = kSlab * 32 * 16;   // one stream's stage in the per-row layout: 16 KB (8 KB per voice)
 constexpr int kStageBytes = 2 * kTileBytes;   // (x, a1, a2) tile + (b0, b1, b2) tile
 constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64 + kStages * 256;  // stages, barriers, staged speculative states (repair)
 

@@ -492,11 +492,6 @@ extern "C" int gac_buffer_destroy(gac_buffer* buf) {
 }
 
 // ------------------------------------------------------------------------------------------ IR prepare (K0)
-static int upload_now(gac_context* ctx, void* dst, const void* src, size_t bytes) {
-  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return GAC_OK;
-}
-
 // `st` = the stream the preparation runs on (the context stream, or the preparation stream in async mode)
 static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir,
                              cudaStream_t st) {

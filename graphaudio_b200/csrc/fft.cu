@@ -104,20 +104,13 @@ constexpr int kFftWarps = 4;  // warps (= concurrent transforms) per CTA
 // K5 forward: block b of job -> packed spectrum row b.
 // grid = (ceil(max_blocks / (kFftWarps*BLOCKS_PER_WARP)), n_jobs)
 // --------------------------------------------------------------------------------------------
-template <int LOG2H, int BPW, bool TR = false>
-__device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2* __restrict__ tw, int64_t ts = 0);
+template <int LOG2H, int BPW>
+__device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2* __restrict__ tw);
 
 template <int LOG2H, int BPW>
 __global__ void __launch_bounds__(kFftWarps * 32) k_rfft_fwd(const FftFwdJob* __restrict__ jobs, const float2* __restrict__ tw) {
   const FftFwdJob job = jobs[blockIdx.y];
   rfft_fwd_body<LOG2H, BPW>(job, tw);
-}
-// transposing variant: the CTA's kFftWarps*BPW spectra are staged in shared memory as [bin][block] and stored as rows of
-// the transposed spectrogram XT[k][b] (fft2.cu), one contiguous run of kFftWarps*BPW blocks per bin
-template <int LOG2H, int BPW>
-__global__ void __launch_bounds__(kFftWarps * 32) k_rfft_fwd_t(const FftFwdJob* __restrict__ jobs, const float2* __restrict__ tw, int64_t ts) {
-  const FftFwdJob job = jobs[blockIdx.y];
-  rfft_fwd_body<LOG2H, BPW, true>(job, tw, ts);
 }
 // same transform, jobs described arithmetically (no job array in HBM): channel y of one buffer.  Used by IR preparation.
 template <int LOG2H, int BPW>
@@ -137,12 +130,10 @@ __global__ void __launch_bounds__(kFftWarps * 32) k_rfft_fwd_uniform(FftFwdUnifo
   rfft_fwd_body<LOG2H, BPW>(job, tw);
 }
 
-template <int LOG2H, int BPW, bool TR>
-__device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2* __restrict__ tw, int64_t ts) {
+template <int LOG2H, int BPW>
+__device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2* __restrict__ tw) {
   using F = WarpFft<LOG2H>;
   constexpr int H = F::H, R = F::R;
-  constexpr int TBK = kFftWarps * BPW, LD = TBK + 1;  // transposed staging tile [H + 1][LD]
-  extern __shared__ float2 tileT[];
   __shared__ float2 tile[kFftWarps][H + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   F fft;
@@ -151,50 +142,6 @@ __device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2
 #pragma unroll
   for (int j = 0; j < R; j++) twk[j] = tw[lane + 32 * j];
   const float sc = job.scale ? *job.scale : 1.0f;
-
-  // TR: the CTA's TBK*H input frames are staged in shared memory first — float4 loads, four groups in flight per thread —
-  // with the gain / silent-gate / down-mix / scale arithmetic applied on the way (same operations, same order as below)
-  float* xs = reinterpret_cast<float*>(tileT + (((H + 1) * LD + 1) & ~1));  // [TBK][H], 16-byte aligned
-  if constexpr (TR) {
-    const int64_t f0 = (int64_t)blockIdx.x * TBK * H;
-    constexpr int NG = TBK * H / 4, U = 4, NT = kFftWarps * 32;
-    for (int i0 = threadIdx.x; i0 < NG; i0 += NT * U) {
-      float4 x[U], gn[U], y[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int i = i0 + NT * u;
-        const int64_t g = f0 + 4 * (int64_t)i;
-        x[u] = y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        gn[u] = make_float4(job.gain_const, job.gain_const, job.gain_const, job.gain_const);
-        if (i < NG && g + 3 < job.n_valid) {  // (n_valid is a multiple of the partition size on this path)
-          x[u] = *reinterpret_cast<const float4*>(job.in + g);
-          if (job.gain) gn[u] = *reinterpret_cast<const float4*>(job.gain + g);
-          if (job.in2) y[u] = *reinterpret_cast<const float4*>(job.in2 + g);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int i = i0 + NT * u;
-        if (i >= NG) continue;
-        const int64_t g = f0 + 4 * (int64_t)i;
-        const float xe[4] = {x[u].x, x[u].y, x[u].z, x[u].w}, ge[4] = {gn[u].x, gn[u].y, gn[u].z, gn[u].w},
-                    ye[4] = {y[u].x, y[u].y, y[u].z, y[u].w};
-        float r[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const bool open = g + e >= job.gate_lo && g + e < job.gate_hi;
-          float a = open ? __fmul_rn(xe[e], ge[e]) : 0.f;
-          if (job.in2) {
-            const float b2 = open ? __fmul_rn(ye[e], ge[e]) : 0.f;
-            a = __fmul_rn(__fadd_rn(a, b2), job.mix_scale);
-          }
-          r[e] = a * sc;
-        }
-        *reinterpret_cast<float4*>(xs + 4 * i) = make_float4(r[0], r[1], r[2], r[3]);
-      }
-    }
-    __syncthreads();
-  }
 
   int64_t b_first = ((int64_t)blockIdx.x * kFftWarps + warp) * BPW;
   for (int bi = 0; bi < BPW; bi++) {
@@ -209,9 +156,7 @@ __device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2
       if (j < R / 2 || R == 1) {
         int n = j * 32 + lane;
         float2 x = make_float2(0.f, 0.f);
-        if constexpr (TR) {
-          if (R > 1 || n < H / 2) x = *reinterpret_cast<const float2*>(xs + (warp * BPW + bi) * H + 2 * n);
-        } else if (R > 1 || n < H / 2) {
+        if (R > 1 || n < H / 2) {
           int64_t g = base + 2 * n;
           if (g + 1 < job.n_valid) {
             x = *reinterpret_cast<const float2*>(in + 2 * n);
@@ -263,25 +208,7 @@ __device__ __forceinline__ void rfft_fwd_body(const FftFwdJob& job, const float2
         float2 wo = cmul(twk[j], o);
         r = make_float2(e.x + wo.x, e.y + wo.y);
       }
-      if constexpr (TR) {
-        const int bl = warp * BPW + bi;
-        if (k == 0) {
-          tileT[bl] = make_float2(r.x, 0.f);           // row 0: DC
-          tileT[H * LD + bl] = make_float2(r.y, 0.f);  // row B: Nyquist
-        } else {
-          tileT[k * LD + bl] = r;
-        }
-      } else {
-        out[k] = r;
-      }
-    }
-  }
-  if constexpr (TR) {
-    __syncthreads();
-    const int64_t b0 = (int64_t)blockIdx.x * TBK;
-    for (int idx = threadIdx.x; idx < (H + 1) * TBK; idx += kFftWarps * 32) {
-      const int row = idx / TBK, c = idx % TBK;
-      if (b0 + c < job.n_blocks) job.out[(int64_t)row * ts + b0 + c] = tileT[row * LD + c];
+      out[k] = r;
     }
   }
 }
@@ -372,196 +299,6 @@ __global__ void __launch_bounds__(kFftWarps * 32) k_irfft_ola(const FftInvJob* _
 #pragma unroll
         for (int j = 0; j < HALF; j++) *reinterpret_cast<float2*>(out2 + 2 * (lane + 32 * j)) = lo[j];
       }
-    }
-  }
-}
-
-// --------------------------------------------------------------------------------------------
-// K7, transposing variant: reads the transposed spectrogram YT[k][b] produced by fft2.cu.  A CTA stages the columns
-// [b0-1, b0+TBK) (TBK = kFftWarps*BPW blocks and their predecessor) in shared memory; each warp inverse-transforms BPW
-// consecutive blocks carrying the upper half in registers; the upper half that crosses a warp boundary is handed over
-// through shared memory, so only warp 0 re-derives a predecessor (one extra transform per TBK).
-// --------------------------------------------------------------------------------------------
-template <int LOG2H, int BPW>
-__global__ void __launch_bounds__(kFftWarps * 32) k_irfft_ola_t(const FftInvJob* __restrict__ jobs, const float2* __restrict__ tw, int64_t ts) {
-  using F = WarpFft<LOG2H>;
-  constexpr int H = F::H, R = F::R;
-  constexpr int TBK = kFftWarps * BPW, NC = TBK + 1, LD = NC | 1;  // odd leading dimension: conflict-free column reads
-  extern __shared__ float2 tileT[];                 // [H + 1][LD], column c <-> block b0 - 1 + c
-  __shared__ float2 tile[kFftWarps][H + 4];
-  constexpr int HALF = (R >= 2) ? R / 2 : 1;
-  __shared__ float2 ovs[kFftWarps][HALF * 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const FftInvJob job = jobs[blockIdx.y];
-  const int64_t b0 = (int64_t)blockIdx.x * TBK;
-  if (b0 >= job.n_blocks) return;
-  // tile load: a thread owns the column cc of the rows rr, rr + RS, ...; eight independent loads are in flight per thread
-  // before anything is stored (the loop is latency-bound otherwise)
-  {
-    constexpr int RS = (kFftWarps * 32) / TBK;     // rows covered per sweep (TBK <= 32 columns per row)
-    const int cc = threadIdx.x % TBK, rr = threadIdx.x / TBK;
-    const int64_t bcol = b0 + cc;
-    const bool col_ok = bcol < job.n_blocks;
-    constexpr int U = 8;
-    for (int r0 = rr; r0 <= H; r0 += RS * U) {
-      float2 y[U], y2[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int row = r0 + RS * u;
-        y[u] = y2[u] = make_float2(0.f, 0.f);
-        if (row <= H && col_ok) {
-          y[u] = job.in[(int64_t)row * ts + bcol];
-          if (job.in2) y2[u] = job.in2[(int64_t)row * ts + bcol];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int row = r0 + RS * u;
-        if (row <= H) tileT[row * LD + cc + 1] = make_float2(y[u].x + y2[u].x, y[u].y + y2[u].y);
-      }
-    }
-    // column 0: the predecessor block b0 - 1 (zero before the first block)
-    for (int row = threadIdx.x; row <= H; row += kFftWarps * 32) {
-      float2 y = make_float2(0.f, 0.f);
-      if (b0 > 0) {
-        y = job.in[(int64_t)row * ts + b0 - 1];
-        if (job.in2) {
-          const float2 y2 = job.in2[(int64_t)row * ts + b0 - 1];
-          y = make_float2(y.x + y2.x, y.y + y2.y);
-        }
-      }
-      tileT[row * LD] = y;
-    }
-  }
-  F fft;
-  fft.init(tw, lane);
-  float2 twk[R];
-#pragma unroll
-  for (int j = 0; j < R; j++) twk[j] = tw[lane + 32 * j];
-  float2 ov[HALF];
-#pragma unroll
-  for (int j = 0; j < HALF; j++) ov[j] = make_float2(0.f, 0.f);
-  const float inv_h = 1.0f / (float)H;
-  __syncthreads();
-  // inverse transform of tile column c: lo[] = float32(r[0:B]) + ov, ov <- float32(r[B:2B])
-  auto pass = [&](int c, float2 (&lo)[HALF]) {
-    float2 v[R];
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      const int k = lane + 32 * j;
-      float2 z;
-      if (k == 0) {
-        const float x0 = tileT[c].x, xh = tileT[H * LD + c].x;  // DC, Nyquist
-        z = make_float2(0.5f * (x0 + xh), 0.5f * (x0 - xh));
-      } else {
-        const float2 a = tileT[k * LD + c];
-        const float2 cc = tileT[(H - k) * LD + c];
-        float2 e = make_float2(0.5f * (a.x + cc.x), 0.5f * (a.y - cc.y));
-        float2 d = make_float2(0.5f * (a.x - cc.x), 0.5f * (a.y + cc.y));
-        float2 o = cmul_conj(d, twk[j]);
-        z = make_float2(e.x - o.y, e.y + o.x);
-      }
-      v[j] = z;
-    }
-    fft.template run<true>(v, lane);
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < R; j++) tile[warp][F::out_index(j, lane)] = make_float2(v[j].x * inv_h, v[j].y * inv_h);
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < HALF; j++) {
-      const float2 r = tile[warp][lane + 32 * j];
-      lo[j] = make_float2(r.x + ov[j].x, r.y + ov[j].y);
-      ov[j] = tile[warp][H / 2 + lane + 32 * j];
-    }
-    __syncwarp();
-  };
-  auto emit = [&](int64_t b, const float2 (&lo)[HALF]) {
-    float* out = job.out + b * H;
-#pragma unroll
-    for (int j = 0; j < HALF; j++) *reinterpret_cast<float2*>(out + 2 * (lane + 32 * j)) = lo[j];
-    if (job.out2) {
-      float* out2 = job.out2 + b * H;
-#pragma unroll
-      for (int j = 0; j < HALF; j++) *reinterpret_cast<float2*>(out2 + 2 * (lane + 32 * j)) = lo[j];
-    }
-  };
-  float2 first_lo[HALF];
-#pragma unroll
-  for (int j = 0; j < HALF; j++) first_lo[j] = make_float2(0.f, 0.f);
-  if (warp == 0) {
-    float2 dummy[HALF];
-    pass(0, dummy);  // the tile's predecessor block (zero column when b0 == 0): only its upper half matters
-  }
-  const int64_t bw = b0 + warp * BPW;  // this warp's first block
-  for (int bi = 0; bi < BPW; bi++) {
-    const int64_t b = bw + bi;
-    if (b >= job.n_blocks) break;
-    float2 lo[HALF];
-    pass(warp * BPW + bi + 1, lo);
-    if (bi == 0 && warp > 0) {
-#pragma unroll
-      for (int j = 0; j < HALF; j++) first_lo[j] = lo[j];
-    } else {
-      emit(b, lo);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < HALF; j++) ovs[warp][lane + 32 * j] = ov[j];
-  __syncthreads();
-  if (warp > 0 && bw < job.n_blocks) {
-#pragma unroll
-    for (int j = 0; j < HALF; j++) {
-      const float2 o = ovs[warp - 1][lane + 32 * j];
-      first_lo[j] = make_float2(first_lo[j].x + o.x, first_lo[j].y + o.y);
-    }
-    emit(bw, first_lo);
-  }
-}
-
-template <int LOG2H, int BPW>
-static void launch_fwd_tt(const FftFwdJob* jobs, int n_jobs, int64_t max_blocks, int64_t ts, const float2* tw, cudaStream_t s) {
-  constexpr int H = 1 << LOG2H, TBK = kFftWarps * BPW;
-  constexpr size_t smem = sizeof(float2) * (size_t)((((H + 1) * (TBK + 1)) + 1) & ~1) + sizeof(float) * (size_t)TBK * H;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_rfft_fwd_t<LOG2H, BPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
-  dim3 grid((unsigned)((max_blocks + TBK - 1) / TBK), (unsigned)n_jobs);
-  k_rfft_fwd_t<LOG2H, BPW><<<grid, kFftWarps * 32, smem, s>>>(jobs, tw, ts);
-}
-template <int LOG2H, int BPW>
-static void launch_inv_tt(const FftInvJob* jobs, int n_jobs, int64_t max_blocks, int64_t ts, const float2* tw, cudaStream_t s) {
-  constexpr int H = 1 << LOG2H, TBK = kFftWarps * BPW;
-  constexpr size_t smem = sizeof(float2) * (size_t)(H + 1) * ((TBK + 1) | 1);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_irfft_ola_t<LOG2H, BPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
-  dim3 grid((unsigned)((max_blocks + TBK - 1) / TBK), (unsigned)n_jobs);
-  k_irfft_ola_t<LOG2H, BPW><<<grid, kFftWarps * 32, smem, s>>>(jobs, tw, ts);
-}
-void launch_rfft_fwd_t(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tw, cudaStream_t s) {
-  if (n_jobs <= 0 || max_blocks <= 0) return;
-  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
-    int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    switch (B) {
-      case 128: launch_fwd_tt<7, 8>(d_jobs + j0, nj, max_blocks, t_stride, d_tw, s); break;
-      case 256: launch_fwd_tt<8, 4>(d_jobs + j0, nj, max_blocks, t_stride, d_tw, s); break;
-      case 512: launch_fwd_tt<9, 2>(d_jobs + j0, nj, max_blocks, t_stride, d_tw, s); break;
-    }
-  }
-}
-void launch_irfft_ola_t(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tw, cudaStream_t s) {
-  if (n_jobs <= 0 || max_blocks <= 0) return;
-  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
-    int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    switch (B) {
-      case 128: launch_inv_tt<7, 8>(d_jobs + j0, nj, max_blocks, t_stride, d_tw, s); break;
-      case 256: launch_inv_tt<8, 4>(d_jobs + j0, nj, max_blocks, t_stride, d_tw, s); break;
-      case 512: launch_inv_tt<9, 2>(d_jobs + j0, nj, max_blocks, t_stride, d_tw, s); break;
     }
   }
 }

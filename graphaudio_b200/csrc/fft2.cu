@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(M / 8) k_fft2_conv(const Fft2Job* __restrict__
                                                      int64_t xs, int64_t ys) {
   using P = Plan<M>;
   constexpr int T = P::T;
-  extern __shared__ __align__(16) float2 sm[];
+  extern __shared__ __align__(128) float2 sm[];
   const Fft2Job job = jobs[blockIdx.z];
   const int seg = blockIdx.x;
   if (seg >= job.nseg) return;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(M / 8) k_fft2_prep(const float2* __restrict__ 
                                                      const float2* __restrict__ tw) {
   using Pl = Plan<M>;
   constexpr int T = Pl::T;
-  extern __shared__ __align__(16) float2 sm[];
+  extern __shared__ __align__(128) float2 sm[];
   const int k = blockIdx.x, ch = blockIdx.y, t = threadIdx.x;
   const float2* __restrict__ Hc = H + (int64_t)ch * h_ch_stride;
   const int col = (k == B) ? 0 : k;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(M / 16) k_fft2_prep16(const float2* __restrict
                                                         const float2* __restrict__ tab) {
   using Pl = r16::Plan<M>;
   constexpr int T = Pl::T;
-  extern __shared__ __align__(16) float2 sm[];
+  extern __shared__ __align__(128) float2 sm[];
   const int k = blockIdx.x, ch = blockIdx.y, t = threadIdx.x;
   const float2* __restrict__ Hc = H + (int64_t)ch * h_ch_stride;
   const int col = (k == B) ? 0 : k;

@@ -29,9 +29,6 @@ struct FftFwdJob {
   float mix_scale = 1.0f;
 };
 void launch_rfft_fwd(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
-// transposing variant (feeds fft2.cu): job.out is the XT channel base; bin k of block b lands at out[k*t_stride + b],
-// k = 0..B (row 0 = (DC, 0), row B = (Nyquist, 0))
-void launch_rfft_fwd_t(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tw, cudaStream_t s);
 // the same transform for the channels of ONE buffer, described arithmetically and passed by value (no job array upload)
 struct FftFwdUniform {
   const float* in_base;     // channel y at in_base + y*in_stride
@@ -51,9 +48,6 @@ struct FftInvJob {
   float* out2 = nullptr;        // optional second destination receiving the same samples (mono -> both rows)
 };
 void launch_irfft_ola(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
-// transposing variant: job.in / job.in2 are YT channel bases (bin k of block b at in[k*t_stride + b], k = 0..B); with in2 the
-// two spectrograms are summed BEFORE the inverse transform (the transform is linear; ConvolverNode.Sum adds afterwards)
-void launch_irfft_ola_t(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tw, cudaStream_t s);
 
 // ------------------------------------------------------------------ spectral MAC (mac.cu)
 // One job = one channel-convolver bin-group of 128 bins:  Y[b][k] = sum_p X[b-p][k] * H[p][k].
@@ -94,7 +88,10 @@ int fft2_h2_row_elems(int M);
 // d_tw2: the 8192-entry table (radix-8 plan, M = 8192); d_tab16: the concatenated radix-16 tables (M = 512 .. 4096)
 int fft2_table_total();              // float2 entries of the concatenated radix-16 tables
 int fft2_table_offset(int M);        // where M's table starts (M = 128, 256: the first-level transforms of fft_r16.cu)
-// K5 / K7 with the radix-16 first-level core (fft_r16.cu; B = 128, 256, 512); same job structs and layouts as the _t launchers
+// K5 / K7 over the TRANSPOSED spectrograms of fft2.cu, radix-16 first-level core (fft_r16.cu; B = 128, 256, 512).  Same job
+// structs as above, but job.out / job.in / job.in2 are XT / YT channel bases: bin k of block b lives at base[k*t_stride + b],
+// k = 0..B (row 0 = (DC, 0), row B = (Nyquist, 0)); with in2 the two spectrograms are summed BEFORE the inverse transform (the
+// transform is linear; ConvolverNode.Sum adds afterwards)
 void launch_rfft_fwd_t8(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tab16, const float2* d_tw,
                         cudaStream_t s);
 void launch_irfft_ola_t8(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, int64_t t_stride, const float2* d_tab16, const float2* d_tw,

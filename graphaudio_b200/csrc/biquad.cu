@@ -206,99 +206,115 @@ __device__ __forceinline__ Coef rbj_shared(const BiquadJob& job, int32_t k, floa
   return c;
 }
 
+constexpr int kResSlabs = 16;  // 32-frame slabs per CTA of k_biquad_resolve
 __global__ void __launch_bounds__(512) k_biquad_resolve(const BiquadJob* __restrict__ jobs, int n_jobs, int sample_rate, int64_t n_quanta,
                                                         int64_t n_frames, const int32_t* __restrict__ ent_base, float4* __restrict__ s1t,
                                                         float4* __restrict__ s2t, const int* __restrict__ wide_flags) {
   __shared__ float4 tile[32][33];
   __shared__ float4 tile2[32][33];
-  const int jv = threadIdx.x >> 5, i = threadIdx.x & 31;
-  const int64_t slab = blockIdx.x;
-  const int g = blockIdx.y;
-  const int jid = g * 16 + jv;
-  const int64_t n = slab * 32 + i;
-  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, u0 = v0, u1 = v0;
   // Voices of a group very often run the SAME filter automation (one table, deduplicated by the engine, or the same constants):
-  // then the coefficient set of (frame, selected frame k) is the same for all of them, and only the group's first voice
-  // evaluates RBJ; the others take it from shared memory when their parameters and their selected frame coincide with its.
-  __shared__ int32_t lead_k[32];
-  __shared__ float lead_c[5][32];
-  const bool in_range = jid < n_jobs && n >= jobs[jid].lo && n < jobs[jid].hi;  // warp-uniform: ranges are multiples of 128 frames
-  int32_t k0 = -1, k1 = -1;
-  if (in_range) {
-    const BiquadJob& job = jobs[jid];
-    k0 = job.idx[n];
-    k1 = job.idx[n_frames + n];
-    if (k0 < 0) k0 = ent_base[((size_t)jid * 2 + 0) * n_quanta + (n >> 7)];
-    if (k1 < 0) k1 = ent_base[((size_t)jid * 2 + 1) * n_quanta + (n >> 7)];
-  }
+  // then the coefficient set of (frame, selected frame k) is the same for all of them.  Phase 1: warp w evaluates RBJ for the
+  // group's FIRST voice over slab w of the CTA's 16 slabs (all 16 warps busy with the expensive part at once); phase 2: slab by
+  // slab, warp = voice copies the first voice's set when its parameters and its selected frame coincide, and evaluates its own
+  // otherwise.
+  __shared__ int32_t lead_k[kResSlabs][32];
+  __shared__ float lead_c[kResSlabs][5][32];
+  const int w = threadIdx.x >> 5, i = threadIdx.x & 31;
+  const int g = blockIdx.y;
+  const int64_t slab0 = (int64_t)blockIdx.x * kResSlabs;
+  const int64_t n_slabs = n_frames / 32;
   const float nyq = (float)sample_rate / 2.f;
-  Coef c0;
-  c0.b0 = c0.b1 = c0.b2 = c0.a1 = c0.a2 = 0.f;
-  if (jv == 0) {
-    if (in_range) c0 = rbj_shared(jobs[jid], k0, nyq, sample_rate);
-    lead_k[i] = in_range ? k0 : INT32_MIN;
-    lead_c[0][i] = c0.b0;
-    lead_c[1][i] = c0.b1;
-    lead_c[2][i] = c0.b2;
-    lead_c[3][i] = c0.a1;
-    lead_c[4][i] = c0.a2;
+  {
+    const int64_t n = (slab0 + w) * 32 + i;
+    const BiquadJob& lead = jobs[g * 16];
+    int32_t k0 = INT32_MIN;
+    Coef c;
+    c.b0 = c.b1 = c.b2 = c.a1 = c.a2 = 0.f;
+    if (slab0 + w < n_slabs && n >= lead.lo && n < lead.hi) {  // warp-uniform: ranges are multiples of 128 frames
+      k0 = lead.idx[n];
+      if (k0 < 0) k0 = ent_base[((size_t)(g * 16) * 2 + 0) * n_quanta + (n >> 7)];
+      c = rbj_shared(lead, k0, nyq, sample_rate);
+    }
+    lead_k[w][i] = k0;
+    lead_c[w][0][i] = c.b0;
+    lead_c[w][1][i] = c.b1;
+    lead_c[w][2][i] = c.b2;
+    lead_c[w][3][i] = c.a1;
+    lead_c[w][4][i] = c.a2;
   }
   __syncthreads();
-  if (in_range) {
+  const int jv = w;
+  const int jid = g * 16 + jv;
+  const bool wide = wide_flags[g] != 0;
+  const size_t group_base = (size_t)g * (size_t)n_frames * 32;
+  bool same_params = false;
+  if (jid < n_jobs) {
     const BiquadJob& job = jobs[jid];
-    if (jv != 0) {
-      const BiquadJob& lead = jobs[g * 16];
-      const bool same_params = job.type == lead.type && job.freq == lead.freq && job.q == lead.q && job.gain == lead.gain &&
-                               job.freq_const == lead.freq_const && job.q_const == lead.q_const && job.gain_const == lead.gain_const;
-      const bool reuse = same_params && k0 == lead_k[i];
+    const BiquadJob& lead = jobs[g * 16];
+    same_params = job.type == lead.type && job.freq == lead.freq && job.q == lead.q && job.gain == lead.gain &&
+                  job.freq_const == lead.freq_const && job.q_const == lead.q_const && job.gain_const == lead.gain_const;
+  }
+  for (int sl = 0; sl < kResSlabs; sl++) {
+    const int64_t slab = slab0 + sl;
+    if (slab >= n_slabs) break;  // uniform for the CTA
+    const int64_t n = slab * 32 + i;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, u0 = v0, u1 = v0;
+    const bool in_range = jid < n_jobs && n >= jobs[jid].lo && n < jobs[jid].hi;  // warp-uniform
+    if (in_range) {
+      const BiquadJob& job = jobs[jid];
+      int32_t k0 = job.idx[n], k1 = job.idx[n_frames + n];
+      if (k0 < 0) k0 = ent_base[((size_t)jid * 2 + 0) * n_quanta + (n >> 7)];
+      if (k1 < 0) k1 = ent_base[((size_t)jid * 2 + 1) * n_quanta + (n >> 7)];
+      Coef c0;
+      const bool reuse = same_params && k0 == lead_k[sl][i];
       if (__all_sync(0xffffffffu, reuse)) {
-        c0.b0 = lead_c[0][i];
-        c0.b1 = lead_c[1][i];
-        c0.b2 = lead_c[2][i];
-        c0.a1 = lead_c[3][i];
-        c0.a2 = lead_c[4][i];
+        c0.b0 = lead_c[sl][0][i];
+        c0.b1 = lead_c[sl][1][i];
+        c0.b2 = lead_c[sl][2][i];
+        c0.a1 = lead_c[sl][3][i];
+        c0.a2 = lead_c[sl][4][i];
       } else {
         c0 = rbj_shared(job, k0, nyq, sample_rate);
       }
+      Coef c1 = c0;
+      if (__any_sync(0xffffffffu, k1 != k0)) {
+        const Coef alt = rbj_shared(job, k1, nyq, sample_rate);
+        if (k1 != k0) c1 = alt;
+      }
+      v0 = make_float4(job.sig[0][n], c0.a1, c0.a2, 0.f);
+      v1 = make_float4(job.sig[1][n], c1.a1, c1.a2, 0.f);
+      u0 = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
+      u1 = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
+    } else if (jid < n_jobs && n < n_frames) {
+      jobs[jid].sig[0][n] = 0.f;
+      jobs[jid].sig[1][n] = 0.f;
     }
-    Coef c1 = c0;
-    if (__any_sync(0xffffffffu, k1 != k0)) {
-      const Coef alt = rbj_shared(job, k1, nyq, sample_rate);
-      if (k1 != k0) c1 = alt;
-    }
-    v0 = make_float4(job.sig[0][n], c0.a1, c0.a2, 0.f);
-    v1 = make_float4(job.sig[1][n], c1.a1, c1.a2, 0.f);
-    u0 = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
-    u1 = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
-  } else if (jid < n_jobs && n < n_frames) {
-    jobs[jid].sig[0][n] = 0.f;
-    jobs[jid].sig[1][n] = 0.f;
-  }
-  const size_t group_base = (size_t)g * (size_t)n_frames * 32;
-  if (wide_flags[g]) {
-    // per-row layout: tile[frame][row] -> S1T / S2T [g][slab][frame][row 0..31], element e = frame * 32 + row
-    tile[i][2 * jv] = v0;
-    tile[i][2 * jv + 1] = v1;
-    tile2[i][2 * jv] = u0;
-    tile2[i][2 * jv + 1] = u1;
-    __syncthreads();
-    float4* dst = s1t + group_base + (size_t)slab * 1024;
-    float4* dst2 = s2t + group_base + (size_t)slab * 1024;
+    if (wide) {
+      // per-row layout: tile[frame][row] -> S1T / S2T [g][slab][frame][row 0..31], element e = frame * 32 + row
+      tile[i][2 * jv] = v0;
+      tile[i][2 * jv + 1] = v1;
+      tile2[i][2 * jv] = u0;
+      tile2[i][2 * jv + 1] = u1;
+      __syncthreads();
+      float4* dst = s1t + group_base + (size_t)slab * 1024;
+      float4* dst2 = s2t + group_base + (size_t)slab * 1024;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int e = threadIdx.x + 512 * h;
-      dst[e] = tile[e >> 5][e & 31];
-      dst2[e] = tile2[e >> 5][e & 31];
+      for (int h = 0; h < 2; h++) {
+        const int e = threadIdx.x + 512 * h;
+        dst[e] = tile[e >> 5][e & 31];
+        dst2[e] = tile2[e >> 5][e & 31];
+      }
+    } else {
+      // per-voice layout (both channels share the coefficient set at every frame of this group):
+      // S1T [g][slab][frame][voice 0..15] = (a1, a2, xL, xR), S2T = (b0, b1, b2, -): half the bytes of the per-row layout
+      tile[i][jv] = make_float4(v0.y, v0.z, v0.x, v1.x);
+      tile2[i][jv] = u0;
+      __syncthreads();
+      const int e = threadIdx.x;  // element e = frame * 16 + voice
+      s1t[group_base + (size_t)slab * 512 + e] = tile[e >> 4][e & 15];
+      s2t[group_base + (size_t)slab * 512 + e] = tile2[e >> 4][e & 15];
     }
-  } else {
-    // per-voice layout (both channels share the coefficient set at every frame of this group):
-    // S1T [g][slab][frame][voice 0..15] = (a1, a2, xL, xR), S2T = (b0, b1, b2, -): half the bytes of the per-row layout
-    tile[i][jv] = make_float4(v0.y, v0.z, v0.x, v1.x);
-    tile2[i][jv] = u0;
-    __syncthreads();
-    const int e = threadIdx.x;  // element e = frame * 16 + voice
-    s1t[group_base + (size_t)slab * 512 + e] = tile[e >> 4][e & 15];
-    s2t[group_base + (size_t)slab * 512 + e] = tile2[e >> 4][e & 15];
+    __syncthreads();  // the tiles are rewritten by the next slab
   }
 }
 
@@ -311,7 +327,7 @@ void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_
   cudaMemsetAsync(d_wide, 0, sizeof(int) * groups, s);
   k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_jobs), kSelWarps * 32, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last, d_wide);
   k_biquad_entry<<<(unsigned)n_jobs, 32, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
-  k_biquad_resolve<<<dim3(n_slabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t, d_wide);
+  k_biquad_resolve<<<dim3((n_slabs + kResSlabs - 1) / kResSlabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t, d_wide);
   launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_flags, s);
 }
 

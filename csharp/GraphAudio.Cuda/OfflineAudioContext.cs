@@ -38,8 +38,12 @@ public sealed unsafe class OfflineAudioContext : IDisposable
             if (output[ch].Length < startIndex + frameCount)
                 throw new ArgumentException($"Channel {ch} buffer is too small. Required: {startIndex + frameCount}, Available: {output[ch].Length}", nameof(output));
         }
-        // GraphFlattener walks Destination <- bus chain <- fan-in <- voice chains <- sources (connection order preserved)
-        // and pins the event arrays; see Flatten() in graphaudio_cuda.hpp for the algorithm.
+        // GraphFlattener cuts the recorded node graph into what the ABI (v3) knows — voices (chains fed by a source), buses (a
+        // node with several inputs plus the chain behind it; `Target` = destination / parent bus) and chains fed by a bus
+        // output (a node whose output fans out ends a bus) — with the connection order of every fan-in preserved, and pins
+        // the event arrays.  The algorithm is the one of graphaudio_b200/api.py::_topology_full (tested against the oracle on
+        // ReverbEffect / AudioBus shaped graphs, tests/test_gpu_graphs.py); Flatten() in graphaudio_cuda.hpp is its C++ twin for
+        // the flat source -> chain -> bus -> destination shape.
         using var flat = GraphFlattener.Flatten(this);
         Native.Check(Native.GraphCreate(Handle, flat.Desc, out IntPtr graph));
         try

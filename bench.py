@@ -353,7 +353,7 @@ def run_ours(args, wl):
             "samples_per_s": V * 2 * n / (dev_ms_step * 1e-3),
             "wall_ms_per_step": wall_ms_step,
             "e2e": {"value": V * wl["render_s"] / (e2e_ms * 1e-3), "unit": "voice-s/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, **({"note": e2e_note} if e2e_note else {})},
+                    "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes, **({"note": e2e_note} if e2e_note else {})},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "clocks": clocks,
             # the dominant kernel against the HBM roofline: bytes the implemented algorithm has to move per launch (XT, H2, YT once;

@@ -127,7 +127,7 @@ def test_mixed_ir_lengths_in_one_render():
     assert np.abs(yg - yo).max() <= TOL
 
 
-@pytest.mark.parametrize("partition", [128, 512])
+@pytest.mark.parametrize("partition", [128, 256, 512])
 def test_c5_resampled_source_second_level_fft(partition):
     G, O = _apis()
     fs, src_rate = 96000, 44100

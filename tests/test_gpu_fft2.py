@@ -203,3 +203,41 @@ def test_long_ir_at_96k_through_the_render_path(partition):
     assert np.abs(yo).max() > 1e-2
     assert np.abs(yg - yo).max() <= TOL
     g.Dispose()
+
+
+@pytest.mark.parametrize("when,offset,duration", [
+    (0.0, 0.0, None),          # read in place from frame 0
+    (0.011, 0.0, None),        # starts in block 4: the alias pointer sits before the buffer start, only [lo, hi) is touched
+    (0.0, 0.0101, None),       # even buffer offset (484 frames): in place
+    (0.0, 0.01002083, None),   # odd buffer offset (481 frames): falls back to the copy
+    (0.004, 0.0025, 0.2),      # duration-limited playback, the tail of the buffer is never read
+])
+def test_sources_read_in_place_by_the_convolver(when, offset, duration):
+    """rate-1 sources that feed a convolver (directly or through a fused GainNode) are not copied: K5 reads the source
+    buffer in place inside the non-silent range.  Start / offset / duration variants against the oracle."""
+    G, O = _apis()
+
+    def build(api):
+        ctx = api.OfflineAudioContext(FS)
+        for v, with_gain in enumerate([True, False]):
+            s = api.AudioBufferSourceNode(ctx)
+            s.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(800 + 4 * v + c, 20000) for c in range(1 + v)], FS)
+            conv = api.ConvolverNode(ctx)
+            conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.decay_ir(810 + 4 * v + c, 128 * 65 + 1) for c in range(2)], FS)
+            node = s
+            if with_gain:
+                g = api.GainNode(ctx)
+                g.Gain.SetValueAtTime(0.9, 0.0)
+                g.Gain.LinearRampToValueAtTime(0.3, 0.3)
+                node = s.Connect(g)
+            node.Connect(conv).Connect(ctx.Destination)
+            if duration is None:
+                s.Start(when, offset)
+            else:
+                s.Start(when, offset, duration)
+        return ctx
+    n = 20000 + 128 * 70
+    yg = build(G).Render(n)
+    yo = build(O).Render(n)
+    assert np.abs(yo).max() > 1e-2
+    assert np.abs(yg - yo).max() <= TOL

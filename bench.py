@@ -379,6 +379,7 @@ def run_ours(args, wl):
         if cpu:
             line["cpu_baseline"] = cpu
         line["e2e"]["async_upload"] = not args.sync_upload
+        line["e2e"]["ms_per_step_quartiles"] = [float(x) * 1e3 for x in np.percentile(lat, [0, 25, 50, 75, 100])]  # this rank's steps
         print(json.dumps(line))
     ctx.Dispose()
     if world > 1:

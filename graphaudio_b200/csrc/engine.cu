@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <tuple>
@@ -95,8 +96,8 @@ struct gac_context {
   float2* d_tw = nullptr;  // e^{-2 pi i k/(2B)}, k < B
   float2* d_tw2 = nullptr; // e^{-2 pi i e/8192}, e < 8192: twiddles of the second-level (block-time) FFT, fft2.cu
   float2* d_tab16 = nullptr; // (points into the d_tw2 allocation) per-M twiddle tables of the radix-16 plan
-  std::vector<double> h_bt;  // block start times, accumulated as AudioContextBase.cs:78-79
-  double* d_bt = nullptr;
+  std::shared_ptr<struct BlockTimes> bt;  // block start times (shared by the contexts of one device and sample rate)
+  double* d_bt = nullptr;                 // = bt->d
   int64_t bt_cap = 0;
   gac_stats stats{};
   // NCCL (optional)
@@ -107,12 +108,65 @@ struct gac_context {
   // preparation and the first voice batches of the next render
   bool async_upload = false;
   cudaStream_t copy_stream = nullptr;
-  // ... and IR preparation runs on its own stream, so that a render never queues behind the preparation of an impulse
-  // response whose upload is still in flight; renders wait on the `ready` event of exactly the IRs they use
-  cudaStream_t prep_stream = nullptr;
+  // ... and IR preparation is DEFERRED: gac_ir_prepare only sizes and allocates, the render that first uses an impulse
+  // response prepares it together with all the others its voice batch needs (three launches per batch instead of three per
+  // IR; a render never queues behind the preparation of an impulse response whose upload is still in flight)
   std::vector<cudaEvent_t> event_pool;  // recycled `ready` events (creating one costs a driver call per buffer)
   std::map<std::tuple<double, int64_t, int64_t, int64_t>, std::shared_ptr<ResampleTable>> resample_cache;
+  // page-locked staging for the small job tables of a render: they reach the device through a copy KERNEL (SM loads over
+  // PCIe), not through the DMA engine, whose queue may hold hundreds of megabytes of asynchronous buffer uploads — a
+  // cudaMemcpyAsync of a 2 KB table would wait behind all of them, and with it every kernel of the render
+  char* h_stage = nullptr;
+  size_t stage_cap = 0, stage_used = 0;
 };
+// Staging blocks are recycled process-wide: page-locking 8 MB costs milliseconds (and cudaFreeHost synchronises the device),
+// far more than the render of a context that lives for one graph.  Blocks are portable (any device's context may take one).
+static constexpr size_t kStageBytes = (size_t)8 << 20;
+static std::mutex g_stage_mu;
+static std::vector<char*> g_stage_free;
+static char* take_stage_block() {
+  {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (!g_stage_free.empty()) {
+      char* p = g_stage_free.back();
+      g_stage_free.pop_back();
+      return p;
+    }
+  }
+  char* p = nullptr;
+  if (cudaHostAlloc((void**)&p, kStageBytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+static void give_stage_block(char* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  g_stage_free.push_back(p);
+}
+// ---- constant device tables, shared process-wide.
+// They are uploaded ONCE per device with a synchronous copy and never through a context's stream: a stream that has used the
+// copy engine orders its next operation behind whatever other streams have queued on that engine since, so one small table
+// copy at context creation made the whole render wait for the last asynchronous buffer upload (scratch/overlap_probe.cu:
+// variants 2, 4, 6 against 1, 8, 9).  They are never freed (a few hundred KB per device).
+struct BlockTimes {
+  std::vector<double> h;  // _currentTime += 128.0 / SampleRate, accumulated block after block (AudioContextBase.cs:78-79)
+  double* d = nullptr;
+  ~BlockTimes() {
+    if (d) cudaFree(d);
+  }
+};
+struct DeviceTables {
+  float2* d_tw[3] = {nullptr, nullptr, nullptr};  // partition 128, 256, 512
+  float2* d_tw2 = nullptr;
+  std::map<int, std::shared_ptr<BlockTimes>> bt;  // by sample rate: the largest table built so far
+};
+static std::mutex g_tables_mu;
+static DeviceTables* device_tables(int dev) {
+  static DeviceTables* tabs = new DeviceTables[64];  // (leaked on purpose: no CUDA calls from static destructors)
+  return &tabs[dev];
+}
 static cudaEvent_t take_event(gac_context* ctx) {
   if (!ctx->event_pool.empty()) {
     cudaEvent_t e = ctx->event_pool.back();
@@ -131,6 +185,8 @@ struct gac_buffer {
   float* d = nullptr;  // [nch][stride]
   int64_t stride;
   cudaEvent_t ready = nullptr;  // async upload: recorded on the copy stream behind the last H2D copy
+  int ir_refs = 0;              // impulse responses whose (deferred) preparation still has to read this buffer
+  bool zombie = false;          // gac_buffer_destroy was called while ir_refs > 0: freed when the last reference goes
 };
 // orders the context stream behind a buffer's (possibly still running) upload
 static inline void wait_ready(gac_context* ctx, const gac_buffer* b) {
@@ -147,11 +203,11 @@ struct gac_ir {
   // second-level spectra (fft2.cu): [nch][B+1][M2], or null when the context's mac_variant never uses them
   float2* d_H2 = nullptr;  // (inside the d_H allocation)
   int M2 = 0, Lh = 0;
-  cudaEvent_t ready = nullptr;  // async mode: recorded on the preparation stream behind the last preparation kernel
+  // deferred preparation (async mode): the source buffer is read by the first render that uses the impulse response
+  bool prepared = true;
+  gac_buffer* src = nullptr;
+  bool normalize = true;
 };
-static inline void wait_ready_ir(gac_context* ctx, const gac_ir* ir) {
-  if (ir && ir->ready) cudaStreamWaitEvent(ctx->stream, ir->ready, 0);
-}
 struct gac_graph {
   gac_context* ctx;
   std::vector<VoiceH> voices;
@@ -172,6 +228,24 @@ static bool use_fft2(const gac_context* c, int P, int M2) {
 
 // ------------------------------------------------------------------------------------------ scratch + timing
 // Stream-ordered scratch allocations, all released at the end of a render.
+// Host table -> device, ordered on the context stream.  With asynchronous uploads the table goes through the context's
+// page-locked staging area and a copy kernel (see gac_context::h_stage); the staging area is recycled by every render
+// (renders synchronise before they return).  The destination must be allocated in multiples of 16 bytes.
+static int table_h2d(gac_context* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return GAC_OK;
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (ctx->h_stage && ctx->stage_used + need <= ctx->stage_cap) {
+    char* slot = ctx->h_stage + ctx->stage_used;
+    ctx->stage_used += need;
+    memcpy(slot, h_src, bytes);
+    launch_copy_from_host(d_dst, slot, need, ctx->stream);
+    return GAC_OK;
+  }
+  cudaError_t e = cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+  return GAC_OK;
+}
+
 struct Scratch {
   gac_context* ctx;
   std::vector<void*> ptrs;
@@ -180,7 +254,7 @@ struct Scratch {
   template <typename T>
   int alloc(T** out, size_t count) {
     void* p = nullptr;
-    size_t b = std::max<size_t>(count * sizeof(T), 16);
+    size_t b = (std::max<size_t>(count * sizeof(T), 16) + 15) & ~(size_t)15;
     cudaError_t e = cudaMallocAsync(&p, b, ctx->stream);
     if (e != cudaSuccess) {
       return fail(e == cudaErrorMemoryAllocation ? GAC_ERR_OUT_OF_MEMORY : GAC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", b,
@@ -196,11 +270,8 @@ struct Scratch {
   int upload(T** out, const std::vector<T>& v) {
     int rc = alloc(out, v.size());
     if (rc) return rc;
-    if (!v.empty()) {
-      cudaError_t e = cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
-    }
-    return GAC_OK;
+    if (v.empty()) return GAC_OK;
+    return table_h2d(ctx, *out, v.data(), v.size() * sizeof(T));  // (the allocation is 16-byte granular)
   }
   void release() {
     for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
@@ -292,20 +363,27 @@ extern "C" int gac_device_count(int* count) {
 }
 
 static int ensure_block_times(gac_context* ctx, int64_t nq) {
-  if ((int64_t)ctx->h_bt.size() >= nq + 1 && ctx->d_bt) return GAC_OK;
-  // _currentTime += 128.0 / SampleRate, accumulated block after block (AudioContextBase.cs:78-79)
-  int64_t want = std::max<int64_t>(nq + 1, 4096);
-  double inc = (double)128 / (double)ctx->fs;
-  double t = ctx->h_bt.empty() ? 0.0 : ctx->h_bt.back();
-  if (ctx->h_bt.empty()) ctx->h_bt.push_back(0.0);
-  while ((int64_t)ctx->h_bt.size() < want) {
-    t = t + inc;
-    ctx->h_bt.push_back(t);
+  if (ctx->bt && (int64_t)ctx->bt->h.size() >= nq + 1) return GAC_OK;
+  std::lock_guard<std::mutex> lk(g_tables_mu);
+  std::shared_ptr<BlockTimes>& cached = device_tables(ctx->device)->bt[ctx->fs];
+  if (!cached || (int64_t)cached->h.size() < nq + 1) {
+    auto t = std::make_shared<BlockTimes>();
+    if (cached) t->h = cached->h;  // (the accumulation continues where the smaller table stopped)
+    const int64_t want = std::max<int64_t>(nq + 1, 8192);
+    const double inc = (double)128 / (double)ctx->fs;
+    double acc = t->h.empty() ? 0.0 : t->h.back();
+    if (t->h.empty()) t->h.push_back(0.0);
+    while ((int64_t)t->h.size() < want) {
+      acc = acc + inc;
+      t->h.push_back(acc);
+    }
+    CU(cudaMalloc(&t->d, t->h.size() * sizeof(double)));
+    CU(cudaMemcpy(t->d, t->h.data(), t->h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    cached = t;  // contexts that still hold the smaller table keep it alive
   }
-  if (ctx->d_bt) cudaFreeAsync(ctx->d_bt, ctx->stream);
-  CU(cudaMallocAsync(&ctx->d_bt, ctx->h_bt.size() * sizeof(double), ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_bt, ctx->h_bt.data(), ctx->h_bt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->bt_cap = (int64_t)ctx->h_bt.size();
+  ctx->bt = cached;
+  ctx->d_bt = cached->d;
+  ctx->bt_cap = (int64_t)cached->h.size();
   return GAC_OK;
 }
 
@@ -354,41 +432,42 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   ctx->tile_blocks = desc->tile_blocks == 64 ? 64 : 32;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->async_upload = (desc->flags & GAC_FLAG_ASYNC_UPLOAD) != 0;
-  if (ctx->async_upload) {
-    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
-  }
+  if (ctx->async_upload) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   ctx->scratch_budget = di.budget;
-  // twiddles e^{-2 pi i k / N}, N = 2B, in double then rounded once
-  std::vector<float2> tw(B);
-  const double pi = 3.14159265358979323846;
-  for (int k = 0; k < B; k++) {
-    double a = -2.0 * pi * (double)k / (double)(2 * B);
-    tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
-  }
-  CU(cudaMallocAsync(&ctx->d_tw, sizeof(float2) * B, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_tw, tw.data(), sizeof(float2) * B, cudaMemcpyHostToDevice, ctx->stream));  // pageable: staged before return
   {
-    static std::vector<float2> tw2;  // same for every context: computed once per process
-    if (tw2.empty()) {
-      tw2.resize(kFft2TwLen + fft2_table_total());
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    DeviceTables* T = device_tables(dev);
+    const double pi = 3.14159265358979323846;
+    const int bi = B == 128 ? 0 : B == 256 ? 1 : 2;
+    if (!T->d_tw[bi]) {
+      // twiddles e^{-2 pi i k / N}, N = 2B, in double then rounded once
+      std::vector<float2> tw(B);
+      for (int k = 0; k < B; k++) {
+        double a = -2.0 * pi * (double)k / (double)(2 * B);
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+      CU(cudaMalloc(&T->d_tw[bi], sizeof(float2) * B));
+      CU(cudaMemcpy(T->d_tw[bi], tw.data(), sizeof(float2) * B, cudaMemcpyHostToDevice));
+    }
+    if (!T->d_tw2) {
+      std::vector<float2> tw2(kFft2TwLen + fft2_table_total());
       for (int e = 0; e < kFft2TwLen; e++) {
         double a = -2.0 * pi * (double)e / (double)kFft2TwLen;
         tw2[e] = make_float2((float)std::cos(a), (float)std::sin(a));
       }
       fft2_fill_tables(tw2.data() + kFft2TwLen);
+      CU(cudaMalloc(&T->d_tw2, sizeof(float2) * tw2.size()));
+      CU(cudaMemcpy(T->d_tw2, tw2.data(), sizeof(float2) * tw2.size(), cudaMemcpyHostToDevice));
     }
-    CU(cudaMallocAsync(&ctx->d_tw2, sizeof(float2) * tw2.size(), ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_tw2, tw2.data(), sizeof(float2) * tw2.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->d_tw = T->d_tw[bi];
+    ctx->d_tw2 = T->d_tw2;
     ctx->d_tab16 = ctx->d_tw2 + kFft2TwLen;
   }
   int rc = ensure_block_times(ctx.get(), 8192);
   if (rc) return rc;
-  if (ctx->prep_stream) {  // the preparation stream reads the twiddle tables uploaded above
-    cudaEvent_t e = take_event(ctx.get());
-    CU(cudaEventRecord(e, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->prep_stream, e, 0));
-    ctx->event_pool.push_back(e);
+  if (ctx->async_upload) {
+    ctx->h_stage = take_stage_block();  // null: falls back to cudaMemcpyAsync for the job tables
+    ctx->stage_cap = ctx->h_stage ? kStageBytes : 0;
   }
   *out = ctx.release();
   return GAC_OK;
@@ -398,7 +477,6 @@ extern "C" int gac_synchronize(gac_context* ctx) {
   if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
   CU(cudaSetDevice(ctx->device));
   if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
-  if (ctx->prep_stream) CU(cudaStreamSynchronize(ctx->prep_stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return GAC_OK;
 }
@@ -413,19 +491,13 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
     if (kv.second->d_k) cudaFreeAsync(kv.second->d_k, ctx->stream);
     if (kv.second->d_t) cudaFreeAsync(kv.second->d_t, ctx->stream);
   }
-  if (ctx->d_tw) cudaFreeAsync(ctx->d_tw, ctx->stream);
-  if (ctx->d_tw2) cudaFreeAsync(ctx->d_tw2, ctx->stream);
-  if (ctx->d_bt) cudaFreeAsync(ctx->d_bt, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
   }
-  if (ctx->prep_stream) {
-    cudaStreamSynchronize(ctx->prep_stream);
-    cudaStreamDestroy(ctx->prep_stream);
-  }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  give_stage_block(ctx->h_stage);
   cudaStreamDestroy(ctx->stream);
   ctx->magic = 0;
   delete ctx;
@@ -449,22 +521,23 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
   b->nch = n_channels;
   b->n = n_frames;
   b->rate = sample_rate;
-  b->stride = ((n_frames + 8 + 63) / 64) * 64;  // a little slack so 4-tap reads never leave the allocation
-  // Asynchronous path (opt-in, and only for page-locked sources — pageable copies are staged synchronously by the
-  // runtime anyway): the copy is queued on the copy stream and the call returns; the arrays must stay valid and
-  // unmodified until the next gac_render* / gac_synchronize returns.
-  // (pageable arrays are still correct here: the runtime stages them before cudaMemcpyAsync returns)
+  // Channel arrays that are rows of one host block (a pinned staging buffer) are uploaded with ONE 1-D copy into rows of the
+  // same pitch: a strided 2-D copy reaches 41 GB/s on this box, one copy per row 46, one contiguous copy 52-55
+  // (tools/h2d_bandwidth.py).  The device rows keep 16-byte alignment (float2 / float4 loads) only if the pitch is a multiple
+  // of 4 frames; otherwise the rows get their own padded pitch and one copy each.
+  bool contiguous = n_channels > 1 && n_frames > 0 && n_frames % 4 == 0;
+  for (int c = 1; c < n_channels && contiguous; c++) contiguous = channels[c] == channels[c - 1] + n_frames;
+  b->stride = contiguous ? n_frames : ((n_frames + 8 + 63) / 64) * 64;
+  // Asynchronous path (opt-in): the copy is queued on the copy stream and the call returns; the arrays must stay valid and
+  // unmodified until the next gac_render* / gac_synchronize returns.  (Pageable arrays are still correct: the runtime stages
+  // them before cudaMemcpyAsync returns.)
   const bool async = ctx->async_upload;
   cudaStream_t st = async ? ctx->copy_stream : ctx->stream;
-  CU(cudaMallocAsync(&b->d, sizeof(float) * b->stride * n_channels, st));
-  // the slack behind each channel is never read: k_source_copy stays inside [0, n) and the resampler's taps are the last
-  // four CONSUMED frames (k + 3 <= n - 1)
-  bool contiguous = n_channels > 1 && n_frames > 0;
-  for (int c = 1; c < n_channels && contiguous; c++) contiguous = channels[c] == channels[c - 1] + n_frames;
+  // a little slack at the end so that 4-tap reads never leave the allocation; the frames behind a channel's last one are never
+  // USED: k_source_copy stays inside [0, n) and the resampler's taps are the last four CONSUMED frames (k + 3 <= n - 1)
+  CU(cudaMallocAsync(&b->d, sizeof(float) * ((size_t)b->stride * n_channels + 64), st));
   if (contiguous) {
-    // the channel arrays are rows of one host block (a pinned staging buffer): one strided copy instead of one per channel
-    CU(cudaMemcpy2DAsync(b->d, sizeof(float) * b->stride, channels[0], sizeof(float) * n_frames, sizeof(float) * n_frames, (size_t)n_channels,
-                         cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->d, channels[0], sizeof(float) * (size_t)n_frames * n_channels, cudaMemcpyHostToDevice, st));
   } else {
     for (int c = 0; c < n_channels; c++)
       CU(cudaMemcpyAsync(b->d + c * b->stride, channels[c], sizeof(float) * n_frames, cudaMemcpyHostToDevice, st));
@@ -480,6 +553,10 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
 }
 extern "C" int gac_buffer_destroy(gac_buffer* buf) {
   if (!buf) return fail(GAC_ERR_INVALID_ARGUMENT, "buffer is null");
+  if (buf->ir_refs > 0) {  // an impulse response prepared from it has not been used yet: it goes when that one is prepared / destroyed
+    buf->zombie = true;
+    return GAC_OK;
+  }
   cudaSetDevice(buf->ctx->device);
   // stream-ordered free: safe behind any render still queued on the context stream
   if (buf->ready) {
@@ -492,9 +569,8 @@ extern "C" int gac_buffer_destroy(gac_buffer* buf) {
 }
 
 // ------------------------------------------------------------------------------------------ IR prepare (K0)
-// `st` = the stream the preparation runs on (the context stream, or the preparation stream in async mode)
-static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir,
-                             cudaStream_t st) {
+// sizes and allocates the spectra of an impulse response (no kernel is launched)
+static int ir_allocate(gac_context* ctx, int nch, int64_t frames, gac_ir* ir) {
   const int B = ctx->B;
   ir->P = (int)((frames + B - 1) / B);  // ceil(L / blockSize)  PartitionedConvolver.cs:44
   ir->P16 = std::max(16, ((ir->P + 15) / 16) * 16);
@@ -503,9 +579,18 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   // one stream-ordered allocation: spectra [nch][P16][B] float2, the second-level spectra, the per-channel scales
   const size_t hbytes = sizeof(float2) * (size_t)nch * ir->P16 * B;
   const size_t h2bytes = ir->M2 > 0 ? sizeof(float2) * (size_t)nch * (B + 1) * fft2_h2_row_elems(ir->M2) : 0;
-  CU(cudaMallocAsync(&ir->d_H, hbytes + h2bytes + sizeof(float) * nch, st));
+  CU(cudaMallocAsync(&ir->d_H, hbytes + h2bytes + sizeof(float) * nch, ctx->stream));
   ir->d_H2 = h2bytes ? reinterpret_cast<float2*>(reinterpret_cast<char*>(ir->d_H) + hbytes) : nullptr;
   ir->d_scale = reinterpret_cast<float*>(reinterpret_cast<char*>(ir->d_H) + hbytes + h2bytes);
+  return GAC_OK;
+}
+
+// prepares one impulse response at once on the context stream (the reference's semantics: ConvolverNode.Buffer = ir does the work)
+static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir) {
+  const int B = ctx->B;
+  cudaStream_t st = ctx->stream;
+  int rc = ir_allocate(ctx, nch, frames, ir);
+  if (rc) return rc;
   // rows P .. P16 stay zero (the register-tiled MAC reads whole 16-row chunks); rows < P are written by the transform
   if (ir->P16 > ir->P)
     CU(cudaMemset2DAsync(ir->d_H + (size_t)ir->P * B, sizeof(float2) * (size_t)ir->P16 * B, 0, sizeof(float2) * (size_t)(ir->P16 - ir->P) * B, nch, st));
@@ -527,8 +612,16 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
     launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, nch, B, ir->P, ir->M2, ir->d_H2, ctx->d_tw2, ctx->d_tab16, st);
     CU(cudaGetLastError());
   }
-  // no host synchronisation: every later use of the spectra is ordered behind `st` (same stream, or the `ready` event)
+  // no host synchronisation: every later use of the spectra is ordered behind the same stream
+  ir->prepared = true;
   return GAC_OK;
+}
+
+static void buffer_unref(gac_buffer* b) {
+  if (b && --b->ir_refs == 0 && b->zombie) {
+    b->zombie = false;
+    gac_buffer_destroy(b);
+  }
 }
 
 extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int normalize, int true_stereo, gac_ir** out) {
@@ -550,16 +643,21 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
   ir->nch = buf->nch;
   ir->true_stereo = ts;
   ir->frames = buf->n;
-  cudaStream_t st = ctx->prep_stream ? ctx->prep_stream : ctx->stream;
-  if (buf->ready) CU(cudaStreamWaitEvent(st, buf->ready, 0));  // the IR's upload may still be in flight
-  int rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get(), st);
-  if (rc) {
-    if (ir->d_H) cudaFreeAsync(ir->d_H, st);
-    return rc;
+  int rc;
+  if (ctx->async_upload && buf->ready) {
+    // deferred: the render that first uses the impulse response prepares it, batched with the others (prepare_irs)
+    rc = ir_allocate(ctx, buf->nch, buf->n, ir.get());
+    ir->prepared = false;
+    ir->src = const_cast<gac_buffer*>(buf);
+    ir->normalize = normalize != 0;
+    if (!rc) ir->src->ir_refs++;
+  } else {
+    wait_ready(ctx, buf);
+    rc = ir_prepare_device(ctx, buf->d, buf->stride, buf->nch, buf->n, normalize != 0, ir.get());
   }
-  if (ctx->prep_stream) {
-    ir->ready = take_event(ctx);
-    CU(cudaEventRecord(ir->ready, st));
+  if (rc) {
+    if (ir->d_H) cudaFreeAsync(ir->d_H, ctx->stream);
+    return rc;
   }
   *out = ir.release();
   return GAC_OK;
@@ -567,11 +665,8 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
 extern "C" int gac_ir_destroy(gac_ir* ir) {
   if (!ir) return fail(GAC_ERR_INVALID_ARGUMENT, "ir is null");
   cudaSetDevice(ir->ctx->device);
-  // stream-ordered free, behind the preparation and behind any render still queued on the context stream
-  if (ir->ready) {
-    cudaStreamWaitEvent(ir->ctx->stream, ir->ready, 0);
-    ir->ctx->event_pool.push_back(ir->ready);
-  }
+  // stream-ordered free, behind any render still queued on the context stream
+  if (!ir->prepared) buffer_unref(ir->src);  // never used: its source buffer is released too
   cudaFreeAsync(ir->d_H, ir->ctx->stream);
   delete ir;
   return GAC_OK;
@@ -1072,6 +1167,97 @@ static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
   return GAC_OK;
 }
 
+// Deferred preparation of the impulse responses a batch of convolvers is about to use (async mode): one scale launch, one
+// first-level transform launch and one second-level launch per transform length for ALL of them
+// (PartitionedConvolver.cs:65-102 per channel; three launches per impulse response when done eagerly).
+static int prepare_irs(RenderEnv& env, const std::vector<const gac_ir*>& irs) {
+  gac_context* ctx = env.ctx;
+  const int B = ctx->B;
+  auto& cj = env.keep->make<IrChanJob>();
+  auto& fj = env.keep->make<FftFwdJob>();
+  std::vector<gac_ir*> todo;
+  int pmax = 0;
+  for (const gac_ir* cir : irs) {
+    gac_ir* ir = const_cast<gac_ir*>(cir);
+    if (ir->prepared) continue;
+    ir->prepared = true;  // (also de-duplicates the list)
+    todo.push_back(ir);
+    wait_ready(ctx, ir->src);
+    const int64_t h2row = ir->M2 > 0 ? fft2_h2_row_elems(ir->M2) : 0;
+    for (int c = 0; c < ir->nch; c++) {
+      IrChanJob j;
+      j.ir = ir->src->d + (size_t)c * ir->src->stride;
+      j.n_frames = ir->frames;
+      j.normalize = ir->normalize && ir->frames > 0 ? 1 : 0;
+      j.scale = ir->d_scale + c;
+      j.H = ir->d_H + (size_t)c * ir->P16 * B;
+      j.P = ir->P;
+      j.P16 = ir->P16;
+      j.H2 = ir->d_H2 ? ir->d_H2 + (size_t)c * (B + 1) * h2row : nullptr;
+      cj.push_back(j);
+      FftFwdJob f;
+      f.in = j.ir;
+      f.out = j.H;
+      f.scale = j.scale;
+      f.gain = nullptr;
+      f.gain_const = 1.0f;
+      f.n_valid = ir->frames;
+      f.n_blocks = ir->P;
+      f.gate_lo = 0;
+      f.gate_hi = std::numeric_limits<int64_t>::max();
+      fj.push_back(f);
+      pmax = std::max(pmax, ir->P);
+    }
+  }
+  if (todo.empty()) return GAC_OK;
+  // channels that share a second-level transform length are contiguous in the job array
+  std::vector<size_t> order(cj.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = i;
+  std::vector<int> m_of(cj.size());
+  {
+    size_t k = 0;
+    for (gac_ir* ir : todo)
+      for (int c = 0; c < ir->nch; c++) m_of[k++] = ir->d_H2 ? ir->M2 : 0;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return m_of[a] < m_of[b]; });
+  auto& cjs = env.keep->make<IrChanJob>();
+  std::vector<int> ms;
+  for (size_t i : order) {
+    cjs.push_back(cj[i]);
+    ms.push_back(m_of[i]);
+  }
+  IrChanJob* dcj = nullptr;
+  FftFwdJob* dfj = nullptr;
+  int rc;
+  if ((rc = env.scratch->upload(&dcj, cjs))) return rc;
+  if ((rc = env.scratch->upload(&dfj, fj))) return rc;
+  const float cal = (float)std::pow(10.0, (double)(-58.f * 0.05f));  // PartitionedConvolver.cs:95,101
+  launch_ir_scale_batch(dcj, (int)cjs.size(), cal, B, ctx->stream);
+  launch_rfft_fwd(dfj, (int)fj.size(), pmax, B, ctx->d_tw, ctx->stream);
+  env.launches += 2;
+  for (size_t i0 = 0; i0 < ms.size();) {
+    size_t i1 = i0;
+    while (i1 < ms.size() && ms[i1] == ms[i0]) i1++;
+    const int M = ms[i0];
+    if (M > 0 && M <= 4096) {
+      launch_fft2_prep_batch(dcj + i0, (int)(i1 - i0), B, M, ctx->d_tab16, ctx->stream);
+      env.launches++;
+    } else if (M > 4096) {  // radix-8 plan: per channel
+      for (size_t i = i0; i < i1; i++) {
+        launch_fft2_prep(cjs[i].H, 0, 1, B, cjs[i].P, M, cjs[i].H2, ctx->d_tw2, ctx->d_tab16, ctx->stream);
+        env.launches++;
+      }
+    }
+    i0 = i1;
+  }
+  CU(cudaGetLastError());
+  for (gac_ir* ir : todo) {
+    buffer_unref(ir->src);
+    ir->src = nullptr;
+  }
+  return GAC_OK;
+}
+
 // Runs every signal's op chain, position by position, batching equal kinds across signals.
 static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
   gac_context* ctx = env.ctx;
@@ -1191,6 +1377,13 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     }
     // ---------------- ConvolverNode (K5, K6, K7)
     if (!convs.empty()) {
+      {
+        std::vector<const gac_ir*> need;
+        for (size_t k : convs)
+          if ((*sigs[k].ops)[pos].ir) need.push_back((*sigs[k].ops)[pos].ir);
+        int rc = prepare_irs(env, need);
+        if (rc) return rc;
+      }
       std::vector<ConvItem> items;
       auto& zj = env.keep->make<GainJob>();
       for (size_t k = 0; k < convs.size(); k++) {
@@ -1218,7 +1411,6 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           env.fused.erase(f);
         }
         const gac_ir* ir = op.ir;
-        wait_ready_ir(ctx, ir);
         auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
         auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(ir->M2)) : (const float2*)nullptr; };
         const float* in0 = s.lazy[0] ? s.lazy[0] : s.p[0];

@@ -11,7 +11,7 @@
 static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices, std::vector<Sig>& sigs) {
   gac_context* ctx = env.ctx;
   const double inc = (double)128 / (double)ctx->fs;
-  const std::vector<double>& bt = ctx->h_bt;
+  const std::vector<double>& bt = ctx->bt->h;
   auto& cj = env.keep->make<SourceJob>();
   auto& rj = env.keep->make<ResampleJob>();
   auto& tables = ctx->resample_cache;  // the phase recurrence depends on (rate, offset, end, length) only: replayed once per context
@@ -87,7 +87,8 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
       const OpH* conv = nullptr;
       if (!ops.empty() && ops[0].kind == GAC_OP_CONVOLVER) conv = &ops[0];
       else if (ops.size() > 1 && ops[0].kind == GAC_OP_GAIN && ops[1].kind == GAC_OP_CONVOLVER) conv = &ops[1];
-      const bool in_place = conv && conv->ir && conv->ir->d_H2 && nb > 0 && ((job.pos0 - job.out0) % 2 == 0);
+      const bool in_place = conv && conv->ir && conv->ir->d_H2 && nb > 0 && ((job.pos0 - job.out0) % 2 == 0) &&
+                            (reinterpret_cast<uintptr_t>(src0) % 8 == 0) && (reinterpret_cast<uintptr_t>(src1) % 8 == 0);
       if (in_place) {
         s.lazy[0] = src0 + (job.pos0 - job.out0);
         s.lazy[1] = src1 + (job.pos0 - job.out0);
@@ -143,10 +144,12 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
           tab->t.resize(tab->k.size());
           if (!tab->k.empty()) {
             // context-owned device copies (not render scratch): later renders of the same source geometry reuse them
-            CU(cudaMallocAsync(&tab->d_k, tab->k.size() * sizeof(int32_t), ctx->stream));
-            CU(cudaMallocAsync(&tab->d_t, tab->t.size() * sizeof(float), ctx->stream));
-            CU(cudaMemcpyAsync(tab->d_k, tab->k.data(), tab->k.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaMemcpyAsync(tab->d_t, tab->t.data(), tab->t.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            const size_t tb = (tab->k.size() * sizeof(int32_t) + 15) & ~(size_t)15;
+            CU(cudaMallocAsync(&tab->d_k, tb, ctx->stream));
+            CU(cudaMallocAsync(&tab->d_t, tb, ctx->stream));
+            int rc;
+            if ((rc = table_h2d(ctx, tab->d_k, tab->k.data(), tab->k.size() * sizeof(int32_t)))) return rc;
+            if ((rc = table_h2d(ctx, tab->d_t, tab->t.data(), tab->t.size() * sizeof(float)))) return rc;
           }
         }
         tables[key] = tab;
@@ -343,6 +346,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
 
   const int B = ctx->B;
   const int64_t total = a.first_frame + a.n_frames;
+  ctx->stage_used = 0;  // the previous render has synchronised: its staged job tables are dead
   RenderEnv env;
   Scratch scratch(ctx);
   HostKeep keep;
@@ -356,6 +360,11 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   env.QB = env.Npad / B;
   int rc = ensure_block_times(ctx, env.NQ + 1);
   if (rc) return rc;
+  cudaEvent_t trace_copy_done = nullptr;
+  if (trace.on && ctx->copy_stream) {
+    cudaEventCreate(&trace_copy_done);
+    cudaEventRecord(trace_copy_done, ctx->copy_stream);
+  }
 
   // ---- voices
   std::vector<const VoiceH*> voices;
@@ -381,7 +390,9 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   auto landed = [&](const VoiceH* v) {
     if (v->src && v->src->ready && cudaEventQuery(v->src->ready) == cudaErrorNotReady) return false;
     for (const OpH& op : v->ops)
-      if (op.kind == GAC_OP_CONVOLVER && op.ir && op.ir->ready && cudaEventQuery(op.ir->ready) == cudaErrorNotReady) return false;
+      if (op.kind == GAC_OP_CONVOLVER && op.ir && !op.ir->prepared && op.ir->src && op.ir->src->ready &&
+          cudaEventQuery(op.ir->src->ready) == cudaErrorNotReady)
+        return false;
     return true;
   };
   std::vector<size_t> src_voices;  // indices of the source-fed chains
@@ -637,6 +648,14 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   gac_stats st{};
   timer.finish(&st);
   trace.mark("device finished");
+  if (trace.on && trace_copy_done) {  // diagnostics: when did the last queued upload land, relative to the render's first / last event?
+    float a = 0.f, b = 0.f;
+    cudaEventSynchronize(trace_copy_done);
+    cudaEventElapsedTime(&a, timer.t0, trace_copy_done);
+    cudaEventElapsedTime(&b, trace_copy_done, timer.t1);
+    fprintf(stderr, "[gac_trace] uploads landed %.3f ms after the render's first event, %.3f ms before its last\n", a, b);
+    cudaEventDestroy(trace_copy_done);
+  }
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "render failed: %s", cudaGetErrorString(e));
   // the async-upload contract releases the caller's arrays when a render returns: buffers this render did not use too
@@ -893,7 +912,7 @@ extern "C" int gac_convolve_batch(gac_context* ctx, const float* x, int n_signal
   gac_ir irh{};
   irh.ctx = ctx;
   irh.nch = n_signals;
-  rc = ir_prepare_device(ctx, dir.as<float>(), stride, n_signals, ir_frames, normalize != 0, &irh, ctx->stream);
+  rc = ir_prepare_device(ctx, dir.as<float>(), stride, n_signals, ir_frames, normalize != 0, &irh);
   DevBuf holdH;
   holdH.p = irh.d_H;  // (the second-level spectra and the scales live in the same allocation)
   if (rc) return rc;

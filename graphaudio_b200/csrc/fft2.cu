@@ -299,6 +299,55 @@ __global__ void __launch_bounds__(M / 16) k_fft2_prep16(const float2* __restrict
   for (int q = 0; q < 8; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
 }
 
+// the same for a batch of channels described by a job array (deferred IR preparation)
+template <int M>
+__global__ void __launch_bounds__(M / 16) k_fft2_prep16_batch(const IrChanJob* __restrict__ jobs, int B, const float2* __restrict__ tab) {
+  using Pl = r16::Plan<M>;
+  constexpr int T = Pl::T;
+  extern __shared__ __align__(128) float2 sm[];
+  const IrChanJob job = jobs[blockIdx.y];
+  const int k = blockIdx.x, t = threadIdx.x;
+  const int col = (k == B) ? 0 : k;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int p = t + T * j;
+    float2 h = make_float2(0.f, 0.f);
+    if (p < job.P) {
+      h = job.H[(int64_t)p * B + col];
+      if (k == 0) h = make_float2(h.x, 0.f);
+      else if (k == B) h = make_float2(h.y, 0.f);
+    }
+    v[j] = h;
+  }
+  r16::fwd_a<M>(v, sm, tab, t);
+  __syncthreads();
+  r16::fwd_b<M>(sm, tab, t);
+  __syncthreads();
+  float2 u[16];
+  r16::load16(u, sm, t);
+  r16::stage_c<Pl::L, false>(u);
+  const float sc = 1.0f / (float)M;
+  constexpr int SE = Pl::SE;
+  float4* __restrict__ out = reinterpret_cast<float4*>(job.H2 + (int64_t)k * SE + r16::pad(16 * t));
+#pragma unroll
+  for (int q = 0; q < 8; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
+}
+template <int M>
+static void prep16_batch_t(const IrChanJob* d_jobs, int n_jobs, int B, const float2* d_tab, cudaStream_t s) {
+  constexpr size_t smem = sizeof(float2) * r16::smem_elems(M);
+  k_fft2_prep16_batch<M><<<dim3((unsigned)(B + 1), (unsigned)n_jobs), M / 16, smem, s>>>(d_jobs, B, d_tab + fft2_table_offset(M));
+}
+void launch_fft2_prep_batch(const IrChanJob* d_jobs, int n_jobs, int B, int M, const float2* d_tab16, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  switch (M) {
+    case 512: prep16_batch_t<512>(d_jobs, n_jobs, B, d_tab16, s); break;
+    case 1024: prep16_batch_t<1024>(d_jobs, n_jobs, B, d_tab16, s); break;
+    case 2048: prep16_batch_t<2048>(d_jobs, n_jobs, B, d_tab16, s); break;
+    case 4096: prep16_batch_t<4096>(d_jobs, n_jobs, B, d_tab16, s); break;
+  }
+}
+
 int fft2_h2_row_elems(int M) { return M <= 4096 ? r16::smem_elems(M) : M; }
 
 int fft2_table_offset(int M) {  // offset of M's radix-16 twiddle table inside the concatenated table buffer

@@ -190,6 +190,22 @@ void launch_mix(const MixJob* d_jobs, int n_jobs, const MixInput* d_inputs, int6
 void launch_ir_scale(const float* d_base, int64_t stride, int n_channels, int64_t n_frames, int normalize, float calibration, float* d_scale,
                      cudaStream_t s);
 
+// one impulse-response channel of a batched (deferred) preparation
+struct IrChanJob {
+  const float* ir;     // the channel's frames
+  int64_t n_frames;
+  int normalize;
+  float* scale;        // the channel's normalisation scale (device scalar)
+  float2* H;           // first-level spectra [P16][B]
+  int P, P16;
+  float2* H2;          // second-level spectra [B+1][row] or nullptr
+};
+void launch_ir_scale_batch(const IrChanJob* d_jobs, int n_jobs, float calibration, int B, cudaStream_t s);
+// second-level spectra of a batch of channels that share the transform length M (<= 4096: radix-16 plan)
+void launch_fft2_prep_batch(const IrChanJob* d_jobs, int n_jobs, int B, int M, const float2* d_tab16, cudaStream_t s);
+
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
+// d_dst <- h_src (page-locked, 16-byte aligned, bytes a multiple of 16) by a copy kernel instead of the DMA engine
+void launch_copy_from_host(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s);
 
 }  // namespace gac

@@ -258,6 +258,52 @@ void launch_ir_scale(const float* d_base, int64_t stride, int n_channels, int64_
   k_ir_scale<<<n_channels, 1024, 0, s>>>(d_base, stride, n_frames, normalize, calibration, d_scale);
 }
 
+// the same for a batch of impulse-response channels described by a job array (deferred preparation: one launch for all the
+// impulse responses a voice batch needs); also clears the rows P .. P16 of the channel's spectra
+__global__ void __launch_bounds__(1024) k_ir_scale_batch(const IrChanJob* __restrict__ jobs, float calibration, int B) {
+  const IrChanJob job = jobs[blockIdx.x];
+  float2* tail = job.H + (size_t)job.P * B;
+  for (int i = threadIdx.x; i < (job.P16 - job.P) * B; i += 1024) tail[i] = make_float2(0.f, 0.f);
+  if (!job.normalize) {
+    if (threadIdx.x == 0) *job.scale = 1.0f;
+    return;
+  }
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < job.n_frames; i += 1024) {
+    float sq = job.ir[i] * job.ir[i];  // float * float (:98)
+    acc += (double)sq;
+  }
+  __shared__ double sm[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = sm[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) {
+      float power = (float)sqrt(acc / (double)job.n_frames);
+      if (isnan(power) || isinf(power) || power < 0.000125f) power = 0.000125f;
+      *job.scale = (1.0f / power) * calibration;
+    }
+  }
+}
+void launch_ir_scale_batch(const IrChanJob* d_jobs, int n_jobs, float calibration, int B, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  k_ir_scale_batch<<<n_jobs, 1024, 0, s>>>(d_jobs, calibration, B);
+}
+
+// device <- page-locked host memory by SM loads (16 bytes per thread): for small job tables that must not queue behind the
+// buffer uploads in the DMA engine (engine.cu, Scratch::upload)
+__global__ void __launch_bounds__(256) k_copy_from_host(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n16) dst[i] = src[i];
+}
+void launch_copy_from_host(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
+  const size_t n16 = bytes / 16;
+  if (n16 == 0) return;
+  k_copy_from_host<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(d_dst), reinterpret_cast<const uint4*>(h_src), n16);
+}
+
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s) { cudaMemsetAsync(p, 0, bytes, s); }
 
 }  // namespace gac

@@ -380,6 +380,7 @@ def run_ours(args, wl):
             line["cpu_baseline"] = cpu
         line["e2e"]["async_upload"] = not args.sync_upload
         line["e2e"]["ms_per_step_quartiles"] = [float(x) * 1e3 for x in np.percentile(lat, [0, 25, 50, 75, 100])]  # this rank's steps
+        line["e2e"]["slowest_step"] = int(np.argmax(lat))
         print(json.dumps(line))
     ctx.Dispose()
     if world > 1:

@@ -116,6 +116,31 @@ internal static unsafe partial class Native
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
     internal static partial int IrDestroy(IntPtr ir);
 
+    // ---- the per-quantum plugin seam (CudaConvolverNode.cs)
+    [LibraryImport(Lib, EntryPoint = "gac_convolver_create")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ConvolverCreate(IntPtr ctx, IntPtr ir, out IntPtr convolver);
+
+    [LibraryImport(Lib, EntryPoint = "gac_convolver_destroy")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ConvolverDestroy(IntPtr convolver);
+
+    [LibraryImport(Lib, EntryPoint = "gac_convolver_channels")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ConvolverChannels(IntPtr convolver, out int inputChannels, out int outputChannels);
+
+    [LibraryImport(Lib, EntryPoint = "gac_convolver_reset")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ConvolverReset(IntPtr convolver);
+
+    [LibraryImport(Lib, EntryPoint = "gac_convolver_process_block")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ConvolverProcessBlock(IntPtr convolver, float** input, int inputChannels, float** output, int outputChannels);
+
+    [LibraryImport(Lib, EntryPoint = "gac_convolver_process")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int ConvolverProcess(IntPtr convolver, float** input, int inputChannels, float** output, int outputChannels, long frames);
+
     [LibraryImport(Lib, EntryPoint = "gac_graph_create")]
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
     internal static partial int GraphCreate(IntPtr ctx, GacGraphDesc* desc, out IntPtr graph);

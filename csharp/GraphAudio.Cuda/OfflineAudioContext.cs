@@ -38,7 +38,7 @@ public sealed unsafe class OfflineAudioContext : IDisposable
             if (output[ch].Length < startIndex + frameCount)
                 throw new ArgumentException($"Channel {ch} buffer is too small. Required: {startIndex + frameCount}, Available: {output[ch].Length}", nameof(output));
         }
-        // GraphFlattener cuts the recorded node graph into what the ABI (v3) knows — voices (chains fed by a source), buses (a
+        // GraphFlattener cuts the recorded node graph into what the ABI (v3 and later) knows — voices (chains fed by a source), buses (a
         // node with several inputs plus the chain behind it; `Target` = destination / parent bus) and chains fed by a bus
         // output (a node whose output fans out ends a bus) — with the connection order of every fan-in preserved, and pins
         // the event arrays.  The algorithm is the one of graphaudio_b200/api.py::_topology_full (tested against the oracle on

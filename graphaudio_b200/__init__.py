@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     AudioParam,
     BiQuadFilterNode,
     ConvolverNode,
+    CudaConvolverNode,
     CudaException,
     FilterType,
     GainNode,
@@ -26,5 +27,5 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "OfflineAudioContext", "PlayableAudioBuffer", "AudioBufferSourceNode", "BiQuadFilterNode", "GainNode", "ConvolverNode",
-    "AudioDestinationNode", "AudioNode", "AudioParam", "FilterType",
+    "AudioDestinationNode", "AudioNode", "AudioParam", "FilterType", "CudaConvolverNode",
 ]

@@ -300,6 +300,82 @@ class ConvolverNode(AudioNode):
         self._buffer, self._ir = value, out.value
 
 
+class CudaConvolverNode:
+    """The literal plugin seam: a ConvolverNode that runs INSIDE a reference-style block loop, one native call
+    per render quantum, the way GraphAudio.SteamAudio's nodes call their native effect from `Process()`
+    (GraphAudio.SteamAudio/Nodes/SteamAudioNodeBase.cs:50-135).  Same members as ConvolverNode (Buffer / Normalize /
+    EnableTrueStereo, Nodes/ConvolverNode.cs:25-95); `Process(input)` is the body of the C# node's `Process()` override:
+    `input` is what `Inputs[0].Buffer` holds (a [channels][128] block already mixed to `InputChannelCount`), the return value
+    is the block handed to `SetOutputBuffer`.  `ProcessFrames` feeds several quanta in one call.  State (delay line, overlap,
+    IR spectra) lives on the device.  Latency-bound by construction — the batched renderer is `OfflineAudioContext.Render`."""
+
+    def __init__(self, context: "OfflineAudioContext"):
+        self.Context = context
+        self.Normalize = True
+        self.EnableTrueStereo = True
+        self._buffer = None
+        self._ir = None
+        self._h = None
+        self.InputChannelCount = 0   # what the C# node sets on Inputs[0] (SetChannelCount + Explicit, ConvolverNode.cs:62-76)
+        self.OutputChannelCount = 0  # _effectiveOutputChannels (:60)
+
+    @property
+    def Buffer(self):
+        return self._buffer
+
+    @Buffer.setter
+    def Buffer(self, value):
+        if value is self._buffer:
+            return
+        L = N.lib()
+        if self._h is not None:
+            self.Context._root()._owned_convolvers.remove(self._h)
+            L.gac_convolver_destroy(self._h)
+            self._h = None
+        self._buffer, self._ir = None, None
+        self.InputChannelCount = self.OutputChannelCount = 0
+        if value is None:
+            return
+        ctx = self.Context
+        if value.SampleRate != ctx.SampleRate:  # Nodes/ConvolverNode.cs:48-49
+            raise InvalidOperationException(
+                "Impulse response buffer sample rate must match the audio context sample rate. "
+                f"Impulse response buffer sample rate: {value.SampleRate}, Audio context sample rate: {ctx.SampleRate}.")
+        ir = C.c_void_p()
+        check(L.gac_ir_prepare(ctx._h, value._handle(ctx), int(self.Normalize), int(self.EnableTrueStereo), C.byref(ir)))
+        ctx._root()._owned_irs.append(ir.value)
+        h = C.c_void_p()
+        check(L.gac_convolver_create(ctx._h, ir.value, C.byref(h)))
+        ctx._root()._owned_convolvers.append(h.value)
+        ni, no = C.c_int(), C.c_int()
+        check(L.gac_convolver_channels(h.value, C.byref(ni), C.byref(no)))
+        self._buffer, self._ir, self._h = value, ir.value, h.value
+        self.InputChannelCount, self.OutputChannelCount = ni.value, no.value
+
+    def Reset(self):
+        if self._h is not None:
+            check(N.lib().gac_convolver_reset(self._h))
+
+    def ProcessFrames(self, block):
+        """`block`: float32 [InputChannelCount][n], n a multiple of the partition; returns [OutputChannelCount][n]."""
+        x = _f32(block)
+        if x.ndim != 2:
+            raise ArgumentException("input must be [channels][frames]")
+        if self._h is None:  # no Buffer: the node outputs silence with the input's channel count (ConvolverNode.cs:107-119)
+            return np.zeros_like(x)
+        y = np.empty((self.OutputChannelCount, x.shape[1]), np.float32)
+        ip = (N.fp * x.shape[0])(*[_fptr(x[c]) for c in range(x.shape[0])])
+        op = (N.fp * y.shape[0])(*[_fptr(y[c]) for c in range(y.shape[0])])
+        if x.shape[1] == 128:
+            check(N.lib().gac_convolver_process_block(self._h, ip, x.shape[0], op, y.shape[0]))
+        else:
+            check(N.lib().gac_convolver_process(self._h, ip, x.shape[0], op, y.shape[0], x.shape[1]))
+        return y
+
+    def Process(self, input_block):
+        return self.ProcessFrames(input_block)
+
+
 class OfflineAudioContext:
     """OfflineAudioContext.cs — `Render` is the one call that crosses into libgraphaudio_cuda.so."""
 
@@ -315,6 +391,7 @@ class OfflineAudioContext:
         self._nodes: List[AudioNode] = []
         self._owned_buffers: List[int] = []
         self._owned_irs: List[int] = []
+        self._owned_convolvers: List[int] = []
         self._record_only = bool(_record_only)
         if not self._record_only:
             desc = N.gac_context_desc()
@@ -613,6 +690,8 @@ class OfflineAudioContext:
             return
         if self._h is not None:
             L = N.lib()
+            for h in self._owned_convolvers:
+                L.gac_convolver_destroy(h)
             for h in self._owned_irs:
                 L.gac_ir_destroy(h)
             for h in self._owned_buffers:

@@ -585,12 +585,10 @@ static int ir_allocate(gac_context* ctx, int nch, int64_t frames, gac_ir* ir) {
   return GAC_OK;
 }
 
-// prepares one impulse response at once on the context stream (the reference's semantics: ConvolverNode.Buffer = ir does the work)
-static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir) {
+// prepares one ALLOCATED impulse response on the context stream (PartitionedConvolver.cs:65-102 per channel)
+static int ir_prepare_run(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir) {
   const int B = ctx->B;
   cudaStream_t st = ctx->stream;
-  int rc = ir_allocate(ctx, nch, frames, ir);
-  if (rc) return rc;
   // rows P .. P16 stay zero (the register-tiled MAC reads whole 16-row chunks); rows < P are written by the transform
   if (ir->P16 > ir->P)
     CU(cudaMemset2DAsync(ir->d_H + (size_t)ir->P * B, sizeof(float2) * (size_t)ir->P16 * B, 0, sizeof(float2) * (size_t)(ir->P16 - ir->P) * B, nch, st));
@@ -615,6 +613,12 @@ static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride
   // no host synchronisation: every later use of the spectra is ordered behind the same stream
   ir->prepared = true;
   return GAC_OK;
+}
+// allocates and prepares at once (the reference's semantics: ConvolverNode.Buffer = ir does the work)
+static int ir_prepare_device(gac_context* ctx, const float* d_ir, int64_t stride, int nch, int64_t frames, bool normalize, gac_ir* ir) {
+  int rc = ir_allocate(ctx, nch, frames, ir);
+  if (rc) return rc;
+  return ir_prepare_run(ctx, d_ir, stride, nch, frames, normalize, ir);
 }
 
 static void buffer_unref(gac_buffer* b) {
@@ -1480,3 +1484,4 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
 
 // source stage, render drivers, NCCL bus reduce and the kernel-level entry points
 #include "engine_render.inl"
+#include "engine_stream.inl"

@@ -71,6 +71,15 @@ void launch_mac_tiled(const MacJob* d_jobs, int n_jobs, const MacTile* d_tiles, 
                       int tile_blocks, int flavour, cudaStream_t s);
 void launch_mac_stream(const MacJob* d_jobs, int n_jobs, int64_t n_blocks, int stride, cudaStream_t s);
 
+// one convolver of a streaming (per-quantum) ConvolverNode: Y[k] = sum_p X[row - p][k] * H[p][k], exact reference order
+struct RingMacJob {
+  const float2* X;  // linear history of the input channel's spectra: row r at X + r*B; rows [row - P + 1, row] are read
+  const float2* H;  // IR spectra, row p at H + p*B
+  float2* Y;        // block j of a call at Y + j*B
+  int P;
+};
+void launch_mac_ring(const RingMacJob* d_jobs, int n_jobs, int64_t row, int n_blocks, int B, cudaStream_t s);
+
 // ------------------------------------------------------------------ second-level FFT MAC (fft2.cu)
 // One job = one channel-convolver over transposed spectrograms: row k (k = 0..B) of XT/YT at X + k*xs / Y + k*ys.
 struct Fft2Job {

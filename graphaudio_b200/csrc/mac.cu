@@ -68,6 +68,41 @@ void launch_mac_stream(const MacJob* d_jobs, int n_jobs, int64_t n_blocks, int s
 }
 
 // --------------------------------------------------------------------------------------------
+// k_mac_ring : ONE block of a streaming convolver (the per-quantum plugin seam, gac_convolver_process_block):
+// acc[k] = sum_{p < P} X[row - p][k] * H[p][k], p ascending, unfused — PartitionedConvolver.cs:154-223 term by term.
+// The delay line is a LINEAR history (rows behind `row` are readable and start zeroed: the reference's cleared
+// FDL contributes x = 0 products too), so there is no modulo in the loop.
+// grid (B / 128, n_jobs, n_blocks), 128 threads, thread = bin; block j of the call reads rows row + j - p and writes Y + j*B.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mac_ring(const RingMacJob* __restrict__ jobs, int64_t row, int stride) {
+  const RingMacJob job = jobs[blockIdx.y];
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  const bool dc = k == 0;
+  float ar = 0.f, ai = 0.f;
+  const float2* __restrict__ X = job.X + (row + blockIdx.z) * stride + k;
+  const float2* __restrict__ H = job.H + k;
+#pragma unroll 8
+  for (int p = 0; p < job.P; p++) {
+    const float2 x = X[-(int64_t)p * stride];
+    const float2 h = H[(int64_t)p * stride];
+    if (dc) {  // packed (DC, Nyquist): two real products
+      ar = __fadd_rn(ar, __fmul_rn(x.x, h.x));
+      ai = __fadd_rn(ai, __fmul_rn(x.y, h.y));
+    } else {
+      const float re = __fsub_rn(__fmul_rn(x.x, h.x), __fmul_rn(x.y, h.y));
+      const float im = __fadd_rn(__fmul_rn(x.x, h.y), __fmul_rn(x.y, h.x));
+      ar = __fadd_rn(ar, re);
+      ai = __fadd_rn(ai, im);
+    }
+  }
+  job.Y[(int64_t)blockIdx.z * stride + k] = make_float2(ar, ai);
+}
+void launch_mac_ring(const RingMacJob* d_jobs, int n_jobs, int64_t row, int n_blocks, int B, cudaStream_t s) {
+  if (n_jobs <= 0 || n_blocks <= 0) return;
+  k_mac_ring<<<dim3((unsigned)(B / 128), (unsigned)n_jobs, (unsigned)n_blocks), 128, 0, s>>>(d_jobs, row, B);
+}
+
+// --------------------------------------------------------------------------------------------
 // k_mac_dc : Y[b][0] = (sum_p X[b-p][0].x * H[p][0].x , sum_p X[b-p][0].y * H[p][0].y), p ascending.
 // grid (ceil(n_blocks / 256), n_jobs), 256 threads, thread = output block.  X column 0 and H column 0 of the job
 // are gathered into shared memory once per CTA.

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GAC_ABI_VERSION 3
+#define GAC_ABI_VERSION 4
 
 /* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */
 typedef enum gac_status {
@@ -44,6 +44,7 @@ typedef struct gac_context gac_context; /* ≙ OfflineAudioContext              
 typedef struct gac_buffer gac_buffer;   /* ≙ PlayableAudioBuffer (device-resident copy)            */
 typedef struct gac_ir gac_ir;           /* ≙ the PartitionedConvolver[] a ConvolverNode owns       */
 typedef struct gac_graph gac_graph;     /* a flattened, immutable render graph                     */
+typedef struct gac_convolver gac_convolver; /* one ConvolverNode processed quantum by quantum       */
 
 /* ---- library ---- */
 int gac_version(void);
@@ -278,6 +279,29 @@ int gac_automation_eval(gac_context* ctx, const gac_param* param, int a_rate, in
 /* CubicResampler over one input, one Process call                                  ≙ CubicResampler.cs:26-63 */
 int gac_resample_cubic(gac_context* ctx, const float* in, int64_t n_in, double rate, int64_t n_out, float* out,
                        int64_t* produced, int64_t* consumed);
+
+/* ---- the literal plugin seam: ONE ConvolverNode inside an ordinary reference graph ----
+ * A `CudaConvolverNode : AudioNode` overrides Process(), pins Inputs[0].Buffer and its pooled output block and calls
+ * gac_convolver_process_block once per render quantum — the pattern of GraphAudio.SteamAudio's nodes
+ * (GraphAudio.SteamAudio/Nodes/SteamAudioNodeBase.cs:50-135).  The delay line, the overlap and the IR spectra stay on the
+ * device between calls.  Channel routing is ConvolverNode's (Nodes/ConvolverNode.cs:58-77,121-151): a mono IR takes 1 channel
+ * and produces 1, a stereo IR 2 -> 2, a 4-channel IR prepared with true_stereo 2 -> 2 (L = c0(inL) + c2(inR),
+ * R = c1(inL) + c3(inR)); the caller's AudioNodeInput mixes to that count (SetChannelCount / Explicit, AudioNodeInput.cs:41-58).
+ * The arithmetic of one block is PartitionedConvolver.Process (PartitionedConvolver.cs:104-152) with the multiply-accumulate in
+ * the reference's order (p ascending, unfused, :154-223); the FFTs are float32.
+ * One call costs a few launches and two small copies: it serves mixed and realtime graphs, it is NOT the throughput path
+ * (that is gac_render*).  `ir` must outlive the convolver. */
+int gac_convolver_create(gac_context* ctx, gac_ir* ir, gac_convolver** out);
+int gac_convolver_destroy(gac_convolver* conv);
+int gac_convolver_channels(gac_convolver* conv, int* n_in, int* n_out);
+/* clears the delay line and the overlap (≙ constructing the PartitionedConvolvers again, PartitionedConvolver.cs:37-63) */
+int gac_convolver_reset(gac_convolver* conv);
+/* one render quantum: in[c] / out[c] are blocks of `partition` frames (128 = AudioBuffer.FramesPerBlock)  ≙ ConvolverNode.Process */
+int gac_convolver_process_block(gac_convolver* conv, const float* const* in, int n_in_channels, float* const* out,
+                                int n_out_channels);
+/* n_frames / partition consecutive quanta in one call (same result as calling process_block for each) */
+int gac_convolver_process(gac_convolver* conv, const float* const* in, int n_in_channels, float* const* out,
+                          int n_out_channels, int64_t n_frames);
 
 #ifdef __cplusplus
 }

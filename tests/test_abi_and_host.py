@@ -25,7 +25,7 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = N.lib()
     declared = _declared_symbols()
-    assert len(declared) >= 24
+    assert len(declared) >= 30
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in graphaudio_cuda.h but not exported"
     # and the ctypes table binds exactly the declared set
@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_version_and_struct_layouts():
-    assert N.lib().gac_version() == 3
+    assert N.lib().gac_version() == 4
     # gac_event must be bit-compatible with AutomationEvent (AudioParam.cs:360-367): int, float, float, (pad), double, double
     assert C.sizeof(N.gac_event) == 32
     assert N.gac_event.time.offset == 16 and N.gac_event.time_constant.offset == 24

@@ -21,3 +21,18 @@ h2 = [x for p in zip(hs, hi) for x in p]
 d2 = [x for p in zip(ds, di) for x in p]
 run("64 x (source 3.84 MB + IR 0.77 MB), strided 2-D copies", h2, d2, lambda a, b: b[:, :a.shape[1]].copy_(a, non_blocking=True))
 run("the same as 256 1-D row copies", h2, d2, lambda a, b: (b[0, :a.shape[1]].copy_(a[0], non_blocking=True), b[1, :a.shape[1]].copy_(a[1], non_blocking=True)))
+# do several copy streams hide the per-copy setup gap of the DMA engine?  (the e2e shape as 128 contiguous copies: 64 x 3.84 MB + 64 x 0.77 MB)
+hs1 = [x.reshape(-1) for x in hs]; hi1 = [x.reshape(-1) for x in hi]
+ds1 = [torch.empty(2 * 480000, dtype=torch.float32, device="cuda") for _ in range(64)]
+di1 = [torch.empty(2 * 96000, dtype=torch.float32, device="cuda") for _ in range(64)]
+h3 = [x for p in zip(hs1, hi1) for x in p]; d3 = [x for p in zip(ds1, di1) for x in p]
+for ns in (1, 2, 3, 4):
+    streams = [torch.cuda.Stream() for _ in range(ns)]
+    for rep in range(3):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for i, (a, b) in enumerate(zip(h3, d3)):
+            with torch.cuda.stream(streams[i % ns]):
+                b.copy_(a, non_blocking=True)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    nbytes = sum(a.numel() * 4 for a in h3)
+    print(f"{'128 contiguous copies (source, IR alternating) over %d stream(s)' % ns:60s} {dt*1e3:7.3f} ms  {nbytes/dt/1e9:6.1f} GB/s")

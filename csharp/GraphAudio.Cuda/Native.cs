@@ -41,10 +41,11 @@ internal unsafe struct GacParam
 [StructLayout(LayoutKind.Sequential)]
 internal unsafe struct GacOpDesc
 {
-    public int Kind;        // 1 biquad, 2 gain, 3 convolver
+    public int Kind;        // 1 biquad, 2 gain, 3 convolver, 4 delay, 5 stereo panner
     public int FilterType;  // (int)FilterType
     public GacParam P0, P1, P2;
     public IntPtr Ir;
+    public double Aux;      // delay: maxDelayTime (seconds)
 }
 
 [StructLayout(LayoutKind.Sequential)]

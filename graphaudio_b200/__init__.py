@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     ConvolverNode,
     CudaConvolverNode,
     CudaException,
+    DelayNode,
     FilterType,
     GainNode,
     InvalidOperationException,
@@ -23,9 +24,10 @@ from .api import (  # noqa: F401
     OfflineAudioContext,
     PlayableAudioBuffer,
     RenderBatch,
+    StereoPannerNode,
 )
 
 __all__ = [
     "OfflineAudioContext", "PlayableAudioBuffer", "AudioBufferSourceNode", "BiQuadFilterNode", "GainNode", "ConvolverNode",
-    "AudioDestinationNode", "AudioNode", "AudioParam", "FilterType", "CudaConvolverNode",
+    "AudioDestinationNode", "AudioNode", "AudioParam", "FilterType", "CudaConvolverNode", "DelayNode", "StereoPannerNode",
 ]

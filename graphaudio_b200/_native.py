@@ -22,7 +22,7 @@ GAC_ERR_OUT_OF_MEMORY = -7
 GAC_ERR_NCCL = -8
 GAC_ERR_UNSUPPORTED = -9
 
-GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER = 1, 2, 3
+GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER, GAC_OP_DELAY, GAC_OP_PANNER = 1, 2, 3, 4, 5
 
 fp = C.POINTER(C.c_float)
 fpp = C.POINTER(fp)
@@ -47,7 +47,7 @@ class gac_param(C.Structure):
 
 class gac_op_desc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("filter_type", C.c_int32), ("p0", gac_param), ("p1", gac_param), ("p2", gac_param),
-                ("ir", C.c_void_p)]
+                ("ir", C.c_void_p), ("aux", C.c_double)]
 
 
 class gac_voice_desc(C.Structure):
@@ -93,6 +93,7 @@ SIGNATURES = {
     "gac_graph_create": (C.c_int, [C.c_void_p, C.POINTER(gac_graph_desc), C.POINTER(C.c_void_p)]),
     "gac_graph_destroy": (C.c_int, [C.c_void_p]),
     "gac_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, fpp, C.c_int, C.c_int64]),
+    "gac_render_interleaved": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, fp, C.c_int, C.c_int64]),
     "gac_render_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int]),
     "gac_render_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int64, fpp, C.c_int]),
     "gac_comm_unique_id": (C.c_int, [C.c_void_p]),

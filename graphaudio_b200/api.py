@@ -267,6 +267,25 @@ class GainNode(AudioNode):
         self.Gain = AudioParam(1.0, -fmax, fmax)  # Nodes/GainNode.cs:19-24
 
 
+class DelayNode(AudioNode):
+    """Nodes/DelayNode.cs — integer-sample delay, a-rate DelayTime in seconds."""
+
+    def __init__(self, context, maxDelayTime=1.0):
+        if maxDelayTime <= 0 or maxDelayTime > 10:  # :25-26
+            raise ArgumentOutOfRangeException("maxDelayTime")
+        super().__init__(context)
+        self.MaxDelayTime = float(maxDelayTime)
+        self.DelayTime = AudioParam(0.0, 0.0, float(np.float32(maxDelayTime)))  # :35-40
+
+
+class StereoPannerNode(AudioNode):
+    """Nodes/StereoPannerNode.cs — equal-power pan, a-rate Pan in [-1, 1]."""
+
+    def __init__(self, context):
+        super().__init__(context)
+        self.Pan = AudioParam(0.0, -1.0, 1.0)  # :28-33
+
+
 class ConvolverNode(AudioNode):
     def __init__(self, context):
         super().__init__(context)
@@ -419,6 +438,12 @@ class OfflineAudioContext:
         elif isinstance(node, ConvolverNode):
             op.kind = N.GAC_OP_CONVOLVER
             op.ir = node._ir
+        elif isinstance(node, DelayNode):
+            op.kind, op.aux = N.GAC_OP_DELAY, node.MaxDelayTime
+            op.p0 = node.DelayTime._desc(keep)
+        elif isinstance(node, StereoPannerNode):
+            op.kind = N.GAC_OP_PANNER
+            op.p0 = node.Pan._desc(keep)
         else:
             raise NotSupportedException(f"{type(node).__name__} is outside the accelerated path")
         return op
@@ -627,6 +652,31 @@ class OfflineAudioContext:
             self.last_stats = st.as_dict()
         finally:
             N.lib().gac_graph_destroy(graph)
+
+    def RenderInterleaved(self, frameCount, channels=2, output=None, startIndex=0):
+        """The render as interleaved frames [frameCount * channels] — the array a caller fills by driving
+        `ProcessBlockInterleaved(float[] interleavedBuffer, int channels)` block after block (AudioContextBase.cs:88-161):
+        destination channels first, zeros in the others.  Continues the timeline like Render."""
+        if self._record_only:
+            raise InvalidOperationException("record-only context: there is no CPU render path (build the library and use a B200)")
+        if self._h is None:
+            raise ObjectDisposedException("OfflineAudioContext")
+        if channels < 1 or channels > 32:
+            raise ArgumentOutOfRangeException("channels")  # :93
+        if frameCount <= 0:
+            raise ArgumentOutOfRangeException("Frame count must be positive.")
+        if output is None:
+            output = np.zeros((startIndex + frameCount) * channels, np.float32)
+        if output.dtype != np.float32 or not output.flags.c_contiguous or output.size < (startIndex + frameCount) * channels:
+            raise ArgumentException("Buffer too small for interleaved output.")  # :94-95
+        graph = self._graph()
+        try:
+            check(N.lib().gac_render_interleaved(self._h, graph, self._frames_rendered, int(frameCount), _fptr(output), int(channels),
+                                                 int(startIndex)))
+            self._frames_rendered += int(frameCount)
+        finally:
+            N.lib().gac_graph_destroy(graph)
+        return output
 
     # ---- multi-GPU: voices sharded over processes, one NCCL reduce of the bus (gac_render_sharded)
     def MarkBus(self, node):

@@ -31,7 +31,7 @@ SOURCES = [
     ("biquad_lanes.cu", ["--fmad=false"]),
     ("engine.cu", ["-Xcompiler", "-fvisibility=default"]),
 ]
-HEADERS = ["gac_kernels.h", "fft2_core.cuh", "engine_render.inl", "engine_stream.inl", os.path.join("..", "..", "include", "graphaudio_cuda.h")]
+HEADERS = ["gac_kernels.h", "fft2_core.cuh", "biquad_math.cuh", "engine_render.inl", "engine_stream.inl", os.path.join("..", "..", "include", "graphaudio_cuda.h")]
 
 
 def _nvcc() -> str:

@@ -67,7 +67,7 @@ struct Coef {
 };
 
 // UpdateCoefficients, BiQuadFilterNode.cs:149-258
-__device__ Coef rbj(int type, float frequency, float q, float gain, int sample_rate) {
+static __device__ Coef rbj(int type, float frequency, float q, float gain, int sample_rate) {
   float w0 = 2.f * 3.14159274f * frequency / (float)sample_rate;  // left to right in float32 (:151)
   float sinW0, cosW0;
   sincosf_libm(w0, &sinW0, &cosW0);

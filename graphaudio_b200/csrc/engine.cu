@@ -56,6 +56,7 @@ struct ParamH {
 struct OpH {
   int kind = 0;
   int ftype = 0;
+  double aux = 0;
   ParamH p0, p1, p2;
   const gac_ir* ir = nullptr;
 };
@@ -711,6 +712,14 @@ static int copy_ops(gac_context* ctx, int n, const gac_op_desc* ops, std::vector
         if (o.ir && o.ir->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "impulse response belongs to another context");
         if (o.ir && !(o.ir->nch == 1 || o.ir->nch == 2 || (o.ir->nch == 4 && o.ir->true_stereo))) return fail(GAC_ERR_UNSUPPORTED, "discrete impulse responses with %d channels are outside the accelerated path", o.ir->nch);
         break;
+      case GAC_OP_DELAY:
+        o.aux = ops[i].aux;
+        if (!(o.aux > 0.0 && o.aux <= 10.0)) return fail(GAC_ERR_OUT_OF_RANGE, "maxDelayTime must be in (0, 10] seconds");  // DelayNode.cs:25-26
+        if ((rc = copy_param(ops[i].p0, &o.p0, "delay.delayTime"))) return rc;
+        break;
+      case GAC_OP_PANNER:
+        if ((rc = copy_param(ops[i].p0, &o.p0, "panner.pan"))) return rc;
+        break;
       default:
         return fail(GAC_ERR_INVALID_ARGUMENT, "unknown op kind %d", o.kind);
     }
@@ -803,6 +812,7 @@ struct Sig {
   const float* lazy[2] = {nullptr, nullptr};
   int64_t lo = 0, hi = 0;  // frames flagged non-silent (multiples of 128)
   int ch = 2;              // logical channel count of the block the reference would carry here (rows are always 2; mono = duplicated)
+  bool from_source = false;  // the chain is fed by an AudioBufferSourceNode (whose idle blocks have ONE channel, AudioBufferSourceNode.cs:391-402)
   const std::vector<OpH>* ops = nullptr;
 };
 
@@ -1268,14 +1278,115 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
   size_t maxlen = 0;
   for (auto& s : sigs) maxlen = std::max(maxlen, s.ops ? s.ops->size() : 0);
   for (size_t pos = 0; pos < maxlen; pos++) {
-    std::vector<size_t> gains, biquads, convs;
+    std::vector<size_t> gains, biquads, convs, delays, panners;
     for (size_t i = 0; i < sigs.size(); i++) {
       if (!sigs[i].ops || pos >= sigs[i].ops->size()) continue;
       switch ((*sigs[i].ops)[pos].kind) {
         case GAC_OP_GAIN: gains.push_back(i); break;
         case GAC_OP_BIQUAD: biquads.push_back(i); break;
         case GAC_OP_CONVOLVER: convs.push_back(i); break;
+        case GAC_OP_DELAY: delays.push_back(i); break;
+        case GAC_OP_PANNER: panners.push_back(i); break;
       }
+    }
+    // ---------------- DelayNode: a gather with a per-sample delay (K2 + k_delay), into fresh rows
+    if (!delays.empty()) {
+      std::vector<ParamJob> pj;
+      std::vector<float*> tabs(delays.size(), nullptr);
+      for (size_t k = 0; k < delays.size(); k++) {
+        int rc = param_table(env, (*sigs[delays[k]].ops)[pos].p0, true, pj, &tabs[k]);
+        if (rc) return rc;
+      }
+      int rc = run_param_jobs(env, pj);
+      if (rc) return rc;
+      float* rows = nullptr;
+      if ((rc = env.scratch->alloc(&rows, delays.size() * 2 * (size_t)env.Npad))) return rc;
+      auto& dj = env.keep->make<DelayJob>();
+      for (size_t k = 0; k < delays.size(); k++) {
+        Sig& s = sigs[delays[k]];
+        const OpH& op = (*s.ops)[pos];
+        DelayJob j;
+        j.in[0] = s.p[0];
+        j.in[1] = s.p[1];
+        j.out[0] = rows + (k * 2 + 0) * (size_t)env.Npad;
+        j.out[1] = rows + (k * 2 + 1) * (size_t)env.Npad;
+        j.dt = tabs[k];
+        j.dt_const = op.p0.value;
+        j.max_delay = (int)(op.aux * ctx->fs);  // (int)(maxDelayTime * context.SampleRate)  DelayNode.cs:28
+        j.in_lo = s.lo;
+        j.in_hi = s.hi;
+        dj.push_back(j);
+        s.p[0] = j.out[0];
+        s.p[1] = j.out[1];
+        s.ch = 2;  // Max-mode input with channelCount 2: a mono upstream is up-mixed by copy (AudioNodeInput.cs:157-166,201-213)
+        // Flags: the node keeps one pooled block and only ever MARKS it non-silent (DelayNode.cs:96-97): silent until the first
+        // block that carries audio, flagged from then on.  With a constant DelayTime that block is known here (assuming the
+        // flagged input blocks carry non-zero samples); with automation the range starts conservatively at the input's.
+        if (s.hi > s.lo) {
+          int64_t first = s.lo;
+          if (!j.dt) {
+            int d = (int)(j.dt_const * (float)ctx->fs);
+            d = d < 0 ? 0 : (d > j.max_delay ? j.max_delay : d);
+            first = d >= 1 ? s.lo + d : env.Npad;  // d = 0 reads nothing (CircularBuffer.Read :140-143)
+          }
+          s.lo = std::min<int64_t>(env.Npad, (first / 128) * 128);
+          s.hi = s.lo < env.Npad ? env.Npad : s.lo;
+        }
+      }
+      DelayJob* dd = nullptr;
+      if ((rc = env.scratch->upload(&dd, dj))) return rc;
+      int t = env.timer->begin(C_GAIN);
+      launch_delay(dd, (int)dj.size(), env.Npad, ctx->fs, ctx->stream);
+      env.timer->end(t);
+      env.launches += 1;
+      CU(cudaGetLastError());
+    }
+    // ---------------- StereoPannerNode (K2 + k_panner), in place
+    if (!panners.empty()) {
+      std::vector<ParamJob> pj;
+      std::vector<float*> tabs(panners.size(), nullptr);
+      for (size_t k = 0; k < panners.size(); k++) {
+        int rc = param_table(env, (*sigs[panners[k]].ops)[pos].p0, true, pj, &tabs[k]);
+        if (rc) return rc;
+      }
+      int rc = run_param_jobs(env, pj);
+      if (rc) return rc;
+      auto& qj = env.keep->make<PannerJob>();
+      unsigned long long* d_first = nullptr;
+      if ((rc = env.scratch->alloc(&d_first, panners.size()))) return rc;
+      CU(cudaMemsetAsync(d_first, 0x7f, sizeof(unsigned long long) * panners.size(), ctx->stream));
+      bool scan = false;
+      for (size_t k = 0; k < panners.size(); k++) {
+        Sig& s = sigs[panners[k]];
+        PannerJob j;
+        j.sig[0] = s.p[0];
+        j.sig[1] = s.p[1];
+        j.pan = tabs[k];
+        j.pan_const = (*s.ops)[pos].p0.value;
+        j.mono = s.ch == 1 ? 1 : 0;  // the input is ClampedMax(2): a mono upstream stays mono (StereoPannerNode.cs:24-26, :62-66)
+        j.lo = s.lo;
+        j.hi = s.hi;
+        j.sp_block = -(int64_t)1 << 40;
+        j.sp_mode = 0;
+        if (s.ch == 1 && s.lo == 0 && s.hi > 0) {  // no upstream block exists before the first quantum: the input takes its own channelCount (2)
+          j.sp_block = 0;
+          j.sp_mode = 1;
+        } else if (s.from_source && pos == 0 && s.ch == 2 && s.lo > 0) {  // the source's idle block before its start had one channel
+          j.sp_block = s.lo;
+          j.sp_mode = 2;
+        }
+        j.first_change = j.pan ? d_first + k : nullptr;
+        scan = scan || (j.pan && j.sp_mode != 0);
+        qj.push_back(j);
+        s.ch = 2;  // the output block always has two channels (:41-47)
+      }
+      PannerJob* dq = nullptr;
+      if ((rc = env.scratch->upload(&dq, qj))) return rc;
+      int t = env.timer->begin(C_GAIN);
+      launch_panner(dq, (int)qj.size(), env.Npad, scan, ctx->stream);
+      env.timer->end(t);
+      env.launches += scan ? 2 : 1;
+      CU(cudaGetLastError());
     }
     // ---------------- GainNode (K2 + K4).  A gain directly followed by a convolver is fused into K5.
     if (!gains.empty()) {

@@ -23,6 +23,7 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
     const gac_buffer* buf = v.src;
     wait_ready(ctx, buf);  // asynchronous upload still in flight: order this voice batch behind it
     s.lo = s.hi = 0;
+    s.from_source = true;
     s.ch = buf->nch;  // the source emits a block with the buffer's channel count (AudioBufferSourceNode.cs:157-163)
     const float* src0 = buf->d;
     const float* src1 = buf->nch > 1 ? buf->d + buf->stride : buf->d;  // mono: 1 -> 2 up-mix copies the channel (AudioNodeInput.cs:201-213)
@@ -290,6 +291,8 @@ struct RenderArgs {
   bool sharded = false;
   int root = 0;
   bool sync = true;
+  float* h_inter = nullptr;  // interleaved host output [start_index + n_frames][inter_channels], or null (one graph)
+  int inter_channels = 0;
 };
 
 static int mix_into(RenderEnv& env, std::vector<MixJob>& jobs, std::vector<MixInput>& inputs) {
@@ -637,13 +640,23 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     for (int g = 0; g < a.n_graphs; g++) {
       for (int c = 0; c < a.n_out; c++) {
         const float* src = (c == 0 ? dest0[g] : dest1[g]) + a.first_frame;
-        if (a.h_out) {
+        if (a.h_inter) {
+          // (handled below: one interleaving pass over both rows)
+        } else if (a.h_out) {
           CU(cudaMemcpyAsync(a.h_out[(size_t)g * a.n_out + c] + a.start_index, src, sizeof(float) * (size_t)a.n_frames, cudaMemcpyDeviceToHost, ctx->stream));
         } else if (a.d_out) {
           CU(cudaMemcpyAsync(a.d_out + ((size_t)g * a.n_out + c) * (size_t)a.n_frames, src, sizeof(float) * (size_t)a.n_frames, cudaMemcpyDeviceToDevice,
                              ctx->stream));
         }
       }
+    }
+    if (a.h_inter) {  // ≙ the interleaving loop of ProcessBlockInterleaved (AudioContextBase.cs:127-160), for the whole render
+      float* d_inter = nullptr;
+      if ((rc = scratch.alloc(&d_inter, (size_t)a.n_frames * a.inter_channels))) return rc;
+      launch_interleave(dest0[0] + a.first_frame, a.n_out > 1 ? dest1[0] + a.first_frame : nullptr, d_inter, a.n_frames, a.inter_channels, ctx->stream);
+      env.launches++;
+      CU(cudaMemcpyAsync(a.h_inter + (size_t)a.start_index * a.inter_channels, d_inter, sizeof(float) * (size_t)a.n_frames * a.inter_channels,
+                         cudaMemcpyDeviceToHost, ctx->stream));
     }
     timer.end(t);
   }
@@ -689,6 +702,22 @@ extern "C" int gac_render(gac_context* ctx, const gac_graph* graph, int64_t firs
   a.n_frames = n_frames;
   a.h_out = out_channels;
   a.n_out = n_out_channels;
+  a.start_index = start_index;
+  return render_core(ctx, a);
+}
+// ≙ rendering with ProcessBlockInterleaved (AudioContextBase.cs:88-161) block after block into one interleaved array
+extern "C" int gac_render_interleaved(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames, float* interleaved,
+                                      int channels, int64_t start_index) {
+  if (!interleaved) return fail(GAC_ERR_INVALID_ARGUMENT, "interleaved buffer is null");
+  if (channels < 1 || channels > 32) return fail(GAC_ERR_OUT_OF_RANGE, "channels must be between 1 and 32");  // AudioContextBase.cs:93
+  RenderArgs a;
+  a.graphs = &graph;
+  a.n_graphs = 1;
+  a.first_frame = first_frame;
+  a.n_frames = n_frames;
+  a.h_inter = interleaved;
+  a.inter_channels = channels;
+  a.n_out = channels < 2 ? 1 : 2;  // usedChannels = min(channels, destination channels) (:125)
   a.start_index = start_index;
   return render_core(ctx, a);
 }

@@ -157,6 +157,30 @@ struct GainJob {
 };
 void launch_gain(const GainJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
 
+struct DelayJob {       // DelayNode: out[n] = d[n] >= 1 ? in[n - d[n]] : 0
+  const float* in[2];
+  float* out[2];        // distinct from `in`
+  const float* dt;      // a-rate DelayTime table (seconds) or nullptr
+  float dt_const;
+  int max_delay;        // (int)(maxDelayTime * sampleRate)
+  int64_t in_lo, in_hi; // frames where the input is non-silent
+};
+void launch_delay(const DelayJob* d_jobs, int n_jobs, int64_t n_frames, int sample_rate, cudaStream_t s);
+
+struct PannerJob {      // StereoPannerNode, in place
+  float* sig[2];
+  const float* pan;     // a-rate table or nullptr
+  float pan_const;
+  int mono;             // the input block has one channel (ProcessMono) — rows duplicated
+  int64_t lo, hi;
+  int64_t sp_block;     // first frame of the one quantum whose channel count differs (see k_panner), or a negative value
+  int sp_mode;          // 1: mono up-mixed to two equal channels, stereo formula; 2: stereo mixed down, mono formula
+  unsigned long long* first_change;  // device scalar (preset huge): first frame behind that quantum whose pan differs from the
+                                     // previous frame's — until then the gain pair of the odd quantum stays cached; nullptr = constant pan
+};
+// scan_changes: some job has sp_mode != 0 and a pan table (runs k_pan_first_change first)
+void launch_panner(const PannerJob* d_jobs, int n_jobs, int64_t n_frames, bool scan_changes, cudaStream_t s);
+
 struct BiquadJob {
   float* sig[2];
   const float* freq;   // a-rate table or nullptr
@@ -213,6 +237,8 @@ void launch_ir_scale_batch(const IrChanJob* d_jobs, int n_jobs, float calibratio
 // second-level spectra of a batch of channels that share the transform length M (<= 4096: radix-16 plan)
 void launch_fft2_prep_batch(const IrChanJob* d_jobs, int n_jobs, int B, int M, const float2* d_tab16, cudaStream_t s);
 
+// out[f*channels + c] = c == 0 ? c0[f] : c == 1 ? c1[f] : 0   (c1 may be null: one destination channel requested)
+void launch_interleave(const float* c0, const float* c1, float* out, int64_t n_frames, int channels, cudaStream_t s);
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
 // d_dst <- h_src (page-locked, 16-byte aligned, bytes a multiple of 16) by a copy kernel instead of the DMA engine
 void launch_copy_from_host(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s);

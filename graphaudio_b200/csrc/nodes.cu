@@ -13,6 +13,7 @@
 #include <math_constants.h>
 
 #include "gac_kernels.h"
+#include "biquad_math.cuh"
 
 namespace gac {
 
@@ -198,6 +199,102 @@ void launch_gain(const GainJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream
   }
 }
 
+// ============================================================================================ delay / stereo panner
+// DelayNode.Process (Nodes/DelayNode.cs:43-100): per sample d = clamp((int)(delayTime[i] * sampleRate), 0, max); the ring is read
+// BEFORE the input sample is written, and Read returns 0 for d <= 0 (:140-147) — so out[n] = d >= 1 ? x[n - d] : 0, with x = 0
+// before the render starts and on silent-flagged input blocks (which write zeros, :63-75).  A gather: nothing recursive.
+__global__ void __launch_bounds__(256) k_delay(const DelayJob* __restrict__ jobs, int64_t n_frames, int sample_rate) {
+  const DelayJob job = jobs[blockIdx.y];
+  const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (n >= n_frames) return;
+  const float t = job.dt ? job.dt[n] : job.dt_const;
+  int d = (int)(t * (float)sample_rate);  // float * int -> float product, truncated (:68,85)
+  d = d < 0 ? 0 : (d > job.max_delay ? job.max_delay : d);
+  const int64_t m = n - d;
+  const bool live = d >= 1 && m >= job.in_lo && m < job.in_hi;
+  job.out[0][n] = live ? job.in[0][m] : 0.f;
+  job.out[1][n] = live ? job.in[1][m] : 0.f;
+}
+void launch_delay(const DelayJob* d_jobs, int n_jobs, int64_t n_frames, int sample_rate, cudaStream_t s) {
+  if (n_jobs <= 0 || n_frames <= 0) return;
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+    k_delay<<<dim3((unsigned)((n_frames + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames, sample_rate);
+  }
+}
+
+// StereoPannerNode.Process (Nodes/StereoPannerNode.cs:36-153).  The node's cached gains are a pure function of the clamped pan
+// value (recomputed whenever it changes, :95-103 / :129-137), so every sample is independent; MathF.Cos / MathF.Sin are the
+// platform libm's cosf / sinf (sincosf_libm), the products and sums stay unfused (--fmad=false).
+__global__ void __launch_bounds__(256) k_panner(const PannerJob* __restrict__ jobs, int64_t n_frames) {
+  const PannerJob job = jobs[blockIdx.y];
+  const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (n >= n_frames) return;
+  float L = 0.f, R = 0.f;
+  if (n >= job.lo && n < job.hi) {  // silent-flagged input -> cleared output (:49-54)
+    float pan = job.pan ? job.pan[n] : job.pan_const;
+    pan = fminf(fmaxf(pan, -1.0f), 1.0f);
+    const float kPi = 3.14159265358979323846f;
+    float a = job.sig[0][n], b = job.sig[1][n];
+    float gl, gr;
+    // The input's channel count is computed from the upstream block of the PREVIOUS quantum (AudioNodeInput.cs:109 precedes :124),
+    // so one block can differ from the rest: a mono signal is up-mixed to two equal channels in the very first quantum (mode 1,
+    // rows are already duplicates), a stereo source that starts later is mixed DOWN to one channel in its first quantum (mode 2:
+    // (0 + L + R) * (1 / sqrt(2)), AudioNodeInput.cs:214-228).
+    bool mono = job.mono != 0;
+    if (n >= job.sp_block && n < job.sp_block + 128) {
+      mono = job.sp_mode == 2;
+      if (mono) a = (a + b) * (1.0f / sqrtf(2.0f));
+    }
+    // The node recomputes its gain pair only when the pan value CHANGES (:95-103, :129-137), with the formula of the variant that
+    // is running at that moment — so the pair computed in the odd first quantum stays in force, across the switch of variants,
+    // until the first sample whose pan differs from its predecessor's (first_change; never, for a constant pan).
+    bool mono_formula = mono;
+    if (job.sp_mode != 0 && n >= job.sp_block && (job.first_change == nullptr || n < (int64_t)*job.first_change)) mono_formula = job.sp_mode == 2;
+    const float x = mono_formula ? (pan + 1.0f) * 0.5f : (pan <= 0.0f ? pan + 1.0f : pan);
+    sincosf_libm(x * kPi / 2.0f, &gr, &gl);
+    if (mono) {  // ProcessMono :77-108
+      L = a * gl;
+      R = a * gr;
+    } else {  // ProcessStereo :110-152
+      if (pan <= 0.0f) {
+        L = a + b * gl;
+        R = b * gr;
+      } else {
+        L = a * gl;
+        R = b + a * gr;
+      }
+    }
+  }
+  job.sig[0][n] = L;
+  job.sig[1][n] = R;
+}
+// first frame behind the odd quantum whose (clamped) pan differs from its predecessor's; first_change must be preset to a huge value
+__global__ void __launch_bounds__(256) k_pan_first_change(const PannerJob* __restrict__ jobs, int64_t n_frames) {
+  const PannerJob job = jobs[blockIdx.y];
+  if (!job.pan || !job.first_change || job.sp_mode == 0) return;
+  const int64_t n0 = job.sp_block + 128 + ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  for (int64_t n = n0; n < n0 + 8 && n < n_frames && n < job.hi; n++) {
+    const float p = fminf(fmaxf(job.pan[n], -1.0f), 1.0f), q = fminf(fmaxf(job.pan[n - 1], -1.0f), 1.0f);
+    if (p != q) {
+      atomicMin(job.first_change, (unsigned long long)n);
+      break;
+    }
+  }
+}
+void launch_panner(const PannerJob* d_jobs, int n_jobs, int64_t n_frames, bool scan_changes, cudaStream_t s) {
+  if (n_jobs <= 0 || n_frames <= 0) return;
+  if (scan_changes)
+    for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+      int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+      k_pan_first_change<<<dim3((unsigned)((n_frames + 2047) / 2048), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames);
+    }
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+    k_panner<<<dim3((unsigned)((n_frames + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames);
+  }
+}
+
 // ============================================================================================ mix
 __global__ void __launch_bounds__(256) k_mix(const MixJob* __restrict__ jobs, const MixInput* __restrict__ inputs, int64_t n_frames) {
   const MixJob job = jobs[blockIdx.y];
@@ -302,6 +399,24 @@ void launch_copy_from_host(void* d_dst, const void* h_src, size_t bytes, cudaStr
   const size_t n16 = bytes / 16;
   if (n16 == 0) return;
   k_copy_from_host<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(d_dst), reinterpret_cast<const uint4*>(h_src), n16);
+}
+
+// planar destination rows -> interleaved frames with `channels` channels (AudioContextBase.cs:127-160: the destination's
+// channels first, the remaining ones zero)
+__global__ void __launch_bounds__(256) k_interleave(const float* __restrict__ c0, const float* __restrict__ c1, float* __restrict__ out,
+                                                    int64_t n_frames, int channels) {
+  const int64_t total = n_frames * channels;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t f = i / channels;
+    const int c = (int)(i - f * channels);
+    out[i] = c == 0 ? c0[f] : (c == 1 && c1 ? c1[f] : 0.0f);
+  }
+}
+void launch_interleave(const float* c0, const float* c1, float* out, int64_t n_frames, int channels, cudaStream_t s) {
+  const int64_t total = n_frames * channels;
+  if (total <= 0) return;
+  const int64_t want = (total + 255) / 256;
+  k_interleave<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(c0, c1, out, n_frames, channels);
 }
 
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s) { cudaMemsetAsync(p, 0, bytes, s); }

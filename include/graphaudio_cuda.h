@@ -129,7 +129,9 @@ typedef struct gac_param {
 typedef enum gac_op_kind {
   GAC_OP_BIQUAD = 1,   /* BiQuadFilterNode  Nodes/BiQuadFilterNode.cs:87-258 */
   GAC_OP_GAIN = 2,     /* GainNode          Nodes/GainNode.cs:29-61          */
-  GAC_OP_CONVOLVER = 3 /* ConvolverNode     Nodes/ConvolverNode.cs:102-155   */
+  GAC_OP_CONVOLVER = 3,/* ConvolverNode     Nodes/ConvolverNode.cs:102-155   */
+  GAC_OP_DELAY = 4,    /* DelayNode         Nodes/DelayNode.cs:43-149        */
+  GAC_OP_PANNER = 5    /* StereoPannerNode  Nodes/StereoPannerNode.cs:36-153 */
 } gac_op_kind;
 
 typedef enum gac_filter_type { /* FilterType, Nodes/BiQuadFilterNode.cs:288-298 */
@@ -146,11 +148,13 @@ typedef enum gac_filter_type { /* FilterType, Nodes/BiQuadFilterNode.cs:288-298 
 typedef struct gac_op_desc {
   int32_t kind;        /* gac_op_kind                                                         */
   int32_t filter_type; /* BIQUAD: gac_filter_type                                             */
-  gac_param p0;        /* BIQUAD: Frequency (a-rate)   GAIN: Gain (a-rate)                    */
+  gac_param p0;        /* BIQUAD: Frequency (a-rate)   GAIN: Gain (a-rate)   DELAY: DelayTime in seconds
+                          (a-rate)   PANNER: Pan (a-rate, -1 .. 1)                             */
   gac_param p1;        /* BIQUAD: Q (a-rate)                                                   */
   gac_param p2;        /* BIQUAD: Gain in dB (k-rate)                                          */
   const gac_ir* ir;    /* CONVOLVER: prepared impulse response; NULL ≙ ConvolverNode without a
                           Buffer, which outputs silence (ConvolverNode.cs:107-119)             */
+  double aux;          /* DELAY: maxDelayTime in seconds, (0, 10] (DelayNode.cs:22-29); else 0  */
 } gac_op_desc;
 
 /* One voice = AudioBufferSourceNode -> ops[0] -> ops[1] -> ... -> bus (or destination).
@@ -212,6 +216,13 @@ int gac_graph_destroy(gac_graph* graph);
  * device->host copy. */
 int gac_render(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames,
                float* const* out_channels, int n_out_channels, int64_t start_index);
+
+/* As gac_render, but the result is written INTERLEAVED: interleaved[(start_index + f) * channels + c], channels in 1..32,
+ * the destination's channels first and zeros in the others — what a caller gets from driving
+ * AudioContextBase.ProcessBlockInterleaved (AudioContextBase.cs:88-161) block after block (the output side of a file writer
+ * or a device callback).  The interleaving runs on the device; one device->host copy. */
+int gac_render_interleaved(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames,
+                           float* interleaved, int channels, int64_t start_index);
 
 /* As gac_render, but the result stays in HBM: d_out is a device pointer to [n_out_channels][n_frames]
  * float32 (row stride n_frames).  Asynchronous on the context's stream unless sync != 0. */

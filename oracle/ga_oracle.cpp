@@ -601,6 +601,93 @@ class Gain : public Node {
   BlockPtr ob;
 };
 
+// Nodes/DelayNode.cs
+class Delay : public Node {
+ public:
+  Delay(Context* c, double maxDelayTime);
+  void process() override;  // :43-100
+  struct Ring {              // CircularBuffer :124-149
+    std::vector<float> buf;
+    int writePos = 0;
+    explicit Ring(int size) : buf((size_t)size, 0.f) {}
+    void write(float v) {
+      buf[writePos] = v;
+      writePos = (writePos + 1) % (int)buf.size();
+    }
+    float read(int d) const {
+      if (d <= 0 || d > (int)buf.size()) return 0.f;
+      int pos = (writePos - d + (int)buf.size()) % (int)buf.size();
+      return buf[pos];
+    }
+  };
+  Param* delayTime;
+  int maxDelaySamples;
+  std::vector<Ring> rings;
+  BlockPtr ob;
+};
+
+// Nodes/StereoPannerNode.cs
+class StereoPanner : public Node {
+ public:
+  explicit StereoPanner(Context* c) : Node(c, 1, 1) {
+    inputs[0]->channelCount = 2;  // :24-26 (Speakers interpretation is the default mixing rule of MixBuffer)
+    inputs[0]->mode = ModeClampedMax;
+    pan = addParam(0.0f, -1.0f, 1.0f, true);
+  }
+  void process() override {
+    Block& in = *inputs[0]->buffer;
+    if (!ob || ob->channels != 2) ob = rent(2);
+    if (in.silent) { ob->clear(); outputs[0]->buffer = ob; return; }  // :49-54
+    float* oL = ob->ch(0);
+    float* oR = ob->ch(1);
+    const float kPi = 3.14159265358979323846f;  // MathF.PI
+    float gL = lastGainL, gR = lastGainR, lp = lastPan;
+    if (in.channels == 1) {  // ProcessMono :77-108
+      const float* x = in.ch(0);
+      for (int i = 0; i < kQuantum; i++) {
+        float p = Param::clampf(pan->values[i], -1.0f, 1.0f);
+        if (p != lp) {
+          float u = (p + 1.0f) * 0.5f;
+          gL = cosf(u * kPi / 2.0f);
+          gR = sinf(u * kPi / 2.0f);
+          lp = p;
+        }
+        float v = x[i];
+        oL[i] = v * gL;
+        oR[i] = v * gR;
+      }
+    } else {  // ProcessStereo :110-152
+      const float* xL = in.ch(0);
+      const float* xR = in.ch(1);
+      for (int i = 0; i < kQuantum; i++) {
+        float p = Param::clampf(pan->values[i], -1.0f, 1.0f);
+        if (p != lp) {
+          float u = p <= 0.0f ? p + 1.0f : p;
+          gL = cosf(u * kPi / 2.0f);
+          gR = sinf(u * kPi / 2.0f);
+          lp = p;
+        }
+        float a = xL[i], b = xR[i];
+        if (p <= 0.0f) {
+          oL[i] = a + b * gL;
+          oR[i] = b * gR;
+        } else {
+          oL[i] = a * gL;
+          oR[i] = b + a * gR;
+        }
+      }
+    }
+    lastPan = lp;
+    lastGainL = gL;
+    lastGainR = gR;
+    ob->markNonSilent();
+    outputs[0]->buffer = ob;
+  }
+  Param* pan;
+  float lastPan = std::numeric_limits<float>::quiet_NaN(), lastGainL = 0.5f, lastGainR = 0.5f;
+  BlockPtr ob;
+};
+
 // Nodes/BiQuadFilterNode.cs
 class Biquad : public Node {
  public:
@@ -868,6 +955,35 @@ class BufferSource : public Node {
   BlockPtr ob;
 };
 
+Delay::Delay(Context* c, double maxDelayTime) : Node(c, 1, 1) {  // :22-41
+  maxDelaySamples = (int)(maxDelayTime * c->sampleRate);
+  for (int i = 0; i < 2; i++) rings.emplace_back(maxDelaySamples);
+  delayTime = addParam(0.0f, 0.0f, (float)maxDelayTime, true);
+}
+void Delay::process() {
+  Block* in = inputs[0]->buffer.get();
+  int channels = in ? in->channels : 2;
+  while ((int)rings.size() < channels) rings.emplace_back(maxDelaySamples);  // EnsureChannelCount :102-113
+  if (!ob || ob->channels != channels) ob = rent(channels);
+  bool hasAudio = false;
+  const bool silentIn = !in || in->silent;
+  for (int ch = 0; ch < channels; ch++) {
+    float* o = ob->ch(ch);
+    const float* x = silentIn ? nullptr : in->ch(ch);
+    for (int i = 0; i < kQuantum; i++) {
+      int d = (int)(delayTime->values[i] * ctx->sampleRate);  // float * int -> float, truncated (:68,85)
+      d = d < 0 ? 0 : (d > maxDelaySamples ? maxDelaySamples : d);
+      o[i] = rings[ch].read(d);
+      rings[ch].write(x ? x[i] : 0.f);
+      if (o[i] != 0.f) hasAudio = true;
+    }
+  }
+  // the node keeps ONE pooled block and only ever sets the flag (:96-97): silent until the first block that carries audio,
+  // non-silent from then on (until a channel-count change rents a fresh block)
+  if (hasAudio) ob->markNonSilent();
+  outputs[0]->buffer = ob;
+}
+
 Context::Context(int fs) : sampleRate(fs) {
   destination = new Destination(this);
   nodes.emplace_back(destination);
@@ -1007,9 +1123,17 @@ int ora_node_create(void* c, int kind) {
     case 1: n = new Biquad(ctx); break;
     case 2: n = new Gain(ctx); break;
     case 3: n = new Convolver(ctx); break;
+    case 4: n = new StereoPanner(ctx); break;
     default: return -1;
   }
   ctx->nodes.emplace_back(n);
+  return (int)ctx->nodes.size() - 1;
+}
+
+int ora_delay_create(void* c, double maxDelayTime) {  // DelayNode(context, maxDelayTime) :22-26
+  auto* ctx = (Context*)c;
+  if (maxDelayTime <= 0 || maxDelayTime > 10) return -1;  // ArgumentOutOfRangeException
+  ctx->nodes.emplace_back(new Delay(ctx, maxDelayTime));
   return (int)ctx->nodes.size() - 1;
 }
 

@@ -57,6 +57,7 @@ def lib():
     L.ora_context_destroy.argtypes = [C.c_void_p]
     L.ora_buffer_create.argtypes = [C.c_void_p, fpp, C.c_int, C.c_int64, C.c_int]
     L.ora_node_create.argtypes = [C.c_void_p, C.c_int]
+    L.ora_delay_create.argtypes = [C.c_void_p, C.c_double]
     L.ora_connect.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_param_set_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
     L.ora_param_event.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
@@ -340,6 +341,27 @@ class ConvolverNode(AudioNode):
         if r != 0:
             raise InvalidOperationException("Impulse response buffer sample rate must match the audio context sample rate.")
         self._buffer = b
+
+
+class StereoPannerNode(AudioNode):
+    """Nodes/StereoPannerNode.cs"""
+    _KIND = 4
+
+    def __init__(self, context):
+        super().__init__(context)
+        self.Pan = AudioParam(self, 0, 0.0, -1.0, 1.0)
+
+
+class DelayNode(AudioNode):
+    """Nodes/DelayNode.cs"""
+
+    def __init__(self, context, maxDelayTime=1.0):
+        if maxDelayTime <= 0 or maxDelayTime > 10:
+            raise ArgumentOutOfRangeException("maxDelayTime")  # :25-26
+        self._ctx = context
+        self.Context = context
+        self._id = lib().ora_delay_create(context._h, float(maxDelayTime))
+        self.DelayTime = AudioParam(self, 0, 0.0, 0.0, float(np.float32(maxDelayTime)))
 
 
 class OfflineAudioContext:

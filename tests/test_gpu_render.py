@@ -267,3 +267,29 @@ def test_biquad_slow_drift_takes_the_general_walk_and_the_per_row_layout():
     yo = build(O).Render(n)
     assert np.abs(yo).max() > 1e-2
     assert np.abs(yg - yo).max() <= TOL
+
+
+def test_interleaved_render_equals_planar_render():
+    """gac_render_interleaved ≙ ProcessBlockInterleaved block after block (AudioContextBase.cs:88-161)."""
+    import graphaudio_b200 as G
+
+    def build():
+        ctx = G.OfflineAudioContext(48000)
+        s = G.AudioBufferSourceNode(ctx)
+        s.Buffer = G.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(900 + c, 5000) for c in range(2)], 48000)
+        g = G.GainNode(ctx)
+        g.Gain.Value = 0.5
+        s.Connect(g).Connect(ctx.Destination)
+        s.Start()
+        return ctx
+    planar = build().Render(4096)
+    for ch in (1, 2, 5):
+        ctx = build()
+        a = ctx.RenderInterleaved(1024, ch).reshape(-1, ch)
+        b = ctx.RenderInterleaved(3072, ch).reshape(-1, ch)  # the timeline continues
+        inter = np.concatenate([a, b])
+        for c in range(ch):
+            assert np.array_equal(inter[:, c], planar[c] if c < 2 else np.zeros(4096, np.float32))
+        ctx.Dispose()
+    with pytest.raises(G.ArgumentOutOfRangeException):
+        build().RenderInterleaved(128, 33)

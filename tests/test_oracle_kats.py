@@ -285,3 +285,102 @@ def test_golden_fixture(name, fn):
     assert y.shape == ref.shape
     # identical on the generating machine; other glibc builds may differ in the last ulp of sinf/cosf/pow
     assert np.abs(y - ref).max() <= 1e-6
+
+
+# ---------------------------------------------------------------- DelayNode / StereoPannerNode
+def _render_chain(make_node, src, n, fs=48000, start=0.0):
+    ctx = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(ctx)
+    s.Buffer = O.PlayableAudioBuffer.FromChannelArrays(src, fs)
+    node = make_node(ctx)
+    s.Connect(node).Connect(ctx.Destination)
+    s.Start(start)
+    return ctx.Render(n)
+
+
+def test_delay_node_is_an_integer_shift_and_zero_delay_reads_nothing():
+    # DelayNode.cs:68-72: d = clamp((int)(delayTime * fs), 0, max); CircularBuffer.Read returns 0 for d <= 0 (:140-143) and is read
+    # before the write, so out[n] = x[n - d] for d >= 1 and silence for d = 0
+    x = [synth.splitmix_uniform(700 + c, 128 * 20) for c in range(2)]
+    for delay, d in ((0.0, 0), (1.0 / 48000, 1), (0.01, 480), (0.0301, 1444), (0.05, 2400), (0.2, 2400)):  # 0.2 s clamps to the 0.05 s maximum
+        def make(ctx):
+            node = O.DelayNode(ctx, 0.05)
+            node.DelayTime.Value = delay
+            return node
+        y = _render_chain(make, x, 128 * 40)
+        emitted = 128 * 19  # the source drops its final block (AudioBufferSourceNode.cs:360-368)
+        want = np.zeros((2, 128 * 40), np.float32)
+        if d >= 1:
+            for c in range(2):
+                want[c, d:d + emitted] = x[c][:emitted]
+        assert np.array_equal(y, want), delay
+
+
+def test_stereo_panner_equal_power_formulas():
+    # StereoPannerNode.cs:77-152 with MathF.Cos / MathF.Sin = libm cosf / sinf on x * pi / 2 formed in float32.
+    # Two properties of the reference that a restatement has to keep:
+    #  (1) the node's input is ClampedMax(2) and AudioNodeInput.Pull computes its channel count from the upstream block of the
+    #      PREVIOUS quantum (AudioNodeInput.cs:109 precedes :124): in the very first quantum there is none and the input has 2
+    #      channels (a mono source is up-mixed by copy and runs through ProcessStereo); a stereo source that starts later is mixed
+    #      down to one channel, (L + R) / sqrt(2), in its first quantum (the idle source block before it had one channel) and runs
+    #      through ProcessMono;
+    #  (2) the gain pair is recomputed only when the pan value changes (:95-103, :129-137), by whichever variant is running: with a
+    #      constant pan the pair of that odd first quantum stays in force for the rest of the render.
+    pi = np.float32(np.pi)
+    mono = [synth.splitmix_uniform(710, 128 * 10)]
+    stereo = [synth.splitmix_uniform(711 + c, 128 * 10) for c in range(2)]
+    n = 128 * 9
+
+    def gains(x):
+        a = np.float32(np.float32(x) * pi) / np.float32(2.0)
+        # float32-rounded cos / sin of a float32 argument (the double evaluation rounds identically for these pan values)
+        return np.float32(np.cos(np.float64(a))), np.float32(np.sin(np.float64(a)))
+
+    def g_mono(p):
+        return gains((p + np.float32(1.0)) * np.float32(0.5))
+
+    def g_stereo(p):
+        return gains(p + np.float32(1.0) if p <= 0 else p)
+
+    def run_mono(x, g):
+        return np.stack([x * g[0], x * g[1]])
+
+    def run_stereo(L, R, p, g):
+        return np.stack([L + R * g[0], R * g[1]]) if p <= 0 else np.stack([L * g[0], R + L * g[1]])
+
+    for pan in (-1.0, -0.5, 0.0, 0.25, 1.0):
+        def make(ctx):
+            node = O.StereoPannerNode(ctx)
+            node.Pan.Value = pan
+            return node
+        p = np.float32(pan)
+        ym = _render_chain(make, mono, n)
+        x = mono[0][:n]
+        assert np.array_equal(ym[:, :128], run_stereo(x[:128], x[:128], p, g_stereo(p)))  # first quantum: two equal channels
+        assert np.array_equal(ym[:, 128:], run_mono(x[128:], g_stereo(p)))                # ... whose gain pair stays cached
+        ys = _render_chain(make, stereo, n)
+        assert np.array_equal(ys, run_stereo(stereo[0][:n], stereo[1][:n], p, g_stereo(p)))
+        # the same stereo source started in the third quantum: its first quantum arrives mixed down
+        yl = _render_chain(make, stereo, n + 256, start=256.0 / 48000)
+        assert not yl[:, :256].any()
+        down = (stereo[0][:128] + stereo[1][:128]) * (np.float32(1.0) / np.sqrt(np.float32(2.0)))
+        assert np.array_equal(yl[:, 256:384], run_mono(down, g_mono(p)))
+        assert np.array_equal(yl[:, 384:], run_stereo(stereo[0][128:n], stereo[1][128:n], p, g_mono(p)))
+    # full left keeps the left channel and adds the right one at unity; full right mirrors it
+    assert gains(np.float32(0.0)) == (np.float32(1.0), np.float32(0.0))
+
+    # a pan that changes with every sample is recomputed with the running variant's formula: mono source, quanta >= 1
+    def make_sweep(ctx):
+        node = O.StereoPannerNode(ctx)
+        node.Pan.SetValueAtTime(-0.9, 0.0)
+        node.Pan.LinearRampToValueAtTime(0.9, 0.02)  # 960 samples
+        return node
+    ym = _render_chain(make_sweep, mono, 128 * 7)
+    ctx = O.OfflineAudioContext(48000)
+    probe = O.StereoPannerNode(ctx)
+    probe.Pan.SetValueAtTime(-0.9, 0.0)
+    probe.Pan.LinearRampToValueAtTime(0.9, 0.02)
+    pv = probe.Pan.evaluate(7)
+    for i in (128, 300, 700, 890):
+        g = g_mono(np.float32(pv[i]))
+        assert ym[0, i] == mono[0][i] * g[0] and ym[1, i] == mono[0][i] * g[1]

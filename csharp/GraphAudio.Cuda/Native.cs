@@ -105,6 +105,12 @@ internal static unsafe partial class Native
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
     internal static partial int BufferCreate(IntPtr ctx, float** channels, int channelCount, long frames, int sampleRate, out IntPtr buffer);
 
+    /// <summary>Interleaved file samples (0 s16, 1 s24, 2 s32, 3 f32), converted and de-interleaved on the device — the
+    /// upload behind AudioDecoder.LoadFromStream (GraphAudio.IO/LibsndfileDecoder.cs:195-220).</summary>
+    [LibraryImport(Lib, EntryPoint = "gac_buffer_create_interleaved")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int BufferCreateInterleaved(IntPtr ctx, void* samples, int sampleFormat, int channelCount, long frames, int sampleRate, out IntPtr buffer);
+
     [LibraryImport(Lib, EntryPoint = "gac_buffer_destroy")]
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
     internal static partial int BufferDestroy(IntPtr buffer);
@@ -153,6 +159,11 @@ internal static unsafe partial class Native
     [LibraryImport(Lib, EntryPoint = "gac_render")]
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
     internal static partial int Render(IntPtr ctx, IntPtr graph, long firstFrame, long frames, float** outChannels, int channelCount, long startIndex);
+
+    /// <summary>The render written interleaved (≙ ProcessBlockInterleaved block after block, AudioContextBase.cs:88-161).</summary>
+    [LibraryImport(Lib, EntryPoint = "gac_render_interleaved")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int RenderInterleaved(IntPtr ctx, IntPtr graph, long firstFrame, long frames, float* interleaved, int channels, long startIndex);
 
     [LibraryImport(Lib, EntryPoint = "gac_render_batch")]
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]

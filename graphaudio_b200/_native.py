@@ -23,6 +23,7 @@ GAC_ERR_NCCL = -8
 GAC_ERR_UNSUPPORTED = -9
 
 GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER, GAC_OP_DELAY, GAC_OP_PANNER = 1, 2, 3, 4, 5
+GAC_SAMPLE_S16, GAC_SAMPLE_S24, GAC_SAMPLE_S32, GAC_SAMPLE_F32 = 0, 1, 2, 3
 
 fp = C.POINTER(C.c_float)
 fpp = C.POINTER(fp)
@@ -87,6 +88,7 @@ SIGNATURES = {
     "gac_context_destroy": (C.c_int, [C.c_void_p]),
     "gac_synchronize": (C.c_int, [C.c_void_p]),
     "gac_buffer_create": (C.c_int, [C.c_void_p, fpp, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
+    "gac_buffer_create_interleaved": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     "gac_buffer_destroy": (C.c_int, [C.c_void_p]),
     "gac_ir_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gac_ir_destroy": (C.c_int, [C.c_void_p]),

@@ -79,11 +79,54 @@ class PlayableAudioBuffer:
             raise ArgumentOutOfRangeException("Channel count must be between 1 and 32")
         if sample_rate <= 0:
             raise ArgumentOutOfRangeException("Sample rate must be positive")
-        self.channels = [_f32(c) for c in channels]
+        self._channels = [_f32(c) for c in channels]
+        self._raw = None  # (interleaved samples as uint8, gac_sample_format) when the buffer came from a decoder (FromInterleaved)
         self.SampleRate = int(sample_rate)
-        self.NumberOfChannels = len(self.channels)
-        self.Length = int(self.channels[0].shape[0])
+        self.NumberOfChannels = len(self._channels)
+        self.Length = int(self._channels[0].shape[0])
         self._handles = {}
+
+    _SAMPLE_BYTES = {N.GAC_SAMPLE_S16: 2, N.GAC_SAMPLE_S24: 3, N.GAC_SAMPLE_S32: 4, N.GAC_SAMPLE_F32: 4}
+
+    @staticmethod
+    def FromInterleaved(samples, sampleFormat, numberOfChannels, sampleRate):
+        """The buffer a decoder produces (GraphAudio.IO AudioDecoder.LoadFromStream, LibsndfileDecoder.cs:195-220), kept as the
+        file's interleaved little-endian samples: they are uploaded as they are and converted + de-interleaved on the device
+        (gac_buffer_create_interleaved).  `samples`: bytes-like / uint8 array."""
+        if numberOfChannels < 1 or numberOfChannels > 32:
+            raise ArgumentOutOfRangeException("Channel count must be between 1 and 32")
+        if sampleRate <= 0:
+            raise ArgumentOutOfRangeException("Sample rate must be positive")
+        if sampleFormat not in PlayableAudioBuffer._SAMPLE_BYTES:
+            raise ArgumentException("unknown sample format")
+        raw = samples if isinstance(samples, np.ndarray) else np.frombuffer(samples, np.uint8)
+        raw = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+        frame_bytes = PlayableAudioBuffer._SAMPLE_BYTES[sampleFormat] * numberOfChannels
+        b = PlayableAudioBuffer.__new__(PlayableAudioBuffer)
+        b._channels = None
+        b.SampleRate, b.NumberOfChannels, b.Length = int(sampleRate), int(numberOfChannels), int(raw.shape[0] // frame_bytes)
+        b._raw = (raw[:b.Length * frame_bytes], int(sampleFormat))
+        b._handles = {}
+        return b
+
+    @property
+    def channels(self):
+        """Planar float32 channel data (GetChannelData, PlayableAudioBuffer.cs:72); converted on the host on first access for
+        buffers that hold interleaved file samples."""
+        if self._channels is None:
+            raw, fmt = self._raw
+            n, c = self.Length, self.NumberOfChannels
+            if fmt == N.GAC_SAMPLE_S16:
+                x = raw.view("<i2").astype(np.float32) * np.float32(2.0 ** -15)
+            elif fmt == N.GAC_SAMPLE_S24:
+                t = raw.reshape(-1, 3).astype(np.int32)
+                x = (((t[:, 0] << 8) | (t[:, 1] << 16) | (t[:, 2] << 24)) >> 8).astype(np.float32) * np.float32(2.0 ** -23)
+            elif fmt == N.GAC_SAMPLE_S32:
+                x = raw.view("<i4").astype(np.float32) * np.float32(2.0 ** -31)
+            else:
+                x = raw.view("<f4").astype(np.float32)
+            self._channels = [np.ascontiguousarray(x.reshape(n, c)[:, k]) for k in range(c)]
+        return self._channels
 
     @staticmethod
     def FromChannelArrays(channelData, sampleRate):  # :122-143
@@ -108,9 +151,14 @@ class PlayableAudioBuffer:
         ctx = ctx._root()  # forks share the parent's device handle
         h = self._handles.get(id(ctx))
         if h is None:
-            ptrs = (N.fp * self.NumberOfChannels)(*[_fptr(c) for c in self.channels])
             out = C.c_void_p()
-            check(N.lib().gac_buffer_create(ctx._h, ptrs, self.NumberOfChannels, self.Length, self.SampleRate, C.byref(out)))
+            if self._raw is not None:
+                raw, fmt = self._raw
+                check(N.lib().gac_buffer_create_interleaved(ctx._h, raw.ctypes.data_as(C.c_void_p), fmt, self.NumberOfChannels, self.Length,
+                                                            self.SampleRate, C.byref(out)))
+            else:
+                ptrs = (N.fp * self.NumberOfChannels)(*[_fptr(c) for c in self.channels])
+                check(N.lib().gac_buffer_create(ctx._h, ptrs, self.NumberOfChannels, self.Length, self.SampleRate, C.byref(out)))
             h = out.value
             self._handles[id(ctx)] = h
             ctx._owned_buffers.append(h)

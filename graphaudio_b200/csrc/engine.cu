@@ -552,6 +552,44 @@ extern "C" int gac_buffer_create(gac_context* ctx, const float* const* channels,
   *out = b.release();
   return GAC_OK;
 }
+// ≙ AudioDecoder.LoadFromStream (GraphAudio.IO/LibsndfileDecoder.cs:195-220) behind the container parser: the interleaved samples
+// of the file go to the device as they are (half the PCIe bytes for 16-bit material) and are converted and de-interleaved there
+extern "C" int gac_buffer_create_interleaved(gac_context* ctx, const void* samples, int sample_format, int n_channels, int64_t n_frames,
+                                             int sample_rate, gac_buffer** out) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!samples || !out) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (n_channels < 1 || n_channels > 32) return fail(GAC_ERR_OUT_OF_RANGE, "Channel count must be between 1 and 32");
+  if (n_frames < 0) return fail(GAC_ERR_OUT_OF_RANGE, "Length must be non-negative");
+  if (sample_rate <= 0) return fail(GAC_ERR_OUT_OF_RANGE, "Sample rate must be positive");
+  if (sample_format < GAC_SAMPLE_S16 || sample_format > GAC_SAMPLE_F32) return fail(GAC_ERR_INVALID_ARGUMENT, "unknown sample format %d", sample_format);
+  static const int bytes_of[4] = {2, 3, 4, 4};
+  CU(cudaSetDevice(ctx->device));
+  auto b = std::make_unique<gac_buffer>();
+  b->ctx = ctx;
+  b->nch = n_channels;
+  b->n = n_frames;
+  b->rate = sample_rate;
+  b->stride = ((n_frames + 8 + 63) / 64) * 64;
+  const bool async = ctx->async_upload;
+  cudaStream_t st = async ? ctx->copy_stream : ctx->stream;
+  const size_t raw_bytes = (size_t)n_frames * n_channels * bytes_of[sample_format];
+  void* d_raw = nullptr;
+  CU(cudaMallocAsync(&b->d, sizeof(float) * ((size_t)b->stride * n_channels + 64), st));
+  CU(cudaMallocAsync(&d_raw, std::max<size_t>(raw_bytes, 16), st));
+  if (raw_bytes) CU(cudaMemcpyAsync(d_raw, samples, raw_bytes, cudaMemcpyHostToDevice, st));
+  launch_deinterleave(d_raw, sample_format, n_channels, n_frames, b->d, b->stride, st);
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_raw, st));
+  if (async) {
+    b->ready = take_event(ctx);
+    CU(cudaEventRecord(b->ready, st));
+  } else {
+    CU(cudaStreamSynchronize(st));
+  }
+  *out = b.release();
+  return GAC_OK;
+}
 extern "C" int gac_buffer_destroy(gac_buffer* buf) {
   if (!buf) return fail(GAC_ERR_INVALID_ARGUMENT, "buffer is null");
   if (buf->ir_refs > 0) {  // an impulse response prepared from it has not been used yet: it goes when that one is prepared / destroyed

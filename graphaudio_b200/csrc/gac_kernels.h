@@ -237,6 +237,8 @@ void launch_ir_scale_batch(const IrChanJob* d_jobs, int n_jobs, float calibratio
 // second-level spectra of a batch of channels that share the transform length M (<= 4096: radix-16 plan)
 void launch_fft2_prep_batch(const IrChanJob* d_jobs, int n_jobs, int B, int M, const float2* d_tab16, cudaStream_t s);
 
+// interleaved samples (fmt 0 s16, 1 s24, 2 s32, 3 f32) -> planar float32 rows d_out[c*stride + f], normalised like sf_readf_float
+void launch_deinterleave(const void* d_raw, int fmt, int n_channels, int64_t n_frames, float* d_out, int64_t stride, cudaStream_t s);
 // out[f*channels + c] = c == 0 ? c0[f] : c == 1 ? c1[f] : 0   (c1 may be null: one destination channel requested)
 void launch_interleave(const float* c0, const float* c1, float* out, int64_t n_frames, int channels, cudaStream_t s);
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);

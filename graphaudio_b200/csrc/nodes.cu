@@ -401,6 +401,31 @@ void launch_copy_from_host(void* d_dst, const void* h_src, size_t bytes, cudaStr
   k_copy_from_host<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(d_dst), reinterpret_cast<const uint4*>(h_src), n16);
 }
 
+// interleaved file samples -> planar float32 rows, the conversion libsndfile's sf_readf_float applies (normalised floats:
+// 16-bit * 2^-15, 24-bit * 2^-23, 32-bit (float)x * 2^-31, float32 as is) followed by the de-interleave of
+// AudioDecoder.DecodePlanar (GraphAudio.IO/LibsndfileDecoder.cs:195-220).  thread = frame; fmt: 0 s16, 1 s24 (3 bytes, LE), 2 s32, 3 f32
+__global__ void __launch_bounds__(256) k_deinterleave(const unsigned char* __restrict__ raw, int fmt, int n_channels, int64_t n_frames,
+                                                      float* __restrict__ out, int64_t stride) {
+  const int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (f >= n_frames) return;
+  for (int c = 0; c < n_channels; c++) {
+    const int64_t i = f * n_channels + c;
+    float v;
+    if (fmt == 0) v = (float)reinterpret_cast<const short*>(raw)[i] * (1.0f / 32768.0f);
+    else if (fmt == 1) {
+      const unsigned char* p = raw + 3 * i;
+      const int x = (int)((unsigned)p[0] << 8 | (unsigned)p[1] << 16 | (unsigned)p[2] << 24) >> 8;  // sign-extended 24 bits
+      v = (float)x * (1.0f / 8388608.0f);
+    } else if (fmt == 2) v = (float)reinterpret_cast<const int*>(raw)[i] * (1.0f / 2147483648.0f);
+    else v = reinterpret_cast<const float*>(raw)[i];
+    out[c * stride + f] = v;
+  }
+}
+void launch_deinterleave(const void* d_raw, int fmt, int n_channels, int64_t n_frames, float* d_out, int64_t stride, cudaStream_t s) {
+  if (n_frames <= 0) return;
+  k_deinterleave<<<(unsigned)((n_frames + 255) / 256), 256, 0, s>>>(reinterpret_cast<const unsigned char*>(d_raw), fmt, n_channels, n_frames, d_out, stride);
+}
+
 // planar destination rows -> interleaved frames with `channels` channels (AudioContextBase.cs:127-160: the destination's
 // channels first, the remaining ones zero)
 __global__ void __launch_bounds__(256) k_interleave(const float* __restrict__ c0, const float* __restrict__ c1, float* __restrict__ out,

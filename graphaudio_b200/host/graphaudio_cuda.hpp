@@ -141,7 +141,7 @@ class AudioNode : public std::enable_shared_from_this<AudioNode> {
     }
     return destination;
   }
-  enum class Kind { Destination, Source, Biquad, Gain, Convolver };
+  enum class Kind { Destination, Source, Biquad, Gain, Convolver, Delay, Panner };
   virtual Kind NodeKind() const = 0;
 
  protected:
@@ -189,6 +189,22 @@ class GainNode : public AudioNode {  // Nodes/GainNode.cs:16-25
  public:
   AudioParam Gain{1.0f, std::numeric_limits<float>::lowest(), std::numeric_limits<float>::max()};
   Kind NodeKind() const override { return Kind::Gain; }
+};
+
+class DelayNode : public AudioNode {  // Nodes/DelayNode.cs:22-41
+ public:
+  explicit DelayNode(double maxDelayTime = 1.0) : MaxDelayTime(maxDelayTime), DelayTime(0.f, 0.f, (float)maxDelayTime) {
+    if (maxDelayTime <= 0 || maxDelayTime > 10) throw ArgumentOutOfRangeException("maxDelayTime");  // :25-26
+  }
+  const double MaxDelayTime;
+  AudioParam DelayTime;
+  Kind NodeKind() const override { return Kind::Delay; }
+};
+
+class StereoPannerNode : public AudioNode {  // Nodes/StereoPannerNode.cs:21-34
+ public:
+  AudioParam Pan{0.f, -1.f, 1.f};
+  Kind NodeKind() const override { return Kind::Panner; }
 };
 
 class ConvolverNode : public AudioNode {  // Nodes/ConvolverNode.cs
@@ -243,6 +259,8 @@ class OfflineAudioContext {
   std::shared_ptr<AudioBufferSourceNode> CreateBufferSource() { return Keep(std::make_shared<AudioBufferSourceNode>()); }
   std::shared_ptr<BiQuadFilterNode> CreateBiQuadFilter() { return Keep(std::make_shared<BiQuadFilterNode>(sampleRate_)); }
   std::shared_ptr<GainNode> CreateGain() { return Keep(std::make_shared<GainNode>()); }
+  std::shared_ptr<DelayNode> CreateDelay(double maxDelayTime = 1.0) { return Keep(std::make_shared<DelayNode>(maxDelayTime)); }
+  std::shared_ptr<StereoPannerNode> CreateStereoPanner() { return Keep(std::make_shared<StereoPannerNode>()); }
   std::shared_ptr<ConvolverNode> CreateConvolver() { return Keep(std::make_shared<ConvolverNode>(ctx_, sampleRate_)); }
 
   // Render(float[][] output, int frameCount, int startIndex = 0)  (OfflineAudioContext.cs:30-102)
@@ -296,6 +314,12 @@ class OfflineAudioContext {
       }
       case AudioNode::Kind::Gain: o.kind = GAC_OP_GAIN; o.p0 = static_cast<GainNode*>(n)->Gain.Desc(); break;
       case AudioNode::Kind::Convolver: o.kind = GAC_OP_CONVOLVER; o.ir = static_cast<ConvolverNode*>(n)->ir_; break;
+      case AudioNode::Kind::Delay: {
+        auto* d = static_cast<DelayNode*>(n);
+        o.kind = GAC_OP_DELAY; o.p0 = d->DelayTime.Desc(); o.aux = d->MaxDelayTime;
+        break;
+      }
+      case AudioNode::Kind::Panner: o.kind = GAC_OP_PANNER; o.p0 = static_cast<StereoPannerNode*>(n)->Pan.Desc(); break;
       default: throw NotSupportedException("node type outside the accelerated path");
     }
     return o;

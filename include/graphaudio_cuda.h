@@ -89,6 +89,13 @@ int gac_synchronize(gac_context* ctx);
  * copies (PlayableAudioBuffer.cs:84-93).  1..32 channels, equal lengths. */
 int gac_buffer_create(gac_context* ctx, const float* const* channels, int n_channels, int64_t n_frames,
                       int sample_rate, gac_buffer** out);
+
+/* ≙ GraphAudio.IO's AudioDecoder.LoadFromStream (GraphAudio.IO/LibsndfileDecoder.cs:195-220) behind the container parser: the
+ * file's INTERLEAVED samples are uploaded as they are and converted + de-interleaved on the device, with the normalisation
+ * libsndfile's sf_readf_float applies (16-bit * 2^-15, 24-bit * 2^-23, 32-bit (float)x * 2^-31, float32 unchanged).  Little-endian. */
+typedef enum gac_sample_format { GAC_SAMPLE_S16 = 0, GAC_SAMPLE_S24 = 1, GAC_SAMPLE_S32 = 2, GAC_SAMPLE_F32 = 3 } gac_sample_format;
+int gac_buffer_create_interleaved(gac_context* ctx, const void* samples, int sample_format, int n_channels,
+                                  int64_t n_frames, int sample_rate, gac_buffer** out);
 int gac_buffer_destroy(gac_buffer* buf);
 
 /* ---- ConvolverNode.Buffer = ir  (Nodes/ConvolverNode.cs:25-79 -> PartitionedConvolver ctor

@@ -281,7 +281,7 @@ struct Scratch {
   ~Scratch() { release(); }
 };
 
-enum Cat { C_SOURCE, C_AUTO, C_BIQUAD, C_GAIN, C_FFT_FWD, C_MAC, C_FFT_INV, C_MIX, C_D2H, C_COUNT };
+enum Cat { C_SOURCE, C_AUTO, C_BIQUAD, C_GAIN, C_FFT_FWD, C_MAC, C_FFT_INV, C_MIX, C_D2H, C_DELAY, C_PANNER, C_COUNT };
 struct Timer {
   gac_context* ctx;
   struct Span {
@@ -326,6 +326,8 @@ struct Timer {
     st->ms_fft_inv = acc[C_FFT_INV];
     st->ms_mix = acc[C_MIX];
     st->ms_d2h = acc[C_D2H];
+    st->ms_delay = acc[C_DELAY];
+    st->ms_panner = acc[C_PANNER];
   }
   ~Timer() {
     for (auto& s : spans) {
@@ -1373,7 +1375,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       }
       DelayJob* dd = nullptr;
       if ((rc = env.scratch->upload(&dd, dj))) return rc;
-      int t = env.timer->begin(C_GAIN);
+      int t = env.timer->begin(C_DELAY);
       launch_delay(dd, (int)dj.size(), env.Npad, ctx->fs, ctx->stream);
       env.timer->end(t);
       env.launches += 1;
@@ -1420,7 +1422,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       }
       PannerJob* dq = nullptr;
       if ((rc = env.scratch->upload(&dq, qj))) return rc;
-      int t = env.timer->begin(C_GAIN);
+      int t = env.timer->begin(C_PANNER);
       launch_panner(dq, (int)qj.size(), env.Npad, scan, ctx->stream);
       env.timer->end(t);
       env.launches += scan ? 2 : 1;

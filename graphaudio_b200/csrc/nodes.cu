@@ -11,6 +11,7 @@
 //   mix k_mix                         AudioNodeInput.Pull/MixBuffer (AudioNodeInput.cs:100-138,182-244)
 //   K0  k_ir_scale                    PartitionedConvolver.CalculateNormalizationScale (PartitionedConvolver.cs:93-102)
 #include <math_constants.h>
+#include <cstdint>
 
 #include "gac_kernels.h"
 #include "biquad_math.cuh"
@@ -205,21 +206,31 @@ void launch_gain(const GainJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream
 // before the render starts and on silent-flagged input blocks (which write zeros, :63-75).  A gather: nothing recursive.
 __global__ void __launch_bounds__(256) k_delay(const DelayJob* __restrict__ jobs, int64_t n_frames, int sample_rate) {
   const DelayJob job = jobs[blockIdx.y];
-  const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (n >= n_frames) return;
-  const float t = job.dt ? job.dt[n] : job.dt_const;
-  int d = (int)(t * (float)sample_rate);  // float * int -> float product, truncated (:68,85)
-  d = d < 0 ? 0 : (d > job.max_delay ? job.max_delay : d);
-  const int64_t m = n - d;
-  const bool live = d >= 1 && m >= job.in_lo && m < job.in_hi;
-  job.out[0][n] = live ? job.in[0][m] : 0.f;
-  job.out[1][n] = live ? job.in[1][m] : 0.f;
+  const int64_t n4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;  // 4 frames per thread: 16-byte stores, neighbouring gathers
+  if (n4 >= n_frames) return;
+  float4 t4 = make_float4(job.dt_const, job.dt_const, job.dt_const, job.dt_const);
+  if (job.dt) t4 = *reinterpret_cast<const float4*>(job.dt + n4);
+  const float* pt = &t4.x;
+  float4 o0, o1;
+  float* p0 = &o0.x;
+  float* p1 = &o1.x;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    int d = (int)(pt[u] * (float)sample_rate);  // float * int -> float product, truncated (:68,85)
+    d = d < 0 ? 0 : (d > job.max_delay ? job.max_delay : d);
+    const int64_t m = n4 + u - d;
+    const bool live = d >= 1 && m >= job.in_lo && m < job.in_hi;
+    p0[u] = live ? job.in[0][m] : 0.f;
+    p1[u] = live ? job.in[1][m] : 0.f;
+  }
+  *reinterpret_cast<float4*>(job.out[0] + n4) = o0;
+  *reinterpret_cast<float4*>(job.out[1] + n4) = o1;
 }
 void launch_delay(const DelayJob* d_jobs, int n_jobs, int64_t n_frames, int sample_rate, cudaStream_t s) {
   if (n_jobs <= 0 || n_frames <= 0) return;
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    k_delay<<<dim3((unsigned)((n_frames + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames, sample_rate);
+    k_delay<<<dim3((unsigned)((n_frames / 4 + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames, sample_rate);
   }
 }
 
@@ -228,46 +239,57 @@ void launch_delay(const DelayJob* d_jobs, int n_jobs, int64_t n_frames, int samp
 // platform libm's cosf / sinf (sincosf_libm), the products and sums stay unfused (--fmad=false).
 __global__ void __launch_bounds__(256) k_panner(const PannerJob* __restrict__ jobs, int64_t n_frames) {
   const PannerJob job = jobs[blockIdx.y];
-  const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (n >= n_frames) return;
-  float L = 0.f, R = 0.f;
-  if (n >= job.lo && n < job.hi) {  // silent-flagged input -> cleared output (:49-54)
-    float pan = job.pan ? job.pan[n] : job.pan_const;
-    pan = fminf(fmaxf(pan, -1.0f), 1.0f);
+  const int64_t n4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;  // 4 frames per thread (a quantum never straddles a thread)
+  if (n4 >= n_frames) return;
+  float4 L4 = make_float4(0.f, 0.f, 0.f, 0.f), R4 = L4;
+  if (n4 >= job.lo && n4 < job.hi) {  // silent-flagged input -> cleared output (:49-54); lo / hi are multiples of 128
+    float4 pan4 = make_float4(job.pan_const, job.pan_const, job.pan_const, job.pan_const);
+    if (job.pan) pan4 = *reinterpret_cast<const float4*>(job.pan + n4);
+    const float4 a4 = *reinterpret_cast<const float4*>(job.sig[0] + n4), b4 = *reinterpret_cast<const float4*>(job.sig[1] + n4);
     const float kPi = 3.14159265358979323846f;
-    float a = job.sig[0][n], b = job.sig[1][n];
-    float gl, gr;
     // The input's channel count is computed from the upstream block of the PREVIOUS quantum (AudioNodeInput.cs:109 precedes :124),
     // so one block can differ from the rest: a mono signal is up-mixed to two equal channels in the very first quantum (mode 1,
     // rows are already duplicates), a stereo source that starts later is mixed DOWN to one channel in its first quantum (mode 2:
     // (0 + L + R) * (1 / sqrt(2)), AudioNodeInput.cs:214-228).
     bool mono = job.mono != 0;
-    if (n >= job.sp_block && n < job.sp_block + 128) {
-      mono = job.sp_mode == 2;
-      if (mono) a = (a + b) * (1.0f / sqrtf(2.0f));
-    }
-    // The node recomputes its gain pair only when the pan value CHANGES (:95-103, :129-137), with the formula of the variant that
-    // is running at that moment — so the pair computed in the odd first quantum stays in force, across the switch of variants,
-    // until the first sample whose pan differs from its predecessor's (first_change; never, for a constant pan).
-    bool mono_formula = mono;
-    if (job.sp_mode != 0 && n >= job.sp_block && (job.first_change == nullptr || n < (int64_t)*job.first_change)) mono_formula = job.sp_mode == 2;
-    const float x = mono_formula ? (pan + 1.0f) * 0.5f : (pan <= 0.0f ? pan + 1.0f : pan);
-    sincosf_libm(x * kPi / 2.0f, &gr, &gl);
-    if (mono) {  // ProcessMono :77-108
-      L = a * gl;
-      R = a * gr;
-    } else {  // ProcessStereo :110-152
-      if (pan <= 0.0f) {
-        L = a + b * gl;
-        R = b * gr;
-      } else {
-        L = a * gl;
-        R = b + a * gr;
+    const bool odd = n4 >= job.sp_block && n4 < job.sp_block + 128;
+    if (odd) mono = job.sp_mode == 2;
+    const int64_t first_change = job.first_change ? (int64_t)*job.first_change : INT64_MAX;
+    float gl = 0.f, gr = 0.f, last = CUDART_NAN_F;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float pan = (&pan4.x)[u];
+      pan = fminf(fmaxf(pan, -1.0f), 1.0f);
+      float a = (&a4.x)[u];
+      const float b = (&b4.x)[u];
+      if (odd && mono) a = (a + b) * (1.0f / sqrtf(2.0f));
+      // The node recomputes its gain pair only when the pan value CHANGES (:95-103, :129-137), with the formula of the variant
+      // that is running at that moment — so the pair computed in the odd first quantum stays in force, across the switch of
+      // variants, until the first sample whose pan differs from its predecessor's (first_change; never, for a constant pan).
+      bool mono_formula = mono;
+      if (job.sp_mode != 0 && n4 >= job.sp_block && n4 + u < first_change) mono_formula = job.sp_mode == 2;
+      if (pan != last || u == 0 || n4 + u == first_change) {  // (the pair is a pure function of pan and the formula: reuse it within the thread)
+        const float x = mono_formula ? (pan + 1.0f) * 0.5f : (pan <= 0.0f ? pan + 1.0f : pan);
+        sincosf_libm(x * kPi / 2.0f, &gr, &gl);
+        last = pan;
       }
+      float l, r;
+      if (mono) {  // ProcessMono :77-108
+        l = a * gl;
+        r = a * gr;
+      } else if (pan <= 0.0f) {  // ProcessStereo :110-152
+        l = a + b * gl;
+        r = b * gr;
+      } else {
+        l = a * gl;
+        r = b + a * gr;
+      }
+      (&L4.x)[u] = l;
+      (&R4.x)[u] = r;
     }
   }
-  job.sig[0][n] = L;
-  job.sig[1][n] = R;
+  *reinterpret_cast<float4*>(job.sig[0] + n4) = L4;
+  *reinterpret_cast<float4*>(job.sig[1] + n4) = R4;
 }
 // first frame behind the odd quantum whose (clamped) pan differs from its predecessor's; first_change must be preset to a huge value
 __global__ void __launch_bounds__(256) k_pan_first_change(const PannerJob* __restrict__ jobs, int64_t n_frames) {
@@ -291,7 +313,7 @@ void launch_panner(const PannerJob* d_jobs, int n_jobs, int64_t n_frames, bool s
     }
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    k_panner<<<dim3((unsigned)((n_frames + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames);
+    k_panner<<<dim3((unsigned)((n_frames / 4 + 255) / 256), (unsigned)nj), 256, 0, s>>>(d_jobs + j0, n_frames);
   }
 }
 

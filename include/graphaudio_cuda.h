@@ -277,6 +277,8 @@ typedef struct gac_stats {
   double mac_bytes_moved;      /* bytes the K6 variant in use has to move through HBM (X, H, Y once) */
   int32_t mac_variant_used;    /* 1 stream, 2/4 register-tiled, 3 second-level FFT (last convolver batch) */
   int32_t reserved;
+  double ms_delay;             /* DelayNode gather                                                  */
+  double ms_panner;            /* StereoPannerNode                                                  */
 } gac_stats;
 int gac_get_stats(gac_context* ctx, gac_stats* out);
 

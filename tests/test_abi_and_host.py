@@ -39,7 +39,7 @@ def test_version_and_struct_layouts():
     assert N.gac_event.time.offset == 16 and N.gac_event.time_constant.offset == 24
     assert C.sizeof(N.gac_param) == 16
     assert C.sizeof(N.gac_context_desc) == 32
-    assert C.sizeof(N.gac_stats) == 152
+    assert C.sizeof(N.gac_stats) == 168
 
 
 def test_no_cpu_fallback_without_device():

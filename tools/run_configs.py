@@ -114,6 +114,52 @@ if "c4" in which:
     assert np.isfinite(out).all() and np.abs(out).max() > 1e-3
     parent.Dispose()
 
+if "f3" in which:
+    # SURVEY.md §8f-3 nodes at the bench workload's size: 64 voices x (stereo 10 s source -> DelayNode -> StereoPannerNode) -> bus, 12 s.
+    # Algorithmic bytes per frame and voice: delay 16 (+4 with an a-rate table), panner 16 (+4); the automation tables are written once (4 each).
+    fs = 48000
+    n = 12 * fs
+    for label, automated in (("constant DelayTime / Pan", False), ("a-rate DelayTime and Pan", True)):
+        ctx = G.OfflineAudioContext(fs)
+        bus = G.GainNode(ctx)
+        bus.Gain.Value = 0.125
+        bus.Connect(ctx.Destination)
+        for v in range(64):
+            s = G.AudioBufferSourceNode(ctx)
+            s.Buffer = G.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(4 * v + c, 10 * fs) for c in range(2)], fs)
+            d = G.DelayNode(ctx, 0.5)
+            p = G.StereoPannerNode(ctx)
+            if automated:
+                d.DelayTime.SetValueAtTime(0.01 + 0.001 * v, 0.0)
+                d.DelayTime.LinearRampToValueAtTime(0.3, 8.0)
+                p.Pan.SetValueAtTime(-1.0, 0.0)
+                p.Pan.LinearRampToValueAtTime(1.0, 6.0 + 0.05 * v)
+            else:
+                d.DelayTime.Value = 0.01 + 0.001 * v
+                p.Pan.Value = -1.0 + v / 32.0
+            s.Connect(d).Connect(p).Connect(bus)
+            s.Start()
+        g = ctx._graph()
+        d_out = torch.empty((2, n), dtype=torch.float32, device="cuda")
+        spans = {"delay": [], "panner": [], "total": []}
+        for i in range(6):
+            check(L.gac_render_device(ctx._h, g, 0, n, C.c_void_p(d_out.data_ptr()), 2, 1))
+            st = stats_of(ctx._h)
+            if i >= 3:
+                spans["total"].append(st["ms_total"]); spans["delay"].append(st["ms_delay"]); spans["panner"].append(st["ms_panner"])
+        frames = 64 * n
+        dms, pms = float(np.mean(spans["delay"])), float(np.mean(spans["panner"]))
+        extra = 4 if automated else 0
+        res[f"f3: 64 voices x (source -> DelayNode -> StereoPannerNode) -> bus, 12 s, {label}"] = {
+            "ms_per_render": float(np.mean(spans["total"])), "ms_delay": dms, "ms_panner": pms,
+            "delay_GBps": frames * (16 + extra) / (dms * 1e-3) / 1e9, "panner_GBps": frames * (16 + extra) / (pms * 1e-3) / 1e9,
+            "hbm_peak_GBps": 6458.4}
+        print(json.dumps(res[f"f3: 64 voices x (source -> DelayNode -> StereoPannerNode) -> bus, 12 s, {label}"]), flush=True)
+        L.gac_graph_destroy(g)
+        ctx.Dispose()
+
 p = os.path.join(ROOT, "gpurun_out", "r01_configs.json")
+if os.path.exists(p) and len(which) < 5:
+    old = json.load(open(p)); old.update(res); res = old
 json.dump(res, open(p, "w"), indent=1)
 print("wrote", p)

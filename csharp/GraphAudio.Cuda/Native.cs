@@ -58,6 +58,9 @@ internal unsafe struct GacVoiceDesc
     public GacOpDesc* Ops;
     public int Bus;
     public int Input;   // 0 = fed by Source; k > 0 = fed by the output of bus k-1
+    public int Loop;    // AudioBufferSourceNode.Loop (rate 1 only)
+    public int Reserved;
+    public double LoopStart, LoopEnd;   // seconds; LoopEnd 0 = end of the buffer
 }
 
 [StructLayout(LayoutKind.Sequential)]

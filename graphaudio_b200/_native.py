@@ -54,7 +54,8 @@ class gac_op_desc(C.Structure):
 class gac_voice_desc(C.Structure):
     _fields_ = [("source", C.c_void_p), ("start_when", C.c_double), ("start_offset", C.c_double),
                 ("start_duration", C.c_double), ("stop_when", C.c_double), ("playback_rate", C.c_float),
-                ("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc)), ("bus", C.c_int32), ("input", C.c_int32)]
+                ("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc)), ("bus", C.c_int32), ("input", C.c_int32),
+                ("loop", C.c_int32), ("reserved", C.c_int32), ("loop_start", C.c_double), ("loop_end", C.c_double)]
 
 
 class gac_bus_desc(C.Structure):

@@ -266,7 +266,9 @@ class AudioBufferSourceNode(AudioNode):
         super().__init__(context, 0, 1)
         self.PlaybackRate = AudioParam(1.0, 0.001, 1000.0)  # k-rate, Nodes/AudioBufferSourceNode.cs:76
         self._buffer: Optional[PlayableAudioBuffer] = None
-        self.Loop = False
+        self.Loop = False            # :40-44 (accelerated at playback rate 1; the looping resampler path raises NotSupportedException)
+        self._loop_start = 0.0
+        self._loop_end = 0.0
         self._started = False
         self._when = math.nan
         self._offset = 0.0
@@ -283,6 +285,22 @@ class AudioBufferSourceNode(AudioNode):
         # upload now rather than at Render: with async_upload the copy engine works while the rest of the graph is built
         if value is not None and not self.Context._record_only and self.Context._h is not None:
             value._handle(self.Context)
+
+    @property
+    def LoopStart(self):  # :49-53
+        return self._loop_start
+
+    @LoopStart.setter
+    def LoopStart(self, v):
+        self._loop_start = max(0.0, float(v))
+
+    @property
+    def LoopEnd(self):  # :58-62 (0 = end of the buffer)
+        return self._loop_end
+
+    @LoopEnd.setter
+    def LoopEnd(self, v):
+        self._loop_end = max(0.0, float(v))
 
     def Start(self, when=0.0, offset=0.0, duration=math.inf):  # :79-114
         if self._started:
@@ -630,8 +648,7 @@ class OfflineAudioContext:
                     when = math.nan
                 else:
                     when = src._when
-                if src.Loop:
-                    raise NotSupportedException("looping sources are outside the accelerated path (SURVEY.md §8f-3)")
+                v.loop, v.loop_start, v.loop_end = int(bool(src.Loop)), src.LoopStart, src.LoopEnd
                 v.source = src.Buffer._handle(self) if src.Buffer is not None else None
                 v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop
                 v.playback_rate = src.PlaybackRate.Value

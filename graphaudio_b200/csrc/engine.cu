@@ -64,6 +64,8 @@ struct VoiceH {
   const gac_buffer* src = nullptr;
   double when = 0, offset = 0, duration = 0, stop_when = 0;
   float rate = 1.f;
+  bool loop = false;
+  double loop_start = 0, loop_end = 0;
   std::vector<OpH> ops;
   int bus = -1;
   int input_bus = -1;  // >= 0: the chain is fed by that bus's output instead of a source buffer
@@ -795,6 +797,9 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
     h.duration = d.start_duration;
     h.stop_when = d.stop_when;
     h.rate = d.playback_rate;
+    h.loop = d.loop != 0;
+    h.loop_start = std::max(0.0, d.loop_start);  // AudioBufferSourceNode.cs:52
+    h.loop_end = std::max(0.0, d.loop_end);      // :61
     h.bus = d.bus;
     int rc = copy_ops(ctx, d.n_ops, d.ops, &h.ops);
     if (rc) return rc;

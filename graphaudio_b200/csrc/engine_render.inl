@@ -69,6 +69,24 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
     const double ratio = (double)buf->rate / (double)ctx->fs;  // :168
     const double eff = ratio * (double)v.rate;                 // :169
     const int64_t max_blocks = std::max<int64_t>(0, b_stop - b_start);
+    if (v.loop) {
+      // Looping playback (:171-177, :197-234): runs until the stop time, duration only sets that stop time (:106-110).
+      int64_t loopEnd = v.loop_end > 0 ? (int64_t)(v.loop_end * (double)buf->rate) : buf->n;
+      loopEnd = std::min(loopEnd, buf->n);
+      const int64_t loopStart = std::min((int64_t)(v.loop_start * (double)buf->rate), loopEnd);
+      if (eff != 1.0) return fail(GAC_ERR_UNSUPPORTED, "looping sources are accelerated at playback rate 1 only (the looping resampler path is SURVEY.md §8f-3)");
+      if (loopEnd - loopStart <= 0) return fail(GAC_ERR_UNSUPPORTED, "looping source with an empty loop region");
+      job.pos0 = pos;
+      job.out0 = b_start * 128;
+      job.n_emit = max_blocks * 128;
+      job.loop_start = loopStart;
+      job.loop_end = loopEnd;
+      job.loop_len = loopEnd - loopStart;
+      s.lo = job.out0;
+      s.hi = job.out0 + job.n_emit;
+      cj.push_back(job);
+      continue;
+    }
     if (max_blocks == 0 || pos >= durEnd) {
       cj.push_back(job);
       continue;

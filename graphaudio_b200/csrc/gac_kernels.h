@@ -135,6 +135,10 @@ struct SourceJob {
   int64_t pos0;         // buffer frame that lands on out frame out0
   int64_t out0;         // first emitted output frame (multiple of 128)
   int64_t n_emit;       // emitted frames (multiple of 128)
+  // looping playback at rate 1 (AudioBufferSourceNode.cs:197-234): loop_len > 0 switches it on.  Emitted frame j reads buffer frame
+  //   k = pos0 + j;  k < loop_end ? k : loop_start + (k - loop_end) % loop_len
+  // except that a start position at or behind loop_end restarts the FIRST block at loop_start (:197-200): j < 128 -> loop_start + j % loop_len
+  int64_t loop_start = 0, loop_end = 0, loop_len = 0;
 };
 void launch_source_copy(const SourceJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
 

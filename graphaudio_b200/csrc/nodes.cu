@@ -124,7 +124,10 @@ __global__ void __launch_bounds__(256) k_source_copy(const SourceJob* __restrict
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       int64_t m = n4 + u - job.out0;
-      pv[u] = (m >= 0 && m < job.n_emit) ? job.src[c][job.pos0 + m] : 0.f;
+      int64_t k = job.pos0 + m;
+      if (job.loop_len > 0 && k >= job.loop_end)
+        k = (job.pos0 >= job.loop_end && m < 128) ? job.loop_start + m % job.loop_len : job.loop_start + (k - job.loop_end) % job.loop_len;
+      pv[u] = (m >= 0 && m < job.n_emit) ? job.src[c][k] : 0.f;
     }
     *reinterpret_cast<float4*>(job.dst[c] + n4) = v;
   }

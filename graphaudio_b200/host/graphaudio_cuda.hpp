@@ -159,6 +159,7 @@ class AudioBufferSourceNode : public AudioNode {  // Nodes/AudioBufferSourceNode
   std::shared_ptr<PlayableAudioBuffer> Buffer;
   AudioParam PlaybackRate{1.f, 0.001f, 1000.f};  // :76
   bool Loop = false;
+  double LoopStart = 0, LoopEnd = 0;  // seconds; LoopEnd 0 = end of the buffer (:49-62)
   void Start(double when = 0, double offset = 0, double duration = std::numeric_limits<double>::infinity()) {  // :79-114
     if (started_) throw InvalidOperationException("AudioBufferSourceNode can only be started once.");
     if (!Buffer) throw InvalidOperationException("Cannot start without a buffer set");
@@ -340,7 +341,6 @@ class OfflineAudioContext {
     return true;
   }
   void AddVoice(Flat& f, AudioBufferSourceNode* s, const std::vector<AudioNode*>& ops, int bus) {
-    if (s->Loop) throw NotSupportedException("looping sources are outside the accelerated path");
     f.ops.emplace_back();
     for (auto* n : ops) f.ops.back().push_back(OpDesc(n));
     gac_voice_desc v{};
@@ -350,6 +350,9 @@ class OfflineAudioContext {
     v.start_duration = s->duration_;
     v.stop_when = s->stop_;
     v.playback_rate = s->PlaybackRate.Value();
+    v.loop = s->Loop ? 1 : 0;  // rate 1 only; the library answers GAC_ERR_UNSUPPORTED otherwise
+    v.loop_start = std::max(0.0, s->LoopStart);
+    v.loop_end = std::max(0.0, s->LoopEnd);
     v.n_ops = (int32_t)f.ops.back().size();
     v.ops = nullptr;  // patched once every list is in place (vectors may reallocate)
     v.bus = bus;

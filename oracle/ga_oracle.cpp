@@ -472,6 +472,7 @@ class Context {
   int currentBlock = 0;       // AudioContextBase.cs:16
   double currentTime = 0.0;   // :17
   bool cycle = false;
+  bool unsupported = false;  // a path this oracle does not restate was reached (looping + resampling)
   std::deque<std::function<void()>> commands;  // :15
   std::vector<std::unique_ptr<Node>> nodes;
   std::vector<std::unique_ptr<PlayBuffer>> buffers;
@@ -889,6 +890,10 @@ class BufferSource : public Node {
                          ? (int64_t)(offset * buf->rate) + (int64_t)(duration * buf->rate)
                          : buf->length;  // :179-182
     durEnd = std::min(durEnd, buf->length);
+    int64_t loopStartFrame = (int64_t)(loopStart * buf->rate);  // :171-177
+    int64_t loopEndFrame = loopEnd > 0 ? (int64_t)(loopEnd * buf->rate) : buf->length;
+    loopEndFrame = std::min(loopEndFrame, buf->length);
+    loopStartFrame = std::min(loopStartFrame, loopEndFrame);
     bool hasMore = false;
     if (eff == 1.0) {  // :186-235
       for (int c = 0; c < oc; c++) {
@@ -897,8 +902,9 @@ class BufferSource : public Node {
         int64_t p = pos;
         int oi = 0;
         while (oi < frames) {
-          if (p >= durEnd) { std::fill(o + oi, o + frames, 0.f); break; }
-          int64_t endFrame = std::min(durEnd, buf->length);
+          if (loop && p >= loopEndFrame) p = loopStartFrame;                                     // :197-200
+          if (p >= durEnd && !loop) { std::fill(o + oi, o + frames, 0.f); break; }               // :202-206
+          int64_t endFrame = loop ? loopEndFrame : std::min(durEnd, buf->length);                // :208
           int avail = (int)std::min<int64_t>(endFrame - p, frames - oi);
           if (avail <= 0) { std::fill(o + oi, o + frames, 0.f); break; }
           std::memcpy(o + oi, d + p, sizeof(float) * avail);
@@ -906,6 +912,14 @@ class BufferSource : public Node {
         }
       }
       pos += frames;  // :224
+      if (loop && pos >= loopEndFrame) {  // :226-234
+        int64_t loopLength = loopEndFrame - loopStartFrame;
+        if (loopLength > 0) pos = loopStartFrame + ((pos - loopEndFrame) % loopLength);
+      }
+    } else if (loop) {
+      // the looping resampler path (:236-358, wrap buffer) is not restated: flagged, never silently approximated
+      ctx->unsupported = true;
+      ob->clear();
     } else {  // :236-358
       if ((int)rs.size() != oc) { rs.assign(oc, CubicResampler()); }
       int64_t totalConsumed = 0;
@@ -932,7 +946,7 @@ class BufferSource : public Node {
       pos += totalConsumed;
     }
     double tEnd = t1;
-    if (!hasMore || pos >= durEnd) {  // :360-368
+    if (!hasMore || (!loop && pos >= durEnd)) {  // :360-368
       ob->clear();
       if (std::isnan(stopTime)) { stopTime = t1; stopped = true; }
     } else {
@@ -947,6 +961,8 @@ class BufferSource : public Node {
   }
   PlayBuffer* buf = nullptr;
   Param* rate;
+  bool loop = false;                    // :40-44
+  double loopStart = 0, loopEnd = 0;    // :49-62 (seconds; loopEnd 0 = end of buffer)
   bool started = false, stopped = false, ended = false;
   double startTime = std::numeric_limits<double>::quiet_NaN(), stopTime = std::numeric_limits<double>::quiet_NaN();
   double offset = 0, duration = std::numeric_limits<double>::infinity();
@@ -1204,6 +1220,15 @@ int ora_source_start(void* c, int node, double when, double offset, double durat
   auto* n = dynamic_cast<BufferSource*>(nodeAt(c, node));
   return n ? n->start(when, offset, duration) : -1;
 }
+int ora_source_set_loop(void* c, int node, int loop, double loopStart, double loopEnd) {
+  auto* s = dynamic_cast<BufferSource*>(nodeAt(c, node));
+  if (!s) return -1;
+  s->loop = loop != 0;
+  s->loopStart = std::max(0.0, loopStart);  // :52
+  s->loopEnd = std::max(0.0, loopEnd);      // :61
+  return 0;
+}
+int ora_unsupported(void* c) { return ((Context*)c)->unsupported ? 1 : 0; }
 int ora_source_stop(void* c, int node, double when) {
   auto* n = dynamic_cast<BufferSource*>(nodeAt(c, node));
   if (!n) return -1;

@@ -66,6 +66,8 @@ def lib():
     L.ora_source_set_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_source_start.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
     L.ora_source_stop.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.ora_source_set_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.ora_unsupported.argtypes = [C.c_void_p]
     L.ora_biquad_set_type.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_convolver_set_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ora_render.argtypes = [C.c_void_p, fpp, C.c_int, C.c_int, C.c_int]
@@ -270,6 +272,7 @@ class AudioBufferSourceNode(AudioNode):
         super().__init__(context)
         self.PlaybackRate = AudioParam(self, 0, 1.0, 0.001, 1000.0)
         self._buffer = None
+        self._loop, self._loop_start, self._loop_end = False, 0.0, 0.0
 
     @property
     def Buffer(self):
@@ -279,6 +282,36 @@ class AudioBufferSourceNode(AudioNode):
     def Buffer(self, b):
         self._buffer = b
         lib().ora_source_set_buffer(self._ctx._h, self._id, b._id(self._ctx))
+
+    def _set_loop(self):
+        lib().ora_source_set_loop(self._ctx._h, self._id, int(self._loop), self._loop_start, self._loop_end)
+
+    @property
+    def Loop(self):
+        return self._loop
+
+    @Loop.setter
+    def Loop(self, v):
+        self._loop = bool(v)
+        self._set_loop()
+
+    @property
+    def LoopStart(self):
+        return self._loop_start
+
+    @LoopStart.setter
+    def LoopStart(self, v):
+        self._loop_start = max(0.0, float(v))
+        self._set_loop()
+
+    @property
+    def LoopEnd(self):
+        return self._loop_end
+
+    @LoopEnd.setter
+    def LoopEnd(self, v):
+        self._loop_end = max(0.0, float(v))
+        self._set_loop()
 
     def Start(self, when=0.0, offset=0.0, duration=math.inf):
         if lib().ora_source_start(self._ctx._h, self._id, float(when), float(offset), float(duration)) != 0:
@@ -398,6 +431,8 @@ class OfflineAudioContext:
         rc = lib().ora_render(self._h, ptrs, len(rows), int(frameCount), int(startIndex))
         if rc == -2:
             raise InvalidOperationException("Audio graph cycle detected")
+        if lib().ora_unsupported(self._h):
+            raise NotImplementedError("the oracle does not restate this path (looping source with resampling)")
         if rc != 0:
             raise ArgumentOutOfRangeException("render failed (%d)" % rc)
 

@@ -293,3 +293,63 @@ def test_interleaved_render_equals_planar_render():
         ctx.Dispose()
     with pytest.raises(G.ArgumentOutOfRangeException):
         build().RenderInterleaved(128, 33)
+
+
+@pytest.mark.parametrize("loop_start,loop_end,offset,start,stop", [
+    (0.0, 0.0, 0.0, 0.0, None),            # whole buffer, forever
+    (100.2, 400.2, 0.0, 0.0, None),        # plays into the loop region, then cycles it (loop shorter than 3 quanta)
+    (100.2, 400.2, 650.0, 0.01, None),     # start position behind the loop end: the first quantum restarts at LoopStart
+    (10.5, 50.5, 20.0, 0.0, 0.1),          # loop shorter than a quantum; Stop(0.1)
+    (0.0, 0.0, 2990.0, 0.005, 0.2),
+])
+def test_looping_source_at_rate_one(loop_start, loop_end, offset, start, stop):
+    """AudioBufferSourceNode.Loop / LoopStart / LoopEnd on the copy path (Nodes/AudioBufferSourceNode.cs:171-177, :186-235)."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+    src = [synth.splitmix_uniform(950 + c, 3001) for c in range(2)]
+
+    def build(api):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, fs)
+        s.Loop = True
+        s.LoopStart = loop_start / fs
+        s.LoopEnd = loop_end / fs
+        g = api.GainNode(ctx)
+        g.Gain.Value = 0.5
+        s.Connect(g).Connect(ctx.Destination)
+        s.Start(start, offset / fs)
+        if stop is not None:
+            s.Stop(stop)
+        return ctx
+    yg, yo = build(G).Render(128 * 150), build(O).Render(128 * 150)
+    assert np.abs(yo).max() > 0.1
+    assert np.array_equal(yg, yo)
+
+
+def test_looping_source_feeding_a_convolver_and_unsupported_variants():
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+    src = [synth.splitmix_uniform(960 + c, 2000) for c in range(2)]
+    ir = [synth.decay_ir(970 + c, 3000) for c in range(2)]
+
+    def build(api, rate=1.0, ls=0.0, le=0.0):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, fs)
+        s.Loop = True
+        s.LoopStart, s.LoopEnd = ls, le
+        s.PlaybackRate.Value = rate
+        conv = api.ConvolverNode(ctx)
+        conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays(ir, fs)
+        s.Connect(conv).Connect(ctx.Destination)
+        s.Start()
+        return ctx
+    yg, yo = build(G).Render(128 * 100), build(O).Render(128 * 100)
+    assert np.abs(yg - yo).max() <= 1e-5
+    with pytest.raises(G.NotSupportedException):
+        build(G, rate=0.5).Render(1280)   # the looping resampler path is not accelerated (and never approximated)
+    with pytest.raises(G.NotSupportedException):
+        build(G, ls=0.01, le=0.01).Render(1280)

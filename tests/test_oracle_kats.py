@@ -384,3 +384,34 @@ def test_stereo_panner_equal_power_formulas():
     for i in (128, 300, 700, 890):
         g = g_mono(np.float32(pv[i]))
         assert ym[0, i] == mono[0][i] * g[0] and ym[1, i] == mono[0][i] * g[1]
+
+
+def test_looping_source_copy_path_closed_form():
+    # AudioBufferSourceNode.cs:171-177, :186-235: emitted frame j reads buffer frame k = pos0 + j while k < loopEnd, then
+    # loopStart + (k - loopEnd) % loopLength; a start position at or behind loopEnd restarts the FIRST quantum at loopStart (:197-200)
+    # while _playbackPosition still advances from the original position (:224-234)
+    fs = 48000
+    x = np.arange(1, 1001, dtype=np.float32)
+
+    def run(loop_start, loop_end, offset, n=128 * 12, stop=None):
+        ctx = O.OfflineAudioContext(fs)
+        s = O.AudioBufferSourceNode(ctx)
+        s.Buffer = O.PlayableAudioBuffer.FromChannelArrays([x], fs)
+        s.Loop = True
+        s.LoopStart, s.LoopEnd = loop_start / fs, loop_end / fs
+        s.Connect(ctx.Destination)
+        s.Start(0.0, offset / fs)
+        if stop is not None:
+            s.Stop(stop)
+        return ctx.Render(n)[0]
+
+    k = np.arange(128 * 12)
+    assert np.array_equal(run(100.2, 400.2, 0), x[np.where(k < 400, k, 100 + (k - 400) % 300)])
+    assert np.array_equal(run(10.5, 50.5, 20), x[np.where(k + 20 < 50, k + 20, 10 + (k + 20 - 50) % 40)])
+    late = run(100.2, 400.2, 650)
+    assert np.array_equal(late[:128], x[100 + np.arange(128) % 300])
+    assert np.array_equal(late[128:], x[100 + (650 + k[128:] - 400) % 300])
+    whole = run(0, 0, 0, n=128 * 20)
+    assert np.array_equal(whole, x[np.arange(128 * 20) % 1000])  # LoopEnd 0 = end of the buffer; never ends by itself
+    stopped = run(0, 0, 0, stop=0.01)  # block-granular stop: quanta with t0 < 0.01 s play (:137-143)
+    assert np.nonzero(stopped)[0][-1] == 511

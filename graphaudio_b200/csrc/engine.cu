@@ -151,7 +151,7 @@ static void give_stage_block(char* p) {
 // ---- constant device tables, shared process-wide.
 // They are uploaded ONCE per device with a synchronous copy and never through a context's stream: a stream that has used the
 // copy engine orders its next operation behind whatever other streams have queued on that engine since, so one small table
-// copy at context creation made the whole render wait for the last asynchronous buffer upload (scratch/overlap_probe.cu:
+// copy at context creation made the whole render wait for the last asynchronous buffer upload (tools/overlap_probe.cu:
 // variants 2, 4, 6 against 1, 8, 9).  They are never freed (a few hundred KB per device).
 struct BlockTimes {
   std::vector<double> h;  // _currentTime += 128.0 / SampleRate, accumulated block after block (AudioContextBase.cs:78-79)

@@ -35,6 +35,7 @@ class gac_context_desc(C.Structure):
 
 
 GAC_FLAG_ASYNC_UPLOAD = 1
+GAC_FLAG_MIXED_SEGMENTS = 2
 
 
 class gac_event(C.Structure):

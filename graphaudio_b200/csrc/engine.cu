@@ -95,6 +95,7 @@ struct gac_context {
   int B = 128;
   int mac_variant = 0;
   int tile_blocks = 32;
+  bool mixed_segments = false;  // K6: double-length segments in front when that saves transform points (GAC_FLAG_MIXED_SEGMENTS; slower today)
   cudaStream_t stream = nullptr;
   float2* d_tw = nullptr;  // e^{-2 pi i k/(2B)}, k < B
   float2* d_tw2 = nullptr; // e^{-2 pi i e/8192}, e < 8192: twiddles of the second-level (block-time) FFT, fft2.cu
@@ -206,6 +207,9 @@ struct gac_ir {
   // second-level spectra (fft2.cu): [nch][B+1][M2], or null when the context's mac_variant never uses them
   float2* d_H2 = nullptr;  // (inside the d_H allocation)
   int M2 = 0, Lh = 0;
+  // second-level spectra for transforms of TWICE the length (own allocation, prepared by the first render that mixes segment
+  // lengths: conv_batch_fft2 / plan_segments), [nch][B+1][fft2_h2_row_elems(2 * M2)]
+  float2* d_H2b = nullptr;
   // deferred preparation (async mode): the source buffer is read by the first render that uses the impulse response
   bool prepared = true;
   gac_buffer* src = nullptr;
@@ -437,6 +441,7 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   ctx->tile_blocks = desc->tile_blocks == 64 ? 64 : 32;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->async_upload = (desc->flags & GAC_FLAG_ASYNC_UPLOAD) != 0;
+  ctx->mixed_segments = (desc->flags & GAC_FLAG_MIXED_SEGMENTS) != 0;
   if (ctx->async_upload) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   ctx->scratch_budget = di.budget;
   {
@@ -714,6 +719,7 @@ extern "C" int gac_ir_destroy(gac_ir* ir) {
   cudaSetDevice(ir->ctx->device);
   // stream-ordered free, behind any render still queued on the context stream
   if (!ir->prepared) buffer_unref(ir->src);  // never used: its source buffer is released too
+  if (ir->d_H2b) cudaFreeAsync(ir->d_H2b, ir->ctx->stream);
   cudaFreeAsync(ir->d_H, ir->ctx->stream);
   delete ir;
   return GAC_OK;
@@ -968,9 +974,11 @@ struct ConvItem {
     int x;            // which forward spectrum feeds this channel-convolver
     const float2* H;  // packed IR spectra [P16][B]
     const float2* H2; // second-level IR spectra [B+1][M2] (null: direct MAC)
+    const float2* H2b = nullptr;  // the same for transforms of length 2 * M2 (n_big > 0)
   } mac[4];
   int P = 0;
   int M2 = 0, Lh = 0;  // second-level transform length / history blocks (0: direct MAC)
+  int n_big = 0, n_small = 0;  // segments of length 2 * M2 in front, of length M2 behind them (plan_segments)
   int n_inv = 0;
   struct {
     int y, y2;        // spectrogram(s) of which channel-convolver(s); y2 = -1: none
@@ -1108,6 +1116,40 @@ static int conv_batch_direct(RenderEnv& env, std::vector<ConvItem>& items) {
   return GAC_OK;
 }
 
+// Overlap-save segments for QB output blocks: every segment spends Lh of its M points on history, so a render of QB = 4500 blocks with
+// Lh = 752 needs four 2048-point segments (V = 1296 valid outputs each) — or one 4096-point segment (V = 3344) followed by one
+// 2048-point segment, 25 % fewer transform points.  Picks the number of double-length segments in front (radix-16 plan: 2 M <= 4096).
+static void plan_segments(int64_t QB, int M, int Lh, int* n_big, int* n_small) {
+  int log2m = 0;
+  while ((1 << log2m) < M) log2m++;
+  const int64_t V = M - Lh;
+  *n_big = 0;
+  *n_small = (int)((QB + V - 1) / V);
+  if (2 * M > 4096) return;
+  const int64_t Vb = 2 * (int64_t)M - Lh;
+  double best = (double)*n_small * M * log2m;
+  for (int nb = 1; (int64_t)(nb - 1) * Vb < QB; nb++) {
+    const int64_t rem = std::max<int64_t>(0, QB - (int64_t)nb * Vb);
+    const int ns = (int)((rem + V - 1) / V);
+    const double cost = (double)nb * 2 * M * (log2m + 1) + (double)ns * M * log2m;
+    if (cost < best * 0.97) {  // (a tie keeps the single-length plan: one launch less)
+      best = cost;
+      *n_big = nb;
+      *n_small = ns;
+    }
+  }
+}
+
+// second-level spectra of length 2 * M2 for an impulse response that a render wants to run with mixed segment lengths
+static int ensure_h2b(gac_context* ctx, gac_ir* ir) {
+  if (ir->d_H2b || ir->M2 <= 0) return GAC_OK;
+  const int B = ctx->B, Mb = 2 * ir->M2;
+  CU(cudaMallocAsync(&ir->d_H2b, sizeof(float2) * (size_t)ir->nch * (B + 1) * fft2_h2_row_elems(Mb), ctx->stream));
+  launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, ir->nch, B, ir->P, Mb, ir->d_H2b, ctx->d_tw2, ctx->d_tab16, ctx->stream);
+  CU(cudaGetLastError());
+  return GAC_OK;
+}
+
 // The convolver with the spectral MAC done as a fast convolution along block time (fft2.cu):
 // K5 (transposing) -> k_fft2_conv -> K7 (transposing), over transposed spectrograms XT/YT[chan][B+1][Qs].
 static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) {
@@ -1134,9 +1176,10 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     if (rc) return rc;
     auto& fj = env.keep->make<FftFwdJob>();
     auto& cj = env.keep->make<Fft2Job>();
+    auto& cjb = env.keep->make<Fft2Job>();  // double-length segments in front (plan_segments)
     auto& ij = env.keep->make<FftInvJob>();
     size_t xi = 0, yi = 0;
-    int max_seg = 0;
+    int max_seg = 0, max_seg_big = 0;
     for (size_t i = 0; i < ni; i++) {
       ConvItem& it = items[i0 + i];
       float2* Xc[2] = {nullptr, nullptr};
@@ -1158,8 +1201,11 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
         fj.push_back(f);
       }
       const int V = M - it.Lh;
-      const int nseg = (int)((QB + V - 1) / V);
+      const int n_big = it.mac[0].H2b ? it.n_big : 0;
+      const int nseg = n_big > 0 ? it.n_small : (int)((QB + V - 1) / V);
+      const int64_t b0 = (int64_t)n_big * (2 * (int64_t)M - it.Lh);  // (multiple of 16: M and Lh are)
       max_seg = std::max(max_seg, nseg);
+      max_seg_big = std::max(max_seg_big, n_big);
       for (int k = 0; k < it.n_mac; k++) {
         Yc[k] = dY + (yi++) * (size_t)C * Qs;
         Fft2Job j;
@@ -1168,13 +1214,21 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
         j.Y = Yc[k];
         j.Lh = it.Lh;
         j.nseg = nseg;
-        cj.push_back(j);
+        j.b0 = b0;
+        if (nseg > 0) cj.push_back(j);
+        if (n_big > 0) {
+          j.H2 = it.mac[k].H2b;
+          j.nseg = n_big;
+          j.b0 = 0;
+          cjb.push_back(j);
+        }
         const double P = it.P;
         env.conv_units += QB;
         env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
         env.macs += (double)QB * P * C;  // complex MACs the direct sum would need (not issued: see mac_flops)
-        env.mac_flops += (double)nseg * C * (2.0 * 5.0 * M * log2m + 6.0 * M);
-        env.mac_bytes += 8.0 * C * ((double)QB + (double)fft2_h2_row_elems(M) + (double)QB);  // XT once (window overlaps hit L2), H2 row, YT
+        env.mac_flops += (double)nseg * C * (2.0 * 5.0 * M * log2m + 6.0 * M) + (double)n_big * C * (2.0 * 5.0 * 2 * M * (log2m + 1) + 6.0 * 2 * M);
+        // XT once (window overlaps hit L2), the H2 row(s), YT
+        env.mac_bytes += 8.0 * C * ((double)QB + (nseg > 0 ? (double)fft2_h2_row_elems(M) : 0.0) + (n_big > 0 ? (double)fft2_h2_row_elems(2 * M) : 0.0) + (double)QB);
       }
       for (int k = 0; k < it.n_inv; k++) {
         FftInvJob v;
@@ -1189,17 +1243,21 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     env.mac_used = 3;
     FftFwdJob* dfj = nullptr;
     Fft2Job* dcj = nullptr;
+    Fft2Job* dcjb = nullptr;
     FftInvJob* dij = nullptr;
     if ((rc = env.scratch->upload(&dfj, fj))) return rc;
     if ((rc = env.scratch->upload(&dcj, cj))) return rc;
+    if ((rc = env.scratch->upload(&dcjb, cjb))) return rc;
     if ((rc = env.scratch->upload(&dij, ij))) return rc;
     int t = env.timer->begin(C_FFT_FWD);
     launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_MAC);
+    launch_fft2_conv(dcjb, (int)cjb.size(), max_seg_big, C, 2 * M, ctx->d_tw2, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
     launch_fft2_conv(dcj, (int)cj.size(), max_seg, C, M, ctx->d_tw2, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
     env.timer->end(t);
+    if (!cjb.empty()) env.launches += 1;
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
     launch_irfft_ola_t8(dij, (int)ij.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
@@ -1580,6 +1638,16 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         it.P = ir->P;
         it.M2 = ir->d_H2 ? ir->M2 : 0;
         it.Lh = ir->Lh;
+        const float2* h2b = nullptr;
+        if (it.M2 > 0 && ctx->mixed_segments) {
+          plan_segments(env.QB, it.M2, it.Lh, &it.n_big, &it.n_small);
+          if (it.n_big > 0) {
+            int rc = ensure_h2b(ctx, const_cast<gac_ir*>(ir));
+            if (rc) return rc;
+            h2b = ir->d_H2b;
+          }
+        }
+        auto H2bch = [&](int c) { return h2b ? h2b + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(2 * ir->M2) : (const float2*)nullptr; };
         it.lo = s.lo;
         it.hi = s.hi;
         it.gain_tab = gtab;
@@ -1590,7 +1658,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           it.n_fwd = 1;
           it.fwd[0] = {in0, s.ch == 2 ? in1 : nullptr, 1.0f / sqrtf(2.0f)};
           it.n_mac = 1;
-          it.mac[0] = {0, Hch(0), H2ch(0)};
+          it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
           it.n_inv = 1;
           it.inv[0] = {0, -1, s.p[0], s.p[1]};
           s.ch = 1;
@@ -1599,8 +1667,8 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           it.fwd[0] = {in0, nullptr, 1.0f};
           it.fwd[1] = {in1, nullptr, 1.0f};
           it.n_mac = 2;
-          it.mac[0] = {0, Hch(0), H2ch(0)};
-          it.mac[1] = {1, Hch(1), H2ch(1)};
+          it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
+          it.mac[1] = {1, Hch(1), H2ch(1), H2bch(1)};
           it.n_inv = 2;
           it.inv[0] = {0, -1, s.p[0], nullptr};
           it.inv[1] = {1, -1, s.p[1], nullptr};
@@ -1611,10 +1679,10 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           it.fwd[0] = {in0, nullptr, 1.0f};
           it.fwd[1] = {in1, nullptr, 1.0f};
           it.n_mac = 4;
-          it.mac[0] = {0, Hch(0), H2ch(0)};
-          it.mac[1] = {1, Hch(2), H2ch(2)};
-          it.mac[2] = {0, Hch(1), H2ch(1)};
-          it.mac[3] = {1, Hch(3), H2ch(3)};
+          it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
+          it.mac[1] = {1, Hch(2), H2ch(2), H2bch(2)};
+          it.mac[2] = {0, Hch(1), H2ch(1), H2bch(1)};
+          it.mac[3] = {1, Hch(3), H2ch(3), H2bch(3)};
           it.n_inv = 2;
           it.inv[0] = {0, 1, s.p[0], nullptr};
           it.inv[1] = {2, 3, s.p[1], nullptr};

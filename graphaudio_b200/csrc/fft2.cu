@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(M / 8) k_fft2_conv(const Fft2Job* __restrict__
   const int k = blockIdx.y;
   const int t = threadIdx.x;
   const int V = M - job.Lh;
-  const int64_t b_first = (int64_t)seg * V - job.Lh;  // block index of window element 0
+  const int64_t b_first = job.b0 + (int64_t)seg * V - job.Lh;  // block index of window element 0
   const float2* __restrict__ xrow = job.X + (int64_t)k * xs;
   float2 v[8];
 #pragma unroll
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(M / 16) k_fft2_conv16(const Fft2Job* __restric
   const int k = blockIdx.y;
   const int t = threadIdx.x;
   const int V = M - job.Lh;
-  const int64_t b_first = (int64_t)seg * V - job.Lh;  // block index of window element 0 (multiple of 16)
+  const int64_t b_first = job.b0 + (int64_t)seg * V - job.Lh;  // block index of window element 0 (multiple of 16)
   const float2* __restrict__ xrow = job.X + (int64_t)k * xs;
   // window elements [n_lo, n_hi) exist in the spectrogram; the rest of the window is zero (blocks < 0, blocks >= n_blocks)
   const int n_lo = b_first < 0 ? (int)(-b_first) : 0;

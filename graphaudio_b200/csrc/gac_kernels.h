@@ -87,7 +87,8 @@ struct Fft2Job {
   const float2* H2;  // prepared second-level IR spectra of the IR channel: [B+1][fft2_h2_row_elems(M)]
   float2* Y;         // YT channel base
   int Lh;            // history blocks per segment (>= P-1, multiple of 16); V = M - Lh valid outputs per segment
-  int nseg;          // ceil(n_blocks / V)
+  int nseg;          // segments of this launch
+  int64_t b0 = 0;    // first output block of segment 0 (multiple of 16): lets two launches with different M share one spectrogram
 };
 constexpr int kFft2TwLen = 8192;  // twiddle table exp(-2 pi i e / 8192)
 // second-level transform length for P partitions (512..8192), 0 if the IR is too long; *Lh = history length

@@ -241,3 +241,39 @@ def test_sources_read_in_place_by_the_convolver(when, offset, duration):
     yo = build(O).Render(n)
     assert np.abs(yo).max() > 1e-2
     assert np.abs(yg - yo).max() <= TOL
+
+
+@pytest.mark.parametrize("n_ir,n_frames,mixed_expected", [
+    (12800, 128 * 1300, True),   # P = 100 (M = 512, V = 400): one 1024-point segment (912 outputs) + one 512-point segment instead of four
+    (12800, 128 * 900, True),    # ... one 1024-point segment alone instead of three 512-point ones
+    (12800, 128 * 350, False),   # a single short segment stays
+    (38400, 128 * 1700, True),   # P = 300 (M = 1024, V = 720): one 2048-point segment (V = 1744) instead of three 1024-point ones
+])
+def test_mixed_segment_lengths_match_uniform_segments_and_the_oracle(n_ir, n_frames, mixed_expected):
+    """K6 with double-length overlap-save segments in front (GAC_FLAG_MIXED_SEGMENTS, plan_segments) against the single-length plan and
+    the CPU oracle."""
+    G, O = _apis()
+    src = [synth.splitmix_uniform(800 + c, n_frames - 256) for c in range(2)]
+    ir = [synth.decay_ir(810 + c, n_ir) for c in range(2)]
+
+    def build(api, **kw):
+        ctx = api.OfflineAudioContext(FS, **kw)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, FS)
+        g = api.GainNode(ctx)
+        g.Gain.SetValueAtTime(0.9, 0.0)
+        g.Gain.LinearRampToValueAtTime(0.3, 1.0)
+        conv = api.ConvolverNode(ctx)
+        conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays(ir, FS)
+        s.Connect(g).Connect(conv).Connect(ctx.Destination)
+        s.Start()
+        return ctx
+    cm, cu = build(G, mixed_segments=True), build(G)
+    ym, yu, yo = cm.Render(n_frames), cu.Render(n_frames), build(O).Render(n_frames)
+    assert cm.last_stats["mac_variant_used"] == 3 and cu.last_stats["mac_variant_used"] == 3
+    assert (cm.last_stats["mac_flops"] < 0.99 * cu.last_stats["mac_flops"]) == mixed_expected
+    assert np.abs(yo).max() > 1e-2
+    assert np.abs(ym - yo).max() <= TOL and np.abs(yu - yo).max() <= TOL
+    assert np.abs(ym - yu).max() <= 2e-6
+    ym2 = cm.Render(128 * 10)  # the cached double-length spectra serve the next render of the context too
+    assert np.isfinite(ym2).all()

@@ -706,6 +706,11 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   st.voices = (int64_t)S;
   st.frames = a.n_frames;
   ctx->stats = st;
+  trace.mark("streams synchronised");
+  if (trace.on) {  // (what the destructors do on return, made visible)
+    scratch.release();
+    trace.mark("scratch released");
+  }
   return GAC_OK;
 }
 

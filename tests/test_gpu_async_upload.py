@@ -46,3 +46,44 @@ def test_async_flag_with_pageable_memory_falls_back_to_copy_during_call():
     ya = synth.build_c1(G, fs, src, ir, async_upload=True).Render(24000)   # pageable numpy arrays: copied during the call
     yb = synth.build_c1(G, fs, src, ir, async_upload=False).Render(24000)
     assert np.array_equal(ya, yb) and ya.any()
+
+
+def test_deferred_ir_preparation_survives_early_buffer_destroy_and_unused_irs():
+    """Async mode defers IR preparation to the first render that uses the IR; until then the IR keeps its source buffer alive even
+    if the caller destroys the buffer handle, and an IR that is never used releases it when it is destroyed."""
+    import ctypes as C
+    import graphaudio_b200 as G
+    from graphaudio_b200 import _native as N
+    from graphaudio_b200.api import check
+    fs = 48000
+    L = N.lib()
+    src, ir = synth.make_voice_inputs(7, 30000, 9000)
+    keep = []
+    pin = lambda xs: [(_pinned(a)) for a in xs]  # noqa: E731
+    ps, pi, pu = pin(src), pin(ir), pin(ir)
+    keep += [t for _, t in ps + pi + pu]
+
+    def render(async_upload, destroy_ir_buffer_early):
+        ctx = G.OfflineAudioContext(fs, async_upload=async_upload)
+        s = G.AudioBufferSourceNode(ctx)
+        s.Buffer = G.PlayableAudioBuffer.FromChannelArrays([a for a, _ in ps], fs)
+        conv = G.ConvolverNode(ctx)
+        irbuf = G.PlayableAudioBuffer.FromChannelArrays([a for a, _ in pi], fs)
+        conv.Buffer = irbuf
+        unused = G.ConvolverNode(ctx)  # prepared (deferred) but never connected: its IR is never used by a render
+        unused.Buffer = G.PlayableAudioBuffer.FromChannelArrays([a for a, _ in pu], fs)
+        if destroy_ir_buffer_early:
+            h = irbuf._handles.pop(id(ctx))
+            ctx._owned_buffers.remove(h)
+            check(L.gac_buffer_destroy(h))  # the handle is gone for the caller; the deferred preparation still reads the data
+        s.Connect(conv).Connect(ctx.Destination)
+        s.Start()
+        y = ctx.Render(40000)
+        y2 = ctx.Render(2000)  # a second render of the same context: the IR is prepared now, nothing is deferred any more
+        ctx.Dispose()
+        return y, y2
+    ya, ya2 = render(True, True)
+    yb, yb2 = render(True, False)
+    ys, ys2 = render(False, False)
+    assert ya.any() and np.array_equal(ya, yb) and np.array_equal(ya, ys)
+    assert np.array_equal(ya2, ys2) and np.array_equal(yb2, ys2)

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from tests import test_oracle_kats as T  # noqa: E402
 
 here = os.path.dirname(os.path.abspath(__file__))
-for name, fn in (("c2_small", T._golden_c2), ("c3_small", T._golden_c3)):
+for name, fn in (("c2_small", T._golden_c2), ("c3_small", T._golden_c3), ("f3_small", T._golden_f3)):
     y = fn()
     np.save(os.path.join(here, name + ".npy"), y)
     print(name, y.shape, float(np.abs(y).max()))

@@ -173,3 +173,15 @@ def test_max_delay_time_is_validated():
         G.DelayNode(ctx, 0.0)
     with pytest.raises(G.ArgumentOutOfRangeException):
         G.DelayNode(ctx, 10.5)
+
+
+def test_f3_graph_against_the_committed_golden_fixture():
+    """The graph of tests/golden/f3_small.npy (looping mono source -> pan sweep; late stereo source -> delay sweep -> pan -> biquad;
+    convolver bus), rendered on the device and compared with the committed fixture — no oracle call in this test."""
+    import os
+    import graphaudio_b200 as G
+    from tests import test_oracle_kats as T
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "f3_small.npy"))
+    y = T._golden_f3(G)
+    assert y.shape == ref.shape and np.abs(ref).max() > 1e-2
+    assert np.abs(y - ref).max() <= TOL

@@ -276,7 +276,40 @@ def _golden_c3():
     return synth.build_c3(O, fs, voices, 0.5, f0=300.0, f1=9000.0, t_scale=0.01, q=2.0).Render(8000)
 
 
-@pytest.mark.parametrize("name,fn", [("c2_small", _golden_c2), ("c3_small", _golden_c3)])
+def _golden_f3(api=None):
+    # looping mono source -> panner sweep (first quantum up-mixed) ; late stereo source -> delay sweep -> panner -> biquad ; both into a convolver bus
+    api = api or O
+    fs = 48000
+    ctx = api.OfflineAudioContext(fs)
+    bus = api.GainNode(ctx)
+    bus.Gain.Value = 0.5
+    a = api.AudioBufferSourceNode(ctx)
+    a.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(20, 1000)], fs)
+    a.Loop = True
+    a.LoopStart, a.LoopEnd = 100.2 / fs, 700.2 / fs
+    pa = api.StereoPannerNode(ctx)
+    pa.Pan.SetValueAtTime(-0.8, 0.0)
+    pa.Pan.LinearRampToValueAtTime(0.8, 0.1)
+    a.Connect(pa).Connect(bus)
+    a.Start()
+    b = api.AudioBufferSourceNode(ctx)
+    b.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(21 + c, 5000) for c in range(2)], fs)
+    d = api.DelayNode(ctx, 0.05)
+    d.DelayTime.SetValueAtTime(0.002, 0.0)
+    d.DelayTime.LinearRampToValueAtTime(0.04, 0.12)
+    pb = api.StereoPannerNode(ctx)
+    pb.Pan.Value = 0.3
+    f = api.BiQuadFilterNode(ctx)
+    f.Frequency.Value = 1200.0
+    b.Connect(d).Connect(pb).Connect(f).Connect(bus)
+    b.Start(0.01)
+    conv = api.ConvolverNode(ctx)
+    conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.decay_ir(23 + c, 1200) for c in range(2)], fs)
+    bus.Connect(conv).Connect(ctx.Destination)
+    return ctx.Render(8000)
+
+
+@pytest.mark.parametrize("name,fn", [("c2_small", _golden_c2), ("c3_small", _golden_c3), ("f3_small", _golden_f3)])
 def test_golden_fixture(name, fn):
     """tests/golden/*.npy were generated by tests/golden/make_golden.py from this oracle; bit-exact on the same libm."""
     path = os.path.join(GOLDEN, name + ".npy")

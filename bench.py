@@ -64,9 +64,9 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def ncu_traffic(variant_used):
-    """DRAM bytes per K6 launch on the C2 workload from the committed ncu --set full capture of the variant in use."""
-    name = {3: "k6_fft2_traffic.json"}.get(variant_used, "mac_traffic.json")
+def ncu_traffic(variant_used, big_segments=0):
+    """DRAM bytes per K6 launch (pair) on the C2 workload from the committed ncu --set full capture of the variant in use."""
+    name = {3: "k6_fft2_mixed_traffic.json" if big_segments > 0 else "k6_fft2_traffic.json"}.get(variant_used, "mac_traffic.json")
     p = os.path.join(ROOT, "profiles", name)
     if os.path.exists(p):
         with open(p) as f:
@@ -224,7 +224,8 @@ def run_ours(args, wl):
     L = N.lib()
 
     def build():
-        return build_graph(G, wl, voices, device_id=local, tile_blocks=args.tile_blocks, partition=args.partition, mac_variant=args.mac_variant)
+        return build_graph(G, wl, voices, device_id=local, tile_blocks=args.tile_blocks, partition=args.partition, mac_variant=args.mac_variant,
+                           uniform_segments=args.uniform_segments)
 
     def comm(ctx):
         if world > 1:
@@ -333,11 +334,15 @@ def run_ours(args, wl):
         alg_bytes = s_last["algorithmic_bytes"]
         achieved = alg_bytes / (mac_ms * 1e-3) / 1e9
         used = int(s_last["mac_variant_used"])
-        traffic = ncu_traffic(used) if args.workload == "c2" and args.partition == 128 else None
+        big = int(s_last.get("mac_big_segments", 0))
+        traffic = ncu_traffic(used, big) if args.workload == "c2" and args.partition == 128 else None
         flops = s_last["mac_flops"]
         k6_name = {1: "k_mac_stream (K6, direct sum, reference op order)", 2: "k_mac_tiled (K6, register-tiled direct sum, FFMA)",
                    4: "k_mac_tiled (K6, register-tiled direct sum, FFMA2)",
                    3: "k_fft2_conv16 (K6 spectral MAC as a fast convolution along block time)"}.get(used, "K6")
+        if used == 3 and big > 0:
+            k6_name = (f"k_fft2_conv16<2M> + k_fft2_conv16<M> (K6 as a fast convolution along block time: {big} double-length overlap-save "
+                       "segment(s) in front, two launches timed together)")
         moved = s_last["mac_bytes_moved"]
         conv_ms = float(np.mean([s["ms_fft_fwd"] + s["ms_mac"] + s["ms_fft_inv"] for s in stats]))
         # bytes the whole convolver (K5 + K6 + K7) has to move once: signal in (+ gain table), XT out/in, H2, YT out/in, signal out
@@ -416,6 +421,8 @@ def main():
                     help="K6 algorithm (gac_context_desc.mac_variant): 0 default (second-level FFT), 1 streaming direct sum, 4 register-tiled direct sum")
     ap.add_argument("--cpu-voices", dest="cpu_voices", type=int, default=8)
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--uniform-segments", dest="uniform_segments", action="store_true",
+                    help="resident arm: K6 without the double-length overlap-save segments in front (GAC_FLAG_UNIFORM_SEGMENTS), for A/B runs")
     ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="(accepted for compatibility; there is no extra measurement any more)")
     ap.add_argument("--sync-upload", dest="sync_upload", action="store_true",
                     help="e2e arm: copy every buffer during gac_buffer_create (reference semantics) instead of GAC_FLAG_ASYNC_UPLOAD")

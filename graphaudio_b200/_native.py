@@ -35,7 +35,7 @@ class gac_context_desc(C.Structure):
 
 
 GAC_FLAG_ASYNC_UPLOAD = 1
-GAC_FLAG_MIXED_SEGMENTS = 2
+GAC_FLAG_UNIFORM_SEGMENTS = 2
 
 
 class gac_event(C.Structure):
@@ -75,7 +75,7 @@ class gac_stats(C.Structure):
                 ("ms_fft_inv", C.c_double), ("ms_mix", C.c_double), ("ms_d2h", C.c_double), ("conv_units", C.c_int64),
                 ("algorithmic_bytes", C.c_double), ("mac_complex_macs", C.c_double), ("kernel_launches", C.c_int64),
                 ("voices", C.c_int64), ("frames", C.c_int64), ("mac_flops", C.c_double), ("mac_bytes_moved", C.c_double),
-                ("mac_variant_used", C.c_int32), ("reserved", C.c_int32), ("ms_delay", C.c_double), ("ms_panner", C.c_double)]
+                ("mac_variant_used", C.c_int32), ("mac_big_segments", C.c_int32), ("ms_delay", C.c_double), ("ms_panner", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -465,7 +465,7 @@ class OfflineAudioContext:
     """OfflineAudioContext.cs — `Render` is the one call that crosses into libgraphaudio_cuda.so."""
 
     def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32, async_upload=False,
-                 mixed_segments=False, _record_only=False):
+                 uniform_segments=False, _record_only=False):
         """partition / device_id / mac_variant / tile_blocks map onto gac_context_desc.  `_record_only=True` builds a context
         without a device handle: nodes, automation and topology can be recorded and inspected (`_topology()`), Render raises.
         It exists for the CPU unit tests of the host-side logic; it is not a fallback."""
@@ -484,7 +484,7 @@ class OfflineAudioContext:
             desc.tile_blocks = tile_blocks
             # async_upload: page-locked source arrays are uploaded asynchronously (GAC_FLAG_ASYNC_UPLOAD); the arrays handed
             # to PlayableAudioBuffer must then stay untouched until Render returns
-            desc.flags = (N.GAC_FLAG_ASYNC_UPLOAD if async_upload else 0) | (N.GAC_FLAG_MIXED_SEGMENTS if mixed_segments else 0)
+            desc.flags = (N.GAC_FLAG_ASYNC_UPLOAD if async_upload else 0) | (N.GAC_FLAG_UNIFORM_SEGMENTS if uniform_segments else 0)
             out = C.c_void_p()
             check(N.lib().gac_context_create(C.byref(desc), C.byref(out)))
             self._h = out.value

@@ -95,7 +95,7 @@ struct gac_context {
   int B = 128;
   int mac_variant = 0;
   int tile_blocks = 32;
-  bool mixed_segments = false;  // K6: double-length segments in front when that saves transform points (GAC_FLAG_MIXED_SEGMENTS; slower today)
+  bool mixed_segments = true;  // K6: double-length overlap-save segments in front when that saves work (GAC_FLAG_UNIFORM_SEGMENTS clears it)
   cudaStream_t stream = nullptr;
   float2* d_tw = nullptr;  // e^{-2 pi i k/(2B)}, k < B
   float2* d_tw2 = nullptr; // e^{-2 pi i e/8192}, e < 8192: twiddles of the second-level (block-time) FFT, fft2.cu
@@ -441,7 +441,7 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   ctx->tile_blocks = desc->tile_blocks == 64 ? 64 : 32;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->async_upload = (desc->flags & GAC_FLAG_ASYNC_UPLOAD) != 0;
-  ctx->mixed_segments = (desc->flags & GAC_FLAG_MIXED_SEGMENTS) != 0;
+  ctx->mixed_segments = (desc->flags & GAC_FLAG_UNIFORM_SEGMENTS) == 0;
   if (ctx->async_upload) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   ctx->scratch_budget = di.budget;
   {
@@ -877,6 +877,7 @@ struct RenderEnv {
   int64_t conv_units = 0;
   double alg_bytes = 0, macs = 0;
   double mac_flops = 0, mac_bytes = 0;  // flops issued / bytes the K6 variant in use has to move (X, H, Y once)
+  int mac_big = 0;                      // double-length segments per channel-convolver of the last second-level-FFT batch
   int mac_used = 0;                     // K6 variant of the last convolver batch (1 stream, 2/4 tiled, 3 second-level FFT)
   std::map<Sig*, std::pair<const float*, float>> fused;  // GainNode folded into the next convolver's forward FFT
   std::map<std::string, float*> param_tables;  // automation tables already evaluated in this render, by (rate, value, events)
@@ -1125,13 +1126,14 @@ static void plan_segments(int64_t QB, int M, int Lh, int* n_big, int* n_small) {
   const int64_t V = M - Lh;
   *n_big = 0;
   *n_small = (int)((QB + V - 1) / V);
-  if (2 * M > 4096) return;
+  if (2 * M > fft2_r16_max()) return;
   const int64_t Vb = 2 * (int64_t)M - Lh;
   double best = (double)*n_small * M * log2m;
   for (int nb = 1; (int64_t)(nb - 1) * Vb < QB; nb++) {
     const int64_t rem = std::max<int64_t>(0, QB - (int64_t)nb * Vb);
     const int ns = (int)((rem + V - 1) / V);
-    const double cost = (double)nb * 2 * M * (log2m + 1) + (double)ns * M * log2m;
+    // (the double-length kernel keeps half as many CTAs resident: measured at ~0.8 of the per-point rate, 4096 against 2048 points)
+    const double cost = (double)nb * 2 * M * (log2m + 1) / 0.8 + (double)ns * M * log2m;
     if (cost < best * 0.97) {  // (a tie keeps the single-length plan: one launch less)
       best = cost;
       *n_big = nb;
@@ -1140,13 +1142,40 @@ static void plan_segments(int64_t QB, int M, int Lh, int* n_big, int* n_small) {
   }
 }
 
-// second-level spectra of length 2 * M2 for an impulse response that a render wants to run with mixed segment lengths
-static int ensure_h2b(gac_context* ctx, gac_ir* ir) {
-  if (ir->d_H2b || ir->M2 <= 0) return GAC_OK;
-  const int B = ctx->B, Mb = 2 * ir->M2;
-  CU(cudaMallocAsync(&ir->d_H2b, sizeof(float2) * (size_t)ir->nch * (B + 1) * fft2_h2_row_elems(Mb), ctx->stream));
-  launch_fft2_prep(ir->d_H, (int64_t)ir->P16 * B, ir->nch, B, ir->P, Mb, ir->d_H2b, ctx->d_tw2, ctx->d_tab16, ctx->stream);
-  CU(cudaGetLastError());
+// Second-level spectra of length 2 * M2 for the impulse responses a voice batch wants to run with mixed segment lengths: allocated
+// on first use, prepared by ONE launch per transform length for the whole batch (the first-level spectra exist: prepare_irs ran).
+static int ensure_h2b_batch(RenderEnv& env, const std::vector<const gac_ir*>& irs) {
+  gac_context* ctx = env.ctx;
+  const int B = ctx->B;
+  std::map<int, std::vector<IrChanJob>> by_m;
+  for (const gac_ir* cir : irs) {
+    gac_ir* ir = const_cast<gac_ir*>(cir);
+    if (ir->d_H2b || ir->M2 <= 0) continue;
+    int n_big = 0, n_small = 0;
+    plan_segments(env.QB, ir->M2, ir->Lh, &n_big, &n_small);
+    if (n_big == 0) continue;
+    const int Mb = 2 * ir->M2;
+    const size_t row = (size_t)fft2_h2_row_elems(Mb);
+    CU(cudaMallocAsync(&ir->d_H2b, sizeof(float2) * (size_t)ir->nch * (B + 1) * row, ctx->stream));
+    for (int c = 0; c < ir->nch; c++) {
+      IrChanJob j{};
+      j.H = ir->d_H + (size_t)c * ir->P16 * B;
+      j.P = ir->P;
+      j.P16 = ir->P16;
+      j.H2 = ir->d_H2b + (size_t)c * (B + 1) * row;
+      by_m[Mb].push_back(j);
+    }
+  }
+  for (auto& kv : by_m) {
+    auto& hj = env.keep->make<IrChanJob>();
+    hj = kv.second;
+    IrChanJob* dj = nullptr;
+    int rc = env.scratch->upload(&dj, hj);
+    if (rc) return rc;
+    launch_fft2_prep_batch(dj, (int)hj.size(), B, kv.first, ctx->d_tab16, ctx->stream);
+    env.launches++;
+    CU(cudaGetLastError());
+  }
   return GAC_OK;
 }
 
@@ -1206,6 +1235,7 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
       const int64_t b0 = (int64_t)n_big * (2 * (int64_t)M - it.Lh);  // (multiple of 16: M and Lh are)
       max_seg = std::max(max_seg, nseg);
       max_seg_big = std::max(max_seg_big, n_big);
+      env.mac_big = std::max(env.mac_big, n_big);
       for (int k = 0; k < it.n_mac; k++) {
         Yc[k] = dY + (yi++) * (size_t)C * Qs;
         Fft2Job j;
@@ -1356,10 +1386,10 @@ static int prepare_irs(RenderEnv& env, const std::vector<const gac_ir*>& irs) {
     size_t i1 = i0;
     while (i1 < ms.size() && ms[i1] == ms[i0]) i1++;
     const int M = ms[i0];
-    if (M > 0 && M <= 4096) {
+    if (M > 0 && M <= fft2_r16_max()) {
       launch_fft2_prep_batch(dcj + i0, (int)(i1 - i0), B, M, ctx->d_tab16, ctx->stream);
       env.launches++;
-    } else if (M > 4096) {  // radix-8 plan: per channel
+    } else if (M > 0) {  // radix-8 plan: per channel
       for (size_t i = i0; i < i1; i++) {
         launch_fft2_prep(cjs[i].H, 0, 1, B, cjs[i].P, M, cjs[i].H2, ctx->d_tw2, ctx->d_tab16, ctx->stream);
         env.launches++;
@@ -1596,11 +1626,17 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     // ---------------- ConvolverNode (K5, K6, K7)
     if (!convs.empty()) {
       {
-        std::vector<const gac_ir*> need;
+        std::vector<const gac_ir*> need, reused;
         for (size_t k : convs)
-          if ((*sigs[k].ops)[pos].ir) need.push_back((*sigs[k].ops)[pos].ir);
+          if (const gac_ir* ir = (*sigs[k].ops)[pos].ir) {
+            need.push_back(ir);
+            // double-length spectra pay for themselves only when the impulse response serves more than one render: an IR whose
+            // (deferred) preparation happens in this very render keeps the single-length plan
+            if (ir->prepared) reused.push_back(ir);
+          }
         int rc = prepare_irs(env, need);
         if (rc) return rc;
+        if (ctx->mixed_segments && (rc = ensure_h2b_batch(env, reused))) return rc;
       }
       std::vector<ConvItem> items;
       auto& zj = env.keep->make<GainJob>();
@@ -1641,11 +1677,8 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         const float2* h2b = nullptr;
         if (it.M2 > 0 && ctx->mixed_segments) {
           plan_segments(env.QB, it.M2, it.Lh, &it.n_big, &it.n_small);
-          if (it.n_big > 0) {
-            int rc = ensure_h2b(ctx, const_cast<gac_ir*>(ir));
-            if (rc) return rc;
-            h2b = ir->d_H2b;
-          }
+          if (it.n_big > 0) h2b = ir->d_H2b;  // (prepared above for the whole batch)
+          if (!h2b) it.n_big = 0;
         }
         auto H2bch = [&](int c) { return h2b ? h2b + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(2 * ir->M2) : (const float2*)nullptr; };
         it.lo = s.lo;

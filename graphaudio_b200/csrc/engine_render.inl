@@ -702,6 +702,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   st.mac_flops = env.mac_flops;
   st.mac_bytes_moved = env.mac_bytes;
   st.mac_variant_used = env.mac_used;
+  st.mac_big_segments = env.mac_big;
   st.kernel_launches = env.launches;
   st.voices = (int64_t)S;
   st.frames = a.n_frames;

@@ -22,6 +22,7 @@
 // order the spectrum differently, so H2 is always prepared by the plan that consumes it.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "fft2_core.cuh"
 #include "gac_kernels.h"
@@ -183,7 +184,7 @@ template <int M>
 constexpr size_t conv16_smem() { return sizeof(float2) * (size_t)(2 * r16::smem_elems(M) + M) + 16; }
 
 template <int M>
-__global__ void __launch_bounds__(M / 16) k_fft2_conv16(const Fft2Job* __restrict__ jobs, const float2* __restrict__ tab, int64_t n_blocks, int64_t xs,
+__global__ void __launch_bounds__(M / 16, 8192 / M) k_fft2_conv16(const Fft2Job* __restrict__ jobs, const float2* __restrict__ tab, int64_t n_blocks, int64_t xs,
                                                         int64_t ys) {
   using P = r16::Plan<M>;
   constexpr int T = P::T;
@@ -348,7 +349,18 @@ void launch_fft2_prep_batch(const IrChanJob* d_jobs, int n_jobs, int B, int M, c
   }
 }
 
-int fft2_h2_row_elems(int M) { return M <= 4096 ? r16::smem_elems(M) : M; }
+// Which plan runs a transform length: radix 16 up to 4096 points, radix 8 (M/8 threads x 8 points) above.  GAC_FFT2_R16_MAX=2048
+// moves the 4096-point transforms to the radix-8 plan as well (A/B measurements: 512 threads and 32 KB per CTA instead of 256
+// threads and 110 KB).  H2 is always prepared by the plan that consumes it.
+int fft2_r16_max() {
+  static const int v = [] {
+    const char* e = getenv("GAC_FFT2_R16_MAX");
+    const int x = e ? atoi(e) : 4096;
+    return (x == 512 || x == 1024 || x == 2048 || x == 4096) ? x : 4096;
+  }();
+  return v;
+}
+int fft2_h2_row_elems(int M) { return M <= fft2_r16_max() ? r16::smem_elems(M) : M; }
 
 int fft2_table_offset(int M) {  // offset of M's radix-16 twiddle table inside the concatenated table buffer
   // order: 512, 1024, 2048, 4096 (second-level transforms), then 128, 256 (first-level transforms of fft_r16.cu)
@@ -425,6 +437,10 @@ void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
     dim3 grid((unsigned)max_seg, (unsigned)C, (unsigned)nj);
+    if (M == 4096 && fft2_r16_max() < 4096) {
+      conv_t<4096>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s);
+      continue;
+    }
     switch (M) {
       case 512: conv16_t<512>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
       case 1024: conv16_t<1024>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
@@ -439,6 +455,10 @@ void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, i
                       cudaStream_t s) {
   if (n_ch <= 0) return;
   dim3 grid((unsigned)(B + 1), (unsigned)n_ch);
+  if (M == 4096 && fft2_r16_max() < 4096) {
+    prep_t<4096>(d_H, h_ch_stride, grid, B, P, d_H2, d_tw2, s);
+    return;
+  }
   switch (M) {
     case 512: prep16_t<512>(d_H, h_ch_stride, grid, B, P, d_H2, d_tab16, s); break;
     case 1024: prep16_t<1024>(d_H, h_ch_stride, grid, B, P, d_H2, d_tab16, s); break;

@@ -95,6 +95,7 @@ constexpr int kFft2TwLen = 8192;  // twiddle table exp(-2 pi i e / 8192)
 int fft2_pick_m(int P, int* Lh);
 // float2 elements of one H2 row (one bin of one IR channel): M for the radix-8 plan, the padded length for the radix-16 plan
 int fft2_h2_row_elems(int M);
+int fft2_r16_max();                  // largest transform length on the radix-16 plan (4096; GAC_FFT2_R16_MAX overrides for A/B runs)
 // d_tw2: the 8192-entry table (radix-8 plan, M = 8192); d_tab16: the concatenated radix-16 tables (M = 512 .. 4096)
 int fft2_table_total();              // float2 entries of the concatenated radix-16 tables
 int fft2_table_offset(int M);        // where M's table starts (M = 128, 256: the first-level transforms of fft_r16.cu)

@@ -78,11 +78,11 @@ typedef struct gac_context_desc {
  * preparation and the first voice batches of the render overlap the remaining copies.  Default (flag clear): the
  * reference's semantics — the data is copied during the call (PlayableAudioBuffer.cs:84-93). */
 #define GAC_FLAG_ASYNC_UPLOAD 1
-/* K6 (second-level FFT): run one or more overlap-save segments of TWICE the transform length in front when that saves transform
- * points (a 12 s render at P = 750: one 4096- and one 2048-point segment instead of four 2048-point ones, -25 % points).  Opt-in:
- * measured on B200 the 4096-point kernel (2 CTAs per SM) runs at half the per-point efficiency of the 2048-point one, so the mixed
- * plan is slower today (0.68 vs 0.49 ms on the bench workload); results agree to 2e-6. */
-#define GAC_FLAG_MIXED_SEGMENTS 2
+/* K6 (second-level FFT) runs one or more overlap-save segments of TWICE the transform length in front when that saves work (a 12 s
+ * render at P = 750: one 4096- and one 2048-point segment instead of four 2048-point ones, -25 % transform points, K6 0.51 -> 0.46 ms
+ * on the bench workload; the double-length spectra of an impulse response are prepared on first use).  This flag keeps every segment
+ * at the length picked for the impulse response (A/B measurements, tests); results agree to 2e-6. */
+#define GAC_FLAG_UNIFORM_SEGMENTS 2
 
 int gac_context_create(const gac_context_desc* desc, gac_context** out);
 int gac_context_destroy(gac_context* ctx);
@@ -286,7 +286,7 @@ typedef struct gac_stats {
   double mac_flops;            /* flops K6 actually issued (direct: 8/cMAC; second-level FFT: 2 FFTs + product per segment) */
   double mac_bytes_moved;      /* bytes the K6 variant in use has to move through HBM (X, H, Y once) */
   int32_t mac_variant_used;    /* 1 stream, 2/4 register-tiled, 3 second-level FFT (last convolver batch) */
-  int32_t reserved;
+  int32_t mac_big_segments;    /* variant 3: double-length overlap-save segments per channel-convolver in front (0: one length) */
   double ms_delay;             /* DelayNode gather                                                  */
   double ms_panner;            /* StereoPannerNode                                                  */
 } gac_stats;

@@ -157,3 +157,28 @@ def test_shard_ranges_partition_exactly():
     with pytest.raises(ValueError):
         sharding.shard_range(4, 2, 2)
     assert math.isclose(sum(len(sharding.shard_list(list(range(10)), r, 4)) for r in range(4)), 10)
+
+
+def test_occupancy_critical_kernels_stay_within_their_register_budget():
+    """K6 (k_fft2_conv16<M>) is sized for 512 resident threads per SM by shared memory (8192 / M CTAs of M / 16 threads); that only
+    holds while ptxas keeps it at <= 128 registers per thread.  A harmless-looking edit once took the 4096-point instantiation to 148
+    registers = ONE CTA per SM and K6 of the C5 shard from 1.23 to 1.89 ms — caught only by a measurement.  cuobjdump needs no GPU."""
+    import shutil
+    import subprocess
+    from graphaudio_b200 import _native as N
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "--dump-resource-usage", N.LIB_PATH], capture_output=True, text=True).stdout
+    regs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    k6 = {n: r for n, r in regs.items() if "k_fft2_conv16" in n}
+    assert len(k6) == 4
+    assert all(r <= 128 for r in k6.values()), k6

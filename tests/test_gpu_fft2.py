@@ -250,7 +250,7 @@ def test_sources_read_in_place_by_the_convolver(when, offset, duration):
     (38400, 128 * 1700, True),   # P = 300 (M = 1024, V = 720): one 2048-point segment (V = 1744) instead of three 1024-point ones
 ])
 def test_mixed_segment_lengths_match_uniform_segments_and_the_oracle(n_ir, n_frames, mixed_expected):
-    """K6 with double-length overlap-save segments in front (GAC_FLAG_MIXED_SEGMENTS, plan_segments) against the single-length plan and
+    """K6 with double-length overlap-save segments in front (the default; plan_segments) against the single-length plan and
     the CPU oracle."""
     G, O = _apis()
     src = [synth.splitmix_uniform(800 + c, n_frames - 256) for c in range(2)]
@@ -268,7 +268,7 @@ def test_mixed_segment_lengths_match_uniform_segments_and_the_oracle(n_ir, n_fra
         s.Connect(g).Connect(conv).Connect(ctx.Destination)
         s.Start()
         return ctx
-    cm, cu = build(G, mixed_segments=True), build(G)
+    cm, cu = build(G), build(G, uniform_segments=True)
     ym, yu, yo = cm.Render(n_frames), cu.Render(n_frames), build(O).Render(n_frames)
     assert cm.last_stats["mac_variant_used"] == 3 and cu.last_stats["mac_variant_used"] == 3
     assert (cm.last_stats["mac_flops"] < 0.99 * cu.last_stats["mac_flops"]) == mixed_expected

@@ -53,14 +53,14 @@ if "c3" in which:
     ctx.Dispose()
     del voices
 
-if "c5" in which:
+if "c5" in which or "c5p512" in which:
     fs, src_rate = 96000, 44100
     voices = []
     for v in range(32):
         src = [synth.splitmix_uniform(4 * v + c, 441000) for c in range(2)]
         ir = [synth.decay_ir(4 * v + 2 + c, 960000) for c in range(2)]
         voices.append((src, ir, synth.voice_gains(v)))
-    for part in (512, 128):
+    for part in ((512,) if "c5p512" in which else (512, 128)):
         ctx = synth.build_c5(G, fs, src_rate, voices, 1.0 / 16, partition=part)
         run_single(f"C5 shard (32 of 256 voices: 44.1->96 kHz resample -> gain -> 10 s IR, 20 s, partition {part})", ctx, 20 * fs, 32, 20.0, reps=3)
         ctx.Dispose()

@@ -22,6 +22,7 @@ GAC_ERR_OUT_OF_MEMORY = -7
 GAC_ERR_NCCL = -8
 GAC_ERR_UNSUPPORTED = -9
 
+GAC_EVENT_EPOCH = 4
 GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER, GAC_OP_DELAY, GAC_OP_PANNER = 1, 2, 3, 4, 5
 GAC_SAMPLE_S16, GAC_SAMPLE_S24, GAC_SAMPLE_S32, GAC_SAMPLE_F32 = 0, 1, 2, 3
 

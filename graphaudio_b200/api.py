@@ -172,6 +172,9 @@ class AudioParam:
         self.DefaultValue, self.MinValue, self.MaxValue = float(default), float(mn), float(mx)
         self._value = np.float32(default)
         self._events: List[tuple] = []  # (type, value, target, time, time_constant)
+        # (first quantum, value, events) as each Render call saw the parameter: edits made between successive Render calls act from
+        # the next unprocessed quantum on (OfflineAudioContext.cs:55-100), earlier quanta keep what they were rendered with
+        self._epochs: List[tuple] = []
 
     def _clamp(self, v):
         v = np.float32(v)
@@ -214,13 +217,30 @@ class AudioParam:
     def CancelScheduledValues(self, cancelTime):  # :312-331
         self._events = [e for e in self._events if e[3] < cancelTime]
 
-    def _desc(self, keep: list) -> N.gac_param:
+    def _commit(self, q_now: int):
+        """Called when a graph is flattened for a render that starts at quantum q_now."""
+        state = (float(self._value), tuple(self._events))
+        if not self._epochs:
+            self._epochs = [(0,) + state]
+        elif state != self._epochs[-1][1:]:
+            if q_now > self._epochs[-1][0]:
+                self._epochs.append((q_now,) + state)
+            else:  # edited again before anything further was rendered
+                self._epochs[-1] = (self._epochs[-1][0],) + state
+
+    def _desc(self, keep: list, q_now: int = 0) -> N.gac_param:
+        self._commit(q_now)
+        flat = []
+        for k, (q0, value, events) in enumerate(self._epochs):
+            if k > 0:
+                flat.append((N.GAC_EVENT_EPOCH, value, 0.0, 0.0, float(q0)))
+            flat.extend(events)
         p = N.gac_param()
-        p.value = float(self._value)
-        p.n_events = len(self._events)
-        if self._events:
-            arr = (N.gac_event * len(self._events))()
-            for i, (t, v, tg, tm, tc) in enumerate(self._events):
+        p.value = self._epochs[0][1]
+        p.n_events = len(flat)
+        if flat:
+            arr = (N.gac_event * len(flat))()
+            for i, (t, v, tg, tm, tc) in enumerate(flat):
                 arr[i].type, arr[i].value, arr[i].target, arr[i].time, arr[i].time_constant = t, v, tg, tm, tc
             keep.append(arr)
             p.events = arr
@@ -235,7 +255,23 @@ class AudioNode:
         self._in: List["AudioNode"] = []   # upstream nodes in connection order (AudioNodeInput._connectedOutputs)
         self._out: List["AudioNode"] = []
         self._n_inputs, self._n_outputs = n_inputs, n_outputs
+        self._born_frames = getattr(context, "_frames_rendered", 0)  # frames the context had rendered when the node was created
         context._nodes.append(self)
+
+    def _existed_in_a_render(self):
+        return self._born_frames < getattr(self.Context, "_frames_rendered", 0)
+
+    def _upstream_existed_in_a_render(self):
+        seen, stack = set(), [self]
+        while stack:
+            n = stack.pop()
+            if id(n) in seen:
+                continue
+            seen.add(id(n))
+            if n._existed_in_a_render():
+                return True
+            stack.extend(n._in)
+        return False
 
     def Connect(self, destination: "AudioNode", outputIndex=0, inputIndex=0):
         if outputIndex < 0 or outputIndex >= self._n_outputs:
@@ -245,6 +281,11 @@ class AudioNode:
         if destination is self:
             raise InvalidOperationException("Cannot connect a node to itself")  # AudioNodeOutput.cs:43-44
         if destination not in self._out:
+            # Between successive Render calls the device path re-renders the timeline from frame 0 with the CURRENT graph, so an edit
+            # is only exact if it cannot change what was already rendered: parameter edits (epochs), sources started / stopped later,
+            # and new branches whose nodes did not exist before.  Re-wiring nodes that already took part in a render is refused.
+            if self._upstream_existed_in_a_render():
+                self.Context._unsupported_edit = "Connect() of a node that already took part in a Render call"
             self._out.append(destination)
             destination._in.append(self)
         return destination
@@ -252,6 +293,8 @@ class AudioNode:
     def Disconnect(self, destination: Optional["AudioNode"] = None):
         for d in ([destination] if destination is not None else list(self._out)):
             if d in self._out:
+                if self._upstream_existed_in_a_render():
+                    self.Context._unsupported_edit = "Disconnect() of a node that already took part in a Render call"
                 self._out.remove(d)
                 d._in.remove(self)
 
@@ -271,6 +314,7 @@ class AudioBufferSourceNode(AudioNode):
         self._loop_end = 0.0
         self._started = False
         self._when = math.nan
+        self._start_frames = 0
         self._offset = 0.0
         self._duration = math.inf
         self._stop = math.nan
@@ -309,21 +353,36 @@ class AudioBufferSourceNode(AudioNode):
             raise InvalidOperationException("Cannot start without a buffer set")
         self._started = True
         self._when, self._offset, self._duration = float(when), float(offset), float(duration)
+        self._start_frames = getattr(self.Context, "_frames_rendered", 0)  # Start() between Render calls acts from the next quantum on
 
     def Stop(self, when=0.0):  # :116-129
+        # called between Render calls it cannot silence quanta that were already rendered: the stop time is at least the start
+        # time of the next unprocessed quantum (the reference tests t0 < stopTime per block, :139)
+        at = max(0.0, float(when), self.Context._block_time(self.Context._q_now()) if hasattr(self.Context, "_q_now") else 0.0)
         if math.isnan(self._stop):
-            self._stop = max(0.0, float(when))
+            self._stop = at
         else:
-            self._stop = min(self._stop, max(0.0, float(when)))
+            self._stop = min(self._stop, at)
 
 
 class BiQuadFilterNode(AudioNode):
     def __init__(self, context):
         super().__init__(context)
-        self.Type = FilterType.Lowpass
+        self._type = FilterType.Lowpass
         self.Frequency = AudioParam(1000.0, 1.0, context.SampleRate / 2.0)  # :63-68
         self.Q = AudioParam(1.0, 0.001, 1000.0)                             # :70-75
         self.Gain = AudioParam(0.0, -60.0, 60.0)                            # :77-82 (k-rate)
+
+
+    @property
+    def Type(self):  # :42-52
+        return self._type
+
+    @Type.setter
+    def Type(self, value):
+        if value != self._type and self._existed_in_a_render():
+            self.Context._unsupported_edit = "BiQuadFilterNode.Type changed after the node took part in a Render call"
+        self._type = value
 
 
 class GainNode(AudioNode):
@@ -368,6 +427,8 @@ class ConvolverNode(AudioNode):
     def Buffer(self, value):  # :25-79: the convolvers are built here, with the Normalize value of this moment
         if value is self._buffer:
             return
+        if self._existed_in_a_render():  # an impulse-response swap mid-timeline (fresh delay lines from that quantum on, :51-77)
+            self.Context._unsupported_edit = "ConvolverNode.Buffer changed after the node took part in a Render call"
         if value is None:
             self._buffer, self._ir = None, None
             return
@@ -493,23 +554,35 @@ class OfflineAudioContext:
         self.last_stats = None
 
     # ---- graph flattening: destination <- (bus chain <- fan-in)? <- voice chain <- source
+    def _q_now(self):
+        """First quantum the next Render call will process (the reference renders whole 128-frame blocks, OfflineAudioContext.cs:55-100)."""
+        return -(-self._frames_rendered // 128)
+
+    def _block_time(self, q):
+        """Start time of quantum q, accumulated like AudioContextBase.cs:78-79 (_currentTime += 128.0 / SampleRate)."""
+        t, inc = 0.0, 128.0 / self.SampleRate
+        for _ in range(int(q)):
+            t = t + inc
+        return t
+
     def _op_desc(self, node, keep):
         op = N.gac_op_desc()
+        q = self._q_now()
         if isinstance(node, BiQuadFilterNode):
             op.kind, op.filter_type = N.GAC_OP_BIQUAD, int(node.Type)
-            op.p0, op.p1, op.p2 = node.Frequency._desc(keep), node.Q._desc(keep), node.Gain._desc(keep)
+            op.p0, op.p1, op.p2 = node.Frequency._desc(keep, q), node.Q._desc(keep, q), node.Gain._desc(keep, q)
         elif isinstance(node, GainNode):
             op.kind = N.GAC_OP_GAIN
-            op.p0 = node.Gain._desc(keep)
+            op.p0 = node.Gain._desc(keep, q)
         elif isinstance(node, ConvolverNode):
             op.kind = N.GAC_OP_CONVOLVER
             op.ir = node._ir
         elif isinstance(node, DelayNode):
             op.kind, op.aux = N.GAC_OP_DELAY, node.MaxDelayTime
-            op.p0 = node.DelayTime._desc(keep)
+            op.p0 = node.DelayTime._desc(keep, q)
         elif isinstance(node, StereoPannerNode):
-            op.kind = N.GAC_OP_PANNER
-            op.p0 = node.Pan._desc(keep)
+            op.kind, op.aux = N.GAC_OP_PANNER, float(-(-node._born_frames // 128))
+            op.p0 = node.Pan._desc(keep, q)
         else:
             raise NotSupportedException(f"{type(node).__name__} is outside the accelerated path")
         return op
@@ -638,6 +711,10 @@ class OfflineAudioContext:
         return voices, buses, dest_inputs
 
     def _flatten(self):
+        if getattr(self, "_unsupported_edit", None):
+            raise NotSupportedException(
+                f"{self._unsupported_edit}: successive Render calls re-render the timeline on the device, which is exact for parameter "
+                "edits, for sources started or stopped in between and for new branches, not for re-wiring what was already rendered")
         keep = []
         voices, buses, dest_inputs, bus_targets, bus_inputs = self._topology_full()
         vdesc = (N.gac_voice_desc * max(1, len(voices)))()
@@ -648,6 +725,8 @@ class OfflineAudioContext:
                     when = math.nan
                 else:
                     when = src._when
+                    if src._start_frames > 0:  # started between Render calls: not before the first quantum that was still unprocessed
+                        when = max(when, self._block_time(-(-src._start_frames // 128)))
                 v.loop, v.loop_start, v.loop_end = int(bool(src.Loop)), src.LoopStart, src.LoopEnd
                 v.source = src.Buffer._handle(self) if src.Buffer is not None else None
                 v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop

@@ -52,6 +52,14 @@ static int fail(int code, const char* fmt, ...) {
 struct ParamH {
   float value = 0.f;
   std::vector<gac_event> ev;
+  // further epochs of a parameter that was edited between successive Render calls (GAC_EVENT_EPOCH): from quantum q0 on the
+  // parameter is (value, ev) of that epoch
+  struct Epoch {
+    int64_t q0;
+    float value;
+    std::vector<gac_event> ev;
+  };
+  std::vector<Epoch> later;
 };
 struct OpH {
   int kind = 0;
@@ -730,10 +738,22 @@ static int copy_param(const gac_param& p, ParamH* out, const char* what) {
   out->value = p.value;
   if (p.n_events < 0) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: negative event count", what);
   if (p.n_events > 0 && !p.events) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: events is null", what);
-  out->ev.assign(p.events, p.events + p.n_events);
+  out->ev.clear();
+  out->later.clear();
+  std::vector<gac_event>* cur = &out->ev;
   for (int i = 0; i < p.n_events; i++) {
-    if (out->ev[i].type < 0 || out->ev[i].type > 3) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: bad event type", what);
-    if (i > 0 && out->ev[i].time < out->ev[i - 1].time) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: events must be sorted by time (AudioParam.AddEvent order)", what);
+    const gac_event& e = p.events[i];
+    if (e.type == GAC_EVENT_EPOCH) {
+      const int64_t q0 = (int64_t)e.time_constant;
+      const int64_t prev = out->later.empty() ? 0 : out->later.back().q0;
+      if (!(e.time_constant >= 1.0) || q0 <= prev) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: epoch markers must carry increasing quantum indices >= 1", what);
+      out->later.push_back({q0, e.value, {}});
+      cur = &out->later.back().ev;
+      continue;
+    }
+    if (e.type < 0 || e.type > 3) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: bad event type", what);
+    if (!cur->empty() && e.time < cur->back().time) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: events must be sorted by time (AudioParam.AddEvent order)", what);
+    cur->push_back(e);
   }
   return GAC_OK;
 }
@@ -766,6 +786,8 @@ static int copy_ops(gac_context* ctx, int n, const gac_op_desc* ops, std::vector
         if ((rc = copy_param(ops[i].p0, &o.p0, "delay.delayTime"))) return rc;
         break;
       case GAC_OP_PANNER:
+        o.aux = ops[i].aux;
+        if (!(o.aux >= 0.0)) return fail(GAC_ERR_OUT_OF_RANGE, "panner: first processed quantum must be >= 0");
         if ((rc = copy_param(ops[i].p0, &o.p0, "panner.pan"))) return rc;
         break;
       default:
@@ -890,16 +912,25 @@ struct RenderEnv {
 
 static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector<ParamJob>& jobs, float** out_table) {
   *out_table = nullptr;
-  if (p.ev.empty()) return GAC_OK;
+  if (p.ev.empty() && p.later.empty()) return GAC_OK;
   // voices that schedule the same automation (same value, same events) share one table: the curve depends on nothing else
   std::string key(1, a_rate ? 'a' : 'k');
   key.append(reinterpret_cast<const char*>(&p.value), sizeof(float));
-  for (const gac_event& e : p.ev) {  // field by field: the struct has 4 bytes of padding
-    key.append(reinterpret_cast<const char*>(&e.type), sizeof(e.type));
-    key.append(reinterpret_cast<const char*>(&e.value), sizeof(e.value));
-    key.append(reinterpret_cast<const char*>(&e.target), sizeof(e.target));
-    key.append(reinterpret_cast<const char*>(&e.time), sizeof(e.time));
-    key.append(reinterpret_cast<const char*>(&e.time_constant), sizeof(e.time_constant));
+  auto key_events = [&](const std::vector<gac_event>& ev) {
+    for (const gac_event& e : ev) {  // field by field: the struct has 4 bytes of padding
+      key.append(reinterpret_cast<const char*>(&e.type), sizeof(e.type));
+      key.append(reinterpret_cast<const char*>(&e.value), sizeof(e.value));
+      key.append(reinterpret_cast<const char*>(&e.target), sizeof(e.target));
+      key.append(reinterpret_cast<const char*>(&e.time), sizeof(e.time));
+      key.append(reinterpret_cast<const char*>(&e.time_constant), sizeof(e.time_constant));
+    }
+  };
+  key_events(p.ev);
+  for (const ParamH::Epoch& ep : p.later) {
+    key.append("|", 1);
+    key.append(reinterpret_cast<const char*>(&ep.q0), sizeof(ep.q0));
+    key.append(reinterpret_cast<const char*>(&ep.value), sizeof(ep.value));
+    key_events(ep.ev);
   }
   auto hit = env.param_tables.find(key);
   if (hit != env.param_tables.end()) {
@@ -919,16 +950,24 @@ static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector
   env.param_tables[key] = tab;
   if (!env.ev_host) env.ev_host = &env.keep->make<DevEvent>();
   static_assert(sizeof(DevEvent) == sizeof(gac_event), "event layout");
-  const size_t off = env.ev_host->size();
-  env.ev_host->resize(off + p.ev.size());
-  memcpy(env.ev_host->data() + off, p.ev.data(), sizeof(gac_event) * p.ev.size());
-  ParamJob j;
-  j.value = p.value;
-  j.n_events = (int)p.ev.size();
-  j.events = reinterpret_cast<const DevEvent*>(off);  // offset into the batch's event block; made a pointer by run_param_jobs
-  j.out = tab;
-  j.a_rate = a_rate ? 1 : 0;
-  jobs.push_back(j);
+  // one job per epoch (a parameter that was never edited between Render calls has one), each writing its own quanta
+  auto add_job = [&](float value, const std::vector<gac_event>& ev, int64_t q_lo, int64_t q_hi) {
+    const size_t off = env.ev_host->size();
+    env.ev_host->resize(off + ev.size());
+    if (!ev.empty()) memcpy(env.ev_host->data() + off, ev.data(), sizeof(gac_event) * ev.size());
+    ParamJob j;
+    j.value = value;
+    j.n_events = (int)ev.size();
+    j.events = reinterpret_cast<const DevEvent*>(off);  // offset into the batch's event block; made a pointer by run_param_jobs
+    j.out = tab;
+    j.a_rate = a_rate ? 1 : 0;
+    j.q_lo = q_lo;
+    j.q_hi = q_hi;
+    jobs.push_back(j);
+  };
+  add_job(p.value, p.ev, 0, p.later.empty() ? std::numeric_limits<int64_t>::max() : p.later[0].q0);
+  for (size_t e = 0; e < p.later.size(); e++)
+    add_job(p.later[e].value, p.later[e].ev, p.later[e].q0, e + 1 < p.later.size() ? p.later[e + 1].q0 : std::numeric_limits<int64_t>::max());
   *out_table = tab;
   return GAC_OK;
 }
@@ -1501,10 +1540,13 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         j.hi = s.hi;
         j.sp_block = -(int64_t)1 << 40;
         j.sp_mode = 0;
-        if (s.ch == 1 && s.lo == 0 && s.hi > 0) {  // no upstream block exists before the first quantum: the input takes its own channelCount (2)
-          j.sp_block = 0;
+        // `first` = the first quantum this node processes (0, or later for a node created between two Render calls): no upstream
+        // block exists yet then, so the input takes its own channelCount (2)
+        const int64_t first = (int64_t)(*s.ops)[pos].aux * 128;
+        if (s.ch == 1 && s.lo <= first && first < s.hi) {
+          j.sp_block = first;
           j.sp_mode = 1;
-        } else if (s.from_source && pos == 0 && s.ch == 2 && s.lo > 0) {  // the source's idle block before its start had one channel
+        } else if (s.from_source && pos == 0 && s.ch == 2 && s.lo > first) {  // the source's idle block before its start had one channel
           j.sp_block = s.lo;
           j.sp_mode = 2;
         }

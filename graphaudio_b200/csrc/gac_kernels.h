@@ -128,6 +128,7 @@ struct ParamJob {
   const DevEvent* events;
   float* out;       // [n_frames] for a-rate, [n_blocks] for k-rate
   int a_rate;
+  int64_t q_lo = 0, q_hi = INT64_MAX;  // quanta this job writes (one job per epoch of a parameter edited between Render calls)
 };
 void launch_param_eval(const ParamJob* d_jobs, int n_jobs, const double* d_block_time, int64_t n_quanta, int sample_rate, cudaStream_t s);
 

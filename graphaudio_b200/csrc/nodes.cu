@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
   float boundary = job.value;
   if (job.a_rate) {
     const int64_t n = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
-    if (n >= n_quanta * 128) return;
+    if (n >= n_quanta * 128 || (n >> 7) < job.q_lo || (n >> 7) >= job.q_hi) return;
     const double t0 = block_time[n >> 7];  // the four frames share a quantum (4 divides 128)
     float v[4];
 #pragma unroll
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
     *reinterpret_cast<float4*>(job.out + n) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
     const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (b >= n_quanta) return;
+    if (b >= n_quanta || b < job.q_lo || b >= job.q_hi) return;
     const double t = block_time[b];
     advance_interval(job.events, job.n_events, t, i, boundary);
     job.out[b] = eval_interval(job.value, job.events, job.n_events, i, boundary, t, lr_i, lr);  // ComputeKRate :144-146

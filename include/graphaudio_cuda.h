@@ -117,7 +117,14 @@ typedef enum gac_event_type {
   GAC_EVENT_SET_VALUE = 0,        /* SetValueAtTime                 AudioParam.cs:252 */
   GAC_EVENT_LINEAR_RAMP = 1,      /* LinearRampToValueAtTime        AudioParam.cs:266 */
   GAC_EVENT_EXPONENTIAL_RAMP = 2, /* ExponentialRampToValueAtTime   AudioParam.cs:280 */
-  GAC_EVENT_SET_TARGET = 3        /* SetTargetAtTime                AudioParam.cs:297 */
+  GAC_EVENT_SET_TARGET = 3,       /* SetTargetAtTime                AudioParam.cs:297 */
+  GAC_EVENT_EPOCH = 4             /* not an AudioParam event: a marker that splits the list into EPOCHS for parameters that were edited
+                                     between successive Render calls of one context (OfflineAudioContext.cs:55-100: the timeline
+                                     continues; AudioParam.Value / scheduling calls made in between act from the next unprocessed
+                                     quantum on).  value = the static value from then on, time_constant = index of the first
+                                     quantum of the epoch (> the previous epoch's), time / target unused; the events behind the
+                                     marker (up to the next one) are the parameter's whole event list during that epoch.  Frames of
+                                     quantum q are evaluated with the (value, events) of the last epoch that starts at or before q */
 } gac_event_type;
 
 typedef struct gac_event {
@@ -166,7 +173,9 @@ typedef struct gac_op_desc {
   gac_param p2;        /* BIQUAD: Gain in dB (k-rate)                                          */
   const gac_ir* ir;    /* CONVOLVER: prepared impulse response; NULL ≙ ConvolverNode without a
                           Buffer, which outputs silence (ConvolverNode.cs:107-119)             */
-  double aux;          /* DELAY: maxDelayTime in seconds, (0, 10] (DelayNode.cs:22-29); else 0  */
+  double aux;          /* DELAY: maxDelayTime in seconds, (0, 10] (DelayNode.cs:22-29).  PANNER: index of the first quantum the
+                          node processes (0; later for a node created between two Render calls): its ClampedMax input has
+                          no upstream block to count channels from in that quantum (AudioNodeInput.cs:109,140-168).  Else 0 */
 } gac_op_desc;
 
 /* One voice = AudioBufferSourceNode -> ops[0] -> ops[1] -> ... -> bus (or destination).

@@ -182,3 +182,27 @@ def test_occupancy_critical_kernels_stay_within_their_register_budget():
     k6 = {n: r for n, r in regs.items() if "k_fft2_conv16" in n}
     assert len(k6) == 4
     assert all(r <= 128 for r in k6.values()), k6
+
+
+def test_parameter_epochs_are_recorded_per_render_call():
+    """Edits between successive Render calls become epochs (GAC_EVENT_EPOCH markers); host logic only."""
+    ctx = G.OfflineAudioContext(48000, _record_only=True)
+    g = G.GainNode(ctx)
+    g.Gain.Value = 0.5
+    g.Gain.LinearRampToValueAtTime(1.0, 0.5)
+    keep = []
+    p = g.Gain._desc(keep, 0)
+    assert (p.value, p.n_events) == (0.5, 1)
+    g.Gain.Value = 0.25           # clears the ramp (AudioParam.cs:34-49) — but only from the next unprocessed quantum on
+    p = g.Gain._desc(keep, 0)     # nothing rendered in between: the first epoch is simply replaced
+    assert (p.value, p.n_events) == (0.25, 0)
+    g.Gain.SetValueAtTime(0.75, 1.0)
+    p = g.Gain._desc(keep, 8)     # 1000 frames rendered -> the edit acts from quantum 8
+    ev = [(p.events[i].type, p.events[i].value, p.events[i].time, p.events[i].time_constant) for i in range(p.n_events)]
+    assert p.value == 0.25 and ev == [(N.GAC_EVENT_EPOCH, 0.25, 0.0, 8.0), (0, 0.75, 1.0, 0.0)]
+    p = g.Gain._desc(keep, 20)    # unchanged since: no new epoch
+    assert p.n_events == 2
+    g.Gain.Value = 0.1
+    p = g.Gain._desc(keep, 20)
+    assert p.n_events == 3 and p.events[2].type == N.GAC_EVENT_EPOCH and p.events[2].time_constant == 20.0 and abs(p.events[2].value - 0.1) < 1e-7
+    assert ctx._block_time(3) == (128.0 / 48000 + 128.0 / 48000) + 128.0 / 48000

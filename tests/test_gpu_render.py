@@ -353,3 +353,68 @@ def test_looping_source_feeding_a_convolver_and_unsupported_variants():
         build(G, rate=0.5).Render(1280)   # the looping resampler path is not accelerated (and never approximated)
     with pytest.raises(G.NotSupportedException):
         build(G, ls=0.01, le=0.01).Render(1280)
+
+
+def test_parameter_edits_and_late_starts_between_successive_render_calls():
+    """OfflineAudioContext.cs:55-100: successive Render calls continue the timeline, and what the caller does in between (AudioParam.Value,
+    scheduling calls, Start / Stop of sources, new branches) acts from the next unprocessed 128-frame quantum on.  The device path
+    re-renders the timeline with per-quantum parameter epochs; same call sequence on the oracle."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+
+    def run(api):
+        ctx = api.OfflineAudioContext(fs)
+        bus = api.GainNode(ctx)
+        bus.Gain.Value = 0.5
+        bus.Connect(ctx.Destination)
+        a = api.AudioBufferSourceNode(ctx)
+        a.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(980 + c, 30000) for c in range(2)], fs)
+        f = api.BiQuadFilterNode(ctx)
+        f.Frequency.Value = 500.0
+        f.Q.Value = 4.0
+        g = api.GainNode(ctx)
+        g.Gain.SetValueAtTime(0.2, 0.0)
+        g.Gain.LinearRampToValueAtTime(1.0, 0.5)
+        d = api.DelayNode(ctx, 0.1)
+        d.DelayTime.Value = 0.01
+        conv = api.ConvolverNode(ctx)
+        conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.decay_ir(990 + c, 3000) for c in range(2)], fs)
+        a.Connect(f).Connect(g).Connect(d).Connect(conv).Connect(bus)
+        a.Start()
+        out = [ctx.Render(1000)]                      # ends inside quantum 7: the edits below act from quantum 8 (frame 1024)
+        g.Gain.Value = 0.6                            # clears the ramp
+        f.Frequency.SetValueAtTime(500.0, 0.0)
+        f.Frequency.ExponentialRampToValueAtTime(4000.0, 0.2)
+        bus.Gain.Value = 0.25
+        b = api.AudioBufferSourceNode(ctx)            # a new branch, started "in the past": plays from the next quantum
+        b.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(985, 6000)], fs)
+        pb = api.StereoPannerNode(ctx)
+        pb.Pan.Value = -0.5
+        b.Connect(pb).Connect(bus)
+        b.Start(0.001)
+        out.append(ctx.Render(3000))                  # frames 1000 .. 4000 (quantum boundary again inside a block)
+        d.DelayTime.Value = 0.03
+        g.Gain.SetTargetAtTime(0.0, 0.1, 0.05)
+        a.Stop(0.0)                                   # "stop now": silent from the next unprocessed quantum
+        out.append(ctx.Render(6000))
+        return np.concatenate(out, axis=1)
+    yg, yo = run(G), run(O)
+    assert np.abs(yo[:, :1000]).max() > 1e-3 and np.abs(yo[:, 1100:4000]).max() > 1e-3 and np.abs(yo[:, 6000:]).max() > 1e-5
+    assert np.abs(yg - yo).max() <= 1e-5
+
+
+def test_rewiring_after_a_render_is_refused_not_approximated():
+    import graphaudio_b200 as G
+    fs = 48000
+    ctx = G.OfflineAudioContext(fs)
+    s = G.AudioBufferSourceNode(ctx)
+    s.Buffer = G.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(995, 4000)], fs)
+    g = G.GainNode(ctx)
+    s.Connect(g).Connect(ctx.Destination)
+    s.Start()
+    ctx.Render(512)
+    extra = G.GainNode(ctx)
+    g.Connect(extra).Connect(ctx.Destination)  # a node that already rendered gets a second consumer
+    with pytest.raises(G.NotSupportedException):
+        ctx.Render(512)

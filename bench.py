@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--tile-blocks", dest="tile_blocks", type=int, default=32)
     ap.add_argument("--mac-variant", dest="mac_variant", type=int, default=0,
                     help="K6 algorithm (gac_context_desc.mac_variant): 0 default (second-level FFT), 1 streaming direct sum, 4 register-tiled direct sum")
-    ap.add_argument("--cpu-voices", dest="cpu_voices", type=int, default=8)
+    ap.add_argument("--cpu-voices", dest="cpu_voices", type=int, default=32)
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--uniform-segments", dest="uniform_segments", action="store_true",
                     help="resident arm: K6 without the double-length overlap-save segments in front (GAC_FLAG_UNIFORM_SEGMENTS), for A/B runs")

@@ -42,6 +42,8 @@ def test_c2_full_length_subset_matches_oracle():
     assert np.abs(yg - yo).max() <= 1e-5
     st = g.last_stats
     assert st["conv_units"] == 8 * 2 * 4500 and st["kernel_launches"] > 0
+    # the production K6 plan of the bench workload: second-level FFT, one 4096-point overlap-save segment in front of one 2048-point one
+    assert st["mac_variant_used"] == 3 and st["mac_big_segments"] == 1
     g.Dispose()
 
 

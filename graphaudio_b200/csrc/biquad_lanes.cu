@@ -18,6 +18,8 @@
 // TMA bulk copies (cp.async.bulk + mbarrier, 3-stage ring); lane r reads frame i at [i][r] — consecutive lanes, consecutive
 // 16 bytes, conflict-free — and y = b0*w + b1*w[n-1] + b2*w[n-2] (:138) is formed from the chain's results while the next
 // loads are in flight; each lane stores its row's 32 results as one 128-byte line.
+#include <cstdlib>
+
 #include "gac_kernels.h"
 
 namespace gac {
@@ -65,7 +67,7 @@ constexpr size_t kLanesSmem = (size_t)kStages * kStageBytes + 64 + kStages * 256
 //   and it moves on to the next broken link.  A segment that never re-joins hands its state on to the next one.
 template <bool REPAIR, bool WIDE>
 __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict__ jobs, int n_jobs, int64_t n_frames,
-                                                     const float4* __restrict__ s1t, const float4* __restrict__ s2t, int seg_slabs, int n_seg,
+                                                     const float4* __restrict__ s1t, const float4* __restrict__ s2t, int seg_slabs, int n_seg, int warm_slabs,
                                                      float2* __restrict__ states, float2* __restrict__ slab_states, const int* __restrict__ first_bad,
                                                      const int* __restrict__ wide_flags, const int* __restrict__ link_bad) {
   extern __shared__ __align__(128) unsigned char lanes_smem[];
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
     const int s_own = seg * seg_slabs;
     if (s_own >= total_slabs) return;
     const int s_end = s_own + seg_slabs < total_slabs ? s_own + seg_slabs : total_slabs;
-    const int s_first = seg == 0 ? s_own : (s_own - kWarmSlabs > 0 ? s_own - kWarmSlabs : 0);
+    const int s_first = seg == 0 ? s_own : (s_own - warm_slabs > 0 ? s_own - warm_slabs : 0);
     run(s_first, s_own - s_first, s_end, false);
     st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
   } else {
@@ -236,6 +238,16 @@ __global__ void __launch_bounds__(32) k_biquad_verify(int n_seg, const float2* _
   if (lane == 0) first_bad[blockIdx.x] = bad;
 }
 
+// warm-up of a speculative segment in 32-frame slabs (GAC_BIQUAD_WARM_SLABS overrides the default for measurements)
+static int warm_slabs() {
+  static const int v = [] {
+    const char* e = getenv("GAC_BIQUAD_WARM_SLABS");
+    const int x = e ? atoi(e) : kWarmSlabs;
+    return x >= 8 && x <= 65536 ? x : kWarmSlabs;
+  }();
+  return v;
+}
+
 int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs_out) {
   // one CTA = one warp with 96 KB of staging, two per SM: as many concurrent segments as there are slots per group, but
   // segments no shorter than the warm-up (below that the redundant work outweighs the concurrency)
@@ -244,7 +256,7 @@ int biquad_lane_segments(int n_jobs, int64_t n_frames, int* seg_slabs_out) {
   int n_seg = kLaneSlots / (groups > 0 ? groups : 1);
   if (n_seg < 1) n_seg = 1;
   int seg_slabs = (total_slabs + n_seg - 1) / n_seg;
-  if (seg_slabs < kWarmSlabs) seg_slabs = kWarmSlabs;
+  if (seg_slabs < warm_slabs()) seg_slabs = warm_slabs();
   n_seg = (total_slabs + seg_slabs - 1) / seg_slabs;
   if (n_seg < 1) n_seg = 1;
   if (seg_slabs_out) *seg_slabs_out = seg_slabs;
@@ -277,12 +289,12 @@ void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, 
   const int* d_wide = d_flags + groups;
   int* d_link = d_flags + 2 * groups;
   // both stream layouts are launched; a CTA whose group uses the other layout exits at once
-  k_biquad_lanes<false, false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, nullptr, d_wide, nullptr);
-  k_biquad_lanes<false, true><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, nullptr, d_wide, nullptr);
+  k_biquad_lanes<false, false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, nullptr, d_wide, nullptr);
+  k_biquad_lanes<false, true><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, nullptr, d_wide, nullptr);
   if (n_seg > 1) {
     k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad, d_link);
-    k_biquad_lanes<true, false><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, d_first_bad, d_wide, d_link);
-    k_biquad_lanes<true, true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, d_states, d_slab, d_first_bad, d_wide, d_link);
+    k_biquad_lanes<true, false><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, d_first_bad, d_wide, d_link);
+    k_biquad_lanes<true, true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, d_first_bad, d_wide, d_link);
   }
 }
 

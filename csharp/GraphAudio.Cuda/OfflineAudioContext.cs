@@ -1,7 +1,7 @@
 // OfflineAudioContext.cs (GraphAudio.Cuda) — the render entry point of the mirror API.  The node / param / buffer
-// mirror types (AudioBufferSourceNode, BiQuadFilterNode, GainNode, ConvolverNode, AudioParam, PlayableAudioBuffer) record
-// topology and automation exactly like graphaudio_b200/host/graphaudio_cuda.hpp (the C++ twin, which IS built and
-// tested in this repository); only the part that crosses the ABI is spelled out here.
+// mirror types live in Nodes.cs, the graph cutting in GraphFlattener.cs; they record topology and automation exactly like
+// graphaudio_b200/api.py and graphaudio_b200/host/graphaudio_cuda.hpp (the Python and C++ twins, which ARE built and tested in
+// this repository).
 // Source only: no dotnet toolchain in this image.
 using System;
 using System.Collections.Generic;
@@ -25,6 +25,15 @@ public sealed unsafe class OfflineAudioContext : IDisposable
     }
 
     internal IntPtr Handle => _ctx != IntPtr.Zero ? _ctx : throw new ObjectDisposedException(nameof(OfflineAudioContext));
+    private readonly List<AudioNode> _nodes = new();
+    internal void Register(AudioNode node) => _nodes.Add(node);
+    internal long FramesRendered => _framesRendered;
+    /// <summary>First quantum the next Render call processes (the reference renders whole 128-frame blocks, :55-100).</summary>
+    internal long QuantumNow => (_framesRendered + 127) / 128;
+    /// <summary>Start time of quantum q, accumulated like AudioContextBase.cs:78-79.</summary>
+    internal double BlockTime(long q) { double t = 0, inc = 128.0 / SampleRate; for (long i = 0; i < q; i++) t += inc; return t; }
+    /// <summary>Set by an edit that the re-rendering model cannot reproduce exactly (Nodes.cs); Render then refuses.</summary>
+    internal string? UnsupportedEdit;
 
     /// <summary>Render(float[][] output, int frameCount, int startIndex = 0) — OfflineAudioContext.cs:30.</summary>
     public void Render(float[][] output, int frameCount, int startIndex = 0)

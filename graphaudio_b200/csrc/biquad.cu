@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(512, 2) k_biquad_resolve(const BiquadJob* __re
   const int32_t* __restrict__ my_idx = have_job ? jobs[jid].idx : nullptr;
   float* __restrict__ sig0 = have_job ? jobs[jid].sig[0] : nullptr;
   float* __restrict__ sig1 = have_job ? jobs[jid].sig[1] : nullptr;
+  const float* __restrict__ in0 = have_job ? (jobs[jid].in[0] ? jobs[jid].in[0] : jobs[jid].sig[0]) : nullptr;
+  const float* __restrict__ in1 = have_job ? (jobs[jid].in[1] ? jobs[jid].in[1] : jobs[jid].sig[1]) : nullptr;
   int32_t pk0 = 0, pk1 = 0;
   float px0 = 0.f, px1 = 0.f;
   auto prefetch = [&](int64_t slab) {
@@ -268,8 +270,8 @@ __global__ void __launch_bounds__(512, 2) k_biquad_resolve(const BiquadJob* __re
     if (slab < n_slabs && have_job && n >= my_lo && n < my_hi) {
       pk0 = my_idx[n];
       pk1 = my_idx[n_frames + n];
-      px0 = sig0[n];
-      px1 = sig1[n];
+      px0 = in0[n];
+      px1 = in1[n];
     }
   };
   prefetch(slab0);

@@ -1625,6 +1625,11 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           s.ch = 2;
           const OpH& op = (*s.ops)[pos];
           BiquadJob j{};
+          if (s.lazy[0]) {  // a rate-1 source feeds this filter directly: its frames are read where they lie, no source copy was made
+            j.in[0] = s.lazy[0];
+            j.in[1] = s.lazy[1];
+            s.lazy[0] = s.lazy[1] = nullptr;  // the filter's output is written to the signal's own rows
+          }
           float *tf = nullptr, *tq = nullptr, *tg = nullptr;
           int rc;
           if ((rc = param_table(env, op.p0, true, pj, &tf))) return rc;

@@ -108,7 +108,10 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
       else if (ops.size() > 1 && ops[0].kind == GAC_OP_GAIN && ops[1].kind == GAC_OP_CONVOLVER) conv = &ops[1];
       const bool in_place = conv && conv->ir && conv->ir->d_H2 && nb > 0 && ((job.pos0 - job.out0) % 2 == 0) &&
                             (reinterpret_cast<uintptr_t>(src0) % 8 == 0) && (reinterpret_cast<uintptr_t>(src1) % 8 == 0);
-      if (in_place) {
+      // ... and so does a BiQuadFilterNode that follows directly: k_biquad_resolve reads scalars (no alignment demands) inside
+      // [lo, hi) only and clears the signal's rows outside it
+      const bool in_place_biquad = !ops.empty() && ops[0].kind == GAC_OP_BIQUAD && nb > 0;
+      if (in_place || in_place_biquad) {
         s.lazy[0] = src0 + (job.pos0 - job.out0);
         s.lazy[1] = src1 + (job.pos0 - job.out0);
       } else {

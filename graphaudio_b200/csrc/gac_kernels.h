@@ -189,7 +189,8 @@ struct PannerJob {      // StereoPannerNode, in place
 void launch_panner(const PannerJob* d_jobs, int n_jobs, int64_t n_frames, bool scan_changes, cudaStream_t s);
 
 struct BiquadJob {
-  float* sig[2];
+  float* sig[2];       // output rows (and the input, unless `in` says otherwise)
+  const float* in[2] = {nullptr, nullptr};  // input rows when they are not `sig`: in[c][n] for n in [lo, hi) — a rate-1 source read in place
   const float* freq;   // a-rate table or nullptr
   const float* q;      // a-rate table or nullptr
   const float* gain;   // k-rate table [n_quanta] or nullptr

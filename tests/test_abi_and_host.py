@@ -206,3 +206,22 @@ def test_parameter_epochs_are_recorded_per_render_call():
     p = g.Gain._desc(keep, 20)
     assert p.n_events == 3 and p.events[2].type == N.GAC_EVENT_EPOCH and p.events[2].time_constant == 20.0 and abs(p.events[2].value - 0.1) < 1e-7
     assert ctx._block_time(3) == (128.0 / 48000 + 128.0 / 48000) + 128.0 / 48000
+
+
+def test_product_package_never_imports_or_links_the_oracle():
+    """oracle/ is test infrastructure: nothing under graphaudio_b200/ (or bench.py's own arm) may import, dlopen or link it."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "graphaudio_b200")
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".inl", ".h", ".hpp")):
+                continue
+            for ln, line in enumerate(open(os.path.join(d, f), errors="replace"), 1):
+                code = line.split("//")[0].split("#")[0] if not f.endswith(".py") else line.split("#")[0]
+                if re.search(r"\b(import|from)\s+oracle\b|ga_oracle|libga_oracle|#include\s+\".*oracle", code):
+                    offenders.append(f"{f}:{ln}: {line.strip()}")
+    assert not offenders, offenders
+    needed = subprocess.run(["ldd", N.LIB_PATH], capture_output=True, text=True).stdout
+    assert "ga_oracle" not in needed

@@ -274,6 +274,8 @@ class AudioNode:
         return False
 
     def Connect(self, destination: "AudioNode", outputIndex=0, inputIndex=0):
+        if isinstance(destination, AudioParam):  # AudioNode.Connect(AudioParam) — Nodes/AudioNode.cs:86-92
+            raise NotSupportedException("node -> AudioParam modulation is outside the accelerated path (SURVEY.md §8f-3; the CPU oracle has it)")
         if outputIndex < 0 or outputIndex >= self._n_outputs:
             raise ArgumentOutOfRangeException("outputIndex")
         if inputIndex < 0 or inputIndex >= destination._n_inputs:

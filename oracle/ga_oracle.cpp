@@ -373,16 +373,26 @@ class Param {
     while (s < events_.size() && events_[s].time < t) s++;
     events_.resize(s);
   }
-  // ComputeValues :93-111 (modulation input = SURVEY "next"; not connected on this path)
-  void computeValues(double blockTime, int sampleRate) {
+  // ComputeValues :93-111.  `mod` is the param's own AudioNodeInput (Explicit, 1 channel, :68-70): nodes connected to the param are
+  // pulled and mixed down to mono, and the sum is added to the intrinsic value, clamped to the param's range (:125-131, :150-156).
+  void computeValues(int blockNumber, double blockTime, int sampleRate) {
+    const bool hasModulation = mod && !mod->from.empty();
+    if (hasModulation) mod->pull(blockNumber, blockTime);
+    const Block* mb = hasModulation ? mod->buffer.get() : nullptr;
+    const bool useMod = mb && !mb->silent;
     if (arate_) {  // ComputeARate :114-141
       double deltaTime = 1.0 / sampleRate;
-      for (int i = 0; i < kQuantum; i++) values[i] = valueAtTime(blockTime + i * deltaTime);
+      for (int i = 0; i < kQuantum; i++) {
+        float v = valueAtTime(blockTime + i * deltaTime);
+        values[i] = useMod ? clampf(v + mb->data[i], min_, max_) : v;
+      }
     } else {  // ComputeKRate :144-166
       float v = valueAtTime(blockTime);
+      if (useMod) v = clampf(v + mb->data[0], min_, max_);
       for (int i = 0; i < kQuantum; i++) values[i] = v;
     }
   }
+  std::unique_ptr<Input> mod;  // created by Node::addParam (needs the owner)
   // ComputeValueAtTime :169-217
   float valueAtTime(double time) const {
     size_t count = events_.size();
@@ -446,7 +456,12 @@ class Node {
   virtual ~Node() {}
   Param* addParam(float def, float mn, float mx, bool arate) {
     params.emplace_back(new Param(this, def, mn, mx, arate));
-    return params.back().get();
+    Param* p = params.back().get();
+    p->mod.reset(new Input());  // AudioParam.cs:68-70: SetChannelCount(1), Explicit
+    p->mod->owner = this;
+    p->mod->channelCount = 1;
+    p->mod->mode = ModeExplicit;
+    return p;
   }
   // ProcessInternal :152-183
   bool processInternal(int blockNumber, double blockTime);
@@ -553,7 +568,7 @@ bool Node::processInternal(int blockNumber, double blockTime) {
   if (processing) { ctx->cycle = true; return false; }  // InvalidOperationException :157-160
   processing = true;
   lastBlock = blockNumber;
-  for (auto& p : params) p->computeValues(blockTime, ctx->sampleRate);
+  for (auto& p : params) p->computeValues(blockNumber, blockTime, ctx->sampleRate);
   for (auto& in : inputs) in->pull(blockNumber, blockTime);
   process();
   processing = false;
@@ -579,6 +594,8 @@ void Node::disposeNow() {
   disposed = true;
   for (auto& o : outputs) { auto ins = o->to; for (auto* in : ins) disconnect(o.get(), in); }
   for (auto& in : inputs) { auto outs = in->from; for (auto* o : outs) disconnect(o, in.get()); in->buffer.reset(); }
+  for (auto& p : params)  // AudioParam.Dispose: its modulation input is disconnected too
+    if (p->mod) { auto outs = p->mod->from; for (auto* o : outs) disconnect(o, p->mod.get()); p->mod->buffer.reset(); }
 }
 
 // Nodes/GainNode.cs:29-61
@@ -971,6 +988,106 @@ class BufferSource : public Node {
   BlockPtr ob;
 };
 
+// Start / Stop bookkeeping shared by OscillatorNode and ConstantSourceNode (IAudioScheduledSourceNode): sample-accurate start and
+// stop inside a block (Nodes/OscillatorNode.cs:97-118, Nodes/ConstantSourceNode.cs:82-110)
+class ScheduledSource : public Node {
+ public:
+  explicit ScheduledSource(Context* c) : Node(c, 0, 1) {}
+  int start(double when, double duration) {
+    if (started) return -1;
+    started = true;
+    startTime = std::max(0.0, when);
+    if (!std::isnan(duration) && duration >= 0) { stopTime = startTime + duration; stopped = true; }
+    return 0;
+  }
+  void stop(double when) {
+    if (stopped) return;
+    double at = std::max(0.0, when);
+    stopTime = std::isnan(stopTime) ? at : std::min(stopTime, at);
+    stopped = true;
+  }
+  // returns false when the block is silent; else [startFrame, endFrame) is the playing part of the block
+  bool window(int* startFrame, int* endFrame) const {
+    double t0 = ctx->currentTime;
+    double t1 = t0 + (double)kQuantum / ctx->sampleRate;
+    *startFrame = 0;
+    *endFrame = kQuantum;
+    if (!started || !(t1 > startTime && (std::isnan(stopTime) || t0 < stopTime))) return false;
+    auto clampi = [](double v) { return (int)(v < 0 ? 0 : (v > kQuantum ? kQuantum : v)); };
+    if (t0 < startTime && startTime < t1) *startFrame = clampi(std::ceil((startTime - t0) * ctx->sampleRate));
+    if (!std::isnan(stopTime) && t0 < stopTime && stopTime < t1) *endFrame = clampi(std::floor((stopTime - t0) * ctx->sampleRate));
+    return true;
+  }
+  void endCheck() {  // TryRaiseEndedAndDispose: Dispose() is posted mid-render and runs at the next block
+    double t1 = ctx->currentTime + (double)kQuantum / ctx->sampleRate;
+    if (started && stopped && !ended && !std::isnan(stopTime) && t1 >= stopTime) {
+      ended = true;
+      ctx->commands.push_back([this]() { disposeNow(); });
+    }
+  }
+  bool started = false, stopped = false, ended = false;
+  double startTime = std::numeric_limits<double>::quiet_NaN(), stopTime = std::numeric_limits<double>::quiet_NaN();
+  BlockPtr ob;
+};
+
+// Nodes/OscillatorNode.cs
+class Oscillator : public ScheduledSource {
+ public:
+  explicit Oscillator(Context* c) : ScheduledSource(c) { frequency = addParam(440.f, 0.f, c->sampleRate / 2.f, true); }  // :42-47
+  static float sample(double phase, int type) {  // GenerateSample :164-188
+    const double kPi = 3.14159265358979323846;
+    switch (type) {
+      case 0: return (float)std::sin(phase);
+      case 1: return phase < kPi ? 1.0f : -1.0f;
+      case 2: return (float)(2.0 * (phase / (2.0 * kPi)) - 1.0);
+      case 3: { double t = phase / (2.0 * kPi); return (float)(4.0 * std::fabs(t - std::floor(t + 0.5)) - 1.0); }
+      default: return 0.f;
+    }
+  }
+  void process() override {  // :91-150
+    if (!ob) ob = rent(1);
+    int sf, ef;
+    if (!window(&sf, &ef)) { ob->clear(); outputs[0]->buffer = ob; endCheck(); return; }
+    const double kPi = 3.14159265358979323846;
+    float* o = ob->ch(0);
+    for (int i = 0; i < sf; i++) o[i] = 0.f;
+    for (int i = sf; i < ef; i++) {
+      o[i] = sample(phase, type);
+      double inc = (2.0 * kPi * frequency->values[i]) / ctx->sampleRate;  // :133
+      phase += inc;
+      if (phase >= 2.0 * kPi) phase -= 2.0 * kPi;
+    }
+    for (int i = ef; i < kQuantum; i++) o[i] = 0.f;
+    ob->markNonSilent();
+    outputs[0]->buffer = ob;
+    endCheck();
+  }
+  Param* frequency;
+  int type = 0;  // OscillatorType: Sine, Square, Sawtooth, Triangle (:207-213)
+  double phase = 0.0;
+};
+
+// Nodes/ConstantSourceNode.cs
+class ConstantSource : public ScheduledSource {
+ public:
+  explicit ConstantSource(Context* c) : ScheduledSource(c) {
+    offset = addParam(1.f, -std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), true);  // :22-28
+  }
+  void process() override {  // :68-137
+    if (!ob) ob = rent(1);
+    int sf, ef;
+    if (!window(&sf, &ef)) { ob->clear(); outputs[0]->buffer = ob; endCheck(); return; }
+    float* o = ob->ch(0);
+    for (int i = 0; i < sf; i++) o[i] = 0.f;
+    for (int i = sf; i < ef; i++) o[i] = offset->values[i];
+    for (int i = ef; i < kQuantum; i++) o[i] = 0.f;
+    ob->markNonSilent();
+    outputs[0]->buffer = ob;
+    endCheck();
+  }
+  Param* offset;
+};
+
 Delay::Delay(Context* c, double maxDelayTime) : Node(c, 1, 1) {  // :22-41
   maxDelaySamples = (int)(maxDelayTime * c->sampleRate);
   for (int i = 0; i < 2; i++) rings.emplace_back(maxDelaySamples);
@@ -1140,6 +1257,8 @@ int ora_node_create(void* c, int kind) {
     case 2: n = new Gain(ctx); break;
     case 3: n = new Convolver(ctx); break;
     case 4: n = new StereoPanner(ctx); break;
+    case 5: n = new Oscillator(ctx); break;
+    case 6: n = new ConstantSource(ctx); break;
     default: return -1;
   }
   ctx->nodes.emplace_back(n);
@@ -1163,6 +1282,31 @@ int ora_connect(void* c, int src, int dst) {  // AudioNode.Connect :68-73 (appli
   Node *a = nodeAt(c, src), *b = nodeAt(c, dst);
   if (!a || !b || a->outputs.empty() || b->inputs.empty() || a == b) return -1;
   connect(a->outputs[0].get(), b->inputs[0].get());
+  return 0;
+}
+
+static Param* paramAt(void* c, int node, int pidx);
+int ora_connect_param(void* c, int src, int dstNode, int pidx) {  // AudioNode.Connect(AudioParam) :86-92
+  Node* a = nodeAt(c, src);
+  Param* p = paramAt(c, dstNode, pidx);
+  if (!a || !p || a->outputs.empty()) return -1;
+  connect(a->outputs[0].get(), p->mod.get());
+  return 0;
+}
+int ora_scheduled_start(void* c, int node, double when, double duration) {
+  auto* s = dynamic_cast<ScheduledSource*>(nodeAt(c, node));
+  return s ? s->start(when, duration) : -1;
+}
+int ora_scheduled_stop(void* c, int node, double when) {
+  auto* s = dynamic_cast<ScheduledSource*>(nodeAt(c, node));
+  if (!s) return -1;
+  s->stop(when);
+  return 0;
+}
+int ora_oscillator_set_type(void* c, int node, int type) {
+  auto* o = dynamic_cast<Oscillator*>(nodeAt(c, node));
+  if (!o || type < 0 || type > 3) return -1;
+  o->type = type;
   return 0;
 }
 
@@ -1202,7 +1346,7 @@ int ora_param_eval(void* c, int node, int pidx, int64_t nBlocks, float* out) {
   if (!p) return -1;
   double t = 0.0;
   for (int64_t b = 0; b < nBlocks; b++) {
-    p->computeValues(t, ctx->sampleRate);
+    p->computeValues((int)b + 1, t, ctx->sampleRate);
     std::memcpy(out + b * kQuantum, p->values, sizeof(float) * kQuantum);
     t = t + (double)kQuantum / ctx->sampleRate;
   }

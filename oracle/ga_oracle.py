@@ -58,6 +58,10 @@ def lib():
     L.ora_buffer_create.argtypes = [C.c_void_p, fpp, C.c_int, C.c_int64, C.c_int]
     L.ora_node_create.argtypes = [C.c_void_p, C.c_int]
     L.ora_delay_create.argtypes = [C.c_void_p, C.c_double]
+    L.ora_connect_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.ora_scheduled_start.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    L.ora_scheduled_stop.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.ora_oscillator_set_type.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_connect.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_param_set_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
     L.ora_param_event.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
@@ -256,6 +260,10 @@ class AudioNode:
         self._id = lib().ora_node_create(context._h, self._KIND) if self._KIND >= 0 else 0
 
     def Connect(self, destination):
+        if isinstance(destination, AudioParam):  # AudioNode.Connect(AudioParam param) — Nodes/AudioNode.cs:86-92
+            if lib().ora_connect_param(self._ctx._h, self._id, destination._node._id, destination._idx) != 0:
+                raise ArgumentOutOfRangeException("cannot connect to the parameter")
+            return None
         if lib().ora_connect(self._ctx._h, self._id, destination._id) != 0:
             raise ArgumentOutOfRangeException("cannot connect")
         return destination
@@ -383,6 +391,48 @@ class StereoPannerNode(AudioNode):
     def __init__(self, context):
         super().__init__(context)
         self.Pan = AudioParam(self, 0, 0.0, -1.0, 1.0)
+
+
+class OscillatorType:  # Nodes/OscillatorNode.cs:207-213
+    Sine, Square, Sawtooth, Triangle = range(4)
+
+
+class _ScheduledSource(AudioNode):
+    def Start(self, when=0.0, offset=0.0, duration=math.nan):
+        if lib().ora_scheduled_start(self._ctx._h, self._id, float(when), float(duration)) != 0:
+            raise InvalidOperationException("The node can only be started once.")
+
+    def Stop(self, when=0.0):
+        lib().ora_scheduled_stop(self._ctx._h, self._id, float(when))
+
+
+class OscillatorNode(_ScheduledSource):
+    """Nodes/OscillatorNode.cs (oracle only so far: the device path is SURVEY.md §8f-3 "next")"""
+    _KIND = 5
+
+    def __init__(self, context):
+        super().__init__(context)
+        self.Frequency = AudioParam(self, 0, 440.0, 0.0, context.SampleRate / 2.0)
+        self._type = OscillatorType.Sine
+
+    @property
+    def Type(self):
+        return self._type
+
+    @Type.setter
+    def Type(self, t):
+        if lib().ora_oscillator_set_type(self._ctx._h, self._id, int(t)) != 0:
+            raise ArgumentOutOfRangeException("Type")
+        self._type = t
+
+
+class ConstantSourceNode(_ScheduledSource):
+    """Nodes/ConstantSourceNode.cs (oracle only so far)"""
+    _KIND = 6
+
+    def __init__(self, context):
+        super().__init__(context)
+        self.Offset = AudioParam(self, 0, 1.0, -3.4028234663852886e38, 3.4028234663852886e38)
 
 
 class DelayNode(AudioNode):

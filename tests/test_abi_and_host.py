@@ -225,3 +225,10 @@ def test_product_package_never_imports_or_links_the_oracle():
     assert not offenders, offenders
     needed = subprocess.run(["ldd", N.LIB_PATH], capture_output=True, text=True).stdout
     assert "ga_oracle" not in needed
+
+
+def test_param_modulation_is_refused_by_the_device_mirror():
+    ctx = G.OfflineAudioContext(48000, _record_only=True)
+    a, b = G.GainNode(ctx), G.GainNode(ctx)
+    with pytest.raises(G.NotSupportedException):
+        a.Connect(b.Gain)

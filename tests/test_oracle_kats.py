@@ -448,3 +448,81 @@ def test_looping_source_copy_path_closed_form():
     assert np.array_equal(whole, x[np.arange(128 * 20) % 1000])  # LoopEnd 0 = end of the buffer; never ends by itself
     stopped = run(0, 0, 0, stop=0.01)  # block-granular stop: quanta with t0 < 0.01 s play (:137-143)
     assert np.nonzero(stopped)[0][-1] == 511
+
+
+# ---------------------------------------------------------------- OscillatorNode / ConstantSourceNode / AudioParam modulation
+# (oracle-side groundwork for SURVEY.md §8f-3: the device path does not accelerate these yet and rejects them)
+def test_constant_source_and_sample_accurate_start_stop():
+    fs = 48000
+    ctx = O.OfflineAudioContext(fs)
+    c = O.ConstantSourceNode(ctx)
+    c.Offset.SetValueAtTime(0.25, 0.0)
+    c.Offset.LinearRampToValueAtTime(0.75, 0.01)
+    c.Connect(ctx.Destination)
+    c.Start(100.5 / fs)   # inside block 0: first playing frame = ceil((start - t0) * fs) = 101 (ConstantSourceNode.cs:88-93)
+    c.Stop(300.5 / fs)    # inside block 2: last playing frame = floor((stop - t0) * fs) - 1 (:95-101)
+    y = ctx.Render(128 * 4)
+    probe = O.OfflineAudioContext(fs)
+    g = O.GainNode(probe)
+    g.Gain.SetValueAtTime(0.25, 0.0)
+    g.Gain.LinearRampToValueAtTime(0.75, 0.01)
+    want = g.Gain.evaluate(4)
+    # 300.5 / fs lies in block 2 (frames 256..383): endFrame = floor((stop - t0) * fs) = floor(44.5) = 44 -> frames 256..299 play
+    want[:101] = 0
+    want[300:] = 0
+    assert np.array_equal(y[0], want) and np.array_equal(y[1], want)  # mono output up-mixed by copy at the destination
+
+
+def test_oscillator_phase_accumulation_and_waveforms():
+    fs = 48000
+    n = 128 * 6
+
+    def run(kind, freq):
+        ctx = O.OfflineAudioContext(fs)
+        o = O.OscillatorNode(ctx)
+        o.Type = kind
+        o.Frequency.Value = freq
+        o.Connect(ctx.Destination)
+        o.Start()
+        return ctx.Render(n)[0]
+
+    def phases(freq):  # OscillatorNode.cs:131-138: double accumulation with a single 2*pi wrap per step
+        ph, out = 0.0, np.empty(n)
+        inc = (2.0 * math.pi * float(np.float32(freq))) / fs
+        for i in range(n):
+            out[i] = ph
+            ph += inc
+            if ph >= 2.0 * math.pi:
+                ph -= 2.0 * math.pi
+        return out
+    ph = phases(997.0)
+    assert np.array_equal(run(O.OscillatorType.Sine, 997.0), np.sin(ph).astype(np.float32))
+    assert np.array_equal(run(O.OscillatorType.Square, 997.0), np.where(ph < math.pi, 1.0, -1.0).astype(np.float32))
+    assert np.array_equal(run(O.OscillatorType.Sawtooth, 997.0), (2.0 * (ph / (2.0 * math.pi)) - 1.0).astype(np.float32))
+    t = ph / (2.0 * math.pi)
+    assert np.array_equal(run(O.OscillatorType.Triangle, 997.0), (4.0 * np.abs(t - np.floor(t + 0.5)) - 1.0).astype(np.float32))
+
+
+def test_audio_param_modulation_adds_the_mono_mix_and_clamps():
+    # AudioParam.cs:93-166: nodes connected to a param are mixed down to ONE channel (Explicit, channelCount 1) and added to the
+    # intrinsic value, clamped to [min, max]; a silent modulation input leaves the intrinsic value alone
+    fs = 48000
+    x = [synth.splitmix_uniform(720 + c, 128 * 8) for c in range(2)]
+    ctx = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(ctx)
+    s.Buffer = O.PlayableAudioBuffer.FromChannelArrays(x, fs)
+    d = O.DelayNode(ctx, 0.01)                  # DelayTime in [0, 0.01]: the clamp is easy to hit
+    d.DelayTime.Value = 0.004
+    lfo = O.ConstantSourceNode(ctx)
+    lfo.Offset.SetValueAtTime(-0.006, 0.0)      # 0.004 - 0.006 < 0 -> clamped to 0 (reads nothing)
+    lfo.Offset.SetValueAtTime(0.002, 256.0 / fs)  # 0.006 s = 288 frames
+    lfo.Offset.SetValueAtTime(0.02, 512.0 / fs)   # clamped to the maximum, 480 frames
+    lfo.Connect(d.DelayTime)
+    lfo.Start(128.0 / fs)                       # block 0: the modulator is silent -> intrinsic 0.004 s = 192 frames
+    s.Connect(d).Connect(ctx.Destination)
+    s.Start()
+    y = ctx.Render(128 * 7)[0]
+    n = np.arange(128 * 7)
+    dly = np.select([n < 128, n < 256, n < 512], [192, 0, 288], 480)
+    src = np.where((dly >= 1) & (n - dly >= 0), x[0][np.maximum(n - dly, 0)], 0.0).astype(np.float32)
+    assert np.array_equal(y, src)

@@ -988,6 +988,49 @@ class BufferSource : public Node {
   BlockPtr ob;
 };
 
+// Nodes/ChannelSplitterNode.cs: output i = channel i of the input as a 1-channel block (cleared when the input has fewer channels or is silent)
+class ChannelSplitter : public Node {
+ public:
+  ChannelSplitter(Context* c, int n) : Node(c, 1, n), obs((size_t)n) {}
+  void process() override {  // :21-55
+    Block* in = inputs[0]->buffer.get();
+    const bool silent = !in || in->silent;
+    for (size_t i = 0; i < obs.size(); i++) {
+      if (!obs[i]) obs[i] = rent(1);
+      if (!silent && (int)i < in->channels) {
+        std::memcpy(obs[i]->ch(0), in->ch((int)i), sizeof(float) * kQuantum);  // CopyChannelFrom clears the silent flag (AudioBuffer.cs:110-121)
+        obs[i]->markNonSilent();
+      } else {
+        obs[i]->clear();
+      }
+      outputs[i]->buffer = obs[i];
+    }
+  }
+  std::vector<BlockPtr> obs;
+};
+
+// Nodes/ChannelMergerNode.cs: output channel i = channel 0 of input i (silent inputs leave zeros)
+class ChannelMerger : public Node {
+ public:
+  ChannelMerger(Context* c, int n) : Node(c, n, 1), n_(n) {}
+  void process() override {  // :21-52
+    if (!ob || ob->channels != n_) ob = rent(n_);
+    ob->clear();
+    bool hasAudio = false;
+    for (int i = 0; i < n_; i++) {
+      Block* in = inputs[i]->buffer.get();
+      if (in && !in->silent && in->channels > 0) {
+        std::memcpy(ob->ch(i), in->ch(0), sizeof(float) * kQuantum);
+        hasAudio = true;
+      }
+    }
+    if (hasAudio) ob->markNonSilent();
+    outputs[0]->buffer = ob;
+  }
+  int n_;
+  BlockPtr ob;
+};
+
 // Start / Stop bookkeeping shared by OscillatorNode and ConstantSourceNode (IAudioScheduledSourceNode): sample-accurate start and
 // stop inside a block (Nodes/OscillatorNode.cs:97-118, Nodes/ConstantSourceNode.cs:82-110)
 class ScheduledSource : public Node {
@@ -1285,6 +1328,24 @@ int ora_connect(void* c, int src, int dst) {  // AudioNode.Connect :68-73 (appli
   return 0;
 }
 
+int ora_splitter_create(void* c, int n) {  // ChannelSplitterNode(context, numberOfOutputs) :12-20
+  auto* ctx = (Context*)c;
+  if (n < 1 || n > 32) return -1;
+  ctx->nodes.emplace_back(new ChannelSplitter(ctx, n));
+  return (int)ctx->nodes.size() - 1;
+}
+int ora_merger_create(void* c, int n) {  // ChannelMergerNode(context, numberOfInputs) :12-19
+  auto* ctx = (Context*)c;
+  if (n < 1 || n > 32) return -1;
+  ctx->nodes.emplace_back(new ChannelMerger(ctx, n));
+  return (int)ctx->nodes.size() - 1;
+}
+int ora_connect_io(void* c, int src, int outIdx, int dst, int inIdx) {  // AudioNode.Connect(destination, outputIndex, inputIndex) :68-84
+  Node *a = nodeAt(c, src), *b = nodeAt(c, dst);
+  if (!a || !b || a == b || outIdx < 0 || outIdx >= (int)a->outputs.size() || inIdx < 0 || inIdx >= (int)b->inputs.size()) return -1;
+  connect(a->outputs[outIdx].get(), b->inputs[inIdx].get());
+  return 0;
+}
 static Param* paramAt(void* c, int node, int pidx);
 int ora_connect_param(void* c, int src, int dstNode, int pidx) {  // AudioNode.Connect(AudioParam) :86-92
   Node* a = nodeAt(c, src);

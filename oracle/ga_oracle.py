@@ -59,6 +59,9 @@ def lib():
     L.ora_node_create.argtypes = [C.c_void_p, C.c_int]
     L.ora_delay_create.argtypes = [C.c_void_p, C.c_double]
     L.ora_connect_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.ora_connect_io.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ora_splitter_create.argtypes = [C.c_void_p, C.c_int]
+    L.ora_merger_create.argtypes = [C.c_void_p, C.c_int]
     L.ora_scheduled_start.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
     L.ora_scheduled_stop.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.ora_oscillator_set_type.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -259,7 +262,11 @@ class AudioNode:
         self.Context = context
         self._id = lib().ora_node_create(context._h, self._KIND) if self._KIND >= 0 else 0
 
-    def Connect(self, destination):
+    def Connect(self, destination, outputIndex=0, inputIndex=0):
+        if outputIndex or inputIndex:  # Connect(destination, outputIndex, inputIndex) — Nodes/AudioNode.cs:68-84
+            if lib().ora_connect_io(self._ctx._h, self._id, int(outputIndex), destination._id, int(inputIndex)) != 0:
+                raise ArgumentOutOfRangeException("cannot connect")
+            return destination
         if isinstance(destination, AudioParam):  # AudioNode.Connect(AudioParam param) — Nodes/AudioNode.cs:86-92
             if lib().ora_connect_param(self._ctx._h, self._id, destination._node._id, destination._idx) != 0:
                 raise ArgumentOutOfRangeException("cannot connect to the parameter")
@@ -433,6 +440,28 @@ class ConstantSourceNode(_ScheduledSource):
     def __init__(self, context):
         super().__init__(context)
         self.Offset = AudioParam(self, 0, 1.0, -3.4028234663852886e38, 3.4028234663852886e38)
+
+
+class ChannelSplitterNode(AudioNode):
+    """Nodes/ChannelSplitterNode.cs (oracle only so far)"""
+
+    def __init__(self, context, numberOfOutputs=2):
+        if numberOfOutputs < 1 or numberOfOutputs > 32:
+            raise ArgumentOutOfRangeException("numberOfOutputs")
+        self._ctx = context
+        self.Context = context
+        self._id = lib().ora_splitter_create(context._h, int(numberOfOutputs))
+
+
+class ChannelMergerNode(AudioNode):
+    """Nodes/ChannelMergerNode.cs (oracle only so far)"""
+
+    def __init__(self, context, numberOfInputs=2):
+        if numberOfInputs < 1 or numberOfInputs > 32:
+            raise ArgumentOutOfRangeException("numberOfInputs")
+        self._ctx = context
+        self.Context = context
+        self._id = lib().ora_merger_create(context._h, int(numberOfInputs))
 
 
 class DelayNode(AudioNode):

@@ -526,3 +526,38 @@ def test_audio_param_modulation_adds_the_mono_mix_and_clamps():
     dly = np.select([n < 128, n < 256, n < 512], [192, 0, 288], 480)
     src = np.where((dly >= 1) & (n - dly >= 0), x[0][np.maximum(n - dly, 0)], 0.0).astype(np.float32)
     assert np.array_equal(y, src)
+
+
+def test_channel_splitter_and_merger_route_single_channels():
+    # ChannelSplitterNode.cs:21-55 (output i = input channel i as a mono block), ChannelMergerNode.cs:21-52 (output channel i = channel 0 of
+    # input i): swap the channels of a stereo source and scale one of them on the way
+    fs = 48000
+    x = [synth.splitmix_uniform(730 + c, 128 * 6) for c in range(2)]
+    ctx = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(ctx)
+    s.Buffer = O.PlayableAudioBuffer.FromChannelArrays(x, fs)
+    split = O.ChannelSplitterNode(ctx, 2)
+    merge = O.ChannelMergerNode(ctx, 2)
+    g = O.GainNode(ctx)
+    g.Gain.Value = 0.5
+    s.Connect(split)
+    split.Connect(g, 0, 0)       # left -> gain -> merger input 1
+    g.Connect(merge, 0, 1)
+    split.Connect(merge, 1, 0)   # right -> merger input 0
+    merge.Connect(ctx.Destination)
+    s.Start()
+    y = ctx.Render(128 * 5)
+    assert np.array_equal(y[0], x[1][:640]) and np.array_equal(y[1], x[0][:640] * np.float32(0.5))
+    # a third splitter output of a stereo input is silence; a merger with one silent input keeps zeros there
+    ctx = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(ctx)
+    s.Buffer = O.PlayableAudioBuffer.FromChannelArrays(x, fs)
+    split = O.ChannelSplitterNode(ctx, 3)
+    merge = O.ChannelMergerNode(ctx, 2)
+    s.Connect(split)
+    split.Connect(merge, 2, 0)
+    split.Connect(merge, 0, 1)
+    merge.Connect(ctx.Destination)
+    s.Start()
+    y = ctx.Render(128 * 5)
+    assert not y[0].any() and np.array_equal(y[1], x[0][:640])

@@ -428,6 +428,7 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   if (dev >= 64) return fail(GAC_ERR_OUT_OF_RANGE, "device_id %d not supported", dev);
   DevInfo& di = dev_info[dev];
   CU(cudaSetDevice(dev));
+  std::unique_lock<std::mutex> dev_lock(g_tables_mu);  // contexts may be created from several threads at once
   if (!di.known) {
     CU(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, dev));
     CU(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, dev));
@@ -440,6 +441,7 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) di.budget = std::max<size_t>((size_t)1 << 30, free_b / 3);
     di.known = true;
   }
+  dev_lock.unlock();
   if (di.major != 10) return fail(GAC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, di.major, di.minor);
   auto ctx = std::make_unique<gac_context>();
   ctx->device = dev;

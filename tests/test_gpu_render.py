@@ -418,3 +418,41 @@ def test_rewiring_after_a_render_is_refused_not_approximated():
     g.Connect(extra).Connect(ctx.Destination)  # a node that already rendered gets a second consumer
     with pytest.raises(G.NotSupportedException):
         ctx.Render(512)
+
+
+def test_distinct_contexts_render_concurrently_from_distinct_threads():
+    """A gac_context is not thread-safe, but distinct contexts may be used from distinct threads (AudioContextBase.cs:266-305 is the
+    same model): context creation, the process-wide table caches, staging blocks and the stream-ordered pool are shared state."""
+    import threading
+    import graphaudio_b200 as G
+    fs = 48000
+    n = 40000
+
+    def build(seed, async_upload):
+        voices = []
+        for v in range(3):
+            src, ir = synth.make_voice_inputs(seed * 10 + v, 30000, 9000)
+            voices.append((src, ir, synth.voice_gains(seed + v)))
+        return synth.build_c2(G, fs, voices, 0.25, t_scale=0.05, async_upload=async_upload)
+    want = [build(s, False).Render(n) for s in range(4)]
+    got = [None] * 4
+    errors = []
+    gate = threading.Barrier(4)
+
+    def worker(s):
+        try:
+            gate.wait()
+            for _ in range(3):  # fresh context every time: creation and destruction race with the other threads' renders
+                ctx = build(s, async_upload=(s % 2 == 1))
+                got[s] = ctx.Render(n)
+                ctx.Dispose()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for s in range(4):
+        assert np.array_equal(got[s], want[s])

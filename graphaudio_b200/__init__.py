@@ -14,6 +14,9 @@ from .api import (  # noqa: F401
     BiQuadFilterNode,
     ConvolverNode,
     CudaConvolverNode,
+    ChannelMergerNode,
+    ChannelSplitterNode,
+    ConstantSourceNode,
     CudaException,
     DelayNode,
     FilterType,
@@ -22,6 +25,8 @@ from .api import (  # noqa: F401
     NotSupportedException,
     ObjectDisposedException,
     OfflineAudioContext,
+    OscillatorNode,
+    OscillatorType,
     PlayableAudioBuffer,
     RenderBatch,
     StereoPannerNode,

@@ -413,6 +413,51 @@ class StereoPannerNode(AudioNode):
         self.Pan = AudioParam(0.0, -1.0, 1.0)  # :28-33
 
 
+class OscillatorType:  # Nodes/OscillatorNode.cs:207-213
+    Sine, Square, Sawtooth, Triangle = range(4)
+
+
+class _RecordedOnlySource(AudioNode):
+    """Nodes of GraphAudio.Core that can be built and connected but are not accelerated yet: a graph that reaches the destination
+    through one of them is refused at Render (NotSupportedException), never rendered with the node left out."""
+
+    def __init__(self, context):
+        super().__init__(context, 0, 1)
+
+    def Start(self, when=0.0, offset=0.0, duration=math.nan):
+        pass
+
+    def Stop(self, when=0.0):
+        pass
+
+
+class OscillatorNode(_RecordedOnlySource):  # Nodes/OscillatorNode.cs
+    def __init__(self, context):
+        super().__init__(context)
+        self.Type = OscillatorType.Sine
+        self.Frequency = AudioParam(440.0, 0.0, context.SampleRate / 2.0)
+
+
+class ConstantSourceNode(_RecordedOnlySource):  # Nodes/ConstantSourceNode.cs
+    def __init__(self, context):
+        super().__init__(context)
+        self.Offset = AudioParam(1.0, -3.4028234663852886e38, 3.4028234663852886e38)
+
+
+class ChannelSplitterNode(AudioNode):  # Nodes/ChannelSplitterNode.cs
+    def __init__(self, context, numberOfOutputs=2):
+        if numberOfOutputs < 1 or numberOfOutputs > 32:
+            raise ArgumentOutOfRangeException("numberOfOutputs")
+        super().__init__(context, 1, numberOfOutputs)
+
+
+class ChannelMergerNode(AudioNode):  # Nodes/ChannelMergerNode.cs
+    def __init__(self, context, numberOfInputs=2):
+        if numberOfInputs < 1 or numberOfInputs > 32:
+            raise ArgumentOutOfRangeException("numberOfInputs")
+        super().__init__(context, numberOfInputs, 1)
+
+
 class ConvolverNode(AudioNode):
     def __init__(self, context):
         super().__init__(context)
@@ -607,6 +652,10 @@ class OfflineAudioContext:
                 continue
             live.add(id(n))
             stack.extend(n._in)
+            # a node type the device path does not accelerate must never render as silence: refuse the whole graph
+            if not isinstance(n, (AudioDestinationNode, AudioBufferSourceNode, BiQuadFilterNode, GainNode, ConvolverNode, DelayNode,
+                                  StereoPannerNode)):
+                raise NotSupportedException(f"{type(n).__name__} is outside the accelerated path (SURVEY.md §8f-3; the CPU oracle has it)")
 
         def outs(n):
             return [d for d in n._out if id(d) in live]

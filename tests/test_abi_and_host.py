@@ -232,3 +232,22 @@ def test_param_modulation_is_refused_by_the_device_mirror():
     a, b = G.GainNode(ctx), G.GainNode(ctx)
     with pytest.raises(G.NotSupportedException):
         a.Connect(b.Gain)
+
+
+def test_unaccelerated_node_types_are_refused_never_rendered_as_silence():
+    for make in (lambda c: G.OscillatorNode(c), lambda c: G.ConstantSourceNode(c), lambda c: G.ChannelSplitterNode(c, 2),
+                 lambda c: G.ChannelMergerNode(c, 2)):
+        ctx = G.OfflineAudioContext(48000, _record_only=True)
+        n = make(ctx)
+        g = G.GainNode(ctx)
+        n.Connect(g).Connect(ctx.Destination)
+        with pytest.raises(G.NotSupportedException):
+            ctx._topology()
+    # ... while such a node that does NOT reach the destination leaves the graph renderable
+    ctx = G.OfflineAudioContext(48000, _record_only=True)
+    s = G.AudioBufferSourceNode(ctx)
+    s.Buffer = G.PlayableAudioBuffer.FromChannelArrays([np.zeros(256, np.float32)], 48000)
+    s.Connect(ctx.Destination)
+    s.Start()
+    G.OscillatorNode(ctx)
+    assert len(ctx._topology()[0]) == 1

@@ -126,6 +126,11 @@ internal static unsafe partial class Native
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
     internal static partial int IrDestroy(IntPtr ir);
 
+    /// <summary>Host-only: how K6 covers a render (transform length, double-length segments in front, segments behind them).</summary>
+    [LibraryImport(Lib, EntryPoint = "gac_plan_segments")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int PlanSegments(long blocks, int partitions, int uniform, out int m, out int big, out int small);
+
     // ---- the per-quantum plugin seam (CudaConvolverNode.cs)
     [LibraryImport(Lib, EntryPoint = "gac_convolver_create")]
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]

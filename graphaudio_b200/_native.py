@@ -113,6 +113,7 @@ SIGNATURES = {
     "gac_automation_eval": (C.c_int, [C.c_void_p, C.POINTER(gac_param), C.c_int, C.c_int64, fp]),
     "gac_resample_cubic": (C.c_int, [C.c_void_p, fp, C.c_int64, C.c_double, C.c_int64, fp, C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int64)]),
+    "gac_plan_segments": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gac_convolver_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "gac_convolver_destroy": (C.c_int, [C.c_void_p]),
     "gac_convolver_channels": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -1183,6 +1183,19 @@ static void plan_segments(int64_t QB, int M, int Lh, int* n_big, int* n_small) {
   }
 }
 
+extern "C" int gac_plan_segments(int64_t n_blocks, int n_partitions, int uniform, int* m, int* n_big, int* n_small) {
+  if (!m || !n_big || !n_small) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_blocks <= 0 || n_partitions <= 0) return fail(GAC_ERR_OUT_OF_RANGE, "block and partition counts must be positive");
+  int Lh = 0;
+  const int M = n_partitions >= kFft2MinP ? fft2_pick_m(n_partitions, &Lh) : 0;
+  *m = M;
+  *n_big = *n_small = 0;
+  if (M == 0) return GAC_OK;
+  if (uniform) *n_small = (int)((n_blocks + (M - Lh) - 1) / (M - Lh));
+  else plan_segments(n_blocks, M, Lh, n_big, n_small);
+  return GAC_OK;
+}
+
 // Second-level spectra of length 2 * M2 for the impulse responses a voice batch wants to run with mixed segment lengths: allocated
 // on first use, prepared by ONE launch per transform length for the whole batch (the first-level spectra exist: prepare_irs ran).
 static int ensure_h2b_batch(RenderEnv& env, const std::vector<const gac_ir*>& irs) {

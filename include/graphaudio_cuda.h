@@ -319,6 +319,11 @@ int gac_automation_eval(gac_context* ctx, const gac_param* param, int a_rate, in
 int gac_resample_cubic(gac_context* ctx, const float* in, int64_t n_in, double rate, int64_t n_out, float* out,
                        int64_t* produced, int64_t* consumed);
 
+/* Host-only planning hook (no device needed): how K6's second-level FFT covers n_blocks output blocks of an impulse response of
+ * n_partitions partitions — *m = transform length (0: direct sum), *n_big = overlap-save segments of length 2m in front,
+ * *n_small = segments of length m behind them (uniform != 0: the single-length plan of GAC_FLAG_UNIFORM_SEGMENTS). */
+int gac_plan_segments(int64_t n_blocks, int n_partitions, int uniform, int* m, int* n_big, int* n_small);
+
 /* ---- the literal plugin seam: ONE ConvolverNode inside an ordinary reference graph ----
  * A `CudaConvolverNode : AudioNode` overrides Process(), pins Inputs[0].Buffer and its pooled output block and calls
  * gac_convolver_process_block once per render quantum — the pattern of GraphAudio.SteamAudio's nodes

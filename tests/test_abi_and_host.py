@@ -251,3 +251,25 @@ def test_unaccelerated_node_types_are_refused_never_rendered_as_silence():
     s.Start()
     G.OscillatorNode(ctx)
     assert len(ctx._topology()[0]) == 1
+
+
+def test_k6_segment_planner():
+    """plan_segments (host-only): every overlap-save segment spends Lh = ceil16(P - 1) of its M points on history; double-length
+    segments in front are used when they save work after pricing in their lower per-point rate."""
+    L = N.lib()
+
+    def plan(q, p, uniform=0):
+        m, nb, ns = C.c_int(), C.c_int(), C.c_int()
+        assert L.gac_plan_segments(q, p, uniform, C.byref(m), C.byref(nb), C.byref(ns)) == 0
+        return m.value, nb.value, ns.value
+    assert plan(4500, 750) == (2048, 1, 1)        # the bench workload: 4096 + 2048 points instead of 4 x 2048
+    assert plan(4500, 750, 1) == (2048, 0, 4)
+    assert plan(1300, 100) == (512, 1, 1) and plan(900, 100) == (512, 1, 0) and plan(350, 100) == (512, 0, 1)
+    assert plan(3750, 1875) == (4096, 0, 2)       # C5 (512-frame partitions): no radix-16 plan beyond 4096 points
+    assert plan(1875, 188) == (512, 0, 6)         # C4: six short segments stay cheaper than 1024-point ones
+    assert plan(100, 10)[0] == 0                  # short impulse responses take the direct sum
+    for q, p in ((4500, 750), (1300, 100), (777, 300), (20000, 1000)):
+        m, nb, ns = plan(q, p)
+        lh = ((p - 1 + 15) // 16) * 16
+        assert nb * (2 * m - lh) + ns * (m - lh) >= q  # the segments cover every output block
+    assert L.gac_plan_segments(0, 10, 0, None, None, None) != 0

@@ -360,7 +360,7 @@ class AudioBufferSourceNode(AudioNode):
     def Stop(self, when=0.0):  # :116-129
         # called between Render calls it cannot silence quanta that were already rendered: the stop time is at least the start
         # time of the next unprocessed quantum (the reference tests t0 < stopTime per block, :139)
-        at = max(0.0, float(when), self.Context._block_time(self.Context._q_now()) if hasattr(self.Context, "_q_now") else 0.0)
+        at = max(0.0, float(when), self.Context._block_time(self.Context._q_now()))
         if math.isnan(self._stop):
             self._stop = at
         else:

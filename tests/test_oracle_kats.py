@@ -561,3 +561,28 @@ def test_channel_splitter_and_merger_route_single_channels():
     s.Start()
     y = ctx.Render(128 * 5)
     assert not y[0].any() and np.array_equal(y[1], x[0][:640])
+
+
+def test_edits_between_render_calls_act_from_the_next_unprocessed_block():
+    # OfflineAudioContext.cs:55-100 renders whole 128-frame blocks and stashes what a call did not hand out; a parameter set after
+    # Render(1000) therefore applies from frame 1024 on (block 8), not from frame 1000 — and a source started "in the past" begins
+    # with the next block (AudioBufferSourceNode.cs:137-143 tests t1 > startTime per block)
+    fs = 48000
+    x = np.ones(128 * 40, np.float32)
+    ctx = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(ctx)
+    s.Buffer = O.PlayableAudioBuffer.FromChannelArrays([x], fs)
+    g = O.GainNode(ctx)
+    g.Gain.Value = 0.5
+    s.Connect(g).Connect(ctx.Destination)
+    s.Start()
+    a = ctx.Render(1000)
+    g.Gain.Value = 0.25
+    late = O.AudioBufferSourceNode(ctx)
+    late.Buffer = O.PlayableAudioBuffer.FromChannelArrays([x * np.float32(4.0)], fs)
+    late.Connect(ctx.Destination)
+    late.Start(0.0)
+    b = ctx.Render(1000)
+    y = np.concatenate([a, b], axis=1)[0]
+    assert np.all(y[:1024] == 0.5)                    # the block that was already processed keeps the old gain
+    assert np.all(y[1024:] == np.float32(0.25) + 4.0)  # new gain and the late source from block 8 on

@@ -8,7 +8,9 @@
 //   Y   float2 [n_conv][1 + chunk][B]     accumulated spectra; row 0 = the previous call's last block (its upper half is the overlap,
 //                                          PartitionedConvolver.cs:146-150)
 // Per call: H2D of the blocks, K5 (forward rFFT into the next rows), k_mac_ring (exact reference order), K7 (inverse + overlap-add),
-// D2H.  It is latency-bound by design — the batched renderer (gac_render*) is the throughput path.
+// D2H.  It is latency-bound by design — the batched renderer (gac_render*) is the throughput path.  (The block copies run on the
+// context stream's copy-engine queue: in a GAC_FLAG_ASYNC_UPLOAD context that orders later renders behind pending uploads, see
+// gac_context::h_stage — use a context of its own for per-quantum work.)
 
 struct gac_convolver {
   uint32_t magic = 0x47414343;  // "GACC"

@@ -414,6 +414,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--voices", type=int, default=0, help="voices per GPU (0: the workload's own count)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--partition", type=int, default=128)
     ap.add_argument("--tile-blocks", dest="tile_blocks", type=int, default=32)
@@ -427,7 +428,9 @@ def main():
     ap.add_argument("--sync-upload", dest="sync_upload", action="store_true",
                     help="e2e arm: copy every buffer during gac_buffer_create (reference semantics) instead of GAC_FLAG_ASYNC_UPLOAD")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.voices > 0:
+        wl["voices"] = args.voices
     if args.impl == "reference":
         run_reference(args, wl)
     else:

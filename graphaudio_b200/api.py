@@ -12,6 +12,7 @@ package sketched in INTEGRATION.md; pytest drives the library through it.  No CP
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import math
 from typing import List, Optional
 
@@ -65,6 +66,9 @@ def _f32(a):
 
 def _fptr(a):
     return a.ctypes.data_as(N.fp)
+
+
+_context_serial = itertools.count(1)
 
 
 class FilterType:  # Nodes/BiQuadFilterNode.cs:288-298
@@ -149,7 +153,8 @@ class PlayableAudioBuffer:
 
     def _handle(self, ctx: "OfflineAudioContext"):
         ctx = ctx._root()  # forks share the parent's device handle
-        h = self._handles.get(id(ctx))
+        # keyed by the context's serial number, never by id(): CPython reuses ids, and a disposed context's handles are freed
+        h = self._handles.get(ctx._serial)
         if h is None:
             out = C.c_void_p()
             if self._raw is not None:
@@ -160,8 +165,9 @@ class PlayableAudioBuffer:
                 ptrs = (N.fp * self.NumberOfChannels)(*[_fptr(c) for c in self.channels])
                 check(N.lib().gac_buffer_create(ctx._h, ptrs, self.NumberOfChannels, self.Length, self.SampleRate, C.byref(out)))
             h = out.value
-            self._handles[id(ctx)] = h
+            self._handles[ctx._serial] = h
             ctx._owned_buffers.append(h)
+            ctx._buffer_objects.append(self)
         return h
 
 
@@ -578,6 +584,8 @@ class OfflineAudioContext:
         without a device handle: nodes, automation and topology can be recorded and inspected (`_topology()`), Render raises.
         It exists for the CPU unit tests of the host-side logic; it is not a fallback."""
         self._h = None
+        self._serial = next(_context_serial)
+        self._buffer_objects: List[PlayableAudioBuffer] = []  # buffers holding a device handle of this context (purged by Dispose)
         if sampleRate <= 0:
             raise ArgumentOutOfRangeException("sampleRate")  # AudioContextBase.cs:37-38
         self.SampleRate = int(sampleRate)
@@ -912,6 +920,8 @@ class OfflineAudioContext:
         handle.  Used with RenderBatch; disposing the parent disposes the shared handle."""
         child = OfflineAudioContext.__new__(OfflineAudioContext)
         child._h = self._h
+        child._serial = self._serial
+        child._buffer_objects = self._buffer_objects
         child.SampleRate = self.SampleRate
         child._nodes = []
         child._owned_buffers = self._owned_buffers
@@ -941,6 +951,9 @@ class OfflineAudioContext:
                 L.gac_ir_destroy(h)
             for h in self._owned_buffers:
                 L.gac_buffer_destroy(h)
+            for b in self._buffer_objects:
+                b._handles.pop(self._serial, None)
+            self._buffer_objects = []
             L.gac_context_destroy(self._h)
             self._h = None
 

@@ -273,14 +273,10 @@ void biquad_scratch_sizes(int n_jobs, int64_t n_frames, size_t* n_float2, size_t
 
 void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,
                          int* d_flags, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_biquad_lanes<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
-    cudaFuncSetAttribute(k_biquad_lanes<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
-    cudaFuncSetAttribute(k_biquad_lanes<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
-    cudaFuncSetAttribute(k_biquad_lanes<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLanesSmem);
-    attr = true;
-  }
+  GAC_SMEM_OPT_IN((k_biquad_lanes<false, false>), kLanesSmem);
+  GAC_SMEM_OPT_IN((k_biquad_lanes<false, true>), kLanesSmem);
+  GAC_SMEM_OPT_IN((k_biquad_lanes<true, false>), kLanesSmem);
+  GAC_SMEM_OPT_IN((k_biquad_lanes<true, true>), kLanesSmem);
   const unsigned groups = (unsigned)((n_jobs + 15) / 16);
   int seg_slabs = 0;
   const int n_seg = biquad_lane_segments(n_jobs, n_frames, &seg_slabs);

@@ -96,6 +96,7 @@ struct ResampleTable {
   float* d_t = nullptr;
 };
 
+constexpr size_t kResampleCacheMax = 16;  // distinct source geometries whose phase tables a context keeps
 struct gac_context {
   uint32_t magic = 0x47414331;  // "GAC1"
   int device = 0;
@@ -128,8 +129,11 @@ struct gac_context {
   // page-locked staging for the small job tables of a render: they reach the device through a copy KERNEL (SM loads over
   // PCIe), not through the DMA engine, whose queue may hold hundreds of megabytes of asynchronous buffer uploads — a
   // cudaMemcpyAsync of a 2 KB table would wait behind all of them, and with it every kernel of the render
-  char* h_stage = nullptr;
-  size_t stage_cap = 0, stage_used = 0;
+  // Every context stages this way (not only async-upload ones): a cudaMemcpyAsync from PAGEABLE memory larger than the driver's
+  // 64 KB staging slot blocks the host until the stream has drained, which serialised planning and execution of large renders
+  // (1024 voices: 57 ms per render of which 25 ms were gaps).  Blocks are taken from the process-wide pool on demand.
+  std::vector<char*> stage_blocks;
+  size_t stage_block = 0, stage_used = 0;  // current block / bytes used in it
 };
 // Staging blocks are recycled process-wide: page-locking 8 MB costs milliseconds (and cudaFreeHost synchronises the device),
 // far more than the render of a context that lives for one graph.  Blocks are portable (any device's context may take one).
@@ -249,12 +253,25 @@ static bool use_fft2(const gac_context* c, int P, int M2) {
 static int table_h2d(gac_context* ctx, void* d_dst, const void* h_src, size_t bytes) {
   if (bytes == 0) return GAC_OK;
   const size_t need = (bytes + 15) & ~(size_t)15;
-  if (ctx->h_stage && ctx->stage_used + need <= ctx->stage_cap) {
-    char* slot = ctx->h_stage + ctx->stage_used;
-    ctx->stage_used += need;
-    memcpy(slot, h_src, bytes);
-    launch_copy_from_host(d_dst, slot, need, ctx->stream);
-    return GAC_OK;
+  if (need <= kStageBytes) {
+    if (ctx->stage_block < ctx->stage_blocks.size() && ctx->stage_used + need > kStageBytes) {
+      ctx->stage_block++;
+      ctx->stage_used = 0;
+    }
+    if (ctx->stage_block >= ctx->stage_blocks.size()) {
+      if (char* p = take_stage_block()) {
+        ctx->stage_blocks.push_back(p);
+        ctx->stage_block = ctx->stage_blocks.size() - 1;
+        ctx->stage_used = 0;
+      }
+    }
+    if (ctx->stage_block < ctx->stage_blocks.size()) {
+      char* slot = ctx->stage_blocks[ctx->stage_block] + ctx->stage_used;
+      ctx->stage_used += need;
+      memcpy(slot, h_src, bytes);
+      launch_copy_from_host(d_dst, slot, need, ctx->stream);
+      return GAC_OK;
+    }
   }
   cudaError_t e = cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
@@ -485,10 +502,6 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   }
   int rc = ensure_block_times(ctx.get(), 8192);
   if (rc) return rc;
-  if (ctx->async_upload) {
-    ctx->h_stage = take_stage_block();  // null: falls back to cudaMemcpyAsync for the job tables
-    ctx->stage_cap = ctx->h_stage ? kStageBytes : 0;
-  }
   *out = ctx.release();
   return GAC_OK;
 }
@@ -517,7 +530,7 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
     cudaStreamDestroy(ctx->copy_stream);
   }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
-  give_stage_block(ctx->h_stage);
+  for (char* p : ctx->stage_blocks) give_stage_block(p);
   cudaStreamDestroy(ctx->stream);
   ctx->magic = 0;
   delete ctx;
@@ -690,6 +703,7 @@ extern "C" int gac_ir_prepare(gac_context* ctx, const gac_buffer* buf, int norma
   if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
   if (!buf || !out) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
+  if (buf->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "buffer belongs to another context");
   if (buf->rate != ctx->fs)  // Nodes/ConvolverNode.cs:48-49
     return fail(GAC_ERR_INVALID_OPERATION,
                 "Impulse response buffer sample rate must match the audio context sample rate. Impulse response buffer sample rate: %d, "

@@ -15,6 +15,23 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
   auto& cj = env.keep->make<SourceJob>();
   auto& rj = env.keep->make<ResampleJob>();
   auto& tables = ctx->resample_cache;  // the phase recurrence depends on (rate, offset, end, length) only: replayed once per context
+  // tables evicted from the cache while this batch was planned: released (stream-ordered) when the function returns, i.e. behind
+  // the resample launch that may still read them; the host vectors stay alive in `keep` (a queued copy may still read them)
+  struct Evicted {
+    gac_context* ctx;
+    HostKeep* keep;
+    std::vector<std::shared_ptr<ResampleTable>> v;
+    void push_back(const std::shared_ptr<ResampleTable>& t) { v.push_back(t); }
+    ~Evicted() {
+      for (auto& t : v) {
+        if (t->d_k) cudaFreeAsync(t->d_k, ctx->stream);
+        if (t->d_t) cudaFreeAsync(t->d_t, ctx->stream);
+        t->d_k = nullptr;
+        t->d_t = nullptr;
+        keep->items.push_back(t);
+      }
+    }
+  } evicted{ctx, env.keep, {}};
   const double inf = std::numeric_limits<double>::infinity();
 
   for (size_t i = 0; i < voices.size(); i++) {
@@ -126,12 +143,10 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
       if (it != tables.end()) {
         tab = it->second;
       } else {
-        if (tables.size() >= 16) {  // bounded: drop everything (stream-ordered frees behind any render still using them)
-          for (auto& kv : tables) {
-            if (kv.second->d_k) cudaFreeAsync(kv.second->d_k, ctx->stream);
-            if (kv.second->d_t) cudaFreeAsync(kv.second->d_t, ctx->stream);
-            env.keep->items.push_back(kv.second);  // host vectors may still be the source of a queued copy
-          }
+        if (tables.size() >= kResampleCacheMax) {
+          // bounded: drop everything.  Jobs already planned for THIS batch still point at the device tables, so the frees are
+          // queued behind launch_resample (`evicted` below), never here.
+          for (auto& kv : tables) evicted.push_back(kv.second);
           tables.clear();
         }
         tab = std::make_shared<ResampleTable>();
@@ -370,6 +385,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
 
   const int B = ctx->B;
   const int64_t total = a.first_frame + a.n_frames;
+  ctx->stage_block = 0;
   ctx->stage_used = 0;  // the previous render has synchronised: its staged job tables are dead
   RenderEnv env;
   Scratch scratch(ctx);
@@ -526,18 +542,47 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         mj.dst[1] = bs.p[1];
         mj.first_input = (int)minputs.size();
         int64_t lo = std::numeric_limits<int64_t>::max(), hi = 0;
+        // Channel count of the fan-in block: the head node's input mode decides (AudioNodeInput.ComputeOutputChannelCount :139-168).
+        //   Max with channelCount 2 (GainNode, BiQuadFilterNode, DelayNode) and Explicit 2 (stereo / true-stereo ConvolverNode): 2,
+        //     a mono input is copied into both channels (:201-213);
+        //   Explicit 1 (ConvolverNode with a mono impulse response, ConvolverNode.cs:72-76): 1 — a mono input is added as it is, a
+        //     stereo input as (L + R) * 1/sqrt(2), each input on its own (:214-228);
+        //   ClampedMax 2 (StereoPannerNode.cs:24-26): min(max over the inputs' blocks, 2), i.e. 1 when every input is mono.
+        auto sig_in = [&](int x) -> const Sig& { return x >= 0 ? buses[bus_base[g] + (size_t)x] : sigs[voice_base[g] + (size_t)(~x)]; };
+        int head_ch = 2;
+        if (bh.ops.empty()) {
+          for (int x : bh.inputs) head_ch = sig_in(x).ch;  // a materialised fan-out point: no node, the signal passes through
+        } else if (bh.ops[0].kind == GAC_OP_CONVOLVER && bh.ops[0].ir && bh.ops[0].ir->nch == 1) {
+          head_ch = 1;
+        } else if (bh.ops[0].kind == GAC_OP_PANNER) {
+          bool all_mono = true, steady2 = false;
+          for (int x : bh.inputs) {
+            const Sig& vs = sig_in(x);
+            if (vs.hi <= vs.lo || vs.ch == 1) continue;
+            all_mono = false;
+            // a source connected directly carries two channels only while it plays (its idle block has one, AudioBufferSourceNode.cs:391-402)
+            const bool direct = x < 0 && vs.from_source && (!vs.ops || vs.ops->empty());
+            if (!direct || (vs.lo == 0 && vs.hi == env.Npad)) steady2 = true;
+          }
+          if (all_mono) head_ch = 1;
+          else if (!steady2)
+            return fail(GAC_ERR_UNSUPPORTED, "a StereoPannerNode fed by several inputs whose channel count changes during the render (stereo sources "
+                                             "connected directly that start late or end early) is outside the accelerated path");
+        }
         for (int x : bh.inputs) {
-          const Sig& vs = x >= 0 ? buses[bus_base[g] + (size_t)x] : sigs[voice_base[g] + (size_t)(~x)];
+          const Sig& vs = sig_in(x);
           if (vs.hi <= vs.lo) continue;  // silent throughout: never mixed (:127)
           MixInput in;
           in.src[0] = vs.p[0];
           in.src[1] = vs.p[1];
           in.lo = vs.lo;
           in.hi = vs.hi;
+          if (head_ch == 1 && vs.ch == 2) in.downmix = 1.0f / sqrtf(2.0f);  // 1.0f / MathF.Sqrt(srcChannels)  (:217)
           minputs.push_back(in);
           lo = std::min(lo, vs.lo);
           hi = std::max(hi, vs.hi);
         }
+        bs.ch = head_ch;
         mj.n_inputs = (int)minputs.size() - mj.first_input;
         bs.lo = mj.n_inputs ? lo : 0;  // non-silent where any input was mixed (convex hull)
         bs.hi = mj.n_inputs ? hi : 0;

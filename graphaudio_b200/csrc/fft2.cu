@@ -397,11 +397,7 @@ void fft2_fill_tables(float2* host) {
 template <int M>
 static void conv16_t(const Fft2Job* d_jobs, dim3 grid, const float2* d_tab, int64_t n_blocks, int64_t xs, int64_t ys, cudaStream_t s) {
   constexpr size_t smem = conv16_smem<M>();
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_fft2_conv16<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  GAC_SMEM_OPT_IN(k_fft2_conv16<M>, smem);
   k_fft2_conv16<M><<<grid, M / 16, smem, s>>>(d_jobs, d_tab + fft2_table_offset(M), n_blocks, xs, ys);
 }
 template <int M>
@@ -413,21 +409,13 @@ static void prep16_t(const float2* d_H, int64_t h_ch_stride, dim3 grid, int B, i
 template <int M>
 static void conv_t(const Fft2Job* d_jobs, dim3 grid, const float2* d_tw2, int64_t n_blocks, int64_t xs, int64_t ys, cudaStream_t s) {
   constexpr size_t smem = sizeof(float2) * smem_elems(M);
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    cudaFuncSetAttribute(k_fft2_conv<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  GAC_SMEM_OPT_IN(k_fft2_conv<M>, smem);
   k_fft2_conv<M><<<grid, M / 8, smem, s>>>(d_jobs, d_tw2, n_blocks, xs, ys);
 }
 template <int M>
 static void prep_t(const float2* d_H, int64_t h_ch_stride, dim3 grid, int B, int P, float2* d_H2, const float2* d_tw2, cudaStream_t s) {
   constexpr size_t smem = sizeof(float2) * smem_elems(M);
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    cudaFuncSetAttribute(k_fft2_prep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  GAC_SMEM_OPT_IN(k_fft2_prep<M>, smem);
   k_fft2_prep<M><<<grid, M / 8, smem, s>>>(d_H, h_ch_stride, B, P, d_H2, d_tw2);
 }
 

@@ -280,11 +280,7 @@ template <int H>
 static void fwd_launch(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
   using G = Geo<H>;
   constexpr size_t smem = sizeof(float2) * (size_t)(G::TILE + G::GROUPS * G::ZS);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_rfft_fwd_t8<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  GAC_SMEM_OPT_IN(k_rfft_fwd_t8<H>, smem);
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
     dim3 grid((unsigned)((max_blocks + G::COLS - 1) / G::COLS), (unsigned)nj);
@@ -295,11 +291,7 @@ template <int H>
 static void inv_launch(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
   using G = Geo<H>;
   constexpr size_t smem = sizeof(float2) * (size_t)(G::TILE + G::GROUPS * G::ZS + G::GROUPS * (H / 2 + 8));
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_irfft_ola_t8<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  GAC_SMEM_OPT_IN(k_irfft_ola_t8<H>, smem);
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
     dim3 grid((unsigned)((max_blocks + G::COLS - 2) / (G::COLS - 1)), (unsigned)nj);

@@ -12,6 +12,26 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: a process-wide "done" flag leaves every
+// device but the first without the opt-in (launches with more than 48 KB of dynamic shared memory then fail with "invalid
+// argument"), and an unsynchronised flag races when two render threads launch the kernel for the first time.  One mutex and one
+// bit per device at each call site; `bytes` may grow over time (the largest value seen per device is kept).
+#define GAC_SMEM_OPT_IN(kernel, bytes)                                                                   \
+  do {                                                                                                    \
+    static std::mutex mu_;                                                                                \
+    static size_t set_[64] = {0};                                                                         \
+    int dev_ = 0;                                                                                         \
+    cudaGetDevice(&dev_);                                                                                 \
+    std::lock_guard<std::mutex> lk_(mu_);                                                                 \
+    if (dev_ >= 0 && dev_ < 64 && (size_t)(bytes) > set_[dev_]) {                                         \
+      if ((size_t)(bytes) > 48 * 1024)                                                                    \
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));          \
+      set_[dev_] = (size_t)(bytes);                                                                       \
+    }                                                                                                     \
+  } while (0)
+
 namespace gac {
 
 // ------------------------------------------------------------------ FFT (fft.cu)
@@ -223,6 +243,8 @@ struct MixJob {       // dst[c][n] = (((0 + src0) + src1) + ...) over active ran
 struct MixInput {
   const float* src[2];
   int64_t lo, hi;     // frames where the input is non-silent
+  float downmix = 0.f;  // != 0: the fan-in has ONE channel and this input two: (L + R) * downmix lands in both rows
+  int pad_ = 0;         //       (AudioNodeInput.cs:214-228; 1 / sqrt(2))
 };
 void launch_mix(const MixJob* d_jobs, int n_jobs, const MixInput* d_inputs, int64_t n_frames, cudaStream_t s);
 

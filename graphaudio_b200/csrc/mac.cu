@@ -355,11 +355,7 @@ int mac_tile_blocks(int variant) { return variant == 64 ? 64 : 32; }
 template <int NS, bool F2>
 static void launch_mac_tiled_t(const MacJob* d_jobs, const MacTile* d_tiles, int n_tiles, int stride, cudaStream_t s) {
   using Cfg = MacCfg<NS>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_mac_tiled<NS, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    attr = true;
-  }
+  GAC_SMEM_OPT_IN((k_mac_tiled<NS, F2>), Cfg::SMEM);
   k_mac_tiled<NS, F2><<<n_tiles, Cfg::THREADS, Cfg::SMEM, s>>>(d_jobs, d_tiles, stride);
 }
 
@@ -376,11 +372,7 @@ void launch_mac_tiled(const MacJob* d_jobs, int n_jobs, const MacTile* d_tiles, 
   }
   // bin 0 = (DC, Nyquist): two real convolutions, written over the generic result
   const size_t smem = (size_t)(2 * p_max + kDcThreads) * sizeof(float2);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(k_mac_dc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
+  GAC_SMEM_OPT_IN(k_mac_dc, smem);
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
     dim3 grid((unsigned)((n_blocks + kDcThreads - 1) / kDcThreads), (unsigned)nj);

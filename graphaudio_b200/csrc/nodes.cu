@@ -321,6 +321,12 @@ void launch_panner(const PannerJob* d_jobs, int n_jobs, int64_t n_frames, bool s
 }
 
 // ============================================================================================ mix
+// N -> 1 channel mix of one input block (AudioNodeInput.cs:214-228): sum = 0; sum += L; sum += R; dst += sum * (1 / sqrt(N)).
+// The mono result is kept in both rows.
+__device__ __forceinline__ void mix_down(float4& l, float4& r, float scale) {
+  l.x = (l.x + r.x) * scale; l.y = (l.y + r.y) * scale; l.z = (l.z + r.z) * scale; l.w = (l.w + r.w) * scale;
+  r = l;
+}
 __global__ void __launch_bounds__(256) k_mix(const MixJob* __restrict__ jobs, const MixInput* __restrict__ inputs, int64_t n_frames) {
   const MixJob job = jobs[blockIdx.y];
   int64_t n4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
@@ -334,10 +340,12 @@ __global__ void __launch_bounds__(256) k_mix(const MixJob* __restrict__ jobs, co
   for (; i + 4 <= job.n_inputs; i += 4) {
     float4 x0[4], x1[4];
     bool on[4];
+    float dm[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const MixInput in = ins[i + k];
       on[k] = n4 >= in.lo && n4 < in.hi;
+      dm[k] = in.downmix;
       if (on[k]) {
         x0[k] = *reinterpret_cast<const float4*>(in.src[0] + n4);
         x1[k] = *reinterpret_cast<const float4*>(in.src[1] + n4);
@@ -346,6 +354,7 @@ __global__ void __launch_bounds__(256) k_mix(const MixJob* __restrict__ jobs, co
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if (on[k]) {  // silent inputs are skipped, not added as zeros (:127)
+        if (dm[k] != 0.f) mix_down(x0[k], x1[k], dm[k]);
         a0.x += x0[k].x; a0.y += x0[k].y; a0.z += x0[k].z; a0.w += x0[k].w;
         a1.x += x1[k].x; a1.y += x1[k].y; a1.z += x1[k].z; a1.w += x1[k].w;
       }
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(256) k_mix(const MixJob* __restrict__ jobs, co
     if (n4 >= in.lo && n4 < in.hi) {
       float4 x0 = *reinterpret_cast<const float4*>(in.src[0] + n4);
       float4 x1 = *reinterpret_cast<const float4*>(in.src[1] + n4);
+      if (in.downmix != 0.f) mix_down(x0, x1, in.downmix);
       a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
       a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
     }

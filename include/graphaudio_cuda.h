@@ -251,7 +251,8 @@ int gac_render_interleaved(gac_context* ctx, const gac_graph* graph, int64_t fir
                            float* interleaved, int channels, int64_t start_index);
 
 /* As gac_render, but the result stays in HBM: d_out is a device pointer to [n_out_channels][n_frames]
- * float32 (row stride n_frames).  Asynchronous on the context's stream unless sync != 0. */
+ * float32 (row stride n_frames).  The call returns when the device has finished (the job tables of a render live on the
+ * host until then); `sync` is kept for ABI compatibility and ignored. */
 int gac_render_device(gac_context* ctx, const gac_graph* graph, int64_t first_frame, int64_t n_frames,
                       float* d_out, int n_out_channels, int sync);
 

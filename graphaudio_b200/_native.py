@@ -76,7 +76,8 @@ class gac_stats(C.Structure):
                 ("ms_fft_inv", C.c_double), ("ms_mix", C.c_double), ("ms_d2h", C.c_double), ("conv_units", C.c_int64),
                 ("algorithmic_bytes", C.c_double), ("mac_complex_macs", C.c_double), ("kernel_launches", C.c_int64),
                 ("voices", C.c_int64), ("frames", C.c_int64), ("mac_flops", C.c_double), ("mac_bytes_moved", C.c_double),
-                ("mac_variant_used", C.c_int32), ("mac_big_segments", C.c_int32), ("ms_delay", C.c_double), ("ms_panner", C.c_double)]
+                ("mac_variant_used", C.c_int32), ("mac_big_segments", C.c_int32), ("ms_delay", C.c_double), ("ms_panner", C.c_double),
+                ("mac_h2_bytes_single", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -113,6 +114,9 @@ SIGNATURES = {
     "gac_automation_eval": (C.c_int, [C.c_void_p, C.POINTER(gac_param), C.c_int, C.c_int64, fp]),
     "gac_resample_cubic": (C.c_int, [C.c_void_p, fp, C.c_int64, C.c_double, C.c_int64, fp, C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int64)]),
+    "gac_biquad_batch": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int64, C.POINTER(C.c_int), C.POINTER(gac_param), C.POINTER(gac_param),
+                                   C.POINTER(gac_param), fp]),
+    "gac_mix": (C.c_int, [C.c_void_p, fpp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), fp, C.c_int, C.c_int64, fp]),
     "gac_plan_segments": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gac_convolver_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "gac_convolver_destroy": (C.c_int, [C.c_void_p]),

@@ -134,6 +134,10 @@ struct gac_context {
   // (1024 voices: 57 ms per render of which 25 ms were gaps).  Blocks are taken from the process-wide pool on demand.
   std::vector<char*> stage_blocks;
   size_t stage_block = 0, stage_used = 0;  // current block / bytes used in it
+  // render scratch arena (struct Scratch): device chunks kept between renders, bump-allocated
+  std::vector<std::pair<char*, size_t>> arena;
+  size_t arena_chunk = 0, arena_used = 0;
+  size_t arena_keep_limit = (size_t)64 << 30;
 };
 // Staging blocks are recycled process-wide: page-locking 8 MB costs milliseconds (and cudaFreeHost synchronises the device),
 // far more than the render of a context that lives for one graph.  Blocks are portable (any device's context may take one).
@@ -278,23 +282,58 @@ static int table_h2d(gac_context* ctx, void* d_dst, const void* h_src, size_t by
   return GAC_OK;
 }
 
+// Render scratch comes from a context-owned ARENA: chunks of device memory that stay with the context between renders, handed out
+// by bumping a pointer.  The first render of a context grows the arena chunk by chunk (stream-ordered allocations from the device
+// pool); the second render replaces several chunks by ONE of their total size, so that from then on a render makes no allocation
+// call at all.  (Allocating and freeing ~20 blocks of up to 24 GB per render through cudaMallocAsync was correct but not
+// steady: whenever a long-lived allocation — an impulse response's double-length spectra — was carved out of the pool's cached
+// blocks in between, the next render paid hundreds of milliseconds of re-mapping: 1024 voices rendered in 33 ms, 164 ms, 477 ms,
+// 33 ms ... on consecutive calls.)  Arenas beyond `arena_keep_limit` are returned to the pool when the render ends.
 struct Scratch {
   gac_context* ctx;
-  std::vector<void*> ptrs;
   size_t bytes = 0;
-  explicit Scratch(gac_context* c) : ctx(c) {}
+  explicit Scratch(gac_context* c) : ctx(c) {
+    ctx->arena_chunk = 0;
+    ctx->arena_used = 0;
+    // several chunks left by the previous render: one chunk of their total size replaces them NOW (not when that render ended: a
+    // context that renders once and is disposed — one OfflineAudioContext per render is the reference's usual pattern — must not
+    // pay for an arena it never uses again)
+    auto& chunks = ctx->arena;
+    if (chunks.size() > 1) {
+      size_t total = 0;
+      for (auto& ch : chunks) {
+        total += ch.second;
+        cudaFreeAsync(ch.first, ctx->stream);
+      }
+      chunks.clear();
+      void* p = nullptr;
+      if (cudaMallocAsync(&p, total, ctx->stream) == cudaSuccess) chunks.emplace_back((char*)p, total);
+      else cudaGetLastError();  // (the render grows the arena chunk by chunk again)
+    }
+  }
   template <typename T>
   int alloc(T** out, size_t count) {
-    void* p = nullptr;
-    size_t b = (std::max<size_t>(count * sizeof(T), 16) + 15) & ~(size_t)15;
-    cudaError_t e = cudaMallocAsync(&p, b, ctx->stream);
-    if (e != cudaSuccess) {
-      return fail(e == cudaErrorMemoryAllocation ? GAC_ERR_OUT_OF_MEMORY : GAC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", b,
-                  cudaGetErrorString(e));
+    const size_t b = (std::max<size_t>(count * sizeof(T), 16) + 255) & ~(size_t)255;
+    auto& chunks = ctx->arena;
+    while (ctx->arena_chunk < chunks.size() && ctx->arena_used + b > chunks[ctx->arena_chunk].second) {
+      ctx->arena_chunk++;
+      ctx->arena_used = 0;
     }
-    ptrs.push_back(p);
+    if (ctx->arena_chunk >= chunks.size()) {
+      void* p = nullptr;
+      const size_t want = std::max(b, (size_t)64 << 20);
+      cudaError_t e = cudaMallocAsync(&p, want, ctx->stream);
+      if (e != cudaSuccess) {
+        return fail(e == cudaErrorMemoryAllocation ? GAC_ERR_OUT_OF_MEMORY : GAC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", want,
+                    cudaGetErrorString(e));
+      }
+      chunks.emplace_back((char*)p, want);
+      ctx->arena_chunk = chunks.size() - 1;
+      ctx->arena_used = 0;
+    }
+    *out = (T*)(chunks[ctx->arena_chunk].first + ctx->arena_used);
+    ctx->arena_used += b;
     bytes += b;
-    *out = (T*)p;
     return GAC_OK;
   }
   // upload a host vector (stream-ordered; the vector must stay alive until the stream is synchronised)
@@ -305,9 +344,14 @@ struct Scratch {
     if (v.empty()) return GAC_OK;
     return table_h2d(ctx, *out, v.data(), v.size() * sizeof(T));  // (the allocation is 16-byte granular)
   }
+  // end of a render: oversized arenas go back to the pool
   void release() {
-    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
-    ptrs.clear();
+    auto& chunks = ctx->arena;
+    size_t total = 0;
+    for (auto& c : chunks) total += c.second;
+    if (total <= ctx->arena_keep_limit) return;
+    for (auto& c : chunks) cudaFreeAsync(c.first, ctx->stream);
+    chunks.clear();
   }
   ~Scratch() { release(); }
 };
@@ -380,6 +424,23 @@ struct HostKeep {
     return *p;
   }
 };
+
+// GAC_TRACE=1: host-side timestamps of a render's phases on stderr (diagnostics only)
+struct HostTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  HostTrace() : on(getenv("GAC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[gac_trace] %-28s +%.3f ms\n", what, ms);
+  }
+};
+static thread_local HostTrace* g_trace = nullptr;
+#define TRACE_MARK(what)              \
+  do {                                \
+    if (g_trace) g_trace->mark(what); \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------ library
 extern "C" int gac_version(void) { return GAC_ABI_VERSION; }
@@ -471,6 +532,7 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   ctx->mixed_segments = (desc->flags & GAC_FLAG_UNIFORM_SEGMENTS) == 0;
   if (ctx->async_upload) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   ctx->scratch_budget = di.budget;
+  ctx->arena_keep_limit = di.budget + di.budget / 2;  // half of the memory that was free when the device was first used
   {
     std::lock_guard<std::mutex> lk(g_tables_mu);
     DeviceTables* T = device_tables(dev);
@@ -520,6 +582,8 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) gac_comm_destroy(ctx);
+  for (auto& c : ctx->arena) cudaFreeAsync(c.first, ctx->stream);
+  ctx->arena.clear();
   for (auto& kv : ctx->resample_cache) {
     if (kv.second->d_k) cudaFreeAsync(kv.second->d_k, ctx->stream);
     if (kv.second->d_t) cudaFreeAsync(kv.second->d_t, ctx->stream);
@@ -914,6 +978,7 @@ struct RenderEnv {
   int64_t launches = 0;
   int64_t conv_units = 0;
   double alg_bytes = 0, macs = 0;
+  double mac_h2_single = 0;             // bytes of ONE set of IR spectra per channel-convolver (the compulsory part of the H reads)
   double mac_flops = 0, mac_bytes = 0;  // flops issued / bytes the K6 variant in use has to move (X, H, Y once)
   int mac_big = 0;                      // double-length segments per channel-convolver of the last second-level-FFT batch
   int mac_used = 0;                     // K6 variant of the last convolver batch (1 stream, 2/4 tiled, 3 second-level FFT)
@@ -1112,6 +1177,7 @@ static int conv_batch_direct(RenderEnv& env, std::vector<ConvItem>& items) {
         env.conv_units += QB;
         env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
         env.mac_bytes += 8.0 * B * ((double)QB * 2 + P);  // X and Y once, H once
+        env.mac_h2_single += 8.0 * B * P;
       }
       for (int k = 0; k < it.n_inv; k++) {
         FftInvJob v;
@@ -1326,6 +1392,7 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
         env.macs += (double)QB * P * C;  // complex MACs the direct sum would need (not issued: see mac_flops)
         env.mac_flops += (double)nseg * C * (2.0 * 5.0 * M * log2m + 6.0 * M) + (double)n_big * C * (2.0 * 5.0 * 2 * M * (log2m + 1) + 6.0 * 2 * M);
         // XT once (window overlaps hit L2), the H2 row(s), YT
+        env.mac_h2_single += 8.0 * C * (double)fft2_h2_row_elems(M);
         env.mac_bytes += 8.0 * C * ((double)QB + (nseg > 0 ? (double)fft2_h2_row_elems(M) : 0.0) + (n_big > 0 ? (double)fft2_h2_row_elems(2 * M) : 0.0) + (double)QB);
       }
       for (int k = 0; k < it.n_inv; k++) {
@@ -1347,6 +1414,7 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     if ((rc = env.scratch->upload(&dcj, cj))) return rc;
     if ((rc = env.scratch->upload(&dcjb, cjb))) return rc;
     if ((rc = env.scratch->upload(&dij, ij))) return rc;
+    TRACE_MARK("conv fft2: tables uploaded");
     int t = env.timer->begin(C_FFT_FWD);
     launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
     env.timer->end(t);
@@ -1633,6 +1701,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       }
     }
     // ---------------- BiQuadFilterNode (K2 + K3)
+    TRACE_MARK("chain position: before biquads");
     if (!biquads.empty()) {
       const size_t per_job = (size_t)env.Npad * (2 * (4 + 16 + 16) + 4 + 4) + (size_t)env.NQ * (16 + 4);
       const size_t max_jobs = std::min<size_t>(65535, std::max<size_t>(1, ctx->scratch_budget / per_job));
@@ -1678,8 +1747,10 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           j.idx = idx_all + k * 2 * (size_t)env.Npad;
           bj.push_back(j);
         }
+        TRACE_MARK("biquad: jobs built");
         int rc = run_param_jobs(env, pj);
         if (rc) return rc;
+        TRACE_MARK("biquad: params queued");
         BiquadJob* dbj = nullptr;
         int32_t *dlast = nullptr, *dent = nullptr;
         if ((rc = env.scratch->upload(&dbj, bj))) return rc;
@@ -1697,6 +1768,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         env.timer->end(t);
         env.launches += n_seg > 1 ? 9 : 6;
         CU(cudaGetLastError());
+        TRACE_MARK("biquad: queued");
       }
     }
     // ---------------- ConvolverNode (K5, K6, K7)
@@ -1808,8 +1880,10 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         launch_gain(dz, (int)zj.size(), env.Npad, ctx->stream);
         env.launches += 1;
       }
+      TRACE_MARK("conv: items built");
       int rc = conv_batch(env, items);
       if (rc) return rc;
+      TRACE_MARK("conv: queued");
     }
   }
   return GAC_OK;

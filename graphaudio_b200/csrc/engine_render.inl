@@ -353,20 +353,12 @@ static int mix_into(RenderEnv& env, std::vector<MixJob>& jobs, std::vector<MixIn
   return GAC_OK;
 }
 
-// GAC_TRACE=1: host-side timestamps of a render's phases on stderr (diagnostics only)
-struct HostTrace {
-  bool on;
-  std::chrono::steady_clock::time_point t0;
-  HostTrace() : on(getenv("GAC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
-  void mark(const char* what) {
-    if (!on) return;
-    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    fprintf(stderr, "[gac_trace] %-28s +%.3f ms\n", what, ms);
-  }
-};
-
 static int render_core(gac_context* ctx, const RenderArgs& a) {
   HostTrace trace;
+  struct TraceScope {
+    explicit TraceScope(HostTrace* t) { g_trace = t->on ? t : nullptr; }
+    ~TraceScope() { g_trace = nullptr; }
+  } trace_scope(&trace);
   if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");  // ObjectDisposedException (AudioContextBase.cs:54-55)
   if (!a.graphs || a.n_graphs <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "no graph");
   if (a.n_frames <= 0) return fail(GAC_ERR_OUT_OF_RANGE, "Frame count must be positive.");         // OfflineAudioContext.cs:35-36
@@ -467,6 +459,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         ssub.push_back(sigs[src_voices[k]]);
       }
       if ((rc = plan_sources(env, vsub, ssub))) return rc;
+      trace.mark("sources planned");
       if ((rc = run_chains(env, ssub))) return rc;
       for (size_t k = v0; k < v1; k++) {
         sigs[src_voices[k]] = ssub[k - v0];
@@ -749,6 +742,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   st.mac_complex_macs = env.macs;
   st.mac_flops = env.mac_flops;
   st.mac_bytes_moved = env.mac_bytes;
+  st.mac_h2_bytes_single = env.mac_h2_single;
   st.mac_variant_used = env.mac_used;
   st.mac_big_segments = env.mac_big;
   st.kernel_launches = env.launches;
@@ -1158,6 +1152,110 @@ extern "C" int gac_resample_cubic(gac_context* ctx, const float* in, int64_t n_i
   launch_resample(dj.as<ResampleJob>(), 1, m, ctx->stream);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, dout.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAC_OK;
+}
+
+// BiQuadFilterNode.Process for n_signals independent stereo signals through the production kernels (k_biquad_select / _entry /
+// _resolve / _lanes / _verify behind run_chains): x, y are [n_signals][2][n_frames] host arrays; frequency / q / gain are one
+// gac_param per signal (a-rate, a-rate, k-rate; events evaluated by k_param_eval exactly as in a render)
+extern "C" int gac_biquad_batch(gac_context* ctx, const float* x, int n_signals, int64_t n_frames, const int* filter_types,
+                                const gac_param* frequency, const gac_param* q, const gac_param* gain_db, float* y) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!x || !y || !filter_types || !frequency || !q || !gain_db || n_signals <= 0 || n_frames <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int64_t Npad = ((n_frames + 127) / 128) * 128;
+  std::vector<std::vector<OpH>> ops((size_t)n_signals);
+  int rc;
+  for (int s = 0; s < n_signals; s++) {
+    ops[s].resize(1);
+    OpH& o = ops[s][0];
+    o.kind = GAC_OP_BIQUAD;
+    o.ftype = filter_types[s];
+    if (o.ftype < 0 || o.ftype > 7) return fail(GAC_ERR_INVALID_ARGUMENT, "bad filter type %d", o.ftype);
+    if ((rc = copy_param(frequency[s], &o.p0, "biquad.frequency")) || (rc = copy_param(q[s], &o.p1, "biquad.Q")) ||
+        (rc = copy_param(gain_db[s], &o.p2, "biquad.gain")))
+      return rc;
+  }
+  if ((rc = ensure_block_times(ctx, Npad / 128 + 1))) return rc;
+  DevBuf dx;
+  if ((rc = dev_alloc(dx, (size_t)n_signals * 2 * Npad * 4))) return rc;
+  CU(cudaMemsetAsync(dx.p, 0, (size_t)n_signals * 2 * Npad * 4, ctx->stream));
+  CU(cudaMemcpy2DAsync(dx.p, (size_t)Npad * 4, x, (size_t)n_frames * 4, (size_t)n_frames * 4, (size_t)n_signals * 2, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ctx->stage_block = 0;
+    ctx->stage_used = 0;
+    RenderEnv env;
+    Scratch scratch(ctx);
+    HostKeep keep;
+    Timer timer(ctx);
+    env.ctx = ctx;
+    env.scratch = &scratch;
+    env.keep = &keep;
+    env.timer = &timer;
+    env.Npad = Npad;
+    env.NQ = Npad / 128;
+    env.QB = Npad / ctx->B;
+    std::vector<Sig> sigs((size_t)n_signals);
+    for (int s = 0; s < n_signals; s++) {
+      sigs[s].p[0] = dx.as<float>() + ((size_t)s * 2 + 0) * Npad;
+      sigs[s].p[1] = dx.as<float>() + ((size_t)s * 2 + 1) * Npad;
+      sigs[s].lo = 0;
+      sigs[s].hi = Npad;
+      sigs[s].ops = &ops[s];
+    }
+    rc = run_chains(env, sigs);
+    gac_stats st{};
+    timer.finish(&st);
+    cudaStreamSynchronize(ctx->stream);
+    if (rc) return rc;
+    st.kernel_launches = env.launches;
+    st.voices = n_signals;
+    st.frames = n_frames;
+    ctx->stats = st;
+  }
+  CU(cudaMemcpy2DAsync(y, (size_t)n_frames * 4, dx.p, (size_t)Npad * 4, (size_t)n_frames * 4, (size_t)n_signals * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAC_OK;
+}
+
+// AudioNodeInput.Pull's fan-in sum (AudioNodeInput.cs:118-137) through k_mix: out[c][n] = ((0 + in_0[c][n]) + in_1[c][n]) + ... over the
+// inputs that are non-silent at n (frames [lo[i], hi[i]), multiples of 128), in the given order.  inputs[i] -> [2][n_frames] host
+// rows; downmix[i] != 0 mixes input i to one channel first ((L + R) * downmix[i] into both rows, :214-228).  downmix may be null.
+extern "C" int gac_mix(gac_context* ctx, const float* const* inputs, const int64_t* lo, const int64_t* hi, const float* downmix, int n_inputs,
+                       int64_t n_frames, float* out) {
+  if (!ctx_ok(ctx)) return fail(GAC_ERR_DISPOSED, "context is null or destroyed");
+  if (!inputs || !lo || !hi || !out || n_inputs < 0 || n_frames <= 0) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int64_t Npad = ((n_frames + 127) / 128) * 128;
+  DevBuf din, dout, dj, di;
+  int rc;
+  if ((rc = dev_alloc(din, (size_t)std::max(1, n_inputs) * 2 * Npad * 4)) || (rc = dev_alloc(dout, (size_t)2 * Npad * 4)) ||
+      (rc = dev_alloc(dj, sizeof(MixJob))) || (rc = dev_alloc(di, sizeof(MixInput) * std::max(1, n_inputs))))
+    return rc;
+  CU(cudaMemsetAsync(din.p, 0, (size_t)std::max(1, n_inputs) * 2 * Npad * 4, ctx->stream));
+  std::vector<MixInput> mi((size_t)n_inputs);
+  for (int i = 0; i < n_inputs; i++) {
+    if (!inputs[i]) return fail(GAC_ERR_INVALID_ARGUMENT, "input %d is null", i);
+    if (lo[i] < 0 || hi[i] > Npad || lo[i] % 128 || hi[i] % 128) return fail(GAC_ERR_INVALID_ARGUMENT, "input %d: the non-silent range must consist of whole quanta", i);
+    float* d = din.as<float>() + (size_t)i * 2 * Npad;
+    CU(cudaMemcpy2DAsync(d, (size_t)Npad * 4, inputs[i], (size_t)n_frames * 4, (size_t)n_frames * 4, 2, cudaMemcpyHostToDevice, ctx->stream));
+    mi[i].src[0] = d;
+    mi[i].src[1] = d + Npad;
+    mi[i].lo = lo[i];
+    mi[i].hi = hi[i];
+    mi[i].downmix = downmix ? downmix[i] : 0.f;
+  }
+  MixJob mj;
+  mj.dst[0] = dout.as<float>();
+  mj.dst[1] = dout.as<float>() + Npad;
+  mj.first_input = 0;
+  mj.n_inputs = n_inputs;
+  if (n_inputs) CU(cudaMemcpyAsync(di.p, mi.data(), sizeof(MixInput) * mi.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dj.p, &mj, sizeof(mj), cudaMemcpyHostToDevice, ctx->stream));
+  launch_mix(dj.as<MixJob>(), 1, di.as<MixInput>(), Npad, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy2DAsync(out, (size_t)n_frames * 4, dout.p, (size_t)Npad * 4, (size_t)n_frames * 4, 2, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return GAC_OK;
 }

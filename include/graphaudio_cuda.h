@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GAC_ABI_VERSION 4
+#define GAC_ABI_VERSION 5
 
 /* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */
 typedef enum gac_status {
@@ -299,6 +299,8 @@ typedef struct gac_stats {
   int32_t mac_big_segments;    /* variant 3: double-length overlap-save segments per channel-convolver in front (0: one length) */
   double ms_delay;             /* DelayNode gather                                                  */
   double ms_panner;            /* StereoPannerNode                                                  */
+  double mac_h2_bytes_single;  /* bytes of ONE set of IR spectra over the channel-convolvers of the render: with the
+                                  spectrograms read and written once, the compulsory traffic of K6   */
 } gac_stats;
 int gac_get_stats(gac_context* ctx, gac_stats* out);
 
@@ -319,6 +321,18 @@ int gac_automation_eval(gac_context* ctx, const gac_param* param, int a_rate, in
 /* CubicResampler over one input, one Process call                                  ≙ CubicResampler.cs:26-63 */
 int gac_resample_cubic(gac_context* ctx, const float* in, int64_t n_in, double rate, int64_t n_out, float* out,
                        int64_t* produced, int64_t* consumed);
+
+/* BiQuadFilterNode.Process (Nodes/BiQuadFilterNode.cs:87-258) for n_signals independent stereo signals through the production
+ * biquad kernels: x, y = [n_signals][2][n_frames]; one Frequency (a-rate), Q (a-rate) and Gain (k-rate, dB) parameter per signal,
+ * evaluated on the device as in a render; filter_types[n_signals] = gac_filter_type. */
+int gac_biquad_batch(gac_context* ctx, const float* x, int n_signals, int64_t n_frames, const int* filter_types,
+                     const gac_param* frequency, const gac_param* q, const gac_param* gain_db, float* y);
+/* The fan-in sum of AudioNodeInput.Pull / MixBuffer (AudioNodeInput.cs:118-137,182-244) over n_inputs stereo blocks sequences:
+ * inputs[i] -> [2][n_frames]; input i is non-silent on frames [lo[i], hi[i]) (whole quanta) and skipped elsewhere; summed in
+ * the given (connection) order in float32.  downmix (may be NULL): downmix[i] != 0 mixes input i down to one channel first,
+ * (L + R) * downmix[i] in both output rows — the N -> 1 rule of :214-228 with downmix = 1/sqrt(2).  out = [2][n_frames]. */
+int gac_mix(gac_context* ctx, const float* const* inputs, const int64_t* lo, const int64_t* hi, const float* downmix,
+            int n_inputs, int64_t n_frames, float* out);
 
 /* Host-only planning hook (no device needed): how K6's second-level FFT covers n_blocks output blocks of an impulse response of
  * n_partitions partitions — *m = transform length (0: direct sum), *n_big = overlap-save segments of length 2m in front,

@@ -103,3 +103,69 @@ def test_c3_full_length_subset_matches_oracle():
     assert np.abs(yo).max() > 0.05
     assert np.abs(yg - yo).max() <= 1e-5
     g.Dispose()
+
+
+def test_c4_full_length_renders_match_oracle():
+    """BASELINE configs[3] at its real size: independent renders of 5 s (240 000 frames), each Source -> BiQuad(lowpass sweep) ->
+    BiQuad(highpass 200 Hz, constant) -> ConvolverNode(0.5 s stereo IR) -> destination, batched by gac_render_batch.  The constant
+    200 Hz highpass is the filter whose speculative time segments never re-join bitwise (poles at radius 0.98): the whole
+    signal goes through the sequential repair path, which is what this test pins at full length (3 renders: the batch crosses
+    the 16-row group of the biquad lanes only with more, so a fourth case runs 17 renders on a shorter signal elsewhere)."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs, n_src, n_ir, n = 48000, 5 * 48000, 24000, 240000
+    parent = G.OfflineAudioContext(fs)
+    ctxs, refs = [], []
+    for r in range(3):
+        src, ir = synth.make_voice_inputs(40 + r, n_src, n_ir)
+
+        class _Api:  # the builder creates its own context: hand it a fork of the shared device context instead
+            pass
+        api = _Api()
+        for name in dir(G):
+            setattr(api, name, getattr(G, name))
+        api.OfflineAudioContext = lambda fs_, **kw: parent.Fork()
+        ctxs.append(synth.build_c4(api, fs, src, ir))
+        refs.append(synth.build_c4(O, fs, src, ir).Render(n))
+    out = G.RenderBatch(ctxs, n)
+    for r in range(3):
+        assert np.abs(refs[r]).max() > 0.02
+        err = np.abs(out[r] - refs[r]).max()
+        assert err <= 1e-5, (r, err)
+    assert parent.last_stats["conv_units"] == 3 * 2 * 1875
+    parent.Dispose()
+
+
+def test_c5_real_geometry_one_voice_matches_partition_512_oracle():
+    """BASELINE configs[4] at its real geometry on one voice: 44.1 kHz stereo source of 10 s in a 96 kHz context (CubicResampler,
+    rate 0.459375, 960 000 output frames) -> GainNode automation -> convolver with a 10 s stereo IR (960 000 frames) at 512-frame
+    partitions (P = 1875, second-level transform M = 4096) -> bus gain, 20 s = 1 920 000 frames.
+    Oracle (note on C5): the graph up to the convolver's input rendered by the oracle's nodes, then
+    PartitionedConvolver(blockSize = 512) per channel driven with 512-frame blocks, then the bus gain — ConvolverNode itself
+    always constructs with 128 (ConvolverNode.cs:55), the 512 partition is the constructor argument of PartitionedConvolver.cs:37."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs, src_rate = 96000, 44100
+    n_src, n_ir, n = 441000, 960000, 1920000
+    src = [synth.splitmix_uniform(4 * 7 + c, n_src) for c in range(2)]
+    ir = [synth.decay_ir(4 * 7 + 2 + c, n_ir) for c in range(2)]
+    gains = synth.voice_gains(7)
+    bus_gain = 0.125  # bus peak ~0.5 (SURVEY.md §8c: inputs scaled so that the bus peak lies in [0.25, 1])
+    g = synth.build_c5(G, fs, src_rate, [(src, ir, gains)], bus_gain, partition=512)
+    yg = g.Render(n)
+    st = g.last_stats
+    assert st["conv_units"] == 2 * 3750 and st["mac_variant_used"] == 3
+    g.Dispose()
+    # oracle: source -> gain (same automation) -> destination, then the 512-frame convolvers
+    o = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(o)
+    s.Buffer = O.PlayableAudioBuffer.FromChannelArrays(src, src_rate)
+    gn = O.GainNode(o)
+    synth.add_gain_automation(gn.Gain, gains)
+    s.Connect(gn).Connect(o.Destination)
+    s.Start()
+    x = o.Render(n)
+    yo = np.stack([O.PartitionedConvolver(ir[c], 512, True).process(x[c]) for c in range(2)]) * np.float32(bus_gain)
+    assert np.abs(yo).max() > 0.01
+    err = np.abs(yg - yo).max()
+    assert err <= 1e-5, err

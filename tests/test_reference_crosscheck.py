@@ -1,0 +1,60 @@
+"""Pins the CPU oracle (and the CUDA path) to outputs of the REAL reference binary — when they exist.
+
+tools/dotnet_crosscheck/run.sh builds the unmodified GraphAudio.Core with the .NET 9 SDK, renders the cases of
+tools/dotnet_crosscheck/dump_cases.py with `OfflineAudioContext.Render` (OfflineAudioContext.cs:30,108) and stores
+tests/golden/ref_<case>.f32.  The SDK exists neither in the build image nor on the GPU box, so until a maintainer runs the script
+these tests SKIP (and DESIGN.md says "parity unpinned"); once the fixtures are committed they run everywhere and need nothing
+but numpy (inputs are re-created from the seeds)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+_spec = importlib.util.spec_from_file_location("dump_cases", os.path.join(ROOT, "tools", "dotnet_crosscheck", "dump_cases.py"))
+dump_cases = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(dump_cases)
+
+
+def _ref(name, frames):
+    p = os.path.join(GOLDEN, f"ref_{name}.f32")
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not present: run tools/dotnet_crosscheck/run.sh with the .NET 9 SDK (parity stays unpinned until then)")
+    return np.fromfile(p, "<f4").reshape(2, frames)
+
+
+@pytest.mark.parametrize("name", list(dump_cases.CASES))
+def test_oracle_matches_the_reference_binary(name):
+    from oracle import ga_oracle as O
+    ctx, c = dump_cases.build_case(O, name)
+    ref = _ref(name, c["frames"])
+    y = ctx.Render(c["frames"])
+    # same algorithm, same libm; the only sanctioned difference is Ooura's FFT against the oracle's (1 ulp of a float32 spectrum value)
+    assert np.abs(y - ref).max() <= 2e-7 * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(dump_cases.CASES))
+def test_cuda_path_matches_the_reference_binary(name):
+    import graphaudio_b200 as G
+    ctx, c = dump_cases.build_case(G, name)
+    ref = _ref(name, c["frames"])
+    y = ctx.Render(c["frames"])
+    ctx.Dispose()
+    assert np.abs(y - ref).max() <= 1e-5
+
+
+def test_dump_cases_are_well_formed(tmp_path):
+    """the dump script runs, the case files parse, and the numpy twin agrees with the oracle on every case"""
+    from oracle import ga_oracle as O
+    from oracle import ga_twin as T
+    for name in dump_cases.CASES:
+        if dump_cases.CASES[name]["kind"] == "c5":
+            continue  # (the twin's python resampler loop is slow; it is covered by tests/test_twin_vs_oracle.py)
+        a, c = dump_cases.build_case(O, name)
+        b, _ = dump_cases.build_case(T, name)
+        ya, yb = a.Render(c["frames"]), b.Render(c["frames"])
+        assert np.abs(ya).max() > 1e-3
+        assert np.abs(ya - yb).max() <= 2e-7, (name, np.abs(ya - yb).max())

@@ -341,6 +341,71 @@ __global__ void __launch_bounds__(512, 2) k_biquad_resolve(const BiquadJob* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared-coefficient path.  Voices very often run the SAME filter: one type, one automation table (the engine evaluates
+// identical automation once and hands every voice the same table), the same non-silent range.  The coefficients in force at
+// (channel, frame) then depend on nothing voice-specific, so select / entry / RBJ run ONCE for a representative of the class
+// and the recursion kernel (k_biquad_lanes_shared, biquad_lanes.cu) reads every voice's samples where they lie: the
+// per-voice coefficient streams — 64 of the ~90 bytes the general path moves per voice and frame — are not written at all.
+//
+// Class stream, per chunk of kBqChunkFrames = 64 frames (one contiguous block a stage of the recursion kernel copies):
+//   float2 A[2 channels][66]  (a1, a2)       float4 B[2 channels][65]  (b0, b1, b2, -)        (66 / 65: channel 1 sits four banks
+//   behind channel 0, so that the two addresses a warp reads at one frame never collide; A is read two frames at a time)
+__global__ void __launch_bounds__(kBqChunkFrames) k_biquad_class_coef(const BiquadJob* __restrict__ reps, int sample_rate, int64_t n_quanta,
+                                                                      int64_t n_frames, const int32_t* __restrict__ ent_base,
+                                                                      unsigned char* __restrict__ cs, size_t cs_stride) {
+  const int cls = blockIdx.y;
+  const int64_t chunk = blockIdx.x;
+  const int i = threadIdx.x;
+  const int64_t n = chunk * kBqChunkFrames + i;
+  const BiquadJob& job = reps[cls];
+  const float nyq = (float)sample_rate / 2.f;
+  Coef c0, c1;
+  c0.b0 = c0.b1 = c0.b2 = c0.a1 = c0.a2 = 0.f;
+  c1 = c0;
+  if (n >= job.lo && n < job.hi) {
+    int32_t k0 = job.idx[n], k1 = job.idx[n_frames + n];
+    if (k0 < 0) k0 = ent_base[((size_t)cls * 2 + 0) * n_quanta + (n >> 7)];
+    if (k1 < 0) k1 = ent_base[((size_t)cls * 2 + 1) * n_quanta + (n >> 7)];
+    if (k0 >= 0) c0 = rbj(job.type, clamped_freq(job, k0, nyq), clamped_q(job, k0), job.gain ? job.gain[k0 >> 7] : job.gain_const, sample_rate);
+    c1 = c0;
+    if (k1 != k0 && k1 >= 0) c1 = rbj(job.type, clamped_freq(job, k1, nyq), clamped_q(job, k1), job.gain ? job.gain[k1 >> 7] : job.gain_const, sample_rate);
+  }
+  unsigned char* blk = cs + (size_t)cls * cs_stride + (size_t)chunk * kBqChunkBytes;
+  float2* A = reinterpret_cast<float2*>(blk);
+  float4* B = reinterpret_cast<float4*>(blk + kBqChunkABytes);
+  A[i] = make_float2(c0.a1, c0.a2);
+  A[kBqChunkFrames + 2 + i] = make_float2(c1.a1, c1.a2);
+  B[i] = make_float4(c0.b0, c0.b1, c0.b2, 0.f);
+  B[kBqChunkFrames + 1 + i] = make_float4(c1.b0, c1.b1, c1.b2, 0.f);
+}
+
+// frames outside a voice's non-silent range: the node's output block is cleared there (:103-108); the recursion kernel only
+// writes inside the range
+__global__ void __launch_bounds__(256) k_biquad_zero_outside(const BiquadJob* __restrict__ jobs, int64_t n_frames) {
+  const BiquadJob& job = jobs[blockIdx.y >> 1];
+  float* __restrict__ row = job.sig[blockIdx.y & 1];
+  // the CTAs of a row walk the frames OUTSIDE [lo, hi) only: [0, lo) then [hi, n_frames)  (ranges are multiples of 128 frames)
+  const int64_t n_out = job.lo + (n_frames - job.hi);
+  for (int64_t e = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; e < n_out; e += (int64_t)gridDim.x * 1024) {
+    const int64_t n4 = e < job.lo ? e : job.hi + (e - job.lo);
+    *reinterpret_cast<float4*>(row + n4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+void launch_biquad_classes(const BiquadJob* d_reps, int n_classes, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last, int32_t* d_ent,
+                           int* d_wide_scratch, unsigned char* d_cs, size_t cs_stride, cudaStream_t s) {
+  if (n_classes <= 0 || n_frames <= 0) return;
+  cudaMemsetAsync(d_wide_scratch, 0, sizeof(int) * ((n_classes + 15) / 16), s);
+  k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_classes), kSelWarps * 32, 0, s>>>(d_reps, sample_rate, n_quanta, n_frames, d_last, d_wide_scratch);
+  k_biquad_entry<<<(unsigned)n_classes, 32, 0, s>>>(n_classes, n_quanta, d_last, d_ent);
+  k_biquad_class_coef<<<dim3((unsigned)(n_frames / kBqChunkFrames), (unsigned)n_classes), kBqChunkFrames, 0, s>>>(d_reps, sample_rate, n_quanta, n_frames, d_ent, d_cs, cs_stride);
+}
+void launch_biquad_zero_outside(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  k_biquad_zero_outside<<<dim3(16, (unsigned)(2 * n_jobs)), 256, 0, s>>>(d_jobs, n_frames);
+}
+
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
                    int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_flags, cudaStream_t s) {
   if (n_jobs <= 0 || n_frames <= 0) return;

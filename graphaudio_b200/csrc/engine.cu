@@ -1703,54 +1703,127 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     // ---------------- BiQuadFilterNode (K2 + K3)
     TRACE_MARK("chain position: before biquads");
     if (!biquads.empty()) {
+      // parameter tables and jobs for every filter of this position
+      std::vector<ParamJob> pj;
+      std::vector<BiquadJob> all(biquads.size());
+      for (size_t k = 0; k < biquads.size(); k++) {
+        Sig& s = sigs[biquads[k]];
+        s.ch = 2;
+        const OpH& op = (*s.ops)[pos];
+        BiquadJob j{};
+        if (s.lazy[0]) {  // a rate-1 source feeds this filter directly: its frames are read where they lie, no source copy was made
+          j.in[0] = s.lazy[0];
+          j.in[1] = s.lazy[1];
+          s.lazy[0] = s.lazy[1] = nullptr;  // the filter's output is written to the signal's own rows
+        }
+        float *tf = nullptr, *tq = nullptr, *tg = nullptr;
+        int rc;
+        if ((rc = param_table(env, op.p0, true, pj, &tf))) return rc;
+        if ((rc = param_table(env, op.p1, true, pj, &tq))) return rc;
+        if ((rc = param_table(env, op.p2, false, pj, &tg))) return rc;
+        j.sig[0] = s.p[0];
+        j.sig[1] = s.p[1];
+        j.freq = tf;
+        j.q = tq;
+        j.gain = tg;
+        j.freq_const = op.p0.value;
+        j.q_const = op.p1.value;
+        j.gain_const = op.p2.value;
+        j.type = op.ftype;
+        j.lo = s.lo;
+        j.hi = s.hi;
+        all[k] = j;
+      }
+      TRACE_MARK("biquad: jobs built");
+      int rc = run_param_jobs(env, pj);
+      if (rc) return rc;
+      TRACE_MARK("biquad: params queued");
+      // Classes: filters with the same type, the same parameter tables / constants and the same non-silent range compute the same
+      // coefficients at every (channel, frame).  A class of at least kSharedMin voices whose input rows are 16-byte aligned takes the
+      // shared-coefficient path (biquad.cu); everything else the general one.
+      constexpr size_t kSharedMin = 4;
+      typedef std::tuple<int, const float*, const float*, const float*, float, float, float, int64_t, int64_t> ClassKey;
+      std::map<ClassKey, std::vector<size_t>> classes;
+      std::vector<size_t> general;
+      for (size_t k = 0; k < all.size(); k++) {
+        const BiquadJob& j = all[k];
+        const float* x0 = j.in[0] ? j.in[0] : j.sig[0];
+        const float* x1 = j.in[1] ? j.in[1] : j.sig[1];
+        const bool aligned = reinterpret_cast<uintptr_t>(x0) % 16 == 0 && reinterpret_cast<uintptr_t>(x1) % 16 == 0;
+        if (!aligned || j.hi <= j.lo || getenv("GAC_BIQUAD_GENERAL")) {
+          general.push_back(k);
+          continue;
+        }
+        classes[ClassKey(j.type, j.freq, j.q, j.gain, j.freq_const, j.q_const, j.gain_const, j.lo, j.hi)].push_back(k);
+      }
+      auto& sj = env.keep->make<BiquadJob>();   // jobs of the shared path, class after class
+      auto& reps = env.keep->make<BiquadJob>();  // one representative per class
+      auto& groups = env.keep->make<BqGroup>();
+      for (auto& kv : classes) {
+        if (kv.second.size() < kSharedMin) {
+          general.insert(general.end(), kv.second.begin(), kv.second.end());
+          continue;
+        }
+        const int cls = (int)reps.size();
+        reps.push_back(all[kv.second[0]]);
+        for (size_t m0 = 0; m0 < kv.second.size(); m0 += 16) {
+          const size_t cnt = std::min<size_t>(16, kv.second.size() - m0);
+          groups.push_back(BqGroup{(int)sj.size(), (int)cnt, cls});
+          for (size_t m = 0; m < cnt; m++) sj.push_back(all[kv.second[m0 + m]]);
+        }
+      }
+      if (!sj.empty()) {
+        const int n_cls = (int)reps.size(), n_groups = (int)groups.size();
+        const size_t cs_stride = (size_t)(env.Npad / kBqChunkFrames) * kBqChunkBytes;
+        int32_t *idx = nullptr, *dlast = nullptr, *dent = nullptr;
+        int* dwide = nullptr;
+        unsigned char* dcs = nullptr;
+        if ((rc = env.scratch->alloc(&idx, (size_t)n_cls * 2 * (size_t)env.Npad))) return rc;
+        if ((rc = env.scratch->alloc(&dlast, (size_t)n_cls * 2 * (size_t)env.NQ))) return rc;
+        if ((rc = env.scratch->alloc(&dent, (size_t)n_cls * 2 * (size_t)env.NQ))) return rc;
+        if ((rc = env.scratch->alloc(&dwide, (size_t)n_cls))) return rc;
+        if ((rc = env.scratch->alloc(&dcs, (size_t)n_cls * cs_stride))) return rc;
+        for (int c = 0; c < n_cls; c++) reps[c].idx = idx + (size_t)c * 2 * (size_t)env.Npad;
+        BiquadJob *dreps = nullptr, *dsj = nullptr;
+        BqGroup* dgroups = nullptr;
+        if ((rc = env.scratch->upload(&dreps, reps))) return rc;
+        if ((rc = env.scratch->upload(&dsj, sj))) return rc;
+        if ((rc = env.scratch->upload(&dgroups, groups))) return rc;
+        size_t n_f2 = 0, n_i = 0;
+        biquad_shared_scratch_sizes(n_groups, env.Npad, &n_f2, &n_i);
+        float2* dstates = nullptr;
+        int* dflags = nullptr;
+        if ((rc = env.scratch->alloc(&dstates, n_f2))) return rc;
+        if ((rc = env.scratch->alloc(&dflags, n_i))) return rc;
+        int t = env.timer->begin(C_BIQUAD);
+        launch_biquad_classes(dreps, n_cls, env.Npad, env.NQ, ctx->fs, dlast, dent, dwide, dcs, cs_stride, ctx->stream);
+        bool partial = false;
+        for (const BiquadJob& j : sj) partial = partial || j.lo > 0 || j.hi < env.Npad;
+        if (partial) launch_biquad_zero_outside(dsj, (int)sj.size(), env.Npad, ctx->stream);
+        launch_biquad_lanes_shared(dsj, dgroups, n_groups, dcs, cs_stride, env.Npad, dstates, dflags, ctx->stream);
+        env.timer->end(t);
+        env.launches += 4 + (partial ? 1 : 0) + (biquad_shared_segments(n_groups, env.Npad, nullptr) > 1 ? 2 : 0);
+        CU(cudaGetLastError());
+        TRACE_MARK("biquad (shared coefficients): queued");
+      }
       const size_t per_job = (size_t)env.Npad * (2 * (4 + 16 + 16) + 4 + 4) + (size_t)env.NQ * (16 + 4);
       const size_t max_jobs = std::min<size_t>(65535, std::max<size_t>(1, ctx->scratch_budget / per_job));
-      for (size_t k0 = 0; k0 < biquads.size(); k0 += max_jobs) {
-        const size_t nk = std::min(max_jobs, biquads.size() - k0);
-        std::vector<ParamJob> pj;
+      for (size_t k0 = 0; k0 < general.size(); k0 += max_jobs) {
+        const size_t nk = std::min(max_jobs, general.size() - k0);
         auto& bj = env.keep->make<BiquadJob>();
         int32_t* idx_all = nullptr;
         float4 *s1_all = nullptr, *s2_all = nullptr;
         {
-          int rc;
           const size_t rows = ((nk + 15) / 16) * 32;  // slab-transposed streams cover whole 32-row groups
           if ((rc = env.scratch->alloc(&idx_all, nk * 2 * (size_t)env.Npad))) return rc;
           if ((rc = env.scratch->alloc(&s1_all, rows * (size_t)env.Npad))) return rc;
           if ((rc = env.scratch->alloc(&s2_all, rows * (size_t)env.Npad))) return rc;
         }
         for (size_t k = 0; k < nk; k++) {
-          Sig& s = sigs[biquads[k0 + k]];
-          s.ch = 2;
-          const OpH& op = (*s.ops)[pos];
-          BiquadJob j{};
-          if (s.lazy[0]) {  // a rate-1 source feeds this filter directly: its frames are read where they lie, no source copy was made
-            j.in[0] = s.lazy[0];
-            j.in[1] = s.lazy[1];
-            s.lazy[0] = s.lazy[1] = nullptr;  // the filter's output is written to the signal's own rows
-          }
-          float *tf = nullptr, *tq = nullptr, *tg = nullptr;
-          int rc;
-          if ((rc = param_table(env, op.p0, true, pj, &tf))) return rc;
-          if ((rc = param_table(env, op.p1, true, pj, &tq))) return rc;
-          if ((rc = param_table(env, op.p2, false, pj, &tg))) return rc;
-          j.sig[0] = s.p[0];
-          j.sig[1] = s.p[1];
-          j.freq = tf;
-          j.q = tq;
-          j.gain = tg;
-          j.freq_const = op.p0.value;
-          j.q_const = op.p1.value;
-          j.gain_const = op.p2.value;
-          j.type = op.ftype;
-          j.lo = s.lo;
-          j.hi = s.hi;
+          BiquadJob j = all[general[k0 + k]];
           j.idx = idx_all + k * 2 * (size_t)env.Npad;
           bj.push_back(j);
         }
-        TRACE_MARK("biquad: jobs built");
-        int rc = run_param_jobs(env, pj);
-        if (rc) return rc;
-        TRACE_MARK("biquad: params queued");
         BiquadJob* dbj = nullptr;
         int32_t *dlast = nullptr, *dent = nullptr;
         if ((rc = env.scratch->upload(&dbj, bj))) return rc;

@@ -231,6 +231,26 @@ void biquad_scratch_sizes(int n_jobs, int64_t n_frames, size_t* n_float2, size_t
 void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last,
                    int32_t* d_ent, float4* d_s1t, float4* d_s2t, float2* d_states, int* d_flags, cudaStream_t s);
 
+// ---- shared-coefficient path (voices of a class run the same filter automation over the same non-silent range: biquad.cu)
+constexpr int kBqChunkFrames = 64;                                               // frames per class-stream chunk
+constexpr int kBqChunkABytes = 2 * (kBqChunkFrames + 2) * 8;                     // (a1, a2) of both channels (channel stride 66: 16-byte aligned, 4 banks apart)
+constexpr int kBqChunkBytes = kBqChunkABytes + 2 * (kBqChunkFrames + 1) * 16;    // + (b0, b1, b2, -): one chunk (3120 bytes)
+// select / entry / RBJ for one representative job per class -> class streams d_cs[class * cs_stride + chunk * kBqChunkBytes]
+// (n_frames multiple of 128; chunk = kBqChunkFrames frames).  d_last, d_ent: int32 [n_classes][2][n_quanta]; reps[c].idx: int32 [2][n_frames];
+// d_wide_scratch: int [ceil(n_classes / 16)]
+void launch_biquad_classes(const BiquadJob* d_reps, int n_classes, int64_t n_frames, int64_t n_quanta, int sample_rate, int32_t* d_last, int32_t* d_ent,
+                           int* d_wide_scratch, unsigned char* d_cs, size_t cs_stride, cudaStream_t s);
+void launch_biquad_zero_outside(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
+// the recursion over groups of up to 16 jobs that all belong to one class; input rows 16-byte aligned, read in place.
+// d_states / d_flags sized by biquad_shared_scratch_sizes
+struct BqGroup {
+  int first, count, cls;  // jobs [first, first + count) of the job array, class stream index
+};
+int biquad_shared_segments(int n_groups, int64_t n_frames, int* seg_chunks);
+void biquad_shared_scratch_sizes(int n_groups, int64_t n_frames, size_t* n_float2, size_t* n_int);
+void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups, int n_groups, const unsigned char* d_cs, size_t cs_stride,
+                                int64_t n_frames, float2* d_states, int* d_flags, cudaStream_t s);
+
 // K3d alone (biquad_lanes.cu): the recursion over the slab-transposed streams, TMA-fed
 void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,
                          int* d_flags, cudaStream_t s);

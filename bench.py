@@ -7,12 +7,13 @@
 Metric: voice-seconds rendered per second (= voices x rendered seconds / render time); realtime factor = rendered
 seconds / render time.
 
-Workload (default `c3` = BASELINE.json configs[2], the north-star target): 1024 voices, each
+Workload (default `c3` = BASELINE.json configs[2], the north-star target): 128 voices PER GPU, each
 AudioBufferSourceNode(stereo 10 s) -> BiQuadFilterNode(lowpass, a-rate cutoff sweep) -> GainNode(a-rate automation) ->
-ConvolverNode(per-voice 2 s stereo IR) -> bus GainNode(1/32) -> destination, 12 s rendered at 48 kHz.  The 1024 voices are
-sharded over the N ranks (STRONG scaling: total work fixed; N = 1 renders all 1024 on one GPU, N = 8 is BASELINE configs[2]
-as written: 128 voices per GPU), ONE ncclReduce(sum) of the [2, frames] float32 bus to rank 0 per render — the only exchange
-step of the path — and the bus gain on the root behind it.  `--workload c2` is BASELINE configs[1] (64 voices per GPU, weak).
+ConvolverNode(per-voice 2 s stereo IR) -> bus GainNode(1/32) -> destination, 12 s rendered at 48 kHz.  The voices are independent
+until the bus, so the path shards by voice with no data-path collective but ONE ncclReduce(sum) of the [2, frames] float32 bus
+to rank 0 per render, the bus gain on the root behind it: WEAK scaling, per-GPU work fixed — at N = 8 the job is BASELINE
+configs[2] exactly as written (1024 voices on 8 GPUs), at N = 1 it is one GPU's share of it.  `--voices 1024` renders the whole
+config on one GPU (it fits); `--workload c2` is BASELINE configs[1] (64 voices per GPU).
 
 A "step" is one complete render of the workload.
   value  = device time of gac_render_sharded at EVERY N (N = 1 included: same entry point, same D2H of the 4.6 MB result into
@@ -55,9 +56,10 @@ from graphaudio_b200 import sharding  # noqa: E402
 FS = 48000
 WORKLOADS = {
     # total_voices: sharded over the ranks (strong scaling); voices_per_gpu: fixed per rank (weak scaling)
-    "c3": dict(total_voices=1024, src_s=10.0, ir_s=2.0, render_s=12.0, bus_gain=1.0 / 32, kind="c3", scaling="strong",
-               desc="C3 (BASELINE configs[2]): 1024 voices x (stereo 10 s noise -> BiQuadFilterNode lowpass, a-rate cutoff 2 -> 12 kHz -> GainNode a-rate "
-                    "automation -> ConvolverNode 2 s stereo IR per voice) -> bus GainNode(1/32), 12 s @ 48 kHz, voices sharded over the GPUs, one ncclReduce"),
+    "c3": dict(voices_per_gpu=128, src_s=10.0, ir_s=2.0, render_s=12.0, bus_gain=1.0 / 32, kind="c3", scaling="weak",
+               desc="C3 (BASELINE configs[2], the north-star config: 1024 voices on 8 GPUs = 128 voices per GPU): per voice stereo 10 s noise -> "
+                    "BiQuadFilterNode lowpass, a-rate cutoff 2 -> 12 kHz -> GainNode a-rate automation -> ConvolverNode 2 s stereo IR per voice; bus "
+                    "GainNode(1/32), 12 s @ 48 kHz; voices sharded over the GPUs, one ncclReduce of the bus"),
     "c2": dict(voices_per_gpu=64, src_s=10.0, ir_s=2.0, render_s=12.0, bus_gain=1.0 / 8, kind="c2", scaling="weak",
                desc="C2 (BASELINE configs[1]): 64 voices per GPU x (stereo 10 s noise -> GainNode a-rate automation -> ConvolverNode 2 s stereo IR per voice) "
                     "-> bus GainNode(1/8), 12 s @ 48 kHz"),

@@ -106,6 +106,11 @@ SIGNATURES = {
     "gac_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "gac_comm_destroy": (C.c_int, [C.c_void_p]),
     "gac_render_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, fpp, C.c_int]),
+    "gac_group_create": (C.c_int, [C.POINTER(gac_context_desc), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "gac_group_destroy": (C.c_int, [C.c_void_p]),
+    "gac_group_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "gac_group_context": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "gac_group_render": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64, C.c_int64, fpp, C.c_int, C.c_int64]),
     "gac_get_stats": (C.c_int, [C.c_void_p, C.POINTER(gac_stats)]),
     "gac_rfft_fwd_batch": (C.c_int, [C.c_void_p, fp, C.c_int, C.c_int64, fp]),
     "gac_spectral_mac": (C.c_int, [C.c_void_p, fp, fp, C.c_int, C.c_int64, C.c_int, C.c_int, fp]),

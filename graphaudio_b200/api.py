@@ -151,21 +151,24 @@ class PlayableAudioBuffer:
             raise ArgumentException("Left and right channels must have the same length")
         return PlayableAudioBuffer([leftChannel, rightChannel], sampleRate)
 
-    def _handle(self, ctx: "OfflineAudioContext"):
+    def _handle(self, ctx: "OfflineAudioContext", member: int = 0):
+        """Device copy of the buffer in `ctx` (member `member` of a multi-GPU context)."""
         ctx = ctx._root()  # forks share the parent's device handle
         # keyed by the context's serial number, never by id(): CPython reuses ids, and a disposed context's handles are freed
-        h = self._handles.get(ctx._serial)
+        key = (ctx._serial, member)
+        h = self._handles.get(key)
         if h is None:
             out = C.c_void_p()
+            ch = ctx._member_handle(member)
             if self._raw is not None:
                 raw, fmt = self._raw
-                check(N.lib().gac_buffer_create_interleaved(ctx._h, raw.ctypes.data_as(C.c_void_p), fmt, self.NumberOfChannels, self.Length,
+                check(N.lib().gac_buffer_create_interleaved(ch, raw.ctypes.data_as(C.c_void_p), fmt, self.NumberOfChannels, self.Length,
                                                             self.SampleRate, C.byref(out)))
             else:
                 ptrs = (N.fp * self.NumberOfChannels)(*[_fptr(c) for c in self.channels])
-                check(N.lib().gac_buffer_create(ctx._h, ptrs, self.NumberOfChannels, self.Length, self.SampleRate, C.byref(out)))
+                check(N.lib().gac_buffer_create(ch, ptrs, self.NumberOfChannels, self.Length, self.SampleRate, C.byref(out)))
             h = out.value
-            self._handles[ctx._serial] = h
+            self._handles[key] = h
             ctx._owned_buffers.append(h)
             ctx._buffer_objects.append(self)
         return h
@@ -335,7 +338,8 @@ class AudioBufferSourceNode(AudioNode):
     def Buffer(self, value):
         self._buffer = value
         # upload now rather than at Render: with async_upload the copy engine works while the rest of the graph is built
-        if value is not None and not self.Context._record_only and self.Context._h is not None:
+        # (a multi-GPU context uploads at Render, when it knows which device renders the voice)
+        if value is not None and not self.Context._record_only and self.Context._h is not None and self.Context._root()._group is None:
             value._handle(self.Context)
 
     @property
@@ -471,6 +475,8 @@ class ConvolverNode(AudioNode):
         self.EnableTrueStereo = True   # :95
         self._buffer = None
         self._ir = None
+        self._ir_args = (1, 1)
+        self._ir_members = {}          # member index -> prepared impulse response (multi-GPU contexts)
 
     @property
     def Buffer(self):
@@ -493,10 +499,28 @@ class ConvolverNode(AudioNode):
         if ctx._record_only:
             self._buffer, self._ir = value, None
             return
+        self._ir_args = (int(self.Normalize), int(self.EnableTrueStereo))  # the convolvers are built with the values of THIS moment
+        self._ir_members = {}
+        if ctx._root()._group is not None:  # multi-GPU context: prepared per member at Render (on the device that renders the voice)
+            self._buffer, self._ir = value, None
+            return
+        self._buffer, self._ir = value, self._ir_for(0, value)
+
+
+def _convolver_ir_for(self, member, buffer=None):
+    """The prepared impulse response of this ConvolverNode in member `member` of its context (prepared on first use)."""
+    buffer = buffer if buffer is not None else self._buffer
+    h = self._ir_members.get(member)
+    if h is None:
+        ctx = self.Context
         out = C.c_void_p()
-        check(N.lib().gac_ir_prepare(ctx._h, value._handle(ctx), int(self.Normalize), int(self.EnableTrueStereo), C.byref(out)))
-        ctx._owned_irs.append(out.value)
-        self._buffer, self._ir = value, out.value
+        check(N.lib().gac_ir_prepare(ctx._root()._member_handle(member), buffer._handle(ctx, member), self._ir_args[0], self._ir_args[1], C.byref(out)))
+        ctx._root()._owned_irs.append(out.value)
+        h = self._ir_members[member] = out.value
+    return h
+
+
+ConvolverNode._ir_for = _convolver_ir_for
 
 
 class CudaConvolverNode:
@@ -579,7 +603,7 @@ class OfflineAudioContext:
     """OfflineAudioContext.cs — `Render` is the one call that crosses into libgraphaudio_cuda.so."""
 
     def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32, async_upload=False,
-                 uniform_segments=False, _record_only=False):
+                 uniform_segments=False, device_ids=None, _record_only=False):
         """partition / device_id / mac_variant / tile_blocks map onto gac_context_desc.  `_record_only=True` builds a context
         without a device handle: nodes, automation and topology can be recorded and inspected (`_topology()`), Render raises.
         It exists for the CPU unit tests of the host-side logic; it is not a fallback."""
@@ -594,6 +618,8 @@ class OfflineAudioContext:
         self._owned_irs: List[int] = []
         self._owned_convolvers: List[int] = []
         self._record_only = bool(_record_only)
+        self._group = None       # gac_group handle of a context that spans several GPUs (device_ids=[...])
+        self._members = None     # its member gac_context handles
         if not self._record_only:
             desc = N.gac_context_desc()
             desc.sample_rate, desc.quantum, desc.partition, desc.device_id, desc.mac_variant = self.SampleRate, 128, partition, device_id, mac_variant
@@ -602,11 +628,27 @@ class OfflineAudioContext:
             # to PlayableAudioBuffer must then stay untouched until Render returns
             desc.flags = (N.GAC_FLAG_ASYNC_UPLOAD if async_upload else 0) | (N.GAC_FLAG_UNIFORM_SEGMENTS if uniform_segments else 0)
             out = C.c_void_p()
-            check(N.lib().gac_context_create(C.byref(desc), C.byref(out)))
-            self._h = out.value
+            if device_ids is not None:
+                # ONE OfflineAudioContext over several GPUs of this process: voices -> bus -> destination graphs
+                # are sharded by voice over the members at Render, anything else renders on member 0
+                ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+                check(N.lib().gac_group_create(C.byref(desc), ids, len(device_ids), C.byref(out)))
+                self._group = out.value
+                self._members = []
+                for i in range(len(device_ids)):
+                    m = C.c_void_p()
+                    check(N.lib().gac_group_context(self._group, i, C.byref(m)))
+                    self._members.append(m.value)
+                self._h = self._members[0]
+            else:
+                check(N.lib().gac_context_create(C.byref(desc), C.byref(out)))
+                self._h = out.value
         self.Destination = AudioDestinationNode(self)
         self._frames_rendered = 0
         self.last_stats = None
+
+    def _member_handle(self, member=0):
+        return self._members[member] if self._members else self._h
 
     # ---- graph flattening: destination <- (bus chain <- fan-in)? <- voice chain <- source
     def _q_now(self):
@@ -620,7 +662,7 @@ class OfflineAudioContext:
             t = t + inc
         return t
 
-    def _op_desc(self, node, keep):
+    def _op_desc(self, node, keep, member=0):
         op = N.gac_op_desc()
         q = self._q_now()
         if isinstance(node, BiQuadFilterNode):
@@ -631,7 +673,7 @@ class OfflineAudioContext:
             op.p0 = node.Gain._desc(keep, q)
         elif isinstance(node, ConvolverNode):
             op.kind = N.GAC_OP_CONVOLVER
-            op.ir = node._ir
+            op.ir = node._ir if (member == 0 and node._ir is not None) else (node._ir_for(member) if node._buffer is not None else None)
         elif isinstance(node, DelayNode):
             op.kind, op.aux = N.GAC_OP_DELAY, node.MaxDelayTime
             op.p0 = node.DelayTime._desc(keep, q)
@@ -769,13 +811,19 @@ class OfflineAudioContext:
         voices, buses, dest_inputs, _, _ = self._topology_full()
         return voices, buses, dest_inputs
 
-    def _flatten(self):
+    def _flatten(self, member=0, voice_range=None):
+        """gac_graph_desc of the recorded graph for member `member`; voice_range = (lo, hi) keeps only those source-fed voices (a
+        shard of a flat graph: the buses are described in full on every member)."""
         if getattr(self, "_unsupported_edit", None):
             raise NotSupportedException(
                 f"{self._unsupported_edit}: successive Render calls re-render the timeline on the device, which is exact for parameter "
                 "edits, for sources started or stopped in between and for new branches, not for re-wiring what was already rendered")
         keep = []
         voices, buses, dest_inputs, bus_targets, bus_inputs = self._topology_full()
+        if voice_range is not None:
+            lo, hi = voice_range
+            voices = voices[lo:hi]
+            bus_inputs = [[] for _ in buses]  # (default order: the shard's voices in index order)
         vdesc = (N.gac_voice_desc * max(1, len(voices)))()
         for i, (src, ops, bus, input_bus) in enumerate(voices):
             v = vdesc[i]
@@ -787,18 +835,18 @@ class OfflineAudioContext:
                     if src._start_frames > 0:  # started between Render calls: not before the first quantum that was still unprocessed
                         when = max(when, self._block_time(-(-src._start_frames // 128)))
                 v.loop, v.loop_start, v.loop_end = int(bool(src.Loop)), src.LoopStart, src.LoopEnd
-                v.source = src.Buffer._handle(self) if src.Buffer is not None else None
+                v.source = src.Buffer._handle(self, member) if src.Buffer is not None else None
                 v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop
                 v.playback_rate = src.PlaybackRate.Value
             else:
                 v.source = None
                 v.playback_rate = 1.0
-            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep) for o in ops])
+            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep, member) for o in ops])
             keep.append(arr)
             v.n_ops, v.ops, v.bus, v.input = len(ops), arr, bus, input_bus + 1
         bdesc = (N.gac_bus_desc * max(1, len(buses)))()
         for i, ops in enumerate(buses):
-            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep) for o in ops])
+            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep, member) for o in ops])
             inp = (C.c_int32 * max(1, len(bus_inputs[i])))(*bus_inputs[i])
             keep += [arr, inp]
             bdesc[i].n_ops, bdesc[i].ops = len(ops), arr
@@ -810,11 +858,42 @@ class OfflineAudioContext:
         keep += [vdesc, bdesc, darr]
         return g, keep
 
-    def _graph(self):
-        g, keep = self._flatten()
+    def _graph(self, member=0, voice_range=None):
+        g, keep = self._flatten(member, voice_range)
         out = C.c_void_p()
-        check(N.lib().gac_graph_create(self._h, C.byref(g), C.byref(out)))
+        check(N.lib().gac_graph_create(self._member_handle(member), C.byref(g), C.byref(out)))
         return out.value
+
+    def _shardable(self):
+        """True when the recorded graph is voices -> ONE bus -> destination with every voice fed by a source: the shape whose
+        voices a multi-GPU context spreads over its members (the bus is what the single ncclReduce sums)."""
+        voices, buses, dest_inputs, bus_targets, _ = self._topology_full()
+        return (len(buses) == 1 and bus_targets[0] == 0 and list(dest_inputs) == [0] and len(voices) > 0
+                and all(src is not None and bus == 0 and input_bus < 0 for src, _, bus, input_bus in voices))
+
+    def _render_group(self, rows, frameCount, startIndex):
+        """Render of a multi-GPU context: contiguous voice ranges per member, one gac_group_render call."""
+        from . import sharding
+        L = N.lib()
+        M = len(self._members)
+        nv = len(self._topology_full()[0])
+        graphs = []
+        try:
+            for m in range(M):
+                graphs.append(self._graph(m, sharding.shard_range(nv, m, M)))
+            garr = (C.c_void_p * M)(*graphs)
+            ptrs = (N.fp * len(rows))(*[_fptr(r) for r in rows])
+            check(L.gac_group_render(self._group, garr, self._frames_rendered, int(frameCount), ptrs, len(rows), int(startIndex)))
+            self._frames_rendered += int(frameCount)
+            self.last_stats_members = []
+            for m in range(M):
+                st = N.gac_stats()
+                check(L.gac_get_stats(self._members[m], C.byref(st)))
+                self.last_stats_members.append(st.as_dict())
+            self.last_stats = self.last_stats_members[0]
+        finally:
+            for g in graphs:
+                L.gac_graph_destroy(g)
 
     def Render(self, output_or_count, frameCount=None, startIndex=0):
         """Render(float[][] output, int frameCount, int startIndex = 0)  (OfflineAudioContext.cs:30)
@@ -845,6 +924,8 @@ class OfflineAudioContext:
                 raise ArgumentException("channel buffers must be contiguous float32")
             if r.shape[0] < startIndex + frameCount:
                 raise ArgumentException(f"Channel {c} buffer is too small. Required: {startIndex + frameCount}, Available: {r.shape[0]}")
+        if self._group is not None and self._shardable():
+            return self._render_group(rows, frameCount, startIndex)
         graph = self._graph()
         try:
             ptrs = (N.fp * len(rows))(*[_fptr(r) for r in rows])
@@ -920,6 +1001,7 @@ class OfflineAudioContext:
         handle.  Used with RenderBatch; disposing the parent disposes the shared handle."""
         child = OfflineAudioContext.__new__(OfflineAudioContext)
         child._h = self._h
+        child._group, child._members = None, None  # (forks record against member 0)
         child._serial = self._serial
         child._buffer_objects = self._buffer_objects
         child.SampleRate = self.SampleRate
@@ -952,9 +1034,14 @@ class OfflineAudioContext:
             for h in self._owned_buffers:
                 L.gac_buffer_destroy(h)
             for b in self._buffer_objects:
-                b._handles.pop(self._serial, None)
+                for key in [k for k in b._handles if k[0] == self._serial]:
+                    b._handles.pop(key, None)
             self._buffer_objects = []
-            L.gac_context_destroy(self._h)
+            if self._group is not None:
+                L.gac_group_destroy(self._group)  # destroys the member contexts
+                self._group, self._members = None, None
+            else:
+                L.gac_context_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <memory>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 

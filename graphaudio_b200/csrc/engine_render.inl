@@ -241,6 +241,9 @@ struct NcclApi {
   int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
 };
 static NcclApi* nccl_api() {
   static NcclApi api;
@@ -258,6 +261,9 @@ static NcclApi* nccl_api() {
       api.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclReduce");
       api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
       api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+      api.CommInitAll = (int (*)(void**, int, const int*))dlsym(api.lib, "ncclCommInitAll");
+      api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
+      api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
     }
   }
   if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.Reduce || !api.CommDestroy) return nullptr;
@@ -828,6 +834,144 @@ extern "C" int gac_render_sharded(gac_context* ctx, const gac_graph* shard, int6
   a.sharded = true;
   a.root = root;
   return render_core(ctx, a);
+}
+
+// ------------------------------------------------------------------------------------------ one process, several GPUs
+// The reference's caller is ONE process holding ONE OfflineAudioContext (OfflineAudioContext.cs:18).  A gac_group is that context
+// spread over several GPUs of the box: one member gac_context (own stream, own scratch arena) per device, one NCCL communicator
+// over the device set (ncclCommInitAll: SURVEY.md §8e), voices sharded over the members by the host mirror.  gac_group_render
+// runs the members' shards concurrently — one host thread per device, because a render is synchronous and the single
+// ncclReduce of the bus needs every rank inside it at the same time — and the root member (index 0) delivers the result.
+struct gac_group {
+  uint32_t magic = 0x47414347;  // "GACG"
+  std::vector<gac_context*> members;
+};
+static bool group_ok(gac_group* g) { return g && g->magic == 0x47414347; }
+
+extern "C" int gac_group_destroy(gac_group* grp);
+extern "C" int gac_group_create(const gac_context_desc* desc, const int* device_ids, int n_devices, gac_group** out) {
+  if (!desc || !out || !device_ids) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (n_devices < 1 || n_devices > 64) return fail(GAC_ERR_OUT_OF_RANGE, "n_devices must be in 1 .. 64");
+  for (int i = 0; i < n_devices; i++)
+    for (int k = 0; k < i; k++)
+      if (device_ids[i] == device_ids[k]) return fail(GAC_ERR_INVALID_ARGUMENT, "device %d listed twice", device_ids[i]);
+  auto grp = std::make_unique<gac_group>();
+  for (int i = 0; i < n_devices; i++) {
+    gac_context_desc d = *desc;
+    d.device_id = device_ids[i];
+    gac_context* c = nullptr;
+    int rc = gac_context_create(&d, &c);
+    if (rc) {
+      gac_group* partial = grp.release();
+      gac_group_destroy(partial);
+      return rc;
+    }
+    grp->members.push_back(c);
+  }
+  if (n_devices > 1) {
+    NcclApi* a = nccl_api();
+    if (!a || !a->CommInitAll || !a->GroupStart || !a->GroupEnd) {
+      gac_group_destroy(grp.release());
+      return fail(GAC_ERR_NCCL, "libnccl.so.2 could not be loaded (ncclCommInitAll)");
+    }
+    std::vector<void*> comms((size_t)n_devices, nullptr);
+    int r = a->CommInitAll(comms.data(), n_devices, device_ids);
+    if (r != 0) {
+      gac_group_destroy(grp.release());
+      return nccl_fail(a, r, "ncclCommInitAll");
+    }
+    for (int i = 0; i < n_devices; i++) {
+      grp->members[i]->comm = comms[i];
+      grp->members[i]->rank = i;
+      grp->members[i]->n_ranks = n_devices;
+    }
+    // NCCL connects its channels lazily on the first collective: pay that here, not inside the first render
+    std::vector<float*> warm((size_t)n_devices, nullptr);
+    for (int i = 0; i < n_devices; i++) {
+      gac_context* c = grp->members[i];
+      cudaSetDevice(c->device);
+      cudaMallocAsync(&warm[i], 256 * sizeof(float), c->stream);
+      cudaMemsetAsync(warm[i], 0, 256 * sizeof(float), c->stream);
+    }
+    a->GroupStart();
+    for (int i = 0; i < n_devices; i++) {
+      gac_context* c = grp->members[i];
+      cudaSetDevice(c->device);
+      r = a->Reduce(warm[i], warm[i], 256, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, c->comm, c->stream);
+      if (r != 0) break;
+    }
+    const int r2 = a->GroupEnd();
+    for (int i = 0; i < n_devices; i++) {
+      gac_context* c = grp->members[i];
+      cudaSetDevice(c->device);
+      cudaFreeAsync(warm[i], c->stream);
+      cudaStreamSynchronize(c->stream);
+    }
+    if (r != 0 || r2 != 0) {
+      gac_group_destroy(grp.release());
+      return nccl_fail(a, r != 0 ? r : r2, "ncclReduce (warm-up)");
+    }
+  }
+  *out = grp.release();
+  return GAC_OK;
+}
+extern "C" int gac_group_destroy(gac_group* grp) {
+  if (!group_ok(grp)) return fail(GAC_ERR_INVALID_ARGUMENT, "group is null or already destroyed");
+  for (gac_context* c : grp->members) gac_context_destroy(c);  // (destroys the member's communicator as well)
+  grp->magic = 0;
+  delete grp;
+  return GAC_OK;
+}
+extern "C" int gac_group_size(gac_group* grp, int* n) {
+  if (!group_ok(grp) || !n) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  *n = (int)grp->members.size();
+  return GAC_OK;
+}
+extern "C" int gac_group_context(gac_group* grp, int index, gac_context** ctx) {
+  if (!group_ok(grp) || !ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (index < 0 || index >= (int)grp->members.size()) return fail(GAC_ERR_OUT_OF_RANGE, "member index %d out of range", index);
+  *ctx = grp->members[(size_t)index];
+  return GAC_OK;
+}
+extern "C" int gac_group_render(gac_group* grp, const gac_graph* const* shards, int64_t first_frame, int64_t n_frames, float* const* out_channels,
+                                int n_out_channels, int64_t start_index) {
+  if (!group_ok(grp)) return fail(GAC_ERR_DISPOSED, "group is null or destroyed");
+  if (!shards || !out_channels) return fail(GAC_ERR_INVALID_ARGUMENT, "null argument");
+  const size_t n = grp->members.size();
+  for (size_t i = 0; i < n; i++) {
+    if (!shards[i]) return fail(GAC_ERR_INVALID_ARGUMENT, "shard %zu is null (a member without voices still takes part in the reduce: pass a graph with the bus and no voices)", i);
+    if (shards[i]->ctx != grp->members[i]) return fail(GAC_ERR_INVALID_ARGUMENT, "shard %zu was not created against member %zu", i, i);
+    for (auto& v : shards[i]->voices)
+      if (v.bus < 0) return fail(GAC_ERR_UNSUPPORTED, "sharded renders need every voice routed through a bus (the bus is what is reduced)");
+    if (shards[i]->buses.empty()) return fail(GAC_ERR_UNSUPPORTED, "sharded renders need at least one bus");
+  }
+  auto member_render = [&](size_t i) {
+    RenderArgs a;
+    a.graphs = &shards[i];
+    a.n_graphs = 1;
+    a.first_frame = first_frame;
+    a.n_frames = n_frames;
+    a.h_out = i == 0 ? out_channels : nullptr;
+    a.n_out = n_out_channels;
+    a.start_index = start_index;
+    a.sharded = true;
+    a.root = 0;
+    return render_core(grp->members[i], a);
+  };
+  if (n == 1) return member_render(0);
+  std::vector<int> rcs(n, GAC_OK);
+  std::vector<std::string> msgs(n);
+  std::vector<std::thread> workers;
+  for (size_t i = 0; i < n; i++)
+    workers.emplace_back([&, i] {
+      rcs[i] = member_render(i);
+      if (rcs[i]) msgs[i] = g_err;  // (thread-local: carried over to the caller below)
+    });
+  for (auto& w : workers) w.join();
+  for (size_t i = 0; i < n; i++)
+    if (rcs[i]) return fail(rcs[i], "member %zu (device %d): %s", i, grp->members[i]->device, msgs[i].c_str());
+  return GAC_OK;
 }
 
 extern "C" int gac_get_stats(gac_context* ctx, gac_stats* out) {

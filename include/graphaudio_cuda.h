@@ -275,6 +275,22 @@ int gac_comm_destroy(gac_context* ctx);
 int gac_render_sharded(gac_context* ctx, const gac_graph* shard, int64_t n_frames, int root,
                        float* const* out_channels, int n_out_channels);
 
+/* ---- one process, several GPUs ----
+ * The reference's caller is one process with one OfflineAudioContext (OfflineAudioContext.cs:18).  A gac_group is that context
+ * spread over `n_devices` GPUs of the box: one member gac_context per device (gac_group_context), created from `desc` (its
+ * device_id is ignored), and one NCCL communicator over the device set (ncclCommInitAll).  Buffers, impulse responses and the
+ * shard graphs are created against the member that renders them; gac_group_render runs the members' shards concurrently (one
+ * host thread per device), reduces the buses onto member 0 with the single ncclReduce of gac_render_sharded and fills
+ * out_channels[c][start_index ...] with frames [first_frame, first_frame + n_frames) as gac_render does.  shards[i] belongs to
+ * member i; a member without voices passes a graph that holds the bus only. */
+typedef struct gac_group gac_group;
+int gac_group_create(const gac_context_desc* desc, const int* device_ids, int n_devices, gac_group** out);
+int gac_group_destroy(gac_group* group);
+int gac_group_size(gac_group* group, int* n_members);
+int gac_group_context(gac_group* group, int index, gac_context** member);
+int gac_group_render(gac_group* group, const gac_graph* const* shards, int64_t first_frame, int64_t n_frames,
+                     float* const* out_channels, int n_out_channels, int64_t start_index);
+
 /* ---- statistics of the last render on this context ---- */
 typedef struct gac_stats {
   double ms_total;      /* device time of the whole render (CUDA events on the context stream)      */

@@ -23,7 +23,7 @@ GAC_ERR_NCCL = -8
 GAC_ERR_UNSUPPORTED = -9
 
 GAC_EVENT_EPOCH = 4
-GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER, GAC_OP_DELAY, GAC_OP_PANNER = 1, 2, 3, 4, 5
+GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER, GAC_OP_DELAY, GAC_OP_PANNER, GAC_OP_CHANNEL = 1, 2, 3, 4, 5, 6
 GAC_SAMPLE_S16, GAC_SAMPLE_S24, GAC_SAMPLE_S32, GAC_SAMPLE_F32 = 0, 1, 2, 3
 
 fp = C.POINTER(C.c_float)
@@ -45,7 +45,8 @@ class gac_event(C.Structure):
 
 
 class gac_param(C.Structure):
-    _fields_ = [("value", C.c_float), ("n_events", C.c_int32), ("events", C.POINTER(gac_event))]
+    _fields_ = [("value", C.c_float), ("n_events", C.c_int32), ("events", C.POINTER(gac_event)), ("mod_bus", C.c_int32),
+                ("min_value", C.c_float), ("max_value", C.c_float), ("reserved", C.c_int32)]
 
 
 class gac_op_desc(C.Structure):
@@ -57,12 +58,17 @@ class gac_voice_desc(C.Structure):
     _fields_ = [("source", C.c_void_p), ("start_when", C.c_double), ("start_offset", C.c_double),
                 ("start_duration", C.c_double), ("stop_when", C.c_double), ("playback_rate", C.c_float),
                 ("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc)), ("bus", C.c_int32), ("input", C.c_int32),
-                ("loop", C.c_int32), ("reserved", C.c_int32), ("loop_start", C.c_double), ("loop_end", C.c_double)]
+                ("loop", C.c_int32), ("source_kind", C.c_int32), ("loop_start", C.c_double), ("loop_end", C.c_double),
+                ("source_param", gac_param), ("oscillator_type", C.c_int32), ("reserved", C.c_int32)]
 
 
 class gac_bus_desc(C.Structure):
     _fields_ = [("n_ops", C.c_int32), ("ops", C.POINTER(gac_op_desc)), ("target", C.c_int32), ("n_inputs", C.c_int32),
-                ("inputs", C.POINTER(C.c_int32))]
+                ("inputs", C.POINTER(C.c_int32)), ("flags", C.c_int32), ("reserved", C.c_int32), ("input_slots", C.POINTER(C.c_int32))]
+
+
+GAC_BUS_MONO_INPUT = 1
+GAC_SOURCE_BUFFER, GAC_SOURCE_CONSTANT, GAC_SOURCE_OSCILLATOR = 0, 1, 2
 
 
 class gac_graph_desc(C.Structure):

@@ -184,6 +184,7 @@ class AudioParam:
         # (first quantum, value, events) as each Render call saw the parameter: edits made between successive Render calls act from
         # the next unprocessed quantum on (OfflineAudioContext.cs:55-100), earlier quanta keep what they were rendered with
         self._epochs: List[tuple] = []
+        self._input_node = None  # the parameter's own fan-in (AudioParam.cs:60-62), created by the first AudioNode.Connect(param)
 
     def _clamp(self, v):
         v = np.float32(v)
@@ -246,6 +247,10 @@ class AudioParam:
             flat.extend(events)
         p = N.gac_param()
         p.value = self._epochs[0][1]
+        p.min_value, p.max_value = float(np.float32(self.MinValue)), float(np.float32(self.MaxValue))
+        p.mod_bus = 0
+        if self._input_node is not None and self._input_node._in:
+            p.mod_bus = self._input_node._bus_index + 1  # (set by the flattening of the graph this parameter belongs to)
         p.n_events = len(flat)
         if flat:
             arr = (N.gac_event * len(flat))()
@@ -283,14 +288,26 @@ class AudioNode:
         return False
 
     def Connect(self, destination: "AudioNode", outputIndex=0, inputIndex=0):
-        if isinstance(destination, AudioParam):  # AudioNode.Connect(AudioParam) — Nodes/AudioNode.cs:86-92
-            raise NotSupportedException("node -> AudioParam modulation is outside the accelerated path (SURVEY.md §8f-3; the CPU oracle has it)")
         if outputIndex < 0 or outputIndex >= self._n_outputs:
             raise ArgumentOutOfRangeException("outputIndex")
+        src = self._output_node(outputIndex)
+        if isinstance(destination, AudioParam):  # AudioNode.Connect(AudioParam) — Nodes/AudioNode.cs:86-92
+            if destination._input_node is None:
+                destination._input_node = _ParamInputNode(self.Context)
+            if src is not self:
+                return src.Connect(destination)
+            if destination._input_node not in self._out:
+                self._out.append(destination._input_node)
+                destination._input_node._in.append(self)
+            return None
         if inputIndex < 0 or inputIndex >= destination._n_inputs:
             raise ArgumentOutOfRangeException("inputIndex")
         if destination is self:
             raise InvalidOperationException("Cannot connect a node to itself")  # AudioNodeOutput.cs:43-44
+        if src is not self:  # an output of a ChannelSplitterNode: the connection starts at that output's own node
+            return src.Connect(destination, 0, inputIndex)
+        if isinstance(destination, ChannelMergerNode):
+            destination._slots[id(self)] = inputIndex + 1
         if destination not in self._out:
             # Between successive Render calls the device path re-renders the timeline from frame 0 with the CURRENT graph, so an edit
             # is only exact if it cannot change what was already rendered: parameter edits (epochs), sources started / stopped later,
@@ -300,6 +317,12 @@ class AudioNode:
             self._out.append(destination)
             destination._in.append(self)
         return destination
+
+    def _output_node(self, outputIndex):
+        return self
+
+    def _params(self):
+        return [v for v in self.__dict__.values() if isinstance(v, AudioParam)]
 
     def Disconnect(self, destination: Optional["AudioNode"] = None):
         for d in ([destination] if destination is not None else list(self._out)):
@@ -427,45 +450,90 @@ class OscillatorType:  # Nodes/OscillatorNode.cs:207-213
     Sine, Square, Sawtooth, Triangle = range(4)
 
 
-class _RecordedOnlySource(AudioNode):
-    """Nodes of GraphAudio.Core that can be built and connected but are not accelerated yet: a graph that reaches the destination
-    through one of them is refused at Render (NotSupportedException), never rendered with the node left out."""
+class _ParamInputNode(AudioNode):
+    """The AudioNodeInput an AudioParam owns (Explicit, one channel: AudioParam.cs:60-62): what AudioNode.Connect(param) connects
+    to.  Flattened into a GAC_BUS_MONO_INPUT bus that feeds nothing but the parameter."""
+
+    def __init__(self, context):
+        super().__init__(context, 1, 0)
+        self._force_bus = True
+        self._bus_index = -1
+
+
+class _ScheduledSourceNode(AudioNode):
+    """IAudioScheduledSourceNode: Start(when, offset, duration = NaN) / Stop(when), sample-accurate inside a quantum
+    (Nodes/OscillatorNode.cs:54-89, Nodes/ConstantSourceNode.cs:38-73)."""
 
     def __init__(self, context):
         super().__init__(context, 0, 1)
+        self._started = False
+        self._when, self._duration, self._stop = math.nan, math.nan, math.nan
+        self._start_frames = 0
 
     def Start(self, when=0.0, offset=0.0, duration=math.nan):
-        pass
+        if self._started:
+            raise InvalidOperationException(f"{type(self).__name__} can only be started once.")
+        self._started = True
+        self._when, self._duration = float(when), float(duration)
+        self._start_frames = getattr(self.Context, "_frames_rendered", 0)
 
     def Stop(self, when=0.0):
-        pass
+        at = max(0.0, float(when), self.Context._block_time(self.Context._q_now()))
+        self._stop = at if math.isnan(self._stop) else min(self._stop, at)
 
 
-class OscillatorNode(_RecordedOnlySource):  # Nodes/OscillatorNode.cs
+class OscillatorNode(_ScheduledSourceNode):  # Nodes/OscillatorNode.cs
     def __init__(self, context):
         super().__init__(context)
         self.Type = OscillatorType.Sine
         self.Frequency = AudioParam(440.0, 0.0, context.SampleRate / 2.0)
 
 
-class ConstantSourceNode(_RecordedOnlySource):  # Nodes/ConstantSourceNode.cs
+class ConstantSourceNode(_ScheduledSourceNode):  # Nodes/ConstantSourceNode.cs
     def __init__(self, context):
         super().__init__(context)
-        self.Offset = AudioParam(1.0, -3.4028234663852886e38, 3.4028234663852886e38)
+        fmax = float(np.finfo(np.float32).max)
+        self.Offset = AudioParam(1.0, -fmax, fmax)
 
 
-class ChannelSplitterNode(AudioNode):  # Nodes/ChannelSplitterNode.cs
+class _SplitterOutput(AudioNode):
+    """Output `index` of a ChannelSplitterNode: channel `index` of the splitter's input as a one-channel signal (GAC_OP_CHANNEL)."""
+
+    def __init__(self, context, index):
+        super().__init__(context)
+        self.Index = int(index)
+
+
+class ChannelSplitterNode(AudioNode):
+    """Nodes/ChannelSplitterNode.cs.  Flattened as: the splitter's input becomes a bus (no ops), every used output a chain fed
+    by that bus that starts with GAC_OP_CHANNEL."""
+
     def __init__(self, context, numberOfOutputs=2):
         if numberOfOutputs < 1 or numberOfOutputs > 32:
             raise ArgumentOutOfRangeException("numberOfOutputs")
         super().__init__(context, 1, numberOfOutputs)
+        self._force_bus = True
+        self._outputs = {}
+
+    def _output_node(self, outputIndex):
+        node = self._outputs.get(outputIndex)
+        if node is None:
+            node = self._outputs[outputIndex] = _SplitterOutput(self.Context, outputIndex)
+            self._out.append(node)
+            node._in.append(self)
+        return node
 
 
-class ChannelMergerNode(AudioNode):  # Nodes/ChannelMergerNode.cs
+class ChannelMergerNode(AudioNode):
+    """Nodes/ChannelMergerNode.cs: output channel i = channel 0 of what input i mixes.  Flattened into a bus whose inputs carry
+    their merger input (gac_bus_desc.input_slots); two inputs at most on the accelerated path."""
+
     def __init__(self, context, numberOfInputs=2):
         if numberOfInputs < 1 or numberOfInputs > 32:
             raise ArgumentOutOfRangeException("numberOfInputs")
         super().__init__(context, numberOfInputs, 1)
+        self._force_bus = True
+        self._slots = {}  # id(upstream node) -> merger input + 1
 
 
 class ConvolverNode(AudioNode):
@@ -680,6 +748,8 @@ class OfflineAudioContext:
         elif isinstance(node, StereoPannerNode):
             op.kind, op.aux = N.GAC_OP_PANNER, float(-(-node._born_frames // 128))
             op.p0 = node.Pan._desc(keep, q)
+        elif isinstance(node, _SplitterOutput):
+            op.kind, op.aux = N.GAC_OP_CHANNEL, float(node.Index)
         else:
             raise NotSupportedException(f"{type(node).__name__} is outside the accelerated path")
         return op
@@ -702,16 +772,27 @@ class OfflineAudioContext:
                 continue
             live.add(id(n))
             stack.extend(n._in)
+            for prm in n._params():  # a connected modulator keeps its branch alive (AudioParam.ComputeValues pulls it, AudioParam.cs:97-101)
+                if prm._input_node is not None and prm._input_node._in:
+                    stack.append(prm._input_node)
             # a node type the device path does not accelerate must never render as silence: refuse the whole graph
             if not isinstance(n, (AudioDestinationNode, AudioBufferSourceNode, BiQuadFilterNode, GainNode, ConvolverNode, DelayNode,
-                                  StereoPannerNode)):
+                                  StereoPannerNode, _ScheduledSourceNode, _ParamInputNode, ChannelSplitterNode, _SplitterOutput,
+                                  ChannelMergerNode)):
                 raise NotSupportedException(f"{type(n).__name__} is outside the accelerated path (SURVEY.md §8f-3; the CPU oracle has it)")
+            if isinstance(n, ChannelMergerNode) and any(sl > 2 for sl in n._slots.values()):
+                raise NotSupportedException("ChannelMergerNode inputs beyond the second are outside the accelerated path (signals carry two channels)")
+            if isinstance(n, AudioBufferSourceNode) and n.PlaybackRate._input_node is not None and n.PlaybackRate._input_node._in:
+                raise NotSupportedException("a modulated PlaybackRate is outside the accelerated path (the resampler's phase is replayed on the host)")
 
         def outs(n):
             return [d for d in n._out if id(d) in live]
 
         def is_src(n):
-            return isinstance(n, AudioBufferSourceNode)
+            return isinstance(n, (AudioBufferSourceNode, _ScheduledSourceNode))
+
+        def ops_of(chain):  # nodes that only shape the flattening (fan-in points without a node behind them) carry no op
+            return [n for n in chain if not isinstance(n, (_ParamInputNode, ChannelSplitterNode, ChannelMergerNode))]
 
         def fan_in(n):  # starts a bus
             return n is not dest and not is_src(n) and (len(n._in) != 1 or getattr(n, "_force_bus", False))
@@ -789,8 +870,10 @@ class OfflineAudioContext:
             if len(n._in) == 0 and not getattr(n, "_force_bus", False):
                 continue  # nothing connected: contributes silence (its consumers see a missing input)
             ch = chain_from(n)
-            b = new_bus(ch)
+            b = new_bus(ops_of(ch))
             bus_of_head[id(n)] = b
+            if isinstance(n, _ParamInputNode):
+                n._bus_index = b
             emit(ch[-1], True, b)
         # 3. resolve targets now that every fan-in has its bus index
         for v, d in pending_voice_target:
@@ -803,6 +886,16 @@ class OfflineAudioContext:
                 b = bus_of_head[id(n)]
                 bus_inputs[b] = [edge_code[(id(u), id(n))] for u in n._in if (id(u), id(n)) in edge_code] + bus_inputs[b]
         dest_inputs = [edge_code[(id(u), id(dest))] for u in dest._in if (id(u), id(dest)) in edge_code]
+        # bus flags (the input of an AudioParam has one channel) and ChannelMergerNode input slots, for _flatten
+        self._bus_flags = [0] * len(bus_ops)
+        self._bus_slots = [None] * len(bus_ops)
+        for n in self._nodes:
+            if id(n) in bus_of_head:
+                b = bus_of_head[id(n)]
+                if isinstance(n, _ParamInputNode):
+                    self._bus_flags[b] = N.GAC_BUS_MONO_INPUT
+                if isinstance(n, ChannelMergerNode):
+                    self._bus_slots[b] = [n._slots.get(id(u), 0) for u in n._in if (id(u), id(n)) in edge_code]
         # materialised fan-out buses keep the single input recorded in emit()
         return [tuple(v) for v in voices], bus_ops, dest_inputs, bus_targets, bus_inputs
 
@@ -827,7 +920,18 @@ class OfflineAudioContext:
         vdesc = (N.gac_voice_desc * max(1, len(voices)))()
         for i, (src, ops, bus, input_bus) in enumerate(voices):
             v = vdesc[i]
-            if src is not None:
+            if isinstance(src, _ScheduledSourceNode):
+                when = src._when if src._started else math.nan
+                if src._started and src._start_frames > 0:
+                    when = max(when, self._block_time(-(-src._start_frames // 128)))
+                osc = isinstance(src, OscillatorNode)
+                v.source = None
+                v.source_kind = N.GAC_SOURCE_OSCILLATOR if osc else N.GAC_SOURCE_CONSTANT
+                v.source_param = (src.Frequency if osc else src.Offset)._desc(keep, self._q_now())
+                v.oscillator_type = int(src.Type) if osc else 0
+                v.start_when, v.start_offset, v.start_duration, v.stop_when = when, 0.0, src._duration, src._stop
+                v.playback_rate = 1.0
+            elif src is not None:
                 if not src._started or src.Buffer is None:
                     when = math.nan
                 else:
@@ -851,6 +955,11 @@ class OfflineAudioContext:
             keep += [arr, inp]
             bdesc[i].n_ops, bdesc[i].ops = len(ops), arr
             bdesc[i].target, bdesc[i].n_inputs, bdesc[i].inputs = bus_targets[i], len(bus_inputs[i]), inp
+            bdesc[i].flags = self._bus_flags[i]
+            if self._bus_slots[i] is not None and voice_range is None:
+                sl = (C.c_int32 * max(1, len(self._bus_slots[i])))(*self._bus_slots[i])
+                keep.append(sl)
+                bdesc[i].input_slots = sl
         darr = (C.c_int32 * max(1, len(dest_inputs)))(*dest_inputs)
         g = N.gac_graph_desc()
         g.n_voices, g.voices, g.n_buses, g.buses = len(voices), vdesc, len(buses), bdesc

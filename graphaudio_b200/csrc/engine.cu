@@ -61,6 +61,8 @@ struct ParamH {
     std::vector<gac_event> ev;
   };
   std::vector<Epoch> later;
+  int mod_bus = -1;  // >= 0: the bus whose (mono) output is the parameter's modulation input
+  float minv = 0.f, maxv = 0.f;
 };
 struct OpH {
   int kind = 0;
@@ -78,11 +80,16 @@ struct VoiceH {
   std::vector<OpH> ops;
   int bus = -1;
   int input_bus = -1;  // >= 0: the chain is fed by that bus's output instead of a source buffer
+  int kind = GAC_SOURCE_BUFFER;  // gac_source_kind
+  ParamH src_param;              // CONSTANT: Offset, OSCILLATOR: Frequency
+  int osc_type = 0;
 };
 struct BusH {
   std::vector<OpH> ops;
   int target = -1;          // -1 destination, >= 0 parent bus, -2 none (only read by bus-fed chains)
   std::vector<int> inputs;  // connection order at the fan-in: >= 0 bus index, < 0 ~voice index
+  std::vector<int> slots;   // per input: 0 ordinary, 1 / 2 = ChannelMergerNode input 0 / 1 (empty: all ordinary)
+  bool mono = false;        // GAC_BUS_MONO_INPUT
 };
 
 struct NcclApi;
@@ -817,6 +824,11 @@ extern "C" int gac_ir_destroy(gac_ir* ir) {
 // ------------------------------------------------------------------------------------------ graph
 static int copy_param(const gac_param& p, ParamH* out, const char* what) {
   out->value = p.value;
+  out->mod_bus = p.mod_bus > 0 ? p.mod_bus - 1 : -1;
+  out->minv = p.min_value;
+  out->maxv = p.max_value;
+  if (p.mod_bus < 0) return fail(GAC_ERR_OUT_OF_RANGE, "%s: negative modulation bus", what);
+  if (p.mod_bus > 0 && !(p.min_value <= p.max_value)) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: a modulated parameter needs its [min, max] range", what);
   if (p.n_events < 0) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: negative event count", what);
   if (p.n_events > 0 && !p.events) return fail(GAC_ERR_INVALID_ARGUMENT, "%s: events is null", what);
   out->ev.clear();
@@ -871,6 +883,11 @@ static int copy_ops(gac_context* ctx, int n, const gac_op_desc* ops, std::vector
         if (!(o.aux >= 0.0)) return fail(GAC_ERR_OUT_OF_RANGE, "panner: first processed quantum must be >= 0");
         if ((rc = copy_param(ops[i].p0, &o.p0, "panner.pan"))) return rc;
         break;
+      case GAC_OP_CHANNEL:
+        o.aux = ops[i].aux;
+        if (!(o.aux >= 0.0 && o.aux < 32.0)) return fail(GAC_ERR_OUT_OF_RANGE, "channel index must be in 0 .. 31");  // ChannelSplitterNode.cs:17-18
+        if (i != 0) return fail(GAC_ERR_INVALID_ARGUMENT, "GAC_OP_CHANNEL must be the first op of a chain fed by a bus");
+        break;
       default:
         return fail(GAC_ERR_INVALID_ARGUMENT, "unknown op kind %d", o.kind);
     }
@@ -893,14 +910,21 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
     VoiceH& h = g->voices[v];
     if (d.input < 0 || d.input > desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: input bus %d out of range", v, d.input - 1);
     h.input_bus = d.input - 1;
-    if (h.input_bus < 0) {
+    h.kind = h.input_bus < 0 ? d.source_kind : GAC_SOURCE_BUFFER;
+    if (h.kind < GAC_SOURCE_BUFFER || h.kind > GAC_SOURCE_OSCILLATOR) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: unknown source kind %d", v, h.kind);
+    if (h.input_bus < 0 && h.kind != GAC_SOURCE_BUFFER) {
+      int rc = copy_param(d.source_param, &h.src_param, h.kind == GAC_SOURCE_CONSTANT ? "constantSource.offset" : "oscillator.frequency");
+      if (rc) return rc;
+      h.osc_type = d.oscillator_type;
+      if (h.kind == GAC_SOURCE_OSCILLATOR && (h.osc_type < 0 || h.osc_type > 3)) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: unknown oscillator type %d", v, h.osc_type);
+    } else if (h.input_bus < 0) {
       if (!d.source) return fail(GAC_ERR_INVALID_OPERATION, "voice %d: Cannot start without a buffer set", v);  // AudioBufferSourceNode.cs:86-87
       if (d.source->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: buffer belongs to another context", v);
       if (d.source->nch > 2) return fail(GAC_ERR_UNSUPPORTED, "voice %d: sources with more than 2 channels are outside the accelerated path", v);
       if (!(d.playback_rate >= 0.001f && d.playback_rate <= 1000.f)) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: playbackRate outside [0.001, 1000]", v);
     }
     if (d.bus < -1 || d.bus >= desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: bus index %d out of range", v, d.bus);
-    h.src = h.input_bus < 0 ? d.source : nullptr;
+    h.src = (h.input_bus < 0 && h.kind == GAC_SOURCE_BUFFER) ? d.source : nullptr;
     h.when = d.start_when;
     h.offset = d.start_offset;
     h.duration = d.start_duration;
@@ -912,6 +936,7 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
     h.bus = d.bus;
     int rc = copy_ops(ctx, d.n_ops, d.ops, &h.ops);
     if (rc) return rc;
+    if (!h.ops.empty() && h.ops[0].kind == GAC_OP_CHANNEL && h.input_bus < 0) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: GAC_OP_CHANNEL needs a chain fed by a bus", v);
   }
   g->buses.resize(desc->n_buses);
   for (int b = 0; b < desc->n_buses; b++) {
@@ -924,6 +949,13 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
   for (int b = 0; b < desc->n_buses; b++) {
     const gac_bus_desc& d = desc->buses[b];
     BusH& h = g->buses[b];
+    h.mono = (d.flags & GAC_BUS_MONO_INPUT) != 0;
+    if (d.input_slots && d.inputs && d.n_inputs > 0) {
+      h.slots.assign(d.input_slots, d.input_slots + d.n_inputs);
+      for (int sl : h.slots)
+        if (sl < 0 || sl > 2) return fail(GAC_ERR_UNSUPPORTED, "bus %d: channel mergers with more than two inputs are outside the accelerated path", b);
+      if (h.mono) return fail(GAC_ERR_INVALID_ARGUMENT, "bus %d: a merger bus cannot be a mono fan-in", b);
+    }
     if (d.inputs && d.n_inputs > 0) {
       h.inputs.assign(d.inputs, d.inputs + d.n_inputs);
       for (int x : h.inputs) {
@@ -949,6 +981,17 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
     for (int v = 0; v < desc->n_voices; v++)
       if (g->voices[v].bus == -1) g->dest_inputs.push_back(~v);
   }
+  // modulation inputs name buses of this graph
+  auto check_mod = [&](const ParamH& p) { return p.mod_bus < desc->n_buses && (p.mod_bus < 0 || g->buses[p.mod_bus].mono); };
+  auto check_ops = [&](const std::vector<OpH>& ops) {
+    for (const OpH& o : ops)
+      if (!check_mod(o.p0) || !check_mod(o.p1) || !check_mod(o.p2)) return false;
+    return true;
+  };
+  for (auto& v : g->voices)
+    if (!check_ops(v.ops) || !check_mod(v.src_param)) return fail(GAC_ERR_OUT_OF_RANGE, "a parameter's modulation bus is out of range or not a GAC_BUS_MONO_INPUT bus");
+  for (auto& b : g->buses)
+    if (!check_ops(b.ops)) return fail(GAC_ERR_OUT_OF_RANGE, "a parameter's modulation bus is out of range or not a GAC_BUS_MONO_INPUT bus");
   *out = g.release();
   return GAC_OK;
 }
@@ -968,6 +1011,7 @@ struct Sig {
   int ch = 2;              // logical channel count of the block the reference would carry here (rows are always 2; mono = duplicated)
   bool from_source = false;  // the chain is fed by an AudioBufferSourceNode (whose idle blocks have ONE channel, AudioBufferSourceNode.cs:391-402)
   const std::vector<OpH>* ops = nullptr;
+  size_t bus_base = 0;       // index of the graph's first bus in RenderEnv::buses (modulation inputs name graph-local buses)
 };
 
 struct RenderEnv {
@@ -990,13 +1034,27 @@ struct RenderEnv {
   float* tab_chunk = nullptr;
   size_t tab_left = 0;
   std::vector<DevEvent>* ev_host = nullptr;
+  std::vector<Sig>* buses = nullptr;     // every bus of the render (modulation inputs are read from here)
+  std::vector<ModJob> mod_jobs;          // modulation sums queued behind the parameter jobs of the current batch
 };
 
-static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector<ParamJob>& jobs, float** out_table) {
+static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector<ParamJob>& jobs, float** out_table, size_t bus_base = 0) {
   *out_table = nullptr;
-  if (p.ev.empty() && p.later.empty()) return GAC_OK;
+  const Sig* mod = nullptr;
+  if (p.mod_bus >= 0 && env.buses) {
+    const Sig& m = (*env.buses)[bus_base + (size_t)p.mod_bus];
+    if (m.hi > m.lo) mod = &m;  // a modulator that is silent throughout leaves the intrinsic value alone (AudioParam.cs:118-126)
+  }
+  if (p.ev.empty() && p.later.empty() && !mod) return GAC_OK;
   // voices that schedule the same automation (same value, same events) share one table: the curve depends on nothing else
   std::string key(1, a_rate ? 'a' : 'k');
+  if (mod) {  // ... unless something is added to it: a modulated parameter owns its table
+    key[0] = a_rate ? 'A' : 'K';
+    const void* who = mod->p[0];
+    key.append(reinterpret_cast<const char*>(&who), sizeof(who));
+    key.append(reinterpret_cast<const char*>(&p.minv), sizeof(float));
+    key.append(reinterpret_cast<const char*>(&p.maxv), sizeof(float));
+  }
   key.append(reinterpret_cast<const char*>(&p.value), sizeof(float));
   auto key_events = [&](const std::vector<gac_event>& ev) {
     for (const gac_event& e : ev) {  // field by field: the struct has 4 bytes of padding
@@ -1050,6 +1108,17 @@ static int param_table(RenderEnv& env, const ParamH& p, bool a_rate, std::vector
   add_job(p.value, p.ev, 0, p.later.empty() ? std::numeric_limits<int64_t>::max() : p.later[0].q0);
   for (size_t e = 0; e < p.later.size(); e++)
     add_job(p.later[e].value, p.later[e].ev, p.later[e].q0, e + 1 < p.later.size() ? p.later[e + 1].q0 : std::numeric_limits<int64_t>::max());
+  if (mod) {
+    ModJob m;
+    m.table = tab;
+    m.mod = mod->p[0];  // the parameter's input has one channel (a GAC_BUS_MONO_INPUT bus keeps it in both rows)
+    m.lo = mod->lo;
+    m.hi = mod->hi;
+    m.minv = p.minv;
+    m.maxv = p.maxv;
+    m.a_rate = a_rate ? 1 : 0;
+    env.mod_jobs.push_back(m);
+  }
   *out_table = tab;
   return GAC_OK;
 }
@@ -1069,6 +1138,15 @@ static int run_param_jobs(RenderEnv& env, std::vector<ParamJob>& jobs) {
   int t = env.timer->begin(C_AUTO);
   // a-rate and k-rate jobs share a launch; the kernel branches per job
   launch_param_eval(dj, (int)hj.size(), env.ctx->d_bt, env.NQ, env.ctx->fs, env.ctx->stream);
+  if (!env.mod_jobs.empty()) {  // intrinsic + modulation, clamped (AudioParam.cs:125-131, :150-155)
+    auto& hm = env.keep->make<ModJob>();
+    hm = env.mod_jobs;
+    env.mod_jobs.clear();
+    ModJob* dm = nullptr;
+    if ((rc = env.scratch->upload(&dm, hm))) return rc;
+    launch_param_modulate(dm, (int)hm.size(), env.Npad, env.ctx->stream);
+    env.launches++;
+  }
   env.timer->end(t);
   env.launches += ((int64_t)hj.size() + 65534) / 65535;
   CU(cudaGetLastError());
@@ -1557,6 +1635,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         case GAC_OP_CONVOLVER: convs.push_back(i); break;
         case GAC_OP_DELAY: delays.push_back(i); break;
         case GAC_OP_PANNER: panners.push_back(i); break;
+        default: break;  // GAC_OP_CHANNEL: applied where the chain is fed from its bus (render_core)
       }
     }
     // ---------------- DelayNode: a gather with a per-sample delay (K2 + k_delay), into fresh rows
@@ -1564,7 +1643,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       std::vector<ParamJob> pj;
       std::vector<float*> tabs(delays.size(), nullptr);
       for (size_t k = 0; k < delays.size(); k++) {
-        int rc = param_table(env, (*sigs[delays[k]].ops)[pos].p0, true, pj, &tabs[k]);
+        int rc = param_table(env, (*sigs[delays[k]].ops)[pos].p0, true, pj, &tabs[k], sigs[delays[k]].bus_base);
         if (rc) return rc;
       }
       int rc = run_param_jobs(env, pj);
@@ -1616,7 +1695,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       std::vector<ParamJob> pj;
       std::vector<float*> tabs(panners.size(), nullptr);
       for (size_t k = 0; k < panners.size(); k++) {
-        int rc = param_table(env, (*sigs[panners[k]].ops)[pos].p0, true, pj, &tabs[k]);
+        int rc = param_table(env, (*sigs[panners[k]].ops)[pos].p0, true, pj, &tabs[k], sigs[panners[k]].bus_base);
         if (rc) return rc;
       }
       int rc = run_param_jobs(env, pj);
@@ -1666,7 +1745,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       std::vector<ParamJob> pj;
       std::vector<float*> tabs(gains.size(), nullptr);
       for (size_t k = 0; k < gains.size(); k++) {
-        int rc = param_table(env, (*sigs[gains[k]].ops)[pos].p0, true, pj, &tabs[k]);
+        int rc = param_table(env, (*sigs[gains[k]].ops)[pos].p0, true, pj, &tabs[k], sigs[gains[k]].bus_base);
         if (rc) return rc;
       }
       int rc = run_param_jobs(env, pj);
@@ -1719,9 +1798,9 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         }
         float *tf = nullptr, *tq = nullptr, *tg = nullptr;
         int rc;
-        if ((rc = param_table(env, op.p0, true, pj, &tf))) return rc;
-        if ((rc = param_table(env, op.p1, true, pj, &tq))) return rc;
-        if ((rc = param_table(env, op.p2, false, pj, &tg))) return rc;
+        if ((rc = param_table(env, op.p0, true, pj, &tf, s.bus_base))) return rc;
+        if ((rc = param_table(env, op.p1, true, pj, &tq, s.bus_base))) return rc;
+        if ((rc = param_table(env, op.p2, false, pj, &tg, s.bus_base))) return rc;
         j.sig[0] = s.p[0];
         j.sig[1] = s.p[1];
         j.freq = tf;

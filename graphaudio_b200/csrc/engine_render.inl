@@ -230,6 +230,100 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
   return GAC_OK;
 }
 
+// Scheduled one-channel sources: ConstantSourceNode (Nodes/ConstantSourceNode.cs:75-141) and OscillatorNode
+// (Nodes/OscillatorNode.cs:91-160).  The host decides the quanta the node plays in and its sample-accurate first / last frame from
+// the accumulated block times, exactly as Process() does block by block; the device fills the rows.
+static int plan_scheduled(RenderEnv& env, const std::vector<const VoiceH*>& voices, std::vector<Sig>& sigs) {
+  gac_context* ctx = env.ctx;
+  const double inc = (double)128 / (double)ctx->fs;
+  const std::vector<double>& bt = ctx->bt->h;
+  auto& jobs = env.keep->make<SchedJob>();
+  std::vector<ParamJob> pj;
+  bool any_osc = false;
+  for (size_t i = 0; i < voices.size(); i++) {
+    const VoiceH& v = *voices[i];
+    Sig& s = sigs[i];
+    s.lo = s.hi = 0;
+    s.ch = 1;  // the node rents a one-channel block (:77-80)
+    s.from_source = false;
+    if (std::isnan(v.when)) continue;  // never started: cleared output, flagged silent
+    const double startTime = std::max(0.0, v.when);  // Start(): _startTime = Math.Max(0, when)
+    double stopTime = std::numeric_limits<double>::quiet_NaN();
+    if (!std::isnan(v.duration) && !std::isinf(v.duration) && v.duration >= 0) stopTime = startTime + v.duration;  // (and Stop() is then ignored)
+    else if (!std::isnan(v.stop_when)) stopTime = std::max(0.0, v.stop_when);
+    // shouldPlay: t1 > _startTime && (NaN(_stopTime) || t0 < _stopTime), t1 = t0 + 128 / fs
+    int64_t b_start = 0;
+    {
+      int64_t lo = 0, hi = env.NQ;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (bt[mid] + inc > startTime) hi = mid; else lo = mid + 1;
+      }
+      b_start = lo;
+    }
+    int64_t b_stop = env.NQ;
+    if (!std::isnan(stopTime)) {
+      int64_t lo = b_start, hi = env.NQ;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (!(bt[mid] < stopTime)) hi = mid; else lo = mid + 1;
+      }
+      b_stop = lo;
+    }
+    if (b_stop <= b_start) continue;
+    int64_t s0 = b_start * 128, s1 = b_stop * 128;
+    {
+      const double t0 = bt[b_start], t1 = t0 + inc;
+      if (t0 < startTime && startTime < t1) {  // startFrame = clamp(ceil((start - t0) * fs), 0, 128)
+        double f = std::ceil((startTime - t0) * (double)ctx->fs);
+        f = f < 0 ? 0 : (f > 128 ? 128 : f);
+        s0 += (int64_t)(int)f;
+      }
+    }
+    if (!std::isnan(stopTime)) {
+      const double t0 = bt[b_stop - 1], t1 = t0 + inc;
+      if (t0 < stopTime && stopTime < t1) {  // endFrame = clamp(floor((stop - t0) * fs), 0, 128)
+        double f = std::floor((stopTime - t0) * (double)ctx->fs);
+        f = f < 0 ? 0 : (f > 128 ? 128 : f);
+        s1 = (b_stop - 1) * 128 + (int64_t)(int)f;
+      }
+    }
+    if (s1 < s0) s1 = s0;  // (a stop inside the start quantum, before the start frame)
+    float* tab = nullptr;
+    int rc = param_table(env, v.src_param, true, pj, &tab, s.bus_base);
+    if (rc) return rc;
+    SchedJob j{};
+    j.dst[0] = s.p[0];
+    j.dst[1] = s.p[1];
+    j.table = tab;
+    j.value = v.src_param.value;
+    j.lo = b_start * 128;
+    j.hi = b_stop * 128;
+    j.s0 = s0;
+    j.s1 = s1;
+    j.osc_type = v.kind == GAC_SOURCE_OSCILLATOR ? v.osc_type : -1;
+    j.chunk_sum = nullptr;
+    if (v.kind == GAC_SOURCE_OSCILLATOR) {
+      any_osc = true;
+      if ((rc = env.scratch->alloc(&j.chunk_sum, (size_t)((s1 - s0) / 1024 + 2)))) return rc;
+    }
+    jobs.push_back(j);
+    s.lo = j.lo;  // every quantum the node plays in is marked non-silent, also its zero-filled frames (:158-159)
+    s.hi = j.hi;
+  }
+  int rc = run_param_jobs(env, pj);
+  if (rc) return rc;
+  if (jobs.empty()) return GAC_OK;
+  SchedJob* dj = nullptr;
+  if ((rc = env.scratch->upload(&dj, jobs))) return rc;
+  int t = env.timer->begin(C_SOURCE);
+  launch_scheduled_sources(dj, (int)jobs.size(), env.Npad, ctx->fs, any_osc, ctx->stream);
+  env.timer->end(t);
+  env.launches += any_osc ? 3 : 1;
+  CU(cudaGetLastError());
+  return GAC_OK;
+}
+
 // ------------------------------------------------------------------------------------------ NCCL (dlopen'ed)
 struct NcclUid {
   char internal[128];
@@ -433,9 +527,23 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         return false;
     return true;
   };
-  std::vector<size_t> src_voices;  // indices of the source-fed chains
-  for (size_t i = 0; i < S; i++)
-    if (voices[i]->input_bus < 0) src_voices.push_back(i);
+  // parameters with a modulation input make their owner wait for the bus that carries the modulator (graph-local bus indices)
+  auto ops_deps = [](const std::vector<OpH>& ops, std::vector<int>& out) {
+    for (const OpH& o : ops)
+      for (const ParamH* p : {&o.p0, &o.p1, &o.p2})
+        if (p->mod_bus >= 0) out.push_back(p->mod_bus);
+  };
+  std::vector<std::vector<int>> voice_deps(S);
+  for (size_t i = 0; i < S; i++) {
+    ops_deps(voices[i]->ops, voice_deps[i]);
+    if (voices[i]->src_param.mod_bus >= 0) voice_deps[i].push_back(voices[i]->src_param.mod_bus);
+  }
+  std::vector<size_t> src_voices;  // the chains fed by buffer sources that wait for nothing: stage 1
+  size_t n_bus_fed = 0;
+  for (size_t i = 0; i < S; i++) {
+    if (voices[i]->input_bus >= 0) n_bus_fed++;
+    if (voices[i]->input_bus < 0 && voices[i]->kind == GAC_SOURCE_BUFFER && voice_deps[i].empty()) src_voices.push_back(i);
+  }
   const size_t S0 = src_voices.size();
   std::vector<char> voice_done(S, 0);
   {
@@ -488,7 +596,8 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
       vb += a.graphs[g]->voices.size();
     }
   }
-  bool hierarchy = S0 != S;
+  bool hierarchy = n_bus_fed != 0;
+  for (size_t i = 0; i < S; i++) hierarchy = hierarchy || !voice_deps[i].empty();
   for (int g = 0; g < a.n_graphs; g++)
     for (auto& b : a.graphs[g]->buses) hierarchy = hierarchy || b.target != -1;
   if (a.sharded && ctx->n_ranks > 1 && hierarchy)
@@ -505,8 +614,22 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         bs.p[0] = d_bus + ((bus_base[g] + b) * 2 + 0) * (size_t)env.Npad;
         bs.p[1] = d_bus + ((bus_base[g] + b) * 2 + 1) * (size_t)env.Npad;
         bs.ops = &a.graphs[g]->buses[b].ops;
+        bs.bus_base = bus_base[g];
       }
   }
+  env.buses = &buses;
+  for (size_t i = 0; i < S; i++) sigs[i].bus_base = bus_base[voice_graph[i]];
+  std::vector<std::vector<int>> bus_deps(NB);
+  for (int g = 0; g < a.n_graphs; g++)
+    for (size_t b = 0; b < a.graphs[g]->buses.size(); b++) ops_deps(a.graphs[g]->buses[b].ops, bus_deps[bus_base[g] + b]);
+  float* d_zero_row = nullptr;  // what a ChannelMergerNode connection adds to the channel it does not feed
+  auto zero_row = [&]() -> int {
+    if (d_zero_row) return GAC_OK;
+    int rc0 = scratch.alloc(&d_zero_row, (size_t)env.Npad);
+    if (rc0) return rc0;
+    CU(cudaMemsetAsync(d_zero_row, 0, sizeof(float) * (size_t)env.Npad, ctx->stream));
+    return GAC_OK;
+  };
   for (size_t round = 0;; round++) {
     // buses whose inputs are all available
     std::vector<size_t> ready;
@@ -516,14 +639,17 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         if (bus_done[bus_base[g] + b]) continue;
         bool ok = true;
         for (int x : gr->buses[b].inputs) ok = ok && (x >= 0 ? bus_done[bus_base[g] + (size_t)x] : voice_done[voice_base[g] + (size_t)(~x)]);
+        for (int d : bus_deps[bus_base[g] + b]) ok = ok && bus_done[bus_base[g] + (size_t)d];
         if (ok) ready.push_back(bus_base[g] + b);
       }
     }
     std::vector<size_t> fed;  // chains fed by a finished bus
     if (ready.empty()) {
       for (size_t i = 0; i < S; i++) {
-        if (voice_done[i] || voices[i]->input_bus < 0) continue;
-        if (bus_done[bus_base[voice_graph[i]] + (size_t)voices[i]->input_bus]) fed.push_back(i);
+        if (voice_done[i]) continue;
+        bool ok = voices[i]->input_bus < 0 || bus_done[bus_base[voice_graph[i]] + (size_t)voices[i]->input_bus];
+        for (int d : voice_deps[i]) ok = ok && bus_done[bus_base[voice_graph[i]] + (size_t)d];
+        if (ok) fed.push_back(i);
       }
       if (fed.empty()) break;
     }
@@ -549,7 +675,11 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         //   ClampedMax 2 (StereoPannerNode.cs:24-26): min(max over the inputs' blocks, 2), i.e. 1 when every input is mono.
         auto sig_in = [&](int x) -> const Sig& { return x >= 0 ? buses[bus_base[g] + (size_t)x] : sigs[voice_base[g] + (size_t)(~x)]; };
         int head_ch = 2;
-        if (bh.ops.empty()) {
+        if (bh.mono) {
+          head_ch = 1;  // the input of an AudioParam: Explicit, one channel (AudioParam.cs:60-62)
+        } else if (!bh.slots.empty()) {
+          head_ch = 2;  // ChannelMergerNode with two inputs: its output has two channels
+        } else if (bh.ops.empty()) {
           for (int x : bh.inputs) head_ch = sig_in(x).ch;  // a materialised fan-out point: no node, the signal passes through
         } else if (bh.ops[0].kind == GAC_OP_CONVOLVER && bh.ops[0].ir && bh.ops[0].ir->nch == 1) {
           head_ch = 1;
@@ -568,7 +698,8 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
             return fail(GAC_ERR_UNSUPPORTED, "a StereoPannerNode fed by several inputs whose channel count changes during the render (stereo sources "
                                              "connected directly that start late or end early) is outside the accelerated path");
         }
-        for (int x : bh.inputs) {
+        for (size_t xi = 0; xi < bh.inputs.size(); xi++) {
+          const int x = bh.inputs[xi];
           const Sig& vs = sig_in(x);
           if (vs.hi <= vs.lo) continue;  // silent throughout: never mixed (:127)
           MixInput in;
@@ -577,6 +708,14 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
           in.lo = vs.lo;
           in.hi = vs.hi;
           if (head_ch == 1 && vs.ch == 2) in.downmix = 1.0f / sqrtf(2.0f);  // 1.0f / MathF.Sqrt(srcChannels)  (:217)
+          const int slot = bh.slots.empty() ? 0 : bh.slots[xi];
+          if (slot) {
+            // ChannelMergerNode (Nodes/ChannelMergerNode.cs:40-62): channel 0 of what merger input slot-1 mixes becomes output
+            // channel slot-1; the other channel receives + 0 from this connection
+            if ((rc = zero_row())) return rc;
+            in.src[slot == 1 ? 0 : 1] = vs.p[0];
+            in.src[slot == 1 ? 1 : 0] = d_zero_row;
+          }
           minputs.push_back(in);
           lo = std::min(lo, vs.lo);
           hi = std::max(hi, vs.hi);
@@ -611,32 +750,63 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
       for (size_t gb : ready) bus_done[gb] = 1;
       continue;
     }
-    // chains fed by bus outputs: the chain works on its own copy of the bus signal ((0 + x) == x, silent quanta stay silent)
+    // chains that became runnable: (a) fed by a bus output — the chain works on its own copy of the bus signal ((0 + x) == x, silent
+    // quanta stay silent), or on ONE channel of it behind a ChannelSplitterNode; (b) buffer sources whose chain waited for a
+    // modulator; (c) scheduled sources (ConstantSourceNode / OscillatorNode)
     std::vector<Sig> sub;
+    std::vector<const VoiceH*> late_src;
+    std::vector<size_t> late_src_pos, sched_pos;
     for (size_t i : fed) {
-      const Sig& src = buses[bus_base[voice_graph[i]] + (size_t)voices[i]->input_bus];
       Sig& s = sigs[i];
-      MixJob mj;
-      mj.dst[0] = s.p[0];
-      mj.dst[1] = s.p[1];
-      mj.first_input = (int)minputs.size();
-      if (src.hi > src.lo) {
-        MixInput in;
-        in.src[0] = src.p[0];
-        in.src[1] = src.p[1];
-        in.lo = src.lo;
-        in.hi = src.hi;
-        minputs.push_back(in);
+      if (voices[i]->input_bus >= 0) {
+        const Sig& src = buses[bus_base[voice_graph[i]] + (size_t)voices[i]->input_bus];
+        MixJob mj;
+        mj.dst[0] = s.p[0];
+        mj.dst[1] = s.p[1];
+        mj.first_input = (int)minputs.size();
+        s.lo = src.lo;
+        s.hi = src.hi;
+        s.ch = src.ch;
+        int pick = -1;  // ChannelSplitterNode output (Nodes/ChannelSplitterNode.cs:29-62): channel `pick` of the input as one channel
+        if (!voices[i]->ops.empty() && voices[i]->ops[0].kind == GAC_OP_CHANNEL) pick = (int)voices[i]->ops[0].aux;
+        if (pick >= 2) s.lo = s.hi = 0;  // the splitter's input has two channels (Max mode, channelCount 2): outputs beyond are cleared
+        if (s.hi > s.lo) {
+          MixInput in;
+          in.src[0] = pick == 1 ? src.p[1] : src.p[0];  // (a mono signal keeps its channel in both rows: the 1 -> 2 up-mix of the input)
+          in.src[1] = pick == 0 ? src.p[0] : src.p[1];
+          in.lo = src.lo;
+          in.hi = src.hi;
+          minputs.push_back(in);
+        }
+        if (pick >= 0) s.ch = 1;
+        mj.n_inputs = (int)minputs.size() - mj.first_input;
+        mjobs.push_back(mj);
+      } else if (voices[i]->kind == GAC_SOURCE_BUFFER) {
+        late_src.push_back(voices[i]);
+        late_src_pos.push_back(sub.size());
+      } else {
+        sched_pos.push_back(sub.size());
       }
-      mj.n_inputs = (int)minputs.size() - mj.first_input;
-      mjobs.push_back(mj);
-      s.lo = src.lo;
-      s.hi = src.hi;
-      s.ch = src.ch;
       sub.push_back(s);
     }
-    if (is_root) {
+    if (is_root || !a.sharded) {
       if ((rc = mix_into(env, mjobs, minputs))) return rc;
+      if (!late_src.empty()) {
+        std::vector<Sig> ls;
+        for (size_t k : late_src_pos) ls.push_back(sub[k]);
+        if ((rc = plan_sources(env, late_src, ls))) return rc;
+        for (size_t k = 0; k < late_src_pos.size(); k++) sub[late_src_pos[k]] = ls[k];
+      }
+      if (!sched_pos.empty()) {
+        std::vector<const VoiceH*> sv;
+        std::vector<Sig> ss;
+        for (size_t k : sched_pos) {
+          sv.push_back(voices[fed[k]]);
+          ss.push_back(sub[k]);
+        }
+        if ((rc = plan_scheduled(env, sv, ss))) return rc;
+        for (size_t k = 0; k < sched_pos.size(); k++) sub[sched_pos[k]] = ss[k];
+      }
       if ((rc = run_chains(env, sub))) return rc;
     }
     for (size_t k = 0; k < fed.size(); k++) {

@@ -152,6 +152,30 @@ struct ParamJob {
 };
 void launch_param_eval(const ParamJob* d_jobs, int n_jobs, const double* d_block_time, int64_t n_quanta, int sample_rate, cudaStream_t s);
 
+// AudioParam with a modulation input: table[n] = clamp(table[n] + mod[n], min, max) on the frames where the modulator is non-silent
+// (a-rate; k-rate tables hold one value per quantum and take the modulator's first frame of the quantum) — AudioParam.cs:114-166
+struct ModJob {
+  float* table;
+  const float* mod;
+  int64_t lo, hi;  // non-silent frames of the modulator (multiples of 128)
+  float minv, maxv;
+  int a_rate;
+};
+void launch_param_modulate(const ModJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
+
+// Scheduled one-channel sources (Nodes/ConstantSourceNode.cs, Nodes/OscillatorNode.cs): frames [s0, s1) carry the source, the rest of
+// [lo, hi) (the quanta the node plays in) zeros; rows outside [lo, hi) are not written (flagged silent)
+struct SchedJob {
+  float* dst[2];       // both rows receive the (mono) signal
+  const float* table;  // a-rate Offset / Frequency values, or nullptr (constant)
+  float value;
+  int64_t lo, hi;      // quanta the node plays in, as frames
+  int64_t s0, s1;      // sample-accurate start / stop
+  int osc_type;        // -1: ConstantSourceNode; 0..3: OscillatorNode type
+  double* chunk_sum;   // oscillator scratch: [ceil((s1 - s0) / 1024) + 1] phase-increment sums of 1024-frame chunks from s0
+};
+void launch_scheduled_sources(const SchedJob* d_jobs, int n_jobs, int64_t n_frames, int sample_rate, bool any_oscillator, cudaStream_t s);
+
 struct SourceJob {
   const float* src[2];  // channel pointers (both the same for a mono buffer: the 1->2 up-mix copy of AudioNodeInput.cs:201-213)
   float* dst[2];        // sig rows

@@ -320,6 +320,171 @@ void launch_panner(const PannerJob* d_jobs, int n_jobs, int64_t n_frames, bool s
   }
 }
 
+// ============================================================================================ AudioParam modulation
+// AudioParam.ComputeARate / ComputeKRate with a connected modulator (AudioParam.cs:114-166): value = Math.Clamp(intrinsic +
+// modulation, min, max) in float32 while the modulation block is non-silent, the intrinsic value otherwise.
+__device__ __forceinline__ float clamp_param(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }  // Math.Clamp(float)
+__global__ void __launch_bounds__(256) k_param_modulate(const ModJob* __restrict__ jobs, int64_t n_frames) {
+  const ModJob job = jobs[blockIdx.y];
+  if (job.a_rate) {
+    const int64_t n4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (n4 < job.lo || n4 >= job.hi || n4 >= n_frames) return;  // (ranges are multiples of 128 frames)
+    float4 t = *reinterpret_cast<float4*>(job.table + n4);
+    const float4 m = *reinterpret_cast<const float4*>(job.mod + n4);
+    t.x = clamp_param(t.x + m.x, job.minv, job.maxv);
+    t.y = clamp_param(t.y + m.y, job.minv, job.maxv);
+    t.z = clamp_param(t.z + m.z, job.minv, job.maxv);
+    t.w = clamp_param(t.w + m.w, job.minv, job.maxv);
+    *reinterpret_cast<float4*>(job.table + n4) = t;
+  } else {
+    const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;  // one value per quantum, modulated by the block's first frame (:152)
+    if (q * 128 < job.lo || q * 128 >= job.hi || q * 128 >= n_frames) return;
+    job.table[q] = clamp_param(job.table[q] + job.mod[q * 128], job.minv, job.maxv);
+  }
+}
+void launch_param_modulate(const ModJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s) {
+  if (n_jobs <= 0 || n_frames <= 0) return;
+  dim3 grid((unsigned)((n_frames / 4 + 255) / 256), (unsigned)n_jobs);
+  k_param_modulate<<<grid, 256, 0, s>>>(d_jobs, n_frames);
+}
+
+// ============================================================================================ scheduled sources
+// ConstantSourceNode (Nodes/ConstantSourceNode.cs:75-141): the Offset values on frames [s0, s1), zeros on the rest of the quanta
+// the node plays in.  OscillatorNode (Nodes/OscillatorNode.cs:91-196): sample n >= s0 is GenerateSample(phase[n]) with
+// phase[s0] = 0, phase[n + 1] = phase[n] + 2*pi*f[n]/fs, minus 2*pi whenever it reaches 2*pi (:150-156).  The reference adds frame by
+// frame; here the increments are summed by a three-pass blocked prefix sum in double and reduced modulo 2*pi — the same number up
+// to ~1e-10 rad (gac_source_kind in the header says what that means for the samples).
+constexpr int kSchedChunk = 1024;
+__device__ __forceinline__ double osc_increment(const SchedJob& job, int64_t n, int sample_rate) {
+  const float f = job.table ? job.table[n] : job.value;
+  return (2.0 * 3.14159265358979323846 * (double)f) / (double)sample_rate;  // (2.0 * Math.PI * freqValues[i]) / Context.SampleRate
+}
+// pass 1: chunk sums of the phase increments
+__global__ void __launch_bounds__(256) k_osc_chunk_sums(const SchedJob* __restrict__ jobs, int sample_rate) {
+  const SchedJob job = jobs[blockIdx.y];
+  if (job.osc_type < 0) return;
+  const int64_t c0 = job.s0 + (int64_t)blockIdx.x * kSchedChunk;
+  if (c0 >= job.s1) return;
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < kSchedChunk; e += 256) {
+    const int64_t n = c0 + e;
+    if (n < job.s1) acc += osc_increment(job, n, sample_rate);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) job.chunk_sum[blockIdx.x] = red[0];
+}
+// pass 2: exclusive scan over the chunk sums (one thread per oscillator: a few hundred chunks)
+__global__ void k_osc_scan_chunks(const SchedJob* __restrict__ jobs, int n_jobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  const SchedJob job = jobs[j];
+  if (job.osc_type < 0 || job.s1 <= job.s0) return;
+  const int64_t nc = (job.s1 - job.s0 + kSchedChunk - 1) / kSchedChunk;
+  double run = 0.0;
+  for (int64_t c = 0; c < nc; c++) {
+    const double v = job.chunk_sum[c];
+    job.chunk_sum[c] = run;
+    run += v;
+  }
+}
+__device__ __forceinline__ float osc_sample(double phase, int type) {  // GenerateSample :176-199
+  const double two_pi = 2.0 * 3.14159265358979323846;
+  switch (type) {
+    case 0: return (float)sin(phase);
+    case 1: return phase < 3.14159265358979323846 ? 1.0f : -1.0f;
+    case 2: return (float)(2.0 * (phase / two_pi) - 1.0);
+    default: {
+      const double t = phase / two_pi;
+      return (float)(4.0 * fabs(t - floor(t + 0.5)) - 1.0);
+    }
+  }
+}
+// pass 3: the samples.  CTA = one chunk of one job; constant sources need no phase
+__global__ void __launch_bounds__(256) k_sched_fill(const SchedJob* __restrict__ jobs, int sample_rate) {
+  const SchedJob job = jobs[blockIdx.y];
+  const int64_t c0 = job.lo + (int64_t)blockIdx.x * kSchedChunk;
+  if (c0 >= job.hi) return;
+  if (job.osc_type < 0) {
+    for (int e = threadIdx.x; e < kSchedChunk; e += 256) {
+      const int64_t n = c0 + e;
+      if (n >= job.hi) break;
+      const float v = (n >= job.s0 && n < job.s1) ? (job.table ? job.table[n] : job.value) : 0.f;
+      job.dst[0][n] = v;
+      job.dst[1][n] = v;
+    }
+    return;
+  }
+  // oscillator: this CTA covers frames [c0, c0 + 1024) of [lo, hi); the phase chunks are aligned to s0
+  __shared__ double sc[kSchedChunk];
+  __shared__ double part[256];
+  const double two_pi = 2.0 * 3.14159265358979323846;
+  for (int half = 0; half < 2; half++) {
+    // frames of this CTA belong to at most two phase chunks (lo and s0 differ by less than a quantum): handle them one after the other
+    const int64_t k = (c0 - job.s0 >= 0 ? (c0 - job.s0) / kSchedChunk : -1) + half;  // phase chunk index
+    if (k < 0) continue;
+    const int64_t p0 = job.s0 + k * kSchedChunk;  // first frame of the phase chunk
+    if (p0 >= job.s1 || p0 >= c0 + kSchedChunk) continue;
+    // exclusive scan of the increments of phase chunk k (4 per thread, then a scan of the 256 partial sums)
+    double v[4], run = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int64_t n = p0 + threadIdx.x * 4 + e;
+      v[e] = n < job.s1 ? osc_increment(job, n, sample_rate) : 0.0;
+      run += v[e];
+    }
+    part[threadIdx.x] = run;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int t = 0; t < 256; t++) {
+        const double x = part[t];
+        part[t] = acc;
+        acc += x;
+      }
+    }
+    __syncthreads();
+    double ph = job.chunk_sum[k] + part[threadIdx.x];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      sc[threadIdx.x * 4 + e] = ph;
+      ph += v[e];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kSchedChunk; e += 256) {
+      const int64_t n = p0 + e;
+      if (n < c0 || n >= c0 + kSchedChunk || n >= job.hi || n >= job.s1) continue;
+      const double phase = fmod(sc[e], two_pi);
+      const float s = osc_sample(phase, job.osc_type);
+      job.dst[0][n] = s;
+      job.dst[1][n] = s;
+    }
+    __syncthreads();
+  }
+  // frames of the playing quanta outside [s0, s1) are zero
+  for (int e = threadIdx.x; e < kSchedChunk; e += 256) {
+    const int64_t n = c0 + e;
+    if (n < job.hi && (n < job.s0 || n >= job.s1)) {
+      job.dst[0][n] = 0.f;
+      job.dst[1][n] = 0.f;
+    }
+  }
+}
+void launch_scheduled_sources(const SchedJob* d_jobs, int n_jobs, int64_t n_frames, int sample_rate, bool any_oscillator, cudaStream_t s) {
+  if (n_jobs <= 0 || n_frames <= 0) return;
+  const unsigned chunks = (unsigned)((n_frames + kSchedChunk - 1) / kSchedChunk) + 1;
+  if (any_oscillator) {
+    k_osc_chunk_sums<<<dim3(chunks, (unsigned)n_jobs), 256, 0, s>>>(d_jobs, sample_rate);
+    k_osc_scan_chunks<<<(unsigned)((n_jobs + 63) / 64), 64, 0, s>>>(d_jobs, n_jobs);
+  }
+  k_sched_fill<<<dim3(chunks, (unsigned)n_jobs), 256, 0, s>>>(d_jobs, sample_rate);
+}
+
 // ============================================================================================ mix
 // N -> 1 channel mix of one input block (AudioNodeInput.cs:214-228): sum = 0; sum += L; sum += R; dst += sum * (1 / sqrt(N)).
 // The mono result is kept in both rows.

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GAC_ABI_VERSION 5
+#define GAC_ABI_VERSION 6
 
 /* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */
 typedef enum gac_status {
@@ -142,6 +142,13 @@ typedef struct gac_param {
   float value;
   int32_t n_events;
   const gac_event* events;
+  /* Modulation input ≙ AudioNode.Connect(AudioParam) (Nodes/AudioNode.cs:86-92): the parameter's own AudioNodeInput (Explicit, ONE
+   * channel: AudioParam.cs:60-62) sums the connected outputs; while that block is non-silent the value is
+   * clamp(intrinsic + modulation, min, max) (AudioParam.cs:114-166; a-rate: per frame, k-rate: frame 0 of the quantum).
+   * mod_bus = 0: none; k > 0: the fan-in is bus k-1 of the graph, which must carry GAC_BUS_MONO_INPUT. */
+  int32_t mod_bus;
+  float min_value, max_value; /* AudioParam.MinValue / MaxValue; used with modulation only */
+  int32_t reserved;
 } gac_param;
 
 /* ---- per-voice processing chain ---- */
@@ -150,7 +157,10 @@ typedef enum gac_op_kind {
   GAC_OP_GAIN = 2,     /* GainNode          Nodes/GainNode.cs:29-61          */
   GAC_OP_CONVOLVER = 3,/* ConvolverNode     Nodes/ConvolverNode.cs:102-155   */
   GAC_OP_DELAY = 4,    /* DelayNode         Nodes/DelayNode.cs:43-149        */
-  GAC_OP_PANNER = 5    /* StereoPannerNode  Nodes/StereoPannerNode.cs:36-153 */
+  GAC_OP_PANNER = 5,   /* StereoPannerNode  Nodes/StereoPannerNode.cs:36-153 */
+  GAC_OP_CHANNEL = 6   /* one output of a ChannelSplitterNode (Nodes/ChannelSplitterNode.cs): the signal becomes channel `aux` of
+                          its input as a ONE-channel signal (silence if the input has no such channel).  Only valid as the first
+                          op of a chain fed by a bus (the splitter's input is that bus)                                       */
 } gac_op_kind;
 
 typedef enum gac_filter_type { /* FilterType, Nodes/BiQuadFilterNode.cs:288-298 */
@@ -198,10 +208,21 @@ typedef struct gac_voice_desc {
                                fields are then ignored                                           */
   int32_t loop;             /* AudioBufferSourceNode.Loop (:40-44).  Supported at effective rate 1 (buffer rate == context
                                rate, PlaybackRate 1) with LoopStart < LoopEnd; otherwise GAC_ERR_UNSUPPORTED at render  */
-  int32_t reserved;
+  int32_t source_kind;      /* gac_source_kind (input == 0 only): what feeds the chain                                */
   double loop_start;        /* LoopStart in seconds (:49-53)                                     */
   double loop_end;          /* LoopEnd in seconds, 0 = end of the buffer (:58-62)                */
+  gac_param source_param;   /* CONSTANT: Offset (a-rate, Nodes/ConstantSourceNode.cs); OSCILLATOR: Frequency (a-rate, Hz)        */
+  int32_t oscillator_type;  /* OSCILLATOR: 0 sine, 1 square, 2 sawtooth, 3 triangle (Nodes/OscillatorNode.cs:207-213)            */
+  int32_t reserved;
 } gac_voice_desc;
+
+/* Scheduled sources (IAudioScheduledSourceNode): one channel, sample-accurate start and stop inside a quantum
+ * (Nodes/OscillatorNode.cs:97-118, Nodes/ConstantSourceNode.cs:82-110).  They use start_when (NaN: never started),
+ * start_duration (NaN: none) and stop_when of the voice; `source`, start_offset, playback_rate and the loop fields are ignored.
+ * The oscillator's phase is the running sum of 2*pi*f[n]/fs (:150-156); the device forms it as a blocked prefix sum in double,
+ * which agrees with the reference's sample-by-sample sum to ~1e-10 rad: within 1e-7 of the reference's samples for sine,
+ * sawtooth and triangle, while a square wave may switch one frame early or late at an edge. */
+typedef enum gac_source_kind { GAC_SOURCE_BUFFER = 0, GAC_SOURCE_CONSTANT = 1, GAC_SOURCE_OSCILLATOR = 2 } gac_source_kind;
 
 /* A bus = fan-in AudioNodeInput (AudioNodeInput.cs:100-138) followed by a chain of ops
  * (typically one GainNode), connected to the destination, to another bus, or read by further chains.
@@ -214,11 +235,20 @@ typedef struct gac_bus_desc {
   const gac_op_desc* ops;
   int32_t target;        /* where the bus output is connected: 0 = the destination, k > 0 = an input of bus
                             k-1 (bus hierarchies, GraphAudio.Kit/AudioBus.cs:76-114), -1 = nowhere directly
-                            (it is only consumed by chains with input = this bus + 1)                      */
+                            (it is only consumed by chains with input = this bus + 1, or by parameters)    */
   int32_t n_inputs;      /* connection order at the bus fan-in (AudioNodeInput.cs:118-137): entries >= 0  */
   const int32_t* inputs; /* are bus indices, entries < 0 are ~voice_index.  NULL = the voices routed here
                             in index order, then the buses targeting this one in index order              */
+  int32_t flags;         /* GAC_BUS_*                                                                      */
+  int32_t reserved;
+  const int32_t* input_slots; /* ChannelMergerNode (Nodes/ChannelMergerNode.cs): one entry per `inputs` entry, or NULL.
+                            0 = an ordinary fan-in connection; 1 / 2 = the connection goes to merger input 0 / 1: channel 0
+                            of what that input mixes becomes the bus's left / right channel.  (Mergers of more than two
+                            inputs are outside the accelerated path.)                                      */
 } gac_bus_desc;
+/* the fan-in has ONE channel (Explicit 1: the input of an AudioParam, AudioParam.cs:60-62): mono inputs are added as they are,
+ * stereo inputs as (L + R) / sqrt(2) (AudioNodeInput.cs:214-228) */
+#define GAC_BUS_MONO_INPUT 1
 
 typedef struct gac_graph_desc {
   int32_t n_voices;

@@ -33,11 +33,11 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_version_and_struct_layouts():
-    assert N.lib().gac_version() == 5
+    assert N.lib().gac_version() == 6
     # gac_event must be bit-compatible with AutomationEvent (AudioParam.cs:360-367): int, float, float, (pad), double, double
     assert C.sizeof(N.gac_event) == 32
     assert N.gac_event.time.offset == 16 and N.gac_event.time_constant.offset == 24
-    assert C.sizeof(N.gac_param) == 16
+    assert C.sizeof(N.gac_param) == 32
     assert C.sizeof(N.gac_context_desc) == 32
     assert C.sizeof(N.gac_stats) == 176
 
@@ -227,30 +227,62 @@ def test_product_package_never_imports_or_links_the_oracle():
     assert "ga_oracle" not in needed
 
 
-def test_param_modulation_is_refused_by_the_device_mirror():
+def test_param_modulation_flattens_into_a_mono_bus():
+    """oscillator -> gain -> OTHER.Gain : the modulator's branch becomes a voice routed to a GAC_BUS_MONO_INPUT bus that feeds
+    nothing but the parameter (AudioParam.cs:60-62: the parameter's input is Explicit, one channel)"""
     ctx = G.OfflineAudioContext(48000, _record_only=True)
-    a, b = G.GainNode(ctx), G.GainNode(ctx)
-    with pytest.raises(G.NotSupportedException):
-        a.Connect(b.Gain)
+    src = G.AudioBufferSourceNode(ctx)
+    src.Buffer = G.PlayableAudioBuffer.FromChannelArrays([np.zeros(256, np.float32)], 48000)
+    amp = G.GainNode(ctx)
+    src.Connect(amp).Connect(ctx.Destination)
+    src.Start()
+    lfo, depth = G.OscillatorNode(ctx), G.GainNode(ctx)
+    lfo.Connect(depth)
+    depth.Connect(amp.Gain)
+    lfo.Start()
+    voices, buses, dest_inputs, targets, inputs = ctx._topology_full()
+    assert len(voices) == 2 and len(buses) == 1
+    assert ctx._bus_flags == [N.GAC_BUS_MONO_INPUT] and targets == [-1]
+    assert amp.Gain._input_node._bus_index == 0
+    lfo_voice = [v for v in voices if isinstance(v[0], G.OscillatorNode)][0]
+    assert lfo_voice[1] == [depth] and lfo_voice[2] == 0
+    # a modulator that is not connected anywhere leaves the graph as it was
+    ctx2 = G.OfflineAudioContext(48000, _record_only=True)
+    s2 = G.AudioBufferSourceNode(ctx2)
+    s2.Buffer = G.PlayableAudioBuffer.FromChannelArrays([np.zeros(256, np.float32)], 48000)
+    s2.Connect(ctx2.Destination)
+    s2.Start()
+    G.OscillatorNode(ctx2)
+    assert len(ctx2._topology()[0]) == 1
 
 
-def test_unaccelerated_node_types_are_refused_never_rendered_as_silence():
-    for make in (lambda c: G.OscillatorNode(c), lambda c: G.ConstantSourceNode(c), lambda c: G.ChannelSplitterNode(c, 2),
-                 lambda c: G.ChannelMergerNode(c, 2)):
-        ctx = G.OfflineAudioContext(48000, _record_only=True)
-        n = make(ctx)
-        g = G.GainNode(ctx)
-        n.Connect(g).Connect(ctx.Destination)
-        with pytest.raises(G.NotSupportedException):
-            ctx._topology()
-    # ... while such a node that does NOT reach the destination leaves the graph renderable
+def test_splitter_and_merger_flatten_into_channel_ops_and_input_slots():
+    """source -> splitter ; output 0 -> gain -> merger input 1 ; output 1 -> merger input 0 (a channel swap with one gain)"""
     ctx = G.OfflineAudioContext(48000, _record_only=True)
     s = G.AudioBufferSourceNode(ctx)
-    s.Buffer = G.PlayableAudioBuffer.FromChannelArrays([np.zeros(256, np.float32)], 48000)
-    s.Connect(ctx.Destination)
+    s.Buffer = G.PlayableAudioBuffer.FromChannelArrays([np.zeros(256, np.float32)] * 2, 48000)
+    sp, mg, g = G.ChannelSplitterNode(ctx, 2), G.ChannelMergerNode(ctx, 2), G.GainNode(ctx)
+    s.Connect(sp)
+    sp.Connect(g, 0, 0)
+    g.Connect(mg, 0, 1)
+    sp.Connect(mg, 1, 0)
+    mg.Connect(ctx.Destination)
     s.Start()
-    G.OscillatorNode(ctx)
-    assert len(ctx._topology()[0]) == 1
+    voices, buses, dest_inputs, targets, inputs = ctx._topology_full()
+    # bus 0: the splitter's input (no ops), bus 1: the merger (no ops); two chains fed by bus 0 starting with a channel pick
+    assert len(buses) == 2 and buses[0] == [] and buses[1] == []
+    fed = [v for v in voices if v[0] is None]
+    assert len(fed) == 2 and all(v[3] == 0 and v[2] == 1 for v in fed)
+    picks = sorted((v[1][0].Index, len(v[1])) for v in fed)
+    assert picks == [(0, 2), (1, 1)]
+    assert sorted(ctx._bus_slots[1]) == [1, 2] and ctx._bus_slots[0] is None
+    with pytest.raises(G.NotSupportedException):
+        c3 = G.OfflineAudioContext(48000, _record_only=True)
+        m3 = G.ChannelMergerNode(c3, 4)
+        x = G.GainNode(c3)
+        x.Connect(m3, 0, 2)
+        m3.Connect(c3.Destination)
+        c3._topology()
 
 
 def test_k6_segment_planner():

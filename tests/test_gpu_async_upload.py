@@ -73,7 +73,7 @@ def test_deferred_ir_preparation_survives_early_buffer_destroy_and_unused_irs():
         unused = G.ConvolverNode(ctx)  # prepared (deferred) but never connected: its IR is never used by a render
         unused.Buffer = G.PlayableAudioBuffer.FromChannelArrays([a for a, _ in pu], fs)
         if destroy_ir_buffer_early:
-            h = irbuf._handles.pop(ctx._serial)
+            h = irbuf._handles.pop((ctx._serial, 0))
             ctx._owned_buffers.remove(h)
             check(L.gac_buffer_destroy(h))  # the handle is gone for the caller; the deferred preparation still reads the data
         s.Connect(conv).Connect(ctx.Destination)

@@ -23,7 +23,7 @@ GAC_ERR_NCCL = -8
 GAC_ERR_UNSUPPORTED = -9
 
 GAC_EVENT_EPOCH = 4
-GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER, GAC_OP_DELAY, GAC_OP_PANNER, GAC_OP_CHANNEL = 1, 2, 3, 4, 5, 6
+GAC_OP_BIQUAD, GAC_OP_GAIN, GAC_OP_CONVOLVER, GAC_OP_DELAY, GAC_OP_PANNER, GAC_OP_CHANNEL, GAC_OP_GATE = 1, 2, 3, 4, 5, 6, 7
 GAC_SAMPLE_S16, GAC_SAMPLE_S24, GAC_SAMPLE_S32, GAC_SAMPLE_F32 = 0, 1, 2, 3
 
 fp = C.POINTER(C.c_float)

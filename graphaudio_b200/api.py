@@ -270,6 +270,9 @@ class AudioNode:
         self._out: List["AudioNode"] = []
         self._n_inputs, self._n_outputs = n_inputs, n_outputs
         self._born_frames = getattr(context, "_frames_rendered", 0)  # frames the context had rendered when the node was created
+        self._edge_on = {}    # id(destination) -> first quantum of the connection (0: before anything was rendered)
+        self._edge_off = {}   # id(destination) -> quantum from which the connection is gone (Disconnect after rendering began)
+        self._first_live_q = None  # first quantum in which the node was pulled (set when a graph that contains it is flattened)
         context._nodes.append(self)
 
     def _existed_in_a_render(self):
@@ -309,13 +312,15 @@ class AudioNode:
         if isinstance(destination, ChannelMergerNode):
             destination._slots[id(self)] = inputIndex + 1
         if destination not in self._out:
-            # Between successive Render calls the device path re-renders the timeline from frame 0 with the CURRENT graph, so an edit
-            # is only exact if it cannot change what was already rendered: parameter edits (epochs), sources started / stopped later,
-            # and new branches whose nodes did not exist before.  Re-wiring nodes that already took part in a render is refused.
-            if self._upstream_existed_in_a_render():
-                self.Context._unsupported_edit = "Connect() of a node that already took part in a Render call"
+            # Between successive Render calls the device path re-renders the timeline from frame 0 with the CURRENT graph.  A
+            # connection made after rendering began acts from the next unprocessed quantum on (Nodes/AudioNode.cs:109-123 posts it to
+            # the render thread): the edge carries that quantum and is flattened into a GAC_OP_GATE.
             self._out.append(destination)
             destination._in.append(self)
+            self._edge_on[id(destination)] = self.Context._q_now()
+        elif id(destination) in self._edge_off:
+            # the reference would resume nodes that were not pulled in between where they stopped: not reproduced
+            self.Context._unsupported_edit = "re-connecting a connection that was removed after rendering began"
         return destination
 
     def _output_node(self, outputIndex):
@@ -325,12 +330,26 @@ class AudioNode:
         return [v for v in self.__dict__.values() if isinstance(v, AudioParam)]
 
     def Disconnect(self, destination: Optional["AudioNode"] = None):
+        q = self.Context._q_now()
         for d in ([destination] if destination is not None else list(self._out)):
-            if d in self._out:
-                if self._upstream_existed_in_a_render():
-                    self.Context._unsupported_edit = "Disconnect() of a node that already took part in a Render call"
-                self._out.remove(d)
-                d._in.remove(self)
+            if d in self._out and id(d) not in self._edge_off:
+                if q > self._edge_on.get(id(d), 0):
+                    # rendered quanta keep the connection; it ends with the next unprocessed quantum (Nodes/AudioNode.cs:125-147).  What
+                    # hangs on it alone is no longer pulled from then on, which a cut reproduces as long as it is not connected again.
+                    self._edge_off[id(d)] = q
+                else:  # nothing was rendered with this connection
+                    self._out.remove(d)
+                    d._in.remove(self)
+                    self._edge_on.pop(id(d), None)
+
+    def _gates(self, d):
+        """GAC_OP_GATE pseudo-nodes for the connection self -> d (none for a connection that always existed)."""
+        g = []
+        if self._edge_on.get(id(d), 0) > 0:
+            g.append(_Gate(0, self._edge_on[id(d)]))
+        if id(d) in self._edge_off:
+            g.append(_Gate(1, self._edge_off[id(d)]))
+        return g
 
 
 class AudioDestinationNode(AudioNode):
@@ -450,6 +469,19 @@ class OscillatorType:  # Nodes/OscillatorNode.cs:207-213
     Sine, Square, Sawtooth, Triangle = range(4)
 
 
+class _Gate:
+    """A connection window in a flattened chain (GAC_OP_GATE): kind 0 = from quantum q on, 1 = until quantum q."""
+
+    def __init__(self, kind, q):
+        self.kind, self.q = int(kind), int(q)
+
+    def __eq__(self, other):
+        return isinstance(other, _Gate) and (self.kind, self.q) == (other.kind, other.q)
+
+    def __repr__(self):
+        return f"_Gate({'until' if self.kind else 'from'} {self.q})"
+
+
 class _ParamInputNode(AudioNode):
     """The AudioNodeInput an AudioParam owns (Explicit, one channel: AudioParam.cs:60-62): what AudioNode.Connect(param) connects
     to.  Flattened into a GAC_BUS_MONO_INPUT bus that feeds nothing but the parameter."""
@@ -542,9 +574,9 @@ class ConvolverNode(AudioNode):
         self.Normalize = True          # Nodes/ConvolverNode.cs:87
         self.EnableTrueStereo = True   # :95
         self._buffer = None
-        self._ir = None
-        self._ir_args = (1, 1)
-        self._ir_members = {}          # member index -> prepared impulse response (multi-GPU contexts)
+        # the impulse responses the node ran with over time: ConvolverNode.Buffer set again between two Render calls builds new
+        # convolvers (cleared delay lines) from the next unprocessed quantum on (Nodes/ConvolverNode.cs:51-77)
+        self._epochs = []              # dicts: q0, buffer (or None), args (normalize, true stereo), irs {member: handle}
 
     @property
     def Buffer(self):
@@ -554,41 +586,45 @@ class ConvolverNode(AudioNode):
     def Buffer(self, value):  # :25-79: the convolvers are built here, with the Normalize value of this moment
         if value is self._buffer:
             return
-        if self._existed_in_a_render():  # an impulse-response swap mid-timeline (fresh delay lines from that quantum on, :51-77)
-            self.Context._unsupported_edit = "ConvolverNode.Buffer changed after the node took part in a Render call"
-        if value is None:
-            self._buffer, self._ir = None, None
-            return
         ctx = self.Context
-        if value.SampleRate != ctx.SampleRate:  # Nodes/ConvolverNode.cs:48-49 (the library checks again)
+        if value is not None and value.SampleRate != ctx.SampleRate:  # Nodes/ConvolverNode.cs:48-49 (the library checks again)
             raise InvalidOperationException(
                 "Impulse response buffer sample rate must match the audio context sample rate. "
                 f"Impulse response buffer sample rate: {value.SampleRate}, Audio context sample rate: {ctx.SampleRate}.")
-        if ctx._record_only:
-            self._buffer, self._ir = value, None
-            return
-        self._ir_args = (int(self.Normalize), int(self.EnableTrueStereo))  # the convolvers are built with the values of THIS moment
-        self._ir_members = {}
-        if ctx._root()._group is not None:  # multi-GPU context: prepared per member at Render (on the device that renders the voice)
-            self._buffer, self._ir = value, None
-            return
-        self._buffer, self._ir = value, self._ir_for(0, value)
+        # the convolvers are built with the Normalize / EnableTrueStereo values of THIS moment (:87-95)
+        ep = dict(q0=ctx._q_now() if self._first_live_q is not None else 0, buffer=value,
+                  args=(int(self.Normalize), int(self.EnableTrueStereo)), irs={})
+        if self._epochs and self._epochs[-1]["q0"] >= ep["q0"]:
+            self._epochs[-1] = ep  # set again before anything further was rendered
+        else:
+            self._epochs.append(ep)
+        self._buffer = value
+        # prepare now (the reference does the work in the setter); a multi-GPU context prepares per member at Render, on the device
+        # that renders the voice
+        if value is not None and not ctx._record_only and ctx._root()._group is None:
+            self._epoch_ir(ep, 0)
+
+    @property
+    def _ir(self):
+        """prepared impulse response of the current epoch in member 0 (None without a Buffer)"""
+        if not self._epochs or self._epochs[-1]["buffer"] is None or self.Context._record_only:
+            return None
+        return self._epoch_ir(self._epochs[-1], 0)
 
 
-def _convolver_ir_for(self, member, buffer=None):
-    """The prepared impulse response of this ConvolverNode in member `member` of its context (prepared on first use)."""
-    buffer = buffer if buffer is not None else self._buffer
-    h = self._ir_members.get(member)
+def _convolver_epoch_ir(self, ep, member):
+    """The prepared impulse response of epoch `ep` of this ConvolverNode in member `member` of its context (prepared on first use)."""
+    h = ep["irs"].get(member)
     if h is None:
         ctx = self.Context
         out = C.c_void_p()
-        check(N.lib().gac_ir_prepare(ctx._root()._member_handle(member), buffer._handle(ctx, member), self._ir_args[0], self._ir_args[1], C.byref(out)))
+        check(N.lib().gac_ir_prepare(ctx._root()._member_handle(member), ep["buffer"]._handle(ctx, member), ep["args"][0], ep["args"][1], C.byref(out)))
         ctx._root()._owned_irs.append(out.value)
-        h = self._ir_members[member] = out.value
+        h = ep["irs"][member] = out.value
     return h
 
 
-ConvolverNode._ir_for = _convolver_ir_for
+ConvolverNode._epoch_ir = _convolver_epoch_ir
 
 
 class CudaConvolverNode:
@@ -730,6 +766,22 @@ class OfflineAudioContext:
             t = t + inc
         return t
 
+    def _op_descs(self, nodes, keep, member=0):
+        """gac_op_desc entries of a flattened chain (a ConvolverNode that was given several impulse responses over time yields one
+        op per epoch)"""
+        out = []
+        for n in nodes:
+            if isinstance(n, ConvolverNode):
+                eps = n._epochs or [dict(q0=0, buffer=None, args=(1, 1), irs={})]
+                for k, ep in enumerate(eps):
+                    op = N.gac_op_desc()
+                    op.kind, op.filter_type, op.aux = N.GAC_OP_CONVOLVER, (1 if k else 0), float(ep["q0"] if k else 0)
+                    op.ir = n._epoch_ir(ep, member) if ep["buffer"] is not None else None
+                    out.append(op)
+            else:
+                out.append(self._op_desc(n, keep, member))
+        return out
+
     def _op_desc(self, node, keep, member=0):
         op = N.gac_op_desc()
         q = self._q_now()
@@ -739,14 +791,13 @@ class OfflineAudioContext:
         elif isinstance(node, GainNode):
             op.kind = N.GAC_OP_GAIN
             op.p0 = node.Gain._desc(keep, q)
-        elif isinstance(node, ConvolverNode):
-            op.kind = N.GAC_OP_CONVOLVER
-            op.ir = node._ir if (member == 0 and node._ir is not None) else (node._ir_for(member) if node._buffer is not None else None)
+        elif isinstance(node, _Gate):
+            op.kind, op.filter_type, op.aux = N.GAC_OP_GATE, node.kind, float(node.q)
         elif isinstance(node, DelayNode):
             op.kind, op.aux = N.GAC_OP_DELAY, node.MaxDelayTime
             op.p0 = node.DelayTime._desc(keep, q)
         elif isinstance(node, StereoPannerNode):
-            op.kind, op.aux = N.GAC_OP_PANNER, float(-(-node._born_frames // 128))
+            op.kind, op.aux = N.GAC_OP_PANNER, float(node._first_live_q or 0)
             op.p0 = node.Pan._desc(keep, q)
         elif isinstance(node, _SplitterOutput):
             op.kind, op.aux = N.GAC_OP_CHANNEL, float(node.Index)
@@ -785,6 +836,11 @@ class OfflineAudioContext:
             if isinstance(n, AudioBufferSourceNode) and n.PlaybackRate._input_node is not None and n.PlaybackRate._input_node._in:
                 raise NotSupportedException("a modulated PlaybackRate is outside the accelerated path (the resampler's phase is replayed on the host)")
 
+        q_now = self._q_now()
+        for n in self._nodes:  # the first quantum in which a node is pulled: it is pulled while it reaches the destination
+            if id(n) in live and n._first_live_q is None:
+                n._first_live_q = q_now
+
         def outs(n):
             return [d for d in n._out if id(d) in live]
 
@@ -809,7 +865,11 @@ class OfflineAudioContext:
                 o = outs(n)
                 if len(o) != 1 or o[0] is dest or fan_in(o[0]):
                     return chain
+                chain.extend(n._gates(o[0]))  # a connection made / removed after rendering began (GAC_OP_GATE)
                 n = o[0]
+
+        def last_node(chain):
+            return [x for x in chain if not isinstance(x, _Gate)][-1]
 
         def new_bus(ops):
             bus_ops.append(ops)
@@ -823,8 +883,10 @@ class OfflineAudioContext:
             if len(o) == 1:
                 edge_code[(id(tail), id(o[0]))] = code if code_is_bus else ~code
                 if code_is_bus:
+                    bus_ops[code] = bus_ops[code] + tail._gates(o[0])
                     pending_bus_target.append((code, o[0]))
                 else:
+                    voices[code][1] = voices[code][1] + tail._gates(o[0])
                     pending_voice_target.append((code, o[0]))
                 return
             # fan-out (or a dead end): every branch reads a bus
@@ -839,14 +901,15 @@ class OfflineAudioContext:
         def branch(bus, tail, d):
             """the edge tail -> d of a signal that lives in bus `bus`"""
             if d is dest or fan_in(d):
-                voices.append([None, [], -2, bus])  # pass-through chain: the bus output as an input of d
+                voices.append([None, tail._gates(d), -2, bus])  # pass-through chain: the bus output as an input of d
                 v = len(voices) - 1
                 edge_code[(id(tail), id(d))] = ~v
                 pending_voice_target.append((v, d))
             else:
                 ch = chain_from(d)
-                voices.append([None, ch, -2, bus])
-                emit(ch[-1], False, len(voices) - 1)
+                first_real = ch[0]
+                voices.append([None, (tail._gates(d) if not isinstance(first_real, _SplitterOutput) else []) + ch, -2, bus])
+                emit(last_node(ch), False, len(voices) - 1)
 
         pending_voice_target, pending_bus_target = [], []
         # 1. source-fed voices: one per live out-edge of every source
@@ -855,14 +918,14 @@ class OfflineAudioContext:
                 continue
             for d in outs(n):
                 if d is dest or fan_in(d):
-                    voices.append([n, [], -2, -1])
+                    voices.append([n, n._gates(d), -2, -1])
                     v = len(voices) - 1
                     edge_code[(id(n), id(d))] = ~v
                     pending_voice_target.append((v, d))
                 else:
                     ch = chain_from(d)
-                    voices.append([n, ch, -2, -1])
-                    emit(ch[-1], False, len(voices) - 1)
+                    voices.append([n, n._gates(d) + ch, -2, -1])
+                    emit(last_node(ch), False, len(voices) - 1)
         # 2. buses: every live fan-in node, with the chain behind it
         for n in self._nodes:
             if id(n) not in live or not fan_in(n):
@@ -874,7 +937,7 @@ class OfflineAudioContext:
             bus_of_head[id(n)] = b
             if isinstance(n, _ParamInputNode):
                 n._bus_index = b
-            emit(ch[-1], True, b)
+            emit(last_node(ch), True, b)
         # 3. resolve targets now that every fan-in has its bus index
         for v, d in pending_voice_target:
             voices[v][2] = -1 if d is dest else bus_of_head[id(d)]
@@ -922,8 +985,9 @@ class OfflineAudioContext:
             v = vdesc[i]
             if isinstance(src, _ScheduledSourceNode):
                 when = src._when if src._started else math.nan
-                if src._started and src._start_frames > 0:
-                    when = max(when, self._block_time(-(-src._start_frames // 128)))
+                q_first = max(-(-src._start_frames // 128), src._first_live_q or 0)
+                if src._started and q_first > 0:
+                    when = max(when, self._block_time(q_first))
                 osc = isinstance(src, OscillatorNode)
                 v.source = None
                 v.source_kind = N.GAC_SOURCE_OSCILLATOR if osc else N.GAC_SOURCE_CONSTANT
@@ -936,8 +1000,10 @@ class OfflineAudioContext:
                     when = math.nan
                 else:
                     when = src._when
-                    if src._start_frames > 0:  # started between Render calls: not before the first quantum that was still unprocessed
-                        when = max(when, self._block_time(-(-src._start_frames // 128)))
+                    # started, or first connected, between Render calls: the node is first processed in a later quantum and begins there
+                    q_first = max(-(-src._start_frames // 128), src._first_live_q or 0)
+                    if q_first > 0:
+                        when = max(when, self._block_time(q_first))
                 v.loop, v.loop_start, v.loop_end = int(bool(src.Loop)), src.LoopStart, src.LoopEnd
                 v.source = src.Buffer._handle(self, member) if src.Buffer is not None else None
                 v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop
@@ -945,15 +1011,17 @@ class OfflineAudioContext:
             else:
                 v.source = None
                 v.playback_rate = 1.0
-            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep, member) for o in ops])
+            descs = self._op_descs(ops, keep, member)
+            arr = (N.gac_op_desc * max(1, len(descs)))(*descs)
             keep.append(arr)
-            v.n_ops, v.ops, v.bus, v.input = len(ops), arr, bus, input_bus + 1
+            v.n_ops, v.ops, v.bus, v.input = len(descs), arr, bus, input_bus + 1
         bdesc = (N.gac_bus_desc * max(1, len(buses)))()
         for i, ops in enumerate(buses):
-            arr = (N.gac_op_desc * max(1, len(ops)))(*[self._op_desc(o, keep, member) for o in ops])
+            descs = self._op_descs(ops, keep, member)
+            arr = (N.gac_op_desc * max(1, len(descs)))(*descs)
             inp = (C.c_int32 * max(1, len(bus_inputs[i])))(*bus_inputs[i])
             keep += [arr, inp]
-            bdesc[i].n_ops, bdesc[i].ops = len(ops), arr
+            bdesc[i].n_ops, bdesc[i].ops = len(descs), arr
             bdesc[i].target, bdesc[i].n_inputs, bdesc[i].inputs = bus_targets[i], len(bus_inputs[i]), inp
             bdesc[i].flags = self._bus_flags[i]
             if self._bus_slots[i] is not None and voice_range is None:

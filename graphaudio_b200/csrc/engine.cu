@@ -868,7 +868,19 @@ static int copy_ops(gac_context* ctx, int n, const gac_op_desc* ops, std::vector
       case GAC_OP_GAIN:
         if ((rc = copy_param(ops[i].p0, &o.p0, "gain.gain"))) return rc;
         break;
+      case GAC_OP_GATE:
+        o.aux = ops[i].aux;
+        if (o.ftype < 0 || o.ftype > 1 || !(o.aux >= 0.0)) return fail(GAC_ERR_INVALID_ARGUMENT, "bad connection window");
+        break;
       case GAC_OP_CONVOLVER:
+        o.aux = ops[i].aux;
+        if (o.ftype == 1) {
+          if (i == 0 || (*out)[i - 1].kind != GAC_OP_CONVOLVER) return fail(GAC_ERR_INVALID_ARGUMENT, "a convolver epoch must follow the convolver op it continues");
+          if (!(o.aux >= 1.0) || o.aux <= (*out)[i - 1].aux) return fail(GAC_ERR_INVALID_ARGUMENT, "convolver epochs must carry increasing quantum indices >= 1");
+        } else {
+          o.ftype = 0;
+          o.aux = 0;
+        }
         o.ir = ops[i].ir;
         if (o.ir && o.ir->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "impulse response belongs to another context");
         if (o.ir && !(o.ir->nch == 1 || o.ir->nch == 2 || (o.ir->nch == 4 && o.ir->true_stereo))) return fail(GAC_ERR_UNSUPPORTED, "discrete impulse responses with %d channels are outside the accelerated path", o.ir->nch);
@@ -1629,7 +1641,17 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     std::vector<size_t> gains, biquads, convs, delays, panners;
     for (size_t i = 0; i < sigs.size(); i++) {
       if (!sigs[i].ops || pos >= sigs[i].ops->size()) continue;
-      switch ((*sigs[i].ops)[pos].kind) {
+      const OpH& opx = (*sigs[i].ops)[pos];
+      if (opx.kind == GAC_OP_GATE) {
+        // a connection that exists only from / until a quantum: outside the window the next input sees nothing connected
+        Sig& s = sigs[i];
+        const int64_t f = std::min<int64_t>(env.Npad, (int64_t)opx.aux * 128);
+        if (opx.ftype == 0) s.lo = std::max(s.lo, f); else s.hi = std::min(s.hi, f);
+        if (s.hi <= s.lo) s.lo = s.hi = 0;
+        continue;
+      }
+      if (opx.kind == GAC_OP_CONVOLVER && opx.ftype == 1) continue;  // a later epoch: handled with the convolver op it continues
+      switch (opx.kind) {
         case GAC_OP_GAIN: gains.push_back(i); break;
         case GAC_OP_BIQUAD: biquads.push_back(i); break;
         case GAC_OP_CONVOLVER: convs.push_back(i); break;
@@ -1926,37 +1948,38 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
     }
     // ---------------- ConvolverNode (K5, K6, K7)
     if (!convs.empty()) {
+      // the epochs of a ConvolverNode whose Buffer was set again between Render calls follow its op (filter_type 1)
+      auto epochs_of = [&](const Sig& s) {
+        std::vector<const OpH*> e;
+        e.push_back(&(*s.ops)[pos]);
+        for (size_t q = pos + 1; q < s.ops->size() && (*s.ops)[q].kind == GAC_OP_CONVOLVER && (*s.ops)[q].ftype == 1; q++) e.push_back(&(*s.ops)[q]);
+        return e;
+      };
       {
         std::vector<const gac_ir*> need, reused;
         for (size_t k : convs)
-          if (const gac_ir* ir = (*sigs[k].ops)[pos].ir) {
-            need.push_back(ir);
-            // double-length spectra pay for themselves only when the impulse response serves more than one render: an IR whose
-            // (deferred) preparation happens in this very render keeps the single-length plan
-            if (ir->prepared) reused.push_back(ir);
-          }
+          for (const OpH* op : epochs_of(sigs[k]))
+            if (const gac_ir* ir = op->ir) {
+              need.push_back(ir);
+              // double-length spectra pay for themselves only when the impulse response serves more than one render: an IR whose
+              // (deferred) preparation happens in this very render keeps the single-length plan
+              if (ir->prepared) reused.push_back(ir);
+            }
         int rc = prepare_irs(env, need);
         if (rc) return rc;
         if (ctx->mixed_segments && (rc = ensure_h2b_batch(env, reused))) return rc;
       }
       std::vector<ConvItem> items;
       auto& zj = env.keep->make<GainJob>();
+      struct Window {  // what a later epoch contributes: frames [w0, w1) of `from` (null: silence) replace the signal's rows
+        float* dst[2];
+        const float* from[2];
+        int64_t w0, w1;
+      };
+      std::vector<Window> windows;
       for (size_t k = 0; k < convs.size(); k++) {
         Sig& s = sigs[convs[k]];
-        const OpH& op = (*s.ops)[pos];
-        if (!op.ir) {
-          // ConvolverNode without a Buffer clears its output (ConvolverNode.cs:107-119): silence from here on
-          GainJob g;
-          g.sig[0] = s.p[0];
-          g.sig[1] = s.p[1];
-          g.gain = nullptr;
-          g.gain_const = 0.f;
-          g.lo = 0;
-          g.hi = 0;
-          zj.push_back(g);
-          s.lo = s.hi = 0;
-          continue;
-        }
+        const std::vector<const OpH*> eps = epochs_of(s);
         const float* gtab = nullptr;
         float gconst = 1.0f;
         auto f = env.fused.find(&s);
@@ -1965,66 +1988,114 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
           gconst = f->second.second;
           env.fused.erase(f);
         }
-        const gac_ir* ir = op.ir;
-        auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
-        auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(ir->M2)) : (const float2*)nullptr; };
         const float* in0 = s.lazy[0] ? s.lazy[0] : s.p[0];
         const float* in1 = s.lazy[0] ? s.lazy[1] : s.p[1];
         s.lazy[0] = s.lazy[1] = nullptr;  // the convolver's output is written to the signal's own rows
-        ConvItem it;
-        it.P = ir->P;
-        it.M2 = ir->d_H2 ? ir->M2 : 0;
-        it.Lh = ir->Lh;
-        const float2* h2b = nullptr;
-        if (it.M2 > 0 && ctx->mixed_segments) {
-          plan_segments(env.QB, it.M2, it.Lh, &it.n_big, &it.n_small);
-          if (it.n_big > 0) h2b = ir->d_H2b;  // (prepared above for the whole batch)
-          if (!h2b) it.n_big = 0;
+        const int in_ch = s.ch;
+        const int64_t in_lo = s.lo, in_hi = s.hi;
+        int64_t out_lo = env.Npad, out_hi = 0;
+        int layout = -1;
+        for (size_t e = 0; e < eps.size(); e++) {
+          const OpH& op = *eps[e];
+          const int64_t w0 = std::min<int64_t>(env.Npad, (int64_t)op.aux * 128);
+          const int64_t w1 = e + 1 < eps.size() ? std::min<int64_t>(env.Npad, (int64_t)eps[e + 1]->aux * 128) : env.Npad;
+          float* out0 = s.p[0];
+          float* out1 = s.p[1];
+          // with several epochs EVERY epoch renders into rows of its own and its window is copied back afterwards: the signal's rows
+          // are the input of all of them, and epochs of different impulse-response lengths run in different kernel batches
+          if (eps.size() > 1) {
+            if (w1 <= w0) continue;
+            if (op.ir) {
+              float* tmp = nullptr;
+              int rc = env.scratch->alloc(&tmp, 2 * (size_t)env.Npad);
+              if (rc) return rc;
+              out0 = tmp;
+              out1 = tmp + env.Npad;
+            }
+            windows.push_back(Window{{s.p[0], s.p[1]}, {op.ir ? out0 : nullptr, op.ir ? out1 : nullptr}, w0, w1});
+          }
+          if (!op.ir) {
+            if (eps.size() == 1) {
+              // ConvolverNode without a Buffer clears its output (ConvolverNode.cs:107-119): silence (until a later epoch)
+              GainJob g;
+              g.sig[0] = s.p[0];
+              g.sig[1] = s.p[1];
+              g.gain = nullptr;
+              g.gain_const = 0.f;
+              g.lo = 0;
+              g.hi = 0;
+              zj.push_back(g);
+            }
+            continue;
+          }
+          const gac_ir* ir = op.ir;
+          const int lay = ir->true_stereo ? 4 : ir->nch;
+          if (layout >= 0 && lay != layout)
+            return fail(GAC_ERR_UNSUPPORTED, "the impulse responses a ConvolverNode is given over time must share the channel layout on the accelerated path");
+          layout = lay;
+          out_lo = std::min(out_lo, w0);
+          out_hi = std::max(out_hi, w1);
+          auto Hch = [&](int c) { return (const float2*)(ir->d_H + (size_t)c * ir->P16 * ctx->B); };
+          auto H2ch = [&](int c) { return ir->d_H2 ? (const float2*)(ir->d_H2 + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(ir->M2)) : (const float2*)nullptr; };
+          ConvItem it;
+          it.P = ir->P;
+          it.M2 = ir->d_H2 ? ir->M2 : 0;
+          it.Lh = ir->Lh;
+          const float2* h2b = nullptr;
+          if (it.M2 > 0 && ctx->mixed_segments) {
+            plan_segments(env.QB, it.M2, it.Lh, &it.n_big, &it.n_small);
+            if (it.n_big > 0) h2b = ir->d_H2b;  // (prepared above for the whole batch)
+            if (!h2b) it.n_big = 0;
+          }
+          auto H2bch = [&](int c) { return h2b ? h2b + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(2 * ir->M2) : (const float2*)nullptr; };
+          // an epoch's convolvers are created when the Buffer is set: they see the input from their first quantum on
+          it.lo = std::max(in_lo, w0);
+          it.hi = in_hi;
+          if (it.hi <= it.lo) it.lo = it.hi = 0;
+          it.gain_tab = gtab;
+          it.gain_const = gconst;
+          if (ir->nch == 1) {
+            // input forced to 1 channel (ConvolverNode.cs:72-76): a stereo upstream is down-mixed (L + R) * (1/sqrt(2)),
+            // a mono upstream is taken as is (AudioNodeInput.cs:188-228); the mono result is copied to both rows
+            it.n_fwd = 1;
+            it.fwd[0] = {in0, in_ch == 2 ? in1 : nullptr, 1.0f / sqrtf(2.0f)};
+            it.n_mac = 1;
+            it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
+            it.n_inv = 1;
+            it.inv[0] = {0, -1, out0, out1};
+            s.ch = 1;
+          } else if (ir->nch == 2) {
+            it.n_fwd = 2;
+            it.fwd[0] = {in0, nullptr, 1.0f};
+            it.fwd[1] = {in1, nullptr, 1.0f};
+            it.n_mac = 2;
+            it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
+            it.mac[1] = {1, Hch(1), H2ch(1), H2bch(1)};
+            it.n_inv = 2;
+            it.inv[0] = {0, -1, out0, nullptr};
+            it.inv[1] = {1, -1, out1, nullptr};
+            s.ch = 2;
+          } else {
+            // true stereo (ConvolverNode.cs:127-144): L = c0(inL) + c2(inR), R = c1(inL) + c3(inR); X spectra shared
+            it.n_fwd = 2;
+            it.fwd[0] = {in0, nullptr, 1.0f};
+            it.fwd[1] = {in1, nullptr, 1.0f};
+            it.n_mac = 4;
+            it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
+            it.mac[1] = {1, Hch(2), H2ch(2), H2bch(2)};
+            it.mac[2] = {0, Hch(1), H2ch(1), H2bch(1)};
+            it.mac[3] = {1, Hch(3), H2ch(3), H2bch(3)};
+            it.n_inv = 2;
+            it.inv[0] = {0, 1, out0, nullptr};
+            it.inv[1] = {2, 3, out1, nullptr};
+            s.ch = 2;
+          }
+          items.push_back(it);
         }
-        auto H2bch = [&](int c) { return h2b ? h2b + (size_t)c * (ctx->B + 1) * fft2_h2_row_elems(2 * ir->M2) : (const float2*)nullptr; };
-        it.lo = s.lo;
-        it.hi = s.hi;
-        it.gain_tab = gtab;
-        it.gain_const = gconst;
-        if (ir->nch == 1) {
-          // input forced to 1 channel (ConvolverNode.cs:72-76): a stereo upstream is down-mixed (L + R) * (1/sqrt(2)),
-          // a mono upstream is taken as is (AudioNodeInput.cs:188-228); the mono result is copied to both rows
-          it.n_fwd = 1;
-          it.fwd[0] = {in0, s.ch == 2 ? in1 : nullptr, 1.0f / sqrtf(2.0f)};
-          it.n_mac = 1;
-          it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
-          it.n_inv = 1;
-          it.inv[0] = {0, -1, s.p[0], s.p[1]};
-          s.ch = 1;
-        } else if (ir->nch == 2) {
-          it.n_fwd = 2;
-          it.fwd[0] = {in0, nullptr, 1.0f};
-          it.fwd[1] = {in1, nullptr, 1.0f};
-          it.n_mac = 2;
-          it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
-          it.mac[1] = {1, Hch(1), H2ch(1), H2bch(1)};
-          it.n_inv = 2;
-          it.inv[0] = {0, -1, s.p[0], nullptr};
-          it.inv[1] = {1, -1, s.p[1], nullptr};
-          s.ch = 2;
-        } else {
-          // true stereo (ConvolverNode.cs:127-144): L = c0(inL) + c2(inR), R = c1(inL) + c3(inR); X spectra shared
-          it.n_fwd = 2;
-          it.fwd[0] = {in0, nullptr, 1.0f};
-          it.fwd[1] = {in1, nullptr, 1.0f};
-          it.n_mac = 4;
-          it.mac[0] = {0, Hch(0), H2ch(0), H2bch(0)};
-          it.mac[1] = {1, Hch(2), H2ch(2), H2bch(2)};
-          it.mac[2] = {0, Hch(1), H2ch(1), H2bch(1)};
-          it.mac[3] = {1, Hch(3), H2ch(3), H2bch(3)};
-          it.n_inv = 2;
-          it.inv[0] = {0, 1, s.p[0], nullptr};
-          it.inv[1] = {2, 3, s.p[1], nullptr};
-          s.ch = 2;
-        }
-        items.push_back(it);
-        s.lo = 0;  // ConvolverNode always marks its output non-silent (ConvolverNode.cs:153)
-        s.hi = env.Npad;
+        // ConvolverNode always marks its output non-silent while it has convolvers (ConvolverNode.cs:153), and clears it while it
+        // has none (:107-119); over several epochs the flagged range is the hull of the epochs that had a Buffer
+        s.lo = out_hi > out_lo ? out_lo : 0;
+        s.hi = out_hi > out_lo ? out_hi : 0;
       }
       if (!zj.empty()) {
         GainJob* dz = nullptr;
@@ -2036,6 +2107,11 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       TRACE_MARK("conv: items built");
       int rc = conv_batch(env, items);
       if (rc) return rc;
+      for (const Window& w : windows)  // later epochs take over from their first quantum on
+        for (int c = 0; c < 2; c++) {
+          if (w.from[c]) CU(cudaMemcpyAsync(w.dst[c] + w.w0, w.from[c] + w.w0, sizeof(float) * (size_t)(w.w1 - w.w0), cudaMemcpyDeviceToDevice, ctx->stream));
+          else CU(cudaMemsetAsync(w.dst[c] + w.w0, 0, sizeof(float) * (size_t)(w.w1 - w.w0), ctx->stream));
+        }
       TRACE_MARK("conv: queued");
     }
   }

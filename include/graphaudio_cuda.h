@@ -158,6 +158,11 @@ typedef enum gac_op_kind {
   GAC_OP_CONVOLVER = 3,/* ConvolverNode     Nodes/ConvolverNode.cs:102-155   */
   GAC_OP_DELAY = 4,    /* DelayNode         Nodes/DelayNode.cs:43-149        */
   GAC_OP_PANNER = 5,   /* StereoPannerNode  Nodes/StereoPannerNode.cs:36-153 */
+  GAC_OP_GATE = 7,     /* a CONNECTION that was made or removed between two Render calls (AudioNode.Connect / Disconnect posted to
+                          the render thread, Nodes/AudioNode.cs:109-147, act from the next unprocessed quantum on): the signal
+                          reaches the next node only from quantum `aux` on (filter_type 0) / only before quantum `aux`
+                          (filter_type 1); outside that window the next node's input sees no connection, i.e. a cleared,
+                          silent-flagged block (AudioNodeInput.cs:102-107)                                                    */
   GAC_OP_CHANNEL = 6   /* one output of a ChannelSplitterNode (Nodes/ChannelSplitterNode.cs): the signal becomes channel `aux` of
                           its input as a ONE-channel signal (silence if the input has no such channel).  Only valid as the first
                           op of a chain fed by a bus (the splitter's input is that bus)                                       */
@@ -176,14 +181,19 @@ typedef enum gac_filter_type { /* FilterType, Nodes/BiQuadFilterNode.cs:288-298 
 
 typedef struct gac_op_desc {
   int32_t kind;        /* gac_op_kind                                                         */
-  int32_t filter_type; /* BIQUAD: gac_filter_type                                             */
+  int32_t filter_type; /* BIQUAD: gac_filter_type.  GATE: 0 "from", 1 "until".  CONVOLVER: 0, or 1 = this op is a LATER
+                          EPOCH of the ConvolverNode described by the preceding CONVOLVER op: ConvolverNode.Buffer was set
+                          again between two Render calls, so from quantum `aux` on the node runs new PartitionedConvolvers
+                          (cleared delay lines and overlap, Nodes/ConvolverNode.cs:51-77) built from this op's `ir`; the
+                          epochs of a node must share the channel layout                                              */
   gac_param p0;        /* BIQUAD: Frequency (a-rate)   GAIN: Gain (a-rate)   DELAY: DelayTime in seconds
                           (a-rate)   PANNER: Pan (a-rate, -1 .. 1)                             */
   gac_param p1;        /* BIQUAD: Q (a-rate)                                                   */
   gac_param p2;        /* BIQUAD: Gain in dB (k-rate)                                          */
   const gac_ir* ir;    /* CONVOLVER: prepared impulse response; NULL ≙ ConvolverNode without a
                           Buffer, which outputs silence (ConvolverNode.cs:107-119)             */
-  double aux;          /* DELAY: maxDelayTime in seconds, (0, 10] (DelayNode.cs:22-29).  PANNER: index of the first quantum the
+  double aux;          /* GATE / later CONVOLVER epoch: the quantum index (above).
+                          DELAY: maxDelayTime in seconds, (0, 10] (DelayNode.cs:22-29).  PANNER: index of the first quantum the
                           node processes (0; later for a node created between two Render calls): its ClampedMax input has
                           no upstream block to count channels from in that quantum (AudioNodeInput.cs:109,140-168).  Else 0 */
 } gac_op_desc;

@@ -1328,6 +1328,20 @@ int ora_connect(void* c, int src, int dst) {  // AudioNode.Connect :68-73 (appli
   return 0;
 }
 
+int ora_disconnect(void* c, int src, int dst) {  // AudioNode.Disconnect(destination) :78-84,129-147; dst < 0: every connection of output 0
+  Node* a = nodeAt(c, src);
+  if (!a || a->outputs.empty()) return -1;
+  Output* o = a->outputs[0].get();
+  if (dst < 0) {
+    while (!o->to.empty()) disconnect(o, o->to.back());
+    return 0;
+  }
+  Node* b = nodeAt(c, dst);
+  if (!b || b->inputs.empty()) return -1;
+  disconnect(o, b->inputs[0].get());
+  return 0;
+}
+
 int ora_splitter_create(void* c, int n) {  // ChannelSplitterNode(context, numberOfOutputs) :12-20
   auto* ctx = (Context*)c;
   if (n < 1 || n > 32) return -1;

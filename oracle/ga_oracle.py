@@ -66,6 +66,7 @@ def lib():
     L.ora_scheduled_stop.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.ora_oscillator_set_type.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_connect.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ora_disconnect.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_param_set_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
     L.ora_param_event.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     L.ora_param_cancel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
@@ -274,6 +275,10 @@ class AudioNode:
         if lib().ora_connect(self._ctx._h, self._id, destination._id) != 0:
             raise ArgumentOutOfRangeException("cannot connect")
         return destination
+
+
+    def Disconnect(self, destination=None):  # Nodes/AudioNode.cs:78-84
+        lib().ora_disconnect(self._ctx._h, self._id, destination._id if destination is not None else -1)
 
 
 class AudioDestinationNode(AudioNode):

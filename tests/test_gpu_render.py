@@ -404,7 +404,89 @@ def test_parameter_edits_and_late_starts_between_successive_render_calls():
     assert np.abs(yg - yo).max() <= 1e-5
 
 
-def test_rewiring_after_a_render_is_refused_not_approximated():
+def _run_both(run):
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    return run(G), run(O)
+
+
+def test_rewiring_between_render_calls_acts_from_the_next_quantum():
+    """Connect / Disconnect after rendering began (Nodes/AudioNode.cs:109-147 post them to the render thread; the offline context
+    drains them in front of the next ProcessBlock, AudioContextBase.cs:272-284): a node that already rendered gets a second
+    consumer (a reverb send added late), a voice is taken off the bus, a source that existed all along is connected late."""
+    fs = 48000
+
+    def run(api):
+        ctx = api.OfflineAudioContext(fs)
+        bus = api.GainNode(ctx)
+        bus.Gain.Value = 0.5
+        bus.Connect(ctx.Destination)
+        voices = []
+        for v in range(3):
+            s = api.AudioBufferSourceNode(ctx)
+            s.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(1400 + 2 * v + c, 30000) for c in range(2)], fs)
+            g = api.GainNode(ctx)
+            g.Gain.Value = 0.3 + 0.1 * v
+            s.Connect(g).Connect(bus)
+            s.Start()
+            voices.append((s, g))
+        late = api.AudioBufferSourceNode(ctx)   # created and started now, connected after the first Render call
+        late.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(1410, 9000)], fs)
+        late.Start()
+        out = [ctx.Render(3000)]
+        # (1) a send from a gain that already rendered into a new convolver
+        conv, wet = api.ConvolverNode(ctx), api.GainNode(ctx)
+        conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.decay_ir(1420 + c, 128 * 70) for c in range(2)], fs)
+        wet.Gain.Value = 0.4
+        voices[0][1].Connect(conv).Connect(wet).Connect(ctx.Destination)
+        # (2) voice 1 leaves the bus; (3) the idle source joins it
+        voices[1][1].Disconnect(bus)
+        late.Connect(bus)
+        out.append(ctx.Render(7000))
+        voices[2][0].Disconnect()               # the source itself is unplugged from its gain
+        out.append(ctx.Render(128 * 120))
+        return np.concatenate(out, axis=1)
+
+    yg, yo = _run_both(run)
+    assert np.abs(yo).max() > 0.1
+    assert np.abs(yg - yo).max() <= 1e-5, np.abs(yg - yo).max()
+
+
+def test_impulse_response_swapped_between_render_calls():
+    """ConvolverNode.Buffer set again mid-timeline (Nodes/ConvolverNode.cs:25-79): new PartitionedConvolvers with cleared delay
+    lines take over from the next unprocessed quantum — the old tail is cut, the new convolvers have not seen the earlier input;
+    then Buffer = null (the node clears its output) and a third impulse response of a different length"""
+    fs = 48000
+
+    def run(api):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(1430 + c, 40000) for c in range(2)], fs)
+        g = api.GainNode(ctx)
+        g.Gain.SetValueAtTime(0.8, 0.0)
+        g.Gain.LinearRampToValueAtTime(0.3, 0.5)
+        conv = api.ConvolverNode(ctx)
+        conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.decay_ir(1440 + c, 128 * 90) for c in range(2)], fs)
+        s.Connect(g).Connect(conv).Connect(ctx.Destination)
+        s.Start()
+        out = [ctx.Render(5000)]
+        conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.decay_ir(1450 + c, 128 * 70) for c in range(2)], fs)
+        out.append(ctx.Render(9000))
+        conv.Buffer = None
+        out.append(ctx.Render(2000))
+        conv.Normalize = False
+        conv.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.decay_ir(1460 + c, 2000) * np.float32(0.02) for c in range(2)], fs)
+        out.append(ctx.Render(12000))
+        return np.concatenate(out, axis=1)
+
+    yg, yo = _run_both(run)
+    assert np.abs(yo[:, :5000]).max() > 0.05 and np.abs(yo[:, 5200:14000]).max() > 0.05 and np.abs(yo[:, 16200:]).max() > 0.01
+    assert np.abs(yo[:, 14100:15900]).max() == 0.0
+    assert np.abs(yg - yo).max() <= 1e-5, np.abs(yg - yo).max()
+
+
+def test_reconnecting_a_removed_connection_is_refused_not_approximated():
+    """the one re-wiring that is NOT reproduced: nodes that nothing pulled for a while would resume where they stopped"""
     import graphaudio_b200 as G
     fs = 48000
     ctx = G.OfflineAudioContext(fs)
@@ -414,10 +496,12 @@ def test_rewiring_after_a_render_is_refused_not_approximated():
     s.Connect(g).Connect(ctx.Destination)
     s.Start()
     ctx.Render(512)
-    extra = G.GainNode(ctx)
-    g.Connect(extra).Connect(ctx.Destination)  # a node that already rendered gets a second consumer
+    g.Disconnect(ctx.Destination)
+    ctx.Render(512)
+    g.Connect(ctx.Destination)
     with pytest.raises(G.NotSupportedException):
         ctx.Render(512)
+    ctx.Dispose()
 
 
 def test_distinct_contexts_render_concurrently_from_distinct_threads():

@@ -223,25 +223,32 @@ __global__ void __launch_bounds__(32) k_biquad_lanes(const BiquadJob* __restrict
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Shared-coefficient variant (biquad.cu: "Shared-coefficient path"): the 16 voices of a group run the same filter over the same
-// non-silent range, so the coefficients come from ONE class stream and every lane reads its row's samples where they lie (the
-// source buffer itself for a rate-1 source, BiquadJob::in) — 16 bytes per voice and frame instead of ~90.
-// Stage = one 64-frame chunk.  Rows are contiguous in time and a lane owns a row, so moving a chunk is a transposition.  Done
-// naively — every lane touching its own row — each memory instruction is 32 separate accesses (a first version with per-lane
-// 16-byte cp.async / STG.128 ran at ~130 cycles per frame), and per-lane bulk copies are worse: cp.async.bulk takes uniform operands,
-// so 32 different row addresses become a 32-trip serialisation loop around every copy (ncu: 12x more instructions executed there
-// than in the recursion).  Instead the WARP moves one row per instruction: lane l copies frames 2l, 2l + 1 of row r (cp.async, 8
-// bytes per lane; see "Moving a chunk" in the kernel) into a 272-byte row of the stage (the 16-byte pad makes every lane's own
-// LDS.128 / STS.128 conflict-free), and the results — written over the samples they consumed — leave the same way with
-// sector-wide stores.  Three stages: two chunks of loads in flight.
-// Same speculate / verify / repair protocol, same state records (one per 32-frame slab), same verification kernel as above.
+// non-silent range, so the coefficients come from ONE class stream and the samples are read where they lie (the source buffer
+// itself for a rate-1 source, BiquadJob::in) — 16 bytes per voice and frame instead of ~90.
+//
+// CTA = TWO warps with different jobs, because the recursion w = x - a1*w1 - a2*w2 (:137) is a 12-cycle dependent chain per frame and
+// everything a warp does besides it lands in the same in-order pipe (measured: 20 cycles per frame for the bare chain, 60-80 with
+// the loads, the output sums and the stores in the same warp):
+//   warp 0, the CHAIN warp: one lane per (voice, channel) row; per 64-frame stage it loads its operands into registers one 16-frame
+//     step ahead (across the loop's back edge: ptxas sinks loads that are consumed in the same trip down to their use), runs the
+//     chain and writes w over the samples it consumed; it also records / compares the slab states of the speculate-verify-repair
+//     protocol (same protocol, same records, same verification kernel as the stream-fed variant above);
+//   warp 1, the MOVER warp: brings the stages in (cp.async, completion signalled to the chain warp through an mbarrier), and, for
+//     chunks whose output counts, forms y = b0*w + b1*w[n-1] + b2*w[n-2] (:138) — embarrassingly parallel once w exists — and
+//     stores it.  Both directions are transpositions (rows are contiguous in time, lanes own rows); done naively every memory
+//     instruction is 32 separate accesses, and per-lane bulk copies are worse (cp.async.bulk takes uniform operands: 32 row
+//     addresses become a 32-trip serialisation loop).  Here instruction (m, k) lets the four lanes of quad q = lane / 4 move the
+//     m-th 32-byte sector of row q + 8k, 8 bytes each: a lane only ever needs the pointers of its quad's four rows.
+// Stage row: [8 bytes unused | w[-2], w[-1] of the previous chunk | 64 samples] = 272 bytes (the 16-byte lead keeps every lane's
+// LDS.128 / STS.128 aligned and conflict-free, and gives the mover warp its two samples of history contiguously).
 constexpr int kChunk = kBqChunkFrames;  // 64
-constexpr int kShStages = 3;
+constexpr int kShStages = 4;  // the chain warp works on chunk s, chunks s + 1, s + 2 have landed or are landing, chunk s - 1's
+                              // output sums are being formed: its stage is refilled only behind them
 constexpr int kShRowBytes = kChunk * 4 + 16;
 constexpr int kShXBytes = 32 * kShRowBytes;
 constexpr int kShStageBytes = kShXBytes + kBqChunkBytes + (kChunk / 32) * 256;
-constexpr size_t kShSmem = (size_t)kShStages * kShStageBytes;
-constexpr int kShSlots = 6 * 148;     // 37 KB per single-warp CTA: six per SM.  The kernel is latency-bound (issue slots ~25 % used), so
-                                      // more concurrent segments shorten it as long as a segment stays longer than its warm-up
+constexpr size_t kShSmem = (size_t)kShStages * kShStageBytes + 128;  // + 2 x 4 mbarriers + the per-stage control words
+constexpr int kShSlots = 4 * 148;     // 49.5 KB per CTA: four per SM = one chain warp and one mover warp per scheduler
 static_assert(kShStageBytes % 16 == 0, "stage alignment");
 
 __device__ __forceinline__ void bq_cp8(uint32_t dst, const void* src) {
@@ -250,14 +257,24 @@ __device__ __forceinline__ void bq_cp8(uint32_t dst, const void* src) {
 __device__ __forceinline__ void bq_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void bq_cp_arrive(uint32_t bar) {  // arrives on `bar` once this thread's earlier cp.async have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bq_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bq_cta_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 template <bool REPAIR>
-__global__ void __launch_bounds__(32) k_biquad_lanes_shared(const BiquadJob* __restrict__ jobs, const BqGroup* __restrict__ groups,
+__global__ void __launch_bounds__(64) k_biquad_lanes_shared(const BiquadJob* __restrict__ jobs, const BqGroup* __restrict__ groups,
                                                             const unsigned char* __restrict__ cs, size_t cs_stride, int64_t n_frames, int seg_chunks,
                                                             int n_seg, int warm_chunks, float2* __restrict__ states, float2* __restrict__ slab_states,
                                                             const int* __restrict__ first_bad, const int* __restrict__ link_bad) {
   extern __shared__ __align__(128) unsigned char sh_smem[];
-  const int lane = threadIdx.x;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sh_smem + kShStages * kShStageBytes);   // full[3], done[3]
+  volatile int* ctrl = reinterpret_cast<volatile int*>(sh_smem + kShStages * kShStageBytes + 16 * kShStages);  // [st]: frames done | rejoined << 16
+  const int lane = threadIdx.x & 31;
+  const bool mover = threadIdx.x >= 32;
   const int g = blockIdx.x;
   const BqGroup grp = groups[g];
   const bool valid = (lane >> 1) < grp.count;
@@ -265,171 +282,197 @@ __global__ void __launch_bounds__(32) k_biquad_lanes_shared(const BiquadJob* __r
   const int ch = lane & 1;
   const int64_t lo = jobs[j].lo, hi = jobs[j].hi;  // the same for every job of the group
   if (hi <= lo) return;
-  const float* __restrict__ xin = jobs[j].in[ch] ? jobs[j].in[ch] : jobs[j].sig[ch];
-  float* __restrict__ yout = jobs[j].sig[ch];
+  const float* xin = jobs[j].in[ch] ? jobs[j].in[ch] : jobs[j].sig[ch];
+  float* yout = jobs[j].sig[ch];
   const unsigned char* __restrict__ cls = cs + (size_t)grp.cls * cs_stride + (size_t)(lo / kChunk) * kBqChunkBytes;
   const int total_chunks = (int)((hi - lo) / kChunk);  // ranges are multiples of 128 frames
   float2* st_group = states + (size_t)g * n_seg * 64;
   float2* slab_group = slab_states + ((size_t)g * (size_t)(n_frames / kSlab) + (size_t)(lo / kSlab)) * 32;  // [32-frame slab relative to lo][row]
   const uint32_t stage0 = bq_smem_u32(sh_smem);
-  // Moving a chunk: instruction (m, k), m = 0..7, k = 0..3: the four lanes of quad q = lane / 4 move the m-th 32-byte sector of row
-  // q + 8k, 8 bytes each — eight rows x one sector per instruction, every row's 256 bytes after the eight m's.  A lane thus only ever
-  // needs the pointers of ITS quad's four rows, fetched once from their owners (a table in shared memory or a shuffle per row and
-  // instruction put ~35 cycles of latency in front of every copy: 30 % of the kernel).
-  const int quad = lane >> 2, tq = lane & 3;
-  const float* xrow[4];
-  float* yrow[4];
+  const uint32_t bar_full = bq_smem_u32(bars), bar_done = bar_full + 8 * kShStages;
+  // the mover's rows: the eight lanes of octet o = lane / 8 move one 128-byte line of row o + 4k per instruction, 16 bytes each
+  // (lane r owns row r: the pointers come from there).  Whole lines, not sectors: what limits a latency-bound stream per SM is the
+  // number of requests in flight, and a request is a line whether one or four of its sectors are wanted.
+  const int oct = lane >> 3, t8 = lane & 7;
+  const float* xrow[8];
+  float* yrow[8];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    xrow[k] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(xin), quad + 8 * k)) + 2 * tq;
-    yrow[k] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(yout), quad + 8 * k)) + 2 * tq;
+  for (int k = 0; k < 8; k++) {
+    xrow[k] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(xin), oct + 4 * k)) + 4 * t8;
+    yrow[k] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(yout), oct + 4 * k)) + 4 * t8;
   }
   const int n_rows = 2 * grp.count;  // rows that are stored
-  float w1 = 0.f, w2 = 0.f;
+  float w1 = 0.f, w2 = 0.f;         // (chain warp) the recursion's state
 
+  // One run: chunks [c_first, c_end) relative to lo, the first n_warm of them recursion only (nothing written).
+  // rejoin: stop as soon as the state after a slab equals the one the speculative pass recorded there; returns true then.
   auto run = [&](const int c_first, const int n_warm, const int c_end, const bool rejoin) -> bool {
     const int n_chunks = c_end - c_first;
-    auto issue = [&](int s) {
-      if (s < n_chunks) {
-        const uint32_t st = stage0 + (uint32_t)(s % kShStages) * kShStageBytes;
-        const bool own = s >= n_warm;  // the output coefficients are not needed while warming up
-        const int64_t off = lo + (int64_t)(c_first + s) * kChunk;
+    // both warps enter a run with quiescent barriers: nothing in flight, every phase at 0
+    bq_cta_sync();
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < 2 * kShStages; s++) bq_mbar_init(bar_full + 8 * s, 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    bq_cta_sync();
+    bool rejoined = false;
+    if (mover) {
+      auto issue = [&](int s) {
+        if (s < n_chunks) {
+          const uint32_t st = stage0 + (uint32_t)(s % kShStages) * kShStageBytes;
+          const bool own = s >= n_warm;  // the output coefficients are not needed while warming up
+          const int64_t off = lo + (int64_t)(c_first + s) * kChunk;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const float* src = xrow[k] + off;
-          const uint32_t dst = st + (uint32_t)((quad + 8 * k) * kShRowBytes + tq * 8);
+          for (int k = 0; k < 8; k++) {
+            const float* src = xrow[k] + off;
+            const uint32_t dst = st + (uint32_t)((oct + 4 * k) * kShRowBytes + 16 + t8 * 16);
 #pragma unroll
-          for (int m = 0; m < kChunk / 8; m++) bq_cp8(dst + m * 32, src + m * 8);
-        }
-        const unsigned char* cc = cls + (size_t)(c_first + s) * kBqChunkBytes;
-        const int n16 = (own ? kBqChunkBytes : kBqChunkABytes) / 16;
-        for (int q = lane; q < n16; q += 32) bq_cp16(st + kShXBytes + (uint32_t)q * 16u, cc + (size_t)q * 16);
-        if (REPAIR && rejoin && own)  // the speculative pass's slab states of this chunk: (kChunk / 32) * 256 bytes
-          for (int q = lane; q < (kChunk / 32) * 16; q += 32)
-            bq_cp16(st + kShXBytes + kBqChunkBytes + (uint32_t)q * 16u,
-                    reinterpret_cast<const unsigned char*>(slab_group + (size_t)(c_first + s) * (kChunk / 32) * 32) + (size_t)q * 16);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");  // (empty groups keep the count uniform)
-    };
-    // rows [0, n_rows) of a finished chunk leave the way they came: quad q stores one sector of row q + 8k per instruction
-    auto store_rows = [&](const unsigned char* stp, int64_t base, int n_frames_done) {
-      __syncwarp();  // every lane's results are in the stage
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (quad + 8 * k < n_rows) {
-          const unsigned char* src = stp + (quad + 8 * k) * kShRowBytes + tq * 8;
-          float* dst = yrow[k] + base;
-#pragma unroll
-          for (int m = 0; m < kChunk / 8; m++)
-            if (8 * m < n_frames_done) *reinterpret_cast<float2*>(dst + m * 8) = *reinterpret_cast<const float2*>(src + m * 32);
-        }
-      }
-    };
-    issue(0);
-    issue(1);
-    for (int s = 0; s < n_chunks; s++) {
-      if (s == n_warm && !REPAIR) st_group[((size_t)blockIdx.y * 2 + 0) * 32 + lane] = make_float2(w1, w2);  // state at the segment's first own frame
-      __syncwarp();  // every lane is done with the stage that is refilled next (chunk s - 1: computed and stored)
-      issue(s + 2);
-      asm volatile("cp.async.wait_group 2;" ::: "memory");
-      __syncwarp();  // the rows and the class chunk were copied by all lanes
-      const int sti = s % kShStages;
-      unsigned char* stp = sh_smem + (size_t)sti * kShStageBytes;
-      float4* __restrict__ xs = reinterpret_cast<float4*>(stp + (size_t)lane * kShRowBytes);
-      const float4* __restrict__ A4 = reinterpret_cast<const float4*>(stp + kShXBytes + ch * (kBqChunkABytes / 2));  // two frames per element
-      const float4* __restrict__ Bc = reinterpret_cast<const float4*>(stp + kShXBytes + kBqChunkABytes) + ch * (kChunk + 1);
-      const float2* __restrict__ specs = reinterpret_cast<const float2*>(stp + kShXBytes + kBqChunkBytes);
-      const bool own = s >= n_warm;
-      const int64_t base = lo + (int64_t)(c_first + s) * kChunk;
-      // The chunk runs in four 16-frame steps.  The dependent chain w -> FMUL -> FADD -> FADD -> w costs ~12 cycles per frame and
-      // nothing else may sit in it: the operands of step k + 1 are loaded into registers during step k and handed over across the
-      // loop's back edge (ptxas sinks loads that are consumed in the same trip down to their use, where their ~30 cycle latency
-      // lands inside the chain).
-      constexpr int NS = kChunk / 16;
-      auto load16 = [&](float (&vx)[16], float (&v1)[16], float (&v2)[16], int step) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const float4 v = xs[step * 4 + q];
-          vx[4 * q] = v.x;
-          vx[4 * q + 1] = v.y;
-          vx[4 * q + 2] = v.z;
-          vx[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const float4 a = A4[step * 8 + q];  // (a1, a2) of two consecutive frames
-          v1[2 * q] = a.x;
-          v2[2 * q] = a.y;
-          v1[2 * q + 1] = a.z;
-          v2[2 * q + 1] = a.w;
-        }
-      };
-      auto ystep = [&](const float (&wv)[18], int step) {  // y of the 16 frames of `step` from their w values, over the consumed samples
-#pragma unroll
-        for (int i4 = 0; i4 < 4; i4++) {
-          float y[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int i = 4 * i4 + e;
-            const float4 b = Bc[step * 16 + i];
-            y[e] = b.x * wv[i + 2] + b.y * wv[i + 1] + b.z * wv[i];  // :138  y = b0*w + b1*w1 + b2*w2
+            for (int m = 0; m < kChunk / 32; m++) bq_cp16(dst + m * 128, src + m * 32);
           }
-          xs[step * 4 + i4] = make_float4(y[0], y[1], y[2], y[3]);
+          const unsigned char* cc = cls + (size_t)(c_first + s) * kBqChunkBytes;
+          const int n16 = (own ? kBqChunkBytes : kBqChunkABytes) / 16;
+          for (int q = lane; q < n16; q += 32) bq_cp16(st + kShXBytes + (uint32_t)q * 16u, cc + (size_t)q * 16);
+          if (REPAIR && rejoin && own)  // the speculative pass's slab states of this chunk: (kChunk / 32) * 256 bytes
+            for (int q = lane; q < (kChunk / 32) * 16; q += 32)
+              bq_cp16(st + kShXBytes + kBqChunkBytes + (uint32_t)q * 16u,
+                      reinterpret_cast<const unsigned char*>(slab_group + (size_t)(c_first + s) * (kChunk / 32) * 32) + (size_t)q * 16);
+          bq_cp_arrive(bar_full + 8 * (s % kShStages));
         }
       };
-      float cx[16], c1[16], c2[16];
-      load16(cx, c1, c2, 0);
-      bool rejoined = false;
-      int done_steps = NS;
-#pragma unroll 1
-      for (int step = 0; step < NS; step++) {
-        float nx[16], n1[16], n2[16];
-        load16(nx, n1, n2, step + 1 < NS ? step + 1 : step);  // consumed by the NEXT trip (the last trip's load is a dummy)
-        float wo[18];
-        wo[0] = w2;
-        wo[1] = w1;
+      for (int s = 0; s < kShStages - 1; s++) issue(s);
+      for (int s = 0; s < n_chunks && !rejoined; s++) {
+        const int sti = s % kShStages;
+        bq_mbar_wait(bar_done + 8 * sti, (uint32_t)((s / kShStages) & 1));  // the chain warp has written w over this stage's samples
+        const int c = ctrl[sti];
+        const int frames_done = c & 0xffff;
+        rejoined = (c >> 16) != 0;
+        // the next request goes out BEFORE this chunk's output sums: into the stage of chunk s - 1, whose sums are done.  (Behind
+        // them, a chunk's samples had one chunk of chain time to arrive and the chain warp spent half its time waiting.)
+        if (!rejoined) issue(s + kShStages - 1);
+        if (s >= n_warm && frames_done > 0) {
+          const unsigned char* stp = sh_smem + (size_t)sti * kShStageBytes;
+          const float4* __restrict__ Bc = reinterpret_cast<const float4*>(stp + kShXBytes + kBqChunkABytes) + (oct & 1) * (kChunk + 1);
+          const int64_t base = lo + (int64_t)(c_first + s) * kChunk;
+          // this lane's frames 32m + 4t .. 32m + 4t + 3 (m = 0, 1) belong to channel oct & 1 in every one of its rows: 8 coefficient sets
+          float4 b[kChunk / 8];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const float w = cx[i] - c1[i] * w1 - c2[i] * w2;  // :137
-          w2 = w1;
-          w1 = w;
-          wo[i + 2] = w;
-        }
-        // the output sums behind the chain, not inside it: issued between the chain's instructions their coefficient loads (which
-        // ptxas places right in front of their use) stalled the in-order pipe, chain included (59 cycles per frame against 20
-        // for the bare chain)
-        if (own) ystep(wo, step);
+          for (int m = 0; m < kChunk / 32; m++)
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          cx[i] = nx[i];
-          c1[i] = n1[i];
-          c2[i] = n2[i];
-        }
-        if (own && (step & 1)) {  // a 32-frame slab is complete: its end state is recorded / compared
-          float2* rec = slab_group + ((size_t)(c_first + s) * (kChunk / 32) + (step >> 1)) * 32 + lane;
-          if (REPAIR && rejoin) {
-            const float2 spec = specs[(step >> 1) * 32 + lane];
-            const bool same = __float_as_uint(spec.x) == __float_as_uint(w1) && __float_as_uint(spec.y) == __float_as_uint(w2);
-            if (__all_sync(0xffffffffu, same)) {
-              // re-joined the speculative trajectory: everything behind this slab is already right
-              rejoined = true;
-              done_steps = step + 1;
-              break;
+            for (int e = 0; e < 4; e++) b[4 * m + e] = Bc[32 * m + 4 * t8 + e];
+          // (a row's sums are independent of each other: all of a row's loads first, then the arithmetic, then the stores — with
+          // per-sum conditions in the loop the compiler keeps every LDS -> FMUL -> FADD -> FADD -> ST sequence to itself, ~100
+          // cycles each, and the mover warp became the bottleneck of the pair)
+          const bool whole = frames_done == kChunk;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            if (oct + 4 * k >= n_rows) continue;
+            const unsigned char* row = stp + (oct + 4 * k) * kShRowBytes + 16 + t8 * 16;
+            float* dst = yrow[k] + base;
+            float4 wc[kChunk / 32], y[kChunk / 32];
+            float2 wp[kChunk / 32];
+#pragma unroll
+            for (int m = 0; m < kChunk / 32; m++) {
+              wc[m] = *reinterpret_cast<const float4*>(row + m * 128);      // w[n .. n + 3]
+              wp[m] = *reinterpret_cast<const float2*>(row + m * 128 - 8);  // w[n - 2], w[n - 1]
             }
+#pragma unroll
+            for (int m = 0; m < kChunk / 32; m++) {  // :138  y = b0*w + b1*w1 + b2*w2
+              y[m].x = b[4 * m].x * wc[m].x + b[4 * m].y * wp[m].y + b[4 * m].z * wp[m].x;
+              y[m].y = b[4 * m + 1].x * wc[m].y + b[4 * m + 1].y * wc[m].x + b[4 * m + 1].z * wp[m].y;
+              y[m].z = b[4 * m + 2].x * wc[m].z + b[4 * m + 2].y * wc[m].y + b[4 * m + 2].z * wc[m].x;
+              y[m].w = b[4 * m + 3].x * wc[m].w + b[4 * m + 3].y * wc[m].z + b[4 * m + 3].z * wc[m].y;
+            }
+#pragma unroll
+            for (int m = 0; m < kChunk / 32; m++)
+              if (whole || 32 * m < frames_done) *reinterpret_cast<float4*>(dst + m * 32) = y[m];
           }
-          *rec = make_float2(w1, w2);
         }
-      }
-      if (own) store_rows(stp, base, done_steps * 16);
-      if (rejoined) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing may still be landing when the next run starts
         __syncwarp();
-        return true;
+        if (rejoined)  // the chunks already requested but never consumed: their arrivals must be in before the barriers are initialised again
+          for (int o = s + 1; o < n_chunks && o < s + kShStages - 1; o++) bq_mbar_wait(bar_full + 8 * (o % kShStages), (uint32_t)((o / kShStages) & 1));
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+      for (int s = 0; s < n_chunks && !rejoined; s++) {
+        if (s == n_warm && !REPAIR) st_group[((size_t)blockIdx.y * 2 + 0) * 32 + lane] = make_float2(w1, w2);  // state at the segment's first own frame
+        const int sti = s % kShStages;
+        bq_mbar_wait(bar_full + 8 * sti, (uint32_t)((s / kShStages) & 1));
+        unsigned char* stp = sh_smem + (size_t)sti * kShStageBytes;
+        float4* __restrict__ xs = reinterpret_cast<float4*>(stp + (size_t)lane * kShRowBytes + 16);
+        const float4* __restrict__ A4 = reinterpret_cast<const float4*>(stp + kShXBytes + ch * (kBqChunkABytes / 2));  // two frames per element
+        const float2* __restrict__ specs = reinterpret_cast<const float2*>(stp + kShXBytes + kBqChunkBytes);
+        const bool own = s >= n_warm;
+        // the two samples of history the mover's output sums need in front of this chunk
+        *reinterpret_cast<float2*>(stp + (size_t)lane * kShRowBytes + 8) = make_float2(w2, w1);
+        constexpr int NS = kChunk / 16;
+        auto load16 = [&](float (&vx)[16], float (&v1)[16], float (&v2)[16], int step) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float4 v = xs[step * 4 + q];
+            vx[4 * q] = v.x;
+            vx[4 * q + 1] = v.y;
+            vx[4 * q + 2] = v.z;
+            vx[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const float4 a = A4[step * 8 + q];  // (a1, a2) of two consecutive frames
+            v1[2 * q] = a.x;
+            v2[2 * q] = a.y;
+            v1[2 * q + 1] = a.z;
+            v2[2 * q + 1] = a.w;
+          }
+        };
+        float cx[16], c1[16], c2[16];
+        load16(cx, c1, c2, 0);
+        int done_steps = NS;
+#pragma unroll 1
+        for (int step = 0; step < NS; step++) {
+          float nx[16], n1[16], n2[16];
+          load16(nx, n1, n2, step + 1 < NS ? step + 1 : step);  // consumed by the NEXT trip (the last trip's load is a dummy)
+          float wv[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const float w = cx[i] - c1[i] * w1 - c2[i] * w2;  // :137
+            w2 = w1;
+            w1 = w;
+            wv[i] = w;
+          }
+          if (own) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) xs[step * 4 + q] = make_float4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            cx[i] = nx[i];
+            c1[i] = n1[i];
+            c2[i] = n2[i];
+          }
+          if (own && (step & 1)) {  // a 32-frame slab is complete: its end state is recorded / compared
+            float2* rec = slab_group + ((size_t)(c_first + s) * (kChunk / 32) + (step >> 1)) * 32 + lane;
+            if (REPAIR && rejoin) {
+              const float2 spec = specs[(step >> 1) * 32 + lane];
+              const bool same = __float_as_uint(spec.x) == __float_as_uint(w1) && __float_as_uint(spec.y) == __float_as_uint(w2);
+              if (__all_sync(0xffffffffu, same)) {
+                // re-joined the speculative trajectory: everything behind this slab is already right
+                rejoined = true;
+                done_steps = step + 1;
+                break;
+              }
+            }
+            *rec = make_float2(w1, w2);
+          }
+        }
+        if (lane == 0) ctrl[sti] = (own ? done_steps * 16 : 0) | (rejoined ? 1 << 16 : 0);
+        __syncwarp();
+        bq_mbar_arrive(bar_done + 8 * sti);  // (release: w and the control word are visible to the mover behind its wait)
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    return false;
+    // the mover learns about a re-join from the control word; both leave the run together
+    // both warps leave the run together and with the same answer (each learnt of a re-join on its own: the chain warp found it, the
+    // mover read it from the chunk's control word)
+    bq_cta_sync();
+    return rejoined;
   };
 
   if (!REPAIR) {
@@ -439,14 +482,14 @@ __global__ void __launch_bounds__(32) k_biquad_lanes_shared(const BiquadJob* __r
     const int c_end = c_own + seg_chunks < total_chunks ? c_own + seg_chunks : total_chunks;
     const int c_first = seg == 0 ? c_own : (c_own - warm_chunks > 0 ? c_own - warm_chunks : 0);
     run(c_first, c_own - c_first, c_end, false);
-    st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
+    if (!mover) st_group[((size_t)seg * 2 + 1) * 32 + lane] = make_float2(w1, w2);
   } else {
     bool carry = false;
     for (int seg = first_bad[g]; seg < n_seg; seg++) {
       const int c_own = seg * seg_chunks;
       if (c_own >= total_chunks) break;
       if (!carry && !link_bad[(size_t)g * n_seg + seg]) continue;
-      if (!carry) {  // the last true state: what segment seg-1 ended with
+      if (!carry && !mover) {  // the last true state: what segment seg-1 ended with
         const float2 e = st_group[((size_t)(seg - 1) * 2 + 1) * 32 + lane];
         w1 = e.x;
         w2 = e.y;
@@ -529,8 +572,17 @@ void biquad_shared_scratch_sizes(int n_groups, int64_t n_frames, size_t* n_float
   *n_int = groups + groups * (size_t)n_seg;
 }
 void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups, int n_groups, const unsigned char* d_cs, size_t cs_stride,
-                                int64_t n_frames, float2* d_states, int* d_flags, cudaStream_t s) {
+                                int64_t n_frames, float2* d_states, int* d_flags, bool sequential, cudaStream_t s) {
   if (n_groups <= 0) return;
+  if (sequential) {
+    // filters that forget too slowly for speculative segments to re-join (constant low cutoff / high Q): one segment per group from
+    // the true initial state — exact by construction, nothing to verify or repair, and no speculative pass thrown away
+    GAC_SMEM_OPT_IN((k_biquad_lanes_shared<false>), kShSmem);
+    const int total_chunks = (int)((n_frames + kChunk - 1) / kChunk);
+    k_biquad_lanes_shared<false><<<dim3((unsigned)n_groups, 1), 64, kShSmem, s>>>(d_jobs, d_groups, d_cs, cs_stride, n_frames, total_chunks, 1, 0, d_states,
+                                                                              d_states + (size_t)n_groups * 64, nullptr, nullptr);
+    return;
+  }
   GAC_SMEM_OPT_IN((k_biquad_lanes_shared<false>), kShSmem);
   GAC_SMEM_OPT_IN((k_biquad_lanes_shared<true>), kShSmem);
   const unsigned groups = (unsigned)n_groups;
@@ -540,11 +592,11 @@ void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups
   float2* d_slab = d_states + (size_t)groups * n_seg * 64;
   int* d_first_bad = d_flags;
   int* d_link = d_flags + groups;
-  k_biquad_lanes_shared<false><<<dim3(groups, (unsigned)n_seg), 32, kShSmem, s>>>(d_jobs, d_groups, d_cs, cs_stride, n_frames, seg_chunks, n_seg,
+  k_biquad_lanes_shared<false><<<dim3(groups, (unsigned)n_seg), 64, kShSmem, s>>>(d_jobs, d_groups, d_cs, cs_stride, n_frames, seg_chunks, n_seg,
                                                                                  warm, d_states, d_slab, nullptr, nullptr);
   if (n_seg > 1) {
     k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad, d_link);
-    k_biquad_lanes_shared<true><<<groups, 32, kShSmem, s>>>(d_jobs, d_groups, d_cs, cs_stride, n_frames, seg_chunks, n_seg, warm, d_states, d_slab,
+    k_biquad_lanes_shared<true><<<groups, 64, kShSmem, s>>>(d_jobs, d_groups, d_cs, cs_stride, n_frames, seg_chunks, n_seg, warm, d_states, d_slab,
                                                             d_first_bad, d_link);
   }
 }

@@ -1860,7 +1860,20 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       }
       auto& sj = env.keep->make<BiquadJob>();   // jobs of the shared path, class after class
       auto& reps = env.keep->make<BiquadJob>();  // one representative per class
-      auto& groups = env.keep->make<BqGroup>();
+      auto& groups = env.keep->make<BqGroup>();  // speculative groups first, then the sequential ones
+      std::vector<BqGroup> slow_groups;
+      // A filter with constant parameters whose poles lie close to the unit circle forgets its state too slowly for speculative
+      // segments to re-join bit for bit (measured: a constant 200 Hz highpass never does).  Pole radius^2 = a2 = (1 - alpha) /
+      // (1 + alpha) for every RBJ type at unit shelf gain; the state decays by 2^-24 in 16.6 / -ln(r) frames.
+      auto forgets_slowly = [&](const BiquadJob& j) {
+        if (j.freq || j.q) return false;  // automated: unknown here, the verified speculation decides
+        const double f = std::min(std::max((double)j.freq_const, 1.0), ctx->fs / 2.0), q = std::max((double)j.q_const, 0.001);
+        const double w0 = 2.0 * 3.14159265358979323846 * f / ctx->fs, alpha = std::sin(w0) / (2.0 * q);
+        const double a2 = (1.0 - alpha) / (1.0 + alpha);
+        if (!(a2 > 0.0)) return false;
+        const double frames = 16.6 / (-0.5 * std::log(a2));
+        return frames > 400.0;
+      };
       for (auto& kv : classes) {
         if (kv.second.size() < kSharedMin) {
           general.insert(general.end(), kv.second.begin(), kv.second.end());
@@ -1868,12 +1881,15 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         }
         const int cls = (int)reps.size();
         reps.push_back(all[kv.second[0]]);
+        const bool slow = forgets_slowly(all[kv.second[0]]) && !getenv("GAC_BIQUAD_SPECULATE");
         for (size_t m0 = 0; m0 < kv.second.size(); m0 += 16) {
           const size_t cnt = std::min<size_t>(16, kv.second.size() - m0);
-          groups.push_back(BqGroup{(int)sj.size(), (int)cnt, cls});
+          (slow ? slow_groups : groups).push_back(BqGroup{(int)sj.size(), (int)cnt, cls});
           for (size_t m = 0; m < cnt; m++) sj.push_back(all[kv.second[m0 + m]]);
         }
       }
+      const int n_spec_groups = (int)groups.size();
+      groups.insert(groups.end(), slow_groups.begin(), slow_groups.end());
       if (!sj.empty()) {
         const int n_cls = (int)reps.size(), n_groups = (int)groups.size();
         const size_t cs_stride = (size_t)(env.Npad / kBqChunkFrames) * kBqChunkBytes;
@@ -1891,20 +1907,25 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if ((rc = env.scratch->upload(&dreps, reps))) return rc;
         if ((rc = env.scratch->upload(&dsj, sj))) return rc;
         if ((rc = env.scratch->upload(&dgroups, groups))) return rc;
-        size_t n_f2 = 0, n_i = 0;
-        biquad_shared_scratch_sizes(n_groups, env.Npad, &n_f2, &n_i);
-        float2* dstates = nullptr;
+        const int n_slow_groups = n_groups - n_spec_groups;
+        size_t n_f2 = 0, n_i = 0, n_f2s = 0, n_is = 0;
+        biquad_shared_scratch_sizes(std::max(1, n_spec_groups), env.Npad, &n_f2, &n_i);
+        biquad_shared_scratch_sizes(std::max(1, n_slow_groups), env.Npad, &n_f2s, &n_is);  // (an upper bound for the one-segment launch)
+        float2 *dstates = nullptr, *dstates_slow = nullptr;
         int* dflags = nullptr;
         if ((rc = env.scratch->alloc(&dstates, n_f2))) return rc;
+        if ((rc = env.scratch->alloc(&dstates_slow, n_f2s))) return rc;
         if ((rc = env.scratch->alloc(&dflags, n_i))) return rc;
         int t = env.timer->begin(C_BIQUAD);
         launch_biquad_classes(dreps, n_cls, env.Npad, env.NQ, ctx->fs, dlast, dent, dwide, dcs, cs_stride, ctx->stream);
         bool partial = false;
         for (const BiquadJob& j : sj) partial = partial || j.lo > 0 || j.hi < env.Npad;
         if (partial) launch_biquad_zero_outside(dsj, (int)sj.size(), env.Npad, ctx->stream);
-        launch_biquad_lanes_shared(dsj, dgroups, n_groups, dcs, cs_stride, env.Npad, dstates, dflags, ctx->stream);
+        launch_biquad_lanes_shared(dsj, dgroups, n_spec_groups, dcs, cs_stride, env.Npad, dstates, dflags, false, ctx->stream);
+        launch_biquad_lanes_shared(dsj, dgroups + n_spec_groups, n_slow_groups, dcs, cs_stride, env.Npad, dstates_slow, nullptr, true, ctx->stream);
         env.timer->end(t);
-        env.launches += 4 + (partial ? 1 : 0) + (biquad_shared_segments(n_groups, env.Npad, nullptr) > 1 ? 2 : 0);
+        env.launches += 3 + (partial ? 1 : 0) + (n_slow_groups > 0 ? 1 : 0) +
+                        (n_spec_groups > 0 ? 1 + (biquad_shared_segments(n_spec_groups, env.Npad, nullptr) > 1 ? 2 : 0) : 0);
         CU(cudaGetLastError());
         TRACE_MARK("biquad (shared coefficients): queued");
       }

@@ -272,8 +272,9 @@ struct BqGroup {
 };
 int biquad_shared_segments(int n_groups, int64_t n_frames, int* seg_chunks);
 void biquad_shared_scratch_sizes(int n_groups, int64_t n_frames, size_t* n_float2, size_t* n_int);
+// sequential: one segment per group (filters known to forget too slowly for the speculative segments); scratch sized the same way
 void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups, int n_groups, const unsigned char* d_cs, size_t cs_stride,
-                                int64_t n_frames, float2* d_states, int* d_flags, cudaStream_t s);
+                                int64_t n_frames, float2* d_states, int* d_flags, bool sequential, cudaStream_t s);
 
 // K3d alone (biquad_lanes.cu): the recursion over the slab-transposed streams, TMA-fed
 void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,

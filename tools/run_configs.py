@@ -1,5 +1,5 @@
 """Device-time measurements of the BASELINE configs other than the bench workload (per-GPU shards of C3, C4, C5 and C1),
-inputs resident in HBM.  Writes profiles/r01_configs.json.   python tools/run_configs.py [c1 c3 c4 c5]"""
+inputs resident in HBM.  Writes profiles/r02_configs.json.   python tools/run_configs.py [c1 c3 c4 c5]"""
 import ctypes as C, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -158,7 +158,7 @@ if "f3" in which:
         L.gac_graph_destroy(g)
         ctx.Dispose()
 
-p = os.path.join(ROOT, "gpurun_out", "r01_configs.json")
+p = os.path.join(ROOT, "gpurun_out", "r02_configs.json")
 if os.path.exists(p) and len(which) < 5:
     old = json.load(open(p)); old.update(res); res = old
 json.dump(res, open(p, "w"), indent=1)

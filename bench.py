@@ -60,6 +60,9 @@ WORKLOADS = {
                desc="C3 (BASELINE configs[2], the north-star config: 1024 voices on 8 GPUs = 128 voices per GPU): per voice stereo 10 s noise -> "
                     "BiQuadFilterNode lowpass, a-rate cutoff 2 -> 12 kHz -> GainNode a-rate automation -> ConvolverNode 2 s stereo IR per voice; bus "
                     "GainNode(1/32), 12 s @ 48 kHz; voices sharded over the GPUs, one ncclReduce of the bus"),
+    "c5": dict(voices_per_gpu=32, src_s=10.0, ir_s=10.0, render_s=20.0, bus_gain=1.0 / 16, kind="c5", scaling="weak", fs=96000, src_rate=44100,
+               desc="C5 (BASELINE configs[4]: 256 voices on 8 GPUs = 32 voices per GPU): per voice stereo 10 s noise at 44.1 kHz -> CubicResampler to 96 kHz "
+                    "-> GainNode a-rate automation -> convolver with a 10 s stereo IR, 512-frame partitions; bus GainNode(1/16), 20 s @ 96 kHz"),
     "c2": dict(voices_per_gpu=64, src_s=10.0, ir_s=2.0, render_s=12.0, bus_gain=1.0 / 8, kind="c2", scaling="weak",
                desc="C2 (BASELINE configs[1]): 64 voices per GPU x (stereo 10 s noise -> GainNode a-rate automation -> ConvolverNode 2 s stereo IR per voice) "
                     "-> bus GainNode(1/8), 12 s @ 48 kHz"),
@@ -81,7 +84,7 @@ def config_of(wl, world, args):
     """The `config` object of the JSON line — the same keys and values from both arms (ours / reference)."""
     V = total_voices(wl, world)
     return {"workload": wl["desc"], "voices": V, "voices_per_gpu": V // world if V % world == 0 else V / world, "partition": args.partition,
-            "sample_rate": FS, "frames": int(wl["render_s"] * FS),
+            "sample_rate": wl.get("fs", FS), "frames": int(wl["render_s"] * wl.get("fs", FS)),
             "parallelism": f"voices sharded x{world}, one ncclReduce of the bus" if world > 1 else "single GPU",
             "l2": "working set per step (sources, signals and spectrograms: GBs) exceeds the 126 MB L2; no flush needed",
             "timing": "CUDA events on the library's launch stream (gac_get_stats.ms_total), max over ranks"}
@@ -195,7 +198,7 @@ def bind_to_gpu_cpus(local):
 def make_inputs(wl, lo, hi, pinned, cheap=False):
     """Per-voice host arrays for global voices [lo, hi) (pinned when torch/cuda is available): (src[2], ir[2], gains).
     cheap: voice v re-uses the samples of voice lo + (v - lo) % 8 (content does not matter: the ncu traffic child)."""
-    nsrc, nir = int(wl["src_s"] * FS), int(wl["ir_s"] * FS)
+    nsrc, nir = int(wl["src_s"] * wl.get("src_rate", wl.get("fs", FS))), int(wl["ir_s"] * wl.get("fs", FS))
     alloc = None
     if pinned:
         import torch
@@ -226,6 +229,8 @@ def build_graph(api, wl, voices, bus_gain=None, **kw):
         return synth.build_c1(api, FS, voices[0][0], voices[0][1], **kw)
     if wl["kind"] == "c3":
         return synth.build_c3(api, FS, voices, bus_gain, **kw)
+    if wl["kind"] == "c5":
+        return synth.build_c5(api, wl["fs"], wl["src_rate"], voices, bus_gain, **kw)
     return synth.build_c2(api, FS, voices, bus_gain, **kw)
 
 
@@ -246,7 +251,7 @@ def cpu_render_sample(wl, n_voices, render_s):
     from oracle import ga_oracle as O
     voices = make_inputs(wl, 0, n_voices, pinned=False)
     ctx = build_graph(O, wl, voices)
-    n = int(render_s * FS)
+    n = int(render_s * wl.get("fs", FS))
     t0 = time.perf_counter()
     out = ctx.Render(n)
     dt = time.perf_counter() - t0
@@ -332,7 +337,7 @@ def ncu_traffic_live(args, wl, n_voices, timeout_s=420):
 def traffic_child(args, wl):
     """Runs under ncu: two resident renders of the workload with cheap inputs (content does not change the traffic)."""
     import graphaudio_b200 as G
-    n = int(wl["render_s"] * FS)
+    n = int(wl["render_s"] * wl.get("fs", FS))
     voices = make_inputs(wl, 0, args.voices, pinned=False, cheap=True)
     ctx = build_graph(G, wl, voices, device_id=0, partition=args.partition, uniform_segments=args.uniform_segments)
     ctx.MarkBus(ctx.bus)
@@ -366,7 +371,7 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = int(wl["render_s"] * FS)
+    n = int(wl["render_s"] * wl.get("fs", FS))
     lo, hi = shard_of(wl, rank, world)
     V = total_voices(wl, world)
     t_gen = time.perf_counter()
@@ -375,6 +380,8 @@ def run_ours(args, wl):
     h2d_bytes = sum(a.nbytes for v in voices for a in (v[0] + v[1]))
     d2h_bytes = 2 * n * 4
     L = N.lib()
+    if wl["kind"] == "c5" and args.partition == 128:
+        args.partition = 512
     ctx_kw = dict(device_id=local, tile_blocks=args.tile_blocks, partition=args.partition, mac_variant=args.mac_variant)
 
     def comm(ctx):
@@ -473,7 +480,7 @@ def run_ours(args, wl):
         lat = []
         for i in range(warm_steps + steps):
             def fresh():
-                return G.OfflineAudioContext(FS, async_upload=async_upload, **ctx_kw)
+                return G.OfflineAudioContext(wl.get("fs", FS), async_upload=async_upload, **ctx_kw)
             if world > 1:
                 c = fresh()
                 comm(c)

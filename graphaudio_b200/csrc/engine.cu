@@ -129,6 +129,7 @@ struct gac_context {
   // preparation and the first voice batches of the next render
   bool async_upload = false;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t d2h_stream = nullptr;  // results of batch renders leave here while the next sub-batch computes (gac_render_batch)
   // ... and IR preparation is DEFERRED: gac_ir_prepare only sizes and allocates, the render that first uses an impulse
   // response prepares it together with all the others its voice batch needs (three launches per batch instead of three per
   // IR; a render never queues behind the preparation of an impulse response whose upload is still in flight)
@@ -600,6 +601,10 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
+  }
+  if (ctx->d2h_stream) {
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
   }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   for (char* p : ctx->stage_blocks) give_stage_block(p);

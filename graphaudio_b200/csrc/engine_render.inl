@@ -429,6 +429,8 @@ struct RenderArgs {
   bool sync = true;
   float* h_inter = nullptr;  // interleaved host output [start_index + n_frames][inter_channels], or null (one graph)
   int inter_channels = 0;
+  bool overlap_d2h = false;  // batch renders: the results leave through ctx->d2h_stream behind a staging copy, so that the copy of
+                             // one sub-batch runs while the next one computes (the caller synchronises ctx->d2h_stream at the end)
 };
 
 static int mix_into(RenderEnv& env, std::vector<MixJob>& jobs, std::vector<MixInput>& inputs) {
@@ -876,6 +878,8 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
         const float* src = (c == 0 ? dest0[g] : dest1[g]) + a.first_frame;
         if (a.h_inter) {
           // (handled below: one interleaving pass over both rows)
+        } else if (a.h_out && a.overlap_d2h) {
+          // (handled below: staged, then copied out on the second stream)
         } else if (a.h_out) {
           CU(cudaMemcpyAsync(a.h_out[(size_t)g * a.n_out + c] + a.start_index, src, sizeof(float) * (size_t)a.n_frames, cudaMemcpyDeviceToHost, ctx->stream));
         } else if (a.d_out) {
@@ -883,6 +887,26 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
                              ctx->stream));
         }
       }
+    }
+    if (a.h_out && a.overlap_d2h && !a.h_inter) {
+      // the destination rows live in the render's scratch arena, which the next sub-batch reuses: they are copied (device to device,
+      // ~0.3 ms per GB) into a block of their own that the copy stream frees when it is done with it
+      float* stage = nullptr;
+      const size_t rows = (size_t)a.n_graphs * a.n_out;
+      CU(cudaMallocAsync(&stage, sizeof(float) * rows * (size_t)a.n_frames, ctx->stream));
+      for (int g = 0; g < a.n_graphs; g++)
+        for (int c = 0; c < a.n_out; c++)
+          CU(cudaMemcpyAsync(stage + ((size_t)g * a.n_out + c) * (size_t)a.n_frames, (c == 0 ? dest0[g] : dest1[g]) + a.first_frame,
+                             sizeof(float) * (size_t)a.n_frames, cudaMemcpyDeviceToDevice, ctx->stream));
+      cudaEvent_t staged = take_event(ctx);
+      CU(cudaEventRecord(staged, ctx->stream));
+      CU(cudaStreamWaitEvent(ctx->d2h_stream, staged, 0));
+      ctx->event_pool.push_back(staged);
+      for (int g = 0; g < a.n_graphs; g++)
+        for (int c = 0; c < a.n_out; c++)
+          CU(cudaMemcpyAsync(a.h_out[(size_t)g * a.n_out + c] + a.start_index, stage + ((size_t)g * a.n_out + c) * (size_t)a.n_frames,
+                             sizeof(float) * (size_t)a.n_frames, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      CU(cudaFreeAsync(stage, ctx->d2h_stream));
     }
     if (a.h_inter) {  // ≙ the interleaving loop of ProcessBlockInterleaved (AudioContextBase.cs:127-160), for the whole render
       float* d_inter = nullptr;
@@ -984,7 +1008,56 @@ extern "C" int gac_render_batch(gac_context* ctx, const gac_graph* const* graphs
   a.n_frames = n_frames;
   a.h_out = out_channels;
   a.n_out = n_out_channels;
-  return render_core(ctx, a);
+  // Opt-in (GAC_BATCH_SPLIT=k): a large batch is cut into k sub-batches whose results leave on a second stream while the next
+  // sub-batch computes.  Measured on a 512-render shard of BASELINE config 4 (983 MB of results, 21 ms over PCIe, 9.1 ms of
+  // compute): 1 batch 31.0 ms, k = 2: 30.9 ms, 3: 31.7 ms, 4: 34.9 ms, 8: 53.8 ms — a render has latency-bound stages (the
+  // sequential biquad pass of a slow filter costs ~5 ms whatever the batch size), so every cut adds about as much compute as it
+  // hides copy time.  Hence off by default; the copy is what bounds this configuration end to end.
+  static const int forced = getenv("GAC_BATCH_SPLIT") ? atoi(getenv("GAC_BATCH_SPLIT")) : 0;
+  const double out_bytes = (double)n_graphs * n_out_channels * (double)n_frames * 4.0;
+  if (forced < 2 || !ctx_ok(ctx) || n_graphs < 32 || out_bytes < 64e6 || n_frames <= 0 || n_out_channels < 1 || n_out_channels > 2) return render_core(ctx, a);
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->d2h_stream) CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  const int n_sub = std::max(1, std::min(forced, n_graphs / 16));
+  gac_stats total{};
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, ctx->stream));
+  int rc = GAC_OK;
+  for (int k = 0; k < n_sub && rc == GAC_OK; k++) {
+    const int g0 = (int)((int64_t)n_graphs * k / n_sub), g1 = (int)((int64_t)n_graphs * (k + 1) / n_sub);
+    RenderArgs sub = a;
+    sub.graphs = graphs + g0;
+    sub.n_graphs = g1 - g0;
+    sub.h_out = out_channels + (size_t)g0 * n_out_channels;
+    sub.overlap_d2h = true;
+    rc = render_core(ctx, sub);
+    if (rc) break;
+    const gac_stats& st = ctx->stats;
+    total.ms_source += st.ms_source; total.ms_automation += st.ms_automation; total.ms_biquad += st.ms_biquad; total.ms_gain += st.ms_gain;
+    total.ms_fft_fwd += st.ms_fft_fwd; total.ms_mac += st.ms_mac; total.ms_fft_inv += st.ms_fft_inv; total.ms_mix += st.ms_mix;
+    total.ms_delay += st.ms_delay; total.ms_panner += st.ms_panner;
+    total.conv_units += st.conv_units; total.algorithmic_bytes += st.algorithmic_bytes; total.mac_complex_macs += st.mac_complex_macs;
+    total.kernel_launches += st.kernel_launches; total.voices += st.voices; total.mac_flops += st.mac_flops;
+    total.mac_bytes_moved += st.mac_bytes_moved; total.mac_h2_bytes_single += st.mac_h2_bytes_single;
+    total.mac_variant_used = st.mac_variant_used; total.mac_big_segments = st.mac_big_segments; total.frames = st.frames;
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->d2h_stream);
+  cudaEventRecord(e1, ctx->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "batch render failed: %s", cudaGetErrorString(e));
+  total.ms_total = ms;  // first kernel to last byte on the host
+  const double compute = total.ms_source + total.ms_automation + total.ms_biquad + total.ms_gain + total.ms_fft_fwd + total.ms_mac + total.ms_fft_inv +
+                         total.ms_mix + total.ms_delay + total.ms_panner;
+  total.ms_d2h = std::max(0.0, (double)ms - compute);  // what the copies add behind the kernels they could not hide under
+  ctx->stats = total;
+  return GAC_OK;
 }
 extern "C" int gac_render_sharded(gac_context* ctx, const gac_graph* shard, int64_t n_frames, int root, float* const* out_channels,
                                   int n_out_channels) {

@@ -10,6 +10,12 @@ from graphaudio_b200.api import check
 from tests import synth
 
 which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
+# under torchrun every rank measures its own shard on its own GPU (C4 / C5 shard by render / voice with no exchange step)
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+RANK = int(os.environ.get("RANK", "0"))
+torch.cuda.set_device(LOCAL)
+_OAC = G.OfflineAudioContext
+G.OfflineAudioContext = lambda fs=48000, **kw: _OAC(fs, **{"device_id": LOCAL, **kw})
 res = {}
 L = N.lib()
 
@@ -72,7 +78,7 @@ if "c4" in which or "c4small" in which:
     parent = G.OfflineAudioContext(fs)
     forks = []
     for r in range(NR):
-        src, ir = synth.make_voice_inputs(r, 5 * fs, fs // 2)
+        src, ir = synth.make_voice_inputs(RANK * NR + r, 5 * fs, fs // 2)
         f = parent.Fork()
         s = G.AudioBufferSourceNode(f)
         s.Buffer = G.PlayableAudioBuffer.FromChannelArrays(src, fs)
@@ -158,7 +164,7 @@ if "f3" in which:
         L.gac_graph_destroy(g)
         ctx.Dispose()
 
-p = os.path.join(ROOT, "gpurun_out", "r02_configs.json")
+p = os.path.join(ROOT, "gpurun_out", "r02_configs.json" if "WORLD_SIZE" not in os.environ else f"r02_configs_rank{RANK}of{os.environ['WORLD_SIZE']}.json")
 if os.path.exists(p) and len(which) < 5:
     old = json.load(open(p)); old.update(res); res = old
 json.dump(res, open(p, "w"), indent=1)

@@ -122,10 +122,111 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
     const int64_t n = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kParamFrames;
     if (n >= n_quanta * 128 || (n >> 7) < job.q_lo || (n >> 7) >= job.q_hi) return;
     const double t0 = block_time[n >> 7];  // the frames share a quantum (16 divides 128)
+    const int f0 = (int)(n & 127);
+    // Fast path: no event time falls between this thread's first and last frame (all but a handful of threads per event).  The
+    // interval is resolved once, its constants are hoisted, and a frame costs a few FP64 operations; same arithmetic per frame as
+    // eval_interval, the quotient (t - t0) / (t1 - t0) of a linear ramp through one IEEE reciprocal per thread and a Markstein
+    // correction step (q = a r; q += fma(-q, b, a) r: the correctly rounded quotient).
+    {
+      const double t_first = t0 + (double)f0 * dt, t_last = t0 + (double)(f0 + kParamFrames - 1) * dt;
+      advance_interval(job.events, job.n_events, t_first, i, boundary);
+      if (i >= job.n_events || t_last < job.events[i].time) {
+        const int count = job.n_events;
+        int mode = 0;  // 0 constant, 1 linear, 2 exponential ramp, 3 SetTarget
+        float cval = job.value, v0 = 0.f, dv = 0.f, tgt = 0.f;
+        double te = 0.0, span = 1.0, rspan = 1.0, lr = 0.0, tc = 1.0;
+        if (count > 0) {
+          const DevEvent* st = nullptr;
+          if (i < count) {
+            if (i == 0) {
+              cval = boundary;
+            } else {
+              const DevEvent e = job.events[i], prev = job.events[i - 1];
+              if (e.type == 1 || (e.type == 2 && (prev.value <= 0.f || e.value <= 0.f))) {
+                mode = 1;
+                v0 = prev.value;
+                dv = e.value - prev.value;
+                te = prev.time;
+                span = e.time - prev.time;
+                rspan = 1.0 / span;
+              } else if (e.type == 2) {
+                mode = 2;
+                v0 = prev.value;
+                te = prev.time;
+                span = e.time - prev.time;
+                lr = log((double)(e.value / prev.value));  // ratio formed in float32 (:235)
+              } else if (prev.type != 3) {
+                cval = prev.value;
+              } else {
+                st = &job.events[i - 1];
+              }
+            }
+          } else if (job.events[count - 1].type != 3) {
+            cval = job.events[count - 1].value;
+          } else {
+            st = &job.events[count - 1];
+          }
+          if (st) {
+            mode = 3;
+            te = st->time;
+            tgt = st->target;
+            dv = boundary - st->target;
+            tc = st->time_constant > 0.001 ? st->time_constant : 0.001;
+          }
+        }
+        // mode-specialised loops (small code: the transcendental calls sit outside of them)
+        float v[kParamFrames];
+        if (mode == 0) {
 #pragma unroll
+          for (int k = 0; k < kParamFrames; k++) v[k] = cval;
+        } else if (mode == 1) {
+          const double dv0 = (double)v0, ddv = (double)dv;
+#pragma unroll
+          for (int k = 0; k < kParamFrames; k++) {
+            const double a = (t0 + (double)(f0 + k) * dt) - te;  // :120
+            double u = a * rspan;
+            u = fma(fma(-u, span, a), rspan, u);  // (in [0, 1): prev.time <= t < e.time, the clamp of :222 is a no-op)
+            v[k] = (float)(dv0 + ddv * u);
+          }
+        } else if (mode == 2) {
+          double u = (t_first - te) / span;
+          u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+          double val = exp(u * lr);
+          const double mul = exp(lr * (dt / span)), dv0 = (double)v0;
+#pragma unroll
+          for (int k = 0; k < kParamFrames; k++) {
+            v[k] = (float)(dv0 * val);
+            val *= mul;
+          }
+        } else {
+          // elapsed = t - te >= 0 here; it is 0 only on a first frame that coincides with the event, which keeps the baseline
+          int k0 = 0;
+          if (t_first - te <= 0.0) {
+            v[0] = boundary;
+            k0 = 1;
+          }
+          double val = exp(-((t0 + (double)(f0 + k0) * dt) - te) / tc);
+          const double mul = exp(-dt / tc), dt0 = (double)tgt, ddv = (double)dv;
+#pragma unroll
+          for (int k = 0; k < kParamFrames; k++) {
+            if (k >= k0) {
+              v[k] = (float)(dt0 + ddv * val);
+              val *= mul;
+            }
+          }
+        }
+#pragma unroll
+        for (int e4 = 0; e4 < kParamFrames / 4; e4++)
+          *reinterpret_cast<float4*>(job.out + n + 4 * e4) = make_float4(v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
+        return;
+      }
+      i = 0;  // an event inside the thread's frames: the general walk below, from the start
+      boundary = job.value;
+    }
+#pragma unroll 1
     for (int e4 = 0; e4 < kParamFrames / 4; e4++) {
       float v[4];
-#pragma unroll
+#pragma unroll 1
       for (int e = 0; e < 4; e++) {
         const double t = t0 + (double)((int)(n & 127) + 4 * e4 + e) * dt;  // :120
         const int before = i;

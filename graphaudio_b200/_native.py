@@ -37,6 +37,7 @@ class gac_context_desc(C.Structure):
 
 GAC_FLAG_ASYNC_UPLOAD = 1
 GAC_FLAG_UNIFORM_SEGMENTS = 2
+GAC_FLAG_NO_FANIN_FUSION = 4
 
 
 class gac_event(C.Structure):
@@ -83,7 +84,7 @@ class gac_stats(C.Structure):
                 ("algorithmic_bytes", C.c_double), ("mac_complex_macs", C.c_double), ("kernel_launches", C.c_int64),
                 ("voices", C.c_int64), ("frames", C.c_int64), ("mac_flops", C.c_double), ("mac_bytes_moved", C.c_double),
                 ("mac_variant_used", C.c_int32), ("mac_big_segments", C.c_int32), ("ms_delay", C.c_double), ("ms_panner", C.c_double),
-                ("mac_h2_bytes_single", C.c_double)]
+                ("mac_h2_bytes_single", C.c_double), ("fanin_groups", C.c_int32), ("fanin_members", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

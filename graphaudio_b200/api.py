@@ -707,7 +707,7 @@ class OfflineAudioContext:
     """OfflineAudioContext.cs — `Render` is the one call that crosses into libgraphaudio_cuda.so."""
 
     def __init__(self, sampleRate=48000, partition=128, device_id=-1, mac_variant=0, tile_blocks=32, async_upload=False,
-                 uniform_segments=False, device_ids=None, _record_only=False):
+                 uniform_segments=False, fanin_fusion=True, device_ids=None, _record_only=False):
         """partition / device_id / mac_variant / tile_blocks map onto gac_context_desc.  `_record_only=True` builds a context
         without a device handle: nodes, automation and topology can be recorded and inspected (`_topology()`), Render raises.
         It exists for the CPU unit tests of the host-side logic; it is not a fallback."""
@@ -730,7 +730,9 @@ class OfflineAudioContext:
             desc.tile_blocks = tile_blocks
             # async_upload: page-locked source arrays are uploaded asynchronously (GAC_FLAG_ASYNC_UPLOAD); the arrays handed
             # to PlayableAudioBuffer must then stay untouched until Render returns
-            desc.flags = (N.GAC_FLAG_ASYNC_UPLOAD if async_upload else 0) | (N.GAC_FLAG_UNIFORM_SEGMENTS if uniform_segments else 0)
+            # fanin_fusion=False keeps one inverse transform and one fan-in input per ConvolverNode (GAC_FLAG_NO_FANIN_FUSION)
+            desc.flags = ((N.GAC_FLAG_ASYNC_UPLOAD if async_upload else 0) | (N.GAC_FLAG_UNIFORM_SEGMENTS if uniform_segments else 0) |
+                          (0 if fanin_fusion else N.GAC_FLAG_NO_FANIN_FUSION))
             out = C.c_void_p()
             if device_ids is not None:
                 # ONE OfflineAudioContext over several GPUs of this process: voices -> bus -> destination graphs

@@ -113,6 +113,8 @@ struct gac_context {
   int mac_variant = 0;
   int tile_blocks = 32;
   bool mixed_segments = true;  // K6: double-length overlap-save segments in front when that saves work (GAC_FLAG_UNIFORM_SEGMENTS clears it)
+  bool fuse_fanin = true;      // convolvers that end their chains and meet in one fan-in are summed as spectra (GAC_FLAG_NO_FANIN_FUSION clears it)
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   float2* d_tw = nullptr;  // e^{-2 pi i k/(2B)}, k < B
   float2* d_tw2 = nullptr; // e^{-2 pi i e/8192}, e < 8192: twiddles of the second-level (block-time) FFT, fft2.cu
@@ -508,7 +510,7 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   // per-device facts are queried once per process (cudaGetDeviceProperties / cudaMemGetInfo cost milliseconds)
   struct DevInfo {
     bool known = false;
-    int major = 0, minor = 0;
+    int major = 0, minor = 0, sms = 148;
     size_t budget = (size_t)24 << 30;
   };
   static DevInfo dev_info[64];
@@ -519,6 +521,7 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   if (!di.known) {
     CU(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, dev));
     CU(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, dev));
+    CU(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
     // keep freed scratch in the pool between renders
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -539,8 +542,10 @@ extern "C" int gac_context_create(const gac_context_desc* desc, gac_context** ou
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->async_upload = (desc->flags & GAC_FLAG_ASYNC_UPLOAD) != 0;
   ctx->mixed_segments = (desc->flags & GAC_FLAG_UNIFORM_SEGMENTS) == 0;
+  ctx->fuse_fanin = (desc->flags & GAC_FLAG_NO_FANIN_FUSION) == 0 && !getenv("GAC_NO_FANIN_FUSION");
   if (ctx->async_upload) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   ctx->scratch_budget = di.budget;
+  ctx->sm_count = di.sms > 0 ? di.sms : 148;
   ctx->arena_keep_limit = di.budget + di.budget / 2;  // half of the memory that was free when the device was first used
   {
     std::lock_guard<std::mutex> lk(g_tables_mu);
@@ -1029,6 +1034,9 @@ struct Sig {
   bool from_source = false;  // the chain is fed by an AudioBufferSourceNode (whose idle blocks have ONE channel, AudioBufferSourceNode.cs:391-402)
   const std::vector<OpH>* ops = nullptr;
   size_t bus_base = 0;       // index of the graph's first bus in RenderEnv::buses (modulation inputs name graph-local buses)
+  // >= 0: the signal's only consumer is a plain two-channel fan-in (this is its id): a ConvolverNode that ends the chain may be
+  // summed with the others that carry the same id (run_chains; the sum lands in the first one's rows, the rest turn silent)
+  int64_t sum_key = -1;
 };
 
 struct RenderEnv {
@@ -1044,6 +1052,7 @@ struct RenderEnv {
   double mac_flops = 0, mac_bytes = 0;  // flops issued / bytes the K6 variant in use has to move (X, H, Y once)
   int mac_big = 0;                      // double-length segments per channel-convolver of the last second-level-FFT batch
   int mac_used = 0;                     // K6 variant of the last convolver batch (1 stream, 2/4 tiled, 3 second-level FFT)
+  int sum_groups = 0, sum_members = 0;  // fan-in groups summed as spectra / convolvers in them
   std::map<Sig*, std::pair<const float*, float>> fused;  // GainNode folded into the next convolver's forward FFT
   std::map<std::string, float*> param_tables;  // automation tables already evaluated in this render, by (rate, value, events)
   // automation tables are carved out of chunks (one stream-ordered allocation per 16 tables) and the events of a batch of
@@ -1202,6 +1211,7 @@ struct ConvItem {
     float* out;
     float* out2;      // duplicate destination or nullptr
   } inv[2];
+  int64_t sum_key = -1;  // fan-in fusion: items with the same key (and segment plan) are summed as spectra (conv_batch_fft2_sum)
 };
 
 static int conv_batch_direct(RenderEnv& env, std::vector<ConvItem>& items) {
@@ -1531,16 +1541,171 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
   return GAC_OK;
 }
 
+// Fan-in fusion: how many voices one CTA of k_fft2_sum16 walks.  A chunk costs (members + ~0.8) transforms (one forward transform
+// and a multiply-accumulate per member, one inverse per chunk); the launches (double-length segments, then single-length ones) run
+// in whole waves of resident CTAs, so the chunk count is picked to fill the last wave.
+static int pick_sum_chunks(int n, int n_big, int n_small, int M, int C, int sms) {
+  int log2m = 0;
+  while ((1 << log2m) < M) log2m++;
+  const char* force = getenv("GAC_SUM_CHUNK");
+  if (force && atoi(force) > 0) return (n + atoi(force) - 1) / atoi(force);
+  int best_chunks = 1;
+  double best = 1e300;
+  for (int nch = 1; nch <= n; nch++) {
+    const int chunk = (n + nch - 1) / nch;
+    if (chunk < 4 && nch > 1) break;
+    double cost = 0.0;
+    if (n_big > 0) {
+      const double ctas = (double)n_big * C * 2 * nch, slots = (double)sms * fft2_sum_ctas_per_sm(2 * M);
+      cost += std::ceil(ctas / slots) * (chunk + 0.8) * 2.0 * M * (log2m + 1) / 0.9;
+    }
+    if (n_small > 0) {
+      const double ctas = (double)n_small * C * 2 * nch, slots = (double)sms * fft2_sum_ctas_per_sm(M);
+      cost += std::ceil(ctas / slots) * (chunk + 0.8) * (double)M * log2m;
+    }
+    if (cost < best) {
+      best = cost;
+      best_chunks = nch;
+    }
+  }
+  return best_chunks;
+}
+
+// One fan-in group (ConvItem::sum_key; stereo impulse responses, one segment plan): K5 per voice, k_fft2_sum16 per chunk of voices
+// and output channel, ONE K7 pair for the group.  The sum lands in the rows of the first item.
+static int conv_batch_fft2_sum(RenderEnv& env, std::vector<ConvItem>& items, int M) {
+  gac_context* ctx = env.ctx;
+  const int B = ctx->B, C = B + 1;
+  const int64_t QB = env.QB;
+  const int64_t Qs = ((QB + 15) / 16) * 16;
+  const size_t plane = (size_t)C * Qs;
+  int log2m = 0;
+  while ((1 << log2m) < M) log2m++;
+  const int n = (int)items.size();
+  const ConvItem& first = items[0];
+  const int V = M - first.Lh;
+  const int n_big = first.n_big;
+  const int nseg = n_big > 0 ? first.n_small : (int)((QB + V - 1) / V);
+  const int64_t b0 = (int64_t)n_big * (2 * (int64_t)M - first.Lh);
+  const int n_chunks = pick_sum_chunks(n, n_big, nseg, M, C, ctx->sm_count);
+  float2 *dX = nullptr, *dYp = nullptr;
+  int rc;
+  if ((rc = env.scratch->alloc(&dX, (size_t)n * 2 * plane))) return rc;
+  if ((rc = env.scratch->alloc(&dYp, (size_t)n_chunks * 2 * plane))) return rc;  // [channel][chunk][C][Qs]
+  auto& fj = env.keep->make<FftFwdJob>();
+  auto& mem = env.keep->make<Fft2SumMember>();    // [channel][voice], single-length spectra
+  auto& memb = env.keep->make<Fft2SumMember>();   // the same with the double-length spectra
+  for (int c = 0; c < 2; c++)
+    for (int i = 0; i < n; i++) {
+      const ConvItem& it = items[i];
+      float2* X = dX + ((size_t)i * 2 + c) * plane;
+      {  // (stereo layout: channel-convolver c reads forward spectrum c)
+        FftFwdJob f;
+        f.in = it.fwd[c].in;
+        f.out = X;
+        f.scale = nullptr;
+        f.gain = it.gain_tab;
+        f.gain_const = it.gain_const;
+        f.n_valid = env.Npad;
+        f.n_blocks = QB;
+        f.gate_lo = it.lo;
+        f.gate_hi = it.hi;
+        f.in2 = it.fwd[c].in2;
+        f.mix_scale = it.fwd[c].mix_scale;
+        fj.push_back(f);
+      }
+      mem.push_back(Fft2SumMember{X, it.mac[c].H2});
+      if (n_big > 0) memb.push_back(Fft2SumMember{X, it.mac[c].H2b});
+      const double P = it.P;
+      env.conv_units += QB;
+      env.alg_bytes += (double)QB * (16.0 * P * C + 8.0 * C + 8.0 * B);
+      env.macs += (double)QB * P * C;
+      // one forward transform and a multiply-accumulate per member and segment (the inverse is counted per chunk below)
+      env.mac_flops += (double)nseg * C * (5.0 * M * log2m + 8.0 * M) + (double)n_big * C * (5.0 * 2 * M * (log2m + 1) + 8.0 * 2 * M);
+      env.mac_h2_single += 8.0 * C * (double)fft2_h2_row_elems(M);
+      env.mac_bytes += 8.0 * C * ((double)QB + (nseg > 0 ? (double)fft2_h2_row_elems(M) : 0.0) + (n_big > 0 ? (double)fft2_h2_row_elems(2 * M) : 0.0));
+    }
+  Fft2SumMember *dmem = nullptr, *dmemb = nullptr;
+  if ((rc = env.scratch->upload(&dmem, mem))) return rc;
+  if ((rc = env.scratch->upload(&dmemb, memb))) return rc;
+  auto& sj = env.keep->make<Fft2SumJob>();
+  auto& sjb = env.keep->make<Fft2SumJob>();
+  auto& ij = env.keep->make<FftInvJob>();
+  for (int c = 0; c < 2; c++) {
+    int at = 0;
+    for (int k = 0; k < n_chunks; k++) {
+      const int cnt = n / n_chunks + (k < n % n_chunks ? 1 : 0);
+      Fft2SumJob j;
+      j.members = dmem + (size_t)c * n + at;
+      j.n_members = cnt;
+      j.Y = dYp + ((size_t)c * n_chunks + k) * plane;
+      j.Lh = first.Lh;
+      j.nseg = nseg;
+      j.b0 = b0;
+      if (nseg > 0) sj.push_back(j);
+      if (n_big > 0) {
+        j.members = dmemb + (size_t)c * n + at;
+        j.nseg = n_big;
+        j.b0 = 0;
+        sjb.push_back(j);
+      }
+      at += cnt;
+      env.mac_flops += (double)nseg * C * (5.0 * M * log2m) + (double)n_big * C * (5.0 * 2 * M * (log2m + 1));
+      env.mac_bytes += 8.0 * C * (double)QB;  // the chunk's partial spectrogram
+    }
+    FftInvJob v;
+    v.in = dYp + (size_t)c * n_chunks * plane;
+    v.out = first.inv[c].out;
+    v.n_blocks = QB;
+    v.n_parts = n_chunks;
+    v.part_stride = (int64_t)plane;
+    ij.push_back(v);
+  }
+  env.mac_big = std::max(env.mac_big, n_big);
+  env.mac_used = 3;
+  env.sum_groups++;
+  env.sum_members += n;
+  FftFwdJob* dfj = nullptr;
+  Fft2SumJob *dsj = nullptr, *dsjb = nullptr;
+  FftInvJob* dij = nullptr;
+  if ((rc = env.scratch->upload(&dfj, fj))) return rc;
+  if ((rc = env.scratch->upload(&dsj, sj))) return rc;
+  if ((rc = env.scratch->upload(&dsjb, sjb))) return rc;
+  if ((rc = env.scratch->upload(&dij, ij))) return rc;
+  TRACE_MARK("conv fft2 (fan-in group): tables uploaded");
+  int t = env.timer->begin(C_FFT_FWD);
+  launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
+  env.timer->end(t);
+  CU(cudaGetLastError());
+  t = env.timer->begin(C_MAC);
+  launch_fft2_sum(dsjb, (int)sjb.size(), n_big, C, 2 * M, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
+  launch_fft2_sum(dsj, (int)sj.size(), nseg, C, M, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
+  env.timer->end(t);
+  CU(cudaGetLastError());
+  t = env.timer->begin(C_FFT_INV);
+  launch_irfft_ola_t8(dij, (int)ij.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
+  env.timer->end(t);
+  CU(cudaGetLastError());
+  env.launches += 3 + (n_big > 0 && nseg > 0 ? 1 : 0);
+  return GAC_OK;
+}
+
 // splits the items by K6 variant (direct MAC / second-level FFT of each length) and runs each class batched
 static int conv_batch(RenderEnv& env, std::vector<ConvItem>& items) {
   std::map<int, std::vector<ConvItem>> classes;
+  std::map<std::tuple<int64_t, int, int, int>, std::vector<ConvItem>> groups;  // fan-in groups: (key, M2, Lh, double-length segments)
   for (auto& it : items) {
     bool f2 = it.M2 > 0;
     for (int k = 0; k < it.n_mac; k++) f2 = f2 && it.mac[k].H2 != nullptr;
-    classes[f2 ? it.M2 : 0].push_back(it);
+    if (f2 && it.sum_key >= 0) groups[std::make_tuple(it.sum_key, it.M2, it.Lh, it.n_big)].push_back(it);
+    else classes[f2 ? it.M2 : 0].push_back(it);
   }
   for (auto& kv : classes) {
     int rc = kv.first == 0 ? conv_batch_direct(env, kv.second) : conv_batch_fft2(env, kv.second, kv.first);
+    if (rc) return rc;
+  }
+  for (auto& kv : groups) {
+    int rc = conv_batch_fft2_sum(env, kv.second, std::get<1>(kv.first));
     if (rc) return rc;
   }
   return GAC_OK;
@@ -1996,6 +2161,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if (ctx->mixed_segments && (rc = ensure_h2b_batch(env, reused))) return rc;
       }
       std::vector<ConvItem> items;
+      std::vector<size_t> item_sig;  // which signal an item belongs to
       auto& zj = env.keep->make<GainJob>();
       struct Window {  // what a later epoch contributes: frames [w0, w1) of `from` (null: silence) replace the signal's rows
         float* dst[2];
@@ -2101,6 +2267,9 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
             it.inv[0] = {0, -1, out0, nullptr};
             it.inv[1] = {1, -1, out1, nullptr};
             s.ch = 2;
+            // fan-in fusion: this convolver ends its chain and its only consumer is a plain fan-in
+            if (ctx->fuse_fanin && s.sum_key >= 0 && eps.size() == 1 && pos + 1 == s.ops->size() && it.M2 > 0 && it.mac[0].H2 && it.mac[1].H2)
+              it.sum_key = s.sum_key;
           } else {
             // true stereo (ConvolverNode.cs:127-144): L = c0(inL) + c2(inR), R = c1(inL) + c3(inR); X spectra shared
             it.n_fwd = 2;
@@ -2117,6 +2286,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
             s.ch = 2;
           }
           items.push_back(it);
+          item_sig.push_back(convs[k]);
         }
         // ConvolverNode always marks its output non-silent while it has convolvers (ConvolverNode.cs:153), and clears it while it
         // has none (:107-119); over several epochs the flagged range is the hull of the epochs that had a Buffer
@@ -2129,6 +2299,28 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if (rc) return rc;
         launch_gain(dz, (int)zj.size(), env.Npad, ctx->stream);
         env.launches += 1;
+      }
+      {
+        // fan-in groups: at least two members with the same consumer and segment plan; the first member's rows receive the sum,
+        // the others carry nothing from here on (a silent input is never mixed, AudioNodeInput.cs:127)
+        std::map<std::tuple<int64_t, int, int, int>, std::vector<size_t>> groups;
+        for (size_t i = 0; i < items.size(); i++)
+          if (items[i].sum_key >= 0) groups[std::make_tuple(items[i].sum_key, items[i].M2, items[i].Lh, items[i].n_big)].push_back(i);
+        for (auto& kv : groups) {
+          if (kv.second.size() < 2) {
+            items[kv.second[0]].sum_key = -1;
+            continue;
+          }
+          Sig& lead = sigs[item_sig[kv.second[0]]];
+          for (size_t m = 1; m < kv.second.size(); m++) {
+            Sig& s = sigs[item_sig[kv.second[m]]];
+            if (s.hi > s.lo) {
+              lead.lo = lead.hi > lead.lo ? std::min(lead.lo, s.lo) : s.lo;
+              lead.hi = std::max(lead.hi, s.hi);
+            }
+            s.lo = s.hi = 0;
+          }
+        }
       }
       TRACE_MARK("conv: items built");
       int rc = conv_batch(env, items);

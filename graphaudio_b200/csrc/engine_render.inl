@@ -517,6 +517,44 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     sigs[i].p[1] = d_sig + (i * 2 + 1) * (size_t)env.Npad;
     sigs[i].ops = &voices[i]->ops;
   }
+  // ---- fan-in fusion: a voice whose ONLY consumer is a plain two-channel fan-in (a bus head that takes its input as two channels, or
+  // the destination) carries that fan-in's id; run_chains sums the ConvolverNodes that end such chains as spectra
+  if (ctx->fuse_fanin) {
+    std::vector<int> consumers(S, 0);
+    size_t vb = 0, nb_total = 0;
+    for (int g = 0; g < a.n_graphs; g++) {
+      const gac_graph* gr = a.graphs[g];
+      for (auto& b : gr->buses)
+        for (int x : b.inputs)
+          if (x < 0) consumers[vb + (size_t)(~x)]++;
+      for (int x : gr->dest_inputs)
+        if (x < 0) consumers[vb + (size_t)(~x)]++;
+      vb += gr->voices.size();
+      nb_total += gr->buses.size();
+    }
+    vb = 0;
+    size_t bb = 0;
+    for (int g = 0; g < a.n_graphs; g++) {
+      const gac_graph* gr = a.graphs[g];
+      for (size_t b = 0; b < gr->buses.size(); b++) {
+        const BusH& bh = gr->buses[b];
+        bool plain = !bh.mono && bh.slots.empty();
+        if (plain && !bh.ops.empty()) {
+          const OpH& h = bh.ops[0];
+          plain = h.kind == GAC_OP_GAIN || h.kind == GAC_OP_BIQUAD || h.kind == GAC_OP_DELAY ||
+                  (h.kind == GAC_OP_CONVOLVER && h.ftype == 0 && h.ir && h.ir->nch != 1);
+        }
+        if (!plain) continue;
+        for (int x : bh.inputs)
+          if (x < 0 && consumers[vb + (size_t)(~x)] == 1) sigs[vb + (size_t)(~x)].sum_key = (int64_t)(bb + b);
+      }
+      if (gr->dest_inputs.size() > 1)
+        for (int x : gr->dest_inputs)
+          if (x < 0 && consumers[vb + (size_t)(~x)] == 1) sigs[vb + (size_t)(~x)].sum_key = (int64_t)(nb_total + (size_t)g);
+      vb += gr->voices.size();
+      bb += gr->buses.size();
+    }
+  }
   // ---- stage 1: the chains fed by source buffers.
   // With asynchronous uploads some buffers may still be in flight (and their impulse responses not yet prepared).  Uploads
   // are queued in creation order, so the voices whose data has landed form a prefix: that prefix runs at once as one batch,
@@ -945,6 +983,8 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   st.mac_h2_bytes_single = env.mac_h2_single;
   st.mac_variant_used = env.mac_used;
   st.mac_big_segments = env.mac_big;
+  st.fanin_groups = env.sum_groups;
+  st.fanin_members = env.sum_members;
   st.kernel_launches = env.launches;
   st.voices = (int64_t)S;
   st.frames = a.n_frames;
@@ -1042,6 +1082,7 @@ extern "C" int gac_render_batch(gac_context* ctx, const gac_graph* const* graphs
     total.kernel_launches += st.kernel_launches; total.voices += st.voices; total.mac_flops += st.mac_flops;
     total.mac_bytes_moved += st.mac_bytes_moved; total.mac_h2_bytes_single += st.mac_h2_bytes_single;
     total.mac_variant_used = st.mac_variant_used; total.mac_big_segments = st.mac_big_segments; total.frames = st.frames;
+    total.fanin_groups += st.fanin_groups; total.fanin_members += st.fanin_members;
   }
   cudaError_t e = cudaStreamSynchronize(ctx->d2h_stream);
   cudaEventRecord(e1, ctx->stream);

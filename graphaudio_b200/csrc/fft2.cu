@@ -177,11 +177,11 @@ __device__ __forceinline__ void f2_bulk_s2g(void* dst, uint32_t src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
-// Shared memory of one CTA: [ FFT buffer (padded) | X window / Y staging (M float2) | H2 row (padded like the FFT buffer) | 2 mbarriers ]
-// H2 rows are stored in global memory in the PADDED order (r16::pad), r16::smem_elems(M) float2 per row, so that one
-// contiguous bulk copy lands them in a layout whose per-thread 128-byte reads are bank-conflict free.
+// Shared memory of one CTA: [ FFT buffer (padded) | X window / Y staging (M float2) | H2 row (M float2, chunk-swizzled) | 2 mbarriers ]
+// H2 rows are stored in global memory in the swizzled order of r16::load16_swz, M float2 per row, so that one contiguous bulk
+// copy lands them in a layout whose per-thread 128-byte reads are bank-conflict free.
 template <int M>
-constexpr size_t conv16_smem() { return sizeof(float2) * (size_t)(2 * r16::smem_elems(M) + M) + 16; }
+constexpr size_t conv16_smem() { return sizeof(float2) * (size_t)(r16::smem_elems(M) + 2 * M) + 16; }
 
 template <int M>
 __global__ void __launch_bounds__(M / 16, 8192 / M) k_fft2_conv16(const Fft2Job* __restrict__ jobs, const float2* __restrict__ tab, int64_t n_blocks, int64_t xs,
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(M / 16, 8192 / M) k_fft2_conv16(const Fft2Job*
   extern __shared__ __align__(128) float2 sm[];
   constexpr int SE = P::SE;
   float2* stage = sm + SE;                   // X window in, Y segment out (unpadded: lanes touch consecutive elements)
-  float2* hrow = stage + M;                  // this bin's H2 row (padded order)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hrow + SE);
+  float2* hrow = stage + M;                  // this bin's H2 row (swizzled order)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hrow + M);
   const Fft2Job job = jobs[blockIdx.z];
   const int seg = blockIdx.x;
   if (seg >= job.nseg) return;
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(M / 16, 8192 / M) k_fft2_conv16(const Fft2Job*
     const uint32_t xbytes = (uint32_t)(((n_hi - n_lo + 1) & ~1) * (int)sizeof(float2));
     f2_mbar_expect_tx(bar_x, xbytes);
     f2_bulk_g2s(f2_smem_u32(stage + n_lo), xrow + b_first + n_lo, xbytes, bar_x);
-    f2_mbar_expect_tx(bar_h, (uint32_t)(SE * sizeof(float2)));
-    f2_bulk_g2s(f2_smem_u32(hrow), job.H2 + (int64_t)k * SE, (uint32_t)(SE * sizeof(float2)), bar_h);
+    f2_mbar_expect_tx(bar_h, (uint32_t)(M * sizeof(float2)));
+    f2_bulk_g2s(f2_smem_u32(hrow), job.H2 + (int64_t)k * M, (uint32_t)(M * sizeof(float2)), bar_h);
   }
   __syncthreads();  // barrier initialisation visible to every waiter
   f2_mbar_wait(bar_x, 0);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(M / 16, 8192 / M) k_fft2_conv16(const Fft2Job*
     r16::stage_c<P::L, false>(u);
     f2_mbar_wait(bar_h, 0);
     float2 h[16];
-    r16::load16(h, hrow, t);
+    r16::load16_swz(h, hrow, t);
 #pragma unroll
     for (int q = 0; q < 16; q++) u[q] = cmulf(u[q], h[q]);
     r16::stage_c<P::L, true>(u);
@@ -253,6 +253,120 @@ __global__ void __launch_bounds__(M / 16, 8192 / M) k_fft2_conv16(const Fft2Job*
   __syncthreads();
   if (t == 0) {
     const int64_t b0 = b_first + job.Lh;            // first output block of the segment
+    int64_t len = n_blocks - b0;
+    if (len > V) len = V;
+    if (len > 0) {
+      const uint32_t ybytes = (uint32_t)(((len + 1) & ~(int64_t)1) * (int64_t)sizeof(float2));
+      f2_bulk_s2g(job.Y + (int64_t)k * ys + b0, f2_smem_u32(stage + job.Lh), ybytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fan-in fusion (Fft2SumJob): one CTA = (output channel of a voice chunk, bin, segment).  The CTA walks the chunk's members:
+// X window and H2 row of member m + 1 are in flight (bulk copies) while member m is transformed, the products accumulate in
+// REGISTERS (the thread's 16 spectrum positions are the same for every member), and only the sum is transformed back.
+// Shared memory as k_fft2_conv16 (one window, one row): the window buffer is free again as soon as every thread holds its 16
+// points, the row buffer as soon as the products are formed — each is re-filled right then.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(M / 16, 8192 / M) k_fft2_sum16(const Fft2SumJob* __restrict__ jobs, const float2* __restrict__ tab, int64_t n_blocks,
+                                                                 int64_t xs, int64_t ys) {
+  using P = r16::Plan<M>;
+  constexpr int T = P::T;
+  extern __shared__ __align__(128) float2 sm[];
+  constexpr int SE = P::SE;
+  float2* stage = sm + SE;
+  float2* hrow = stage + M;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hrow + M);
+  const Fft2SumJob job = jobs[blockIdx.z];
+  const int seg = blockIdx.x;
+  if (seg >= job.nseg) return;
+  const int k = blockIdx.y;
+  const int t = threadIdx.x;
+  const int V = M - job.Lh;
+  const int64_t b_first = job.b0 + (int64_t)seg * V - job.Lh;
+  const int n_lo = b_first < 0 ? (int)(-b_first) : 0;
+  const int64_t avail = n_blocks - b_first;
+  const int n_hi = avail < M ? (int)avail : M;
+  const uint32_t bar_x = f2_smem_u32(bars), bar_h = bar_x + 8;
+  const uint32_t xbytes = (uint32_t)(((n_hi - n_lo + 1) & ~1) * (int)sizeof(float2));
+  constexpr uint32_t hbytes = (uint32_t)(M * sizeof(float2));
+  const int64_t xoff = (int64_t)k * xs + b_first + n_lo, hoff = (int64_t)k * M;
+  const uint32_t x_dst = f2_smem_u32(stage + n_lo), h_dst = f2_smem_u32(hrow);
+  if (t == 0) {
+    f2_mbar_init(bar_x, 1);
+    f2_mbar_init(bar_h, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const Fft2SumMember m0 = job.members[0];
+    f2_mbar_expect_tx(bar_x, xbytes);
+    f2_bulk_g2s(x_dst, m0.X + xoff, xbytes, bar_x);
+    f2_mbar_expect_tx(bar_h, hbytes);
+    f2_bulk_g2s(h_dst, m0.H2 + hoff, hbytes, bar_h);
+  }
+  __syncthreads();
+  float2 acc[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) acc[q] = make_float2(0.f, 0.f);
+  for (int m = 0; m < job.n_members; m++) {
+    const uint32_t ph = (uint32_t)(m & 1);
+    Fft2SumMember nxt{nullptr, nullptr};
+    if (t == 0 && m + 1 < job.n_members) nxt = job.members[m + 1];
+    f2_mbar_wait(bar_x, ph);
+    {
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int n = t + T * j;
+        const float2 x = stage[n];
+        v[j] = (n >= n_lo && n < n_hi) ? x : make_float2(0.f, 0.f);
+      }
+      r16::fwd_a<M>(v, sm, tab, t);
+    }
+    __syncthreads();  // (everyone holds its window points: the window buffer is free)
+    if (nxt.X) {
+      f2_mbar_expect_tx(bar_x, xbytes);
+      f2_bulk_g2s(x_dst, nxt.X + xoff, xbytes, bar_x);
+    }
+    r16::fwd_b<M>(sm, tab, t);
+    __syncthreads();
+    {
+      float2 u[16];
+      r16::load16(u, sm, t);
+      r16::stage_c<P::L, false>(u);
+      f2_mbar_wait(bar_h, ph);
+      const float4* hp = reinterpret_cast<const float4*>(hrow);
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const float4 h = hp[r16::swz_chunk(t, q)];
+        const float2 a = u[2 * q], b = u[2 * q + 1];
+        acc[2 * q].x += a.x * h.x - a.y * h.y;
+        acc[2 * q].y += a.x * h.y + a.y * h.x;
+        acc[2 * q + 1].x += b.x * h.z - b.y * h.w;
+        acc[2 * q + 1].y += b.x * h.w + b.y * h.z;
+      }
+    }
+    __syncthreads();  // (the row has been consumed, and the FFT buffer may be overwritten by the next member)
+    if (nxt.H2) {
+      f2_mbar_expect_tx(bar_h, hbytes);
+      f2_bulk_g2s(h_dst, nxt.H2 + hoff, hbytes, bar_h);
+    }
+  }
+  r16::stage_c<P::L, true>(acc);
+  r16::store16(acc, sm, t);
+  __syncthreads();
+  r16::inv_b<M>(sm, tab, t);
+  __syncthreads();
+  float2 v[16];
+  r16::inv_a<M>(v, sm, tab, t);
+#pragma unroll
+  for (int j = 0; j < 16; j++) stage[t + T * j] = v[j];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (t == 0) {
+    const int64_t b0 = b_first + job.Lh;
     int64_t len = n_blocks - b0;
     if (len > V) len = V;
     if (len > 0) {
@@ -292,12 +406,7 @@ __global__ void __launch_bounds__(M / 16) k_fft2_prep16(const float2* __restrict
   float2 u[16];
   r16::load16(u, sm, t);
   r16::stage_c<Pl::L, false>(u);
-  const float sc = 1.0f / (float)M;
-  constexpr int SE = Pl::SE;
-  float2* __restrict__ row = H2 + ((int64_t)ch * (B + 1) + k) * SE;
-  float4* __restrict__ out = reinterpret_cast<float4*>(row + r16::pad(16 * t));
-#pragma unroll
-  for (int q = 0; q < 8; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
+  r16::store16_swz(u, 1.0f / (float)M, H2 + ((int64_t)ch * (B + 1) + k) * M, t);
 }
 
 // the same for a batch of channels described by a job array (deferred IR preparation)
@@ -328,11 +437,7 @@ __global__ void __launch_bounds__(M / 16) k_fft2_prep16_batch(const IrChanJob* _
   float2 u[16];
   r16::load16(u, sm, t);
   r16::stage_c<Pl::L, false>(u);
-  const float sc = 1.0f / (float)M;
-  constexpr int SE = Pl::SE;
-  float4* __restrict__ out = reinterpret_cast<float4*>(job.H2 + (int64_t)k * SE + r16::pad(16 * t));
-#pragma unroll
-  for (int q = 0; q < 8; q++) out[q] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
+  r16::store16_swz(u, 1.0f / (float)M, job.H2 + (int64_t)k * M, t);
 }
 template <int M>
 static void prep16_batch_t(const IrChanJob* d_jobs, int n_jobs, int B, const float2* d_tab, cudaStream_t s) {
@@ -360,7 +465,7 @@ int fft2_r16_max() {
   }();
   return v;
 }
-int fft2_h2_row_elems(int M) { return M <= fft2_r16_max() ? r16::smem_elems(M) : M; }
+int fft2_h2_row_elems(int M) { return M; }  // (both plans: M float2 per row; the radix-16 plan swizzles the row's 16-byte chunks)
 
 int fft2_table_offset(int M) {  // offset of M's radix-16 twiddle table inside the concatenated table buffer
   // order: 512, 1024, 2048, 4096 (second-level transforms), then 128, 256 (first-level transforms of fft_r16.cu)
@@ -401,6 +506,12 @@ static void conv16_t(const Fft2Job* d_jobs, dim3 grid, const float2* d_tab, int6
   k_fft2_conv16<M><<<grid, M / 16, smem, s>>>(d_jobs, d_tab + fft2_table_offset(M), n_blocks, xs, ys);
 }
 template <int M>
+static void sum16_t(const Fft2SumJob* d_jobs, dim3 grid, const float2* d_tab, int64_t n_blocks, int64_t xs, int64_t ys, cudaStream_t s) {
+  constexpr size_t smem = conv16_smem<M>();
+  GAC_SMEM_OPT_IN(k_fft2_sum16<M>, smem);
+  k_fft2_sum16<M><<<grid, M / 16, smem, s>>>(d_jobs, d_tab + fft2_table_offset(M), n_blocks, xs, ys);
+}
+template <int M>
 static void prep16_t(const float2* d_H, int64_t h_ch_stride, dim3 grid, int B, int P, float2* d_H2, const float2* d_tab, cudaStream_t s) {
   constexpr size_t smem = sizeof(float2) * r16::smem_elems(M);
   k_fft2_prep16<M><<<grid, M / 16, smem, s>>>(d_H, h_ch_stride, B, P, d_H2, d_tab + fft2_table_offset(M));
@@ -437,6 +548,33 @@ void launch_fft2_conv(const Fft2Job* d_jobs, int n_jobs, int max_seg, int C, int
       case 8192: conv_t<8192>(d_jobs + j0, grid, d_tw2, n_blocks, xs, ys, s); break;
     }
   }
+}
+
+void launch_fft2_sum(const Fft2SumJob* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tab16, int64_t n_blocks, int64_t xs, int64_t ys,
+                     cudaStream_t s) {
+  if (n_jobs <= 0 || max_seg <= 0) return;
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+    dim3 grid((unsigned)max_seg, (unsigned)C, (unsigned)nj);
+    switch (M) {
+      case 512: sum16_t<512>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
+      case 1024: sum16_t<1024>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
+      case 2048: sum16_t<2048>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
+      case 4096: sum16_t<4096>(d_jobs + j0, grid, d_tab16, n_blocks, xs, ys, s); break;
+    }
+  }
+}
+int fft2_sum_ctas_per_sm(int M) {
+  size_t smem = 0;
+  switch (M) {
+    case 512: smem = conv16_smem<512>(); break;
+    case 1024: smem = conv16_smem<1024>(); break;
+    case 2048: smem = conv16_smem<2048>(); break;
+    case 4096: smem = conv16_smem<4096>(); break;
+    default: return 1;
+  }
+  const int by_smem = (int)((size_t)227 * 1024 / (smem + 1024)), by_regs = 8192 / M;  // (launch bounds: 128 registers per thread)
+  return by_smem < by_regs ? (by_smem < 1 ? 1 : by_smem) : by_regs;
 }
 
 void launch_fft2_prep(const float2* d_H, int64_t h_ch_stride, int n_ch, int B, int P, int M, float2* d_H2, const float2* d_tw2, const float2* d_tab16,

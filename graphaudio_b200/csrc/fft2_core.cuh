@@ -437,6 +437,25 @@ F2_HD void store16(const float2 (&u)[16], float2* sm, int t) {
 #pragma unroll
   for (int q = 0; q < 8; q++) p[q] = make_float4(u[2 * q].x, u[2 * q].y, u[2 * q + 1].x, u[2 * q + 1].y);
 }
+// Rows of second-level IR spectra (H2) are kept UNPADDED, M float2 per row, with their 16-byte chunks XOR-swizzled: spectrum
+// positions 16 t + 2 q, 16 t + 2 q + 1 (register slots 2q, 2q+1 of thread t after stage C) live in chunk 8 t + (q ^ (t & 7)).
+// One bulk copy lands a row in shared memory as it lies in global memory, and the eight threads of a quarter-warp read eight
+// different bank groups with every 128-bit load (a padded row did the same with 19 % more bytes to move).
+F2_HD int swz_chunk(int t, int q) { return 8 * t + (q ^ (t & 7)); }
+F2_HD void load16_swz(float2 (&u)[16], const float2* row, int t) {
+  const float4* p = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 x = p[swz_chunk(t, q)];
+    u[2 * q] = make_float2(x.x, x.y);
+    u[2 * q + 1] = make_float2(x.z, x.w);
+  }
+}
+F2_HD void store16_swz(const float2 (&u)[16], float sc, float2* row, int t) {
+  float4* p = reinterpret_cast<float4*>(row);
+#pragma unroll
+  for (int q = 0; q < 8; q++) p[swz_chunk(t, q)] = make_float4(u[2 * q].x * sc, u[2 * q].y * sc, u[2 * q + 1].x * sc, u[2 * q + 1].y * sc);
+}
 // ---- inverse
 template <int M>
 F2_HD void inv_b(float2* sm, const float2* __restrict__ tab, int t) {

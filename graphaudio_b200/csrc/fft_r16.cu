@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
     const int cc = tid % COLS, rr = tid / COLS;
     const int64_t bcol = b0 - 1 + cc;
     const bool col_ok = bcol >= 0 && bcol < job.n_blocks;
-    if (!job.in2) {
+    if (!job.in2 && job.n_parts <= 1) {
       const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(tileT + cc);
       const float2* src0 = job.in + (col_ok ? bcol : 0);
       const uint32_t nbytes = col_ok ? 8u : 0u;
@@ -185,22 +185,32 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
+      // spectrograms that are summed before the inverse transform (linear): the pair of a true-stereo output, or the partial
+      // sums of a fan-in group
       constexpr int U = 8;
+      const int np = job.in2 ? 2 : job.n_parts;
+      const int64_t pstride = job.in2 ? (int64_t)(job.in2 - job.in) : job.part_stride;
       for (int r0 = rr; r0 <= H; r0 += RSTEP * U) {
-        float2 y[U], y2[U];
+        float2 y[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int row = r0 + RSTEP * u;
-          y[u] = y2[u] = make_float2(0.f, 0.f);
-          if (row <= H && col_ok) {
-            y[u] = job.in[(int64_t)row * ts + bcol];
-            y2[u] = job.in2[(int64_t)row * ts + bcol];  // true stereo: the pair is summed as spectra (linear)
+        for (int u = 0; u < U; u++) y[u] = make_float2(0.f, 0.f);
+        if (col_ok) {
+          for (int p = 0; p < np; p++) {
+            const float2* src = job.in + (int64_t)p * pstride + bcol;
+            float2 a[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              const int row = r0 + RSTEP * u;
+              a[u] = row <= H ? src[(int64_t)row * ts] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) y[u] = make_float2(y[u].x + a[u].x, y[u].y + a[u].y);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const int row = r0 + RSTEP * u;
-          if (row <= H) tileT[row * LD + cc] = make_float2(y[u].x + y2[u].x, y[u].y + y2[u].y);
+          if (row <= H) tileT[row * LD + cc] = y[u];
         }
       }
     }

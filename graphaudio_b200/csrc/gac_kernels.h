@@ -66,6 +66,10 @@ struct FftInvJob {
   int64_t n_blocks;
   const float2* in2 = nullptr;  // optional second spectrogram: out = ola(in) + ola(in2)  (true-stereo Sum)
   float* out2 = nullptr;        // optional second destination receiving the same samples (mono -> both rows)
+  // k_irfft_ola_t8 only: `in` is the first of n_parts partial spectrograms, part_stride float2 apart, summed BEFORE the inverse
+  // transform (the partial sums of a fan-in group, Fft2SumJob)
+  int n_parts = 1;
+  int64_t part_stride = 0;
 };
 void launch_irfft_ola(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int B, const float2* d_tw, cudaStream_t s);
 
@@ -110,10 +114,29 @@ struct Fft2Job {
   int nseg;          // segments of this launch
   int64_t b0 = 0;    // first output block of segment 0 (multiple of 16): lets two launches with different M share one spectrogram
 };
+// Fan-in fusion: the convolvers of several voices that end in the SAME fan-in (AudioNodeInput.MixBuffer, AudioNodeInput.cs:118-137)
+// are summed where the sum is cheapest — as second-level spectra.  One job = one output channel of a chunk of such voices:
+//     Y[k][.] = IFFT_M( sum_v FFT_M(X_v[k][window]) * H2_v[k][.] )
+// one forward transform + multiply-accumulate per member, ONE inverse transform and one Y segment per job (linear: the same
+// samples as transforming every member back and adding the results, up to float32 rounding order).
+struct Fft2SumMember {
+  const float2* X;   // the member's XT channel base
+  const float2* H2;  // the member's second-level IR spectra [B+1][M]
+};
+struct Fft2SumJob {
+  const Fft2SumMember* members;  // device array
+  int n_members;
+  float2* Y;         // partial YT channel base of this chunk
+  int Lh, nseg;
+  int64_t b0 = 0;
+};
+void launch_fft2_sum(const Fft2SumJob* d_jobs, int n_jobs, int max_seg, int C, int M, const float2* d_tab16, int64_t n_blocks, int64_t xs, int64_t ys,
+                     cudaStream_t s);
+int fft2_sum_ctas_per_sm(int M);  // resident CTAs per SM of k_fft2_sum16<M> (shared-memory bound): the planner sizes chunks with it
 constexpr int kFft2TwLen = 8192;  // twiddle table exp(-2 pi i e / 8192)
 // second-level transform length for P partitions (512..8192), 0 if the IR is too long; *Lh = history length
 int fft2_pick_m(int P, int* Lh);
-// float2 elements of one H2 row (one bin of one IR channel): M for the radix-8 plan, the padded length for the radix-16 plan
+// float2 elements of one H2 row (one bin of one IR channel): M (the radix-16 plan keeps the row's 16-byte chunks XOR-swizzled)
 int fft2_h2_row_elems(int M);
 int fft2_r16_max();                  // largest transform length on the radix-16 plan (4096; GAC_FFT2_R16_MAX overrides for A/B runs)
 // d_tw2: the 8192-entry table (radix-8 plan, M = 8192); d_tab16: the concatenated radix-16 tables (M = 512 .. 4096)

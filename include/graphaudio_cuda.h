@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GAC_ABI_VERSION 6
+#define GAC_ABI_VERSION 7
 
 /* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */
 typedef enum gac_status {
@@ -83,6 +83,12 @@ typedef struct gac_context_desc {
  * on the bench workload; the double-length spectra of an impulse response are prepared on first use).  This flag keeps every segment
  * at the length picked for the impulse response (A/B measurements, tests); results agree to 2e-6. */
 #define GAC_FLAG_UNIFORM_SEGMENTS 2
+/* Fan-in fusion (default ON): ConvolverNodes that are the last node of their chain and whose outputs meet in the same fan-in
+ * (AudioNodeInput.MixBuffer, AudioNodeInput.cs:118-137: a bus head or the destination) are summed as second-level spectra, so
+ * that a whole group of voices pays for ONE inverse transform pair and one fan-in input (csrc/fft2.cu, k_fft2_sum16).  The sum
+ * is the same linear combination in another float32 rounding order (measured <= 3e-7 of the bus peak).  This flag keeps one
+ * inverse transform and one fan-in input per voice: the reference's order of additions (A/B measurements, tests). */
+#define GAC_FLAG_NO_FANIN_FUSION 4
 
 int gac_context_create(const gac_context_desc* desc, gac_context** out);
 int gac_context_destroy(gac_context* ctx);
@@ -357,6 +363,8 @@ typedef struct gac_stats {
   double ms_panner;            /* StereoPannerNode                                                  */
   double mac_h2_bytes_single;  /* bytes of ONE set of IR spectra over the channel-convolvers of the render: with the
                                   spectrograms read and written once, the compulsory traffic of K6   */
+  int32_t fanin_groups;        /* fan-in groups whose convolvers were summed as spectra (GAC_FLAG_NO_FANIN_FUSION: 0)  */
+  int32_t fanin_members;       /* convolver nodes in those groups                                                    */
 } gac_stats;
 int gac_get_stats(gac_context* ctx, gac_stats* out);
 

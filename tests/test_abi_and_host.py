@@ -33,13 +33,13 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_version_and_struct_layouts():
-    assert N.lib().gac_version() == 6
+    assert N.lib().gac_version() == 7
     # gac_event must be bit-compatible with AutomationEvent (AudioParam.cs:360-367): int, float, float, (pad), double, double
     assert C.sizeof(N.gac_event) == 32
     assert N.gac_event.time.offset == 16 and N.gac_event.time_constant.offset == 24
     assert C.sizeof(N.gac_param) == 32
     assert C.sizeof(N.gac_context_desc) == 32
-    assert C.sizeof(N.gac_stats) == 176
+    assert C.sizeof(N.gac_stats) == 184
 
 
 def test_no_cpu_fallback_without_device():

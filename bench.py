@@ -290,7 +290,7 @@ def run_reference(args, wl):
 
 
 # ----------------------------------------------------------------------------------------------- ncu traffic (child process)
-K6_REGEX = "regex:k_fft2_conv"
+K6_REGEX = "regex:k_fft2_conv|k_fft2_sum16"
 
 
 def ncu_traffic_live(args, wl, n_voices, timeout_s=420):
@@ -536,13 +536,20 @@ def run_ours(args, wl):
         # compulsory bytes of K6: XT in, YT out (B+1 rows of Qs blocks per channel-convolver), ONE set of second-level IR spectra
         spectro = units / (Npad // Bp) * Cb * Qs * 8.0
         h2_one = s_last.get("mac_h2_bytes_single", 0.0)
-        compulsory = 2 * spectro + h2_one if used == 3 else moved
+        fused = int(s_last.get("fanin_members", 0))   # convolvers summed as spectra (fan-in fusion): per-voice YT, K7 and fan-in inputs are gone
+        # moved = XT once + every H2 table the plan reads (single length: M float2 per row, + the double-length rows, 2 M, with mixed
+        # segments) + what K6 writes (per-voice YT, or one partial spectrogram per voice chunk with fan-in fusion)
+        compulsory = moved - (2 * h2_one if big > 0 else 0.0) if used == 3 else moved
+        yt_bytes = max(0.0, compulsory - spectro - h2_one) if used == 3 else spectro   # what K6 writes and K7 reads
         k6_name = {1: "k_mac_stream (K6, direct sum, reference op order)", 2: "k_mac_tiled (K6, register-tiled direct sum, FFMA)",
                    4: "k_mac_tiled (K6, register-tiled direct sum, FFMA2)",
                    3: "k_fft2_conv16 (K6 spectral MAC as a fast convolution along block time)"}.get(used, "K6")
+        kn = "k_fft2_sum16" if fused else "k_fft2_conv16"
+        if used == 3 and fused:
+            k6_name = "k_fft2_sum16 (K6 as a fast convolution along block time, the voices of a fan-in summed as second-level spectra)"
         if used == 3 and big > 0:
-            k6_name = (f"k_fft2_conv16<2M> + k_fft2_conv16<M> (K6 as a fast convolution along block time: {big} double-length overlap-save "
-                       "segment(s) in front, two launches timed together)")
+            k6_name = (f"{kn}<2M> + {kn}<M> (K6 as a fast convolution along block time" + (", the voices of a fan-in summed as second-level spectra" if fused else "") +
+                       f": {big} double-length overlap-save segment(s) in front, two launches timed together)")
         # bytes every kernel of the render has to move once (compulsory): source in (biquad or K5), biquad streams, signal rows,
         # automation tables out + in, K5 signal in + XT out, K6, K7 YT in + signal out, fan-in reads + bus write
         sig_bytes = nvox * 2 * Npad * 4.0
@@ -552,8 +559,8 @@ def run_ours(args, wl):
             "biquad": (sig_bytes * 2 + Npad * 4.0) if wl["kind"] == "c3" else 0.0,      # source in, filtered signal out, cutoff table
             "K5": sig_bytes + nvox * Npad * 4.0 + spectro,                              # signal + gain table in, XT out
             "K6": compulsory,
-            "K7": spectro + sig_bytes,                                                   # YT in, signal out
-            "mix": sig_bytes + 2 * Npad * 4.0 * 2,                                       # fan-in reads, bus write + bus gain pass
+            "K7": yt_bytes + (2 * Npad * 4.0 if fused else sig_bytes),                   # YT in, signal out (fused: the group's sum)
+            "mix": (2 * Npad * 4.0 if fused else sig_bytes) + 2 * Npad * 4.0 * 2,        # fan-in reads, bus write + bus gain pass
         }
         whole_bytes = float(sum(whole.values()))
         conv_ms = mean("ms_fft_fwd") + mac_ms + mean("ms_fft_inv")
@@ -591,8 +598,10 @@ def run_ours(args, wl):
                          "traffic": traffic.get("dram_bytes") if traffic else None,
                          "traffic_detail": traffic,
                          "kernel": k6_name, "peak_source": peak_src, "ms_per_launch": mac_ms, "algorithmic_bytes_per_launch": compulsory,
-                         "bytes_definition": "compulsory: XT read once + YT written once + ONE set of second-level IR spectra (the second, "
-                                             "double-length table the mixed-segment plan also reads is NOT counted)",
+                         "bytes_definition": "compulsory: XT read once + ONE set of second-level IR spectra (the second, double-length table the "
+                                             "mixed-segment plan also reads is NOT counted) + what K6 writes (with fan-in fusion: one partial "
+                                             "spectrogram per voice chunk and output channel instead of one YT per channel-convolver)",
+                         "fanin_fusion": {"groups": int(s_last.get("fanin_groups", 0)), "convolvers": fused},
                          "moved_bytes_per_launch": moved, "frac_on_moved_bytes": moved / (mac_ms * 1e-3) / 1e9 / peak,
                          "convolver_K5_K6_K7": {"ms": conv_ms, "bytes": conv_bytes, "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9,
                                                 "frac": conv_bytes / (conv_ms * 1e-3) / 1e9 / peak},

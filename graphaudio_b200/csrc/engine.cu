@@ -145,6 +145,8 @@ struct gac_context {
   // (1024 voices: 57 ms per render of which 25 ms were gaps).  Blocks are taken from the process-wide pool on demand.
   std::vector<char*> stage_blocks;
   size_t stage_block = 0, stage_used = 0;  // current block / bytes used in it
+  CopySegments pending;                    // staged tables whose copy to the device has not been launched yet (kstream() flushes)
+  bool defer_copies = false;               // inside render_core: table copies wait for the next kernel launch and travel together
   // render scratch arena (struct Scratch): device chunks kept between renders, bump-allocated
   std::vector<std::pair<char*, size_t>> arena;
   size_t arena_chunk = 0, arena_used = 0;
@@ -265,6 +267,16 @@ static bool use_fft2(const gac_context* c, int P, int M2) {
 // Host table -> device, ordered on the context stream.  With asynchronous uploads the table goes through the context's
 // page-locked staging area and a copy kernel (see gac_context::h_stage); the staging area is recycled by every render
 // (renders synchronise before they return).  The destination must be allocated in multiples of 16 bytes.
+static void flush_copies(gac_context* ctx) {
+  if (ctx->pending.n == 0) return;
+  launch_copy_from_host_multi(ctx->pending, ctx->stream);
+  ctx->pending.n = 0;
+}
+// the stream kernels are launched on, with every table they may read on its way
+static inline cudaStream_t kstream(gac_context* ctx) {
+  flush_copies(ctx);
+  return ctx->stream;
+}
 static int table_h2d(gac_context* ctx, void* d_dst, const void* h_src, size_t bytes) {
   if (bytes == 0) return GAC_OK;
   const size_t need = (bytes + 15) & ~(size_t)15;
@@ -284,10 +296,19 @@ static int table_h2d(gac_context* ctx, void* d_dst, const void* h_src, size_t by
       char* slot = ctx->stage_blocks[ctx->stage_block] + ctx->stage_used;
       ctx->stage_used += need;
       memcpy(slot, h_src, bytes);
-      launch_copy_from_host(d_dst, slot, need, ctx->stream);
+      // the copy is deferred: every kernel launch on the context stream goes through kstream(), which sends the pending tables
+      // with one launch first
+      if (ctx->pending.n == kCopySegs) flush_copies(ctx);
+      CopySegments& pc = ctx->pending;
+      pc.dst[pc.n] = d_dst;
+      pc.src[pc.n] = slot;
+      pc.n16[pc.n] = need / 16;
+      pc.n++;
+      if (!ctx->defer_copies) flush_copies(ctx);
       return GAC_OK;
     }
   }
+  flush_copies(ctx);  // (keeps the order of writes to a destination that is uploaded twice)
   cudaError_t e = cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) return fail(GAC_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
   return GAC_OK;
@@ -1163,14 +1184,14 @@ static int run_param_jobs(RenderEnv& env, std::vector<ParamJob>& jobs) {
   if (rc) return rc;
   int t = env.timer->begin(C_AUTO);
   // a-rate and k-rate jobs share a launch; the kernel branches per job
-  launch_param_eval(dj, (int)hj.size(), env.ctx->d_bt, env.NQ, env.ctx->fs, env.ctx->stream);
+  launch_param_eval(dj, (int)hj.size(), env.ctx->d_bt, env.NQ, env.ctx->fs, kstream(env.ctx));
   if (!env.mod_jobs.empty()) {  // intrinsic + modulation, clamped (AudioParam.cs:125-131, :150-155)
     auto& hm = env.keep->make<ModJob>();
     hm = env.mod_jobs;
     env.mod_jobs.clear();
     ModJob* dm = nullptr;
     if ((rc = env.scratch->upload(&dm, hm))) return rc;
-    launch_param_modulate(dm, (int)hm.size(), env.Npad, env.ctx->stream);
+    launch_param_modulate(dm, (int)hm.size(), env.Npad, kstream(env.ctx));
     env.launches++;
   }
   env.timer->end(t);
@@ -1320,22 +1341,22 @@ static int conv_batch_direct(RenderEnv& env, std::vector<ConvItem>& items) {
     if ((rc = env.scratch->upload(&dt, tiles))) return rc;
 
     int t = env.timer->begin(C_FFT_FWD);
-    launch_rfft_fwd(dfj, (int)fj.size(), QB, B, ctx->d_tw, ctx->stream);
+    launch_rfft_fwd(dfj, (int)fj.size(), QB, B, ctx->d_tw, kstream(ctx));
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_MAC);
     if (ctx->mac_variant == 1)
-      launch_mac_stream(dmj, (int)mj.size(), QB, B, ctx->stream);
+      launch_mac_stream(dmj, (int)mj.size(), QB, B, kstream(ctx));
     else
     {
       int pmax = 1;
       for (auto& m : mj) pmax = std::max(pmax, m.P);
-      launch_mac_tiled(dmj, (int)mj.size(), dt, (int)tiles.size(), QB, pmax, B, TB, ctx->mac_variant == 2 ? 2 : 0, ctx->stream);
+      launch_mac_tiled(dmj, (int)mj.size(), dt, (int)tiles.size(), QB, pmax, B, TB, ctx->mac_variant == 2 ? 2 : 0, kstream(ctx));
     }
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
-    launch_irfft_ola(dij, (int)ij.size(), QB, B, ctx->d_tw, ctx->stream);
+    launch_irfft_ola(dij, (int)ij.size(), QB, B, ctx->d_tw, kstream(ctx));
     env.timer->end(t);
     CU(cudaGetLastError());
     env.launches += (ctx->mac_variant == 1) ? 3 : 4;  // K5, K6 (+ k_mac_dc), K7
@@ -1412,7 +1433,7 @@ static int ensure_h2b_batch(RenderEnv& env, const std::vector<const gac_ir*>& ir
     IrChanJob* dj = nullptr;
     int rc = env.scratch->upload(&dj, hj);
     if (rc) return rc;
-    launch_fft2_prep_batch(dj, (int)hj.size(), B, kv.first, ctx->d_tab16, ctx->stream);
+    launch_fft2_prep_batch(dj, (int)hj.size(), B, kv.first, ctx->d_tab16, kstream(ctx));
     env.launches++;
     CU(cudaGetLastError());
   }
@@ -1522,17 +1543,17 @@ static int conv_batch_fft2(RenderEnv& env, std::vector<ConvItem>& items, int M) 
     if ((rc = env.scratch->upload(&dij, ij))) return rc;
     TRACE_MARK("conv fft2: tables uploaded");
     int t = env.timer->begin(C_FFT_FWD);
-    launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
+    launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, kstream(ctx));
     env.timer->end(t);
     CU(cudaGetLastError());
     t = env.timer->begin(C_MAC);
-    launch_fft2_conv(dcjb, (int)cjb.size(), max_seg_big, C, 2 * M, ctx->d_tw2, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
-    launch_fft2_conv(dcj, (int)cj.size(), max_seg, C, M, ctx->d_tw2, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
+    launch_fft2_conv(dcjb, (int)cjb.size(), max_seg_big, C, 2 * M, ctx->d_tw2, ctx->d_tab16, QB, Qs, Qs, kstream(ctx));
+    launch_fft2_conv(dcj, (int)cj.size(), max_seg, C, M, ctx->d_tw2, ctx->d_tab16, QB, Qs, Qs, kstream(ctx));
     env.timer->end(t);
     if (!cjb.empty()) env.launches += 1;
     CU(cudaGetLastError());
     t = env.timer->begin(C_FFT_INV);
-    launch_irfft_ola_t8(dij, (int)ij.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
+    launch_irfft_ola_t8(dij, (int)ij.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, kstream(ctx));
     env.timer->end(t);
     CU(cudaGetLastError());
     env.launches += 3;
@@ -1674,16 +1695,16 @@ static int conv_batch_fft2_sum(RenderEnv& env, std::vector<ConvItem>& items, int
   if ((rc = env.scratch->upload(&dij, ij))) return rc;
   TRACE_MARK("conv fft2 (fan-in group): tables uploaded");
   int t = env.timer->begin(C_FFT_FWD);
-  launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
+  launch_rfft_fwd_t8(dfj, (int)fj.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, kstream(ctx));
   env.timer->end(t);
   CU(cudaGetLastError());
   t = env.timer->begin(C_MAC);
-  launch_fft2_sum(dsjb, (int)sjb.size(), n_big, C, 2 * M, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
-  launch_fft2_sum(dsj, (int)sj.size(), nseg, C, M, ctx->d_tab16, QB, Qs, Qs, ctx->stream);
+  launch_fft2_sum(dsjb, (int)sjb.size(), n_big, C, 2 * M, ctx->d_tab16, QB, Qs, Qs, kstream(ctx));
+  launch_fft2_sum(dsj, (int)sj.size(), nseg, C, M, ctx->d_tab16, QB, Qs, Qs, kstream(ctx));
   env.timer->end(t);
   CU(cudaGetLastError());
   t = env.timer->begin(C_FFT_INV);
-  launch_irfft_ola_t8(dij, (int)ij.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, ctx->stream);
+  launch_irfft_ola_t8(dij, (int)ij.size(), QB, B, Qs, ctx->d_tab16, ctx->d_tw, kstream(ctx));
   env.timer->end(t);
   CU(cudaGetLastError());
   env.launches += 3 + (n_big > 0 && nseg > 0 ? 1 : 0);
@@ -1776,19 +1797,19 @@ static int prepare_irs(RenderEnv& env, const std::vector<const gac_ir*>& irs) {
   if ((rc = env.scratch->upload(&dcj, cjs))) return rc;
   if ((rc = env.scratch->upload(&dfj, fj))) return rc;
   const float cal = (float)std::pow(10.0, (double)(-58.f * 0.05f));  // PartitionedConvolver.cs:95,101
-  launch_ir_scale_batch(dcj, (int)cjs.size(), cal, B, ctx->stream);
-  launch_rfft_fwd(dfj, (int)fj.size(), pmax, B, ctx->d_tw, ctx->stream);
+  launch_ir_scale_batch(dcj, (int)cjs.size(), cal, B, kstream(ctx));
+  launch_rfft_fwd(dfj, (int)fj.size(), pmax, B, ctx->d_tw, kstream(ctx));
   env.launches += 2;
   for (size_t i0 = 0; i0 < ms.size();) {
     size_t i1 = i0;
     while (i1 < ms.size() && ms[i1] == ms[i0]) i1++;
     const int M = ms[i0];
     if (M > 0 && M <= fft2_r16_max()) {
-      launch_fft2_prep_batch(dcj + i0, (int)(i1 - i0), B, M, ctx->d_tab16, ctx->stream);
+      launch_fft2_prep_batch(dcj + i0, (int)(i1 - i0), B, M, ctx->d_tab16, kstream(ctx));
       env.launches++;
     } else if (M > 0) {  // radix-8 plan: per channel
       for (size_t i = i0; i < i1; i++) {
-        launch_fft2_prep(cjs[i].H, 0, 1, B, cjs[i].P, M, cjs[i].H2, ctx->d_tw2, ctx->d_tab16, ctx->stream);
+        launch_fft2_prep(cjs[i].H, 0, 1, B, cjs[i].P, M, cjs[i].H2, ctx->d_tw2, ctx->d_tab16, kstream(ctx));
         env.launches++;
       }
     }
@@ -1877,7 +1898,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       DelayJob* dd = nullptr;
       if ((rc = env.scratch->upload(&dd, dj))) return rc;
       int t = env.timer->begin(C_DELAY);
-      launch_delay(dd, (int)dj.size(), env.Npad, ctx->fs, ctx->stream);
+      launch_delay(dd, (int)dj.size(), env.Npad, ctx->fs, kstream(ctx));
       env.timer->end(t);
       env.launches += 1;
       CU(cudaGetLastError());
@@ -1927,7 +1948,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
       PannerJob* dq = nullptr;
       if ((rc = env.scratch->upload(&dq, qj))) return rc;
       int t = env.timer->begin(C_PANNER);
-      launch_panner(dq, (int)qj.size(), env.Npad, scan, ctx->stream);
+      launch_panner(dq, (int)qj.size(), env.Npad, scan, kstream(ctx));
       env.timer->end(t);
       env.launches += scan ? 2 : 1;
       CU(cudaGetLastError());
@@ -1966,7 +1987,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         GainJob* dg = nullptr;
         if ((rc = env.scratch->upload(&dg, gj))) return rc;
         int t = env.timer->begin(C_GAIN);
-        launch_gain(dg, (int)gj.size(), env.Npad, ctx->stream);
+        launch_gain(dg, (int)gj.size(), env.Npad, kstream(ctx));
         env.timer->end(t);
         env.launches += 1;
         CU(cudaGetLastError());
@@ -2087,12 +2108,12 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if ((rc = env.scratch->alloc(&dstates_slow, n_f2s))) return rc;
         if ((rc = env.scratch->alloc(&dflags, n_i))) return rc;
         int t = env.timer->begin(C_BIQUAD);
-        launch_biquad_classes(dreps, n_cls, env.Npad, env.NQ, ctx->fs, dlast, dent, dwide, dcs, cs_stride, ctx->stream);
+        launch_biquad_classes(dreps, n_cls, env.Npad, env.NQ, ctx->fs, dlast, dent, dwide, dcs, cs_stride, kstream(ctx));
         bool partial = false;
         for (const BiquadJob& j : sj) partial = partial || j.lo > 0 || j.hi < env.Npad;
-        if (partial) launch_biquad_zero_outside(dsj, (int)sj.size(), env.Npad, ctx->stream);
-        launch_biquad_lanes_shared(dsj, dgroups, n_spec_groups, dcs, cs_stride, env.Npad, dstates, dflags, false, ctx->stream);
-        launch_biquad_lanes_shared(dsj, dgroups + n_spec_groups, n_slow_groups, dcs, cs_stride, env.Npad, dstates_slow, nullptr, true, ctx->stream);
+        if (partial) launch_biquad_zero_outside(dsj, (int)sj.size(), env.Npad, kstream(ctx));
+        launch_biquad_lanes_shared(dsj, dgroups, n_spec_groups, dcs, cs_stride, env.Npad, dstates, dflags, false, kstream(ctx));
+        launch_biquad_lanes_shared(dsj, dgroups + n_spec_groups, n_slow_groups, dcs, cs_stride, env.Npad, dstates_slow, nullptr, true, kstream(ctx));
         env.timer->end(t);
         env.launches += 3 + (partial ? 1 : 0) + (n_slow_groups > 0 ? 1 : 0) +
                         (n_spec_groups > 0 ? 1 + (biquad_shared_segments(n_spec_groups, env.Npad, nullptr) > 1 ? 2 : 0) : 0);
@@ -2130,7 +2151,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if ((rc = env.scratch->alloc(&dstates, n_f2))) return rc;
         if ((rc = env.scratch->alloc(&dbad, n_i))) return rc;
         int t = env.timer->begin(C_BIQUAD);
-        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, s2_all, dstates, dbad, ctx->stream);
+        launch_biquad(dbj, (int)nk, env.Npad, env.NQ, ctx->fs, dlast, dent, s1_all, s2_all, dstates, dbad, kstream(ctx));
         env.timer->end(t);
         env.launches += n_seg > 1 ? 9 : 6;
         CU(cudaGetLastError());
@@ -2297,7 +2318,7 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         GainJob* dz = nullptr;
         int rc = env.scratch->upload(&dz, zj);
         if (rc) return rc;
-        launch_gain(dz, (int)zj.size(), env.Npad, ctx->stream);
+        launch_gain(dz, (int)zj.size(), env.Npad, kstream(ctx));
         env.launches += 1;
       }
       {

@@ -215,14 +215,14 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
     SourceJob* d = nullptr;
     int rc = env.scratch->upload(&d, cj);
     if (rc) return rc;
-    launch_source_copy(d, (int)cj.size(), env.Npad, ctx->stream);
+    launch_source_copy(d, (int)cj.size(), env.Npad, kstream(ctx));
     env.launches++;
   }
   if (!rj.empty()) {
     ResampleJob* d = nullptr;
     int rc = env.scratch->upload(&d, rj);
     if (rc) return rc;
-    launch_resample(d, (int)rj.size(), env.Npad, ctx->stream);
+    launch_resample(d, (int)rj.size(), env.Npad, kstream(ctx));
     env.launches++;
   }
   env.timer->end(t);
@@ -317,7 +317,7 @@ static int plan_scheduled(RenderEnv& env, const std::vector<const VoiceH*>& voic
   SchedJob* dj = nullptr;
   if ((rc = env.scratch->upload(&dj, jobs))) return rc;
   int t = env.timer->begin(C_SOURCE);
-  launch_scheduled_sources(dj, (int)jobs.size(), env.Npad, ctx->fs, any_osc, ctx->stream);
+  launch_scheduled_sources(dj, (int)jobs.size(), env.Npad, ctx->fs, any_osc, kstream(ctx));
   env.timer->end(t);
   env.launches += any_osc ? 3 : 1;
   CU(cudaGetLastError());
@@ -447,7 +447,7 @@ static int mix_into(RenderEnv& env, std::vector<MixJob>& jobs, std::vector<MixIn
   int t = env.timer->begin(C_MIX);
   for (size_t j0 = 0; j0 < hj.size(); j0 += 65535) {
     size_t nj = std::min<size_t>(65535, hj.size() - j0);
-    launch_mix(dj + j0, (int)nj, di, env.Npad, env.ctx->stream);
+    launch_mix(dj + j0, (int)nj, di, env.Npad, kstream(env.ctx));
     env.launches++;
   }
   env.timer->end(t);
@@ -481,6 +481,15 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   const int64_t total = a.first_frame + a.n_frames;
   ctx->stage_block = 0;
   ctx->stage_used = 0;  // the previous render has synchronised: its staged job tables are dead
+  ctx->pending.n = 0;
+  struct DeferScope {  // job tables staged during the render travel with the next kernel launch, several per copy launch
+    gac_context* c;
+    explicit DeferScope(gac_context* x) : c(x) { c->defer_copies = true; }
+    ~DeferScope() {
+      flush_copies(c);
+      c->defer_copies = false;
+    }
+  } defer_scope(ctx);
   RenderEnv env;
   Scratch scratch(ctx);
   HostKeep keep;
@@ -949,7 +958,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     if (a.h_inter) {  // ≙ the interleaving loop of ProcessBlockInterleaved (AudioContextBase.cs:127-160), for the whole render
       float* d_inter = nullptr;
       if ((rc = scratch.alloc(&d_inter, (size_t)a.n_frames * a.inter_channels))) return rc;
-      launch_interleave(dest0[0] + a.first_frame, a.n_out > 1 ? dest1[0] + a.first_frame : nullptr, d_inter, a.n_frames, a.inter_channels, ctx->stream);
+      launch_interleave(dest0[0] + a.first_frame, a.n_out > 1 ? dest1[0] + a.first_frame : nullptr, d_inter, a.n_frames, a.inter_channels, kstream(ctx));
       env.launches++;
       CU(cudaMemcpyAsync(a.h_inter + (size_t)a.start_index * a.inter_channels, d_inter, sizeof(float) * (size_t)a.n_frames * a.inter_channels,
                          cudaMemcpyDeviceToHost, ctx->stream));
@@ -957,6 +966,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     timer.end(t);
   }
   // ---- finish: the host job arrays in `keep` must outlive the stream work, so every render synchronises here
+  flush_copies(ctx);
   trace.mark("everything queued");
   gac_stats st{};
   timer.finish(&st);
@@ -1293,7 +1303,7 @@ extern "C" int gac_rfft_fwd_batch(gac_context* ctx, const float* x, int n_signal
                         n_blocks * B, n_blocks, 0, std::numeric_limits<int64_t>::max()};
   }
   CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(FftFwdJob) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
-  launch_rfft_fwd(dj.as<FftFwdJob>(), n_signals, n_blocks, B, ctx->d_tw, ctx->stream);
+  launch_rfft_fwd(dj.as<FftFwdJob>(), n_signals, n_blocks, B, ctx->d_tw, kstream(ctx));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(spectra, dX.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1314,7 +1324,7 @@ extern "C" int gac_irfft_ola_batch(gac_context* ctx, const float* Y, int n_signa
   for (int s = 0; s < n_signals; s++)
     jobs[s] = FftInvJob{dY.as<float2>() + (size_t)s * n_blocks * B, dy.as<float>() + (size_t)s * n_blocks * B, n_blocks};
   CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(FftInvJob) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
-  launch_irfft_ola(dj.as<FftInvJob>(), n_signals, n_blocks, B, ctx->d_tw, ctx->stream);
+  launch_irfft_ola(dj.as<FftInvJob>(), n_signals, n_blocks, B, ctx->d_tw, kstream(ctx));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(y, dy.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1359,14 +1369,14 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
     for (int s = 0; s < n_signals; s++)
       CU(cudaMemcpyAsync(dH.as<float2>() + (size_t)s * P16 * B, H + (size_t)s * n_partitions * B * 2, (size_t)n_partitions * B * 8,
                          cudaMemcpyHostToDevice, ctx->stream));
-    launch_fft2_prep(dH.as<float2>(), (int64_t)P16 * B, n_signals, B, n_partitions, M, dH2.as<float2>(), ctx->d_tw2, ctx->d_tab16, ctx->stream);
+    launch_fft2_prep(dH.as<float2>(), (int64_t)P16 * B, n_signals, B, n_partitions, M, dH2.as<float2>(), ctx->d_tw2, ctx->d_tab16, kstream(ctx));
     const int V = M - Lh;
     const int nseg = (int)((n_blocks + V - 1) / V);
     std::vector<Fft2Job> jobs(n_signals);
     for (int s = 0; s < n_signals; s++)
       jobs[s] = Fft2Job{dXT.as<float2>() + (size_t)s * C * Qs, dH2.as<float2>() + (size_t)s * C * fft2_h2_row_elems(M), dYT.as<float2>() + (size_t)s * C * Qs, Lh, nseg};
     CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(Fft2Job) * n_signals, cudaMemcpyHostToDevice, ctx->stream));
-    launch_fft2_conv(dj.as<Fft2Job>(), n_signals, nseg, C, M, ctx->d_tw2, ctx->d_tab16, n_blocks, Qs, Qs, ctx->stream);
+    launch_fft2_conv(dj.as<Fft2Job>(), n_signals, nseg, C, M, ctx->d_tw2, ctx->d_tab16, n_blocks, Qs, Qs, kstream(ctx));
     CU(cudaGetLastError());
     std::vector<float2> yt(xt.size());
     CU(cudaMemcpyAsync(yt.data(), dYT.p, yt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1409,9 +1419,9 @@ extern "C" int gac_spectral_mac(gac_context* ctx, const float* X, const float* H
   CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(MacJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(dt.p, tiles.data(), sizeof(MacTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (variant == 1)
-    launch_mac_stream(dj.as<MacJob>(), (int)jobs.size(), n_blocks, B, ctx->stream);
+    launch_mac_stream(dj.as<MacJob>(), (int)jobs.size(), n_blocks, B, kstream(ctx));
   else
-    launch_mac_tiled(dj.as<MacJob>(), (int)jobs.size(), dt.as<MacTile>(), (int)tiles.size(), n_blocks, n_partitions, B, TB, variant == 2 ? 2 : 0, ctx->stream);
+    launch_mac_tiled(dj.as<MacJob>(), (int)jobs.size(), dt.as<MacTile>(), (int)tiles.size(), n_blocks, n_partitions, B, TB, variant == 2 ? 2 : 0, kstream(ctx));
   CU(cudaGetLastError());
   for (int s = 0; s < n_signals; s++)
     CU(cudaMemcpyAsync(Y + (size_t)s * n_blocks * B * 2, dY.as<float2>() + (size_t)s * QBpad * B, (size_t)n_blocks * B * 8, cudaMemcpyDeviceToHost,
@@ -1514,7 +1524,7 @@ extern "C" int gac_automation_eval(gac_context* ctx, const gac_param* param, int
   if (!p.ev.empty()) CU(cudaMemcpyAsync(dev.p, p.ev.data(), sizeof(gac_event) * p.ev.size(), cudaMemcpyHostToDevice, ctx->stream));
   ParamJob j{p.value, (int)p.ev.size(), dev.as<DevEvent>(), dout.as<float>(), a_rate ? 1 : 0};
   CU(cudaMemcpyAsync(dj.p, &j, sizeof(j), cudaMemcpyHostToDevice, ctx->stream));
-  launch_param_eval(dj.as<ParamJob>(), 1, ctx->d_bt, NQ, ctx->fs, ctx->stream);
+  launch_param_eval(dj.as<ParamJob>(), 1, ctx->d_bt, NQ, ctx->fs, kstream(ctx));
   CU(cudaGetLastError());
   if (a_rate) {
     CU(cudaMemcpyAsync(values, dout.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1577,7 +1587,7 @@ extern "C" int gac_resample_cubic(gac_context* ctx, const float* in, int64_t n_i
   j.n_emit = m;
   j.n_zero_from = m;
   CU(cudaMemcpyAsync(dj.p, &j, sizeof(j), cudaMemcpyHostToDevice, ctx->stream));
-  launch_resample(dj.as<ResampleJob>(), 1, m, ctx->stream);
+  launch_resample(dj.as<ResampleJob>(), 1, m, kstream(ctx));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, dout.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1681,7 +1691,7 @@ extern "C" int gac_mix(gac_context* ctx, const float* const* inputs, const int64
   mj.n_inputs = n_inputs;
   if (n_inputs) CU(cudaMemcpyAsync(di.p, mi.data(), sizeof(MixInput) * mi.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(dj.p, &mj, sizeof(mj), cudaMemcpyHostToDevice, ctx->stream));
-  launch_mix(dj.as<MixJob>(), 1, di.as<MixInput>(), Npad, ctx->stream);
+  launch_mix(dj.as<MixJob>(), 1, di.as<MixInput>(), Npad, kstream(ctx));
   CU(cudaGetLastError());
   CU(cudaMemcpy2DAsync(out, (size_t)n_frames * 4, dout.p, (size_t)Npad * 4, (size_t)n_frames * 4, 2, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

@@ -68,20 +68,27 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
 
   // Both rounds' input frames (and gain-table entries) are requested before anything is computed: 32 independent 8-byte
   // loads in flight per thread.  Thread t of a group owns z[n] = x[2n] + i x[2n+1] for n = t + T j, j < 8.
+  // Gate: frames outside the non-silent range [gate_lo, gate_hi) read as zero and are NOT loaded (`in` may alias a source buffer
+  // that only covers that range).  The bounds are multiples of 128 and n_valid is a multiple of the partition size on this path,
+  // so the test is made once per block: [lo_b, hi_b) = the open frames of the block, relative to its first frame.
   float2 xin[2][8], gin[2][8];
+  int lo_b[2], hi_b[2];
 #pragma unroll
   for (int rnd = 0; rnd < 2; rnd++) {
     const int64_t f0 = (b0 + G::tile_col(tid, rnd)) * H;
+    const int64_t lo = job.gate_lo - f0, hi = (job.gate_hi < job.n_valid ? job.gate_hi : job.n_valid) - f0;
+    lo_b[rnd] = lo < 0 ? 0 : (lo > H ? H : (int)lo);
+    hi_b[rnd] = hi < 0 ? 0 : (hi > H ? H : (int)hi);
+    const float* __restrict__ src = job.in + f0;
+    const float* __restrict__ gsrc = job.gain ? job.gain + f0 : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const int64_t g = f0 + 2 * (t + T * j);
+      const int fi = 2 * (t + T * j);
       xin[rnd][j] = make_float2(0.f, 0.f);
       gin[rnd][j] = make_float2(job.gain_const, job.gain_const);
-      // n_valid is a multiple of the partition size on this path; frames outside the non-silent range [gate_lo, gate_hi)
-      // (multiples of 128) read as zero and are NOT loaded: `in` may alias a source buffer that only covers that range
-      if (g + 1 < job.n_valid && g >= job.gate_lo && g < job.gate_hi) {
-        xin[rnd][j] = *reinterpret_cast<const float2*>(job.in + g);
-        if (job.gain) gin[rnd][j] = *reinterpret_cast<const float2*>(job.gain + g);
+      if (fi >= lo_b[rnd] && fi < hi_b[rnd]) {  // (the bounds are even: a pair is open or closed as a whole)
+        xin[rnd][j] = *reinterpret_cast<const float2*>(src + fi);
+        if (gsrc) gin[rnd][j] = *reinterpret_cast<const float2*>(gsrc + fi);
       }
     }
   }
@@ -94,19 +101,19 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
     float2 v[16];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const int64_t g = f0 + 2 * (t + T * j);
-      const bool open0 = g >= job.gate_lo && g < job.gate_hi, open1 = g + 1 >= job.gate_lo && g + 1 < job.gate_hi;
-      float a0 = open0 ? __fmul_rn(xin[rnd][j].x, gin[rnd][j].x) : 0.f;
-      float a1 = open1 ? __fmul_rn(xin[rnd][j].y, gin[rnd][j].y) : 0.f;
+      const int fi = 2 * (t + T * j);
+      const bool open = fi >= lo_b[rnd] && fi < hi_b[rnd];
+      float a0 = open ? __fmul_rn(xin[rnd][j].x, gin[rnd][j].x) : 0.f;
+      float a1 = open ? __fmul_rn(xin[rnd][j].y, gin[rnd][j].y) : 0.f;
       if (job.in2) {
         float2 y = make_float2(0.f, 0.f);
-        if (g + 1 < job.n_valid && g >= job.gate_lo && g < job.gate_hi) y = *reinterpret_cast<const float2*>(job.in2 + g);
-        const float c0 = open0 ? __fmul_rn(y.x, gin[rnd][j].x) : 0.f;
-        const float c1 = open1 ? __fmul_rn(y.y, gin[rnd][j].y) : 0.f;
+        if (open) y = *reinterpret_cast<const float2*>(job.in2 + f0 + fi);
+        const float c0 = open ? __fmul_rn(y.x, gin[rnd][j].x) : 0.f;
+        const float c1 = open ? __fmul_rn(y.y, gin[rnd][j].y) : 0.f;
         a0 = __fmul_rn(__fadd_rn(a0, c0), job.mix_scale);
         a1 = __fmul_rn(__fadd_rn(a1, c1), job.mix_scale);
       }
-      v[j] = make_float2(a0 * sc, a1 * sc);
+      v[j] = job.scale ? make_float2(a0 * sc, a1 * sc) : make_float2(a0, a1);
       v[j + 8] = make_float2(0.f, 0.f);
     }
     r16::fwd_a<H>(v, zg, tab, t);
@@ -141,9 +148,15 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
     __syncwarp();
   }
   __syncthreads();
-  for (int idx = tid; idx < (H + 1) * COLS; idx += NTHR) {
-    const int row = idx / COLS, c = idx % COLS;
-    if (b0 + c < job.n_blocks) job.out[(int64_t)row * ts + b0 + c] = tileT[row * LD + c];
+  {
+    // a thread stores column c of rows r0, r0 + NTHR / COLS, ...: every warp-wide store is one COLS * 8-byte run of an XT row
+    constexpr int RSTEP = NTHR / COLS;
+    const int c = tid % COLS;
+    if (b0 + c < job.n_blocks) {
+      float2* __restrict__ dst = job.out + b0 + c;
+#pragma unroll 8
+      for (int row = tid / COLS; row <= H; row += RSTEP) dst[(int64_t)row * ts] = tileT[row * LD + c];
+    }
   }
 }
 

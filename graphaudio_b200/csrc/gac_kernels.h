@@ -342,5 +342,13 @@ void launch_interleave(const float* c0, const float* c1, float* out, int64_t n_f
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
 // d_dst <- h_src (page-locked, 16-byte aligned, bytes a multiple of 16) by a copy kernel instead of the DMA engine
 void launch_copy_from_host(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s);
+constexpr int kCopySegs = 24;
+struct CopySegments {
+  void* dst[kCopySegs];
+  const void* src[kCopySegs];
+  size_t n16[kCopySegs];  // 16-byte units
+  int n = 0;
+};
+void launch_copy_from_host_multi(const CopySegments& segs, cudaStream_t s);
 
 }  // namespace gac

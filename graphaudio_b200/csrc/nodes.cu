@@ -11,6 +11,7 @@
 //   mix k_mix                         AudioNodeInput.Pull/MixBuffer (AudioNodeInput.cs:100-138,182-244)
 //   K0  k_ir_scale                    PartitionedConvolver.CalculateNormalizationScale (PartitionedConvolver.cs:93-102)
 #include <math_constants.h>
+#include <algorithm>
 #include <cstdint>
 
 #include "gac_kernels.h"
@@ -764,6 +765,23 @@ void launch_copy_from_host(void* d_dst, const void* h_src, size_t bytes, cudaStr
   const size_t n16 = bytes / 16;
   if (n16 == 0) return;
   k_copy_from_host<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(d_dst), reinterpret_cast<const uint4*>(h_src), n16);
+}
+// several such tables with ONE launch (the segments travel as a kernel argument): a render uploads a few dozen job tables, and a
+// launch per table cost more than the copies
+__global__ void __launch_bounds__(256) k_copy_from_host_multi(const __grid_constant__ CopySegments segs) {
+  const int g = blockIdx.y;
+  const size_t n16 = segs.n16[g];
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(segs.src[g]);
+  uint4* __restrict__ dst = reinterpret_cast<uint4*>(segs.dst[g]);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+}
+void launch_copy_from_host_multi(const CopySegments& segs, cudaStream_t s) {
+  if (segs.n <= 0) return;
+  size_t mx = 0;
+  for (int g = 0; g < segs.n; g++) mx = segs.n16[g] > mx ? segs.n16[g] : mx;
+  if (mx == 0) return;
+  const unsigned bx = (unsigned)std::min<size_t>((mx + 255) / 256, 64);
+  k_copy_from_host_multi<<<dim3(bx, (unsigned)segs.n), 256, 0, s>>>(segs);
 }
 
 // interleaved file samples -> planar float32 rows, the conversion libsndfile's sf_readf_float applies (normalised floats:

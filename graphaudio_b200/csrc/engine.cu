@@ -2289,7 +2289,9 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
             it.inv[1] = {1, -1, out1, nullptr};
             s.ch = 2;
             // fan-in fusion: this convolver ends its chain and its only consumer is a plain fan-in
-            if (ctx->fuse_fanin && s.sum_key >= 0 && eps.size() == 1 && pos + 1 == s.ops->size() && it.M2 > 0 && it.mac[0].H2 && it.mac[1].H2)
+            // (k_fft2_sum16 exists for the radix-16 plans: impulse responses that need 8192-point segments keep the plain path)
+            if (ctx->fuse_fanin && s.sum_key >= 0 && eps.size() == 1 && pos + 1 == s.ops->size() && it.M2 > 0 && it.M2 <= fft2_r16_max() && it.mac[0].H2 &&
+                it.mac[1].H2)
               it.sum_key = s.sum_key;
           } else {
             // true stereo (ConvolverNode.cs:127-144): L = c0(inL) + c2(inR), R = c1(inL) + c3(inR); X spectra shared

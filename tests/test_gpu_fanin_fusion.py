@@ -166,3 +166,18 @@ def test_chunked_render_calls_with_fusion_equal_one_call():
     assert np.abs(y1 - y2).max() <= 2e-6
     c1.Dispose()
     c2.Dispose()
+
+
+def test_impulse_responses_beyond_the_radix16_plans_stay_unfused():
+    """P = 2100 partitions need 8192-point second-level segments (radix-8 plan): no k_fft2_sum16 instantiation, the voices keep
+    one inverse transform each and still meet the oracle."""
+    G, O = _apis()
+    n = 128 * 2300
+    voices = _voices(2, 128 * 300, 128 * 2100 - 17, seed=90)
+    cf = synth.build_c2(G, FS, voices, 0.5, t_scale=0.05)
+    yf = cf.Render(n)
+    yo = synth.build_c2(O, FS, voices, 0.5, t_scale=0.05).Render(n)
+    assert cf.last_stats["mac_variant_used"] == 3 and cf.last_stats["fanin_groups"] == 0
+    assert np.abs(yo).max() > 1e-2
+    assert np.abs(yf - yo).max() <= TOL
+    cf.Dispose()

@@ -552,10 +552,15 @@ void biquad_scratch_sizes(int n_jobs, int64_t n_frames, size_t* n_float2, size_t
 }
 
 static int warm_slabs();
-int biquad_shared_segments(int n_groups, int64_t n_frames, int* seg_chunks_out) {
+// warm-up of the shared path in chunks: the caller's hint (32-frame slabs; 0 = none) unless GAC_BIQUAD_WARM_SLABS forces a value
+static int shared_warm_chunks(int warm_hint_slabs) {
+  const int slabs = (warm_hint_slabs > 0 && !getenv("GAC_BIQUAD_WARM_SLABS")) ? warm_hint_slabs : warm_slabs();
+  return std::max(2, slabs / (kChunk / 32));
+}
+int biquad_shared_segments(int n_groups, int64_t n_frames, int* seg_chunks_out, int warm_hint_slabs) {
   const int groups = n_groups;
   const int total_chunks = (int)((n_frames + kChunk - 1) / kChunk);
-  const int warm = std::max(2, warm_slabs() / (kChunk / 32));
+  const int warm = shared_warm_chunks(warm_hint_slabs);
   int n_seg = kShSlots / (groups > 0 ? groups : 1);
   if (n_seg < 1) n_seg = 1;
   int seg_chunks = (total_chunks + n_seg - 1) / n_seg;
@@ -565,14 +570,14 @@ int biquad_shared_segments(int n_groups, int64_t n_frames, int* seg_chunks_out) 
   if (seg_chunks_out) *seg_chunks_out = seg_chunks;
   return n_seg;
 }
-void biquad_shared_scratch_sizes(int n_groups, int64_t n_frames, size_t* n_float2, size_t* n_int) {
+void biquad_shared_scratch_sizes(int n_groups, int64_t n_frames, size_t* n_float2, size_t* n_int, int warm_hint_slabs) {
   const size_t groups = (size_t)n_groups;
-  const int n_seg = biquad_shared_segments(n_groups, n_frames, nullptr);
+  const int n_seg = biquad_shared_segments(n_groups, n_frames, nullptr, warm_hint_slabs);
   *n_float2 = groups * (size_t)n_seg * 64 + groups * (size_t)(n_frames / kSlab + 4) * 32;
   *n_int = groups + groups * (size_t)n_seg;
 }
 void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups, int n_groups, const unsigned char* d_cs, size_t cs_stride,
-                                int64_t n_frames, float2* d_states, int* d_flags, bool sequential, cudaStream_t s) {
+                                int64_t n_frames, float2* d_states, int* d_flags, bool sequential, cudaStream_t s, int warm_hint_slabs) {
   if (n_groups <= 0) return;
   if (sequential) {
     // filters that forget too slowly for speculative segments to re-join (constant low cutoff / high Q): one segment per group from
@@ -587,8 +592,8 @@ void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups
   GAC_SMEM_OPT_IN((k_biquad_lanes_shared<true>), kShSmem);
   const unsigned groups = (unsigned)n_groups;
   int seg_chunks = 0;
-  const int n_seg = biquad_shared_segments(n_groups, n_frames, &seg_chunks);
-  const int warm = std::max(2, warm_slabs() / (kChunk / 32));
+  const int n_seg = biquad_shared_segments(n_groups, n_frames, &seg_chunks, warm_hint_slabs);
+  const int warm = shared_warm_chunks(warm_hint_slabs);
   float2* d_slab = d_states + (size_t)groups * n_seg * 64;
   int* d_first_bad = d_flags;
   int* d_link = d_flags + groups;

@@ -2065,6 +2065,45 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         const double frames = 16.6 / (-0.5 * std::log(a2));
         return frames > 400.0;
       };
+      // Warm-up of the speculative segments (32-frame slabs): a filter whose poles stay well inside the unit circle over the whole
+      // automation forgets its state within a few hundred frames, so 8192 frames of warm-up per segment would double the recursion's
+      // work for nothing.  Pole radius^2 = a2 = (1 - alpha) / (1 + alpha), alpha = sin(w0) / (2 Q) (divided by the shelf / peaking
+      // amplitude in the worst case); the bound is taken over the values the parameters can reach (static value, event values and
+      // targets: ramps stay between their end points).  Modulated parameters keep the default.  Only speed depends on this: every
+      // segment is verified bit for bit and repaired where it did not re-join.
+      auto warm_slabs_of = [&](const OpH& op) -> int {
+        auto range = [](const ParamH& p, double& lo, double& hi) {
+          if (p.mod_bus >= 0) return false;
+          lo = hi = p.value;
+          auto take = [&](const std::vector<gac_event>& ev) {
+            for (const gac_event& e : ev) {
+              const double v = e.type == 3 ? e.target : e.value;
+              lo = std::min(lo, v);
+              hi = std::max(hi, v);
+            }
+          };
+          take(p.ev);
+          for (const auto& ep : p.later) {
+            lo = std::min(lo, (double)ep.value);
+            hi = std::max(hi, (double)ep.value);
+            take(ep.ev);
+          }
+          return true;
+        };
+        double f0, f1, q0, q1, g0, g1;
+        if (!range(op.p0, f0, f1) || !range(op.p1, q0, q1) || !range(op.p2, g0, g1)) return 0;
+        const double nyq = ctx->fs / 2.0, pi = 3.14159265358979323846;
+        f0 = std::min(std::max(f0, 1.0), nyq);
+        f1 = std::min(std::max(f1, 1.0), nyq);
+        const double smin = std::min(std::sin(2.0 * pi * f0 / ctx->fs), std::sin(2.0 * pi * f1 / ctx->fs));  // (sin is concave on [0, pi])
+        const double amp = std::pow(10.0, std::max(std::fabs(g0), std::fabs(g1)) / 40.0);
+        const double alpha = smin / (2.0 * std::max(q1, 0.001)) / amp;
+        const double a2 = (1.0 - alpha) / (1.0 + alpha);
+        if (!(alpha > 0.0) || !(a2 > 0.0)) return alpha >= 1.0 ? 32 : 0;
+        const double frames = 16.6 / (-0.5 * std::log(a2));  // the state decays by 2^-24
+        return frames <= 128.0 ? 32 : frames <= 400.0 ? 128 : 0;
+      };
+      int warm_hint = -1;  // the longest warm-up any speculative class asks for (0 = the default)
       for (auto& kv : classes) {
         if (kv.second.size() < kSharedMin) {
           general.insert(general.end(), kv.second.begin(), kv.second.end());
@@ -2073,6 +2112,10 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         const int cls = (int)reps.size();
         reps.push_back(all[kv.second[0]]);
         const bool slow = forgets_slowly(all[kv.second[0]]) && !getenv("GAC_BIQUAD_SPECULATE");
+        if (!slow) {
+          const int w = warm_slabs_of((*sigs[biquads[kv.second[0]]].ops)[pos]);
+          warm_hint = warm_hint < 0 ? w : (w == 0 || warm_hint == 0 ? 0 : std::max(warm_hint, w));
+        }
         for (size_t m0 = 0; m0 < kv.second.size(); m0 += 16) {
           const size_t cnt = std::min<size_t>(16, kv.second.size() - m0);
           (slow ? slow_groups : groups).push_back(BqGroup{(int)sj.size(), (int)cnt, cls});
@@ -2100,7 +2143,8 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         if ((rc = env.scratch->upload(&dgroups, groups))) return rc;
         const int n_slow_groups = n_groups - n_spec_groups;
         size_t n_f2 = 0, n_i = 0, n_f2s = 0, n_is = 0;
-        biquad_shared_scratch_sizes(std::max(1, n_spec_groups), env.Npad, &n_f2, &n_i);
+        if (warm_hint < 0) warm_hint = 0;
+        biquad_shared_scratch_sizes(std::max(1, n_spec_groups), env.Npad, &n_f2, &n_i, warm_hint);
         biquad_shared_scratch_sizes(std::max(1, n_slow_groups), env.Npad, &n_f2s, &n_is);  // (an upper bound for the one-segment launch)
         float2 *dstates = nullptr, *dstates_slow = nullptr;
         int* dflags = nullptr;
@@ -2112,11 +2156,11 @@ static int run_chains(RenderEnv& env, std::vector<Sig>& sigs) {
         bool partial = false;
         for (const BiquadJob& j : sj) partial = partial || j.lo > 0 || j.hi < env.Npad;
         if (partial) launch_biquad_zero_outside(dsj, (int)sj.size(), env.Npad, kstream(ctx));
-        launch_biquad_lanes_shared(dsj, dgroups, n_spec_groups, dcs, cs_stride, env.Npad, dstates, dflags, false, kstream(ctx));
+        launch_biquad_lanes_shared(dsj, dgroups, n_spec_groups, dcs, cs_stride, env.Npad, dstates, dflags, false, kstream(ctx), warm_hint);
         launch_biquad_lanes_shared(dsj, dgroups + n_spec_groups, n_slow_groups, dcs, cs_stride, env.Npad, dstates_slow, nullptr, true, kstream(ctx));
         env.timer->end(t);
         env.launches += 3 + (partial ? 1 : 0) + (n_slow_groups > 0 ? 1 : 0) +
-                        (n_spec_groups > 0 ? 1 + (biquad_shared_segments(n_spec_groups, env.Npad, nullptr) > 1 ? 2 : 0) : 0);
+                        (n_spec_groups > 0 ? 1 + (biquad_shared_segments(n_spec_groups, env.Npad, nullptr, warm_hint) > 1 ? 2 : 0) : 0);
         CU(cudaGetLastError());
         TRACE_MARK("biquad (shared coefficients): queued");
       }

@@ -293,11 +293,13 @@ void launch_biquad_zero_outside(const BiquadJob* d_jobs, int n_jobs, int64_t n_f
 struct BqGroup {
   int first, count, cls;  // jobs [first, first + count) of the job array, class stream index
 };
-int biquad_shared_segments(int n_groups, int64_t n_frames, int* seg_chunks);
-void biquad_shared_scratch_sizes(int n_groups, int64_t n_frames, size_t* n_float2, size_t* n_int);
+// warm_hint_slabs: warm-up of a speculative segment in 32-frame slabs (0 = the default of 256 = 8192 frames); the same value must be
+// passed to all three.  Whatever the warm-up, the result is verified bit for bit and repaired where a segment did not re-join.
+int biquad_shared_segments(int n_groups, int64_t n_frames, int* seg_chunks, int warm_hint_slabs = 0);
+void biquad_shared_scratch_sizes(int n_groups, int64_t n_frames, size_t* n_float2, size_t* n_int, int warm_hint_slabs = 0);
 // sequential: one segment per group (filters known to forget too slowly for the speculative segments); scratch sized the same way
 void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups, int n_groups, const unsigned char* d_cs, size_t cs_stride,
-                                int64_t n_frames, float2* d_states, int* d_flags, bool sequential, cudaStream_t s);
+                                int64_t n_frames, float2* d_states, int* d_flags, bool sequential, cudaStream_t s, int warm_hint_slabs = 0);
 
 // K3d alone (biquad_lanes.cu): the recursion over the slab-transposed streams, TMA-fed
 void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, const float4* d_s1t, const float4* d_s2t, float2* d_states,

@@ -31,18 +31,21 @@ internal struct GacEvent
 }
 
 [StructLayout(LayoutKind.Sequential)]
-internal unsafe struct GacParam
+internal unsafe struct GacParam   // gac_param (ABI v6+): 32 bytes
 {
     public float Value;
     public int EventCount;
     public GacEvent* Events;
+    public int ModBus;            // 0 = no modulation input; k > 0: the fan-in is bus k-1 (GAC_BUS_MONO_INPUT) — AudioNode.Connect(AudioParam)
+    public float MinValue, MaxValue;
+    public int Reserved;
 }
 
 [StructLayout(LayoutKind.Sequential)]
 internal unsafe struct GacOpDesc
 {
-    public int Kind;        // 1 biquad, 2 gain, 3 convolver, 4 delay, 5 stereo panner
-    public int FilterType;  // (int)FilterType
+    public int Kind;        // 1 biquad, 2 gain, 3 convolver, 4 delay, 5 stereo panner, 6 splitter channel, 7 connection gate
+    public int FilterType;  // (int)FilterType; gate: 0 from / 1 until quantum Aux; convolver: 1 = later epoch of the preceding convolver op
     public GacParam P0, P1, P2;
     public IntPtr Ir;
     public double Aux;      // delay: maxDelayTime (seconds)
@@ -59,8 +62,11 @@ internal unsafe struct GacVoiceDesc
     public int Bus;
     public int Input;   // 0 = fed by Source; k > 0 = fed by the output of bus k-1
     public int Loop;    // AudioBufferSourceNode.Loop (rate 1 only)
-    public int Reserved;
+    public int SourceKind;              // 0 buffer, 1 ConstantSourceNode, 2 OscillatorNode
     public double LoopStart, LoopEnd;   // seconds; LoopEnd 0 = end of the buffer
+    public GacParam SourceParam;        // constant: Offset; oscillator: Frequency
+    public int OscillatorType;          // 0 sine, 1 square, 2 sawtooth, 3 triangle
+    public int Reserved;
 }
 
 [StructLayout(LayoutKind.Sequential)]
@@ -71,6 +77,9 @@ internal unsafe struct GacBusDesc
     public int Target;      // 0 = destination, k > 0 = input of bus k-1, -1 = only read by bus-fed chains
     public int InputCount;  // connection order at the fan-in (entries >= 0: bus indices, < 0: ~voice index); 0 / null = default
     public int* Inputs;
+    public int Flags;       // GAC_BUS_MONO_INPUT = 1: the fan-in of an AudioParam (one channel)
+    public int Reserved;
+    public int* InputSlots; // ChannelMergerNode: per input 0 ordinary, 1 / 2 = merger input 0 / 1; null = all ordinary
 }
 
 [StructLayout(LayoutKind.Sequential)]
@@ -87,6 +96,10 @@ internal unsafe struct GacGraphDesc
 internal static unsafe partial class Native
 {
     private const string Lib = "graphaudio_cuda";
+    internal const int AbiVersion = 7;                 // GAC_ABI_VERSION this binding was written against (checked once at start-up)
+    internal const int FlagAsyncUpload = 1;            // GAC_FLAG_ASYNC_UPLOAD
+    internal const int FlagUniformSegments = 2;        // GAC_FLAG_UNIFORM_SEGMENTS
+    internal const int FlagNoFaninFusion = 4;          // GAC_FLAG_NO_FANIN_FUSION: one inverse transform and one fan-in input per ConvolverNode
 
     [LibraryImport(Lib, EntryPoint = "gac_version")]
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
@@ -176,6 +189,28 @@ internal static unsafe partial class Native
     [LibraryImport(Lib, EntryPoint = "gac_render_batch")]
     [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
     internal static partial int RenderBatch(IntPtr ctx, IntPtr* graphs, int graphCount, long frames, float** outChannels, int channelCount);
+
+    // ---- one process, several GPUs (gac_group: a member context per device, ncclCommInitAll, one ncclReduce of the bus)
+    [LibraryImport(Lib, EntryPoint = "gac_group_create")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int GroupCreate(GacContextDesc* desc, int* deviceIds, int deviceCount, out IntPtr group);
+
+    [LibraryImport(Lib, EntryPoint = "gac_group_destroy")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int GroupDestroy(IntPtr group);
+
+    [LibraryImport(Lib, EntryPoint = "gac_group_size")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int GroupSize(IntPtr group, out int members);
+
+    [LibraryImport(Lib, EntryPoint = "gac_group_context")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int GroupContext(IntPtr group, int index, out IntPtr member);
+
+    /// <summary>shards[i] belongs to member i (voices sharded contiguously, the bus described on every member).</summary>
+    [LibraryImport(Lib, EntryPoint = "gac_group_render")]
+    [UnmanagedCallConv(CallConvs = new[] { typeof(CallConvCdecl) })]
+    internal static partial int GroupRender(IntPtr group, IntPtr* shards, long firstFrame, long frames, float** outChannels, int channelCount, long startIndex);
 
     internal static string LastError() => Marshal.PtrToStringUTF8(LastErrorPtr()) ?? string.Empty;
 

@@ -129,21 +129,28 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
 #pragma unroll
     for (int q = 0; q < 16; q++) zg[G::slot_k(t, q)] = u[q];  // natural order Z[k]
     __syncwarp();
-    // split step: E = (Z[k] + conj Z[H-k]) / 2 ; O = (Z[k] - conj Z[H-k]) / (2i) ; X[k] = E + e^{-2 pi i k / 2H} O
+    // split step: E = (Z[k] + conj Z[H-k]) / 2 ; O = (Z[k] - conj Z[H-k]) / (2i) ; X[k] = E + w_k O, w_k = e^{-2 pi i k / 2H}.
+    // Bins k and H - k come from the same pair: E[H-k] = conj E[k], O[H-k] = conj O[k], w_{H-k} = -conj w_k, so
+    // X[H-k] = conj(E - w_k O): one complex product and two shared-memory reads for two bins.
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const int k = t + T * j;
+    for (int j = 0; j < 8; j++) {
+      const int k = t + T * j;  // 0 .. H/2 - 1
       const float2 a = zg[k];
-      const float2 c = zg[(H - k) & (H - 1)];
       if (k == 0) {
         tileT[bl] = make_float2(a.x + a.y, 0.f);           // row 0: DC
         tileT[H * LD + bl] = make_float2(a.x - a.y, 0.f);  // row H: Nyquist
       } else {
+        const float2 c = zg[H - k];
         const float2 e = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
         const float2 o = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));
         const float2 wo = cmul1(tw[k], o);
         tileT[k * LD + bl] = make_float2(e.x + wo.x, e.y + wo.y);
+        tileT[(H - k) * LD + bl] = make_float2(e.x - wo.x, -(e.y - wo.y));
       }
+    }
+    if (t == 0) {  // k = H/2 pairs with itself: E = (Re Z, 0), O = (Im Z, 0), w = -i
+      const float2 a = zg[H / 2];
+      tileT[(H / 2) * LD + bl] = make_float2(a.x, -a.y);
     }
     __syncwarp();
   }

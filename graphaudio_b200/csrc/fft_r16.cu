@@ -8,6 +8,8 @@
 // Same arithmetic contract as fft.cu: Forward == numpy.fft.rfft of the zero-padded 256-frame block, Inverse == irfft +
 // overlap-add (FftFlat/RealFourierTransform.cs:62-131, PartitionedConvolver.cs:106-124 and :134-150), float32.
 // Both kernels work on the TRANSPOSED spectrograms of fft2.cu (row k = 0..128 of XT / YT, block time contiguous).
+#include <cstdlib>
+
 #include "fft2_core.cuh"
 #include "gac_kernels.h"
 
@@ -15,6 +17,7 @@ namespace gac {
 
 namespace {
 constexpr int NTHR = 128;         // threads per CTA
+constexpr int K5_DEFAULT_ROUNDS = 1;
 
 __device__ __forceinline__ float2 cmul1(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cmulc1(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
@@ -51,14 +54,30 @@ struct Geo {
 // K5: COLS consecutive blocks of one channel -> H+1 rows x COLS columns of XT.
 // tab = radix-16 twiddle table of M = H; tw = split twiddles e^{-2 pi i k / (2H)}, k < H.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int H>
-__global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const FftFwdJob* __restrict__ jobs, const float2* __restrict__ tab,
-                                                                        const float2* __restrict__ tw, int64_t ts) {
+// R = rounds per CTA (transforms per thread group): 2 -> COLS = 2 GROUPS columns and 256-byte runs of XT per tile row; 1 -> half the
+// tile, half the prefetch registers, more CTAs per SM (H = 128: 37 KB and <= 96 registers: 5 CTAs instead of 4).
+template <int H, int R>
+struct GeoF {
   using G = Geo<H>;
-  constexpr int T = G::T, LD = G::LD, COLS = G::COLS;
+  static constexpr int COLS = R * G::GROUPS;
+  static constexpr int LD = COLS + 1;
+  static constexpr int TILE = ((H + 1) * LD + 1) & ~1;
+  __device__ __forceinline__ static int tile_col(int tid, int rnd) {
+    if (R == 2) return G::tile_col(tid, rnd);
+    // one column per group; H = 128: the two groups of a half-warp take columns m and m + 8 (16 different bank pairs per access)
+    if (H == 128) return ((tid >> 3) >> 1) + 8 * ((tid >> 3) & 1);
+    return tid / G::T;
+  }
+};
+template <int H, int R>
+__global__ void __launch_bounds__(NTHR, (H == 128 ? (R == 1 ? 6 : 4) : 3)) k_rfft_fwd_t8(const FftFwdJob* __restrict__ jobs, const float2* __restrict__ tab,
+                                                                                       const float2* __restrict__ tw, int64_t ts) {
+  using G = Geo<H>;
+  using F = GeoF<H, R>;
+  constexpr int T = G::T, LD = F::LD, COLS = F::COLS;
   extern __shared__ __align__(16) float2 smem[];
   float2* tileT = smem;            // [H + 1][LD]
-  float2* zb = smem + G::TILE;     // [GROUPS][ZS]
+  float2* zb = smem + F::TILE;     // [GROUPS][ZS]
   const FftFwdJob job = jobs[blockIdx.y];
   const int tid = threadIdx.x;
   const float sc = job.scale ? *job.scale : 1.0f;
@@ -71,11 +90,11 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
   // Gate: frames outside the non-silent range [gate_lo, gate_hi) read as zero and are NOT loaded (`in` may alias a source buffer
   // that only covers that range).  The bounds are multiples of 128 and n_valid is a multiple of the partition size on this path,
   // so the test is made once per block: [lo_b, hi_b) = the open frames of the block, relative to its first frame.
-  float2 xin[2][8], gin[2][8];
-  int lo_b[2], hi_b[2];
+  float2 xin[R][8], gin[R][8];
+  int lo_b[R], hi_b[R];
 #pragma unroll
-  for (int rnd = 0; rnd < 2; rnd++) {
-    const int64_t f0 = (b0 + G::tile_col(tid, rnd)) * H;
+  for (int rnd = 0; rnd < R; rnd++) {
+    const int64_t f0 = (b0 + F::tile_col(tid, rnd)) * H;
     const int64_t lo = job.gate_lo - f0, hi = (job.gate_hi < job.n_valid ? job.gate_hi : job.n_valid) - f0;
     lo_b[rnd] = lo < 0 ? 0 : (lo > H ? H : (int)lo);
     hi_b[rnd] = hi < 0 ? 0 : (hi > H ? H : (int)hi);
@@ -93,8 +112,8 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? 4 : 3)) k_rfft_fwd_t8(const 
     }
   }
 #pragma unroll
-  for (int rnd = 0; rnd < 2; rnd++) {
-    const int bl = G::tile_col(tid, rnd);
+  for (int rnd = 0; rnd < R; rnd++) {
+    const int bl = F::tile_col(tid, rnd);
     const int64_t f0 = (b0 + bl) * H;
     // fused GainNode multiply (Nodes/GainNode.cs:49-58), silent-quantum gate, stereo -> mono down-mix (AudioNodeInput.cs:214-228),
     // IR scale; the zero-padded upper half of the block (PartitionedConvolver.cs:107) gives z[n >= H/2] = 0
@@ -306,16 +325,31 @@ __global__ void __launch_bounds__(NTHR) k_irfft_ola_t8(const FftInvJob* __restri
   }
 }
 
-template <int H>
-static void fwd_launch(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
+template <int H, int R>
+static void fwd_launch_r(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
   using G = Geo<H>;
-  constexpr size_t smem = sizeof(float2) * (size_t)(G::TILE + G::GROUPS * G::ZS);
-  GAC_SMEM_OPT_IN(k_rfft_fwd_t8<H>, smem);
+  using F = GeoF<H, R>;
+  constexpr size_t smem = sizeof(float2) * (size_t)(F::TILE + G::GROUPS * G::ZS);
+  GAC_SMEM_OPT_IN((k_rfft_fwd_t8<H, R>), smem);
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
-    dim3 grid((unsigned)((max_blocks + G::COLS - 1) / G::COLS), (unsigned)nj);
-    k_rfft_fwd_t8<H><<<grid, NTHR, smem, s>>>(d_jobs + j0, d_tab, d_tw, t_stride);
+    dim3 grid((unsigned)((max_blocks + F::COLS - 1) / F::COLS), (unsigned)nj);
+    k_rfft_fwd_t8<H, R><<<grid, NTHR, smem, s>>>(d_jobs + j0, d_tab, d_tw, t_stride);
   }
+}
+// rounds per CTA of the 128-frame K5: 1 by default (72 registers, 37 KB: 6 CTAs per SM; measured 0.50 vs 0.52 ms on the C3 shard);
+// GAC_K5_ROUNDS=2 for A/B measurements
+static int k5_rounds() {
+  static const int v = [] {
+    const char* e = getenv("GAC_K5_ROUNDS");
+    return e && atoi(e) == 1 ? 1 : (e && atoi(e) == 2 ? 2 : K5_DEFAULT_ROUNDS);
+  }();
+  return v;
+}
+template <int H>
+static void fwd_launch(const FftFwdJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {
+  if (H == 128 && k5_rounds() == 1) fwd_launch_r<128, 1>(d_jobs, n_jobs, max_blocks, t_stride, d_tab, d_tw, s);
+  else fwd_launch_r<H, 2>(d_jobs, n_jobs, max_blocks, t_stride, d_tab, d_tw, s);
 }
 template <int H>
 static void inv_launch(const FftInvJob* d_jobs, int n_jobs, int64_t max_blocks, int64_t t_stride, const float2* d_tab, const float2* d_tw, cudaStream_t s) {

@@ -61,7 +61,7 @@ internal unsafe struct GacVoiceDesc
     public GacOpDesc* Ops;
     public int Bus;
     public int Input;   // 0 = fed by Source; k > 0 = fed by the output of bus k-1
-    public int Loop;    // AudioBufferSourceNode.Loop (rate 1 only)
+    public int Loop;    // AudioBufferSourceNode.Loop (any effective rate)
     public int SourceKind;              // 0 buffer, 1 ConstantSourceNode, 2 OscillatorNode
     public double LoopStart, LoopEnd;   // seconds; LoopEnd 0 = end of the buffer
     public GacParam SourceParam;        // constant: Offset; oscillator: Frequency

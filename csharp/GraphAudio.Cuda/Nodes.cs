@@ -170,7 +170,7 @@ public sealed class AudioBufferSourceNode : AudioNode   // Nodes/AudioBufferSour
     public AudioBufferSourceNode(OfflineAudioContext c) : base(c) { }
     public AudioParam PlaybackRate { get; } = new(1.0f, 0.001f, 1000.0f);   // :76 (k-rate)
     public PlayableAudioBuffer? Buffer { get; set; }                          // :67-71
-    public bool Loop { get; set; }                                            // :40-44 (accelerated at playback rate 1)
+    public bool Loop { get; set; }                                            // :40-44 (any effective rate)
     private double _loopStart, _loopEnd;
     public double LoopStart { get => _loopStart; set => _loopStart = Math.Max(0, value); }   // :49-53
     public double LoopEnd { get => _loopEnd; set => _loopEnd = Math.Max(0, value); }         // :58-62

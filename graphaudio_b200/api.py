@@ -365,7 +365,7 @@ class AudioBufferSourceNode(AudioNode):
         super().__init__(context, 0, 1)
         self.PlaybackRate = AudioParam(1.0, 0.001, 1000.0)  # k-rate, Nodes/AudioBufferSourceNode.cs:76
         self._buffer: Optional[PlayableAudioBuffer] = None
-        self.Loop = False            # :40-44 (accelerated at playback rate 1; the looping resampler path raises NotSupportedException)
+        self.Loop = False            # :40-44 (rate 1: in-place wrap; any other effective rate: the wrap-buffer resampler path :236-358)
         self._loop_start = 0.0
         self._loop_end = 0.0
         self._started = False

@@ -98,10 +98,12 @@ struct NcclApi;
 struct ResampleTable {
   std::vector<int32_t> k;
   std::vector<float> t;
+  std::vector<int32_t> x;  // looping sources: windows that straddle the loop seam, four source frame indices each (ResampleJob::x)
   int64_t n_active_blocks = 0;
   int64_t n_zero_from = 0;
   int32_t* d_k = nullptr;
   float* d_t = nullptr;
+  int32_t* d_x = nullptr;
 };
 
 constexpr size_t kResampleCacheMax = 16;  // distinct source geometries whose phase tables a context keeps
@@ -136,7 +138,7 @@ struct gac_context {
   // response prepares it together with all the others its voice batch needs (three launches per batch instead of three per
   // IR; a render never queues behind the preparation of an impulse response whose upload is still in flight)
   std::vector<cudaEvent_t> event_pool;  // recycled `ready` events (creating one costs a driver call per buffer)
-  std::map<std::tuple<double, int64_t, int64_t, int64_t>, std::shared_ptr<ResampleTable>> resample_cache;
+  std::map<std::tuple<double, int64_t, int64_t, int64_t, int64_t>, std::shared_ptr<ResampleTable>> resample_cache;  // last: loop start, -1 = no loop
   // page-locked staging for the small job tables of a render: they reach the device through a copy KERNEL (SM loads over
   // PCIe), not through the DMA engine, whose queue may hold hundreds of megabytes of asynchronous buffer uploads — a
   // cudaMemcpyAsync of a 2 KB table would wait behind all of them, and with it every kernel of the render
@@ -622,6 +624,7 @@ extern "C" int gac_context_destroy(gac_context* ctx) {
   for (auto& kv : ctx->resample_cache) {
     if (kv.second->d_k) cudaFreeAsync(kv.second->d_k, ctx->stream);
     if (kv.second->d_t) cudaFreeAsync(kv.second->d_t, ctx->stream);
+    if (kv.second->d_x) cudaFreeAsync(kv.second->d_x, ctx->stream);
   }
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) {

@@ -5,7 +5,7 @@
 // ------------------------------------------------------------------------------------------ source stage (K1)
 // (struct ResampleTable lives in engine.cu: the tables are cached in the context across renders)
 
-// Nodes/AudioBufferSourceNode.cs:131-376, non-loop paths.  Decides, on the host, which quanta the source emits
+// Nodes/AudioBufferSourceNode.cs:131-376, all four paths (rate 1 / CubicResampler, with and without Loop).  Decides, on the host, which quanta the source emits
 // (block-granular start/stop :137-143; final block dropped :360-368) and, for the CubicResampler path, replays
 // the data-independent phase recurrence of CubicResampler.cs:40-60 exactly (double Pos, (int)Pos consumes).
 static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices, std::vector<Sig>& sigs) {
@@ -26,13 +26,38 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
       for (auto& t : v) {
         if (t->d_k) cudaFreeAsync(t->d_k, ctx->stream);
         if (t->d_t) cudaFreeAsync(t->d_t, ctx->stream);
+        if (t->d_x) cudaFreeAsync(t->d_x, ctx->stream);
         t->d_k = nullptr;
         t->d_t = nullptr;
+        t->d_x = nullptr;
         keep->items.push_back(t);
       }
     }
   } evicted{ctx, env.keep, {}};
   const double inf = std::numeric_limits<double>::infinity();
+  auto make_room = [&]() {
+    if (tables.size() >= kResampleCacheMax) {
+      // bounded: drop everything.  Jobs already planned for THIS batch still point at the device tables, so the frees are
+      // queued behind launch_resample (`evicted`), never here.
+      for (auto& kv : tables) evicted.push_back(kv.second);
+      tables.clear();
+    }
+  };
+  // context-owned device copies (not render scratch): later renders of the same source geometry reuse them
+  auto upload_table = [&](ResampleTable& tab) -> int {
+    if (tab.k.empty()) return GAC_OK;
+    const size_t tb = (tab.k.size() * sizeof(int32_t) + 15) & ~(size_t)15;
+    CU(cudaMallocAsync(&tab.d_k, tb, ctx->stream));
+    CU(cudaMallocAsync(&tab.d_t, tb, ctx->stream));
+    int rc;
+    if ((rc = table_h2d(ctx, tab.d_k, tab.k.data(), tab.k.size() * sizeof(int32_t)))) return rc;
+    if ((rc = table_h2d(ctx, tab.d_t, tab.t.data(), tab.t.size() * sizeof(float)))) return rc;
+    if (!tab.x.empty()) {
+      CU(cudaMallocAsync(&tab.d_x, tab.x.size() * sizeof(int32_t), ctx->stream));
+      if ((rc = table_h2d(ctx, tab.d_x, tab.x.data(), tab.x.size() * sizeof(int32_t)))) return rc;
+    }
+    return GAC_OK;
+  };
 
   for (size_t i = 0; i < voices.size(); i++) {
     const VoiceH& v = *voices[i];
@@ -91,8 +116,117 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
       int64_t loopEnd = v.loop_end > 0 ? (int64_t)(v.loop_end * (double)buf->rate) : buf->n;
       loopEnd = std::min(loopEnd, buf->n);
       const int64_t loopStart = std::min((int64_t)(v.loop_start * (double)buf->rate), loopEnd);
-      if (eff != 1.0) return fail(GAC_ERR_UNSUPPORTED, "looping sources are accelerated at playback rate 1 only (the looping resampler path is SURVEY.md §8f-3)");
       if (loopEnd - loopStart <= 0) return fail(GAC_ERR_UNSUPPORTED, "looping source with an empty loop region");
+      if (eff != 1.0) {
+        // The CubicResampler path with _loop set (:236-358).  Every Process call is fed from the 512-float wrap buffer (:296-314:
+        // `pos + available` IS loopEndFrame, so the test against loopEndFrame - 4 always holds): the frames pos .. loopEnd-1 followed
+        // by ONE pass over the loop region, cut at min(128 - outIdx + 4, 512) entries.  Which buffer frames are shifted in, and the
+        // phase of every output, depend on positions only — so the block loop is replayed here with frame indices, and the device
+        // evaluates the float32 polynomial.  A window whose four frames are not consecutive (at a loop seam) goes to `x`; a frame the
+        // reference clears (a call that neither consumes nor produces, :334-338) is kResampleCleared; a quantum without any output
+        // ends the source (:360-368).
+        if (max_blocks == 0) {
+          cj.push_back(job);
+          continue;
+        }
+        const int64_t n_out_max = max_blocks * 128;
+        auto key = std::make_tuple(eff, pos, loopEnd, n_out_max, loopStart);
+        auto it = tables.find(key);
+        std::shared_ptr<ResampleTable> tab;
+        if (it != tables.end()) {
+          tab = it->second;
+        } else {
+          make_room();
+          tab = std::make_shared<ResampleTable>();
+          tab->k.reserve((size_t)n_out_max);
+          tab->t.reserve((size_t)n_out_max);
+          int64_t win[4] = {0, 0, 0, 0};
+          int ready = 0;
+          double Pos = 0.0;
+          int64_t position = pos, active = 0;
+          std::vector<int64_t> wrap;
+          wrap.reserve(512);
+          auto shift = [&](int64_t f) { win[0] = win[1]; win[1] = win[2]; win[2] = win[3]; win[3] = f; };
+          for (int64_t blk = 0; blk < max_blocks; blk++) {
+            int64_t p = position, consumedCh = 0;
+            int oi = 0;
+            bool more = false;
+            while (oi < 128) {
+              if (p >= loopEnd) p = loopStart;                                   // :265-268
+              const int64_t fromEnd = loopEnd - p;
+              const int64_t needed = std::min<int64_t>(128 - oi + 4, 512);       // :301
+              wrap.clear();
+              for (int64_t q = 0; q < fromEnd && (int64_t)wrap.size() < needed; q++) wrap.push_back(p + q);                        // :303-306
+              for (int64_t q = 0; (int64_t)wrap.size() < needed && q < loopEnd - loopStart; q++) wrap.push_back(loopStart + q);    // :308-311
+              const int64_t n_in = (int64_t)wrap.size();
+              int64_t ip = 0;
+              int op = 0;
+              while (ready < 4 && ip < n_in) {   // CubicResampler.cs:31-35
+                shift(wrap[ip++]);
+                ready++;
+              }
+              if (ready == 4) {
+                while (oi + op < 128) {          // :40-60
+                  const int consume = (int)Pos;
+                  if (ip + consume > n_in) break;
+                  for (int q = 0; q < consume; q++) shift(wrap[ip++]);
+                  Pos -= consume;
+                  if (win[1] == win[0] + 1 && win[2] == win[0] + 2 && win[3] == win[0] + 3) {
+                    tab->k.push_back((int32_t)win[0]);
+                  } else {
+                    tab->k.push_back(-(int32_t)(tab->x.size() / 4) - 1);
+                    for (int q = 0; q < 4; q++) tab->x.push_back((int32_t)win[q]);
+                  }
+                  tab->t.push_back((float)Pos);
+                  op++;
+                  Pos += eff;
+                }
+              }
+              more = more || op > 0;
+              int64_t np = p + ip;
+              if (np >= loopEnd) np = loopStart + (np - loopEnd);                                         // :323-328 (no modulo here)
+              consumedCh += (np >= p) ? (np - p) : (loopEnd - p + np - loopStart);                        // :330
+              p = np;
+              oi += op;
+              if (ip == 0 && op == 0) break;                                                              // :334-338
+            }
+            for (; oi < 128; oi++) {  // the cleared rest of the quantum
+              tab->k.push_back(kResampleCleared);
+              tab->t.push_back(0.f);
+            }
+            position += consumedCh;                                                                       // :347
+            if (position >= loopEnd) position = loopStart + (position - loopEnd) % (loopEnd - loopStart); // :349-357
+            if (!more) break;  // nothing produced: the quantum is cleared and the source ends (:360-368)
+            active = blk + 1;
+          }
+          tab->n_active_blocks = active;
+          tab->k.resize((size_t)(active * 128));
+          tab->t.resize(tab->k.size());
+          tab->n_zero_from = (int64_t)tab->k.size();
+          int rc = upload_table(*tab);
+          if (rc) return rc;
+          tables[key] = tab;
+        }
+        if (tab->n_active_blocks == 0) {
+          cj.push_back(job);
+          continue;
+        }
+        ResampleJob r{};
+        r.src[0] = src0;  // the table holds absolute frame indices
+        r.src[1] = src1;
+        r.dst[0] = s.p[0];
+        r.dst[1] = s.p[1];
+        r.k = tab->d_k;
+        r.t = tab->d_t;
+        r.x = tab->d_x;
+        r.out0 = b_start * 128;
+        r.n_emit = tab->n_active_blocks * 128;
+        r.n_zero_from = tab->n_zero_from;
+        s.lo = r.out0;
+        s.hi = r.out0 + r.n_emit;
+        rj.push_back(r);
+        continue;
+      }
       job.pos0 = pos;
       job.out0 = b_start * 128;
       job.n_emit = max_blocks * 128;
@@ -137,18 +271,13 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
     } else {
       const int64_t avail = durEnd - pos;
       const int64_t n_out_max = max_blocks * 128;
-      auto key = std::make_tuple(eff, pos, durEnd, n_out_max);
+      auto key = std::make_tuple(eff, pos, durEnd, n_out_max, (int64_t)-1);
       auto it = tables.find(key);
       std::shared_ptr<ResampleTable> tab;
       if (it != tables.end()) {
         tab = it->second;
       } else {
-        if (tables.size() >= kResampleCacheMax) {
-          // bounded: drop everything.  Jobs already planned for THIS batch still point at the device tables, so the frees are
-          // queued behind launch_resample (`evicted` below), never here.
-          for (auto& kv : tables) evicted.push_back(kv.second);
-          tables.clear();
-        }
+        make_room();
         tab = std::make_shared<ResampleTable>();
         if (avail >= 4) {
           tab->k.reserve((size_t)n_out_max);
@@ -179,15 +308,8 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
           tab->n_zero_from = (M >= 0) ? M : m;
           tab->k.resize((size_t)std::min<int64_t>(m, active * 128));
           tab->t.resize(tab->k.size());
-          if (!tab->k.empty()) {
-            // context-owned device copies (not render scratch): later renders of the same source geometry reuse them
-            const size_t tb = (tab->k.size() * sizeof(int32_t) + 15) & ~(size_t)15;
-            CU(cudaMallocAsync(&tab->d_k, tb, ctx->stream));
-            CU(cudaMallocAsync(&tab->d_t, tb, ctx->stream));
-            int rc;
-            if ((rc = table_h2d(ctx, tab->d_k, tab->k.data(), tab->k.size() * sizeof(int32_t)))) return rc;
-            if ((rc = table_h2d(ctx, tab->d_t, tab->t.data(), tab->t.size() * sizeof(float)))) return rc;
-          }
+          int rc = upload_table(*tab);
+          if (rc) return rc;
         }
         tables[key] = tab;
       }

@@ -212,11 +212,15 @@ struct SourceJob {
 };
 void launch_source_copy(const SourceJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s);
 
+constexpr int32_t kResampleCleared = INT32_MIN;
 struct ResampleJob {
   const float* src[2];
   float* dst[2];
-  const int32_t* k;   // per output frame: index of S0 in the source (S0..S3 = src[k..k+3])
+  const int32_t* k;   // per output frame: k >= 0: index of S0 in the source (S0..S3 = src[k..k+3]); k == kResampleCleared: the frame
+                      // is zero; other k < 0: the window is not contiguous (a looping source at a loop seam), its four frame
+                      // indices are x[4 * (-k - 1) ..]
   const float* t;     // per output frame: fractional position
+  const int32_t* x;   // window exceptions, four source frame indices each (looping sources only; else nullptr)
   int64_t out0;       // first output frame
   int64_t n_emit;     // frames for which (k,t) exist and the block is kept
   int64_t n_zero_from;  // frames >= this (relative to out0) inside kept blocks are zero (stall point)

@@ -296,12 +296,18 @@ __global__ void __launch_bounds__(256) k_resample(const ResampleJob* __restrict_
     k = job.k[m];
     t = job.t[m];
   }
+  int4 w = make_int4(k, k + 1, k + 2, k + 3);
+  bool live_w = live;
+  if (k < 0) {  // looping sources: a cleared frame (AudioBufferSourceNode.cs:334-338) or a window that straddles the loop seam
+    live_w = live && k != kResampleCleared;
+    if (live_w) w = *reinterpret_cast<const int4*>(job.x + 4 * (int64_t)(-(k + 1)));
+  }
 #pragma unroll
   for (int c = 0; c < 2; c++) {
     float y = 0.f;
-    if (live) {
-      const float* p = job.src[c] + k;
-      float S0 = p[0], S1 = p[1], S2 = p[2], S3 = p[3];
+    if (live_w) {
+      const float* p = job.src[c];
+      float S0 = p[w.x], S1 = p[w.y], S2 = p[w.z], S3 = p[w.w];
       // CubicResampler.cs:52-57 (float32, left to right, unfused)
       y = S1 + t * (0.5f * (S2 - S0) + t * ((S0 - 2.5f * S1 + 2.f * S2 - 0.5f * S3) + t * (0.5f * (S3 - S0) + 1.5f * (S1 - S2))));
     }

@@ -350,7 +350,7 @@ class OfflineAudioContext {
     v.start_duration = s->duration_;
     v.stop_when = s->stop_;
     v.playback_rate = s->PlaybackRate.Value();
-    v.loop = s->Loop ? 1 : 0;  // rate 1 only; the library answers GAC_ERR_UNSUPPORTED otherwise
+    v.loop = s->Loop ? 1 : 0;  // any effective rate; an empty loop region answers GAC_ERR_UNSUPPORTED
     v.loop_start = std::max(0.0, s->LoopStart);
     v.loop_end = std::max(0.0, s->LoopEnd);
     v.n_ops = (int32_t)f.ops.back().size();

@@ -222,8 +222,8 @@ typedef struct gac_voice_desc {
                                processed signal, e.g. the dry / wet branches of GraphAudio.Kit's
                                ReverbEffect, Effects/ReverbEffect.cs:63-91); `source` and the Start/Stop
                                fields are then ignored                                           */
-  int32_t loop;             /* AudioBufferSourceNode.Loop (:40-44).  Supported at effective rate 1 (buffer rate == context
-                               rate, PlaybackRate 1) with LoopStart < LoopEnd; otherwise GAC_ERR_UNSUPPORTED at render  */
+  int32_t loop;             /* AudioBufferSourceNode.Loop (:40-44): at effective rate 1 the copy path (:186-235), otherwise the
+                               wrap-buffer CubicResampler path (:236-358).  LoopStart >= LoopEnd: GAC_ERR_UNSUPPORTED at render  */
   int32_t source_kind;      /* gac_source_kind (input == 0 only): what feeds the chain                                */
   double loop_start;        /* LoopStart in seconds (:49-53)                                     */
   double loop_end;          /* LoopEnd in seconds, 0 = end of the buffer (:58-62)                */

@@ -487,7 +487,7 @@ class Context {
   int currentBlock = 0;       // AudioContextBase.cs:16
   double currentTime = 0.0;   // :17
   bool cycle = false;
-  bool unsupported = false;  // a path this oracle does not restate was reached (looping + resampling)
+  bool unsupported = false;  // a path this oracle does not restate was reached (a looping source with an empty loop region: the reference never returns)
   std::deque<std::function<void()>> commands;  // :15
   std::vector<std::unique_ptr<Node>> nodes;
   std::vector<std::unique_ptr<PlayBuffer>> buffers;
@@ -865,7 +865,7 @@ class Convolver : public Node {
   BlockPtr ob;
 };
 
-// Nodes/AudioBufferSourceNode.cs (non-loop paths; Loop stays false on this path)
+// Nodes/AudioBufferSourceNode.cs:79-402 (all four paths: rate 1 / resampled, with and without Loop)
 class BufferSource : public Node {
  public:
   explicit BufferSource(Context* c) : Node(c, 0, 1) { rate = addParam(1.f, 0.001f, 1000.f, false); }  // :76
@@ -933,10 +933,46 @@ class BufferSource : public Node {
         int64_t loopLength = loopEndFrame - loopStartFrame;
         if (loopLength > 0) pos = loopStartFrame + ((pos - loopEndFrame) % loopLength);
       }
-    } else if (loop) {
-      // the looping resampler path (:236-358, wrap buffer) is not restated: flagged, never silently approximated
-      ctx->unsupported = true;
-      ob->clear();
+    } else if (loop) {  // :236-358 with _loop set: every Process call is fed from the 512-float wrap buffer (:296-314)
+      // (available = loopEndFrame - pos because loopEndFrame <= Length, so `pos + available >= loopEndFrame - 4` (:296) always holds)
+      if ((int)rs.size() != oc) { rs.assign(oc, CubicResampler()); }
+      float wrap[512];
+      int64_t totalConsumed = 0;
+      for (int c = 0; c < oc; c++) {
+        const float* d = buf->data[c].data();
+        float* o = ob->ch(c);
+        int64_t p = pos, consumedCh = 0;
+        int oi = 0;
+        while (oi < frames) {
+          if (p >= loopEndFrame) p = loopStartFrame;                                          // :265-268
+          int avail = (int)std::min<int64_t>(loopEndFrame - p, buf->length - p);             // :276-277
+          if (avail <= 0) {                                                                   // :279-285 (an empty loop region never leaves this branch)
+            ctx->unsupported = true;
+            std::fill(o + oi, o + frames, 0.f);
+            break;
+          }
+          int64_t loopLength = loopEndFrame - loopStartFrame;
+          int fromEnd = (int)(loopEndFrame - p);
+          int needed = std::min(frames - oi + 4, 512);                                        // :301
+          int copied = 0;
+          for (int i = 0; i < fromEnd && copied < needed; i++) wrap[copied++] = d[p + i];     // :303-306
+          for (int64_t i = 0; copied < needed && i < loopLength; i++) wrap[copied++] = d[loopStartFrame + i];  // :308-311
+          int ic, op;
+          rs[c].process(wrap, copied, o + oi, frames - oi, eff, &ic, &op);                    // :313
+          if (op > 0) hasMore = true;
+          int64_t np = p + ic;
+          if (np >= loopEndFrame) np = loopStartFrame + (np - loopEndFrame);                  // :323-328 (no modulo here)
+          consumedCh += (np >= p) ? (np - p) : (loopEndFrame - p + np - loopStartFrame);      // :330
+          p = np; oi += op;
+          if (ic == 0 && op == 0) { std::fill(o + oi, o + frames, 0.f); break; }              // :334-338
+        }
+        if (c == 0) totalConsumed = consumedCh;
+      }
+      pos += totalConsumed;                                                                   // :347
+      if (pos >= loopEndFrame) {                                                              // :349-357
+        int64_t loopLength = loopEndFrame - loopStartFrame;
+        if (loopLength > 0) pos = loopStartFrame + ((pos - loopEndFrame) % loopLength);
+      }
     } else {  // :236-358
       if ((int)rs.size() != oc) { rs.assign(oc, CubicResampler()); }
       int64_t totalConsumed = 0;
@@ -951,7 +987,7 @@ class BufferSource : public Node {
           int avail = (int)std::min<int64_t>(endFrame - p, buf->length - p);
           if (avail <= 0) { std::fill(o + oi, o + frames, 0.f); break; }
           int ic, op;
-          rs[c].process(d + p, avail, o + oi, frames - oi, eff, &ic, &op);  // :317
+          rs[c].process(d + p, avail, o + oi, frames - oi, eff, &ic, &op);  // :330
           if (op > 0) hasMore = true;
           int64_t np = p + ic;
           consumedCh += np - p;

@@ -516,7 +516,7 @@ class OfflineAudioContext:
         if rc == -2:
             raise InvalidOperationException("Audio graph cycle detected")
         if lib().ora_unsupported(self._h):
-            raise NotImplementedError("the oracle does not restate this path (looping source with resampling)")
+            raise NotImplementedError("the oracle does not restate this path (resampled looping source with an empty loop region: the reference spins forever)")
         if rc != 0:
             raise ArgumentOutOfRangeException("render failed (%d)" % rc)
 

@@ -148,3 +148,66 @@ def build_c5(api, fs, src_rate, voices, bus_gain, t_scale=1.0, **ctx_kw):
         s.Connect(gn).Connect(conv).Connect(bus)
         s.Start()
     return ctx
+
+
+def loop_resample_model(x, pos0, loop_start, loop_end, eff, n_blocks):
+    """Index-level model of a LOOPING AudioBufferSourceNode on the CubicResampler path (Nodes/AudioBufferSourceNode.cs:236-358 with
+    _loop set), one channel.  Which buffer frames are shifted into the resampler and the phase of every output depend on positions only,
+    never on sample values, so the model replays the block loop with indices: per Process call the wrap buffer holds the frames
+    pos .. loopEnd-1 followed by ONE pass over the loop region, cut at min(128 - outIdx + 4, 512) entries (:296-314); a call that
+    neither consumes nor produces clears the rest of the quantum (:334-338); a quantum without any output ends the source (:360-368).
+    Returns (y, n_live_blocks): y[n_blocks * 128] float32 and the number of leading quanta that are flagged non-silent."""
+    x = np.asarray(x, dtype=np.float32)
+    idx = np.zeros((n_blocks * 128, 4), dtype=np.int64)
+    tt = np.zeros(n_blocks * 128, dtype=np.float32)
+    live = np.zeros(n_blocks * 128, dtype=bool)
+    win, ready, Pos = [0, 0, 0, 0], 0, 0.0
+    position = pos0
+    n_live = 0
+    for b in range(n_blocks):
+        pos, consumed_ch, oi, more = position, 0, 0, False
+        while oi < 128:
+            if pos >= loop_end:
+                pos = loop_start
+            from_end = loop_end - pos
+            needed = min(128 - oi + 4, 512)
+            wrap = list(range(pos, pos + min(from_end, needed)))
+            wrap += list(range(loop_start, loop_start + min(loop_end - loop_start, needed - len(wrap))))
+            ip, op = 0, 0
+            while ready < 4 and ip < len(wrap):   # CubicResampler.cs:31-35
+                win = win[1:] + [wrap[ip]]
+                ip += 1
+                ready += 1
+            if ready == 4:
+                while oi + op < 128:               # :40-60
+                    consume = int(Pos)
+                    if ip + consume > len(wrap):
+                        break
+                    for _ in range(consume):
+                        win = win[1:] + [wrap[ip]]
+                        ip += 1
+                    Pos -= consume
+                    idx[b * 128 + oi + op] = win
+                    tt[b * 128 + oi + op] = np.float32(Pos)
+                    live[b * 128 + oi + op] = True
+                    op += 1
+                    Pos += eff
+            more = more or op > 0
+            new_pos = pos + ip
+            if new_pos >= loop_end:
+                new_pos = loop_start + (new_pos - loop_end)
+            consumed_ch += (new_pos - pos) if new_pos >= pos else (loop_end - pos + new_pos - loop_start)
+            pos, oi = new_pos, oi + op
+            if ip == 0 and op == 0:
+                break
+        position += consumed_ch
+        if position >= loop_end:
+            position = loop_start + (position - loop_end) % (loop_end - loop_start)
+        if not more:
+            live[b * 128:(b + 1) * 128] = False
+            break
+        n_live = b + 1
+    S0, S1, S2, S3 = (x[idx[:, i]] for i in range(4))
+    h, q, t = np.float32(0.5), np.float32(1.5), tt
+    y = S1 + t * (h * (S2 - S0) + t * ((S0 - np.float32(2.5) * S1 + np.float32(2.0) * S2 - h * S3) + t * (h * (S3 - S0) + q * (S1 - S2))))
+    return np.where(live, y, np.float32(0)).astype(np.float32), n_live

@@ -349,10 +349,79 @@ def test_looping_source_feeding_a_convolver_and_unsupported_variants():
         return ctx
     yg, yo = build(G).Render(128 * 100), build(O).Render(128 * 100)
     assert np.abs(yg - yo).max() <= 1e-5
+    yg, yo = build(G, rate=0.5).Render(128 * 100), build(O, rate=0.5).Render(128 * 100)   # the looping resampler path in front of K5
+    assert np.abs(yo).max() > 0.05 and np.abs(yg - yo).max() <= 1e-5
     with pytest.raises(G.NotSupportedException):
-        build(G, rate=0.5).Render(1280)   # the looping resampler path is not accelerated (and never approximated)
-    with pytest.raises(G.NotSupportedException):
-        build(G, ls=0.01, le=0.01).Render(1280)
+        build(G, ls=0.01, le=0.01).Render(1280)   # an empty loop region: the reference never returns from it on the resampler path
+
+
+@pytest.mark.parametrize("rate,loop,offset,fs_buf,start,stop,nch", [
+    (0.5, (100.2, 400.2), 0.0, 48000, 0.0, None, 2),      # below 1: one Process call per quantum
+    (1.37, (100.2, 400.2), 650.0, 48000, 0.01, None, 2),  # start position behind LoopEnd: the first call restarts at LoopStart
+    (1.0, (10.5, 47.5), 20.0, 44100, 0.0, 0.1, 2),        # 44.1 -> 48 kHz, a 37-frame loop, Stop(0.1)
+    (2.5, (0.0, 0.0), 0.0, 48000, 0.005, None, 1),        # mono buffer, LoopEnd 0 = end of the buffer, late start
+    (8.0, (100.2, 400.2), 0.0, 48000, 0.0, None, 2),      # the tail of every quantum is cleared (:334-338)
+    (0.9, (5.2, 8.2), 2.0, 48000, 0.0, None, 2),          # a 3-frame loop: priming takes two calls
+    (200.0, (0.0, 0.0), 0.0, 48000, 0.0, None, 2),        # one output, then the source ends (:360-368)
+    (0.731, (0.0, 2500.0), 1234.0, 32000, 0.0, 0.35, 2),
+])
+def test_looping_source_on_the_resampler_path(rate, loop, offset, fs_buf, start, stop, nch):
+    """AudioBufferSourceNode.Loop on the CubicResampler path (Nodes/AudioBufferSourceNode.cs:236-358: the 512-float wrap buffer, one pass
+    over the loop region per Process call, cleared tails, the position bookkeeping of :323-357): the host replays the block loop with
+    frame indices, the device evaluates the polynomial — bit-exact against the oracle, which restates the path with samples, and
+    against the index-level model the oracle's own KATs use."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+    src = [synth.splitmix_uniform(955 + c, 3001) for c in range(nch)]
+
+    def build(api):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, fs_buf)
+        s.Loop = True
+        s.LoopStart, s.LoopEnd = loop[0] / fs_buf, loop[1] / fs_buf
+        s.PlaybackRate.Value = rate
+        g = api.GainNode(ctx)
+        g.Gain.Value = 0.5
+        s.Connect(g).Connect(ctx.Destination)
+        s.Start(start, offset / fs_buf)
+        if stop is not None:
+            s.Stop(stop)
+        return ctx
+    nb = 150
+    yg, yo = build(G).Render(128 * nb), build(O).Render(128 * nb)
+    assert np.count_nonzero(yo) >= 1
+    assert np.array_equal(yg, yo)
+    if start == 0.0 and stop is None:
+        le = min(int(loop[1] / fs_buf * fs_buf) if loop[1] > 0 else 3001, 3001)
+        ls = min(int(loop[0] / fs_buf * fs_buf), le)
+        eff = (fs_buf / float(fs)) * float(np.float32(rate))
+        want, _ = synth.loop_resample_model(src[0], int(offset / fs_buf * fs_buf), ls, le, eff, nb)
+        assert np.array_equal(yg[0], np.float32(0.5) * want)
+
+
+def test_seventeen_looping_resampled_geometries_in_one_batch():
+    """More distinct (rate, loop) geometries than the context's table cache holds (kResampleCacheMax = 16), seam windows included."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+
+    def build(api):
+        ctx = api.OfflineAudioContext(fs)
+        for v in range(19):
+            x = [synth.splitmix_uniform(3000 + 2 * v + c, 900 + 37 * v) for c in range(2)]
+            s = api.AudioBufferSourceNode(ctx)
+            s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(x, fs)
+            s.Loop = v % 5 != 4
+            s.LoopStart, s.LoopEnd = (50.2 + 3 * v) / fs, (600.2 + 11 * v) / fs
+            s.PlaybackRate.Value = 0.6 + 0.07 * v
+            s.Connect(ctx.Destination)
+            s.Start(0.0, (10.0 * v) / fs)
+        return ctx
+    yg, yo = build(G).Render(128 * 40), build(O).Render(128 * 40)
+    assert np.abs(yo).max() > 1.0
+    assert np.array_equal(yg, yo)
 
 
 def test_parameter_edits_and_late_starts_between_successive_render_calls():

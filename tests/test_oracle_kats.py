@@ -450,6 +450,67 @@ def test_looping_source_copy_path_closed_form():
     assert np.nonzero(stopped)[0][-1] == 511
 
 
+def _looping_resampled(x, fs_buf, fs, rate, loop_start, loop_end, offset, n, stop=None, api=O):
+    ctx = api.OfflineAudioContext(fs)
+    s = api.AudioBufferSourceNode(ctx)
+    s.Buffer = api.PlayableAudioBuffer.FromChannelArrays([x], fs_buf)
+    s.Loop = True
+    s.LoopStart, s.LoopEnd = loop_start / fs_buf, loop_end / fs_buf
+    s.PlaybackRate.Value = rate
+    s.Connect(ctx.Destination)
+    s.Start(0.0, offset / fs_buf)
+    if stop is not None:
+        s.Stop(stop)
+    return ctx.Render(n)[0]
+
+
+@pytest.mark.parametrize("rate", [0.5, 0.73, 1.37, 2.0, 3.9])
+def test_looping_resampler_equals_the_resampler_over_the_unrolled_loop(rate):
+    # Nodes/AudioBufferSourceNode.cs:236-358 with Loop: the wrap buffer (:296-314) presents pos .. loopEnd-1 followed by the loop
+    # region, so the CubicResampler sees ONE continuous stream — the same samples, phases and float32 polynomial as a non-looping
+    # source playing the unrolled buffer.  (Rates below ~5 never hit the cleared-tail branch :334-338.)
+    fs = 48000
+    x = synth.splitmix_uniform(901, 1000)
+    n = 128 * 10
+    k = np.arange(int(n * rate) + 600)
+    unrolled = x[np.where(k < 400, k, 100 + (k - 400) % 300)]
+    got = _looping_resampled(x, fs, fs, rate, 100.2, 400.2, 0, n)
+    ctx = O.OfflineAudioContext(fs)
+    s = O.AudioBufferSourceNode(ctx)
+    s.Buffer = O.PlayableAudioBuffer.FromChannelArrays([unrolled], fs)
+    s.PlaybackRate.Value = rate
+    s.Connect(ctx.Destination)
+    s.Start(0.0)
+    want = ctx.Render(n)[0]
+    assert np.count_nonzero(want) > n - 8
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("rate,loop,offset,fs_buf", [
+    (0.5, (100.2, 400.2), 0, 48000),       # below 1: one Process call per quantum
+    (1.37, (100.2, 400.2), 650, 48000),    # start position behind loopEnd: the first call restarts at loopStart (:265-268)
+    (1.0, (10.5, 47.5), 20, 44100),        # 44.1 -> 48 kHz, a 37-frame loop: ONE pass over the loop region per call (:308-311)
+    (2.5, (0, 0), 0, 48000),               # LoopEnd 0 = end of the buffer
+    (8.0, (100.2, 400.2), 0, 48000),       # the tail of every quantum is cleared once fewer than (int)Pos inputs are offered (:334-338)
+    (0.9, (5.2, 8.2), 2, 48000),           # a 3-frame loop: priming needs two calls (CubicResampler.cs:31-38)
+    (200.0, (0, 0), 0, 48000),             # (int)Pos above the 132 frames a call is offered: one output (phase 0), then the source ends
+])
+def test_looping_resampler_matches_the_index_model(rate, loop, offset, fs_buf):
+    fs = 48000
+    x = synth.splitmix_uniform(902, 1000)
+    nb = 12
+    got = _looping_resampled(x, fs_buf, fs, rate, loop[0], loop[1], offset, 128 * nb)
+    le = min(int(loop[1] / fs_buf * fs_buf) if loop[1] > 0 else 1000, 1000)
+    ls = min(int(loop[0] / fs_buf * fs_buf), le)
+    eff = (fs_buf / float(fs)) * float(np.float32(rate))
+    want, n_live = synth.loop_resample_model(x, int(offset / fs_buf * fs_buf), ls, le, eff, nb)
+    assert np.array_equal(got, want)
+    if rate == 8.0:
+        assert np.all(want.reshape(nb, 128)[:, -3:] == 0) and np.count_nonzero(want.reshape(nb, 128)[:, :120]) > 110 * nb
+    if rate == 200.0:
+        assert n_live == 1 and np.count_nonzero(got) == 1 and got[0] == x[1]
+
+
 # ---------------------------------------------------------------- OscillatorNode / ConstantSourceNode / AudioParam modulation
 # (oracle-side groundwork for SURVEY.md §8f-3: the device path does not accelerate these yet and rejects them)
 def test_constant_source_and_sample_accurate_start_stop():

@@ -70,7 +70,8 @@ internal sealed unsafe class GraphFlattener : IDisposable
                 Source = s.Buffer?.Handle(ctx) ?? IntPtr.Zero,
                 StartWhen = when, StartOffset = s.Offset, StartDuration = s.Duration, StopWhen = s.StopWhen,
                 PlaybackRate = s.PlaybackRate.Value, OpCount = chain.Count, Ops = f.Ops(chain, q), Bus = bus, Input = 0,
-                Loop = s.Loop ? 1 : 0, LoopStart = s.LoopStart, LoopEnd = s.LoopEnd
+                Loop = s.Loop ? 1 : 0, LoopStart = s.LoopStart, LoopEnd = s.LoopEnd,
+                SourceParam = f.Param(s.PlaybackRate, q)   // read by the library when it carries events / epochs (k-rate, per quantum on the host)
             });
         }
         // node .. upstream through single-input nodes; returns the chain in processing order and the node it starts from

@@ -64,7 +64,7 @@ internal unsafe struct GacVoiceDesc
     public int Loop;    // AudioBufferSourceNode.Loop (any effective rate)
     public int SourceKind;              // 0 buffer, 1 ConstantSourceNode, 2 OscillatorNode
     public double LoopStart, LoopEnd;   // seconds; LoopEnd 0 = end of the buffer
-    public GacParam SourceParam;        // constant: Offset; oscillator: Frequency
+    public GacParam SourceParam;        // constant: Offset; oscillator: Frequency; buffer source: PlaybackRate when it carries events
     public int OscillatorType;          // 0 sine, 1 square, 2 sawtooth, 3 triangle
     public int Reserved;
 }

@@ -1013,6 +1013,9 @@ class OfflineAudioContext:
                 v.source = src.Buffer._handle(self, member) if src.Buffer is not None else None
                 v.start_when, v.start_offset, v.start_duration, v.stop_when = when, src._offset, src._duration, src._stop
                 v.playback_rate = src.PlaybackRate.Value
+                # PlaybackRate as a full parameter: read by the library when it carries events (automation, or epochs of a Value that
+                # was edited between Render calls); k-rate, evaluated per quantum on the host
+                v.source_param = src.PlaybackRate._desc(keep, self._q_now())
             else:
                 v.source = None
                 v.playback_rate = 1.0

@@ -64,6 +64,51 @@ struct ParamH {
   int mod_bus = -1;  // >= 0: the bus whose (mono) output is the parameter's modulation input
   float minv = 0.f, maxv = 0.f;
 };
+// AudioParam.ComputeValueAtTime (AudioParam.cs:169-217) with InterpolateLinear / InterpolateExponential / ComputeSetTargetFromBaseline
+// (:220-247) on the HOST, for the one parameter whose values steer host-side planning: AudioBufferSourceNode.PlaybackRate (k-rate: the
+// value at the quantum's start time, :146-165).  `q` selects the epoch (parameters edited between successive Render calls).
+static float host_param_value(const ParamH& p, int64_t q, double time) {
+  float value = p.value;
+  const std::vector<gac_event>* ev = &p.ev;
+  for (const auto& e : p.later) {
+    if (e.q0 > q) break;
+    value = e.value;
+    ev = &e.ev;
+  }
+  const int count = (int)ev->size();
+  if (count == 0) return value;
+  auto lin = [](float v0, double t0, float v1, double t1, double t) {
+    double u = (t - t0) / (t1 - t0);
+    u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+    return (float)((double)v0 + (double)(v1 - v0) * u);
+  };
+  auto set_target = [](const gac_event& e, float base, double t) {
+    const double elapsed = t - e.time;
+    if (elapsed <= 0) return base;
+    const double tc = std::max(e.time_constant, 0.001);
+    return (float)((double)e.target + (double)(base - e.target) * std::exp(-elapsed / tc));
+  };
+  float boundary = value;
+  for (int i = 0; i < count; i++) {
+    const gac_event& e = (*ev)[i];
+    if (time < e.time) {
+      if (i == 0) return boundary;
+      const gac_event& pv = (*ev)[i - 1];
+      if (e.type == GAC_EVENT_LINEAR_RAMP) return lin(pv.value, pv.time, e.value, e.time, time);
+      if (e.type == GAC_EVENT_EXPONENTIAL_RAMP) {
+        if (pv.value <= 0 || e.value <= 0) return lin(pv.value, pv.time, e.value, e.time, time);
+        double u = (time - pv.time) / (e.time - pv.time);
+        u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        return (float)((double)pv.value * std::pow((double)(e.value / pv.value), u));
+      }
+      if (pv.type == GAC_EVENT_SET_TARGET) return set_target(pv, boundary, time);
+      return pv.value;
+    }
+    if (e.type != GAC_EVENT_SET_TARGET) boundary = e.value;
+  }
+  const gac_event& last = (*ev)[count - 1];
+  return last.type == GAC_EVENT_SET_TARGET ? set_target(last, boundary, time) : last.value;
+}
 struct OpH {
   int kind = 0;
   int ftype = 0;
@@ -81,7 +126,8 @@ struct VoiceH {
   int bus = -1;
   int input_bus = -1;  // >= 0: the chain is fed by that bus's output instead of a source buffer
   int kind = GAC_SOURCE_BUFFER;  // gac_source_kind
-  ParamH src_param;              // CONSTANT: Offset, OSCILLATOR: Frequency
+  ParamH src_param;              // CONSTANT: Offset, OSCILLATOR: Frequency, BUFFER: PlaybackRate when it carries events (rate_events)
+  bool rate_events = false;
   int osc_type = 0;
 };
 struct BusH {
@@ -968,6 +1014,12 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
       if (d.source->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: buffer belongs to another context", v);
       if (d.source->nch > 2) return fail(GAC_ERR_UNSUPPORTED, "voice %d: sources with more than 2 channels are outside the accelerated path", v);
       if (!(d.playback_rate >= 0.001f && d.playback_rate <= 1000.f)) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: playbackRate outside [0.001, 1000]", v);
+      if (d.source_param.n_events > 0) {  // PlaybackRate with automation events / epochs: evaluated per quantum on the host
+        int rc = copy_param(d.source_param, &h.src_param, "bufferSource.playbackRate");
+        if (rc) return rc;
+        if (h.src_param.mod_bus >= 0) return fail(GAC_ERR_UNSUPPORTED, "voice %d: a modulated PlaybackRate is outside the accelerated path (the resampler's phase is replayed on the host)", v);
+        h.rate_events = true;
+      }
     }
     if (d.bus < -1 || d.bus >= desc->n_buses) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: bus index %d out of range", v, d.bus);
     h.src = (h.input_bus < 0 && h.kind == GAC_SOURCE_BUFFER) ? d.source : nullptr;

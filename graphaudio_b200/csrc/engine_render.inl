@@ -111,122 +111,171 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
     const double ratio = (double)buf->rate / (double)ctx->fs;  // :168
     const double eff = ratio * (double)v.rate;                 // :169
     const int64_t max_blocks = std::max<int64_t>(0, b_stop - b_start);
-    if (v.loop) {
-      // Looping playback (:171-177, :197-234): runs until the stop time, duration only sets that stop time (:106-110).
-      int64_t loopEnd = v.loop_end > 0 ? (int64_t)(v.loop_end * (double)buf->rate) : buf->n;
-      loopEnd = std::min(loopEnd, buf->n);
-      const int64_t loopStart = std::min((int64_t)(v.loop_start * (double)buf->rate), loopEnd);
-      if (loopEnd - loopStart <= 0) return fail(GAC_ERR_UNSUPPORTED, "looping source with an empty loop region");
-      if (eff != 1.0) {
-        // The CubicResampler path with _loop set (:236-358).  Every Process call is fed from the 512-float wrap buffer (:296-314:
-        // `pos + available` IS loopEndFrame, so the test against loopEndFrame - 4 always holds): the frames pos .. loopEnd-1 followed
-        // by ONE pass over the loop region, cut at min(128 - outIdx + 4, 512) entries.  Which buffer frames are shifted in, and the
-        // phase of every output, depend on positions only — so the block loop is replayed here with frame indices, and the device
-        // evaluates the float32 polynomial.  A window whose four frames are not consecutive (at a loop seam) goes to `x`; a frame the
-        // reference clears (a call that neither consumes nor produces, :334-338) is kResampleCleared; a quantum without any output
-        // ends the source (:360-368).
-        if (max_blocks == 0) {
-          cj.push_back(job);
-          continue;
-        }
-        const int64_t n_out_max = max_blocks * 128;
-        auto key = std::make_tuple(eff, pos, loopEnd, n_out_max, loopStart);
+    if (v.rate_events || (v.loop && eff != 1.0)) {
+      // The general case: a looping source on the CubicResampler path (:236-358 with _loop set) and / or a PlaybackRate that changes from
+      // quantum to quantum (k-rate automation, evaluated on the host: host_param_value).  Which buffer frames are shifted into the
+      // resampler and the phase of every output depend on positions only, so Process() is replayed here quantum by quantum WITH FRAME
+      // INDICES — the copy path (:186-235) when the quantum's effective rate is exactly 1, else the resampler path, whose Process calls
+      // are fed from the 512-float wrap buffer when looping (:296-314: `pos + available` IS loopEndFrame, so the test against
+      // loopEndFrame - 4 always holds; frames pos .. loopEnd-1, then ONE pass over the loop region, cut at min(128 - outIdx + 4, 512)).
+      // The device evaluates the float32 polynomial: a window of four consecutive frames is `k`, any other window (loop seams, buffer
+      // edges) goes to `x`, a copied frame is the window around it with t = 0 (S1 + 0 * (...) == S1), a frame the reference clears
+      // is kResampleCleared.  A quantum without output — or, not looping, after which every input frame is consumed — ends the source
+      // (:360-368).
+      int64_t loopEnd = 0, loopStart = 0;
+      if (v.loop) {
+        loopEnd = v.loop_end > 0 ? (int64_t)(v.loop_end * (double)buf->rate) : buf->n;  // :171-177
+        loopEnd = std::min(loopEnd, buf->n);
+        loopStart = std::min((int64_t)(v.loop_start * (double)buf->rate), loopEnd);
+        if (loopEnd - loopStart <= 0) return fail(GAC_ERR_UNSUPPORTED, "looping source with an empty loop region");
+      }
+      if (max_blocks == 0 || buf->n <= 0) {
+        cj.push_back(job);
+        continue;
+      }
+      const int64_t n_out_max = max_blocks * 128;
+      std::shared_ptr<ResampleTable> tab;
+      auto key = std::make_tuple(eff, pos, loopEnd, n_out_max, loopStart);
+      if (!v.rate_events) {
         auto it = tables.find(key);
-        std::shared_ptr<ResampleTable> tab;
-        if (it != tables.end()) {
-          tab = it->second;
-        } else {
-          make_room();
-          tab = std::make_shared<ResampleTable>();
-          tab->k.reserve((size_t)n_out_max);
-          tab->t.reserve((size_t)n_out_max);
-          int64_t win[4] = {0, 0, 0, 0};
-          int ready = 0;
-          double Pos = 0.0;
-          int64_t position = pos, active = 0;
-          std::vector<int64_t> wrap;
-          wrap.reserve(512);
-          auto shift = [&](int64_t f) { win[0] = win[1]; win[1] = win[2]; win[2] = win[3]; win[3] = f; };
-          for (int64_t blk = 0; blk < max_blocks; blk++) {
-            int64_t p = position, consumedCh = 0;
-            int oi = 0;
-            bool more = false;
+        if (it != tables.end()) tab = it->second;
+      }
+      if (!tab) {
+        tab = std::make_shared<ResampleTable>();
+        tab->k.reserve((size_t)n_out_max);
+        tab->t.reserve((size_t)n_out_max);
+        const bool loop = v.loop;
+        const int64_t len = buf->n, loopLen = loopEnd - loopStart;
+        int64_t win[4] = {0, 0, 0, 0};
+        int ready = 0;
+        double Pos = 0.0;
+        int64_t position = pos, active = 0;
+        std::vector<int64_t> wrap;
+        wrap.reserve(512);
+        auto shift = [&](int64_t f) { win[0] = win[1]; win[1] = win[2]; win[2] = win[3]; win[3] = f; };
+        auto emit = [&](const int64_t* w, float t) {
+          if (w[1] == w[0] + 1 && w[2] == w[0] + 2 && w[3] == w[0] + 3) {
+            tab->k.push_back((int32_t)w[0]);
+          } else {
+            tab->k.push_back(-(int32_t)(tab->x.size() / 4) - 1);
+            for (int q = 0; q < 4; q++) tab->x.push_back((int32_t)w[q]);
+          }
+          tab->t.push_back(t);
+        };
+        for (int64_t blk = 0; blk < max_blocks; blk++) {
+          double eff_b = eff;
+          if (v.rate_events) eff_b = ratio * (double)host_param_value(v.src_param, b_start + blk, bt[b_start + blk]);  // :165-169
+          int oi = 0;
+          bool more = false;
+          if (eff_b == 1.0) {  // :186-235
+            int64_t p = position;
             while (oi < 128) {
-              if (p >= loopEnd) p = loopStart;                                   // :265-268
-              const int64_t fromEnd = loopEnd - p;
-              const int64_t needed = std::min<int64_t>(128 - oi + 4, 512);       // :301
-              wrap.clear();
-              for (int64_t q = 0; q < fromEnd && (int64_t)wrap.size() < needed; q++) wrap.push_back(p + q);                        // :303-306
-              for (int64_t q = 0; (int64_t)wrap.size() < needed && q < loopEnd - loopStart; q++) wrap.push_back(loopStart + q);    // :308-311
-              const int64_t n_in = (int64_t)wrap.size();
+              if (loop && p >= loopEnd) p = loopStart;
+              if (p >= durEnd && !loop) break;
+              const int64_t endFrame = loop ? loopEnd : std::min(durEnd, len);
+              const int64_t avail = std::min<int64_t>(endFrame - p, 128 - oi);
+              if (avail <= 0) break;
+              for (int64_t q = 0; q < avail; q++) {
+                const int64_t f = p + q;
+                const int64_t w[4] = {std::max<int64_t>(f - 1, 0), f, std::min(f + 1, len - 1), std::min(f + 2, len - 1)};
+                emit(w, 0.f);
+              }
+              p += avail;
+              oi += (int)avail;
+              more = true;
+            }
+            position += 128;  // :224
+          } else {             // :236-358
+            int64_t p = position, consumedCh = 0;
+            while (oi < 128) {
+              if (loop && p >= loopEnd) p = loopStart;                             // :265-268
+              if (p >= durEnd && !loop) break;                                      // :270-274
+              const int64_t endFrame = loop ? loopEnd : std::min(durEnd, len);
+              const int64_t avail = std::min(endFrame - p, len - p);                // :277
+              if (avail <= 0) break;  // (looping: only an empty loop region gets here, refused above)
+              int64_t n_in = avail;
+              if (loop) {
+                const int64_t needed = std::min<int64_t>(128 - oi + 4, 512);        // :301
+                wrap.clear();
+                for (int64_t q = 0; q < loopEnd - p && (int64_t)wrap.size() < needed; q++) wrap.push_back(p + q);          // :303-306
+                for (int64_t q = 0; (int64_t)wrap.size() < needed && q < loopLen; q++) wrap.push_back(loopStart + q);      // :308-311
+                n_in = (int64_t)wrap.size();
+              }
+              auto in_frame = [&](int64_t i) { return loop ? wrap[(size_t)i] : p + i; };
               int64_t ip = 0;
               int op = 0;
               while (ready < 4 && ip < n_in) {   // CubicResampler.cs:31-35
-                shift(wrap[ip++]);
+                shift(in_frame(ip++));
                 ready++;
               }
               if (ready == 4) {
                 while (oi + op < 128) {          // :40-60
                   const int consume = (int)Pos;
                   if (ip + consume > n_in) break;
-                  for (int q = 0; q < consume; q++) shift(wrap[ip++]);
+                  for (int q = 0; q < consume; q++) shift(in_frame(ip++));
                   Pos -= consume;
-                  if (win[1] == win[0] + 1 && win[2] == win[0] + 2 && win[3] == win[0] + 3) {
-                    tab->k.push_back((int32_t)win[0]);
-                  } else {
-                    tab->k.push_back(-(int32_t)(tab->x.size() / 4) - 1);
-                    for (int q = 0; q < 4; q++) tab->x.push_back((int32_t)win[q]);
-                  }
-                  tab->t.push_back((float)Pos);
+                  emit(win, (float)Pos);
                   op++;
-                  Pos += eff;
+                  Pos += eff_b;
                 }
               }
               more = more || op > 0;
               int64_t np = p + ip;
-              if (np >= loopEnd) np = loopStart + (np - loopEnd);                                         // :323-328 (no modulo here)
-              consumedCh += (np >= p) ? (np - p) : (loopEnd - p + np - loopStart);                        // :330
+              if (loop && np >= loopEnd) np = loopStart + (np - loopEnd);                                  // :323-328 (no modulo here)
+              consumedCh += (np >= p) ? (np - p) : (loopEnd - p + np - loopStart);                         // :330
               p = np;
               oi += op;
-              if (ip == 0 && op == 0) break;                                                              // :334-338
+              if (ip == 0 && op == 0) break;                                                               // :334-338
             }
-            for (; oi < 128; oi++) {  // the cleared rest of the quantum
-              tab->k.push_back(kResampleCleared);
-              tab->t.push_back(0.f);
-            }
-            position += consumedCh;                                                                       // :347
-            if (position >= loopEnd) position = loopStart + (position - loopEnd) % (loopEnd - loopStart); // :349-357
-            if (!more) break;  // nothing produced: the quantum is cleared and the source ends (:360-368)
-            active = blk + 1;
+            position += consumedCh;  // :347
           }
-          tab->n_active_blocks = active;
-          tab->k.resize((size_t)(active * 128));
-          tab->t.resize(tab->k.size());
-          tab->n_zero_from = (int64_t)tab->k.size();
-          int rc = upload_table(*tab);
-          if (rc) return rc;
+          for (; oi < 128; oi++) {  // the cleared rest of the quantum
+            tab->k.push_back(kResampleCleared);
+            tab->t.push_back(0.f);
+          }
+          if (loop && position >= loopEnd) position = loopStart + (position - loopEnd) % loopLen;          // :226-234, :349-357
+          if (!more || (!loop && position >= durEnd)) break;  // the quantum is cleared and the source ends (:360-368)
+          active = blk + 1;
+        }
+        tab->n_active_blocks = active;
+        tab->k.resize((size_t)(active * 128));
+        tab->t.resize(tab->k.size());
+        tab->n_zero_from = (int64_t)tab->k.size();
+        int rc = upload_table(*tab);
+        if (rc) return rc;
+        if (v.rate_events) {
+          evicted.push_back(tab);  // not cached (the key would be the whole event list): released behind the resample launch
+        } else {
+          make_room();
           tables[key] = tab;
         }
-        if (tab->n_active_blocks == 0) {
-          cj.push_back(job);
-          continue;
-        }
-        ResampleJob r{};
-        r.src[0] = src0;  // the table holds absolute frame indices
-        r.src[1] = src1;
-        r.dst[0] = s.p[0];
-        r.dst[1] = s.p[1];
-        r.k = tab->d_k;
-        r.t = tab->d_t;
-        r.x = tab->d_x;
-        r.out0 = b_start * 128;
-        r.n_emit = tab->n_active_blocks * 128;
-        r.n_zero_from = tab->n_zero_from;
-        s.lo = r.out0;
-        s.hi = r.out0 + r.n_emit;
-        rj.push_back(r);
+      }
+      if (tab->n_active_blocks == 0) {
+        cj.push_back(job);
         continue;
       }
+      ResampleJob r{};
+      r.src[0] = src0;  // the table holds absolute frame indices
+      r.src[1] = src1;
+      r.dst[0] = s.p[0];
+      r.dst[1] = s.p[1];
+      r.k = tab->d_k;
+      r.t = tab->d_t;
+      r.x = tab->d_x;
+      r.out0 = b_start * 128;
+      r.n_emit = tab->n_active_blocks * 128;
+      r.n_zero_from = tab->n_zero_from;
+      s.lo = r.out0;
+      s.hi = r.out0 + r.n_emit;
+      rj.push_back(r);
+      continue;
+    }
+    if (v.loop) {
+      // Looping playback (:171-177, :197-234): runs until the stop time, duration only sets that stop time (:106-110).
+      int64_t loopEnd = v.loop_end > 0 ? (int64_t)(v.loop_end * (double)buf->rate) : buf->n;
+      loopEnd = std::min(loopEnd, buf->n);
+      const int64_t loopStart = std::min((int64_t)(v.loop_start * (double)buf->rate), loopEnd);
+      if (loopEnd - loopStart <= 0) return fail(GAC_ERR_UNSUPPORTED, "looping source with an empty loop region");
       job.pos0 = pos;
       job.out0 = b_start * 128;
       job.n_emit = max_blocks * 128;

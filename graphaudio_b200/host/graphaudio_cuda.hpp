@@ -350,6 +350,7 @@ class OfflineAudioContext {
     v.start_duration = s->duration_;
     v.stop_when = s->stop_;
     v.playback_rate = s->PlaybackRate.Value();
+    v.source_param = s->PlaybackRate.Desc();  // read when it carries automation events (k-rate, evaluated per quantum on the host)
     v.loop = s->Loop ? 1 : 0;  // any effective rate; an empty loop region answers GAC_ERR_UNSUPPORTED
     v.loop_start = std::max(0.0, s->LoopStart);
     v.loop_end = std::max(0.0, s->LoopEnd);

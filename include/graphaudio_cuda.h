@@ -213,7 +213,11 @@ typedef struct gac_voice_desc {
   double start_offset;
   double start_duration;
   double stop_when;         /* Stop(when); NaN = never called                                   */
-  float playback_rate;      /* PlaybackRate.Value (k-rate, no automation on this path)          */
+  float playback_rate;      /* PlaybackRate.Value (k-rate).  A PlaybackRate with automation events, or one whose Value was edited
+                               between Render calls (epochs), is passed in full as `source_param` (n_events > 0), which then takes
+                               precedence: evaluated per quantum on the host (Nodes/AudioBufferSourceNode.cs:165-169), the path
+                               (copy / CubicResampler) is chosen per quantum as the reference does.  A modulation input on it is
+                               GAC_ERR_UNSUPPORTED */
   int32_t n_ops;
   const gac_op_desc* ops;
   int32_t bus;              /* index into buses, or -1: connected straight to the destination   */
@@ -227,7 +231,8 @@ typedef struct gac_voice_desc {
   int32_t source_kind;      /* gac_source_kind (input == 0 only): what feeds the chain                                */
   double loop_start;        /* LoopStart in seconds (:49-53)                                     */
   double loop_end;          /* LoopEnd in seconds, 0 = end of the buffer (:58-62)                */
-  gac_param source_param;   /* CONSTANT: Offset (a-rate, Nodes/ConstantSourceNode.cs); OSCILLATOR: Frequency (a-rate, Hz)        */
+  gac_param source_param;   /* CONSTANT: Offset (a-rate, Nodes/ConstantSourceNode.cs); OSCILLATOR: Frequency (a-rate, Hz);
+                               BUFFER: PlaybackRate when n_events > 0 (k-rate; see playback_rate)                                 */
   int32_t oscillator_type;  /* OSCILLATOR: 0 sine, 1 square, 2 sawtooth, 3 triangle (Nodes/OscillatorNode.cs:207-213)            */
   int32_t reserved;
 } gac_voice_desc;

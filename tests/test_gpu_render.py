@@ -609,3 +609,75 @@ def test_distinct_contexts_render_concurrently_from_distinct_threads():
     assert not errors, errors
     for s in range(4):
         assert np.array_equal(got[s], want[s])
+
+
+@pytest.mark.parametrize("case", ["ramp", "steps_through_one", "looping_ramp", "set_target", "resampled_buffer"])
+def test_playback_rate_automation_is_evaluated_per_quantum(case):
+    """AudioBufferSourceNode.PlaybackRate is a k-rate AudioParam (Nodes/AudioBufferSourceNode.cs:76,165-169): its value at the start of
+    every quantum picks the path (copy at an effective rate of exactly 1, else CubicResampler — whose window and phase survive the
+    quanta in between) and the phase increment.  The host evaluates the schedule and replays the positions; bit-exact against the oracle."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+    fs_buf = 44100 if case == "resampled_buffer" else fs
+    src = [synth.splitmix_uniform(975 + c, 20000) for c in range(2)]
+
+    def build(api):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, fs_buf)
+        r = s.PlaybackRate
+        if case == "ramp":
+            r.SetValueAtTime(0.5, 0.0)
+            r.LinearRampToValueAtTime(2.0, 0.05)
+            r.ExponentialRampToValueAtTime(0.8, 0.12)
+        elif case == "steps_through_one":   # resampler -> copy path -> resampler (stale window) -> copy
+            r.Value = 0.75
+            r.SetValueAtTime(1.0, 0.02)
+            r.SetValueAtTime(1.5, 0.04)
+            r.SetValueAtTime(1.0, 0.06)
+            r.SetValueAtTime(0.3, 0.09)
+        elif case == "looping_ramp":
+            s.Loop = True
+            s.LoopStart, s.LoopEnd = 300.2 / fs, 2500.2 / fs
+            r.SetValueAtTime(1.0, 0.0)
+            r.SetValueAtTime(0.9, 0.03)
+            r.LinearRampToValueAtTime(3.0, 0.2)
+        elif case == "set_target":
+            r.Value = 2.0
+            r.SetTargetAtTime(0.5, 0.01, 0.03)
+        else:
+            r.SetValueAtTime(1.0, 0.0)
+            r.LinearRampToValueAtTime(1.2, 0.1)
+        g = api.GainNode(ctx)
+        g.Gain.Value = 0.5
+        s.Connect(g).Connect(ctx.Destination)
+        s.Start(0.004, 100.0 / fs_buf)
+        return ctx
+    n = 128 * 120
+    yg, yo = build(G).Render(n), build(O).Render(n)
+    assert np.count_nonzero(yo) > 4000
+    assert np.array_equal(yg, yo)
+
+
+def test_playback_rate_value_edited_between_render_calls():
+    """PlaybackRate.Value set between successive Render calls acts from the next unprocessed quantum on (an epoch of the parameter)."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    fs = 48000
+    src = [synth.splitmix_uniform(985 + c, 30000) for c in range(2)]
+
+    def run(api):
+        ctx = api.OfflineAudioContext(fs)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, fs)
+        s.Connect(ctx.Destination)
+        s.Start()
+        a = ctx.Render(128 * 20)
+        s.PlaybackRate.Value = 1.7
+        b = ctx.Render(128 * 20)
+        s.PlaybackRate.Value = 1.0
+        c = ctx.Render(128 * 20)
+        return np.concatenate([np.asarray(a), np.asarray(b), np.asarray(c)], axis=1)
+    yg, yo = run(G), run(O)
+    assert np.array_equal(yg, yo)

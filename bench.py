@@ -656,6 +656,7 @@ def run_ours(args, wl):
         if cpu:
             line["cpu_baseline"] = cpu
         line["e2e"]["ms_per_step_quartiles"] = [float(x) * 1e3 for x in np.percentile(lat, [0, 25, 50, 75, 100])]  # this rank's steps
+        line["e2e"]["ms_per_step_all"] = [round(float(x) * 1e3, 3) for x in lat]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

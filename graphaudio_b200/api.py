@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import itertools
 import math
+import struct
 from typing import List, Optional
 
 import numpy as np
@@ -179,17 +180,19 @@ class AudioParam:
 
     def __init__(self, default, mn, mx):
         self.DefaultValue, self.MinValue, self.MaxValue = float(default), float(mn), float(mx)
-        self._value = np.float32(default)
+        r = AudioParam._RANGES.get((default, mn, mx))
+        if r is None:  # (default, min, max) rounded to float32, once per distinct triple (Math.Clamp works on floats)
+            r = AudioParam._RANGES[(default, mn, mx)] = (float(np.float32(default)), float(np.float32(mn)), float(np.float32(mx)))
+        self._value, self._mn32, self._mx32 = r  # Python floats that hold float32 values
         self._events: List[tuple] = []  # (type, value, target, time, time_constant)
         # (first quantum, value, events) as each Render call saw the parameter: edits made between successive Render calls act from
         # the next unprocessed quantum on (OfflineAudioContext.cs:55-100), earlier quanta keep what they were rendered with
         self._epochs: List[tuple] = []
-        self._minmax32 = None    # (MinValue, MaxValue) rounded to float32, cached for _desc
         self._input_node = None  # the parameter's own fan-in (AudioParam.cs:60-62), created by the first AudioNode.Connect(param)
 
     def _clamp(self, v):
-        v = np.float32(v)
-        return np.float32(min(max(v, np.float32(self.MinValue)), np.float32(self.MaxValue)))
+        v = float(np.float32(v))
+        return self._mn32 if v < self._mn32 else (self._mx32 if v > self._mx32 else v)
 
     @property
     def Value(self):
@@ -201,6 +204,9 @@ class AudioParam:
         self._events = []
 
     def _add(self, ev):  # AddEvent :333-352, stable upper-bound insert
+        if not self._events or not ev[3] < self._events[-1][3]:  # (the usual case: scheduled in time order)
+            self._events.append(ev)
+            return
         lo, hi = 0, len(self._events)
         while lo < hi:
             mid = (lo + hi) >> 1
@@ -230,7 +236,7 @@ class AudioParam:
 
     def _commit(self, q_now: int):
         """Called when a graph is flattened for a render that starts at quantum q_now."""
-        state = (float(self._value), tuple(self._events))
+        state = (self._value, tuple(self._events))
         if not self._epochs:
             self._epochs = [(0,) + state]
         elif state != self._epochs[-1][1:]:
@@ -239,30 +245,48 @@ class AudioParam:
             else:  # edited again before anything further was rendered
                 self._epochs[-1] = (self._epochs[-1][0],) + state
 
+    _RANGES = {}
+    _EVENT_ARRAYS = {}  # n -> (gac_event * n, struct.Struct of n events): array types and packers are built once per length
+
     def _desc(self, keep: list, q_now: int = 0) -> N.gac_param:
-        self._commit(q_now)
-        flat = []
-        for k, (q0, value, events) in enumerate(self._epochs):
-            if k > 0:
-                flat.append((N.GAC_EVENT_EPOCH, value, 0.0, 0.0, float(q0)))
-            flat.extend(events)
-        mm = self._minmax32
-        if mm is None:
-            mm = self._minmax32 = (float(np.float32(self.MinValue)), float(np.float32(self.MaxValue)))
         mod_bus = 0
         if self._input_node is not None and self._input_node._in:
             mod_bus = self._input_node._bus_index + 1  # (set by the flattening of the graph this parameter belongs to)
+        eps = self._epochs
+        if not self._events and (not eps or (len(eps) == 1 and eps[0][1] == self._value and not eps[0][2])):
+            # a plain value that was never scheduled or edited (most parameters of a graph): nothing to flatten
+            if not eps:
+                self._epochs = [(0, self._value, ())]
+            return N.gac_param(self._value, 0, None, mod_bus, self._mn32, self._mx32)
+        self._commit(q_now)
+        eps = self._epochs
+        if len(eps) == 1:
+            flat = eps[0][2]
+        else:
+            flat = []
+            for k, (q0, value, events) in enumerate(eps):
+                if k > 0:
+                    flat.append((N.GAC_EVENT_EPOCH, value, 0.0, 0.0, float(q0)))
+                flat.extend(events)
         arr = None
-        if flat:
-            arr = (N.gac_event * len(flat))(*flat)  # (type, value, target, time, time_constant): the struct's field order
+        n = len(flat)
+        if n:
+            ta = AudioParam._EVENT_ARRAYS.get(n)
+            if ta is None:
+                ta = AudioParam._EVENT_ARRAYS[n] = (N.gac_event * n, struct.Struct("<" + "iffxxxxdd" * n))
+            # (type, value, target, time, time_constant): the struct's field order, packed in one call (a ctypes array built from
+            # tuples converts field by field: 5 us instead of 1.3 for four events, ~400 parameters per 128-voice graph)
+            arr = ta[0].from_buffer_copy(ta[1].pack(*[x for e in flat for x in e]))
             keep.append(arr)
-        # positional initialiser: value, n_events, events, mod_bus, min_value, max_value (one call instead of six attribute writes:
-        # flattening a 128-voice graph builds ~500 of these inside the end-to-end step)
-        return N.gac_param(self._epochs[0][1], len(flat), arr, mod_bus, mm[0], mm[1])
+        # positional initialiser: value, n_events, events, mod_bus, min_value, max_value
+        return N.gac_param(eps[0][1], n, arr, mod_bus, self._mn32, self._mx32)
 
 
 class AudioNode:
     """Nodes/AudioNode.cs — records connections; Connect returns the destination to allow chaining (:68-73)."""
+    _is_source = False   # AudioBufferSourceNode / scheduled sources: the head of a voice
+    _force_bus = False   # nodes that always start a bus, whatever their number of inputs (set per instance)
+    _accelerated = False  # node types the device path renders (anything else must never render as silence: the graph is refused)
 
     def __init__(self, context: "OfflineAudioContext", n_inputs=1, n_outputs=1):
         self.Context = context
@@ -327,10 +351,17 @@ class AudioNode:
         return self
 
     def _params(self):
-        ps = self.__dict__.get("_param_list")
-        if ps is None:  # (a node's parameters are created by its constructor: the list is built once)
-            ps = self._param_list = [v for v in self.__dict__.values() if isinstance(v, AudioParam)]
-        return ps
+        # a node's parameters are created by its constructor, under the same attribute names for every instance of the class: the
+        # names are found once per class (scanning __dict__ per node cost 1 ms per 128-voice graph)
+        cls = type(self)
+        names = cls.__dict__.get("_param_names")
+        if names is None:
+            names = tuple(k for k, v in self.__dict__.items() if isinstance(v, AudioParam))
+            cls._param_names = names
+        if not names:
+            return ()
+        d = self.__dict__
+        return [d[k] for k in names]
 
     def Disconnect(self, destination: Optional["AudioNode"] = None):
         q = self.Context._q_now()
@@ -356,11 +387,14 @@ class AudioNode:
 
 
 class AudioDestinationNode(AudioNode):
+    _accelerated = True
     def __init__(self, context):
         super().__init__(context, 1, 0)
 
 
 class AudioBufferSourceNode(AudioNode):
+    _accelerated = True
+    _is_source = True
     def __init__(self, context):
         super().__init__(context, 0, 1)
         self.PlaybackRate = AudioParam(1.0, 0.001, 1000.0)  # k-rate, Nodes/AudioBufferSourceNode.cs:76
@@ -423,6 +457,7 @@ class AudioBufferSourceNode(AudioNode):
 
 
 class BiQuadFilterNode(AudioNode):
+    _accelerated = True
     def __init__(self, context):
         super().__init__(context)
         self._type = FilterType.Lowpass
@@ -443,6 +478,7 @@ class BiQuadFilterNode(AudioNode):
 
 
 class GainNode(AudioNode):
+    _accelerated = True
     def __init__(self, context):
         super().__init__(context)
         fmax = float(np.finfo(np.float32).max)
@@ -450,6 +486,7 @@ class GainNode(AudioNode):
 
 
 class DelayNode(AudioNode):
+    _accelerated = True
     """Nodes/DelayNode.cs — integer-sample delay, a-rate DelayTime in seconds."""
 
     def __init__(self, context, maxDelayTime=1.0):
@@ -461,6 +498,7 @@ class DelayNode(AudioNode):
 
 
 class StereoPannerNode(AudioNode):
+    _accelerated = True
     """Nodes/StereoPannerNode.cs — equal-power pan, a-rate Pan in [-1, 1]."""
 
     def __init__(self, context):
@@ -486,6 +524,7 @@ class _Gate:
 
 
 class _ParamInputNode(AudioNode):
+    _accelerated = True
     """The AudioNodeInput an AudioParam owns (Explicit, one channel: AudioParam.cs:60-62): what AudioNode.Connect(param) connects
     to.  Flattened into a GAC_BUS_MONO_INPUT bus that feeds nothing but the parameter."""
 
@@ -496,6 +535,8 @@ class _ParamInputNode(AudioNode):
 
 
 class _ScheduledSourceNode(AudioNode):
+    _accelerated = True
+    _is_source = True
     """IAudioScheduledSourceNode: Start(when, offset, duration = NaN) / Stop(when), sample-accurate inside a quantum
     (Nodes/OscillatorNode.cs:54-89, Nodes/ConstantSourceNode.cs:38-73)."""
 
@@ -532,6 +573,7 @@ class ConstantSourceNode(_ScheduledSourceNode):  # Nodes/ConstantSourceNode.cs
 
 
 class _SplitterOutput(AudioNode):
+    _accelerated = True
     """Output `index` of a ChannelSplitterNode: channel `index` of the splitter's input as a one-channel signal (GAC_OP_CHANNEL)."""
 
     def __init__(self, context, index):
@@ -540,6 +582,7 @@ class _SplitterOutput(AudioNode):
 
 
 class ChannelSplitterNode(AudioNode):
+    _accelerated = True
     """Nodes/ChannelSplitterNode.cs.  Flattened as: the splitter's input becomes a bus (no ops), every used output a chain fed
     by that bus that starts with GAC_OP_CHANNEL."""
 
@@ -560,6 +603,7 @@ class ChannelSplitterNode(AudioNode):
 
 
 class ChannelMergerNode(AudioNode):
+    _accelerated = True
     """Nodes/ChannelMergerNode.cs: output channel i = channel 0 of what input i mixes.  Flattened into a bus whose inputs carry
     their merger input (gac_bus_desc.input_slots); two inputs at most on the accelerated path."""
 
@@ -572,6 +616,7 @@ class ChannelMergerNode(AudioNode):
 
 
 class ConvolverNode(AudioNode):
+    _accelerated = True
     def __init__(self, context):
         super().__init__(context)
         self.Normalize = True          # Nodes/ConvolverNode.cs:87
@@ -832,9 +877,7 @@ class OfflineAudioContext:
                 if prm._input_node is not None and prm._input_node._in:
                     stack.append(prm._input_node)
             # a node type the device path does not accelerate must never render as silence: refuse the whole graph
-            if not isinstance(n, (AudioDestinationNode, AudioBufferSourceNode, BiQuadFilterNode, GainNode, ConvolverNode, DelayNode,
-                                  StereoPannerNode, _ScheduledSourceNode, _ParamInputNode, ChannelSplitterNode, _SplitterOutput,
-                                  ChannelMergerNode)):
+            if not n._accelerated:
                 raise NotSupportedException(f"{type(n).__name__} is outside the accelerated path (SURVEY.md §8f-3; the CPU oracle has it)")
             if isinstance(n, ChannelMergerNode) and any(sl > 2 for sl in n._slots.values()):
                 raise NotSupportedException("ChannelMergerNode inputs beyond the second are outside the accelerated path (signals carry two channels)")
@@ -850,13 +893,13 @@ class OfflineAudioContext:
             return [d for d in n._out if id(d) in live]
 
         def is_src(n):
-            return isinstance(n, (AudioBufferSourceNode, _ScheduledSourceNode))
+            return n._is_source
 
         def ops_of(chain):  # nodes that only shape the flattening (fan-in points without a node behind them) carry no op
             return [n for n in chain if not isinstance(n, (_ParamInputNode, ChannelSplitterNode, ChannelMergerNode))]
 
         def fan_in(n):  # starts a bus
-            return n is not dest and not is_src(n) and (len(n._in) != 1 or getattr(n, "_force_bus", False))
+            return n is not dest and not n._is_source and (len(n._in) != 1 or n._force_bus)
 
         voices, bus_ops, bus_targets, bus_inputs, dest_inputs = [], [], [], [], []
         bus_of_head = {}   # id(fan-in node or materialised tail) -> bus index
@@ -935,7 +978,7 @@ class OfflineAudioContext:
         for n in self._nodes:
             if id(n) not in live or not fan_in(n):
                 continue
-            if len(n._in) == 0 and not getattr(n, "_force_bus", False):
+            if len(n._in) == 0 and not n._force_bus:
                 continue  # nothing connected: contributes silence (its consumers see a missing input)
             ch = chain_from(n)
             b = new_bus(ops_of(ch))
@@ -965,6 +1008,7 @@ class OfflineAudioContext:
                 if isinstance(n, ChannelMergerNode):
                     self._bus_slots[b] = [n._slots.get(id(u), 0) for u in n._in if (id(u), id(n)) in edge_code]
         # materialised fan-out buses keep the single input recorded in emit()
+        emit = branch = None  # (the two closures refer to each other: cut the cycle, or every flattening leaves its lists to the collector)
         return [tuple(v) for v in voices], bus_ops, dest_inputs, bus_targets, bus_inputs
 
     def _topology(self):
@@ -1228,6 +1272,14 @@ class OfflineAudioContext:
             else:
                 L.gac_context_destroy(self._h)
             self._h = None
+        # The recorded graph is a web of mutual references (node <-> node, node -> context -> node): left alone it is cyclic garbage
+        # that only the generational collector frees — one OfflineAudioContext per render (the reference's usual pattern) then pays a
+        # full collection of ~40 000 objects every tenth 128-voice render (+10 ms).  Cut the web here; reference counting does the rest.
+        nodes, self._nodes = self._nodes, []
+        for n in nodes:
+            n._in, n._out = [], []
+            for prm in n._params():
+                prm._input_node = None
 
     def __del__(self):
         try:

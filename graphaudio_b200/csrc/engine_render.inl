@@ -650,6 +650,10 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
 
   const int B = ctx->B;
   const int64_t total = a.first_frame + a.n_frames;
+  if (ctx->kick_pending) {  // impulse responses prepared ahead of this render: their staged job tables must have been read
+    cudaEventSynchronize(ctx->kick_done);
+    ctx->kick_pending = false;
+  }
   ctx->stage_block = 0;
   ctx->stage_used = 0;  // the previous render has synchronised: its staged job tables are dead
   ctx->pending.n = 0;
@@ -774,11 +778,14 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
     cuts.push_back(0);
     if (v_ready < S0 && S0 >= 16) {
       if (v_ready >= 4) cuts.push_back(v_ready);
-      // the rest in three batches: each one is queued while its uploads are still in flight.  (Halving batches down to two or three
-      // voices were measured too: the fixed cost of six more launches outweighs the shorter last batch, 0.74 vs 0.62 ms behind the
-      // last upload on the 64-voice bench workload.)
+      // the rest in up to three batches: each one is queued while its uploads are still in flight.  (Halving batches down to two or
+      // three voices were measured too: the fixed cost of six more launches outweighs the shorter last batch, 0.74 vs 0.62 ms behind
+      // the last upload on the 64-voice bench workload.)  A small rest is ONE batch: the landed prefix keeps the device busy longer
+      // than the rest needs to arrive, and every further batch adds its fixed cost behind the last upload (C3 shard, 21 of 128 voices
+      // in flight at the call: 3.65 ms of device time in four batches).
       const size_t rest = S0 - cuts.back();
-      const size_t chunk = std::max<size_t>(4, (rest + 2) / 3);
+      const size_t n_rest = rest * 3 <= S0 ? 1 : (rest * 2 <= S0 ? 2 : 3);
+      const size_t chunk = std::max<size_t>(4, (rest + n_rest - 1) / n_rest);
       for (size_t v = cuts.back() + chunk; v < S0; v += chunk) cuts.push_back(v);
     }
     cuts.push_back(S0);
@@ -1792,6 +1799,10 @@ extern "C" int gac_biquad_batch(gac_context* ctx, const float* x, int n_signals,
   CU(cudaMemsetAsync(dx.p, 0, (size_t)n_signals * 2 * Npad * 4, ctx->stream));
   CU(cudaMemcpy2DAsync(dx.p, (size_t)Npad * 4, x, (size_t)n_frames * 4, (size_t)n_frames * 4, (size_t)n_signals * 2, cudaMemcpyHostToDevice, ctx->stream));
   {
+    if (ctx->kick_pending) {
+      cudaEventSynchronize(ctx->kick_done);
+      ctx->kick_pending = false;
+    }
     ctx->stage_block = 0;
     ctx->stage_used = 0;
     RenderEnv env;

@@ -533,6 +533,9 @@ def run_ours(args, wl):
 
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
     e2e_ms, lat = e2e_arm(not args.sync_upload, e2e_steps, 2)
+    # the end-to-end arm renders the same graph as the resident arm (fresh context, uploads in flight, voice batches, impulse
+    # responses prepared on the way): its last result against the resident arm's
+    e2e_err = float(np.abs(out_host - timed_result).max()) if rank == 0 else 0.0
     e2e_other_ms, _ = e2e_arm(args.sync_upload, max(2, e2e_steps // 2), 1)  # the other upload mode, beside the headline
 
     # ---- cpu baseline (rank 0, N = 1 only): bounded sample of the same workload on the host
@@ -614,7 +617,7 @@ def run_ours(args, wl):
             "bus_peak": bus_peak,
             "e2e": {"value": V * wl["render_s"] / (e2e_ms * 1e-3), "unit": "voice-s/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(V * h2d_bytes / max(1, nvox)), "d2h_bytes_per_step": d2h_bytes,
-                    "async_upload": not args.sync_upload, "steps": e2e_steps,
+                    "async_upload": not args.sync_upload, "steps": e2e_steps, "vs_resident_max_err": e2e_err,
                     ("sync_upload_ms_per_step" if not args.sync_upload else "async_upload_ms_per_step"): e2e_other_ms,
                     "h2d_gb_per_s_per_rank": h2d_bytes / (e2e_ms * 1e-3) / 1e9,
                     "note": ("communicator bootstrap outside the timed region; " if world > 1 else "") +

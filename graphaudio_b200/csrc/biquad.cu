@@ -6,7 +6,7 @@
 //   k_biquad_select   parallel over quanta   the hysteresis walk (usedFreq restarts at 1000 Hz in EVERY block, :13-14,111-112;
 //                                            channel 1 inherits channel 0's end state): for every (channel, frame) the frame
 //                                            whose (f, Q) produced the coefficients in force, or -1 = "what the block started with"
-//   k_biquad_entry    one thread per voice   which coefficient set the reference's fields hold when a quantum starts
+//   k_biquad_entry    one CTA per voice      which coefficient set the reference's fields hold when a quantum starts
 //   k_biquad_resolve  parallel over frames   RBJ (glibc-exact sinf/cosf, :149-258) of the frame in force; writes (b0, b1, b2) per
 //                                            (channel, frame) and the slab-transposed stream (x, a1, a2) the lanes read
 //   k_biquad_lanes    one lane per (voice, channel): w = x - a1*w1 - a2*w2 (:137) is the sequential chain, y = b0*w + b1*w1 +
@@ -148,31 +148,47 @@ __global__ void __launch_bounds__(kSelWarps * 32) k_biquad_select(const BiquadJo
 
 // K3b: which coefficient set the reference's fields (_b0.._a2) hold when channel c of quantum b starts.
 // ent[c][b] = frame index whose (f, Q) applies, or -1 (only before the very first recompute).  A "last recompute so far"
-// scan over the quanta: one warp per job, every lane owns a contiguous chunk of quanta (chunk summary, carry across the
-// lanes by shuffles, replay).
-__global__ void __launch_bounds__(32) k_biquad_entry(int n_jobs, int64_t n_quanta, const int32_t* __restrict__ last_base,
-                                                     int32_t* __restrict__ ent_base) {
-  const int jid = blockIdx.x, lane = threadIdx.x;
+// scan over the quanta: one CTA per job, every thread owns a short contiguous run of quanta (run summary, exclusive scan of the
+// summaries over the CTA with the operator "the right-most one that recomputed at all", replay).
+constexpr int kEntThreads = 512;
+__global__ void __launch_bounds__(kEntThreads) k_biquad_entry(int n_jobs, int64_t n_quanta, const int32_t* __restrict__ last_base,
+                                                              int32_t* __restrict__ ent_base) {
+  const int jid = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (jid >= n_jobs) return;
   const int32_t* last0 = last_base + (size_t)jid * 2 * n_quanta;
   const int32_t* last1 = last0 + n_quanta;
   int32_t* ent0 = ent_base + (size_t)jid * 2 * n_quanta;
   int32_t* ent1 = ent0 + n_quanta;
-  const int64_t chunk = (n_quanta + 31) / 32;
-  const int64_t b_lo = lane * chunk, b_hi = (b_lo + chunk < n_quanta) ? b_lo + chunk : n_quanta;
-  // summary of the chunk: the last recompute inside it (channel 1's wins over channel 0's within a quantum), or -2 = none
+  const int64_t chunk = (n_quanta + kEntThreads - 1) / kEntThreads;
+  const int64_t b_lo = tid * chunk < n_quanta ? tid * chunk : n_quanta, b_hi = (b_lo + chunk < n_quanta) ? b_lo + chunk : n_quanta;
+  // summary of the run: the last recompute inside it (channel 1's wins over channel 0's within a quantum), or -2 = none
   int32_t tail = -2;
   for (int64_t b = b_lo; b < b_hi; b++) {
     const int32_t l0 = last0[b], l1 = last1[b];
     if (l0 >= 0) tail = l0;
     if (l1 >= 0) tail = l1;
   }
-  // carry into this lane = summary of the nearest lower lane that recomputed at all, else -1
-  int32_t cur = -1;
-  for (int src = 0; src < 31; src++) {
-    const int32_t t = __shfl_sync(0xffffffffu, tail, src);
-    if (src < lane && t != -2) cur = t;
+  // inclusive scan inside the warp, then across the warps
+  int32_t inc = tail;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d && inc == -2) inc = t;
   }
+  __shared__ int32_t warp_tail[kEntThreads / 32];
+  if (lane == 31) warp_tail[warp] = inc;
+  __syncthreads();
+  // carry into this thread = summary of the nearest lower thread that recomputed at all, else -1
+  int32_t cur = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) cur = -2;
+  if (cur == -2) {
+    for (int w = warp - 1; w >= 0; w--)
+      if (warp_tail[w] != -2) {
+        cur = warp_tail[w];
+        break;
+      }
+  }
+  if (cur == -2) cur = -1;
   for (int64_t b = b_lo; b < b_hi; b++) {
     ent0[b] = cur;                      // channel 0 starts from the fields as the previous block left them
     const int32_t l0 = last0[b];
@@ -398,7 +414,7 @@ void launch_biquad_classes(const BiquadJob* d_reps, int n_classes, int64_t n_fra
   if (n_classes <= 0 || n_frames <= 0) return;
   cudaMemsetAsync(d_wide_scratch, 0, sizeof(int) * ((n_classes + 15) / 16), s);
   k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_classes), kSelWarps * 32, 0, s>>>(d_reps, sample_rate, n_quanta, n_frames, d_last, d_wide_scratch);
-  k_biquad_entry<<<(unsigned)n_classes, 32, 0, s>>>(n_classes, n_quanta, d_last, d_ent);
+  k_biquad_entry<<<(unsigned)n_classes, kEntThreads, 0, s>>>(n_classes, n_quanta, d_last, d_ent);
   k_biquad_class_coef<<<dim3((unsigned)(n_frames / kBqChunkFrames), (unsigned)n_classes), kBqChunkFrames, 0, s>>>(d_reps, sample_rate, n_quanta, n_frames, d_ent, d_cs, cs_stride);
 }
 void launch_biquad_zero_outside(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, cudaStream_t s) {
@@ -414,7 +430,7 @@ void launch_biquad(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, int64_
   int* d_wide = d_flags + groups;  // [groups] stream layout flags, set by the select pass (layout of d_flags: biquad_lanes.cu)
   cudaMemsetAsync(d_wide, 0, sizeof(int) * groups, s);
   k_biquad_select<<<dim3((unsigned)((n_quanta + kSelWarps - 1) / kSelWarps), (unsigned)n_jobs), kSelWarps * 32, 0, s>>>(d_jobs, sample_rate, n_quanta, n_frames, d_last, d_wide);
-  k_biquad_entry<<<(unsigned)n_jobs, 32, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
+  k_biquad_entry<<<(unsigned)n_jobs, kEntThreads, 0, s>>>(n_jobs, n_quanta, d_last, d_ent);
   k_biquad_resolve<<<dim3((n_slabs + kResSlabs - 1) / kResSlabs, (unsigned)groups), 512, 0, s>>>(d_jobs, n_jobs, sample_rate, n_quanta, n_frames, d_ent, d_s1t, d_s2t, d_wide);
   launch_biquad_lanes(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, d_states, d_flags, s);
 }

@@ -501,21 +501,30 @@ __global__ void __launch_bounds__(64) k_biquad_lanes_shared(const BiquadJob* __r
 }
 
 // first_bad[g] = first segment k >= 1 whose speculative start state differs (bitwise, any of the 32 rows) from the state
-// segment k-1 ended with (n_seg if the whole chain verifies); link_bad[g][k] says so for every link.  One warp per group.
-__global__ void __launch_bounds__(32) k_biquad_verify(int n_seg, const float2* __restrict__ states, int* __restrict__ first_bad,
-                                                      int* __restrict__ link_bad) {
-  const int lane = threadIdx.x;
+// segment k-1 ended with (n_seg if the whole chain verifies); link_bad[g][k] says so for every link.  One CTA per group, the links
+// dealt out to its warps.
+constexpr int kVerifyWarps = 8;
+__global__ void __launch_bounds__(kVerifyWarps * 32) k_biquad_verify(int n_seg, const float2* __restrict__ states, int* __restrict__ first_bad,
+                                                                     int* __restrict__ link_bad) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint2* st = reinterpret_cast<const uint2*>(states) + (size_t)blockIdx.x * n_seg * 64;
+  __shared__ int s_bad[kVerifyWarps];
   int bad = n_seg;
-  if (lane == 0) link_bad[(size_t)blockIdx.x * n_seg] = 0;
-  for (int k = 1; k < n_seg; k++) {
+  if (threadIdx.x == 0) link_bad[(size_t)blockIdx.x * n_seg] = 0;
+  for (int k = 1 + warp; k < n_seg; k += kVerifyWarps) {
     const uint2 e = st[((size_t)(k - 1) * 2 + 1) * 32 + lane];
     const uint2 b = st[((size_t)k * 2 + 0) * 32 + lane];
     const bool differ = __any_sync(0xffffffffu, e.x != b.x || e.y != b.y);
-    if (differ && bad == n_seg) bad = k;
+    if (differ && bad == n_seg) bad = k;  // (k ascends inside a warp: the first one found is the warp's smallest)
     if (lane == 0) link_bad[(size_t)blockIdx.x * n_seg + k] = differ ? 1 : 0;
   }
-  if (lane == 0) first_bad[blockIdx.x] = bad;
+  if (lane == 0) s_bad[warp] = bad;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = n_seg;
+    for (int w = 0; w < kVerifyWarps; w++) m = s_bad[w] < m ? s_bad[w] : m;
+    first_bad[blockIdx.x] = m;
+  }
 }
 
 // warm-up of a speculative segment in 32-frame slabs (GAC_BIQUAD_WARM_SLABS overrides the default for measurements)
@@ -600,7 +609,7 @@ void launch_biquad_lanes_shared(const BiquadJob* d_jobs, const BqGroup* d_groups
   k_biquad_lanes_shared<false><<<dim3(groups, (unsigned)n_seg), 64, kShSmem, s>>>(d_jobs, d_groups, d_cs, cs_stride, n_frames, seg_chunks, n_seg,
                                                                                  warm, d_states, d_slab, nullptr, nullptr);
   if (n_seg > 1) {
-    k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad, d_link);
+    k_biquad_verify<<<groups, kVerifyWarps * 32, 0, s>>>(n_seg, d_states, d_first_bad, d_link);
     k_biquad_lanes_shared<true><<<groups, 64, kShSmem, s>>>(d_jobs, d_groups, d_cs, cs_stride, n_frames, seg_chunks, n_seg, warm, d_states, d_slab,
                                                             d_first_bad, d_link);
   }
@@ -623,7 +632,7 @@ void launch_biquad_lanes(const BiquadJob* d_jobs, int n_jobs, int64_t n_frames, 
   k_biquad_lanes<false, false><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, nullptr, d_wide, nullptr);
   k_biquad_lanes<false, true><<<dim3(groups, (unsigned)n_seg), 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, nullptr, d_wide, nullptr);
   if (n_seg > 1) {
-    k_biquad_verify<<<groups, 32, 0, s>>>(n_seg, d_states, d_first_bad, d_link);
+    k_biquad_verify<<<groups, kVerifyWarps * 32, 0, s>>>(n_seg, d_states, d_first_bad, d_link);
     k_biquad_lanes<true, false><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, d_first_bad, d_wide, d_link);
     k_biquad_lanes<true, true><<<groups, 32, kLanesSmem, s>>>(d_jobs, n_jobs, n_frames, d_s1t, d_s2t, seg_slabs, n_seg, warm_slabs(), d_states, d_slab, d_first_bad, d_wide, d_link);
   }

@@ -112,9 +112,21 @@ __device__ __forceinline__ float eval_interval(float value, const DevEvent* __re
 
 // a-rate: a thread evaluates 16 consecutive frames (four float4 stores); k-rate: one quantum per thread
 constexpr int kParamFrames = 16;
+constexpr int kParamSmemEvents = 32;  // event lists up to this length are staged in shared memory (32 bytes per event)
+static_assert(sizeof(DevEvent) == 32, "DevEvent is staged as two int4 words");
 __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__ jobs, const double* __restrict__ block_time,
                                                     int64_t n_quanta, int sample_rate) {
   const ParamJob job = jobs[blockIdx.y];
+  // The CTA's threads walk the same event list: short lists are staged in shared memory first (resolving the interval is a chain of
+  // dependent loads — long-scoreboard stalls were the kernel's top stall reason with the list in global memory).
+  __shared__ int4 s_ev[2 * kParamSmemEvents];
+  const DevEvent* __restrict__ ev = job.events;
+  if (job.n_events > 0 && job.n_events <= kParamSmemEvents) {  // (uniform over the CTA)
+    const int4* __restrict__ src = reinterpret_cast<const int4*>(job.events);
+    for (int w = threadIdx.x; w < 2 * job.n_events; w += 256) s_ev[w] = src[w];
+    __syncthreads();
+    ev = reinterpret_cast<const DevEvent*>(s_ev);
+  }
   const double dt = 1.0 / (double)sample_rate;  // AudioParam.cs:116
   int i = 0;
   Rec rec;
@@ -130,8 +142,8 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
     // correction step (q = a r; q += fma(-q, b, a) r: the correctly rounded quotient).
     {
       const double t_first = t0 + (double)f0 * dt, t_last = t0 + (double)(f0 + kParamFrames - 1) * dt;
-      advance_interval(job.events, job.n_events, t_first, i, boundary);
-      if (i >= job.n_events || t_last < job.events[i].time) {
+      advance_interval(ev, job.n_events, t_first, i, boundary);
+      if (i >= job.n_events || t_last < ev[i].time) {
         const int count = job.n_events;
         int mode = 0;  // 0 constant, 1 linear, 2 exponential ramp, 3 SetTarget
         float cval = job.value, v0 = 0.f, dv = 0.f, tgt = 0.f;
@@ -142,7 +154,7 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
             if (i == 0) {
               cval = boundary;
             } else {
-              const DevEvent e = job.events[i], prev = job.events[i - 1];
+              const DevEvent e = ev[i], prev = ev[i - 1];
               if (e.type == 1 || (e.type == 2 && (prev.value <= 0.f || e.value <= 0.f))) {
                 mode = 1;
                 v0 = prev.value;
@@ -159,13 +171,13 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
               } else if (prev.type != 3) {
                 cval = prev.value;
               } else {
-                st = &job.events[i - 1];
+                st = &ev[i - 1];
               }
             }
-          } else if (job.events[count - 1].type != 3) {
-            cval = job.events[count - 1].value;
+          } else if (ev[count - 1].type != 3) {
+            cval = ev[count - 1].value;
           } else {
-            st = &job.events[count - 1];
+            st = &ev[count - 1];
           }
           if (st) {
             mode = 3;
@@ -231,9 +243,9 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
       for (int e = 0; e < 4; e++) {
         const double t = t0 + (double)((int)(n & 127) + 4 * e4 + e) * dt;  // :120
         const int before = i;
-        advance_interval(job.events, job.n_events, t, i, boundary);
+        advance_interval(ev, job.n_events, t, i, boundary);
         if (i != before) rec.i = -2;  // a new interval starts its own recurrence
-        v[e] = eval_interval(job.value, job.events, job.n_events, i, boundary, t, dt, rec);
+        v[e] = eval_interval(job.value, ev, job.n_events, i, boundary, t, dt, rec);
       }
       *reinterpret_cast<float4*>(job.out + n + 4 * e4) = make_float4(v[0], v[1], v[2], v[3]);
     }
@@ -241,8 +253,8 @@ __global__ void __launch_bounds__(256) k_param_eval(const ParamJob* __restrict__
     const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (b >= n_quanta || b < job.q_lo || b >= job.q_hi) return;
     const double t = block_time[b];
-    advance_interval(job.events, job.n_events, t, i, boundary);
-    job.out[b] = eval_interval(job.value, job.events, job.n_events, i, boundary, t, dt, rec);  // ComputeKRate :144-146
+    advance_interval(ev, job.n_events, t, i, boundary);
+    job.out[b] = eval_interval(job.value, ev, job.n_events, i, boundary, t, dt, rec);  // ComputeKRate :144-146
   }
 }
 

@@ -16,7 +16,7 @@ It follows the reference's own structure (pull graph, one 128-frame block at a t
   AudioNode.ProcessInternal            Nodes/AudioNode.cs:152-183
   AudioNodeInput.Pull / MixBuffer      AudioNodeInput.cs:100-244
   AudioParam                           AudioParam.cs:93-352
-  AudioBufferSourceNode                Nodes/AudioBufferSourceNode.cs:79-402 (no looping)
+  AudioBufferSourceNode                Nodes/AudioBufferSourceNode.cs:79-402 (incl. Loop / LoopStart / LoopEnd on both paths)
   CubicResampler                       CubicResampler.cs:19-97
   BiQuadFilterNode                     Nodes/BiQuadFilterNode.cs:87-258
   GainNode                             Nodes/GainNode.cs:29-61
@@ -634,7 +634,7 @@ class CubicResampler:
         return ip, op
 
 
-class AudioBufferSourceNode(AudioNode):   # Nodes/AudioBufferSourceNode.cs (Loop = false)
+class AudioBufferSourceNode(AudioNode):   # Nodes/AudioBufferSourceNode.cs
     def __init__(self, context):
         super().__init__(context, 0, 1)
         self.PlaybackRate = self._param(1.0, 0.001, 1000.0, a_rate=False)
@@ -645,6 +645,10 @@ class AudioBufferSourceNode(AudioNode):   # Nodes/AudioBufferSourceNode.cs (Loop
         self._position = 0
         self._resamplers = None
         self._out = None
+        self.Loop = False                 # :40-44
+        self.LoopStart = 0.0              # :49-53 (seconds; the setter clamps at 0)
+        self.LoopEnd = 0.0                # :58-62 (0 = end of the buffer)
+        self._wrap = None                 # _loopWrapBuffer, 512 floats (:247-250)
 
     def Start(self, when=0.0, offset=0.0, duration=math.inf):  # :79-114
         if self._started:
@@ -692,16 +696,24 @@ class AudioBufferSourceNode(AudioNode):   # Nodes/AudioBufferSourceNode.cs (Loop
         else:
             dur_end = buf.Length
         dur_end = min(dur_end, buf.Length)
+        loop = bool(self.Loop)
+        loop_start = int(max(0.0, self.LoopStart) * buf.SampleRate)                   # :171
+        loop_end = int(max(0.0, self.LoopEnd) * buf.SampleRate) if self.LoopEnd > 0 else buf.Length  # :172-174
+        loop_end = min(loop_end, buf.Length)                                          # :176
+        loop_start = min(loop_start, loop_end)                                        # :177
         more = False
         if eff == 1.0:                    # :186-235
             for ch in range(nch):
                 data, row = buf.channels[ch], self._out.data[ch]
                 pos, oi = self._position, 0
                 while oi < FRAMES:
-                    if pos >= dur_end:
+                    if loop and pos >= loop_end:                                      # :197-200
+                        pos = loop_start
+                    if pos >= dur_end and not loop:                                   # :202-206
                         row[oi:] = 0
                         break
-                    avail = int(min(min(dur_end, buf.Length) - pos, FRAMES - oi))
+                    end = loop_end if loop else min(dur_end, buf.Length)              # :208
+                    avail = int(min(end - pos, FRAMES - oi))
                     if avail <= 0:
                         row[oi:] = 0
                         break
@@ -709,7 +721,9 @@ class AudioBufferSourceNode(AudioNode):   # Nodes/AudioBufferSourceNode.cs (Loop
                     pos += avail
                     oi += avail
                     more = True
-            self._position += FRAMES
+            self._position += FRAMES                                                  # :224
+            if loop and self._position >= loop_end and loop_end - loop_start > 0:     # :226-234
+                self._position = loop_start + (self._position - loop_end) % (loop_end - loop_start)
         else:                             # :236-358
             if self._resamplers is None or len(self._resamplers) != nch:
                 self._resamplers = [CubicResampler() for _ in range(nch)]
@@ -718,21 +732,46 @@ class AudioBufferSourceNode(AudioNode):   # Nodes/AudioBufferSourceNode.cs (Loop
                 data, row = buf.channels[ch], self._out.data[ch]
                 pos, consumed_ch, oi = self._position, 0, 0
                 rs = self._resamplers[ch]
+                if self._wrap is None:
+                    self._wrap = np.zeros(512, F)
                 while oi < FRAMES:
-                    if pos >= dur_end:
+                    if loop and pos >= loop_end:                                      # :265-268
+                        pos = loop_start
+                    if pos >= dur_end and not loop:                                   # :270-274
                         row[oi:] = 0
                         break
-                    end = min(dur_end, buf.Length)
-                    avail = int(min(end - pos, buf.Length - pos))
-                    if avail <= 0:
+                    end = loop_end if loop else min(dur_end, buf.Length)              # :276
+                    avail = int(min(end - pos, buf.Length - pos))                     # :277
+                    if avail <= 0:                                                    # :279-292
+                        if loop:
+                            raise NotImplementedError("empty loop region: the reference never leaves this branch")
                         row[oi:] = 0
                         break
                     out_slice = row[oi:]
-                    c, p = rs.process(data[pos:pos + avail], out_slice, eff)
+                    if loop and pos + avail >= loop_end - 4:                          # :296 (always, since avail = loop_end - pos)
+                        loop_len = loop_end - loop_start
+                        from_end = int(loop_end - pos)
+                        needed = min(FRAMES - oi + 4, 512)                            # :301
+                        copied = 0
+                        i = 0
+                        while i < from_end and copied < needed:                       # :303-306
+                            self._wrap[copied] = data[pos + i]
+                            copied += 1
+                            i += 1
+                        i = 0
+                        while copied < needed and i < loop_len:                       # :308-311
+                            self._wrap[copied] = data[loop_start + i]
+                            copied += 1
+                            i += 1
+                        c, p = rs.process(self._wrap[:copied], out_slice, eff)        # :313
+                    else:
+                        c, p = rs.process(data[pos:pos + avail], out_slice, eff)      # :317
                     if p > 0:
                         more = True
                     new_pos = pos + c
-                    consumed_ch += new_pos - pos
+                    if loop and new_pos >= loop_end:                                  # :323-328
+                        new_pos = loop_start + (new_pos - loop_end)
+                    consumed_ch += (new_pos - pos) if new_pos >= pos else (loop_end - pos + new_pos - loop_start)  # :330
                     pos = new_pos
                     oi += p
                     if c == 0 and p == 0:
@@ -740,8 +779,10 @@ class AudioBufferSourceNode(AudioNode):   # Nodes/AudioBufferSourceNode.cs (Loop
                         break
                 if ch == 0:
                     total = consumed_ch
-            self._position += total
-        if not more or self._position >= dur_end:  # :360-372
+            self._position += total                                                   # :347
+            if loop and self._position >= loop_end and loop_end - loop_start > 0:     # :349-357
+                self._position = loop_start + (self._position - loop_end) % (loop_end - loop_start)
+        if not more or (not loop and self._position >= dur_end):  # :360-372
             self._out.clear()
             if math.isnan(self._stop):
                 self._stop = t1

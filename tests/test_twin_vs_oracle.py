@@ -85,6 +85,58 @@ def test_resampled_source_is_bit_equal(rate, buf_rate):
     assert np.array_equal(a, b), np.abs(a - b).max()
 
 
+@pytest.mark.parametrize("rate,buf_rate,loop,offset,stop", [
+    (1.0, 48000, (100.2, 400.2), 0.0, None),      # copy path, plays into the loop region and cycles it
+    (1.0, 48000, (10.5, 50.5), 650.0, 0.05),      # start position behind LoopEnd; Stop()
+    (0.5, 48000, (100.2, 400.2), 0.0, None),      # CubicResampler path through the wrap buffer
+    (1.37, 44100, (0.0, 0.0), 20.0, None),        # LoopEnd 0 = end of the buffer
+    (8.0, 48000, (100.2, 400.2), 0.0, None),      # cleared tails (:334-338)
+    (0.9, 48000, (5.2, 8.2), 2.0, None),          # a 3-frame loop
+])
+def test_looping_source_is_bit_equal(rate, buf_rate, loop, offset, stop):
+    """AudioBufferSourceNode.Loop on both paths (Nodes/AudioBufferSourceNode.cs:171-177, :186-235, :236-358): the numpy twin (a second
+    reading of the C# source) against the C++ oracle."""
+    n = 128 * 24
+
+    def build(api):
+        ctx = api.OfflineAudioContext(FS)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(75 + c, 1000) for c in range(2)], buf_rate)
+        s.Loop = True
+        s.LoopStart, s.LoopEnd = loop[0] / buf_rate, loop[1] / buf_rate
+        s.PlaybackRate.Value = rate
+        s.Connect(ctx.Destination)
+        s.Start(0.004, offset / buf_rate)
+        if stop is not None:
+            s.Stop(stop)
+        return ctx
+
+    a, b = _both(build, n)
+    assert np.abs(a).max() > 0.1
+    assert np.array_equal(a, b), np.abs(a - b).max()
+
+
+def test_playback_rate_automation_is_bit_equal():
+    """PlaybackRate is a k-rate parameter: its value at the start of a quantum picks the path and the phase increment (:165-186)."""
+    n = 128 * 40
+
+    def build(api):
+        ctx = api.OfflineAudioContext(FS)
+        s = api.AudioBufferSourceNode(ctx)
+        s.Buffer = api.PlayableAudioBuffer.FromChannelArrays([synth.splitmix_uniform(77 + c, 9000) for c in range(2)], FS)
+        s.PlaybackRate.Value = 0.75
+        s.PlaybackRate.SetValueAtTime(1.0, 0.02)
+        s.PlaybackRate.SetValueAtTime(1.5, 0.04)
+        s.PlaybackRate.LinearRampToValueAtTime(0.6, 0.08)
+        s.Connect(ctx.Destination)
+        s.Start()
+        return ctx
+
+    a, b = _both(build, n)
+    assert np.abs(a).max() > 0.1
+    assert np.array_equal(a, b), np.abs(a - b).max()
+
+
 def test_partitioned_convolver_spectra_and_output():
     ir = synth.decay_ir(80, 1000)
     x = synth.splitmix_uniform(81, 128 * 30)

@@ -24,6 +24,8 @@
 extern "C" {
 #endif
 
+/* v7.  Compatible additions since: gac_voice_desc.source_param is read for buffer sources too (PlaybackRate with events; a
+ * zero-initialised field keeps the static playback_rate), looping sources at any effective rate. */
 #define GAC_ABI_VERSION 7
 
 /* ---- status codes; the C# layer maps them onto the exception types the reference throws ---- */

@@ -881,8 +881,6 @@ class OfflineAudioContext:
                 raise NotSupportedException(f"{type(n).__name__} is outside the accelerated path (SURVEY.md §8f-3; the CPU oracle has it)")
             if isinstance(n, ChannelMergerNode) and any(sl > 2 for sl in n._slots.values()):
                 raise NotSupportedException("ChannelMergerNode inputs beyond the second are outside the accelerated path (signals carry two channels)")
-            if isinstance(n, AudioBufferSourceNode) and n.PlaybackRate._input_node is not None and n.PlaybackRate._input_node._in:
-                raise NotSupportedException("a modulated PlaybackRate is outside the accelerated path (the resampler's phase is replayed on the host)")
 
         q_now = self._q_now()
         for n in self._nodes:  # the first quantum in which a node is pulled: it is pulled while it reaches the destination

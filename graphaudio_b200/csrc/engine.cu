@@ -1038,10 +1038,11 @@ extern "C" int gac_graph_create(gac_context* ctx, const gac_graph_desc* desc, ga
       if (d.source->ctx != ctx) return fail(GAC_ERR_INVALID_ARGUMENT, "voice %d: buffer belongs to another context", v);
       if (d.source->nch > 2) return fail(GAC_ERR_UNSUPPORTED, "voice %d: sources with more than 2 channels are outside the accelerated path", v);
       if (!(d.playback_rate >= 0.001f && d.playback_rate <= 1000.f)) return fail(GAC_ERR_OUT_OF_RANGE, "voice %d: playbackRate outside [0.001, 1000]", v);
-      if (d.source_param.n_events > 0) {  // PlaybackRate with automation events / epochs: evaluated per quantum on the host
+      if (d.source_param.n_events > 0 || d.source_param.mod_bus > 0) {
+        // PlaybackRate with automation events / epochs (evaluated per quantum on the host) or with a modulation input (its k-rate
+        // table is evaluated on the device behind the modulator's bus and read back before the positions are replayed)
         int rc = copy_param(d.source_param, &h.src_param, "bufferSource.playbackRate");
         if (rc) return rc;
-        if (h.src_param.mod_bus >= 0) return fail(GAC_ERR_UNSUPPORTED, "voice %d: a modulated PlaybackRate is outside the accelerated path (the resampler's phase is replayed on the host)", v);
         h.rate_events = true;
       }
     }

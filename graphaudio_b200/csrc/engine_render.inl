@@ -134,6 +134,20 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
         continue;
       }
       const int64_t n_out_max = max_blocks * 128;
+      // a modulated PlaybackRate (AudioNode.Connect(AudioParam), AudioParam.cs:144-158: clamp(intrinsic + the modulator's first frame of
+      // the quantum) while the modulator's block is non-silent): the k-rate table is evaluated on the device — the voice was scheduled
+      // behind the bus that carries the modulator — and read back; the one point where a render waits for the device in its middle
+      std::vector<float> rate_q;
+      if (v.rate_events && v.src_param.mod_bus >= 0) {
+        std::vector<ParamJob> pj;
+        float* d_rate = nullptr;
+        int rc = param_table(env, v.src_param, false, pj, &d_rate, s.bus_base);
+        if (rc) return rc;
+        if ((rc = run_param_jobs(env, pj))) return rc;
+        rate_q.resize((size_t)env.NQ);
+        CU(cudaMemcpyAsync(rate_q.data(), d_rate, sizeof(float) * (size_t)env.NQ, cudaMemcpyDeviceToHost, kstream(ctx)));
+        CU(cudaStreamSynchronize(ctx->stream));
+      }
       std::shared_ptr<ResampleTable> tab;
       auto key = std::make_tuple(eff, pos, loopEnd, n_out_max, loopStart);
       if (!v.rate_events) {
@@ -164,7 +178,8 @@ static int plan_sources(RenderEnv& env, const std::vector<const VoiceH*>& voices
         };
         for (int64_t blk = 0; blk < max_blocks; blk++) {
           double eff_b = eff;
-          if (v.rate_events) eff_b = ratio * (double)host_param_value(v.src_param, b_start + blk, bt[b_start + blk]);  // :165-169
+          if (v.rate_events)  // :165-169
+            eff_b = ratio * (double)(rate_q.empty() ? host_param_value(v.src_param, b_start + blk, bt[b_start + blk]) : rate_q[(size_t)(b_start + blk)]);
           int oi = 0;
           bool more = false;
           if (eff_b == 1.0) {  // :186-235

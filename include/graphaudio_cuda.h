@@ -218,8 +218,9 @@ typedef struct gac_voice_desc {
   float playback_rate;      /* PlaybackRate.Value (k-rate).  A PlaybackRate with automation events, or one whose Value was edited
                                between Render calls (epochs), is passed in full as `source_param` (n_events > 0), which then takes
                                precedence: evaluated per quantum on the host (Nodes/AudioBufferSourceNode.cs:165-169), the path
-                               (copy / CubicResampler) is chosen per quantum as the reference does.  A modulation input on it is
-                               GAC_ERR_UNSUPPORTED */
+                               (copy / CubicResampler) is chosen per quantum as the reference does.  With a modulation input
+                               (source_param.mod_bus > 0) the k-rate values are evaluated on the device behind the modulator and
+                               read back before the positions are replayed */
   int32_t n_ops;
   const gac_op_desc* ops;
   int32_t bus;              /* index into buses, or -1: connected straight to the destination   */

@@ -228,3 +228,40 @@ def test_mid_side_through_splitter_merger_and_a_convolver():
     yg, yo = _both(build, n + 128 * 70)
     assert np.abs(yo).max() > 0.05
     assert np.abs(yg - yo).max() <= 1e-5, np.abs(yg - yo).max()
+
+
+@pytest.mark.parametrize("loop", [False, True])
+def test_modulated_playback_rate(loop):
+    """A node connected to AudioBufferSourceNode.PlaybackRate (k-rate: clamp(intrinsic + the modulator's first frame of the quantum) while
+    the modulator's block is non-silent, AudioParam.cs:144-158; the value picks the path and the phase increment, Nodes/
+    AudioBufferSourceNode.cs:165-186).  The device evaluates the k-rate table behind the modulator's bus, the host replays the positions
+    with it.  Modulators whose samples are bit-exact on both sides (a ConstantSourceNode ramp and a buffer source through a GainNode):
+    the render is bit-exact."""
+    n = 128 * 100
+
+    def build(api):
+        ctx = api.OfflineAudioContext(FS)
+        s = _noise(api, ctx, 1400, 30000)
+        s.PlaybackRate.Value = 1.0
+        if loop:
+            s.Loop = True
+            s.LoopStart, s.LoopEnd = 500.2 / FS, 9000.2 / FS
+        s.Connect(ctx.Destination)
+        s.Start(0.003)
+        ramp = api.ConstantSourceNode(ctx)
+        ramp.Offset.SetValueAtTime(0.0, 0.0)
+        ramp.Offset.LinearRampToValueAtTime(0.8, 0.1)
+        ramp.Offset.LinearRampToValueAtTime(-0.6, 0.2)
+        ramp.Connect(s.PlaybackRate)
+        ramp.Start(0.02)
+        ramp.Stop(0.22)      # before and after: the intrinsic value alone (exactly 1: the copy path)
+        wobble, depth = _noise(api, ctx, 1401, 4000, channels=1), api.GainNode(ctx)
+        depth.Gain.Value = 0.05
+        wobble.Connect(depth)
+        depth.Connect(s.PlaybackRate)
+        wobble.Start(0.05)
+        return ctx
+
+    yg, yo = _both(build, n)
+    assert np.abs(yo).max() > 0.5
+    assert np.array_equal(yg, yo), np.abs(yg - yo).max()

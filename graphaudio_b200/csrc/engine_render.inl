@@ -799,7 +799,11 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
       // than the rest needs to arrive, and every further batch adds its fixed cost behind the last upload (C3 shard, 21 of 128 voices
       // in flight at the call: 3.65 ms of device time in four batches).
       const size_t rest = S0 - cuts.back();
-      const size_t n_rest = rest * 3 <= S0 ? 1 : (rest * 2 <= S0 ? 2 : 3);
+      size_t n_rest = rest * 3 <= S0 ? 1 : (rest * 2 <= S0 ? 2 : 3);
+      if (const char* e = getenv("GAC_REST_BATCHES")) {  // (measurements)
+        const int x = atoi(e);
+        if (x >= 1 && x <= 8) n_rest = (size_t)x;
+      }
       const size_t chunk = std::max<size_t>(4, (rest + n_rest - 1) / n_rest);
       for (size_t v = cuts.back() + chunk; v < S0; v += chunk) cuts.push_back(v);
     }

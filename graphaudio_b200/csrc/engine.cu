@@ -198,6 +198,7 @@ struct gac_context {
   int deferred_since_kick = 0;
   cudaEvent_t kick_done = nullptr;         // behind the launches of the last kick: its staged job tables are dead once it has fired
   bool kick_pending = false;
+  int64_t copy_launches = 0;               // k_copy_from_host_multi launches so far (counted into gac_stats.kernel_launches per render)
   bool defer_copies = false;               // inside render_core: table copies wait for the next kernel launch and travel together
   // render scratch arena (struct Scratch): device chunks kept between renders, bump-allocated
   std::vector<std::pair<char*, size_t>> arena;
@@ -324,6 +325,7 @@ static bool use_fft2(const gac_context* c, int P, int M2) {
 // (renders synchronise before they return).  The destination must be allocated in multiples of 16 bytes.
 static void flush_copies(gac_context* ctx) {
   if (ctx->pending.n == 0) return;
+  ctx->copy_launches++;
   launch_copy_from_host_multi(ctx->pending, ctx->stream);
   ctx->pending.n = 0;
 }

@@ -671,6 +671,7 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   }
   ctx->stage_block = 0;
   ctx->stage_used = 0;  // the previous render has synchronised: its staged job tables are dead
+  const int64_t copy_launches_before = ctx->copy_launches;
   ctx->pending.n = 0;
   struct DeferScope {  // job tables staged during the render travel with the next kernel launch, several per copy launch
     gac_context* c;
@@ -1192,7 +1193,8 @@ static int render_core(gac_context* ctx, const RenderArgs& a) {
   st.mac_big_segments = env.mac_big;
   st.fanin_groups = env.sum_groups;
   st.fanin_members = env.sum_members;
-  st.kernel_launches = env.launches;
+  flush_copies(ctx);
+  st.kernel_launches = env.launches + (ctx->copy_launches - copy_launches_before);  // (the table-copy kernels included)
   st.voices = (int64_t)S;
   st.frames = a.n_frames;
   ctx->stats = st;

@@ -131,8 +131,10 @@ def build_c4(api, fs, src, ir, t_scale=1.0, **ctx_kw):
     return ctx
 
 
-def build_c5(api, fs, src_rate, voices, bus_gain, t_scale=1.0, **ctx_kw):
-    """C5: Source(44.1 kHz buffer in a 96 kHz context -> CubicResampler) -> GainNode -> Convolver -> bus -> destination."""
+def build_c5(api, fs, src_rate, voices, bus_gain, t_scale=1.0, loop=None, rate_ramp=None, **ctx_kw):
+    """C5: Source(44.1 kHz buffer in a 96 kHz context -> CubicResampler) -> GainNode -> Convolver -> bus -> destination.
+    loop = (LoopStart, LoopEnd) in seconds: the sources loop; rate_ramp = (r0, r1, t1): PlaybackRate.SetValueAtTime(r0, 0) and
+    LinearRampToValueAtTime(r1, t1) (the "loop" cross-check case: the wrap-buffer resampler path under a k-rate rate sweep)."""
     ctx = api.OfflineAudioContext(fs, **ctx_kw)
     bus = api.GainNode(ctx)
     bus.Gain.Value = bus_gain
@@ -141,6 +143,12 @@ def build_c5(api, fs, src_rate, voices, bus_gain, t_scale=1.0, **ctx_kw):
     for src, ir, g in voices:
         s = api.AudioBufferSourceNode(ctx)
         s.Buffer = api.PlayableAudioBuffer.FromChannelArrays(src, src_rate)
+        if loop is not None:
+            s.Loop = True
+            s.LoopStart, s.LoopEnd = loop
+        if rate_ramp is not None:
+            s.PlaybackRate.SetValueAtTime(rate_ramp[0], 0.0)
+            s.PlaybackRate.LinearRampToValueAtTime(rate_ramp[1], rate_ramp[2])
         gn = api.GainNode(ctx)
         add_gain_automation(gn.Gain, g, t_scale)
         conv = api.ConvolverNode(ctx)

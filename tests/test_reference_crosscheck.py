@@ -58,3 +58,18 @@ def test_dump_cases_are_well_formed(tmp_path):
         ya, yb = a.Render(c["frames"]), b.Render(c["frames"])
         assert np.abs(ya).max() > 1e-3
         assert np.abs(ya - yb).max() <= 2e-7, (name, np.abs(ya - yb).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(dump_cases.CASES))
+def test_cuda_path_matches_the_oracle_on_the_crosscheck_cases(name):
+    """The cases the reference binary would render, device against oracle — so that the day ref_<case>.f32 exist, a mismatch points
+    at the oracle's reading of the source, not at the device path."""
+    import graphaudio_b200 as G
+    from oracle import ga_oracle as O
+    cg, c = dump_cases.build_case(G, name)
+    co, _ = dump_cases.build_case(O, name)
+    yg, yo = cg.Render(c["frames"]), co.Render(c["frames"])
+    cg.Dispose()
+    assert np.abs(yo).max() > 1e-3
+    assert np.abs(yg - yo).max() <= 1e-5, (name, np.abs(yg - yo).max())

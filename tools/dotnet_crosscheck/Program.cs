@@ -8,7 +8,7 @@
 //   case.txt        key = value lines (kind, sample_rate, frames, voices, bus_gain, automation times, ...)
 //   v<k>_src<c>.f32 / v<k>_ir<c>.f32   little-endian float32 channel data of voice k
 // and the output is <out dir>/ref_<case>.f32: the two rendered channels, planar, little-endian float32, preceded by nothing.
-// Every graph is built exactly like tests/synth.py builds it (build_c1 .. build_c5): the same node order, the same automation calls.
+// Every graph is built exactly like tests/synth.py builds it (build_c1 .. build_c5, the latter also with looping, rate-swept sources): the same node order, the same automation calls.
 // Timing of each Render call is printed as well: this is the reference's own CPU baseline (one context = one thread).
 using System.Diagnostics;
 using System.Globalization;
@@ -62,7 +62,7 @@ static float[][] RenderCase(string dir, Dictionary<string, string> c, out double
     double ts = D(c, "t_scale", 1.0);
     var ctx = new OfflineAudioContext(fs);
     AudioNode sink = ctx.Destination;
-    if (kind is "c2" or "c3" or "c5")
+    if (kind is "c2" or "c3" or "c5" or "loop")
     {
         var bus = new GainNode(ctx);
         bus.Gain.Value = (float)D(c, "bus_gain", 1.0);
@@ -77,6 +77,14 @@ static float[][] RenderCase(string dir, Dictionary<string, string> c, out double
         for (int ch = 0; ch < irCh; ch++) ir[ch] = ReadF32(Path.Combine(dir, $"v{v}_ir{ch}.f32"));
         var s = new AudioBufferSourceNode(ctx);
         s.Buffer = PlayableAudioBuffer.FromChannelArrays(src, srcRate);
+        if (kind == "loop")   // tests/synth.py: build_c5(loop = ..., rate_ramp = ...)
+        {
+            s.Loop = true;
+            s.LoopStart = D(c, "loop_start");
+            s.LoopEnd = D(c, "loop_end");
+            s.PlaybackRate.SetValueAtTime((float)D(c, "rate0", 1.0), 0.0);
+            s.PlaybackRate.LinearRampToValueAtTime((float)D(c, "rate1", 1.0), D(c, "rate_t1", 1.0));
+        }
         AudioNode tail = s;
         if (kind is "c3" or "c4")
         {
@@ -95,7 +103,7 @@ static float[][] RenderCase(string dir, Dictionary<string, string> c, out double
             hp.Q.Value = 0.707f;
             tail = tail.Connect(hp);
         }
-        if (kind is "c2" or "c3" or "c5")
+        if (kind is "c2" or "c3" or "c5" or "loop")
         {
             var gn = new GainNode(ctx);
             GainAutomation(gn.Gain, (float)D(c, $"v{v}_g0"), (float)D(c, $"v{v}_g1"), (float)D(c, $"v{v}_g2"), ts);

@@ -3,7 +3,7 @@ them, the CPU oracle's render of each case (oracle_<case>.f32) for eyeballing.
 
     python tools/dotnet_crosscheck/dump_cases.py [<cases dir>]     (default: tools/dotnet_crosscheck/cases, git-ignored)
 
-The cases are C1 .. C5 of BASELINE.json at sizes the oracle renders in well under a second each, built by the same
+The cases are C1 .. C5 of BASELINE.json (plus a looping, rate-swept variant of C5) at sizes the oracle renders in well under a second each, built by the same
 tests/synth.py builders the parity tests use; tests/test_reference_crosscheck.py re-creates the inputs from the seeds (nothing
 but the reference's outputs has to be committed: tests/golden/ref_<case>.f32)."""
 import os
@@ -24,6 +24,10 @@ CASES = {
     "c4_small": dict(kind="c4", sample_rate=48000, frames=12000, voices=1, src=9000, ir=2000, t_scale=0.04, f0=2000.0, f1=12000.0, q=0.707,
                      sweep_end=4.0),
     "c5_small": dict(kind="c5", sample_rate=96000, source_rate=44100, frames=24000, voices=2, src=8000, ir=5000, bus_gain=0.5, t_scale=0.02),
+    # looping sources on the CubicResampler path (the 512-float wrap buffer, Nodes/AudioBufferSourceNode.cs:236-358) under a k-rate
+    # PlaybackRate sweep that crosses an effective rate of exactly 1 nowhere (44.1 kHz buffers in a 48 kHz context)
+    "loop_small": dict(kind="loop", sample_rate=48000, source_rate=44100, frames=12000, voices=2, src=3000, ir=2000, bus_gain=0.5, t_scale=0.02,
+                       loop_start=0.01, loop_end=0.05, rate0=0.8, rate1=1.6, rate_t1=0.2),
 }
 
 
@@ -47,6 +51,9 @@ def build_case(api, name):
         return synth.build_c3(api, fs, voices, c["bus_gain"], f0=c["f0"], f1=c["f1"], t_scale=ts, q=c["q"]), c
     if c["kind"] == "c4":
         return synth.build_c4(api, fs, voices[0][0], voices[0][1], t_scale=ts), c
+    if c["kind"] == "loop":
+        return synth.build_c5(api, fs, c["source_rate"], voices, c["bus_gain"], t_scale=ts, loop=(c["loop_start"], c["loop_end"]),
+                              rate_ramp=(c["rate0"], c["rate1"], c["rate_t1"])), c
     return synth.build_c5(api, fs, c["source_rate"], voices, c["bus_gain"], t_scale=ts), c
 
 

@@ -144,44 +144,52 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? (R == 1 ? 6 : 4) : 3)) k_rff
     float2 u[16];
     r16::load16(u, zg, t);
     r16::stage_c<r16::Plan<H>::L, false>(u);
-    __syncwarp();
+    // Z[k] goes straight into the tile, column bl, natural order (slot_k): the split step is done by the store phase below, on the way
+    // out — two shared-memory crossings fewer per transform (the L1 data pipe was this kernel's busiest unit: ncu, 78 %)
 #pragma unroll
-    for (int q = 0; q < 16; q++) zg[G::slot_k(t, q)] = u[q];  // natural order Z[k]
-    __syncwarp();
-    // split step: E = (Z[k] + conj Z[H-k]) / 2 ; O = (Z[k] - conj Z[H-k]) / (2i) ; X[k] = E + w_k O, w_k = e^{-2 pi i k / 2H}.
-    // Bins k and H - k come from the same pair: E[H-k] = conj E[k], O[H-k] = conj O[k], w_{H-k} = -conj w_k, so
-    // X[H-k] = conj(E - w_k O): one complex product and two shared-memory reads for two bins.
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int k = t + T * j;  // 0 .. H/2 - 1
-      const float2 a = zg[k];
-      if (k == 0) {
-        tileT[bl] = make_float2(a.x + a.y, 0.f);           // row 0: DC
-        tileT[H * LD + bl] = make_float2(a.x - a.y, 0.f);  // row H: Nyquist
-      } else {
-        const float2 c = zg[H - k];
-        const float2 e = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
-        const float2 o = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));
-        const float2 wo = cmul1(tw[k], o);
-        tileT[k * LD + bl] = make_float2(e.x + wo.x, e.y + wo.y);
-        tileT[(H - k) * LD + bl] = make_float2(e.x - wo.x, -(e.y - wo.y));
-      }
-    }
-    if (t == 0) {  // k = H/2 pairs with itself: E = (Re Z, 0), O = (Im Z, 0), w = -i
-      const float2 a = zg[H / 2];
-      tileT[(H / 2) * LD + bl] = make_float2(a.x, -a.y);
-    }
-    __syncwarp();
+    for (int q = 0; q < 16; q++) tileT[G::slot_k(t, q) * LD + bl] = u[q];
+    __syncwarp();  // (zg is re-used by the group's next round)
   }
   __syncthreads();
   {
-    // a thread stores column c of rows r0, r0 + NTHR / COLS, ...: every warp-wide store is one COLS * 8-byte run of an XT row
+    // Split step + store.  E = (Z[k] + conj Z[H-k]) / 2 ; O = (Z[k] - conj Z[H-k]) / (2i) ; X[k] = E + w_k O, w_k = e^{-2 pi i k / 2H}.
+    // Bins k and H - k come from the same pair: E[H-k] = conj E[k], O[H-k] = conj O[k], w_{H-k} = -conj w_k, so
+    // X[H-k] = conj(E - w_k O): one complex product and two shared-memory reads for two bins.  A thread takes column c of the
+    // pairs k = tid / COLS, + NTHR / COLS, ... <= H/2 and stores rows k and H - k: every warp-wide store is COLS * 8-byte runs of XT rows.
     constexpr int RSTEP = NTHR / COLS;
     const int c = tid % COLS;
     if (b0 + c < job.n_blocks) {
       float2* __restrict__ dst = job.out + b0 + c;
-#pragma unroll 8
-      for (int row = tid / COLS; row <= H; row += RSTEP) dst[(int64_t)row * ts] = tileT[row * LD + c];
+      constexpr int ITERS = (H / 2 + RSTEP) / RSTEP;  // pairs per thread, the last sweep partly idle
+      // every pair's operands are requested before the first product (the loop is unrolled in full, predicated on k <= H/2)
+      float2 av[ITERS], zv[ITERS], wv[ITERS];
+#pragma unroll
+      for (int it = 0; it < ITERS; it++) {
+        const int k = tid / COLS + it * RSTEP;
+        const bool ok = k <= H / 2;
+        av[it] = ok ? tileT[k * LD + c] : make_float2(0.f, 0.f);
+        zv[it] = (ok && k > 0) ? tileT[(H - k) * LD + c] : make_float2(0.f, 0.f);
+        wv[it] = (ok && k > 0 && k < H / 2) ? tw[k] : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; it++) {
+        const int k = tid / COLS + it * RSTEP;
+        if (k > H / 2) break;
+        const float2 a = av[it];
+        if (k == 0) {
+          dst[0] = make_float2(a.x + a.y, 0.f);                   // row 0: DC
+          dst[(int64_t)H * ts] = make_float2(a.x - a.y, 0.f);     // row H: Nyquist
+        } else if (k == H / 2) {  // pairs with itself: E = (Re Z, 0), O = (Im Z, 0), w = -i
+          dst[(int64_t)k * ts] = make_float2(a.x, -a.y);
+        } else {
+          const float2 z = zv[it];
+          const float2 e = make_float2(0.5f * (a.x + z.x), 0.5f * (a.y - z.y));
+          const float2 o = make_float2(0.5f * (a.y + z.y), -0.5f * (a.x - z.x));
+          const float2 wo = cmul1(wv[it], o);
+          dst[(int64_t)k * ts] = make_float2(e.x + wo.x, e.y + wo.y);
+          dst[(int64_t)(H - k) * ts] = make_float2(e.x - wo.x, -(e.y - wo.y));
+        }
+      }
     }
   }
 }

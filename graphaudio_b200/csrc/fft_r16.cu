@@ -64,8 +64,8 @@ struct GeoF {
   static constexpr int TILE = ((H + 1) * LD + 1) & ~1;
   __device__ __forceinline__ static int tile_col(int tid, int rnd) {
     if (R == 2) return G::tile_col(tid, rnd);
-    // one column per group; H = 128: the two groups of a half-warp take columns m and m + 8 (16 different bank pairs per access)
-    if (H == 128) return ((tid >> 3) >> 1) + 8 * ((tid >> 3) & 1);
+    // one column per group.  H = 128: a thread writes the rows 2 t + const of its column into the tile (leading dimension COLS + 1:
+    // bank pair = row + column), so the two groups of a half-warp take NEIGHBOURING columns: 16 different bank pairs per 64-bit access
     return tid / G::T;
   }
 };

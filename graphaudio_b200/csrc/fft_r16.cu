@@ -61,7 +61,10 @@ struct GeoF {
   using G = Geo<H>;
   static constexpr int COLS = R * G::GROUPS;
   static constexpr int LD = COLS + 1;
-  static constexpr int TILE = ((H + 1) * LD + 1) & ~1;
+  static constexpr int TILE = (((H + 1) * LD + 1) & ~1) + 32;
+  // tile index of (row k, column c): rows 128 apart would meet in the same bank pair (H = 512: a half-warp writes rows r and r + 128
+  // of one column), so every block of 128 rows is shifted by eight entries
+  __device__ __forceinline__ static int tix(int k, int c) { return k * LD + c + 8 * (k >> 7); }
   __device__ __forceinline__ static int tile_col(int tid, int rnd) {
     if (R == 2) return G::tile_col(tid, rnd);
     // one column per group.  H = 128: a thread writes the rows 2 t + const of its column into the tile (leading dimension COLS + 1:
@@ -74,9 +77,9 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? (R == 1 ? 6 : 4) : 3)) k_rff
                                                                                        const float2* __restrict__ tw, int64_t ts) {
   using G = Geo<H>;
   using F = GeoF<H, R>;
-  constexpr int T = G::T, LD = F::LD, COLS = F::COLS;
+  constexpr int T = G::T, COLS = F::COLS;
   extern __shared__ __align__(16) float2 smem[];
-  float2* tileT = smem;            // [H + 1][LD]
+  float2* tileT = smem;            // Z[k] of every column: F::tix(k, column)
   float2* zb = smem + F::TILE;     // [GROUPS][ZS]
   const FftFwdJob job = jobs[blockIdx.y];
   const int tid = threadIdx.x;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? (R == 1 ? 6 : 4) : 3)) k_rff
     // Z[k] goes straight into the tile, column bl, natural order (slot_k): the split step is done by the store phase below, on the way
     // out — two shared-memory crossings fewer per transform (the L1 data pipe was this kernel's busiest unit: ncu, 78 %)
 #pragma unroll
-    for (int q = 0; q < 16; q++) tileT[G::slot_k(t, q) * LD + bl] = u[q];
+    for (int q = 0; q < 16; q++) tileT[F::tix(G::slot_k(t, q), bl)] = u[q];
     __syncwarp();  // (zg is re-used by the group's next round)
   }
   __syncthreads();
@@ -167,8 +170,8 @@ __global__ void __launch_bounds__(NTHR, (H == 128 ? (R == 1 ? 6 : 4) : 3)) k_rff
       for (int it = 0; it < ITERS; it++) {
         const int k = tid / COLS + it * RSTEP;
         const bool ok = k <= H / 2;
-        av[it] = ok ? tileT[k * LD + c] : make_float2(0.f, 0.f);
-        zv[it] = (ok && k > 0) ? tileT[(H - k) * LD + c] : make_float2(0.f, 0.f);
+        av[it] = ok ? tileT[F::tix(k, c)] : make_float2(0.f, 0.f);
+        zv[it] = (ok && k > 0) ? tileT[F::tix(H - k, c)] : make_float2(0.f, 0.f);
         wv[it] = (ok && k > 0 && k < H / 2) ? tw[k] : make_float2(0.f, 0.f);
       }
 #pragma unroll
